@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched 2D Ra=1e5 environment action steps (dt = 1) on B200.
+
+Contract (one JSON line on rank 0):
+  python bench.py --gpus N --steps K --warmup W            -> this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  -> the reference's CPU algorithm (oracle port) on host cores
+A "step" is one pass of the hot path over one batch: every environment of the batch advances by
+one action step (34 RK3 steps = 102 projected stages at dt = 1, dt_solver = 0.03).
+
+Workload = BASELINE.json configs[1]: 4096 envs per GPU, 96x64, 12 heaters, obs (3,8,48), Ra = 1e5, Pr = 0.7,
+initial state of env e = episode (e mod 20) of data/checkpoints/train/ckpt_ra100000.h5, actions ~ U(-1,1)
+from a device Philox generator seeded 1234 + rank.  Envs shard across ranks with no data-path collective
+(weak scaling); NCCL only reduces episode statistics and the timing.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ENVS_PER_GPU = 4096
+RA, DT_ACTION, DT_SOLVER = 1e5, 1.0, 0.03
+CKPT = ROOT / "data/checkpoints/train/ckpt_ra100000.h5"
+S_VALUES = 2 * 96 * 64 + 96 * 65                  # 18528 stored values per env
+METRIC = "2D Ra=1e5 env-steps/s (dt=1)"
+UNIT = "env-steps/s"
+
+
+def algorithmic_bytes_per_env_step(nsub: int, real_bytes: int) -> float:
+    """stage-streaming formulation, 10 * S values per RK3 step."""
+    return nsub * 10 * S_VALUES * real_bytes
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc, self.thread = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(sample_env_steps: int, threads: int):
+    """Time the CPU oracle (fp64 port of the reference scheme) on `sample_env_steps` env action-steps."""
+    from oracle import oracle as O
+    from rbc_gym_b200.h5lite import load_checkpoint_2d
+    c = load_checkpoint_2d(CKPT)
+    P = O.make_params(RA, split_phy=True)
+    dts = O.substep_schedule(DT_ACTION, DT_SOLVER)
+    n = sample_env_steps
+    idx = np.arange(n) % c.num_episodes
+    b, u, w = c.b[idx].copy(), c.u[idx].copy(), c.w[idx].copy()
+    acts = np.random.default_rng(1234).uniform(-1, 1, (n, 12))
+    O.step_batch(P, b[:threads].copy(), u[:threads].copy(), w[:threads].copy(), acts[:threads], dts[:2], threads)  # warm
+    t0 = time.perf_counter()
+    bad = O.step_batch(P, b, u, w, acts, dts, threads)
+    el = time.perf_counter() - t0
+    assert not bad
+    return n / el, el
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; Julia cannot run here),
+    all host threads, each step a bounded sample of the workload."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = max(threads * 2, 16)
+    rates = []
+    for _ in range(args.warmup):
+        cpu_reference_rate(threads, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, _ = cpu_reference_rate(per_step, threads)
+        rates.append(r)
+    el = time.perf_counter() - t0
+    value = per_step * args.steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "2D Ra=1e5 96x64 dt=1 (34 RK3 steps), reset from train checkpoints, U(-1,1) actions",
+                   "sample_envs_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{per_step} env action-steps per step x {args.steps} steps, oracle fp64 C port, {threads} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "Julia/Oceananigans reference cannot run here (no julia); CPU oracle port of the same scheme. "
+                "Reference's published figure: 8.3 env-steps/s per process (README.md:62, Apple silicon).",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rbc_gym_b200 import backend
+    from rbc_gym_b200.sharding import EpisodeStats, shard_range
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.envs_per_gpu
+    lo, hi = shard_range(B * world, world, rank)           # this rank's slice of the global batch
+    sim = backend.Sim2D(B, ra=RA, dt_action=DT_ACTION, dt_solver=DT_SOLVER, precision=args.precision, device=local_rank)
+    n_ep = sim.load_checkpoints(CKPT)
+    gid = torch.arange(lo, hi, device=dev, dtype=torch.int64)
+    sim.reset_from_checkpoints((gid % n_ep).to(torch.int32))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    K, W = args.steps, args.warmup
+    actions = torch.rand((W + K, B, sim.heaters), device=dev, generator=gen) * 2 - 1
+    stats = EpisodeStats(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for i in range(W):
+        sim.step(actions[i])
+    kernel_ms = []
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sim.launch_info()["launches"]
+    e0.record()
+    for i in range(K):
+        obs, rew, nus, nuo, trunc, nan = sim.step(actions[W + i])
+        stats.accumulate(rew, nuo, nus, nan)
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = sim.launch_info()["launches"] - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # per-launch duration of the dominant kernel, measured by the library's own CUDA events on the launch stream
+    for i in range(3):
+        sim.step(actions[W + i])
+        kernel_ms.append(sim.last_step_kernel_ms())
+    tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    elapsed_ms = tmax.item()
+    totals = stats.reduce(world)                         # NCCL all_reduce of a handful of scalars
+    value = world * B * K / (elapsed_ms * 1e-3)
+
+    # ---------------- end to end through the host-buffer C-ABI entry point (`e2e`) ----------------
+    host_actions = [torch.empty((B, sim.heaters), dtype=torch.float32).pin_memory() for _ in range(K)]
+    for i in range(K):
+        host_actions[i].copy_(actions[W + i].cpu())
+    out = sim.alloc_host_outputs(pinned=True)
+    sim.step_host(host_actions[0].numpy(), out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        sim.step_host(host_actions[i].numpy(), out)       # H2D actions, kernel, D2H obs/reward/nu/flags, sync
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    tmax = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (tmax.item() * 1e-3)
+    h2d = B * sim.heaters * 4
+    d2h = sum(v.nbytes for v in out.values())
+
+    if rank == 0:
+        real_bytes = args.precision // 8
+        per_env = algorithmic_bytes_per_env_step(sim.nsub, real_bytes)
+        k_ms = float(np.mean(kernel_ms))
+        achieved = per_env * B / (k_ms * 1e-3) / 1e9
+        peak, peak_src = hbm_peak()
+        traffic = None
+        tj = ROOT / "profiles" / "traffic.json"
+        if tj.exists():
+            try:
+                traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cpu = None
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n = max(4 * threads, 32)
+            rate, el = cpu_reference_rate(n, threads)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{n} env action-steps of the same workload (oracle fp64 C port, {threads} threads, {el:.1f} s)"}
+        flop_per_env_step = 0.18e9                        # SURVEY §8d estimate (~290 flop / cell-stage)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: 2D Ra=1e5 96x64 dt=1 (34 RK3 steps / 102 projected stages), "
+                                   f"{B} envs per GPU, reset from train checkpoints, U(-1,1) actions",
+                       "envs_per_gpu": B, "global_envs": world * B, "parallelism": f"env-sharded x{world}",
+                       "l2": "inputs larger than L2 (%.0f MB of state per GPU)" % (B * S_VALUES * real_bytes / 1e6)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "rbc2d_env_kernel",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": per_env * B,
+                         "note": "algorithmic bytes = stage-streaming formulation (SURVEY 8d); the kernel keeps each env "
+                                 "on-chip for the whole action step, so measured DRAM traffic is far below this figure",
+                         "fp32_tflops_est": flop_per_env_step * B / (k_ms * 1e-3) / 1e12},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "episode_stats": totals,
+        }
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,125 @@
+/*
+ * rbc_b200.h — C ABI of the B200-native Rayleigh-Benard simulation backend.
+ *
+ * Drop-in boundary for RBC-Gym's simulation step.  In the reference, the Python environments
+ * reach the simulation through juliacall: one Julia module of globals per env object
+ * (src/rbc_gym/envs/rbc2D.py:111-115) exposing
+ *     initialize_simulation   src/rbc_gym/sim/rbc_sim2D_api.jl:17-70
+ *     step_simulation         src/rbc_gym/sim/rbc_sim2D_api.jl:75-97
+ *     get_state               src/rbc_gym/sim/rbc_sim2D_api.jl:102-118
+ *     get_observation         src/rbc_gym/sim/rbc_sim2D_api.jl:123-129
+ *     get_info                src/rbc_gym/sim/rbc_sim2D_api.jl:134-137
+ *     get_nusselt             src/rbc_gym/sim/rbc_sim2D_api.jl:142-163
+ * This library replaces that bridge with a handle-based, *batched* interface: one handle owns
+ * B independent environments on one GPU (replacing the process-per-env vector env of
+ * example/run_vectorized.py:11-20 / experiments/run_sarl.py:130-153).
+ *
+ * Conventions
+ *   - plain C types only; no torch/CUDA types in signatures (a CUDA stream is passed as void*).
+ *   - pointers named *_dev are device pointers on the handle's device, *_host are host pointers
+ *     (pinned memory makes the copies asynchronous; pageable memory works too).
+ *   - every call returns 0 on success, <0 on error; rbc_last_error() returns the message of the
+ *     last failing call on this thread.  NaNs in the fields are *reported* per environment
+ *     (nan flag), never raised here: the Python facade turns them into the reference's
+ *     RuntimeError (rbc2D.py:170-171).
+ *   - all work is enqueued on the handle's stream (rbc2d_set_stream); *_host calls synchronise
+ *     that stream before returning, *_dev calls do not.
+ *   - a handle is not thread-safe.  There is no CPU fallback: creation fails without a GPU.
+ *   - array layouts follow the Python side of the reference (already transposed, rbc2D.py:184-196):
+ *     state (C, Nz, Nx) and observation (C, No_z, No_x), z = 0 at the bottom plate, x fastest.
+ */
+#ifndef RBC_B200_H
+#define RBC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBC_B200_ABI_VERSION 1
+
+/* Configuration = the keyword arguments of initialize_simulation (rbc_sim2D_api.jl:17) plus the
+ * constants that the Julia API hard-codes (rbc_sim2D_api.jl:28-41), made explicit. */
+typedef struct rbc2d_config {
+    int32_t num_envs;        /* B: environments in the on-device batch                                 */
+    int32_t nx, nz;          /* grid = state_shape[::-1]; this build supports 96 x 64                  */
+    int32_t obs_nx, obs_nz;  /* sensors = observation_shape[::-1]; must divide nx, nz (48, 8)          */
+    int32_t heaters;         /* heater segments (12), <= 32                                            */
+    double heater_limit;     /* 0.75                                                                   */
+    double ra;               /* Rayleigh number                                                        */
+    double pr;               /* Prandtl number, reference hard-codes 0.7                               */
+    double dt_action;        /* heater_duration: simulated time per action step                        */
+    double dt_solver;        /* RK3 step, reference hard-codes 0.03                                    */
+    double episode_length;   /* truncation time (300)                                                  */
+    int32_t precision;       /* 32 = throughput mode, 64 = validation mode                             */
+    int32_t pressure;        /* 1: hydrostatic-pressure split scheme + pHY', pNHS channels (pressure=True) */
+    int32_t device;          /* CUDA device ordinal                                                    */
+} rbc2d_config;
+
+typedef struct rbc2d_sim rbc2d_sim;
+
+int rbc_abi_version(void);
+const char* rbc_last_error(void);
+
+/* initialize_simulation, configuration part: allocates state, scratch and tables on the device. */
+int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out);
+int rbc2d_destroy(rbc2d_sim* sim);
+int rbc2d_set_stream(rbc2d_sim* sim, void* cuda_stream);
+int rbc2d_num_envs(const rbc2d_sim* sim);
+int rbc2d_state_values_per_env(const rbc2d_sim* sim);   /* 2*nx*nz + nx*(nz+1) */
+
+/* Checkpoint bank (data/checkpoints/.../ckpt_ra*.h5 read on the host; initialize_from_checkpoint,
+ * rbc_sim2D.jl:173-186).  Arrays are [n_episodes][nz|nz+1][nx] float64, z = 0 bottom. */
+int rbc2d_load_checkpoints(rbc2d_sim* sim, const double* b_host, const double* u_host, const double* w_host,
+                           int32_t n_episodes);
+
+/* Reset environments from the bank: initialize_simulation with checkpoint_path.  env_ids_dev lists
+ * the n environments to reset (NULL = all B, then n is ignored); ckpt_idx_dev gives the episode
+ * index per listed environment.  t := 0, step := 1, the observation outputs are refreshed. */
+int rbc2d_reset_from_checkpoints_dev(rbc2d_sim* sim, const int32_t* env_ids_dev, const int32_t* ckpt_idx_dev, int32_t n);
+
+/* Reset environments from explicit fields (noise initialisation, rbc_sim2D.jl:163-171, or any
+ * state).  fields_host is [n][2*nx*nz + nx*(nz+1)] float64 in checkpoint layout (b, u, w).
+ * project != 0 applies the pressure projection Oceananigans' set! performs.  env_ids_host lists
+ * the environments (NULL = the first n). */
+int rbc2d_reset_from_fields_host(rbc2d_sim* sim, const int32_t* env_ids_host, const double* fields_host, int32_t n,
+                                 int32_t project);
+
+/* step_simulation for the whole batch + get_observation + get_nusselt + truncation, fused.
+ *   actions      [B][heaters] float32 in [-1,1]
+ *   obs          [B][C][obs_nz][obs_nx] float32, C = 3 (b,u,w) or 5 with pressure
+ *   reward       [B] float32 = -nusselt_obs          (rbc2D.py:198-200)
+ *   nu_state/obs [B] float64                         (info["nusselt_state"], info["nusselt_obs"])
+ *   truncated    [B] int32: t >= episode_length      (rbc2D.py:178-180)
+ *   nan          [B] int32: step_contains_NaNs       (rbc_sim2D.jl:223-228)
+ * Any output pointer may be NULL except obs. */
+int rbc2d_step_dev(rbc2d_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, double* nu_state_dev,
+                   double* nu_obs_dev, int32_t* truncated_dev, int32_t* nan_dev);
+int rbc2d_step_host(rbc2d_sim* sim, const float* actions_host, float* obs_host, float* reward_host, double* nu_state_host,
+                    double* nu_obs_host, int32_t* truncated_host, int32_t* nan_host);
+
+/* get_observation / get_nusselt without stepping (what reset() returns). */
+int rbc2d_observe_dev(rbc2d_sim* sim, float* obs_dev, double* nu_state_dev, double* nu_obs_dev);
+int rbc2d_observe_host(rbc2d_sim* sim, float* obs_host, double* nu_state_host, double* nu_obs_host);
+
+/* get_state: [B][C][nz][nx] float32 in the Python layout, channels b,u,w(+pHY',pNHS). */
+int rbc2d_get_state_dev(rbc2d_sim* sim, float* out_dev, int32_t channels);
+int rbc2d_get_state_host(rbc2d_sim* sim, float* out_host, int32_t channels);
+
+/* Raw fields in checkpoint layout [B][2*nx*nz + nx*(nz+1)] float64 (for parity tests / checkpoint writing). */
+int rbc2d_get_fields_host(rbc2d_sim* sim, double* fields_host);
+
+/* get_info: simulation time and step counter per environment (rbc_sim2D_api.jl:134-137). */
+int rbc2d_get_info_host(rbc2d_sim* sim, double* t_host, int32_t* step_host);
+
+/* Introspection for benchmarks: kernels launched so far, CTAs per step launch, dynamic smem bytes. */
+int rbc2d_launch_count(const rbc2d_sim* sim, int64_t* launches, int32_t* grid, int32_t* smem_bytes);
+/* Device time of the most recent step kernel in milliseconds (CUDA events on the handle's stream;
+ * synchronises). */
+int rbc2d_last_step_kernel_ms(rbc2d_sim* sim, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBC_B200_H */

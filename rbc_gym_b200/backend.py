@@ -1,0 +1,307 @@
+"""ctypes binding of `librbc_b200.so` (C ABI in `include/rbc_b200.h`).
+
+This is the replacement for the reference's juliacall bridge
+(`src/rbc_gym/envs/rbc2D.py:111-115`: ``juliacall.newmodule`` + ``include(rbc_sim2D_api.jl)``).
+PyTorch is used only for device memory and streams; every numerical operation happens in the
+hand-written CUDA kernels behind the C ABI.  There is no CPU fallback: constructing a simulation
+without the built library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from pathlib import Path
+from typing import Optional, Sequence, Union
+
+import numpy as np
+
+from . import build as _build
+from .h5lite import Checkpoint2D, load_checkpoint_2d
+
+NX, NZ = 96, 64
+NCELL = NX * NZ
+NSTATE = 2 * NCELL + NX * (NZ + 1)
+
+
+class Rbc2dConfig(C.Structure):
+    """Mirror of ``rbc2d_config`` (include/rbc_b200.h)."""
+
+    _fields_ = [
+        ("num_envs", C.c_int32),
+        ("nx", C.c_int32), ("nz", C.c_int32),
+        ("obs_nx", C.c_int32), ("obs_nz", C.c_int32),
+        ("heaters", C.c_int32),
+        ("heater_limit", C.c_double),
+        ("ra", C.c_double), ("pr", C.c_double),
+        ("dt_action", C.c_double), ("dt_solver", C.c_double),
+        ("episode_length", C.c_double),
+        ("precision", C.c_int32), ("pressure", C.c_int32), ("device", C.c_int32),
+    ]
+
+
+# every symbol include/rbc_b200.h declares; tests check that the built library exports them all
+ABI_SYMBOLS = (
+    "rbc_abi_version", "rbc_last_error", "rbc2d_create", "rbc2d_destroy", "rbc2d_set_stream", "rbc2d_num_envs",
+    "rbc2d_state_values_per_env", "rbc2d_load_checkpoints", "rbc2d_reset_from_checkpoints_dev",
+    "rbc2d_reset_from_fields_host", "rbc2d_step_dev", "rbc2d_step_host", "rbc2d_observe_dev", "rbc2d_observe_host",
+    "rbc2d_get_state_dev", "rbc2d_get_state_host", "rbc2d_get_fields_host", "rbc2d_get_info_host",
+    "rbc2d_launch_count", "rbc2d_last_step_kernel_ms",
+)
+
+_lib = None
+
+
+class BackendUnavailable(RuntimeError):
+    pass
+
+
+def library_path() -> Path:
+    return _build.LIB
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen the C-ABI library; builds it in-tree with nvcc when missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc and no prebuilt library: fail loudly
+            if not _build.LIB.exists():
+                raise BackendUnavailable(
+                    f"{_build.LIB} is missing and could not be built ({e}); run `python -m rbc_gym_b200.build`"
+                ) from e
+    if not _build.LIB.exists():
+        raise BackendUnavailable(f"{_build.LIB} is missing; run `python -m rbc_gym_b200.build`")
+    L = C.CDLL(str(_build.LIB))
+    vp, ip = C.c_void_p, C.c_int32
+    L.rbc_abi_version.restype = C.c_int
+    L.rbc_last_error.restype = C.c_char_p
+    L.rbc2d_create.argtypes = [C.POINTER(Rbc2dConfig), C.POINTER(vp)]
+    L.rbc2d_destroy.argtypes = [vp]
+    L.rbc2d_set_stream.argtypes = [vp, vp]
+    L.rbc2d_num_envs.argtypes = [vp]
+    L.rbc2d_state_values_per_env.argtypes = [vp]
+    L.rbc2d_load_checkpoints.argtypes = [vp, vp, vp, vp, ip]
+    L.rbc2d_reset_from_checkpoints_dev.argtypes = [vp, vp, vp, ip]
+    L.rbc2d_reset_from_fields_host.argtypes = [vp, vp, vp, ip, ip]
+    L.rbc2d_step_dev.argtypes = [vp] * 8
+    L.rbc2d_step_host.argtypes = [vp] * 8
+    L.rbc2d_observe_dev.argtypes = [vp] * 4
+    L.rbc2d_observe_host.argtypes = [vp] * 4
+    L.rbc2d_get_state_dev.argtypes = [vp, vp, ip]
+    L.rbc2d_get_state_host.argtypes = [vp, vp, ip]
+    L.rbc2d_get_fields_host.argtypes = [vp, vp]
+    L.rbc2d_get_info_host.argtypes = [vp, vp, vp]
+    L.rbc2d_launch_count.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ip), C.POINTER(ip)]
+    L.rbc2d_last_step_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    if L.rbc_abi_version() != 1:
+        raise BackendUnavailable("librbc_b200.so ABI version mismatch; rebuild with `python -m rbc_gym_b200.build`")
+    _lib = L
+    return L
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def substep_schedule(dt_action: float, dt_solver: float = 0.03):
+    """run!'s ``dt' = min(dt_solver, stop_time - t)`` from t = 0 (same rule as the C++ side)."""
+    out, t = [], 0.0
+    while dt_action - t > 1e-10:
+        d = min(dt_solver, dt_action - t)
+        out.append(d)
+        t += d
+    return out
+
+
+class Sim2D:
+    """A batch of B independent 2D RBC environments on one GPU (one `rbc2d_sim` handle).
+
+    Mirrors the Julia API surface of `rbc_sim2D_api.jl` in batched form:
+    ``initialize_simulation`` -> constructor + `reset_*`, ``step_simulation`` -> `step`,
+    ``get_state`` -> `get_state`, ``get_observation``/``get_nusselt`` -> outputs of `step`/`observe`,
+    ``get_info`` -> `info`.
+    """
+
+    def __init__(self, num_envs: int, ra: float, dt_action: float = 1.5, *, obs_shape=(8, 48), state_shape=(64, 96),
+                 heaters: int = 12, heater_limit: float = 0.75, pr: float = 0.7, dt_solver: float = 0.03,
+                 episode_length: float = 300.0, precision: int = 32, pressure: bool = False, device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise BackendUnavailable("rbc_gym_b200 needs a CUDA device (there is no CPU fallback)")
+        self._L = load_library()
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.B = int(num_envs)
+        self.obs_shape = (int(obs_shape[0]), int(obs_shape[1]))
+        self.state_shape = (int(state_shape[0]), int(state_shape[1]))
+        self.heaters = int(heaters)
+        self.channels = 5 if pressure else 3
+        self.precision = int(precision)
+        self.ra, self.pr = float(ra), float(pr)
+        self.kappa = 1.0 / math.sqrt(self.pr * self.ra)
+        self.nu = math.sqrt(self.pr / self.ra)
+        self.dt_action, self.dt_solver = float(dt_action), float(dt_solver)
+        self.nsub = len(substep_schedule(self.dt_action, self.dt_solver))
+        self.cfg = Rbc2dConfig(self.B, self.state_shape[1], self.state_shape[0], self.obs_shape[1], self.obs_shape[0],
+                               self.heaters, float(heater_limit), self.ra, self.pr, self.dt_action, self.dt_solver,
+                               float(episode_length), self.precision, int(bool(pressure)), device)
+        h = C.c_void_p()
+        self._h = None
+        self._check(self._L.rbc2d_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+        with torch.cuda.device(self.device):
+            f32, f64, i32 = torch.float32, torch.float64, torch.int32
+            self.obs = torch.zeros((self.B, self.channels, *self.obs_shape), dtype=f32, device=self.device)
+            self.reward = torch.zeros(self.B, dtype=f32, device=self.device)
+            self.nu_state = torch.zeros(self.B, dtype=f64, device=self.device)
+            self.nu_obs = torch.zeros(self.B, dtype=f64, device=self.device)
+            self.truncated = torch.zeros(self.B, dtype=i32, device=self.device)
+            self.nan = torch.zeros(self.B, dtype=i32, device=self.device)
+        self.n_episodes = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RuntimeError(f"rbc_b200: {self._L.rbc_last_error().decode()}")
+
+    def _use_current_stream(self):
+        self._check(self._L.rbc2d_set_stream(self._h, C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rbc2d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ reset
+    def load_checkpoints(self, ckpt: Union[str, Path, Checkpoint2D]) -> int:
+        """Upload a checkpoint bank (`data/checkpoints/*/ckpt_ra*.h5`) to the device once."""
+        if not isinstance(ckpt, Checkpoint2D):
+            ckpt = load_checkpoint_2d(ckpt)
+        if ckpt.shape != self.state_shape:
+            raise ValueError(f"checkpoint grid {ckpt.shape} != state_shape {self.state_shape}")
+        b, u, w = (np.ascontiguousarray(a, dtype=np.float64) for a in (ckpt.b, ckpt.u, ckpt.w))
+        self._use_current_stream()
+        self._check(self._L.rbc2d_load_checkpoints(self._h, _np_ptr(b), _np_ptr(u), _np_ptr(w), ckpt.num_episodes))
+        self.n_episodes = ckpt.num_episodes
+        return self.n_episodes
+
+    def reset_from_checkpoints(self, ckpt_idx, env_ids=None):
+        """`initialize_simulation(checkpoint_path=...)` for all or the listed environments.
+
+        ckpt_idx / env_ids: int32 CUDA tensors (or anything convertible)."""
+        t = self.torch
+        idx = t.as_tensor(ckpt_idx, dtype=t.int32, device=self.device).contiguous()
+        ids = None if env_ids is None else t.as_tensor(env_ids, dtype=t.int32, device=self.device).contiguous()
+        n = self.B if ids is None else int(ids.numel())
+        if idx.numel() != n:
+            raise ValueError("ckpt_idx must have one entry per environment being reset")
+        self._use_current_stream()
+        self._check(self._L.rbc2d_reset_from_checkpoints_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
+                                                            C.c_void_p(idx.data_ptr()), n))
+
+    def reset_from_fields(self, fields: np.ndarray, env_ids: Optional[Sequence[int]] = None, project: bool = True):
+        """Reset from explicit `[n, 18528]` float64 fields (b,u,w); `project` mirrors Oceananigans' `set!`."""
+        f = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1, NSTATE)
+        ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
+        self._use_current_stream()
+        self._check(self._L.rbc2d_reset_from_fields_host(self._h, _np_ptr(ids), _np_ptr(f), f.shape[0], int(project)))
+
+    # ------------------------------------------------------------------ step / observe
+    def step(self, actions):
+        """One action step for the whole batch; actions `[B, heaters]` float32 CUDA tensor.
+
+        Returns views of the handle-owned output tensors (obs, reward, nu_state, nu_obs, truncated, nan)."""
+        t = self.torch
+        a = t.as_tensor(actions, dtype=t.float32, device=self.device).contiguous()
+        if a.shape != (self.B, self.heaters):
+            raise ValueError(f"actions must have shape {(self.B, self.heaters)}, got {tuple(a.shape)}")
+        self._use_current_stream()
+        p = lambda x: C.c_void_p(x.data_ptr())
+        self._check(self._L.rbc2d_step_dev(self._h, p(a), p(self.obs), p(self.reward), p(self.nu_state), p(self.nu_obs),
+                                           p(self.truncated), p(self.nan)))
+        return self.obs, self.reward, self.nu_state, self.nu_obs, self.truncated, self.nan
+
+    def step_host(self, actions: np.ndarray, out: Optional[dict] = None) -> dict:
+        """Same step through host buffers (H2D of the actions and D2H of all outputs inside the call)."""
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        if a.shape != (self.B, self.heaters):
+            raise ValueError(f"actions must have shape {(self.B, self.heaters)}, got {a.shape}")
+        if out is None:
+            out = self.alloc_host_outputs()
+        self._use_current_stream()
+        self._check(self._L.rbc2d_step_host(self._h, _np_ptr(a), _np_ptr(out["obs"]), _np_ptr(out["reward"]),
+                                            _np_ptr(out["nu_state"]), _np_ptr(out["nu_obs"]), _np_ptr(out["truncated"]),
+                                            _np_ptr(out["nan"])))
+        return out
+
+    def alloc_host_outputs(self, pinned: bool = False) -> dict:
+        shapes = {"obs": ((self.B, self.channels, *self.obs_shape), np.float32), "reward": ((self.B,), np.float32),
+                  "nu_state": ((self.B,), np.float64), "nu_obs": ((self.B,), np.float64),
+                  "truncated": ((self.B,), np.int32), "nan": ((self.B,), np.int32)}
+        if not pinned:
+            return {k: np.zeros(s, d) for k, (s, d) in shapes.items()}
+        t = self.torch
+        return {k: t.zeros(s, dtype=getattr(t, np.dtype(d).name)).pin_memory().numpy() for k, (s, d) in shapes.items()}
+
+    def observe(self):
+        """`get_observation` + `get_nusselt` of the current state without stepping."""
+        self._use_current_stream()
+        p = lambda x: C.c_void_p(x.data_ptr())
+        self._check(self._L.rbc2d_observe_dev(self._h, p(self.obs), p(self.nu_state), p(self.nu_obs)))
+        return self.obs, self.nu_state, self.nu_obs
+
+    def get_state(self, channels: Optional[int] = None):
+        """`get_state` in the Python layout: float32 CUDA tensor `[B, C, Nz, Nx]`."""
+        ch = self.channels if channels is None else int(channels)
+        out = self.torch.empty((self.B, ch, NZ, NX), dtype=self.torch.float32, device=self.device)
+        self._use_current_stream()
+        self._check(self._L.rbc2d_get_state_dev(self._h, C.c_void_p(out.data_ptr()), ch))
+        return out
+
+    def fields(self) -> np.ndarray:
+        """Raw (b,u,w) in checkpoint layout `[B, 18528]` float64 on the host."""
+        out = np.empty((self.B, NSTATE), np.float64)
+        self._use_current_stream()
+        self._check(self._L.rbc2d_get_fields_host(self._h, _np_ptr(out)))
+        return out
+
+    def info(self):
+        """`get_info`: (t[B] float64, step[B] int32) on the host."""
+        t = np.empty(self.B, np.float64)
+        s = np.empty(self.B, np.int32)
+        self._use_current_stream()
+        self._check(self._L.rbc2d_get_info_host(self._h, _np_ptr(t), _np_ptr(s)))
+        return t, s
+
+    def launch_info(self):
+        n, g, s = C.c_int64(), C.c_int32(), C.c_int32()
+        self._check(self._L.rbc2d_launch_count(self._h, C.byref(n), C.byref(g), C.byref(s)))
+        return {"launches": n.value, "grid": g.value, "smem_bytes": s.value}
+
+    def last_step_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._L.rbc2d_last_step_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+
+def split_fields(fields: np.ndarray):
+    """`[B, 18528]` -> b[B,64,96], u[B,64,96], w[B,65,96]."""
+    B = fields.shape[0]
+    return (fields[:, :NCELL].reshape(B, NZ, NX), fields[:, NCELL:2 * NCELL].reshape(B, NZ, NX),
+            fields[:, 2 * NCELL:].reshape(B, NZ + 1, NX))
+
+
+def pack_fields(b, u, w) -> np.ndarray:
+    b, u, w = (np.asarray(a, dtype=np.float64) for a in (b, u, w))
+    B = b.shape[0]
+    return np.concatenate([b.reshape(B, -1), u.reshape(B, -1), w.reshape(B, -1)], axis=1)

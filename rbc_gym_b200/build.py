@@ -1,0 +1,60 @@
+"""In-tree build of the sm_100a shared library (`rbc_gym_b200/csrc/librbc_b200.so`).
+
+nvcc cross-compiles without a GPU; the built `.so` is git-ignored but travels with the repo
+snapshot to the GPU box.  Run as ``python -m rbc_gym_b200.build [-v]``.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB = CSRC / "librbc_b200.so"
+SOURCES = [CSRC / "rbc2d_lib.cu"]
+HEADERS = [CSRC / "rbc2d_core.h", CSRC.parent.parent / "include" / "rbc_b200.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def find_nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA toolkit is required to build rbc_gym_b200")
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any(p.stat().st_mtime > t for p in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    cmd = [find_nvcc(), *NVCC_FLAGS]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    # $CC/$CXX in this image point at a wrapper compiler; let nvcc use the system g++
+    host = shutil.which("g++")
+    if host:
+        cmd += ["-ccbin", host]
+    cmd += ["-o", str(LIB), *map(str, SOURCES)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({res.returncode}): {' '.join(cmd)}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose="-v" in sys.argv))

@@ -1,0 +1,818 @@
+// rbc2d_core.h — the 2D Rayleigh-Benard action step as one CTA-per-environment program.
+//
+// Replaces, for the hot path, the reference's
+//   step_simulation -> run!(simulation)            src/rbc_gym/sim/rbc_sim2D_api.jl:75-97
+//   NonhydrostaticModel configuration               src/rbc_gym/sim/rbc_sim2D.jl:149-160
+//   bottom_T / collate_actions_colin                src/rbc_gym/sim/rbc_sim2D.jl:87-138
+//   get_state / get_observation / get_nusselt       src/rbc_gym/sim/rbc_sim2D_api.jl:102-163
+//   step_contains_NaNs                              src/rbc_gym/sim/rbc_sim2D.jl:223-228
+// (the PDE arithmetic of run! lives in Oceananigans.jl 0.92.0; scheme per SURVEY.md 8a).
+//
+// The file is plain C++ shared between nvcc (the sm_100a kernel in rbc2d_kernels.cu) and g++
+// (tests/emu: a sequential "one CTA" emulator used to check the exact kernel logic against the
+// fp64 oracle on a machine without a GPU).  A "phase" is a piece of per-thread work followed by
+// a CTA-wide barrier; RBC_PHASE runs it for threadIdx.x on the device and for tid = 0..NT-1 on
+// the host.
+//
+// Data layout (one environment): b[NZ][NX] centres, u[NZ][NX] left x-faces, w[NZ+1][NX] bottom
+// z-faces — exactly the checkpoint layout, x fastest.  One CTA keeps the whole
+// environment in shared memory for all RK3 stages of an action step.
+//
+// Thread map: NT = 384 = 96 columns x 4 strips of 16 rows.  In the tendency phase a thread
+// marches up its strip holding 7-row sliding windows of its own column in registers, so z-fluxes
+// are computed once and carried; x-neighbours come from shared memory (consecutive lanes ->
+// consecutive words, conflict-free; 96 = 3 x 32 keeps periodic wrap on the same banks).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RBC_HD __host__ __device__ __forceinline__
+#else
+#define RBC_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define RBC_PHASE(...) { const int tid = threadIdx.x; __VA_ARGS__ } __syncthreads();
+#define RBC_UNROLL _Pragma("unroll")
+#else
+#define RBC_PHASE(...) for (int tid = 0; tid < rbc2d::NT; ++tid) { __VA_ARGS__ }
+#define RBC_UNROLL
+#endif
+
+namespace rbc2d {
+
+constexpr int NX = 96, NZ = 64;
+constexpr int NSTRIP = 4, RS = NZ / NSTRIP;      // 4 strips of 16 rows
+constexpr int NT = NX * NSTRIP;                  // 384 threads
+constexpr int NCELL = NX * NZ;                   // 6144
+constexpr int NWF = NX * (NZ + 1);               // 6240 (w incl. both wall faces)
+constexpr int NSTATE = 2 * NCELL + NWF;          // 18528 values per environment
+constexpr int OFF_B = 0, OFF_U = NCELL, OFF_W = 2 * NCELL;
+constexpr int RSTR = 108;                        // row stride (words) of the Poisson scratch
+constexpr int NR = NZ * RSTR;                    // scratch size in words
+constexpr int NH = NX / 2;                       // 48 complex points per packed row
+constexpr int MAX_HEATERS = 32;
+constexpr int NRED = 7;                          // partial sums per thread in the epilogue
+
+// ------------------------------------------------------------------------------------------
+// constants of one simulation configuration (host-computed in fp64, then cast)
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+struct Consts {
+    Real idx, idz, idx2, idz2;   // 1/dx, 1/dz, 1/dx^2, 1/dz^2
+    Real nu, kappa, b_top;
+    Real dt_full, dt_last;       // run!'s substep schedule: (nsub-1) x dt_full + dt_last
+    int nsub;
+    int heaters;
+    double heater_limit, lx, dx; // heater profile is evaluated in fp64 like the reference
+    double kappa_d, dt_action, episode_length;
+    int obs_nz, obs_nx;          // sensors (8, 48)
+    int channels;                // 3, or 5 with pressure
+};
+
+// tables in global memory, staged to shared memory by the CTA
+template <typename Real>
+struct Tables {
+    const Real* tinv;   // [NZ][NX]  Thomas pivots per spectral word (see build_tables)
+    const Real* tw48;   // [48][2]   cos/sin(2 pi j / 48)
+    const Real* tw96;   // [25][2]   cos/sin(2 pi m / 96)
+    Real thomas_scale;  // dz^2 / 48
+};
+
+template <typename Real>
+struct EnvIO {
+    // per-environment global arrays, indexed by env
+    Real* state;              // [B][NSTATE]
+    const float* actions;     // [B][heaters]
+    float* obs;               // [B][channels][obs_nz][obs_nx]
+    float* reward;            // [B]
+    double* nu_state;         // [B]
+    double* nu_obs;           // [B]
+    double* t;                // [B] simulation time of the episode
+    int* step_count;          // [B]
+    int* truncated;           // [B]
+    int* nan_flag;            // [B]
+    Real* pressure;           // [B][2][NZ][NX] (pHY', pNHS) or nullptr
+};
+
+// everything one CTA needs while it owns an environment
+template <typename Real>
+struct Ctx {
+    Real* s0;        // shared: state buffer 0 (NSTATE)
+    Real* s1;        // second state buffer: shared (fp32) or global (fp64)
+    Real* R;         // shared: Poisson scratch / pHY' (NR)
+    Real* Tb;        // shared: bottom wall temperature per column (NX)
+    Real* tw48;      // shared twiddles
+    Real* tw96;
+    Real* gm;        // global: previous-stage tendencies of this CTA (NSTATE)
+    const Real* tinv;
+    double* red;     // shared: NRED*NT doubles for the epilogue reductions (may alias R.. no: separate)
+};
+
+// what one kernel launch does with each environment it visits
+struct RunFlags {
+    int nsub;            // RK3 steps to take (Consts::nsub for a step, 0 for observe-only)
+    int project_first;   // 1: project the loaded velocity first (Oceananigans set!, dtau = 1)
+    int advance_clock;   // 1: t += dt_action, step += 1, truncation flag (step_simulation)
+};
+
+RBC_HD int wrapx(int i) { return i < 0 ? i + NX : (i >= NX ? i - NX : i); }
+
+// ------------------------------------------------------------------------------------------
+// heater profile (collate_actions_colin, rbc_sim2D.jl:87-133), fp64 like the reference
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+RBC_HD double heater_T(const Consts<Real>& C, const float* action, double x)
+{
+    const int na = C.heaters;
+    const double ampl = C.heater_limit, dx = 0.03;
+    double mean = 0.0;
+    for (int s = 0; s < na; ++s) mean += ampl * (double)action[s];
+    mean /= na;
+    double dev = 0.0;
+    for (int s = 0; s < na; ++s) {
+        double d = fabs(ampl * (double)action[s] - mean);
+        if (d > dev) dev = d;
+    }
+    double K2 = dev / ampl;
+    if (!(K2 > 1.0)) K2 = 1.0;
+    const double seg = C.lx / na;
+    int s = (int)floor(x / seg);
+    if (s >= na) s = na - 1;
+    const int sm = (s == 0) ? na - 1 : s - 1, sp = (s == na - 1) ? 0 : s + 1;
+    const double T0 = 2 + (ampl * (double)action[sm] - mean) / K2;
+    const double T1 = 2 + (ampl * (double)action[s] - mean) / K2;
+    const double T2 = 2 + (ampl * (double)action[sp] - mean) / K2;
+    const double xp = x - s * seg;
+    if (xp < dx) return T0 + ((T0 - T1) / (4 * dx * dx * dx)) * (xp - 2 * dx) * (xp + dx) * (xp + dx);
+    if (xp >= seg - dx)
+        return T1 + ((T1 - T2) / (4 * dx * dx * dx)) * (xp - seg - 2 * dx) * (xp - seg + dx) * (xp - seg + dx);
+    return T1;
+}
+
+// ------------------------------------------------------------------------------------------
+// reconstruction on a 6-value window win[0..5] = c[j-3 .. j+2] around the face j-1|j
+// (SURVEY 8a "Advection"); the right-biased stencil is the mirror image of the left one.
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+RBC_HD Real upwind5(Real vel, const Real* win)
+{
+    const bool pos = vel > Real(0);
+    const Real x0 = pos ? win[0] : win[5], x1 = pos ? win[1] : win[4], x2 = pos ? win[2] : win[3];
+    const Real x3 = pos ? win[3] : win[2], x4 = pos ? win[4] : win[1];
+    const Real phi = (Real(2) * x0 - Real(13) * x1 + Real(47) * x2 + Real(27) * x3 - Real(3) * x4) * Real(1.0 / 60.0);
+    return vel * phi;
+}
+template <typename Real>
+RBC_HD Real upwind3(Real vel, const Real* win)
+{
+    const bool pos = vel > Real(0);
+    const Real x1 = pos ? win[1] : win[4], x2 = pos ? win[2] : win[3], x3 = pos ? win[3] : win[2];
+    return vel * ((-x1 + Real(5) * x2 + Real(2) * x3) * Real(1.0 / 6.0));
+}
+template <typename Real>
+RBC_HD Real upwind1(Real vel, const Real* win)
+{
+    return vel * (vel > Real(0) ? win[2] : win[3]);
+}
+// order: 5, 3 or 1 (uniform across a warp: it depends on the row only)
+template <typename Real>
+RBC_HD Real upwind_ord(Real vel, const Real* win, int ord)
+{
+    if (ord == 5) return upwind5(vel, win);
+    if (ord == 3) return upwind3(vel, win);
+    return upwind1(vel, win);
+}
+template <typename Real>
+RBC_HD Real centred4(Real a, Real b, Real c, Real d)   // values at j-2, j-1, j, j+1
+{
+    return (Real(7) * (b + c) - (a + d)) * Real(1.0 / 12.0);
+}
+template <typename Real>
+RBC_HD Real centred_ord(Real a, Real b, Real c, Real d, int ord)
+{
+    return ord == 4 ? centred4(a, b, c, d) : (b + c) * Real(0.5);
+}
+// wall-order rules (0-based), SURVEY 8a: centres->z-face kf, and z-faces->centre kc
+RBC_HD int ord_up_face(int kf) { return (kf >= 3 && kf <= NZ - 3) ? 5 : ((kf == 2 || kf == NZ - 2) ? 3 : 1); }
+RBC_HD int ord_ce_face(int kf) { return (kf >= 2 && kf <= NZ - 2) ? 4 : 2; }
+RBC_HD int ord_up_cen(int kc) { return (kc >= 2 && kc <= NZ - 3) ? 5 : ((kc == 1 || kc == NZ - 2) ? 3 : 1); }
+RBC_HD int ord_ce_cen(int kc) { return (kc >= 1 && kc <= NZ - 2) ? 4 : 2; }
+
+// ------------------------------------------------------------------------------------------
+// phase: hydrostatic pressure anomaly (split mode only), column integral from the top
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+RBC_HD void phase_phy(int tid, const Consts<Real>& C, const Real* cb, Real* phy)
+{
+    if (tid >= NX) return;
+    const Real dz = Real(1) / C.idz;
+    Real below = cb[(NZ - 1) * NX + tid];
+    Real acc = -Real(0.5) * (below + (Real(2) * C.b_top - below)) * dz;
+    phy[(NZ - 1) * RSTR + tid] = acc;
+    for (int k = NZ - 2; k >= 0; --k) {
+        const Real bk = cb[k * NX + tid];
+        acc = acc - Real(0.5) * (bk + below) * dz;
+        phy[k * RSTR + tid] = acc;
+        below = bk;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase: tendencies + RK3 substep for one strip.  Reads the current state `c`, writes the
+// predicted state `n` (U* = U + dt (gam G + zet G-)), stores G into the CTA's G- slab.
+// ------------------------------------------------------------------------------------------
+template <typename Real, bool SPLIT>
+RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* c, Real* n, const Real* phy,
+                           const Real* Tb, Real* gm, Real dt, Real gam, Real zet, bool use_gm)
+{
+    const int i = tid % NX, s = tid / NX, k0 = s * RS;
+    const Real* cb = c + OFF_B;
+    const Real* cu = c + OFF_U;
+    const Real* cw = c + OFF_W;
+    int col[7];
+    RBC_UNROLL
+    for (int j = 0; j < 7; ++j) col[j] = wrapx(i - 3 + j);
+
+    // sliding windows of the own column; index j <-> row k-3+j
+    Real bz[7], uz[7], wz[7], u1z[4], wxr[7];
+    RBC_UNROLL
+    for (int j = 0; j < 7; ++j) {
+        const int k = k0 - 3 + j;
+        const bool ok = (k >= 0 && k < NZ);
+        bz[j] = ok ? cb[k * NX + i] : Real(0);
+        uz[j] = ok ? cu[k * NX + i] : Real(0);
+        wz[j] = (k >= 0 && k <= NZ) ? cw[k * NX + i] : Real(0);
+    }
+    RBC_UNROLL
+    for (int j = 0; j < 4; ++j) {                      // u(i+1, k-2 .. k+1)
+        const int k = k0 - 2 + j;
+        u1z[j] = (k >= 0 && k < NZ) ? cu[k * NX + col[4]] : Real(0);
+    }
+    RBC_UNROLL
+    for (int j = 0; j < 7; ++j) wxr[j] = cw[k0 * NX + col[j]];   // w(i-3..i+3, face k0)
+
+    // fluxes through the strip's lower boundary (carried afterwards)
+    Real Fzb_lo = Real(0), Wu_lo = Real(0), Ww_lo = Real(0);
+    if (k0 >= 1) {
+        const int o = ord_up_face(k0);
+        Fzb_lo = upwind_ord(wz[3], bz, o);
+        Wu_lo = upwind_ord(centred4(wxr[1], wxr[2], wxr[3], wxr[4]), uz, o);
+        const int kc = k0 - 1;
+        Ww_lo = upwind_ord(centred_ord(wz[1], wz[2], wz[3], wz[4], ord_ce_cen(kc)), wz, ord_up_cen(kc));
+    }
+    const Real tb = Tb[i];
+
+    RBC_UNROLL
+    for (int r = 0; r < RS; ++r) {
+        const int k = k0 + r;
+        Real bx[7], ux[7], wxn[7];
+        RBC_UNROLL
+        for (int j = 0; j < 7; ++j) {
+            bx[j] = (j == 3) ? bz[3] : cb[k * NX + col[j]];
+            ux[j] = (j == 3) ? uz[3] : ((j == 4) ? u1z[2] : cu[k * NX + col[j]]);
+            wxn[j] = (j == 3) ? wz[4] : cw[(k + 1) * NX + col[j]];      // face k+1 <= NZ always valid
+        }
+        const bool top = (k == NZ - 1);
+
+        // ---- tracer ----
+        const Real Fx0 = upwind5(ux[3], bx);
+        const Real Fx1 = upwind5(ux[4], bx + 1);
+        const Real Fzb_hi = top ? Real(0) : upwind_ord(wz[4], bz + 1, ord_up_face(k + 1));
+        const Real bdn = (k == 0) ? (Real(2) * tb - bz[3]) : bz[2];
+        const Real bup = top ? (Real(2) * C.b_top - bz[3]) : bz[4];
+        const Real Gb = -((Fx1 - Fx0) * C.idx + (Fzb_hi - Fzb_lo) * C.idz) +
+                        C.kappa * ((bx[4] - Real(2) * bx[3] + bx[2]) * C.idx2 + (bup - Real(2) * bz[3] + bdn) * C.idz2);
+
+        // ---- u ----
+        const Real F0 = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);          // centre i-1
+        const Real F1 = upwind5(centred4(ux[2], ux[3], ux[4], ux[5]), ux + 1);      // centre i
+        const Real Wu_hi = top ? Real(0)
+                               : upwind_ord(centred4(wxn[1], wxn[2], wxn[3], wxn[4]), uz + 1, ord_up_face(k + 1));
+        const Real udn = (k == 0) ? -uz[3] : uz[2];
+        const Real uup = top ? -uz[3] : uz[4];
+        Real Gu = -((F1 - F0) * C.idx + (Wu_hi - Wu_lo) * C.idz) +
+                  C.nu * ((ux[4] - Real(2) * ux[3] + ux[2]) * C.idx2 + (uup - Real(2) * uz[3] + udn) * C.idz2);
+        if (SPLIT) Gu -= (phy[k * RSTR + i] - phy[k * RSTR + col[2]]) * C.idx;
+
+        // ---- w (face k; face 0 is the wall) ----
+        const int oc = ord_ce_face(k);
+        const Real ut0 = centred_ord(uz[1], uz[2], uz[3], uz[4], oc);               // x-face i,   z-face k
+        const Real ut1 = centred_ord(u1z[0], u1z[1], u1z[2], u1z[3], oc);           // x-face i+1, z-face k
+        const Real Fw0 = upwind5(ut0, wxr);
+        const Real Fw1 = upwind5(ut1, wxr + 1);
+        const Real Ww_hi = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], ord_ce_cen(k)), wz + 1, ord_up_cen(k));
+        Real Gw = -((Fw1 - Fw0) * C.idx + (Ww_hi - Ww_lo) * C.idz) +
+                  C.nu * ((wxr[4] - Real(2) * wxr[3] + wxr[2]) * C.idx2 + (wz[4] - Real(2) * wz[3] + wz[2]) * C.idz2);
+        if (!SPLIT) Gw += Real(0.5) * (bz[2] + bz[3]);
+        if (k == 0) Gw = Real(0);
+
+        // ---- RK3 substep; G- lives in a per-CTA global slab, [field][r][tid] (coalesced) ----
+        Real gb0 = Real(0), gu0 = Real(0), gw0 = Real(0);
+        if (use_gm) {
+            gb0 = gm[(0 * RS + r) * NT + tid];
+            gu0 = gm[(1 * RS + r) * NT + tid];
+            gw0 = gm[(2 * RS + r) * NT + tid];
+        }
+        gm[(0 * RS + r) * NT + tid] = Gb;
+        gm[(1 * RS + r) * NT + tid] = Gu;
+        gm[(2 * RS + r) * NT + tid] = Gw;
+        n[OFF_B + k * NX + i] = bz[3] + dt * (gam * Gb + zet * gb0);
+        n[OFF_U + k * NX + i] = uz[3] + dt * (gam * Gu + zet * gu0);
+        n[OFF_W + k * NX + i] = (k == 0) ? Real(0) : wz[3] + dt * (gam * Gw + zet * gw0);
+
+        // ---- slide ----
+        Fzb_lo = Fzb_hi; Wu_lo = Wu_hi; Ww_lo = Ww_hi;
+        RBC_UNROLL
+        for (int j = 0; j < 6; ++j) { bz[j] = bz[j + 1]; uz[j] = uz[j + 1]; wz[j] = wz[j + 1]; }
+        const int kn = k + 4;
+        bz[6] = (kn < NZ) ? cb[kn * NX + i] : Real(0);
+        uz[6] = (kn < NZ) ? cu[kn * NX + i] : Real(0);
+        wz[6] = (kn <= NZ) ? cw[kn * NX + i] : Real(0);
+        u1z[0] = u1z[1]; u1z[1] = u1z[2]; u1z[2] = u1z[3];
+        u1z[3] = (k + 2 < NZ) ? cu[(k + 2) * NX + col[4]] : Real(0);
+        RBC_UNROLL
+        for (int j = 0; j < 7; ++j) wxr[j] = wxn[j];
+    }
+    if (s == NSTRIP - 1) n[OFF_W + NZ * NX + i] = Real(0);       // top wall face
+}
+
+// ------------------------------------------------------------------------------------------
+// phase: copy a state slab (used when the predicted state lives in global memory, fp64 mode)
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+RBC_HD void phase_copy(int tid, const Real* src, Real* dst, int nvals)
+{
+    for (int q = tid; q < nvals; q += NT) dst[q] = src[q];
+}
+
+// ------------------------------------------------------------------------------------------
+// phase: divergence of the predicted velocity -> scratch R[k][i]
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+RBC_HD void phase_div(int tid, const Consts<Real>& C, const Real* p, Real* R)
+{
+    const int i = tid % NX, s = tid / NX, ip = wrapx(i + 1);
+    const Real* pu = p + OFF_U;
+    const Real* pw = p + OFF_W;
+    RBC_UNROLL
+    for (int r = 0; r < RS; ++r) {
+        const int k = s * RS + r;
+        R[k * RSTR + i] = (pu[k * NX + ip] - pu[k * NX + i]) * C.idx + (pw[(k + 1) * NX + i] - pw[k * NX + i]) * C.idz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small complex DFTs (SIGN = -1 forward, +1 inverse), natural in/out order
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+struct cx {
+    Real re, im;
+};
+template <typename Real> RBC_HD cx<Real> cadd(cx<Real> a, cx<Real> b) { return {a.re + b.re, a.im + b.im}; }
+template <typename Real> RBC_HD cx<Real> csub(cx<Real> a, cx<Real> b) { return {a.re - b.re, a.im - b.im}; }
+template <typename Real> RBC_HD cx<Real> cmul(cx<Real> a, Real c, Real s) { return {a.re * c - a.im * s, a.re * s + a.im * c}; }
+template <int SIGN, typename Real> RBC_HD cx<Real> muli(cx<Real> a)   // multiply by SIGN*i
+{
+    return SIGN > 0 ? cx<Real>{-a.im, a.re} : cx<Real>{a.im, -a.re};
+}
+
+template <int SIGN, typename Real>
+RBC_HD void dft4(cx<Real>& x0, cx<Real>& x1, cx<Real>& x2, cx<Real>& x3)
+{
+    const cx<Real> t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = muli<SIGN>(csub(x1, x3));
+    x0 = cadd(t0, t2); x2 = csub(t0, t2);
+    x1 = cadd(t1, t3); x3 = csub(t1, t3);
+}
+template <int SIGN, typename Real>
+RBC_HD void dft8(cx<Real>* x)
+{
+    cx<Real> e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6], o0 = x[1], o1 = x[3], o2 = x[5], o3 = x[7];
+    dft4<SIGN>(e0, e1, e2, e3);
+    dft4<SIGN>(o0, o1, o2, o3);
+    const Real h = Real(0.70710678118654752440);
+    // W8^k O[k]: k=1: h(1 + SIGN i) ; k=2: SIGN i ; k=3: h(-1 + SIGN i)
+    const cx<Real> w1 = cmul(o1, h, Real(SIGN) * h);
+    const cx<Real> w2 = muli<SIGN>(o2);
+    const cx<Real> w3 = cmul(o3, -h, Real(SIGN) * h);
+    x[0] = cadd(e0, o0); x[4] = csub(e0, o0);
+    x[1] = cadd(e1, w1); x[5] = csub(e1, w1);
+    x[2] = cadd(e2, w2); x[6] = csub(e2, w2);
+    x[3] = cadd(e3, w3); x[7] = csub(e3, w3);
+}
+template <int SIGN, typename Real>
+RBC_HD void dft3(cx<Real>& x0, cx<Real>& x1, cx<Real>& x2)
+{
+    const Real q = Real(0.86602540378443864676);
+    const cx<Real> s = cadd(x1, x2), d = muli<SIGN>(csub(x1, x2));
+    const cx<Real> m = {x0.re - Real(0.5) * s.re, x0.im - Real(0.5) * s.im};
+    x0 = cadd(x0, s);
+    x1 = {m.re + q * d.re, m.im + q * d.im};
+    x2 = {m.re - q * d.re, m.im - q * d.im};
+}
+template <int SIGN, typename Real>
+RBC_HD void dft6(cx<Real>* x)
+{
+    cx<Real> e0 = x[0], e1 = x[2], e2 = x[4], o0 = x[1], o1 = x[3], o2 = x[5];
+    dft3<SIGN>(e0, e1, e2);
+    dft3<SIGN>(o0, o1, o2);
+    const Real q = Real(0.86602540378443864676);
+    const cx<Real> w1 = cmul(o1, Real(0.5), Real(SIGN) * q);
+    const cx<Real> w2 = cmul(o2, Real(-0.5), Real(SIGN) * q);
+    x[0] = cadd(e0, o0); x[3] = csub(e0, o0);
+    x[1] = cadd(e1, w1); x[4] = csub(e1, w1);
+    x[2] = cadd(e2, w2); x[5] = csub(e2, w2);
+}
+
+// A row of R holds 48 complex numbers z[n] = (R[2n], R[2n+1]).  The 48-point transform is
+// 6 x 8 Cooley-Tukey done in place: pass A = 8-point DFTs over n2 (n = n1 + 6 n2) + twiddle,
+// pass B = 6-point DFTs over n1.  Output X[8 k1 + k2] sits in slot k1 + 6 k2.
+template <typename Real>
+RBC_HD void fft_passA_fwd(int item, Real* R, const Real* tw48)
+{
+    const int row = item / 6, n1 = item % 6;
+    Real* z = R + row * RSTR;
+    cx<Real> a[8];
+    RBC_UNROLL
+    for (int n2 = 0; n2 < 8; ++n2) a[n2] = {z[2 * (n1 + 6 * n2)], z[2 * (n1 + 6 * n2) + 1]};
+    dft8<-1>(a);
+    RBC_UNROLL
+    for (int k2 = 0; k2 < 8; ++k2) {
+        const int j = n1 * k2;                       // W48^(n1 k2), forward: e^{-i theta}
+        const cx<Real> v = cmul(a[k2], tw48[2 * j], -tw48[2 * j + 1]);
+        z[2 * (n1 + 6 * k2)] = v.re; z[2 * (n1 + 6 * k2) + 1] = v.im;
+    }
+}
+template <typename Real>
+RBC_HD void fft_passB_fwd(int item, Real* R)
+{
+    const int row = item / 8, k2 = item % 8;
+    Real* z = R + row * RSTR + 12 * k2;
+    cx<Real> a[6];
+    RBC_UNROLL
+    for (int n1 = 0; n1 < 6; ++n1) a[n1] = {z[2 * n1], z[2 * n1 + 1]};
+    dft6<-1>(a);
+    RBC_UNROLL
+    for (int k1 = 0; k1 < 6; ++k1) { z[2 * k1] = a[k1].re; z[2 * k1 + 1] = a[k1].im; }
+}
+template <typename Real>
+RBC_HD void fft_passB_inv(int item, Real* R, const Real* tw48)
+{
+    const int row = item / 8, k2 = item % 8;
+    Real* z = R + row * RSTR + 12 * k2;
+    cx<Real> a[6];
+    RBC_UNROLL
+    for (int k1 = 0; k1 < 6; ++k1) a[k1] = {z[2 * k1], z[2 * k1 + 1]};
+    dft6<+1>(a);
+    RBC_UNROLL
+    for (int n1 = 0; n1 < 6; ++n1) {
+        const int j = n1 * k2;                       // conj twiddle
+        const cx<Real> v = cmul(a[n1], tw48[2 * j], tw48[2 * j + 1]);
+        z[2 * n1] = v.re; z[2 * n1 + 1] = v.im;
+    }
+}
+template <typename Real>
+RBC_HD void fft_passA_inv(int item, Real* R)
+{
+    const int row = item / 6, n1 = item % 6;
+    Real* z = R + row * RSTR;
+    cx<Real> a[8];
+    RBC_UNROLL
+    for (int k2 = 0; k2 < 8; ++k2) a[k2] = {z[2 * (n1 + 6 * k2)], z[2 * (n1 + 6 * k2) + 1]};
+    dft8<+1>(a);
+    RBC_UNROLL
+    for (int n2 = 0; n2 < 8; ++n2) { z[2 * (n1 + 6 * n2)] = a[n2].re; z[2 * (n1 + 6 * n2) + 1] = a[n2].im; }
+}
+RBC_HD int slot48(int k) { return (k >> 3) + 6 * (k & 7); }
+
+// real-FFT split: Z (48-point transform of the packed row) <-> X[0..48] (96-point spectrum).
+// item = (row, m), m = 0..24 handles the pair (m, 48-m) in place.
+template <typename Real>
+RBC_HD void fft_untangle(int item, Real* R, const Real* tw96)
+{
+    const int row = item / 25, m = item % 25;
+    Real* z = R + row * RSTR;
+    if (m == 0) {
+        const Real a = z[0], b = z[1];
+        z[0] = a + b; z[1] = a - b;                  // X[0], X[48] (both real)
+        return;
+    }
+    const int pa = 2 * slot48(m), pb = 2 * slot48(48 - m);
+    if (m == 24) { z[pa + 1] = -z[pa + 1]; return; }  // X[24] = conj Z[24]
+    const cx<Real> Zm = {z[pa], z[pa + 1]}, Zc = {z[pb], -z[pb + 1]};
+    const cx<Real> E = {Real(0.5) * (Zm.re + Zc.re), Real(0.5) * (Zm.im + Zc.im)};
+    const cx<Real> D = {Real(0.5) * (Zm.re - Zc.re), Real(0.5) * (Zm.im - Zc.im)};
+    const cx<Real> O = {D.im, -D.re};                // -i D
+    const cx<Real> WO = cmul(O, tw96[2 * m], -tw96[2 * m + 1]);
+    z[pa] = E.re + WO.re; z[pa + 1] = E.im + WO.im;              // X[m]
+    z[pb] = E.re - WO.re; z[pb + 1] = -(E.im - WO.im);           // X[48-m] = conj(E - W O)
+}
+template <typename Real>
+RBC_HD void fft_tangle(int item, Real* R, const Real* tw96)
+{
+    const int row = item / 25, m = item % 25;
+    Real* z = R + row * RSTR;
+    if (m == 0) {
+        const Real a = z[0], b = z[1];
+        z[0] = Real(0.5) * (a + b); z[1] = Real(0.5) * (a - b);    // Z[0] = E0 + i O0
+        return;
+    }
+    const int pa = 2 * slot48(m), pb = 2 * slot48(48 - m);
+    if (m == 24) { z[pa + 1] = -z[pa + 1]; return; }
+    const cx<Real> Xm = {z[pa], z[pa + 1]}, Xc = {z[pb], -z[pb + 1]};
+    const cx<Real> E = {Real(0.5) * (Xm.re + Xc.re), Real(0.5) * (Xm.im + Xc.im)};
+    const cx<Real> WO = {Real(0.5) * (Xm.re - Xc.re), Real(0.5) * (Xm.im - Xc.im)};
+    const cx<Real> O = cmul(WO, tw96[2 * m], tw96[2 * m + 1]);   // conj(W) * WO
+    // Z[m] = E + iO ; Z[48-m] = conj(E) + i conj(O)
+    z[pa] = E.re - O.im; z[pa + 1] = E.im + O.re;
+    z[pb] = E.re + O.im; z[pb + 1] = -E.im + O.re;
+}
+
+// ------------------------------------------------------------------------------------------
+// phase: tridiagonal solves in z, one thread per spectral word (96 real systems, in place).
+//   p(k-1) - (2 + lam dz^2) p(k) + p(k+1) = dz^2 r(k),  p(-1)=p(0), p(NZ)=p(NZ-1)
+// tinv[k][t] = 1/(diag_k - tinv[k-1][t]) precomputed per word; `scale` = dz^2/48 folds the
+// inverse-FFT normalisation.
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+RBC_HD void phase_thomas(int tid, Real* R, const Real* tinv, Real scale)
+{
+    if (tid >= NX) return;
+    Real d = Real(0);
+    for (int k = 0; k < NZ; ++k) {
+        const Real iv = tinv[k * NX + tid];
+        d = (R[k * RSTR + tid] * scale) * iv - d * iv;
+        R[k * RSTR + tid] = d;
+    }
+    Real p = d;                                       // p(NZ-1) = d'(NZ-1)
+    for (int k = NZ - 2; k >= 0; --k) {
+        p = R[k * RSTR + tid] - tinv[k * NX + tid] * p;
+        R[k * RSTR + tid] = p;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase: pressure correction  u -= d_x phi, w -= d_z phi  (phi = dtau * pNHS in R)
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+RBC_HD void phase_correct(int tid, const Consts<Real>& C, Real* p, const Real* R)
+{
+    const int i = tid % NX, s = tid / NX, im = wrapx(i - 1);
+    Real* pu = p + OFF_U;
+    Real* pw = p + OFF_W;
+    RBC_UNROLL
+    for (int r = 0; r < RS; ++r) {
+        const int k = s * RS + r;
+        const Real ph = R[k * RSTR + i];
+        pu[k * NX + i] -= (ph - R[k * RSTR + im]) * C.idx;
+        if (k >= 1) pw[k * NX + i] -= (ph - R[(k - 1) * RSTR + i]) * C.idz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the Poisson projection of the state `p` (FFT-x, tridiagonal-z, SURVEY 8a "Poisson solver")
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+RBC_HD void project(const Consts<Real>& C, const Ctx<Real>& X, Real* p, Real scale)
+{
+    RBC_PHASE(phase_div(tid, C, p, X.R);)
+    RBC_PHASE(fft_passA_fwd(tid, X.R, X.tw48);)
+    RBC_PHASE(for (int it = tid; it < NZ * 8; it += NT) fft_passB_fwd(it, X.R);)
+    RBC_PHASE(for (int it = tid; it < NZ * 25; it += NT) fft_untangle(it, X.R, X.tw96);)
+    RBC_PHASE(phase_thomas(tid, X.R, X.tinv, scale);)
+    RBC_PHASE(for (int it = tid; it < NZ * 25; it += NT) fft_tangle(it, X.R, X.tw96);)
+    RBC_PHASE(for (int it = tid; it < NZ * 8; it += NT) fft_passB_inv(it, X.R, X.tw48);)
+    RBC_PHASE(fft_passA_inv(tid, X.R);)
+    RBC_PHASE(phase_correct(tid, C, p, X.R);)
+}
+
+// ------------------------------------------------------------------------------------------
+// epilogue pieces
+// ------------------------------------------------------------------------------------------
+// per-thread partial sums for Nusselt numbers and the NaN flag (get_nusselt, rbc_sim2D_api.jl:142-163)
+//   red[0] sum b*w (state)           red[1] sum b*w on the sensor grid
+//   red[2],red[3] sum_x b on rows (0,1) [strip 0] or (NZ-2,NZ-1) [strip 3]
+//   red[4],red[5] same for rows (NZ-2, NZ-1); sensor-row sums: phase_reduce_obs_partials
+//   red[6] NaN count
+template <typename Real>
+RBC_HD void phase_reduce_partials(int tid, const Consts<Real>& C, const Real* p, double* red)
+{
+    const int i = tid % NX, s = tid / NX;
+    const int oz = NZ / C.obs_nz, ox = NX / C.obs_nx;
+    const bool xs = (i % ox) == 0;
+    double q1 = 0, q1o = 0, ta = 0, tb = 0, bad = 0;
+    for (int r = 0; r < RS; ++r) {
+        const int k = s * RS + r;
+        const double b = (double)p[OFF_B + k * NX + i], u = (double)p[OFF_U + k * NX + i], w = (double)p[OFF_W + k * NX + i];
+        if (b != b || u != u || w != w) bad += 1;
+        q1 += b * w;
+        const bool zs = (k % oz) == 0;
+        if (zs && xs) q1o += b * w;
+        if (k == 0 || k == NZ - 2) ta += b;
+        if (k == 1 || k == NZ - 1) tb += b;
+    }
+    // rows 0/1 and NZ-2/NZ-1 (and the sensor rows) live in different strips; tag by strip half
+    const bool lower = (s * RS < NZ / 2);
+    red[0 * NT + tid] = q1;
+    red[1 * NT + tid] = q1o;
+    red[2 * NT + tid] = lower ? ta : 0;   red[3 * NT + tid] = lower ? tb : 0;
+    red[4 * NT + tid] = lower ? 0 : ta;   red[5 * NT + tid] = lower ? 0 : tb;
+    red[6 * NT + tid] = bad;
+}
+template <typename Real>
+RBC_HD void phase_reduce_obs_partials(int tid, const Consts<Real>& C, const Real* p, double* red)
+{
+    // sums over sensor columns of b on sensor rows 0, 1, nzo-2, nzo-1 -> red[0..3][tid]
+    const int i = tid % NX, s = tid / NX;
+    const int oz = NZ / C.obs_nz, ox = NX / C.obs_nx;
+    double v[4] = {0, 0, 0, 0};
+    if ((i % ox) == 0) {
+        const int rows[4] = {0, oz, (C.obs_nz - 2) * oz, (C.obs_nz - 1) * oz};
+        for (int q = 0; q < 4; ++q)
+            if (rows[q] / RS == s) v[q] += (double)p[OFF_B + rows[q] * NX + i];
+    }
+    for (int q = 0; q < 4; ++q) red[q * NT + tid] = v[q];
+}
+RBC_HD double sum_serial(const double* a, int n)
+{
+    double s = 0;
+    for (int q = 0; q < n; ++q) s += a[q];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// one action step of one environment (the whole of step_simulation + observation + reward)
+// ------------------------------------------------------------------------------------------
+template <typename Real, bool SPLIT, bool NXT_GLOBAL>
+RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const EnvIO<Real>& io, const Ctx<Real>& X, int env,
+                            const RunFlags& F)
+{
+    const Real gam[3] = {Real(8.0 / 15.0), Real(5.0 / 12.0), Real(3.0 / 4.0)};
+    const Real zet[3] = {Real(0), Real(-17.0 / 60.0), Real(-5.0 / 12.0)};
+    Real* st = io.state + (size_t)env * NSTATE;
+
+    // load the environment, evaluate the heater profile for this action
+    RBC_PHASE(
+        for (int q = tid; q < NSTATE; q += NT) X.s0[q] = st[q];
+        if (tid < NX) X.Tb[tid] = (Real)heater_T(C, io.actions + (size_t)env * C.heaters, (tid + 0.5) * C.dx);
+    )
+    Real* cur = X.s0;
+    Real* nxt = X.s1;
+    Real last_dtau = Real(1);
+    if (F.project_first) project(C, X, cur, T.thomas_scale);
+    for (int sub = 0; sub < F.nsub; ++sub) {
+        const Real dt = (sub == F.nsub - 1) ? C.dt_last : C.dt_full;
+        for (int stage = 0; stage < 3; ++stage) {
+            if (SPLIT) { RBC_PHASE(phase_phy(tid, C, cur + OFF_B, X.R);) }
+            RBC_PHASE((phase_tendency<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, X.gm, dt, gam[stage], zet[stage], stage > 0));)
+            Real* P;
+            if (NXT_GLOBAL) {
+                RBC_PHASE(phase_copy(tid, nxt, cur, NSTATE);)
+                P = cur;
+            } else {
+                P = nxt; nxt = cur; cur = P;
+            }
+            project(C, X, P, T.thomas_scale);
+            last_dtau = (gam[stage] + zet[stage]) * dt;
+        }
+    }
+
+    // ---- epilogue: NaN check, observation, Nusselt numbers, reward, bookkeeping ----
+    const int oz = NZ / C.obs_nz, ox = NX / C.obs_nx, nobs = C.obs_nz * C.obs_nx;
+    double nu_s = 0, nu_o = 0;
+    RBC_PHASE(phase_reduce_partials(tid, C, cur, X.red);)
+#if defined(__CUDA_ARCH__)
+    __shared__ double fin[12];
+#else
+    double fin[12];
+#endif
+    RBC_PHASE(if (tid < NRED) fin[tid] = sum_serial(X.red + tid * NT, NT);)
+    RBC_PHASE(phase_reduce_obs_partials(tid, C, cur, X.red);)
+    RBC_PHASE(if (tid < 4) fin[NRED + tid] = sum_serial(X.red + tid * NT, NT);)
+    {
+        const double kap = C.kappa_d, dbH = kap * 1.0 / 2.0;    // kappa * db / H, db = 1, H = 2
+        const double q1 = fin[0] / (double)NCELL, q1o = fin[1] / (double)nobs;
+        const double T0 = fin[2] / NX, T1 = fin[3] / NX, Tm2 = fin[4] / NX, Tm1 = fin[5] / NX;
+        const double g = (1.5 * Tm1 - 0.5 * Tm2 + 0.5 * T1 - 1.5 * T0) / NZ;
+        nu_s = (q1 - kap * g) / dbH;
+        const double o0 = fin[7] / C.obs_nx, o1 = fin[8] / C.obs_nx, om2 = fin[9] / C.obs_nx, om1 = fin[10] / C.obs_nx;
+        const double go = (1.5 * om1 - 0.5 * om2 + 0.5 * o1 - 1.5 * o0) / C.obs_nz;
+        nu_o = (q1o - kap * go) / dbH;
+    }
+    RBC_PHASE(
+        // store the state back and emit the observation (strided sub-sample, channel-major)
+        for (int q = tid; q < NSTATE; q += NT) st[q] = cur[q];
+        float* ob = io.obs + (size_t)env * C.channels * nobs;
+        for (int q = tid; q < 3 * nobs; q += NT) {
+            const int ch = q / nobs, zo = (q % nobs) / C.obs_nx, xo = q % C.obs_nx;
+            const int off = (ch == 0 ? OFF_B : (ch == 1 ? OFF_U : OFF_W));
+            ob[q] = (float)cur[off + (zo * oz) * NX + xo * ox];
+        }
+        if (tid == 0) {
+            io.nu_state[env] = nu_s;
+            io.nu_obs[env] = nu_o;
+            io.reward[env] = (float)(-nu_o);
+            io.nan_flag[env] = fin[6] > 0 ? 1 : 0;
+            if (F.advance_clock) {
+                const double tn = io.t[env] + C.dt_action;
+                io.t[env] = tn;
+                io.step_count[env] += 1;
+                io.truncated[env] = tn >= C.episode_length ? 1 : 0;
+            }
+        }
+    )
+    if (io.pressure != nullptr && (F.nsub > 0 || F.project_first)) {
+        // pressure channels of get_state (rbc_sim2D_api.jl:114-115): pHY' from the final b (as the
+        // last update_state! leaves it) and pNHS = phi / dtau of the last stage, zero-mean gauge.
+        Real* pr = io.pressure + (size_t)env * 2 * NCELL;
+        RBC_PHASE(
+            double acc = 0;
+            for (int q = tid; q < NCELL; q += NT) acc += (double)X.R[(q / NX) * RSTR + (q % NX)];
+            X.red[tid] = acc;
+        )
+        RBC_PHASE(if (tid == 0) fin[11] = sum_serial(X.red, NT) / (double)NCELL;)
+        RBC_PHASE(
+            for (int q = tid; q < NCELL; q += NT)
+                pr[NCELL + q] = (Real)(((double)X.R[(q / NX) * RSTR + (q % NX)] - fin[11]) / (double)last_dtau);
+        )
+        RBC_PHASE(phase_phy(tid, C, cur + OFF_B, X.R);)
+        RBC_PHASE(for (int q = tid; q < NCELL; q += NT) pr[q] = X.R[(q / NX) * RSTR + (q % NX)];)
+        if (C.channels == 5) {
+            RBC_PHASE(
+                float* ob = io.obs + (size_t)env * C.channels * nobs;
+                for (int q = tid; q < 2 * nobs; q += NT) {
+                    const int ch = q / nobs, zo = (q % nobs) / C.obs_nx, xo = q % C.obs_nx;
+                    ob[3 * nobs + q] = (float)pr[ch * NCELL + (zo * oz) * NX + xo * ox];
+                }
+            )
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side table construction (fp64), shared by the library and the emulator
+// ------------------------------------------------------------------------------------------
+// run!'s substep schedule dt' = min(dt_solver, stop - t) from t = 0 (SURVEY 8a "run! semantics"):
+// (nsub-1) full steps + one clipped step; remainders below 1e-10 are dropped.
+inline int substep_schedule(double dt_action, double dt_solver, double* dt_last)
+{
+    int n = 0;
+    double t = 0.0, last = dt_solver;
+    while (dt_action - t > 1e-10) {
+        const double d = (dt_solver < dt_action - t) ? dt_solver : dt_action - t;
+        last = d; t += d; ++n;
+    }
+    *dt_last = last;
+    return n;
+}
+struct HostConfig {
+    double ra, pr, lx, lz, b_top, heater_limit, dt_action, dt_solver, episode_length;
+    int heaters, obs_nz, obs_nx, channels;
+};
+template <typename Real>
+inline Consts<Real> make_consts(const HostConfig& h)
+{
+    Consts<Real> C;
+    const double dx = h.lx / NX, dz = h.lz / NZ;
+    const double nu = sqrt(h.pr / h.ra), kappa = 1.0 / sqrt(h.pr * h.ra);   // rbc_sim2D_api.jl:40-41
+    C.idx = (Real)(1.0 / dx); C.idz = (Real)(1.0 / dz);
+    C.idx2 = (Real)(1.0 / (dx * dx)); C.idz2 = (Real)(1.0 / (dz * dz));
+    C.nu = (Real)nu; C.kappa = (Real)kappa; C.b_top = (Real)h.b_top;
+    double last;
+    C.nsub = substep_schedule(h.dt_action, h.dt_solver, &last);
+    C.dt_full = (Real)h.dt_solver; C.dt_last = (Real)last;
+    C.heaters = h.heaters; C.heater_limit = h.heater_limit; C.lx = h.lx; C.dx = dx;
+    C.kappa_d = kappa; C.dt_action = h.dt_action; C.episode_length = h.episode_length;
+    C.obs_nz = h.obs_nz; C.obs_nx = h.obs_nx; C.channels = h.channels;
+    return C;
+}
+// mode index of spectral word t of a row after fft_untangle
+inline int word_mode(int t)
+{
+    const int p = t / 2;
+    if (p == 0) return (t == 0) ? 0 : NX / 2;
+    return 8 * (p % 6) + p / 6;
+}
+inline void build_tables_host(double lx, double lz, double* tinv /*NZ*NX*/, double* tw48 /*96*/, double* tw96 /*50*/)
+{
+    const double PI = 3.14159265358979323846;
+    const double dx = lx / NX, dz = lz / NZ;
+    for (int t = 0; t < NX; ++t) {
+        const int m = word_mode(t);
+        const double sx = 2.0 * sin(PI * m / NX) / dx, lam = sx * sx * dz * dz;
+        double prev = 0.0;
+        for (int k = 0; k < NZ; ++k) {
+            double diag = -(2.0 + lam);
+            if (k == 0 || k == NZ - 1) diag += 1.0;
+            if (m == 0 && k == 0) diag -= 1.0;          // pin the null space of the mean mode
+            const double iv = 1.0 / (diag - prev);
+            tinv[k * NX + t] = iv;
+            prev = iv;
+        }
+    }
+    for (int j = 0; j < 48; ++j) { tw48[2 * j] = cos(2 * PI * j / 48); tw48[2 * j + 1] = sin(2 * PI * j / 48); }
+    for (int m = 0; m < 25; ++m) { tw96[2 * m] = cos(2 * PI * m / 96); tw96[2 * m + 1] = sin(2 * PI * m / 96); }
+}
+
+}  // namespace rbc2d

@@ -1,0 +1,507 @@
+// rbc2d_lib.cu — sm_100a kernels + the C ABI declared in include/rbc_b200.h.
+//
+// One persistent CTA per SM; each CTA owns one environment at a time and keeps it in shared
+// memory for the whole action step (rbc2d_core.h).  Environments are independent, so the grid
+// simply strides over the batch.  No CPU fallback exists: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rbc_b200.h"
+#include "rbc2d_core.h"
+
+using namespace rbc2d;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                        \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+struct SmemLayout {
+    static constexpr bool kNxtGlobal = sizeof(Real) == 8;     // fp64: predicted state lives in global memory
+    static constexpr size_t s0 = 0;
+    static constexpr size_t s1 = s0 + sizeof(Real) * NSTATE;
+    static constexpr size_t R = kNxtGlobal ? s1 : s1 + sizeof(Real) * NSTATE;
+    static constexpr size_t red = R + sizeof(Real) * NR;
+    static constexpr size_t Tb = red + sizeof(double) * NRED * NT;
+    static constexpr size_t tw48 = Tb + sizeof(Real) * NX;
+    static constexpr size_t tw96 = tw48 + sizeof(Real) * 96;
+    static constexpr size_t total = tw96 + sizeof(Real) * 50;
+};
+
+template <typename Real, bool SPLIT>
+__global__ void __launch_bounds__(NT, 1)
+rbc2d_env_kernel(Consts<Real> C, Tables<Real> T, EnvIO<Real> io, Real* gm_all, Real* nxt_all, const int* env_ids, int n,
+                 RunFlags F)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    using L = SmemLayout<Real>;
+    Ctx<Real> X;
+    X.s0 = reinterpret_cast<Real*>(smem + L::s0);
+    X.s1 = L::kNxtGlobal ? nxt_all + (size_t)blockIdx.x * NSTATE : reinterpret_cast<Real*>(smem + L::s1);
+    X.R = reinterpret_cast<Real*>(smem + L::R);
+    X.red = reinterpret_cast<double*>(smem + L::red);
+    X.Tb = reinterpret_cast<Real*>(smem + L::Tb);
+    X.tw48 = reinterpret_cast<Real*>(smem + L::tw48);
+    X.tw96 = reinterpret_cast<Real*>(smem + L::tw96);
+    X.gm = gm_all + (size_t)blockIdx.x * NSTATE;
+    X.tinv = T.tinv;
+    for (int q = threadIdx.x; q < 96; q += NT) X.tw48[q] = T.tw48[q];
+    for (int q = threadIdx.x; q < 50; q += NT) X.tw96[q] = T.tw96[q];
+    __syncthreads();
+    for (int j = blockIdx.x; j < n; j += gridDim.x) {
+        const int env = env_ids ? env_ids[j] : j;
+        env_action_step<Real, SPLIT, L::kNxtGlobal>(C, T, io, X, env, F);
+    }
+}
+
+// state[env_ids[j]] <- bank[ckpt_idx[j]] (fp64 -> Real); clock reset (initialize_simulation, rbc_sim2D_api.jl:66-68)
+template <typename Real>
+__global__ void rbc2d_reset_kernel(Real* state, const double* bank, const int* env_ids, const int* ckpt_idx, int n, int n_ep,
+                                   double* t, int* step, int* trunc, int* nan)
+{
+    for (int j = blockIdx.y; j < n; j += gridDim.y) {
+        const int env = env_ids ? env_ids[j] : j;
+        int ep = ckpt_idx[j];
+        ep = ep < 0 ? 0 : (ep >= n_ep ? n_ep - 1 : ep);
+        const double* src = bank + (size_t)ep * NSTATE;
+        Real* dst = state + (size_t)env * NSTATE;
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < NSTATE; q += gridDim.x * blockDim.x) dst[q] = (Real)src[q];
+        if (blockIdx.x == 0 && threadIdx.x == 0) { t[env] = 0.0; step[env] = 1; trunc[env] = 0; nan[env] = 0; }
+    }
+}
+
+template <typename Real>
+__global__ void rbc2d_set_fields_kernel(Real* state, const double* fields, const int* env_ids, int n, double* t, int* step,
+                                        int* trunc, int* nan)
+{
+    for (int j = blockIdx.y; j < n; j += gridDim.y) {
+        const int env = env_ids ? env_ids[j] : j;
+        const double* src = fields + (size_t)j * NSTATE;
+        Real* dst = state + (size_t)env * NSTATE;
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < NSTATE; q += gridDim.x * blockDim.x) dst[q] = (Real)src[q];
+        if (blockIdx.x == 0 && threadIdx.x == 0) { t[env] = 0.0; step[env] = 1; trunc[env] = 0; nan[env] = 0; }
+    }
+}
+
+// get_state (rbc_sim2D_api.jl:102-118 + rbc2D.py:184-189): [B][C][NZ][NX] float32; w channel = faces 0..NZ-1
+template <typename Real>
+__global__ void rbc2d_get_state_kernel(const Real* state, const Real* pressure, float* out, int B, int channels)
+{
+    const size_t per = (size_t)channels * NCELL, total = per * B;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int env = (int)(q / per), r = (int)(q % per), ch = r / NCELL, c = r % NCELL;
+        float v;
+        if (ch < 3) v = (float)state[(size_t)env * NSTATE + (ch == 0 ? OFF_B : (ch == 1 ? OFF_U : OFF_W)) + c];
+        else v = pressure ? (float)pressure[(size_t)env * 2 * NCELL + (size_t)(ch - 3) * NCELL + c] : 0.0f;
+        out[q] = v;
+    }
+}
+
+template <typename Real>
+__global__ void rbc2d_get_fields_kernel(const Real* state, double* out, size_t total)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x)
+        out[q] = (double)state[q];
+}
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct rbc2d_sim {
+    rbc2d_config cfg;
+    HostConfig hc;
+    int B = 0, channels = 3, grid = 0, n_ep = 0;
+    size_t smem = 0, real_size = 4;
+    cudaStream_t stream = nullptr;
+    void *state = nullptr, *gm = nullptr, *nxt = nullptr, *pressure = nullptr;
+    void *tinv = nullptr, *tw48 = nullptr, *tw96 = nullptr;
+    double* bank = nullptr;
+    double *t = nullptr, *nu_s = nullptr, *nu_o = nullptr;
+    int *step = nullptr, *trunc = nullptr, *nan = nullptr;
+    float *obs = nullptr, *reward = nullptr, *actions = nullptr;
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+template <typename Real>
+static int upload_tables(rbc2d_sim* s)
+{
+    std::vector<double> tinv(NZ * NX), tw48(96), tw96(50);
+    build_tables_host(s->hc.lx, s->hc.lz, tinv.data(), tw48.data(), tw96.data());
+    std::vector<Real> a(tinv.begin(), tinv.end()), b(tw48.begin(), tw48.end()), c(tw96.begin(), tw96.end());
+    CK(cudaMalloc(&s->tinv, a.size() * sizeof(Real)));
+    CK(cudaMalloc(&s->tw48, b.size() * sizeof(Real)));
+    CK(cudaMalloc(&s->tw96, c.size() * sizeof(Real)));
+    CK(cudaMemcpy(s->tinv, a.data(), a.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->tw48, b.data(), b.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->tw96, c.data(), c.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+template <typename Real, bool SPLIT>
+static int prepare_kernel(rbc2d_sim* s)
+{
+    auto k = rbc2d_env_kernel<Real, SPLIT>;
+    s->smem = SmemLayout<Real>::total;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    int per_sm = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, s->smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->cfg.device));
+    if (per_sm < 1) return fail("step kernel does not fit on an SM");
+    s->grid = per_sm * sms;
+    return 0;
+}
+
+template <typename Real, bool SPLIT>
+static int launch_env(rbc2d_sim* s, const float* actions, float* obs, float* reward, double* nu_s, double* nu_o, int* trunc,
+                      int* nan, const int* env_ids, int n, RunFlags F, bool time_it)
+{
+    Consts<Real> C = make_consts<Real>(s->hc);
+    Tables<Real> T{(const Real*)s->tinv, (const Real*)s->tw48, (const Real*)s->tw96,
+                   (Real)((s->hc.lz / NZ) * (s->hc.lz / NZ) / 48.0)};
+    EnvIO<Real> io;
+    io.state = (Real*)s->state;
+    io.actions = actions ? actions : s->actions;
+    io.obs = obs ? obs : s->obs;
+    io.reward = reward ? reward : s->reward;
+    io.nu_state = nu_s ? nu_s : s->nu_s;
+    io.nu_obs = nu_o ? nu_o : s->nu_o;
+    io.t = s->t;
+    io.step_count = s->step;
+    io.truncated = trunc ? trunc : s->trunc;
+    io.nan_flag = nan ? nan : s->nan;
+    io.pressure = (Real*)s->pressure;
+    const int grid = n < s->grid ? n : s->grid;
+    if (grid <= 0) return 0;
+    if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
+    rbc2d_env_kernel<Real, SPLIT><<<grid, NT, s->smem, s->stream>>>(C, T, io, (Real*)s->gm, (Real*)s->nxt, env_ids, n, F);
+    CK(cudaGetLastError());
+    if (time_it) { CK(cudaEventRecord(s->ev1, s->stream)); s->timed = true; }
+    s->launches += 1;
+    return 0;
+}
+
+static int dispatch_env(rbc2d_sim* s, const float* actions, float* obs, float* reward, double* nu_s, double* nu_o, int* trunc,
+                        int* nan, const int* env_ids, int n, RunFlags F, bool time_it)
+{
+    const bool f32 = s->cfg.precision == 32, split = s->cfg.pressure != 0;
+    if (f32) return split ? launch_env<float, true>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it)
+                          : launch_env<float, false>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it);
+    return split ? launch_env<double, true>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it)
+                 : launch_env<double, false>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it);
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int rbc_abi_version(void) { return RBC_B200_ABI_VERSION; }
+const char* rbc_last_error(void) { return g_err.c_str(); }
+
+int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
+{
+    if (!cfg || !out) return fail("rbc2d_create: null argument");
+    *out = nullptr;
+    if (cfg->nx != NX || cfg->nz != NZ) return fail("rbc2d_create: this build supports a 96 x 64 grid only");
+    if (cfg->num_envs < 1) return fail("rbc2d_create: num_envs must be >= 1");
+    if (cfg->precision != 32 && cfg->precision != 64) return fail("rbc2d_create: precision must be 32 or 64");
+    if (cfg->heaters < 1 || cfg->heaters > MAX_HEATERS) return fail("rbc2d_create: heaters must be in 1..32");
+    if (cfg->obs_nx < 1 || cfg->obs_nz < 2 || NX % cfg->obs_nx || NZ % cfg->obs_nz)
+        return fail("rbc2d_create: sensors must divide the grid (and obs_nz >= 2)");
+    if (!(cfg->ra > 0) || !(cfg->pr > 0) || !(cfg->dt_action > 0) || !(cfg->dt_solver > 0))
+        return fail("rbc2d_create: ra, pr, dt_action, dt_solver must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail("rbc2d_create: no CUDA device available (this backend has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("rbc2d_create: bad device ordinal");
+    CK(cudaSetDevice(cfg->device));
+
+    rbc2d_sim* s = new rbc2d_sim();
+    s->cfg = *cfg;
+    s->B = cfg->num_envs;
+    s->channels = cfg->pressure ? 5 : 3;
+    s->real_size = cfg->precision == 32 ? 4 : 8;
+    s->hc = HostConfig{cfg->ra, cfg->pr, 2.0 * 3.14159265358979323846, 2.0, 1.0, cfg->heater_limit, cfg->dt_action,
+                       cfg->dt_solver, cfg->episode_length, cfg->heaters, cfg->obs_nz, cfg->obs_nx, s->channels};
+    int rc;
+    const bool f32 = cfg->precision == 32, split = cfg->pressure != 0;
+    rc = f32 ? upload_tables<float>(s) : upload_tables<double>(s);
+    if (rc) { rbc2d_destroy(s); return rc; }
+    if (f32) rc = split ? prepare_kernel<float, true>(s) : prepare_kernel<float, false>(s);
+    else rc = split ? prepare_kernel<double, true>(s) : prepare_kernel<double, false>(s);
+    if (rc) { rbc2d_destroy(s); return rc; }
+
+    const size_t B = s->B, rs = s->real_size;
+    const size_t nobs = (size_t)s->channels * cfg->obs_nz * cfg->obs_nx;
+#define ALLOC(ptr, bytes)                                                         \
+    do {                                                                          \
+        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                     \
+        if (e_ != cudaSuccess) {                                                  \
+            std::string m = std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_); \
+            rbc2d_destroy(s);                                                     \
+            return fail(m);                                                       \
+        }                                                                         \
+        cudaMemset((ptr), 0, (bytes));                                            \
+    } while (0)
+    ALLOC(s->state, B * NSTATE * rs);
+    ALLOC(s->gm, (size_t)s->grid * NSTATE * rs);
+    if (!f32) ALLOC(s->nxt, (size_t)s->grid * NSTATE * rs);
+    if (split) ALLOC(s->pressure, B * 2 * NCELL * rs);
+    ALLOC(s->t, B * sizeof(double));
+    ALLOC(s->nu_s, B * sizeof(double));
+    ALLOC(s->nu_o, B * sizeof(double));
+    ALLOC(s->step, B * sizeof(int));
+    ALLOC(s->trunc, B * sizeof(int));
+    ALLOC(s->nan, B * sizeof(int));
+    ALLOC(s->obs, B * nobs * sizeof(float));
+    ALLOC(s->reward, B * sizeof(float));
+    ALLOC(s->actions, B * (size_t)cfg->heaters * sizeof(float));
+#undef ALLOC
+    if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
+        rbc2d_destroy(s);
+        return fail("cudaEventCreate failed");
+    }
+    *out = s;
+    return 0;
+}
+
+int rbc2d_destroy(rbc2d_sim* s)
+{
+    if (!s) return 0;
+    cudaSetDevice(s->cfg.device);
+    void* ptrs[] = {s->state, s->gm, s->nxt, s->pressure, s->tinv, s->tw48, s->tw96, s->bank, s->t, s->nu_s, s->nu_o,
+                    s->step, s->trunc, s->nan, s->obs, s->reward, s->actions};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+    return 0;
+}
+
+int rbc2d_set_stream(rbc2d_sim* s, void* stream)
+{
+    if (!s) return fail("null handle");
+    s->stream = (cudaStream_t)stream;
+    return 0;
+}
+int rbc2d_num_envs(const rbc2d_sim* s) { return s ? s->B : -1; }
+int rbc2d_state_values_per_env(const rbc2d_sim* s) { return s ? NSTATE : -1; }
+
+int rbc2d_load_checkpoints(rbc2d_sim* s, const double* b, const double* u, const double* w, int32_t n_ep)
+{
+    if (!s || !b || !u || !w || n_ep < 1) return fail("rbc2d_load_checkpoints: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    if (s->bank) { cudaFree(s->bank); s->bank = nullptr; }
+    CK(cudaMalloc((void**)&s->bank, (size_t)n_ep * NSTATE * sizeof(double)));
+    for (int e = 0; e < n_ep; ++e) {
+        double* d = s->bank + (size_t)e * NSTATE;
+        CK(cudaMemcpyAsync(d + OFF_B, b + (size_t)e * NCELL, NCELL * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(d + OFF_U, u + (size_t)e * NCELL, NCELL * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(d + OFF_W, w + (size_t)e * NWF, NWF * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    s->n_ep = n_ep;
+    return 0;
+}
+
+int rbc2d_reset_from_checkpoints_dev(rbc2d_sim* s, const int32_t* env_ids, const int32_t* ckpt_idx, int32_t n)
+{
+    if (!s || !ckpt_idx) return fail("rbc2d_reset_from_checkpoints_dev: bad argument");
+    if (!s->bank) return fail("rbc2d_reset_from_checkpoints_dev: no checkpoint bank loaded");
+    CK(cudaSetDevice(s->cfg.device));
+    if (!env_ids) n = s->B;
+    if (n <= 0) return 0;
+    dim3 grid(8, n < 4096 ? n : 4096);
+    if (s->cfg.precision == 32)
+        rbc2d_reset_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, s->bank, env_ids, ckpt_idx, n, s->n_ep, s->t, s->step, s->trunc, s->nan);
+    else
+        rbc2d_reset_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, s->bank, env_ids, ckpt_idx, n, s->n_ep, s->t, s->step, s->trunc, s->nan);
+    CK(cudaGetLastError());
+    s->launches += 1;
+    if (s->cfg.pressure) {   // set! projects and leaves pNHS; pHY' follows from b
+        RunFlags F{0, 1, 0};
+        return dispatch_env(s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, env_ids, n, F, false);
+    }
+    return 0;
+}
+
+int rbc2d_reset_from_fields_host(rbc2d_sim* s, const int32_t* env_ids_host, const double* fields, int32_t n, int32_t project)
+{
+    if (!s || !fields || n < 1 || n > s->B) return fail("rbc2d_reset_from_fields_host: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    double* dfields = nullptr;
+    int* dids = nullptr;
+    CK(cudaMalloc((void**)&dfields, (size_t)n * NSTATE * sizeof(double)));
+    CK(cudaMemcpyAsync(dfields, fields, (size_t)n * NSTATE * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (env_ids_host) {
+        CK(cudaMalloc((void**)&dids, n * sizeof(int)));
+        CK(cudaMemcpyAsync(dids, env_ids_host, n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    }
+    dim3 grid(8, n < 4096 ? n : 4096);
+    if (s->cfg.precision == 32)
+        rbc2d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, dfields, dids, n, s->t, s->step, s->trunc, s->nan);
+    else
+        rbc2d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, dfields, dids, n, s->t, s->step, s->trunc, s->nan);
+    CK(cudaGetLastError());
+    s->launches += 1;
+    int rc = 0;
+    if (project || s->cfg.pressure) {
+        RunFlags F{0, 1, 0};
+        rc = dispatch_env(s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dids, n, F, false);
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(dfields);
+    if (dids) cudaFree(dids);
+    return rc;
+}
+
+int rbc2d_step_dev(rbc2d_sim* s, const float* actions, float* obs, float* reward, double* nu_s, double* nu_o, int32_t* trunc,
+                   int32_t* nan)
+{
+    if (!s || !actions) return fail("rbc2d_step_dev: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    Consts<float> tmp = make_consts<float>(s->hc);
+    RunFlags F{tmp.nsub, 0, 1};
+    return dispatch_env(s, actions, obs, reward, nu_s, nu_o, trunc, nan, nullptr, s->B, F, true);
+}
+
+int rbc2d_step_host(rbc2d_sim* s, const float* actions, float* obs, float* reward, double* nu_s, double* nu_o, int32_t* trunc,
+                    int32_t* nan)
+{
+    if (!s || !actions) return fail("rbc2d_step_host: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    const size_t B = s->B;
+    const size_t nobs = (size_t)s->channels * s->cfg.obs_nz * s->cfg.obs_nx;
+    CK(cudaMemcpyAsync(s->actions, actions, B * s->cfg.heaters * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    int rc = rbc2d_step_dev(s, s->actions, s->obs, s->reward, s->nu_s, s->nu_o, s->trunc, s->nan);
+    if (rc) return rc;
+    if (obs) CK(cudaMemcpyAsync(obs, s->obs, B * nobs * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (reward) CK(cudaMemcpyAsync(reward, s->reward, B * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (nu_s) CK(cudaMemcpyAsync(nu_s, s->nu_s, B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (nu_o) CK(cudaMemcpyAsync(nu_o, s->nu_o, B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (trunc) CK(cudaMemcpyAsync(trunc, s->trunc, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (nan) CK(cudaMemcpyAsync(nan, s->nan, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int rbc2d_observe_dev(rbc2d_sim* s, float* obs, double* nu_s, double* nu_o)
+{
+    if (!s) return fail("null handle");
+    CK(cudaSetDevice(s->cfg.device));
+    RunFlags F{0, 0, 0};
+    // truncated / nan flags of the handle are left untouched: write them to scratch copies
+    return dispatch_env(s, nullptr, obs, nullptr, nu_s, nu_o, nullptr, nullptr, nullptr, s->B, F, false);
+}
+
+int rbc2d_observe_host(rbc2d_sim* s, float* obs, double* nu_s, double* nu_o)
+{
+    if (!s) return fail("null handle");
+    int rc = rbc2d_observe_dev(s, s->obs, s->nu_s, s->nu_o);
+    if (rc) return rc;
+    const size_t B = s->B, nobs = (size_t)s->channels * s->cfg.obs_nz * s->cfg.obs_nx;
+    if (obs) CK(cudaMemcpyAsync(obs, s->obs, B * nobs * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (nu_s) CK(cudaMemcpyAsync(nu_s, s->nu_s, B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (nu_o) CK(cudaMemcpyAsync(nu_o, s->nu_o, B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int rbc2d_get_state_dev(rbc2d_sim* s, float* out, int32_t channels)
+{
+    if (!s || !out) return fail("rbc2d_get_state_dev: bad argument");
+    if (channels != 3 && channels != 5) return fail("rbc2d_get_state_dev: channels must be 3 or 5");
+    if (channels == 5 && !s->pressure) return fail("rbc2d_get_state_dev: pressure channels need pressure=1 at creation");
+    CK(cudaSetDevice(s->cfg.device));
+    const int blocks = 148 * 8;
+    if (s->cfg.precision == 32)
+        rbc2d_get_state_kernel<float><<<blocks, 256, 0, s->stream>>>((const float*)s->state, (const float*)s->pressure, out, s->B, channels);
+    else
+        rbc2d_get_state_kernel<double><<<blocks, 256, 0, s->stream>>>((const double*)s->state, (const double*)s->pressure, out, s->B, channels);
+    CK(cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
+int rbc2d_get_state_host(rbc2d_sim* s, float* out, int32_t channels)
+{
+    if (!s || !out) return fail("rbc2d_get_state_host: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    float* tmp = nullptr;
+    const size_t bytes = (size_t)s->B * channels * NCELL * sizeof(float);
+    CK(cudaMalloc((void**)&tmp, bytes));
+    int rc = rbc2d_get_state_dev(s, tmp, channels);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) rc = fail(std::string("rbc2d_get_state_host: ") + cudaGetErrorString(e));
+    }
+    cudaFree(tmp);
+    return rc;
+}
+
+int rbc2d_get_fields_host(rbc2d_sim* s, double* out)
+{
+    if (!s || !out) return fail("rbc2d_get_fields_host: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    const size_t total = (size_t)s->B * NSTATE;
+    double* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, total * sizeof(double)));
+    if (s->cfg.precision == 32) rbc2d_get_fields_kernel<float><<<148 * 8, 256, 0, s->stream>>>((const float*)s->state, tmp, total);
+    else rbc2d_get_fields_kernel<double><<<148 * 8, 256, 0, s->stream>>>((const double*)s->state, tmp, total);
+    s->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, total * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(std::string("rbc2d_get_fields_host: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int rbc2d_get_info_host(rbc2d_sim* s, double* t, int32_t* step)
+{
+    if (!s) return fail("null handle");
+    CK(cudaSetDevice(s->cfg.device));
+    if (t) CK(cudaMemcpyAsync(t, s->t, s->B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (step) CK(cudaMemcpyAsync(step, s->step, s->B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int rbc2d_launch_count(const rbc2d_sim* s, int64_t* launches, int32_t* grid, int32_t* smem_bytes)
+{
+    if (!s) return fail("null handle");
+    if (launches) *launches = s->launches;
+    if (grid) *grid = s->B < s->grid ? s->B : s->grid;
+    if (smem_bytes) *smem_bytes = (int32_t)s->smem;
+    return 0;
+}
+
+int rbc2d_last_step_kernel_ms(rbc2d_sim* s, float* ms)
+{
+    if (!s || !ms) return fail("rbc2d_last_step_kernel_ms: bad argument");
+    if (!s->timed) return fail("rbc2d_last_step_kernel_ms: no step has been launched");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaEventSynchronize(s->ev1));
+    CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+"""ctypes wrapper of the CPU emulator of the CUDA kernel core (test infrastructure)."""
+import ctypes as C
+import math
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_ROOT = _HERE.parent.parent
+_SO = _HERE / "libemu_rbc2d.so"
+
+
+class HostConfig(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("ra", "pr", "lx", "lz", "b_top", "heater_limit", "dt_action", "dt_solver", "episode_length")] + \
+               [(n, C.c_int) for n in ("heaters", "obs_nz", "obs_nx", "channels")]
+
+
+def build():
+    srcs = [_HERE / "emu_rbc2d.cpp", _ROOT / "rbc_gym_b200" / "csrc" / "rbc2d_core.h"]
+    if not _SO.exists() or _SO.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", str(_SO), str(srcs[0])], check=True)
+    return _SO
+
+
+def step(state, actions, ra, dt_action, precision=64, split=False, nxt_global=False, dt_solver=0.03,
+         obs=(8, 48), heaters=12, heater_limit=0.75, episode_length=300.0, pressure=False, t0=None):
+    """state: [B, 18528] (b,u,w flattened) in the given precision; returns dict."""
+    lib = C.CDLL(str(build()))
+    B = state.shape[0]
+    dt = np.float64 if precision == 64 else np.float32
+    st = np.array(state, dtype=dt, order="C")
+    ch = 5 if pressure else 3
+    h = HostConfig(ra, 0.7, 2 * math.pi, 2.0, 1.0, heater_limit, dt_action, dt_solver, episode_length, heaters, obs[0], obs[1], ch)
+    a = np.ascontiguousarray(actions, dtype=np.float32)
+    ob = np.zeros((B, ch, obs[0], obs[1]), np.float32)
+    rew = np.zeros(B, np.float32)
+    nus, nuo = np.zeros(B), np.zeros(B)
+    t = np.zeros(B) if t0 is None else np.array(t0, dtype=np.float64)
+    sc, tr, nf = np.ones(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    pr = np.zeros((B, 2, 64, 96), dt) if pressure else None
+    vp = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
+    rc = lib.emu_rbc2d_step(C.byref(h), precision, int(split), int(nxt_global), B, vp(st), vp(a), vp(ob), vp(rew), vp(nus), vp(nuo),
+                            vp(t), vp(sc), vp(tr), vp(nf), vp(pr))
+    assert rc == 0
+    return dict(state=st, obs=ob, reward=rew, nu_state=nus, nu_obs=nuo, t=t, step=sc, truncated=tr, nan=nf, pressure=pr)
+
+
+def pack(b, u, w):
+    return np.concatenate([b.reshape(b.shape[0], -1), u.reshape(u.shape[0], -1), w.reshape(w.shape[0], -1)], axis=1)
+
+
+def unpack(st):
+    B = st.shape[0]
+    return st[:, :6144].reshape(B, 64, 96), st[:, 6144:12288].reshape(B, 64, 96), st[:, 12288:].reshape(B, 65, 96)

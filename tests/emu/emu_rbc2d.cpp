@@ -1,0 +1,43 @@
+// Sequential "one CTA" emulator of rbc2d_core.h for machines without a GPU.
+// Test infrastructure: lets tests/ check the exact kernel logic (phases, FFT passes, Thomas,
+// epilogue reductions) against the fp64 oracle.  Not part of the product path.
+#include <vector>
+#include <cstring>
+#include "../../rbc_gym_b200/csrc/rbc2d_core.h"
+
+using namespace rbc2d;
+
+template <typename Real, bool SPLIT>
+static void run(const HostConfig& h, int B, Real* state, const float* actions, float* obs, float* reward,
+                double* nu_state, double* nu_obs, double* t, int* step_count, int* truncated, int* nan_flag,
+                Real* pressure, bool nxt_global)
+{
+    Consts<Real> C = make_consts<Real>(h);
+    std::vector<double> tinv_d(NZ * NX), tw48_d(96), tw96_d(50);
+    build_tables_host(h.lx, h.lz, tinv_d.data(), tw48_d.data(), tw96_d.data());
+    std::vector<Real> tinv(tinv_d.begin(), tinv_d.end()), tw48(tw48_d.begin(), tw48_d.end()), tw96(tw96_d.begin(), tw96_d.end());
+    Tables<Real> T{tinv.data(), tw48.data(), tw96.data(), (Real)((h.lz / NZ) * (h.lz / NZ) / 48.0)};
+    EnvIO<Real> io{state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, pressure};
+    std::vector<Real> s0(NSTATE), s1(NSTATE), R(NR), Tb(NX), gm(NSTATE);
+    std::vector<double> red(NRED * NT);
+    Ctx<Real> X{s0.data(), s1.data(), R.data(), Tb.data(), tw48.data(), tw96.data(), gm.data(), tinv.data(), red.data()};
+    RunFlags F{C.nsub, 0, 1};
+    for (int e = 0; e < B; ++e) {
+        if (nxt_global) env_action_step<Real, SPLIT, true>(C, T, io, X, e, F);
+        else env_action_step<Real, SPLIT, false>(C, T, io, X, e, F);
+    }
+}
+
+extern "C" int emu_rbc2d_step(const HostConfig* h, int precision, int split, int nxt_global, int B, void* state,
+                              const float* actions, float* obs, float* reward, double* nu_state, double* nu_obs, double* t,
+                              int* step_count, int* truncated, int* nan_flag, void* pressure)
+{
+    if (precision == 64) {
+        if (split) run<double, true>(*h, B, (double*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (double*)pressure, nxt_global);
+        else run<double, false>(*h, B, (double*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (double*)pressure, nxt_global);
+    } else if (precision == 32) {
+        if (split) run<float, true>(*h, B, (float*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (float*)pressure, nxt_global);
+        else run<float, false>(*h, B, (float*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (float*)pressure, nxt_global);
+    } else return -1;
+    return 0;
+}
