@@ -47,9 +47,16 @@ constexpr int NSTRIP = 4, RS = NZ / NSTRIP;      // 4 strips of 16 rows
 constexpr int NT = NX * NSTRIP;                  // 384 threads
 constexpr int NCELL = NX * NZ;                   // 6144
 constexpr int NWF = NX * (NZ + 1);               // 6240 (w incl. both wall faces)
-constexpr int NSTATE = 2 * NCELL + NWF;          // 18528 values per environment
-constexpr int OFF_B = 0, OFF_U = NCELL, OFF_W = 2 * NCELL;
-constexpr int RSTR = 108;                        // row stride (words) of the Poisson scratch
+constexpr int NSTATE = 2 * NCELL + NWF;          // 18528 values per environment (global / checkpoint layout)
+// On-chip rows are padded to SX = 98 words: with lanes mapped to consecutive ROWS (FFT passes) a 64-bit
+// access then walks the banks two at a time (98 = 3*32 + 2), and with lanes mapped to consecutive
+// COLUMNS (stencils, Thomas) any stride is conflict-free.
+constexpr int SX = 98;
+constexpr int NROWS = 3 * NZ + 1;                // 193 rows: b (64), u (64), w (65)
+constexpr int NS_SM = NROWS * SX;                // 18914 words per on-chip state buffer
+constexpr int OFF_B = 0, OFF_U = NZ * SX, OFF_W = 2 * NZ * SX;       // on-chip (padded) field offsets
+constexpr int GOFF_B = 0, GOFF_U = NCELL, GOFF_W = 2 * NCELL;         // global / checkpoint layout offsets
+constexpr int RSTR = SX;                         // row stride (words) of the Poisson scratch
 constexpr int NR = NZ * RSTR;                    // scratch size in words
 constexpr int NH = NX / 2;                       // 48 complex points per packed row
 constexpr int MAX_HEATERS = 32;
@@ -76,7 +83,7 @@ template <typename Real>
 struct Tables {
     const Real* tinv;   // [NZ][NX]  Thomas pivots per spectral word (see build_tables)
     const Real* tw48;   // [48][2]   cos/sin(2 pi j / 48)
-    const Real* tw96;   // [25][2]   cos/sin(2 pi m / 96)
+    const Real* tw96;   // [48][2]   cos/sin(2 pi m / 96)
     Real thomas_scale;  // dz^2 / 48
 };
 
@@ -99,15 +106,15 @@ struct EnvIO {
 // everything one CTA needs while it owns an environment
 template <typename Real>
 struct Ctx {
-    Real* s0;        // shared: state buffer 0 (NSTATE)
-    Real* s1;        // second state buffer: shared (fp32) or global (fp64)
+    Real* s0;        // shared: state buffer 0 (NS_SM, rows padded to SX)
+    Real* s1;        // second state buffer (NS_SM): shared (fp32) or global (fp64)
     Real* R;         // shared: Poisson scratch / pHY' (NR)
     Real* Tb;        // shared: bottom wall temperature per column (NX)
     Real* tw48;      // shared twiddles
     Real* tw96;
     Real* gm;        // global: previous-stage tendencies of this CTA (NSTATE)
-    const Real* tinv;
-    double* red;     // shared: NRED*NT doubles for the epilogue reductions (may alias R.. no: separate)
+    const Real* tinv; // Thomas pivots [NZ][NX]: shared copy (fp32) or the global table (fp64)
+    double* red;     // shared: NRED*NT doubles for the epilogue reductions (fp64 mode; fp32 aliases s0/s1)
 };
 
 // what one kernel launch does with each environment it visits
@@ -208,11 +215,11 @@ RBC_HD void phase_phy(int tid, const Consts<Real>& C, const Real* cb, Real* phy)
 {
     if (tid >= NX) return;
     const Real dz = Real(1) / C.idz;
-    Real below = cb[(NZ - 1) * NX + tid];
+    Real below = cb[(NZ - 1) * SX + tid];
     Real acc = -Real(0.5) * (below + (Real(2) * C.b_top - below)) * dz;
     phy[(NZ - 1) * RSTR + tid] = acc;
     for (int k = NZ - 2; k >= 0; --k) {
-        const Real bk = cb[k * NX + tid];
+        const Real bk = cb[k * SX + tid];
         acc = acc - Real(0.5) * (bk + below) * dz;
         phy[k * RSTR + tid] = acc;
         below = bk;
@@ -241,17 +248,17 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* c, Real* 
     for (int j = 0; j < 7; ++j) {
         const int k = k0 - 3 + j;
         const bool ok = (k >= 0 && k < NZ);
-        bz[j] = ok ? cb[k * NX + i] : Real(0);
-        uz[j] = ok ? cu[k * NX + i] : Real(0);
-        wz[j] = (k >= 0 && k <= NZ) ? cw[k * NX + i] : Real(0);
+        bz[j] = ok ? cb[k * SX + i] : Real(0);
+        uz[j] = ok ? cu[k * SX + i] : Real(0);
+        wz[j] = (k >= 0 && k <= NZ) ? cw[k * SX + i] : Real(0);
     }
     RBC_UNROLL
     for (int j = 0; j < 4; ++j) {                      // u(i+1, k-2 .. k+1)
         const int k = k0 - 2 + j;
-        u1z[j] = (k >= 0 && k < NZ) ? cu[k * NX + col[4]] : Real(0);
+        u1z[j] = (k >= 0 && k < NZ) ? cu[k * SX + col[4]] : Real(0);
     }
     RBC_UNROLL
-    for (int j = 0; j < 7; ++j) wxr[j] = cw[k0 * NX + col[j]];   // w(i-3..i+3, face k0)
+    for (int j = 0; j < 7; ++j) wxr[j] = cw[k0 * SX + col[j]];   // w(i-3..i+3, face k0)
 
     // fluxes through the strip's lower boundary (carried afterwards)
     Real Fzb_lo = Real(0), Wu_lo = Real(0), Ww_lo = Real(0);
@@ -267,12 +274,20 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* c, Real* 
     RBC_UNROLL
     for (int r = 0; r < RS; ++r) {
         const int k = k0 + r;
+        // previous-stage tendencies: per-CTA global slab [field][r][tid] (coalesced); issue the loads first
+        // so their L2 latency hides behind this row's arithmetic (stage 1 has zet = 0 and must not read)
+        Real gb0 = Real(0), gu0 = Real(0), gw0 = Real(0);
+        if (use_gm) {
+            gb0 = gm[(0 * RS + r) * NT + tid];
+            gu0 = gm[(1 * RS + r) * NT + tid];
+            gw0 = gm[(2 * RS + r) * NT + tid];
+        }
         Real bx[7], ux[7], wxn[7];
         RBC_UNROLL
         for (int j = 0; j < 7; ++j) {
-            bx[j] = (j == 3) ? bz[3] : cb[k * NX + col[j]];
-            ux[j] = (j == 3) ? uz[3] : ((j == 4) ? u1z[2] : cu[k * NX + col[j]]);
-            wxn[j] = (j == 3) ? wz[4] : cw[(k + 1) * NX + col[j]];      // face k+1 <= NZ always valid
+            bx[j] = (j == 3) ? bz[3] : cb[k * SX + col[j]];
+            ux[j] = (j == 3) ? uz[3] : ((j == 4) ? u1z[2] : cu[k * SX + col[j]]);
+            wxn[j] = (j == 3) ? wz[4] : cw[(k + 1) * SX + col[j]];      // face k+1 <= NZ always valid
         }
         const bool top = (k == NZ - 1);
 
@@ -308,34 +323,28 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* c, Real* 
         if (!SPLIT) Gw += Real(0.5) * (bz[2] + bz[3]);
         if (k == 0) Gw = Real(0);
 
-        // ---- RK3 substep; G- lives in a per-CTA global slab, [field][r][tid] (coalesced) ----
-        Real gb0 = Real(0), gu0 = Real(0), gw0 = Real(0);
-        if (use_gm) {
-            gb0 = gm[(0 * RS + r) * NT + tid];
-            gu0 = gm[(1 * RS + r) * NT + tid];
-            gw0 = gm[(2 * RS + r) * NT + tid];
-        }
+        // ---- RK3 substep ----
         gm[(0 * RS + r) * NT + tid] = Gb;
         gm[(1 * RS + r) * NT + tid] = Gu;
         gm[(2 * RS + r) * NT + tid] = Gw;
-        n[OFF_B + k * NX + i] = bz[3] + dt * (gam * Gb + zet * gb0);
-        n[OFF_U + k * NX + i] = uz[3] + dt * (gam * Gu + zet * gu0);
-        n[OFF_W + k * NX + i] = (k == 0) ? Real(0) : wz[3] + dt * (gam * Gw + zet * gw0);
+        n[OFF_B + k * SX + i] = bz[3] + dt * (gam * Gb + zet * gb0);
+        n[OFF_U + k * SX + i] = uz[3] + dt * (gam * Gu + zet * gu0);
+        n[OFF_W + k * SX + i] = (k == 0) ? Real(0) : wz[3] + dt * (gam * Gw + zet * gw0);
 
         // ---- slide ----
         Fzb_lo = Fzb_hi; Wu_lo = Wu_hi; Ww_lo = Ww_hi;
         RBC_UNROLL
         for (int j = 0; j < 6; ++j) { bz[j] = bz[j + 1]; uz[j] = uz[j + 1]; wz[j] = wz[j + 1]; }
         const int kn = k + 4;
-        bz[6] = (kn < NZ) ? cb[kn * NX + i] : Real(0);
-        uz[6] = (kn < NZ) ? cu[kn * NX + i] : Real(0);
-        wz[6] = (kn <= NZ) ? cw[kn * NX + i] : Real(0);
+        bz[6] = (kn < NZ) ? cb[kn * SX + i] : Real(0);
+        uz[6] = (kn < NZ) ? cu[kn * SX + i] : Real(0);
+        wz[6] = (kn <= NZ) ? cw[kn * SX + i] : Real(0);
         u1z[0] = u1z[1]; u1z[1] = u1z[2]; u1z[2] = u1z[3];
-        u1z[3] = (k + 2 < NZ) ? cu[(k + 2) * NX + col[4]] : Real(0);
+        u1z[3] = (k + 2 < NZ) ? cu[(k + 2) * SX + col[4]] : Real(0);
         RBC_UNROLL
         for (int j = 0; j < 7; ++j) wxr[j] = wxn[j];
     }
-    if (s == NSTRIP - 1) n[OFF_W + NZ * NX + i] = Real(0);       // top wall face
+    if (s == NSTRIP - 1) n[OFF_W + NZ * SX + i] = Real(0);       // top wall face
 }
 
 // ------------------------------------------------------------------------------------------
@@ -345,22 +354,6 @@ template <typename Real>
 RBC_HD void phase_copy(int tid, const Real* src, Real* dst, int nvals)
 {
     for (int q = tid; q < nvals; q += NT) dst[q] = src[q];
-}
-
-// ------------------------------------------------------------------------------------------
-// phase: divergence of the predicted velocity -> scratch R[k][i]
-// ------------------------------------------------------------------------------------------
-template <typename Real>
-RBC_HD void phase_div(int tid, const Consts<Real>& C, const Real* p, Real* R)
-{
-    const int i = tid % NX, s = tid / NX, ip = wrapx(i + 1);
-    const Real* pu = p + OFF_U;
-    const Real* pw = p + OFF_W;
-    RBC_UNROLL
-    for (int r = 0; r < RS; ++r) {
-        const int k = s * RS + r;
-        R[k * RSTR + i] = (pu[k * NX + ip] - pu[k * NX + i]) * C.idx + (pw[(k + 1) * NX + i] - pw[k * NX + i]) * C.idz;
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -377,6 +370,9 @@ template <int SIGN, typename Real> RBC_HD cx<Real> muli(cx<Real> a)   // multipl
 {
     return SIGN > 0 ? cx<Real>{-a.im, a.re} : cx<Real>{a.im, -a.re};
 }
+// 64-/128-bit shared-memory access of one complex number (address is always 2*sizeof(Real) aligned)
+template <typename Real> RBC_HD cx<Real> ldc(const Real* p) { return *reinterpret_cast<const cx<Real>*>(p); }
+template <typename Real> RBC_HD void stc(Real* p, cx<Real> v) { *reinterpret_cast<cx<Real>*>(p) = v; }
 
 template <int SIGN, typename Real>
 RBC_HD void dft4(cx<Real>& x0, cx<Real>& x1, cx<Real>& x2, cx<Real>& x3)
@@ -425,148 +421,201 @@ RBC_HD void dft6(cx<Real>* x)
     x[2] = cadd(e2, w2); x[5] = csub(e2, w2);
 }
 
-// A row of R holds 48 complex numbers z[n] = (R[2n], R[2n+1]).  The 48-point transform is
-// 6 x 8 Cooley-Tukey done in place: pass A = 8-point DFTs over n2 (n = n1 + 6 n2) + twiddle,
-// pass B = 6-point DFTs over n1.  Output X[8 k1 + k2] sits in slot k1 + 6 k2.
+// ------------------------------------------------------------------------------------------
+// The x-transform.  A row of the scratch R holds 48 complex numbers z[n] = (r[2n], r[2n+1]); the
+// 96-point real FFT is a 48-point complex FFT (6 x 8 Cooley-Tukey, in place) plus the real-FFT
+// split.  Lanes map to consecutive ROWS (item = group*64 + row) so that every 64-bit access of a
+// warp walks the padded rows conflict-free.
+//   pass A fwd : divergence of the predicted velocity (computed on the fly from u*, w*) ->
+//                8-point DFTs over n2 (n = n1 + 6 n2) -> twiddle W48^(n1 k2) -> slot n1 + 6 k2
+//   pass B fwd : 6-point DFTs over n1 for the column pair (k2, 8-k2) [or (0,4)] -> Z[8 k1 + k2],
+//                then the real-FFT split in registers -> X[m] in slot (m>>3) + 6 (m&7)
+//   pass B inv / pass A inv : the exact inverses (conjugate twiddles), leaving phi in natural order.
+// ------------------------------------------------------------------------------------------
+RBC_HD int slot48(int k) { return (k >> 3) + 6 * (k & 7); }
+
 template <typename Real>
-RBC_HD void fft_passA_fwd(int item, Real* R, const Real* tw48)
+RBC_HD void fft_passA_fwd_div(int item, const Consts<Real>& C, const Real* p, Real* R, const Real* tw48)
 {
-    const int row = item / 6, n1 = item % 6;
-    Real* z = R + row * RSTR;
+    const int n1 = item >> 6, row = item & 63;
+    const Real* pu = p + OFF_U + row * SX;
+    const Real* pw0 = p + OFF_W + row * SX;
+    const Real* pw1 = pw0 + SX;
     cx<Real> a[8];
     RBC_UNROLL
-    for (int n2 = 0; n2 < 8; ++n2) a[n2] = {z[2 * (n1 + 6 * n2)], z[2 * (n1 + 6 * n2) + 1]};
+    for (int n2 = 0; n2 < 8; ++n2) {
+        const int x = 2 * (n1 + 6 * n2);
+        const cx<Real> u01 = ldc(pu + x), w0 = ldc(pw0 + x), w1 = ldc(pw1 + x);
+        const Real u2 = pu[(x + 2 == NX) ? 0 : x + 2];
+        a[n2].re = (u01.im - u01.re) * C.idx + (w1.re - w0.re) * C.idz;
+        a[n2].im = (u2 - u01.im) * C.idx + (w1.im - w0.im) * C.idz;
+    }
     dft8<-1>(a);
+    Real* z = R + row * RSTR;
     RBC_UNROLL
     for (int k2 = 0; k2 < 8; ++k2) {
         const int j = n1 * k2;                       // W48^(n1 k2), forward: e^{-i theta}
-        const cx<Real> v = cmul(a[k2], tw48[2 * j], -tw48[2 * j + 1]);
-        z[2 * (n1 + 6 * k2)] = v.re; z[2 * (n1 + 6 * k2) + 1] = v.im;
-    }
-}
-template <typename Real>
-RBC_HD void fft_passB_fwd(int item, Real* R)
-{
-    const int row = item / 8, k2 = item % 8;
-    Real* z = R + row * RSTR + 12 * k2;
-    cx<Real> a[6];
-    RBC_UNROLL
-    for (int n1 = 0; n1 < 6; ++n1) a[n1] = {z[2 * n1], z[2 * n1 + 1]};
-    dft6<-1>(a);
-    RBC_UNROLL
-    for (int k1 = 0; k1 < 6; ++k1) { z[2 * k1] = a[k1].re; z[2 * k1 + 1] = a[k1].im; }
-}
-template <typename Real>
-RBC_HD void fft_passB_inv(int item, Real* R, const Real* tw48)
-{
-    const int row = item / 8, k2 = item % 8;
-    Real* z = R + row * RSTR + 12 * k2;
-    cx<Real> a[6];
-    RBC_UNROLL
-    for (int k1 = 0; k1 < 6; ++k1) a[k1] = {z[2 * k1], z[2 * k1 + 1]};
-    dft6<+1>(a);
-    RBC_UNROLL
-    for (int n1 = 0; n1 < 6; ++n1) {
-        const int j = n1 * k2;                       // conj twiddle
-        const cx<Real> v = cmul(a[n1], tw48[2 * j], tw48[2 * j + 1]);
-        z[2 * n1] = v.re; z[2 * n1 + 1] = v.im;
+        stc(z + 2 * (n1 + 6 * k2), cmul(a[k2], tw48[2 * j], -tw48[2 * j + 1]));
     }
 }
 template <typename Real>
 RBC_HD void fft_passA_inv(int item, Real* R)
 {
-    const int row = item / 6, n1 = item % 6;
+    const int n1 = item >> 6, row = item & 63;
     Real* z = R + row * RSTR;
     cx<Real> a[8];
     RBC_UNROLL
-    for (int k2 = 0; k2 < 8; ++k2) a[k2] = {z[2 * (n1 + 6 * k2)], z[2 * (n1 + 6 * k2) + 1]};
+    for (int k2 = 0; k2 < 8; ++k2) a[k2] = ldc(z + 2 * (n1 + 6 * k2));
     dft8<+1>(a);
     RBC_UNROLL
-    for (int n2 = 0; n2 < 8; ++n2) { z[2 * (n1 + 6 * n2)] = a[n2].re; z[2 * (n1 + 6 * n2) + 1] = a[n2].im; }
+    for (int n2 = 0; n2 < 8; ++n2) stc(z + 2 * (n1 + 6 * n2), a[n2]);
 }
-RBC_HD int slot48(int k) { return (k >> 3) + 6 * (k & 7); }
 
-// real-FFT split: Z (48-point transform of the packed row) <-> X[0..48] (96-point spectrum).
-// item = (row, m), m = 0..24 handles the pair (m, 48-m) in place.
+// real-FFT split of the pair (m, 48-m): Z (48-point transform of the packed row) <-> X (96-point spectrum)
+//   E = (Z[m] + conj Z[48-m])/2, O = -i (Z[m] - conj Z[48-m])/2, X[m] = E + W96^m O, X[48-m] = conj(E - W96^m O)
 template <typename Real>
-RBC_HD void fft_untangle(int item, Real* R, const Real* tw96)
+RBC_HD void untangle_pair(cx<Real>& zm, cx<Real>& zp, Real c, Real s)
 {
-    const int row = item / 25, m = item % 25;
-    Real* z = R + row * RSTR;
-    if (m == 0) {
-        const Real a = z[0], b = z[1];
-        z[0] = a + b; z[1] = a - b;                  // X[0], X[48] (both real)
-        return;
-    }
-    const int pa = 2 * slot48(m), pb = 2 * slot48(48 - m);
-    if (m == 24) { z[pa + 1] = -z[pa + 1]; return; }  // X[24] = conj Z[24]
-    const cx<Real> Zm = {z[pa], z[pa + 1]}, Zc = {z[pb], -z[pb + 1]};
-    const cx<Real> E = {Real(0.5) * (Zm.re + Zc.re), Real(0.5) * (Zm.im + Zc.im)};
-    const cx<Real> D = {Real(0.5) * (Zm.re - Zc.re), Real(0.5) * (Zm.im - Zc.im)};
-    const cx<Real> O = {D.im, -D.re};                // -i D
-    const cx<Real> WO = cmul(O, tw96[2 * m], -tw96[2 * m + 1]);
-    z[pa] = E.re + WO.re; z[pa + 1] = E.im + WO.im;              // X[m]
-    z[pb] = E.re - WO.re; z[pb + 1] = -(E.im - WO.im);           // X[48-m] = conj(E - W O)
+    const cx<Real> E = {Real(0.5) * (zm.re + zp.re), Real(0.5) * (zm.im - zp.im)};
+    const cx<Real> D = {Real(0.5) * (zm.re - zp.re), Real(0.5) * (zm.im + zp.im)};
+    const cx<Real> WO = cmul(cx<Real>{D.im, -D.re}, c, -s);
+    zm = {E.re + WO.re, E.im + WO.im};
+    zp = {E.re - WO.re, -(E.im - WO.im)};
 }
 template <typename Real>
-RBC_HD void fft_tangle(int item, Real* R, const Real* tw96)
+RBC_HD void tangle_pair(cx<Real>& xm, cx<Real>& xp, Real c, Real s)
 {
-    const int row = item / 25, m = item % 25;
-    Real* z = R + row * RSTR;
-    if (m == 0) {
-        const Real a = z[0], b = z[1];
-        z[0] = Real(0.5) * (a + b); z[1] = Real(0.5) * (a - b);    // Z[0] = E0 + i O0
-        return;
+    const cx<Real> E = {Real(0.5) * (xm.re + xp.re), Real(0.5) * (xm.im - xp.im)};
+    const cx<Real> WO = {Real(0.5) * (xm.re - xp.re), Real(0.5) * (xm.im + xp.im)};
+    const cx<Real> O = cmul(WO, c, s);               // conj(W96^m) * (W96^m O)
+    xm = {E.re - O.im, E.im + O.re};                 // Z[m]    = E + i O
+    xp = {E.re + O.im, -E.im + O.re};                // Z[48-m] = conj(E) + i conj(O)
+}
+
+// item = g*64 + row, g = 0..3: column pair (ka, kb) = (0,4) for g = 0, else (g, 8-g)
+template <typename Real>
+RBC_HD void fft_passB_fwd_untangle(int item, Real* R, const Real* tw96)
+{
+    const int g = item >> 6, row = item & 63;
+    const int ka = g, kb = (g == 0) ? 4 : 8 - g;
+    Real* za = R + row * RSTR + 12 * ka;
+    Real* zb = R + row * RSTR + 12 * kb;
+    cx<Real> a[6], b[6];
+    RBC_UNROLL
+    for (int n1 = 0; n1 < 6; ++n1) { a[n1] = ldc(za + 2 * n1); b[n1] = ldc(zb + 2 * n1); }
+    dft6<-1>(a);                                     // a[k1] = Z[8 k1 + ka]
+    dft6<-1>(b);                                     // b[k1] = Z[8 k1 + kb]
+    if (g == 0) {
+        // column 0: m = 8 k1: (0 | 48) real pair, 8<->40, 16<->32, 24 self-conjugate
+        const Real x0 = a[0].re + a[0].im, x48 = a[0].re - a[0].im;
+        a[0] = {x0, x48};
+        untangle_pair(a[1], a[5], tw96[2 * 8], tw96[2 * 8 + 1]);
+        untangle_pair(a[2], a[4], tw96[2 * 16], tw96[2 * 16 + 1]);
+        a[3].im = -a[3].im;
+        // column 4: m = 8 k1 + 4 <-> 8 (5-k1) + 4
+        untangle_pair(b[0], b[5], tw96[2 * 4], tw96[2 * 4 + 1]);
+        untangle_pair(b[1], b[4], tw96[2 * 12], tw96[2 * 12 + 1]);
+        untangle_pair(b[2], b[3], tw96[2 * 20], tw96[2 * 20 + 1]);
+    } else {
+        // m = 8 k1 + g  <->  48 - m = 8 (5-k1) + (8-g)
+        RBC_UNROLL
+        for (int k1 = 0; k1 < 6; ++k1) {
+            const int m = 8 * k1 + g;
+            untangle_pair(a[k1], b[5 - k1], tw96[2 * m], tw96[2 * m + 1]);
+        }
     }
-    const int pa = 2 * slot48(m), pb = 2 * slot48(48 - m);
-    if (m == 24) { z[pa + 1] = -z[pa + 1]; return; }
-    const cx<Real> Xm = {z[pa], z[pa + 1]}, Xc = {z[pb], -z[pb + 1]};
-    const cx<Real> E = {Real(0.5) * (Xm.re + Xc.re), Real(0.5) * (Xm.im + Xc.im)};
-    const cx<Real> WO = {Real(0.5) * (Xm.re - Xc.re), Real(0.5) * (Xm.im - Xc.im)};
-    const cx<Real> O = cmul(WO, tw96[2 * m], tw96[2 * m + 1]);   // conj(W) * WO
-    // Z[m] = E + iO ; Z[48-m] = conj(E) + i conj(O)
-    z[pa] = E.re - O.im; z[pa + 1] = E.im + O.re;
-    z[pb] = E.re + O.im; z[pb + 1] = -E.im + O.re;
+    RBC_UNROLL
+    for (int k1 = 0; k1 < 6; ++k1) { stc(za + 2 * k1, a[k1]); stc(zb + 2 * k1, b[k1]); }
+}
+template <typename Real>
+RBC_HD void fft_passB_inv_tangle(int item, Real* R, const Real* tw48, const Real* tw96)
+{
+    const int g = item >> 6, row = item & 63;
+    const int ka = g, kb = (g == 0) ? 4 : 8 - g;
+    Real* za = R + row * RSTR + 12 * ka;
+    Real* zb = R + row * RSTR + 12 * kb;
+    cx<Real> a[6], b[6];
+    RBC_UNROLL
+    for (int k1 = 0; k1 < 6; ++k1) { a[k1] = ldc(za + 2 * k1); b[k1] = ldc(zb + 2 * k1); }
+    if (g == 0) {
+        const Real x0 = a[0].re, x48 = a[0].im;
+        a[0] = {Real(0.5) * (x0 + x48), Real(0.5) * (x0 - x48)};      // Z[0] = E0 + i O0
+        tangle_pair(a[1], a[5], tw96[2 * 8], tw96[2 * 8 + 1]);
+        tangle_pair(a[2], a[4], tw96[2 * 16], tw96[2 * 16 + 1]);
+        a[3].im = -a[3].im;
+        tangle_pair(b[0], b[5], tw96[2 * 4], tw96[2 * 4 + 1]);
+        tangle_pair(b[1], b[4], tw96[2 * 12], tw96[2 * 12 + 1]);
+        tangle_pair(b[2], b[3], tw96[2 * 20], tw96[2 * 20 + 1]);
+    } else {
+        RBC_UNROLL
+        for (int k1 = 0; k1 < 6; ++k1) {
+            const int m = 8 * k1 + g;
+            tangle_pair(a[k1], b[5 - k1], tw96[2 * m], tw96[2 * m + 1]);
+        }
+    }
+    dft6<+1>(a);
+    dft6<+1>(b);
+    RBC_UNROLL
+    for (int n1 = 0; n1 < 6; ++n1) {                  // conjugate twiddles W48^-(n1 k2)
+        const int ja = n1 * ka, jb = n1 * kb;
+        stc(za + 2 * n1, cmul(a[n1], tw48[2 * ja], tw48[2 * ja + 1]));
+        stc(zb + 2 * n1, cmul(b[n1], tw48[2 * jb], tw48[2 * jb + 1]));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // phase: tridiagonal solves in z, one thread per spectral word (96 real systems, in place).
 //   p(k-1) - (2 + lam dz^2) p(k) + p(k+1) = dz^2 r(k),  p(-1)=p(0), p(NZ)=p(NZ-1)
 // tinv[k][t] = 1/(diag_k - tinv[k-1][t]) precomputed per word; `scale` = dz^2/48 folds the
-// inverse-FFT normalisation.
+// inverse-FFT normalisation.  Rows are processed in blocks of 8 with all loads issued up front so
+// only the 4-cycle FMA chain is serial.
 // ------------------------------------------------------------------------------------------
 template <typename Real>
 RBC_HD void phase_thomas(int tid, Real* R, const Real* tinv, Real scale)
 {
     if (tid >= NX) return;
+    constexpr int BK = 8;
     Real d = Real(0);
-    for (int k = 0; k < NZ; ++k) {
-        const Real iv = tinv[k * NX + tid];
-        d = (R[k * RSTR + tid] * scale) * iv - d * iv;
-        R[k * RSTR + tid] = d;
+    for (int kb = 0; kb < NZ; kb += BK) {
+        Real iv[BK], rs[BK];
+        RBC_UNROLL
+        for (int j = 0; j < BK; ++j) { iv[j] = tinv[(kb + j) * NX + tid]; rs[j] = R[(kb + j) * RSTR + tid]; }
+        RBC_UNROLL
+        for (int j = 0; j < BK; ++j) rs[j] = rs[j] * scale * iv[j];
+        RBC_UNROLL
+        for (int j = 0; j < BK; ++j) { d = rs[j] - d * iv[j]; R[(kb + j) * RSTR + tid] = d; }
     }
-    Real p = d;                                       // p(NZ-1) = d'(NZ-1)
-    for (int k = NZ - 2; k >= 0; --k) {
-        p = R[k * RSTR + tid] - tinv[k * NX + tid] * p;
-        R[k * RSTR + tid] = p;
+    Real pv = d;                                      // p(NZ-1) = d'(NZ-1)
+    for (int kb = NZ - BK; kb >= 0; kb -= BK) {
+        Real iv[BK], dd[BK];
+        RBC_UNROLL
+        for (int j = 0; j < BK; ++j) { iv[j] = tinv[(kb + j) * NX + tid]; dd[j] = R[(kb + j) * RSTR + tid]; }
+        RBC_UNROLL
+        for (int j = BK - 1; j >= 0; --j) {
+            if (kb + j == NZ - 1) continue;
+            pv = dd[j] - iv[j] * pv;
+            R[(kb + j) * RSTR + tid] = pv;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// phase: pressure correction  u -= d_x phi, w -= d_z phi  (phi = dtau * pNHS in R)
+// phase: pressure correction  u -= d_x phi, w -= d_z phi  (phi = dtau * pNHS in R); strip march
 // ------------------------------------------------------------------------------------------
 template <typename Real>
 RBC_HD void phase_correct(int tid, const Consts<Real>& C, Real* p, const Real* R)
 {
-    const int i = tid % NX, s = tid / NX, im = wrapx(i - 1);
+    const int i = tid % NX, s = tid / NX, im = wrapx(i - 1), k0 = s * RS;
     Real* pu = p + OFF_U;
     Real* pw = p + OFF_W;
+    Real below = (k0 >= 1) ? R[(k0 - 1) * RSTR + i] : Real(0);
     RBC_UNROLL
     for (int r = 0; r < RS; ++r) {
-        const int k = s * RS + r;
+        const int k = k0 + r;
         const Real ph = R[k * RSTR + i];
-        pu[k * NX + i] -= (ph - R[k * RSTR + im]) * C.idx;
-        if (k >= 1) pw[k * NX + i] -= (ph - R[(k - 1) * RSTR + i]) * C.idz;
+        pu[k * SX + i] -= (ph - R[k * RSTR + im]) * C.idx;
+        if (k >= 1) pw[k * SX + i] -= (ph - below) * C.idz;
+        below = ph;
     }
 }
 
@@ -576,13 +625,10 @@ RBC_HD void phase_correct(int tid, const Consts<Real>& C, Real* p, const Real* R
 template <typename Real>
 RBC_HD void project(const Consts<Real>& C, const Ctx<Real>& X, Real* p, Real scale)
 {
-    RBC_PHASE(phase_div(tid, C, p, X.R);)
-    RBC_PHASE(fft_passA_fwd(tid, X.R, X.tw48);)
-    RBC_PHASE(for (int it = tid; it < NZ * 8; it += NT) fft_passB_fwd(it, X.R);)
-    RBC_PHASE(for (int it = tid; it < NZ * 25; it += NT) fft_untangle(it, X.R, X.tw96);)
+    RBC_PHASE(fft_passA_fwd_div(tid, C, p, X.R, X.tw48);)
+    RBC_PHASE(if (tid < 4 * NZ) fft_passB_fwd_untangle(tid, X.R, X.tw96);)
     RBC_PHASE(phase_thomas(tid, X.R, X.tinv, scale);)
-    RBC_PHASE(for (int it = tid; it < NZ * 25; it += NT) fft_tangle(it, X.R, X.tw96);)
-    RBC_PHASE(for (int it = tid; it < NZ * 8; it += NT) fft_passB_inv(it, X.R, X.tw48);)
+    RBC_PHASE(if (tid < 4 * NZ) fft_passB_inv_tangle(tid, X.R, X.tw48, X.tw96);)
     RBC_PHASE(fft_passA_inv(tid, X.R);)
     RBC_PHASE(phase_correct(tid, C, p, X.R);)
 }
@@ -592,9 +638,8 @@ RBC_HD void project(const Consts<Real>& C, const Ctx<Real>& X, Real* p, Real sca
 // ------------------------------------------------------------------------------------------
 // per-thread partial sums for Nusselt numbers and the NaN flag (get_nusselt, rbc_sim2D_api.jl:142-163)
 //   red[0] sum b*w (state)           red[1] sum b*w on the sensor grid
-//   red[2],red[3] sum_x b on rows (0,1) [strip 0] or (NZ-2,NZ-1) [strip 3]
-//   red[4],red[5] same for rows (NZ-2, NZ-1); sensor-row sums: phase_reduce_obs_partials
-//   red[6] NaN count
+//   red[2],red[3] sum_x b on rows (0,1)      red[4],red[5] same for rows (NZ-2, NZ-1)
+//   red[6] NaN count;  sensor-row sums: phase_reduce_obs_partials
 template <typename Real>
 RBC_HD void phase_reduce_partials(int tid, const Consts<Real>& C, const Real* p, double* red)
 {
@@ -604,7 +649,7 @@ RBC_HD void phase_reduce_partials(int tid, const Consts<Real>& C, const Real* p,
     double q1 = 0, q1o = 0, ta = 0, tb = 0, bad = 0;
     for (int r = 0; r < RS; ++r) {
         const int k = s * RS + r;
-        const double b = (double)p[OFF_B + k * NX + i], u = (double)p[OFF_U + k * NX + i], w = (double)p[OFF_W + k * NX + i];
+        const double b = (double)p[OFF_B + k * SX + i], u = (double)p[OFF_U + k * SX + i], w = (double)p[OFF_W + k * SX + i];
         if (b != b || u != u || w != w) bad += 1;
         q1 += b * w;
         const bool zs = (k % oz) == 0;
@@ -612,7 +657,6 @@ RBC_HD void phase_reduce_partials(int tid, const Consts<Real>& C, const Real* p,
         if (k == 0 || k == NZ - 2) ta += b;
         if (k == 1 || k == NZ - 1) tb += b;
     }
-    // rows 0/1 and NZ-2/NZ-1 (and the sensor rows) live in different strips; tag by strip half
     const bool lower = (s * RS < NZ / 2);
     red[0 * NT + tid] = q1;
     red[1 * NT + tid] = q1o;
@@ -630,7 +674,7 @@ RBC_HD void phase_reduce_obs_partials(int tid, const Consts<Real>& C, const Real
     if ((i % ox) == 0) {
         const int rows[4] = {0, oz, (C.obs_nz - 2) * oz, (C.obs_nz - 1) * oz};
         for (int q = 0; q < 4; ++q)
-            if (rows[q] / RS == s) v[q] += (double)p[OFF_B + rows[q] * NX + i];
+            if (rows[q] / RS == s) v[q] += (double)p[OFF_B + rows[q] * SX + i];
     }
     for (int q = 0; q < 4; ++q) red[q * NT + tid] = v[q];
 }
@@ -639,6 +683,17 @@ RBC_HD double sum_serial(const double* a, int n)
     double s = 0;
     for (int q = 0; q < n; ++q) s += a[q];
     return s;
+}
+// global (compact rows of NX) <-> on-chip (rows of SX) state copies
+template <typename Real>
+RBC_HD void phase_load_state(int tid, const Real* g, Real* sm)
+{
+    for (int q = tid; q < NSTATE; q += NT) sm[(q / NX) * SX + (q % NX)] = g[q];
+}
+template <typename Real>
+RBC_HD void phase_store_state(int tid, const Real* sm, Real* g)
+{
+    for (int q = tid; q < NSTATE; q += NT) g[q] = sm[(q / NX) * SX + (q % NX)];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -654,7 +709,7 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
 
     // load the environment, evaluate the heater profile for this action
     RBC_PHASE(
-        for (int q = tid; q < NSTATE; q += NT) X.s0[q] = st[q];
+        phase_load_state(tid, st, X.s0);
         if (tid < NX) X.Tb[tid] = (Real)heater_T(C, io.actions + (size_t)env * C.heaters, (tid + 0.5) * C.dx);
     )
     Real* cur = X.s0;
@@ -668,7 +723,7 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
             RBC_PHASE((phase_tendency<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, X.gm, dt, gam[stage], zet[stage], stage > 0));)
             Real* P;
             if (NXT_GLOBAL) {
-                RBC_PHASE(phase_copy(tid, nxt, cur, NSTATE);)
+                RBC_PHASE(phase_copy(tid, nxt, cur, NS_SM);)
                 P = cur;
             } else {
                 P = nxt; nxt = cur; cur = P;
@@ -679,17 +734,19 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
     }
 
     // ---- epilogue: NaN check, observation, Nusselt numbers, reward, bookkeeping ----
+    // the reduction scratch aliases the dead second state buffer when that one is on-chip
+    double* red = NXT_GLOBAL ? X.red : reinterpret_cast<double*>(nxt);
     const int oz = NZ / C.obs_nz, ox = NX / C.obs_nx, nobs = C.obs_nz * C.obs_nx;
     double nu_s = 0, nu_o = 0;
-    RBC_PHASE(phase_reduce_partials(tid, C, cur, X.red);)
+    RBC_PHASE(phase_reduce_partials(tid, C, cur, red);)
 #if defined(__CUDA_ARCH__)
     __shared__ double fin[12];
 #else
     double fin[12];
 #endif
-    RBC_PHASE(if (tid < NRED) fin[tid] = sum_serial(X.red + tid * NT, NT);)
-    RBC_PHASE(phase_reduce_obs_partials(tid, C, cur, X.red);)
-    RBC_PHASE(if (tid < 4) fin[NRED + tid] = sum_serial(X.red + tid * NT, NT);)
+    RBC_PHASE(if (tid < NRED) fin[tid] = sum_serial(red + tid * NT, NT);)
+    RBC_PHASE(phase_reduce_obs_partials(tid, C, cur, red);)
+    RBC_PHASE(if (tid < 4) fin[NRED + tid] = sum_serial(red + tid * NT, NT);)
     {
         const double kap = C.kappa_d, dbH = kap * 1.0 / 2.0;    // kappa * db / H, db = 1, H = 2
         const double q1 = fin[0] / (double)NCELL, q1o = fin[1] / (double)nobs;
@@ -702,12 +759,12 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
     }
     RBC_PHASE(
         // store the state back and emit the observation (strided sub-sample, channel-major)
-        for (int q = tid; q < NSTATE; q += NT) st[q] = cur[q];
+        if (F.nsub > 0 || F.project_first) phase_store_state(tid, cur, st);
         float* ob = io.obs + (size_t)env * C.channels * nobs;
         for (int q = tid; q < 3 * nobs; q += NT) {
             const int ch = q / nobs, zo = (q % nobs) / C.obs_nx, xo = q % C.obs_nx;
             const int off = (ch == 0 ? OFF_B : (ch == 1 ? OFF_U : OFF_W));
-            ob[q] = (float)cur[off + (zo * oz) * NX + xo * ox];
+            ob[q] = (float)cur[off + (zo * oz) * SX + xo * ox];
         }
         if (tid == 0) {
             io.nu_state[env] = nu_s;
@@ -729,9 +786,9 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
         RBC_PHASE(
             double acc = 0;
             for (int q = tid; q < NCELL; q += NT) acc += (double)X.R[(q / NX) * RSTR + (q % NX)];
-            X.red[tid] = acc;
+            red[tid] = acc;
         )
-        RBC_PHASE(if (tid == 0) fin[11] = sum_serial(X.red, NT) / (double)NCELL;)
+        RBC_PHASE(if (tid == 0) fin[11] = sum_serial(red, NT) / (double)NCELL;)
         RBC_PHASE(
             for (int q = tid; q < NCELL; q += NT)
                 pr[NCELL + q] = (Real)(((double)X.R[(q / NX) * RSTR + (q % NX)] - fin[11]) / (double)last_dtau);
@@ -794,7 +851,7 @@ inline int word_mode(int t)
     if (p == 0) return (t == 0) ? 0 : NX / 2;
     return 8 * (p % 6) + p / 6;
 }
-inline void build_tables_host(double lx, double lz, double* tinv /*NZ*NX*/, double* tw48 /*96*/, double* tw96 /*50*/)
+inline void build_tables_host(double lx, double lz, double* tinv /*NZ*NX*/, double* tw48 /*96*/, double* tw96 /*96*/)
 {
     const double PI = 3.14159265358979323846;
     const double dx = lx / NX, dz = lz / NZ;
@@ -812,7 +869,7 @@ inline void build_tables_host(double lx, double lz, double* tinv /*NZ*NX*/, doub
         }
     }
     for (int j = 0; j < 48; ++j) { tw48[2 * j] = cos(2 * PI * j / 48); tw48[2 * j + 1] = sin(2 * PI * j / 48); }
-    for (int m = 0; m < 25; ++m) { tw96[2 * m] = cos(2 * PI * m / 96); tw96[2 * m + 1] = sin(2 * PI * m / 96); }
+    for (int m = 0; m < 48; ++m) { tw96[2 * m] = cos(2 * PI * m / 96); tw96[2 * m + 1] = sin(2 * PI * m / 96); }
 }
 
 }  // namespace rbc2d

@@ -32,15 +32,25 @@ static int fail(const std::string& m) { g_err = m; return -1; }
 // ------------------------------------------------------------------------------------------
 template <typename Real>
 struct SmemLayout {
-    static constexpr bool kNxtGlobal = sizeof(Real) == 8;     // fp64: predicted state lives in global memory
+    // fp32: both state buffers, the Poisson scratch and the Thomas table live on-chip (the epilogue's
+    //       reduction scratch aliases the dead state buffer).
+    // fp64: one state buffer on-chip, the predicted state and the Thomas table in global memory.
+    static constexpr bool kNxtGlobal = sizeof(Real) == 8;
+    static constexpr bool kTinvShared = !kNxtGlobal;
     static constexpr size_t s0 = 0;
-    static constexpr size_t s1 = s0 + sizeof(Real) * NSTATE;
-    static constexpr size_t R = kNxtGlobal ? s1 : s1 + sizeof(Real) * NSTATE;
-    static constexpr size_t red = R + sizeof(Real) * NR;
-    static constexpr size_t Tb = red + sizeof(double) * NRED * NT;
+    static constexpr size_t s1 = s0 + sizeof(Real) * NS_SM;
+    static constexpr size_t R = kNxtGlobal ? s1 : s1 + sizeof(Real) * NS_SM;
+    static constexpr size_t tinv = R + sizeof(Real) * NR;
+    static constexpr size_t red = tinv + (kTinvShared ? sizeof(Real) * NZ * NX : 0);
+    static constexpr size_t Tb = red + (kNxtGlobal ? sizeof(double) * NRED * NT : 0);
     static constexpr size_t tw48 = Tb + sizeof(Real) * NX;
     static constexpr size_t tw96 = tw48 + sizeof(Real) * 96;
-    static constexpr size_t total = tw96 + sizeof(Real) * 50;
+    static constexpr size_t total = tw96 + sizeof(Real) * 96;
+    static_assert(total <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+    static constexpr size_t kAlign = 2 * sizeof(Real);     // one complex number per shared-memory access
+    static_assert(s1 % kAlign == 0 && R % kAlign == 0 && tinv % kAlign == 0 && red % 8 == 0 && Tb % kAlign == 0, "alignment");
+    static_assert((SX * sizeof(Real)) % kAlign == 0, "row stride must keep complex accesses aligned");
+    static_assert(kNxtGlobal || sizeof(double) * NRED * NT <= sizeof(Real) * NS_SM, "reduction scratch must fit a state buffer");
 };
 
 template <typename Real, bool SPLIT>
@@ -52,16 +62,23 @@ rbc2d_env_kernel(Consts<Real> C, Tables<Real> T, EnvIO<Real> io, Real* gm_all, R
     using L = SmemLayout<Real>;
     Ctx<Real> X;
     X.s0 = reinterpret_cast<Real*>(smem + L::s0);
-    X.s1 = L::kNxtGlobal ? nxt_all + (size_t)blockIdx.x * NSTATE : reinterpret_cast<Real*>(smem + L::s1);
+    X.s1 = L::kNxtGlobal ? nxt_all + (size_t)blockIdx.x * NS_SM : reinterpret_cast<Real*>(smem + L::s1);
     X.R = reinterpret_cast<Real*>(smem + L::R);
     X.red = reinterpret_cast<double*>(smem + L::red);
     X.Tb = reinterpret_cast<Real*>(smem + L::Tb);
     X.tw48 = reinterpret_cast<Real*>(smem + L::tw48);
     X.tw96 = reinterpret_cast<Real*>(smem + L::tw96);
     X.gm = gm_all + (size_t)blockIdx.x * NSTATE;
-    X.tinv = T.tinv;
-    for (int q = threadIdx.x; q < 96; q += NT) X.tw48[q] = T.tw48[q];
-    for (int q = threadIdx.x; q < 50; q += NT) X.tw96[q] = T.tw96[q];
+    if (L::kTinvShared) {
+        Real* tv = reinterpret_cast<Real*>(smem + L::tinv);
+        for (int q = threadIdx.x; q < NZ * NX; q += NT) tv[q] = T.tinv[q];
+        X.tinv = tv;
+    } else {
+        X.tinv = T.tinv;
+    }
+    for (int q = threadIdx.x; q < 96; q += NT) { X.tw48[q] = T.tw48[q]; X.tw96[q] = T.tw96[q]; }
+    // the padding columns of the on-chip rows are never read; zero them once so nothing is uninitialised
+    for (int q = threadIdx.x; q < NS_SM; q += NT) { X.s0[q] = Real(0); if (!L::kNxtGlobal) X.s1[q] = Real(0); }
     __syncthreads();
     for (int j = blockIdx.x; j < n; j += gridDim.x) {
         const int env = env_ids ? env_ids[j] : j;
@@ -106,7 +123,7 @@ __global__ void rbc2d_get_state_kernel(const Real* state, const Real* pressure, 
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
         const int env = (int)(q / per), r = (int)(q % per), ch = r / NCELL, c = r % NCELL;
         float v;
-        if (ch < 3) v = (float)state[(size_t)env * NSTATE + (ch == 0 ? OFF_B : (ch == 1 ? OFF_U : OFF_W)) + c];
+        if (ch < 3) v = (float)state[(size_t)env * NSTATE + (ch == 0 ? GOFF_B : (ch == 1 ? GOFF_U : GOFF_W)) + c];
         else v = pressure ? (float)pressure[(size_t)env * 2 * NCELL + (size_t)(ch - 3) * NCELL + c] : 0.0f;
         out[q] = v;
     }
@@ -142,7 +159,7 @@ struct rbc2d_sim {
 template <typename Real>
 static int upload_tables(rbc2d_sim* s)
 {
-    std::vector<double> tinv(NZ * NX), tw48(96), tw96(50);
+    std::vector<double> tinv(NZ * NX), tw48(96), tw96(96);
     build_tables_host(s->hc.lx, s->hc.lz, tinv.data(), tw48.data(), tw96.data());
     std::vector<Real> a(tinv.begin(), tinv.end()), b(tw48.begin(), tw48.end()), c(tw96.begin(), tw96.end());
     CK(cudaMalloc(&s->tinv, a.size() * sizeof(Real)));
@@ -262,7 +279,7 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
     } while (0)
     ALLOC(s->state, B * NSTATE * rs);
     ALLOC(s->gm, (size_t)s->grid * NSTATE * rs);
-    if (!f32) ALLOC(s->nxt, (size_t)s->grid * NSTATE * rs);
+    if (!f32) ALLOC(s->nxt, (size_t)s->grid * NS_SM * rs);
     if (split) ALLOC(s->pressure, B * 2 * NCELL * rs);
     ALLOC(s->t, B * sizeof(double));
     ALLOC(s->nu_s, B * sizeof(double));
@@ -312,9 +329,9 @@ int rbc2d_load_checkpoints(rbc2d_sim* s, const double* b, const double* u, const
     CK(cudaMalloc((void**)&s->bank, (size_t)n_ep * NSTATE * sizeof(double)));
     for (int e = 0; e < n_ep; ++e) {
         double* d = s->bank + (size_t)e * NSTATE;
-        CK(cudaMemcpyAsync(d + OFF_B, b + (size_t)e * NCELL, NCELL * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-        CK(cudaMemcpyAsync(d + OFF_U, u + (size_t)e * NCELL, NCELL * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-        CK(cudaMemcpyAsync(d + OFF_W, w + (size_t)e * NWF, NWF * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(d + GOFF_B, b + (size_t)e * NCELL, NCELL * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(d + GOFF_U, u + (size_t)e * NCELL, NCELL * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(d + GOFF_W, w + (size_t)e * NWF, NWF * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     }
     CK(cudaStreamSynchronize(s->stream));
     s->n_ep = n_ep;
