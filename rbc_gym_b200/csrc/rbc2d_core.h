@@ -31,6 +31,7 @@
 #else
 #define RBC_HD inline
 #endif
+#define RBC_RESTRICT __restrict__
 
 #if defined(__CUDA_ARCH__)
 #define RBC_PHASE(...) { const int tid = threadIdx.x; __VA_ARGS__ } __syncthreads();
@@ -110,9 +111,10 @@ struct Ctx {
     Real* s1;        // second state buffer (NS_SM): shared (fp32) or global (fp64)
     Real* R;         // shared: Poisson scratch / pHY' (NR)
     Real* Tb;        // shared: bottom wall temperature per column (NX)
+    Real* mid;       // shared: 2*NX values exchanged between the two Thomas sweeps
     Real* tw48;      // shared twiddles
     Real* tw96;
-    Real* gm;        // global: previous-stage tendencies of this CTA (NSTATE)
+    Real* gm;        // global: two slabs (2 x NSTATE) of stage tendencies of this CTA, used ping-pong
     const Real* tinv; // Thomas pivots [NZ][NX]: shared copy (fp32) or the global table (fp64)
     double* red;     // shared: NRED*NT doubles for the epilogue reductions (fp64 mode; fp32 aliases s0/s1)
 };
@@ -231,13 +233,14 @@ RBC_HD void phase_phy(int tid, const Consts<Real>& C, const Real* cb, Real* phy)
 // predicted state `n` (U* = U + dt (gam G + zet G-)), stores G into the CTA's G- slab.
 // ------------------------------------------------------------------------------------------
 template <typename Real, bool SPLIT>
-RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* c, Real* n, const Real* phy,
-                           const Real* Tb, Real* gm, Real dt, Real gam, Real zet, bool use_gm)
+RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTRICT c, Real* RBC_RESTRICT n,
+                           const Real* RBC_RESTRICT phy, const Real* RBC_RESTRICT Tb, const Real* RBC_RESTRICT gm_in,
+                           Real* RBC_RESTRICT gm_out, Real dt, Real gam, Real zet, bool use_gm)
 {
     const int i = tid % NX, s = tid / NX, k0 = s * RS;
-    const Real* cb = c + OFF_B;
-    const Real* cu = c + OFF_U;
-    const Real* cw = c + OFF_W;
+    const Real* RBC_RESTRICT cb = c + OFF_B;
+    const Real* RBC_RESTRICT cu = c + OFF_U;
+    const Real* RBC_RESTRICT cw = c + OFF_W;
     int col[7];
     RBC_UNROLL
     for (int j = 0; j < 7; ++j) col[j] = wrapx(i - 3 + j);
@@ -274,13 +277,14 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* c, Real* 
     RBC_UNROLL
     for (int r = 0; r < RS; ++r) {
         const int k = k0 + r;
-        // previous-stage tendencies: per-CTA global slab [field][r][tid] (coalesced); issue the loads first
+        // previous-stage tendencies: per-CTA global slabs [field][r][tid] (coalesced; read one slab, write the
+        // other, so loads never alias stores); issue the loads first
         // so their L2 latency hides behind this row's arithmetic (stage 1 has zet = 0 and must not read)
         Real gb0 = Real(0), gu0 = Real(0), gw0 = Real(0);
         if (use_gm) {
-            gb0 = gm[(0 * RS + r) * NT + tid];
-            gu0 = gm[(1 * RS + r) * NT + tid];
-            gw0 = gm[(2 * RS + r) * NT + tid];
+            gb0 = gm_in[(0 * RS + r) * NT + tid];
+            gu0 = gm_in[(1 * RS + r) * NT + tid];
+            gw0 = gm_in[(2 * RS + r) * NT + tid];
         }
         Real bx[7], ux[7], wxn[7];
         RBC_UNROLL
@@ -324,9 +328,9 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* c, Real* 
         if (k == 0) Gw = Real(0);
 
         // ---- RK3 substep ----
-        gm[(0 * RS + r) * NT + tid] = Gb;
-        gm[(1 * RS + r) * NT + tid] = Gu;
-        gm[(2 * RS + r) * NT + tid] = Gw;
+        gm_out[(0 * RS + r) * NT + tid] = Gb;
+        gm_out[(1 * RS + r) * NT + tid] = Gu;
+        gm_out[(2 * RS + r) * NT + tid] = Gw;
         n[OFF_B + k * SX + i] = bz[3] + dt * (gam * Gb + zet * gb0);
         n[OFF_U + k * SX + i] = uz[3] + dt * (gam * Gu + zet * gu0);
         n[OFF_W + k * SX + i] = (k == 0) ? Real(0) : wz[3] + dt * (gam * Gw + zet * gw0);
@@ -435,7 +439,8 @@ RBC_HD void dft6(cx<Real>* x)
 RBC_HD int slot48(int k) { return (k >> 3) + 6 * (k & 7); }
 
 template <typename Real>
-RBC_HD void fft_passA_fwd_div(int item, const Consts<Real>& C, const Real* p, Real* R, const Real* tw48)
+RBC_HD void fft_passA_fwd_div(int item, const Consts<Real>& C, const Real* RBC_RESTRICT p, Real* RBC_RESTRICT R,
+                              const Real* RBC_RESTRICT tw48)
 {
     const int n1 = item >> 6, row = item & 63;
     const Real* pu = p + OFF_U + row * SX;
@@ -494,7 +499,7 @@ RBC_HD void tangle_pair(cx<Real>& xm, cx<Real>& xp, Real c, Real s)
 
 // item = g*64 + row, g = 0..3: column pair (ka, kb) = (0,4) for g = 0, else (g, 8-g)
 template <typename Real>
-RBC_HD void fft_passB_fwd_untangle(int item, Real* R, const Real* tw96)
+RBC_HD void fft_passB_fwd_untangle(int item, Real* RBC_RESTRICT R, const Real* RBC_RESTRICT tw96)
 {
     const int g = item >> 6, row = item & 63;
     const int ka = g, kb = (g == 0) ? 4 : 8 - g;
@@ -528,7 +533,7 @@ RBC_HD void fft_passB_fwd_untangle(int item, Real* R, const Real* tw96)
     for (int k1 = 0; k1 < 6; ++k1) { stc(za + 2 * k1, a[k1]); stc(zb + 2 * k1, b[k1]); }
 }
 template <typename Real>
-RBC_HD void fft_passB_inv_tangle(int item, Real* R, const Real* tw48, const Real* tw96)
+RBC_HD void fft_passB_inv_tangle(int item, Real* RBC_RESTRICT R, const Real* RBC_RESTRICT tw48, const Real* RBC_RESTRICT tw96)
 {
     const int g = item >> 6, row = item & 63;
     const int ka = g, kb = (g == 0) ? 4 : 8 - g;
@@ -564,37 +569,75 @@ RBC_HD void fft_passB_inv_tangle(int item, Real* R, const Real* tw48, const Real
 }
 
 // ------------------------------------------------------------------------------------------
-// phase: tridiagonal solves in z, one thread per spectral word (96 real systems, in place).
+// phase: tridiagonal solves in z, in place, one pair of threads per spectral word (96 real systems)
 //   p(k-1) - (2 + lam dz^2) p(k) + p(k+1) = dz^2 r(k),  p(-1)=p(0), p(NZ)=p(NZ-1)
-// tinv[k][t] = 1/(diag_k - tinv[k-1][t]) precomputed per word; `scale` = dz^2/48 folds the
-// inverse-FFT normalisation.  Rows are processed in blocks of 8 with all loads issued up front so
-// only the 4-cycle FMA chain is serial.
+// Two-sided elimination ("burn at both ends"): thread t sweeps rows 0..31 upward, thread NX+t sweeps
+// rows 63..32 downward, the two meet in a 2x2 system, then both back-substitute outward — half the
+// serial FMA chain of a one-sided Thomas solve, on twice the threads.
+//   tinv[k][t], k < 32 : 1/(diag_k - tinv[k-1][t])   (pivots of the upward sweep)
+//   tinv[k][t], k >= 32: 1/(diag_k - tinv[k+1][t])   (pivots of the downward sweep)
+// `scale` = dz^2/48 folds the inverse-FFT normalisation.  Rows are processed in blocks of 8 with all
+// loads issued up front so only the 4-cycle FMA chain is serial.
 // ------------------------------------------------------------------------------------------
+constexpr int NZH = NZ / 2;
 template <typename Real>
-RBC_HD void phase_thomas(int tid, Real* R, const Real* tinv, Real scale)
+RBC_HD void phase_thomas_sweep(int tid, Real* RBC_RESTRICT R, const Real* RBC_RESTRICT tinv, Real* RBC_RESTRICT mid, Real scale)
 {
-    if (tid >= NX) return;
+    if (tid >= 2 * NX) return;
+    const int t = tid % NX;
+    const bool hi = tid >= NX;
     constexpr int BK = 8;
     Real d = Real(0);
-    for (int kb = 0; kb < NZ; kb += BK) {
+    for (int kb = 0; kb < NZH; kb += BK) {
         Real iv[BK], rs[BK];
         RBC_UNROLL
-        for (int j = 0; j < BK; ++j) { iv[j] = tinv[(kb + j) * NX + tid]; rs[j] = R[(kb + j) * RSTR + tid]; }
+        for (int j = 0; j < BK; ++j) {
+            const int k = hi ? (NZ - 1 - kb - j) : (kb + j);
+            iv[j] = tinv[k * NX + t];
+            rs[j] = R[k * RSTR + t];
+        }
         RBC_UNROLL
         for (int j = 0; j < BK; ++j) rs[j] = rs[j] * scale * iv[j];
         RBC_UNROLL
-        for (int j = 0; j < BK; ++j) { d = rs[j] - d * iv[j]; R[(kb + j) * RSTR + tid] = d; }
+        for (int j = 0; j < BK; ++j) {
+            const int k = hi ? (NZ - 1 - kb - j) : (kb + j);
+            d = rs[j] - d * iv[j];
+            R[k * RSTR + t] = d;
+        }
     }
-    Real pv = d;                                      // p(NZ-1) = d'(NZ-1)
-    for (int kb = NZ - BK; kb >= 0; kb -= BK) {
+    mid[tid] = d;                                     // d'(31) from the upward sweep, e'(32) from the downward one
+}
+template <typename Real>
+RBC_HD void phase_thomas_back(int tid, Real* RBC_RESTRICT R, const Real* RBC_RESTRICT tinv, const Real* RBC_RESTRICT mid)
+{
+    if (tid >= 2 * NX) return;
+    const int t = tid % NX;
+    const bool hi = tid >= NX;
+    constexpr int BK = 8;
+    // p(31) = d - iv31 p(32),  p(32) = e - jv32 p(31)
+    const Real dlo = mid[t], ehi = mid[NX + t], iv31 = tinv[(NZH - 1) * NX + t], jv32 = tinv[NZH * NX + t];
+    const Real p31 = (dlo - iv31 * ehi) / (Real(1) - iv31 * jv32);
+    const Real p32 = ehi - jv32 * p31;
+    Real pv = hi ? p32 : p31;
+    R[(hi ? NZH : NZH - 1) * RSTR + t] = pv;
+    for (int kb = 1; kb < NZH; kb += BK) {            // rows 30..0 (lo) / 33..63 (hi), outward from the middle
         Real iv[BK], dd[BK];
         RBC_UNROLL
-        for (int j = 0; j < BK; ++j) { iv[j] = tinv[(kb + j) * NX + tid]; dd[j] = R[(kb + j) * RSTR + tid]; }
+        for (int j = 0; j < BK; ++j) {
+            const int o = kb + j;                     // distance from the middle row of this half
+            const int k = hi ? (NZH + o) : (NZH - 1 - o);
+            const bool ok = o < NZH;
+            iv[j] = ok ? tinv[k * NX + t] : Real(0);
+            dd[j] = ok ? R[k * RSTR + t] : Real(0);
+        }
         RBC_UNROLL
-        for (int j = BK - 1; j >= 0; --j) {
-            if (kb + j == NZ - 1) continue;
-            pv = dd[j] - iv[j] * pv;
-            R[(kb + j) * RSTR + tid] = pv;
+        for (int j = 0; j < BK; ++j) {
+            const int o = kb + j;
+            const int k = hi ? (NZH + o) : (NZH - 1 - o);
+            if (o < NZH) {
+                pv = dd[j] - iv[j] * pv;
+                R[k * RSTR + t] = pv;
+            }
         }
     }
 }
@@ -603,19 +646,26 @@ RBC_HD void phase_thomas(int tid, Real* R, const Real* tinv, Real scale)
 // phase: pressure correction  u -= d_x phi, w -= d_z phi  (phi = dtau * pNHS in R); strip march
 // ------------------------------------------------------------------------------------------
 template <typename Real>
-RBC_HD void phase_correct(int tid, const Consts<Real>& C, Real* p, const Real* R)
+RBC_HD void phase_correct(int tid, const Consts<Real>& C, Real* RBC_RESTRICT p, const Real* RBC_RESTRICT R)
 {
     const int i = tid % NX, s = tid / NX, im = wrapx(i - 1), k0 = s * RS;
-    Real* pu = p + OFF_U;
-    Real* pw = p + OFF_W;
-    Real below = (k0 >= 1) ? R[(k0 - 1) * RSTR + i] : Real(0);
+    Real* RBC_RESTRICT pu = p + OFF_U;
+    Real* RBC_RESTRICT pw = p + OFF_W;
+    Real ph[RS + 1], pm[RS], uu[RS], ww[RS];
+    ph[0] = (k0 >= 1) ? R[(k0 - 1) * RSTR + i] : Real(0);
+    RBC_UNROLL
+    for (int r = 0; r < RS; ++r) {                      // all loads first: nothing serialises behind a store
+        const int k = k0 + r;
+        ph[r + 1] = R[k * RSTR + i];
+        pm[r] = R[k * RSTR + im];
+        uu[r] = pu[k * SX + i];
+        ww[r] = pw[k * SX + i];
+    }
     RBC_UNROLL
     for (int r = 0; r < RS; ++r) {
         const int k = k0 + r;
-        const Real ph = R[k * RSTR + i];
-        pu[k * SX + i] -= (ph - R[k * RSTR + im]) * C.idx;
-        if (k >= 1) pw[k * SX + i] -= (ph - below) * C.idz;
-        below = ph;
+        pu[k * SX + i] = uu[r] - (ph[r + 1] - pm[r]) * C.idx;
+        if (k >= 1) pw[k * SX + i] = ww[r] - (ph[r + 1] - ph[r]) * C.idz;
     }
 }
 
@@ -627,7 +677,8 @@ RBC_HD void project(const Consts<Real>& C, const Ctx<Real>& X, Real* p, Real sca
 {
     RBC_PHASE(fft_passA_fwd_div(tid, C, p, X.R, X.tw48);)
     RBC_PHASE(if (tid < 4 * NZ) fft_passB_fwd_untangle(tid, X.R, X.tw96);)
-    RBC_PHASE(phase_thomas(tid, X.R, X.tinv, scale);)
+    RBC_PHASE(phase_thomas_sweep(tid, X.R, X.tinv, X.mid, scale);)
+    RBC_PHASE(phase_thomas_back(tid, X.R, X.tinv, X.mid);)
     RBC_PHASE(if (tid < 4 * NZ) fft_passB_inv_tangle(tid, X.R, X.tw48, X.tw96);)
     RBC_PHASE(fft_passA_inv(tid, X.R);)
     RBC_PHASE(phase_correct(tid, C, p, X.R);)
@@ -720,7 +771,9 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
         const Real dt = (sub == F.nsub - 1) ? C.dt_last : C.dt_full;
         for (int stage = 0; stage < 3; ++stage) {
             if (SPLIT) { RBC_PHASE(phase_phy(tid, C, cur + OFF_B, X.R);) }
-            RBC_PHASE((phase_tendency<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, X.gm, dt, gam[stage], zet[stage], stage > 0));)
+            const Real* gin = X.gm + ((stage & 1) ? 0 : NSTATE);      // stage s reads what stage s-1 wrote
+            Real* gout = X.gm + ((stage & 1) ? NSTATE : 0);
+            RBC_PHASE((phase_tendency<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, gin, gout, dt, gam[stage], zet[stage], stage > 0));)
             Real* P;
             if (NXT_GLOBAL) {
                 RBC_PHASE(phase_copy(tid, nxt, cur, NS_SM);)
@@ -858,12 +911,21 @@ inline void build_tables_host(double lx, double lz, double* tinv /*NZ*NX*/, doub
     for (int t = 0; t < NX; ++t) {
         const int m = word_mode(t);
         const double sx = 2.0 * sin(PI * m / NX) / dx, lam = sx * sx * dz * dz;
+        auto diag = [&](int k) {
+            double dg = -(2.0 + lam);
+            if (k == 0 || k == NZ - 1) dg += 1.0;
+            if (m == 0 && k == 0) dg -= 1.0;            // pin the null space of the mean mode
+            return dg;
+        };
         double prev = 0.0;
-        for (int k = 0; k < NZ; ++k) {
-            double diag = -(2.0 + lam);
-            if (k == 0 || k == NZ - 1) diag += 1.0;
-            if (m == 0 && k == 0) diag -= 1.0;          // pin the null space of the mean mode
-            const double iv = 1.0 / (diag - prev);
+        for (int k = 0; k < NZ / 2; ++k) {              // upward sweep pivots
+            const double iv = 1.0 / (diag(k) - prev);
+            tinv[k * NX + t] = iv;
+            prev = iv;
+        }
+        prev = 0.0;
+        for (int k = NZ - 1; k >= NZ / 2; --k) {        // downward sweep pivots
+            const double iv = 1.0 / (diag(k) - prev);
             tinv[k * NX + t] = iv;
             prev = iv;
         }

@@ -43,7 +43,8 @@ struct SmemLayout {
     static constexpr size_t tinv = R + sizeof(Real) * NR;
     static constexpr size_t red = tinv + (kTinvShared ? sizeof(Real) * NZ * NX : 0);
     static constexpr size_t Tb = red + (kNxtGlobal ? sizeof(double) * NRED * NT : 0);
-    static constexpr size_t tw48 = Tb + sizeof(Real) * NX;
+    static constexpr size_t mid = Tb + sizeof(Real) * NX;
+    static constexpr size_t tw48 = mid + sizeof(Real) * 2 * NX;
     static constexpr size_t tw96 = tw48 + sizeof(Real) * 96;
     static constexpr size_t total = tw96 + sizeof(Real) * 96;
     static_assert(total <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
@@ -66,9 +67,10 @@ rbc2d_env_kernel(Consts<Real> C, Tables<Real> T, EnvIO<Real> io, Real* gm_all, R
     X.R = reinterpret_cast<Real*>(smem + L::R);
     X.red = reinterpret_cast<double*>(smem + L::red);
     X.Tb = reinterpret_cast<Real*>(smem + L::Tb);
+    X.mid = reinterpret_cast<Real*>(smem + L::mid);
     X.tw48 = reinterpret_cast<Real*>(smem + L::tw48);
     X.tw96 = reinterpret_cast<Real*>(smem + L::tw96);
-    X.gm = gm_all + (size_t)blockIdx.x * NSTATE;
+    X.gm = gm_all + (size_t)blockIdx.x * 2 * NSTATE;
     if (L::kTinvShared) {
         Real* tv = reinterpret_cast<Real*>(smem + L::tinv);
         for (int q = threadIdx.x; q < NZ * NX; q += NT) tv[q] = T.tinv[q];
@@ -278,7 +280,7 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
         cudaMemset((ptr), 0, (bytes));                                            \
     } while (0)
     ALLOC(s->state, B * NSTATE * rs);
-    ALLOC(s->gm, (size_t)s->grid * NSTATE * rs);
+    ALLOC(s->gm, (size_t)s->grid * 2 * NSTATE * rs);
     if (!f32) ALLOC(s->nxt, (size_t)s->grid * NS_SM * rs);
     if (split) ALLOC(s->pressure, B * 2 * NCELL * rs);
     ALLOC(s->t, B * sizeof(double));

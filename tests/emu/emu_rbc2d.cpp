@@ -18,9 +18,9 @@ static void run(const HostConfig& h, int B, Real* state, const float* actions, f
     std::vector<Real> tinv(tinv_d.begin(), tinv_d.end()), tw48(tw48_d.begin(), tw48_d.end()), tw96(tw96_d.begin(), tw96_d.end());
     Tables<Real> T{tinv.data(), tw48.data(), tw96.data(), (Real)((h.lz / NZ) * (h.lz / NZ) / 48.0)};
     EnvIO<Real> io{state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, pressure};
-    std::vector<Real> s0(NS_SM), s1(NS_SM), R(NR), Tb(NX), gm(NSTATE);
+    std::vector<Real> s0(NS_SM), s1(NS_SM), R(NR), Tb(NX), mid(2 * NX), gm(2 * NSTATE);
     std::vector<double> red(NRED * NT);
-    Ctx<Real> X{s0.data(), s1.data(), R.data(), Tb.data(), tw48.data(), tw96.data(), gm.data(), tinv.data(), red.data()};
+    Ctx<Real> X{s0.data(), s1.data(), R.data(), Tb.data(), mid.data(), tw48.data(), tw96.data(), gm.data(), tinv.data(), red.data()};
     RunFlags F{C.nsub, 0, 1};
     for (int e = 0; e < B; ++e) {
         if (nxt_global) env_action_step<Real, SPLIT, true>(C, T, io, X, e, F);
