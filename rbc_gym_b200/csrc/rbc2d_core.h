@@ -126,6 +126,11 @@ struct RunFlags {
     int advance_clock;   // 1: t += dt_action, step += 1, truncation flag (step_simulation)
 };
 
+template <bool V>
+struct BoolTag {
+    static constexpr bool value = V;
+};
+
 RBC_HD int wrapx(int i) { return i < 0 ? i + NX : (i >= NX ? i - NX : i); }
 
 // ------------------------------------------------------------------------------------------
@@ -170,7 +175,8 @@ RBC_HD Real upwind5(Real vel, const Real* win)
     const bool pos = vel > Real(0);
     const Real x0 = pos ? win[0] : win[5], x1 = pos ? win[1] : win[4], x2 = pos ? win[2] : win[3];
     const Real x3 = pos ? win[3] : win[2], x4 = pos ? win[4] : win[1];
-    const Real phi = (Real(2) * x0 - Real(13) * x1 + Real(47) * x2 + Real(27) * x3 - Real(3) * x4) * Real(1.0 / 60.0);
+    const Real phi = Real(2.0 / 60.0) * x0 - Real(13.0 / 60.0) * x1 + Real(47.0 / 60.0) * x2 + Real(27.0 / 60.0) * x3 -
+                     Real(3.0 / 60.0) * x4;
     return vel * phi;
 }
 template <typename Real>
@@ -178,7 +184,7 @@ RBC_HD Real upwind3(Real vel, const Real* win)
 {
     const bool pos = vel > Real(0);
     const Real x1 = pos ? win[1] : win[4], x2 = pos ? win[2] : win[3], x3 = pos ? win[3] : win[2];
-    return vel * ((-x1 + Real(5) * x2 + Real(2) * x3) * Real(1.0 / 6.0));
+    return vel * (Real(5.0 / 6.0) * x2 + Real(2.0 / 6.0) * x3 - Real(1.0 / 6.0) * x1);
 }
 template <typename Real>
 RBC_HD Real upwind1(Real vel, const Real* win)
@@ -196,7 +202,7 @@ RBC_HD Real upwind_ord(Real vel, const Real* win, int ord)
 template <typename Real>
 RBC_HD Real centred4(Real a, Real b, Real c, Real d)   // values at j-2, j-1, j, j+1
 {
-    return (Real(7) * (b + c) - (a + d)) * Real(1.0 / 12.0);
+    return Real(7.0 / 12.0) * (b + c) - Real(1.0 / 12.0) * (a + d);
 }
 template <typename Real>
 RBC_HD Real centred_ord(Real a, Real b, Real c, Real d, int ord)
@@ -265,26 +271,30 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
 
     // fluxes through the strip's lower boundary (carried afterwards)
     Real Fzb_lo = Real(0), Wu_lo = Real(0), Ww_lo = Real(0);
-    if (k0 >= 1) {
-        const int o = ord_up_face(k0);
-        Fzb_lo = upwind_ord(wz[3], bz, o);
-        Wu_lo = upwind_ord(centred4(wxr[1], wxr[2], wxr[3], wxr[4]), uz, o);
-        const int kc = k0 - 1;
-        Ww_lo = upwind_ord(centred_ord(wz[1], wz[2], wz[3], wz[4], ord_ce_cen(kc)), wz, ord_up_cen(kc));
+    if (k0 >= 1) {                                       // k0 is 16, 32 or 48: full-order stencils
+        Fzb_lo = upwind5(wz[3], bz);
+        Wu_lo = upwind5(centred4(wxr[1], wxr[2], wxr[3], wxr[4]), uz);
+        Ww_lo = upwind5(centred4(wz[1], wz[2], wz[3], wz[4]), wz);
     }
     const Real tb = Tb[i];
 
-    RBC_UNROLL
-    for (int r = 0; r < RS; ++r) {
+    // previous-stage tendencies live in per-CTA global slabs [field][r][tid] (coalesced; one slab is read,
+    // the other written, so loads never alias stores).  They are fetched one row ahead so their L2 latency
+    // hides behind a whole row of arithmetic (stage 1 has zet = 0 and must not read).
+    Real gnb = Real(0), gnu = Real(0), gnw = Real(0);
+    if (use_gm) { gnb = gm_in[(0 * RS) * NT + tid]; gnu = gm_in[(1 * RS) * NT + tid]; gnw = gm_in[(2 * RS) * NT + tid]; }
+
+    // One row of the march.  EDGE = false is the interior fast path (rows 2..60: all stencils at full order,
+    // no wall ghosts) with every order decision resolved at compile time; EDGE = true handles rows
+    // 0, 1, 61, 62, 63 with the wall-order rules.  The choice is uniform across a warp.
+    auto row = [&](auto edge_tag, const int r) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
         const int k = k0 + r;
-        // previous-stage tendencies: per-CTA global slabs [field][r][tid] (coalesced; read one slab, write the
-        // other, so loads never alias stores); issue the loads first
-        // so their L2 latency hides behind this row's arithmetic (stage 1 has zet = 0 and must not read)
-        Real gb0 = Real(0), gu0 = Real(0), gw0 = Real(0);
-        if (use_gm) {
-            gb0 = gm_in[(0 * RS + r) * NT + tid];
-            gu0 = gm_in[(1 * RS + r) * NT + tid];
-            gw0 = gm_in[(2 * RS + r) * NT + tid];
+        const Real gb0 = gnb, gu0 = gnu, gw0 = gnw;
+        if (r + 1 < RS && use_gm) {
+            gnb = gm_in[(0 * RS + r + 1) * NT + tid];
+            gnu = gm_in[(1 * RS + r + 1) * NT + tid];
+            gnw = gm_in[(2 * RS + r + 1) * NT + tid];
         }
         Real bx[7], ux[7], wxn[7];
         RBC_UNROLL
@@ -293,13 +303,18 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
             ux[j] = (j == 3) ? uz[3] : ((j == 4) ? u1z[2] : cu[k * SX + col[j]]);
             wxn[j] = (j == 3) ? wz[4] : cw[(k + 1) * SX + col[j]];      // face k+1 <= NZ always valid
         }
-        const bool top = (k == NZ - 1);
+        const bool top = EDGE && (k == NZ - 1);
+        const bool bot = EDGE && (k == 0);
+        const int o_face_hi = EDGE ? ord_up_face(k + 1) : 5;
+        const int o_ce_face = EDGE ? ord_ce_face(k) : 4;
+        const int o_up_cen = EDGE ? ord_up_cen(k) : 5;
+        const int o_ce_cen = EDGE ? ord_ce_cen(k) : 4;
 
         // ---- tracer ----
         const Real Fx0 = upwind5(ux[3], bx);
         const Real Fx1 = upwind5(ux[4], bx + 1);
-        const Real Fzb_hi = top ? Real(0) : upwind_ord(wz[4], bz + 1, ord_up_face(k + 1));
-        const Real bdn = (k == 0) ? (Real(2) * tb - bz[3]) : bz[2];
+        const Real Fzb_hi = top ? Real(0) : upwind_ord(wz[4], bz + 1, o_face_hi);
+        const Real bdn = bot ? (Real(2) * tb - bz[3]) : bz[2];
         const Real bup = top ? (Real(2) * C.b_top - bz[3]) : bz[4];
         const Real Gb = -((Fx1 - Fx0) * C.idx + (Fzb_hi - Fzb_lo) * C.idz) +
                         C.kappa * ((bx[4] - Real(2) * bx[3] + bx[2]) * C.idx2 + (bup - Real(2) * bz[3] + bdn) * C.idz2);
@@ -307,25 +322,23 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         // ---- u ----
         const Real F0 = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);          // centre i-1
         const Real F1 = upwind5(centred4(ux[2], ux[3], ux[4], ux[5]), ux + 1);      // centre i
-        const Real Wu_hi = top ? Real(0)
-                               : upwind_ord(centred4(wxn[1], wxn[2], wxn[3], wxn[4]), uz + 1, ord_up_face(k + 1));
-        const Real udn = (k == 0) ? -uz[3] : uz[2];
+        const Real Wu_hi = top ? Real(0) : upwind_ord(centred4(wxn[1], wxn[2], wxn[3], wxn[4]), uz + 1, o_face_hi);
+        const Real udn = bot ? -uz[3] : uz[2];
         const Real uup = top ? -uz[3] : uz[4];
         Real Gu = -((F1 - F0) * C.idx + (Wu_hi - Wu_lo) * C.idz) +
                   C.nu * ((ux[4] - Real(2) * ux[3] + ux[2]) * C.idx2 + (uup - Real(2) * uz[3] + udn) * C.idz2);
         if (SPLIT) Gu -= (phy[k * RSTR + i] - phy[k * RSTR + col[2]]) * C.idx;
 
         // ---- w (face k; face 0 is the wall) ----
-        const int oc = ord_ce_face(k);
-        const Real ut0 = centred_ord(uz[1], uz[2], uz[3], uz[4], oc);               // x-face i,   z-face k
-        const Real ut1 = centred_ord(u1z[0], u1z[1], u1z[2], u1z[3], oc);           // x-face i+1, z-face k
+        const Real ut0 = centred_ord(uz[1], uz[2], uz[3], uz[4], o_ce_face);        // x-face i,   z-face k
+        const Real ut1 = centred_ord(u1z[0], u1z[1], u1z[2], u1z[3], o_ce_face);    // x-face i+1, z-face k
         const Real Fw0 = upwind5(ut0, wxr);
         const Real Fw1 = upwind5(ut1, wxr + 1);
-        const Real Ww_hi = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], ord_ce_cen(k)), wz + 1, ord_up_cen(k));
+        const Real Ww_hi = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen), wz + 1, o_up_cen);
         Real Gw = -((Fw1 - Fw0) * C.idx + (Ww_hi - Ww_lo) * C.idz) +
                   C.nu * ((wxr[4] - Real(2) * wxr[3] + wxr[2]) * C.idx2 + (wz[4] - Real(2) * wz[3] + wz[2]) * C.idz2);
         if (!SPLIT) Gw += Real(0.5) * (bz[2] + bz[3]);
-        if (k == 0) Gw = Real(0);
+        if (bot) Gw = Real(0);
 
         // ---- RK3 substep ----
         gm_out[(0 * RS + r) * NT + tid] = Gb;
@@ -333,7 +346,7 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         gm_out[(2 * RS + r) * NT + tid] = Gw;
         n[OFF_B + k * SX + i] = bz[3] + dt * (gam * Gb + zet * gb0);
         n[OFF_U + k * SX + i] = uz[3] + dt * (gam * Gu + zet * gu0);
-        n[OFF_W + k * SX + i] = (k == 0) ? Real(0) : wz[3] + dt * (gam * Gw + zet * gw0);
+        n[OFF_W + k * SX + i] = bot ? Real(0) : wz[3] + dt * (gam * Gw + zet * gw0);
 
         // ---- slide ----
         Fzb_lo = Fzb_hi; Wu_lo = Wu_hi; Ww_lo = Ww_hi;
@@ -347,6 +360,17 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         u1z[3] = (k + 2 < NZ) ? cu[(k + 2) * SX + col[4]] : Real(0);
         RBC_UNROLL
         for (int j = 0; j < 7; ++j) wxr[j] = wxn[j];
+    };
+
+    RBC_UNROLL
+    for (int r = 0; r < RS; ++r) {
+        if (r >= 2 && r < RS - 3) {
+            row(BoolTag<false>{}, r);                         // rows that are interior in every strip
+        } else {
+            const bool edge = (r < 2) ? (s == 0) : (s == NSTRIP - 1);
+            if (edge) row(BoolTag<true>{}, r);
+            else row(BoolTag<false>{}, r);
+        }
     }
     if (s == NSTRIP - 1) n[OFF_W + NZ * SX + i] = Real(0);       // top wall face
 }
@@ -587,23 +611,20 @@ RBC_HD void phase_thomas_sweep(int tid, Real* RBC_RESTRICT R, const Real* RBC_RE
     const int t = tid % NX;
     const bool hi = tid >= NX;
     constexpr int BK = 8;
+    // row k = k_first + step*n, n = 0..31: pointer + signed stride instead of per-element selects
+    const int sgn = hi ? -1 : 1;
+    Real* RBC_RESTRICT pr = R + (hi ? (NZ - 1) * RSTR : 0) + t;
+    const Real* RBC_RESTRICT pt = tinv + (hi ? (NZ - 1) * NX : 0) + t;
+    const int sr = sgn * RSTR, st = sgn * NX;
     Real d = Real(0);
     for (int kb = 0; kb < NZH; kb += BK) {
         Real iv[BK], rs[BK];
         RBC_UNROLL
-        for (int j = 0; j < BK; ++j) {
-            const int k = hi ? (NZ - 1 - kb - j) : (kb + j);
-            iv[j] = tinv[k * NX + t];
-            rs[j] = R[k * RSTR + t];
-        }
+        for (int j = 0; j < BK; ++j) { iv[j] = pt[(kb + j) * st]; rs[j] = pr[(kb + j) * sr]; }
         RBC_UNROLL
         for (int j = 0; j < BK; ++j) rs[j] = rs[j] * scale * iv[j];
         RBC_UNROLL
-        for (int j = 0; j < BK; ++j) {
-            const int k = hi ? (NZ - 1 - kb - j) : (kb + j);
-            d = rs[j] - d * iv[j];
-            R[k * RSTR + t] = d;
-        }
+        for (int j = 0; j < BK; ++j) { d = rs[j] - d * iv[j]; pr[(kb + j) * sr] = d; }
     }
     mid[tid] = d;                                     // d'(31) from the upward sweep, e'(32) from the downward one
 }
@@ -619,24 +640,25 @@ RBC_HD void phase_thomas_back(int tid, Real* RBC_RESTRICT R, const Real* RBC_RES
     const Real p31 = (dlo - iv31 * ehi) / (Real(1) - iv31 * jv32);
     const Real p32 = ehi - jv32 * p31;
     Real pv = hi ? p32 : p31;
-    R[(hi ? NZH : NZH - 1) * RSTR + t] = pv;
-    for (int kb = 1; kb < NZH; kb += BK) {            // rows 30..0 (lo) / 33..63 (hi), outward from the middle
+    // row k = k_mid + step*o, o = distance from the middle row of this half (outward)
+    const int sgn = hi ? 1 : -1;
+    Real* RBC_RESTRICT pr = R + (hi ? NZH : NZH - 1) * RSTR + t;
+    const Real* RBC_RESTRICT pt = tinv + (hi ? NZH : NZH - 1) * NX + t;
+    const int sr = sgn * RSTR, st = sgn * NX;
+    pr[0] = pv;
+    for (int kb = 1; kb < NZH; kb += BK) {            // rows 30..0 (lo) / 33..63 (hi)
         Real iv[BK], dd[BK];
         RBC_UNROLL
         for (int j = 0; j < BK; ++j) {
-            const int o = kb + j;                     // distance from the middle row of this half
-            const int k = hi ? (NZH + o) : (NZH - 1 - o);
-            const bool ok = o < NZH;
-            iv[j] = ok ? tinv[k * NX + t] : Real(0);
-            dd[j] = ok ? R[k * RSTR + t] : Real(0);
+            const bool ok = kb + j < NZH;
+            iv[j] = ok ? pt[(kb + j) * st] : Real(0);
+            dd[j] = ok ? pr[(kb + j) * sr] : Real(0);
         }
         RBC_UNROLL
         for (int j = 0; j < BK; ++j) {
-            const int o = kb + j;
-            const int k = hi ? (NZH + o) : (NZH - 1 - o);
-            if (o < NZH) {
+            if (kb + j < NZH) {
                 pv = dd[j] - iv[j] * pv;
-                R[k * RSTR + t] = pv;
+                pr[(kb + j) * sr] = pv;
             }
         }
     }
