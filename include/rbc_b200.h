@@ -57,6 +57,20 @@ typedef struct rbc2d_config {
     int32_t device;          /* CUDA device ordinal                                                    */
 } rbc2d_config;
 
+/* Wrappers fused into the step epilogue (src/rbc_gym/wrappers/), applied in the order of
+ * example/run_wrapped.py:15-19: RBCNormalizeObservation -> RBCNormalizeReward -> RBCRewardShaping. */
+typedef struct rbc2d_wrappers {
+    int32_t normalize_obs;   /* rbc_normalize_observation.py:64-74: maxval*(2(obs-lo)/(hi-lo)-1) on channels 0..3   */
+    int32_t obs_clip;        /* clip to [-maxval, maxval]                                                        */
+    float obs_lo[4];         /* [1, -u_limit, -u_limit, -u_limit]                                                */
+    float obs_hi[4];         /* [2 + heater_limit, u_limit, u_limit, u_limit]                                    */
+    float obs_maxval;
+    int32_t normalize_reward; /* rbc_normalize_reward.py:27-32: (r + s)/(s - 1)                                   */
+    double reward_scale;     /* s = 0.1 * Ra^0.4 in 2D                                                           */
+    int32_t shaping;         /* rbc_reward_shaping.py:53-140: r <- (1-w) r + w (pi - cell_dist)/pi               */
+    double shaping_weight;
+} rbc2d_wrappers;
+
 typedef struct rbc2d_sim rbc2d_sim;
 
 int rbc_abi_version(void);
@@ -98,6 +112,11 @@ int rbc2d_step_dev(rbc2d_sim* sim, const float* actions_dev, float* obs_dev, flo
                    double* nu_obs_dev, int32_t* truncated_dev, int32_t* nan_dev);
 int rbc2d_step_host(rbc2d_sim* sim, const float* actions_host, float* obs_host, float* reward_host, double* nu_state_host,
                     double* nu_obs_host, int32_t* truncated_host, int32_t* nan_host);
+
+/* Enable/disable the fused wrappers (NULL = all off).  Takes effect from the next step/observe. */
+int rbc2d_set_wrappers(rbc2d_sim* sim, const rbc2d_wrappers* w);
+/* info["cell_dist"] of the last step (rbc_reward_shaping.py:61-66), [B] float64. */
+int rbc2d_get_cell_dist_host(rbc2d_sim* sim, double* out_host);
 
 /* get_observation / get_nusselt without stepping (what reset() returns). */
 int rbc2d_observe_dev(rbc2d_sim* sim, float* obs_dev, double* nu_state_dev, double* nu_obs_dev);

@@ -39,13 +39,24 @@ class Rbc2dConfig(C.Structure):
     ]
 
 
+class Rbc2dWrappers(C.Structure):
+    """Mirror of ``rbc2d_wrappers`` (include/rbc_b200.h)."""
+
+    _fields_ = [
+        ("normalize_obs", C.c_int32), ("obs_clip", C.c_int32),
+        ("obs_lo", C.c_float * 4), ("obs_hi", C.c_float * 4), ("obs_maxval", C.c_float),
+        ("normalize_reward", C.c_int32), ("reward_scale", C.c_double),
+        ("shaping", C.c_int32), ("shaping_weight", C.c_double),
+    ]
+
+
 # every symbol include/rbc_b200.h declares; tests check that the built library exports them all
 ABI_SYMBOLS = (
     "rbc_abi_version", "rbc_last_error", "rbc2d_create", "rbc2d_destroy", "rbc2d_set_stream", "rbc2d_num_envs",
     "rbc2d_state_values_per_env", "rbc2d_load_checkpoints", "rbc2d_reset_from_checkpoints_dev",
     "rbc2d_reset_from_fields_host", "rbc2d_step_dev", "rbc2d_step_host", "rbc2d_observe_dev", "rbc2d_observe_host",
     "rbc2d_get_state_dev", "rbc2d_get_state_host", "rbc2d_get_fields_host", "rbc2d_get_info_host",
-    "rbc2d_launch_count", "rbc2d_last_step_kernel_ms",
+    "rbc2d_launch_count", "rbc2d_last_step_kernel_ms", "rbc2d_set_wrappers", "rbc2d_get_cell_dist_host",
 )
 
 _lib = None
@@ -94,6 +105,8 @@ def load_library(build_if_missing: bool = True):
     L.rbc2d_get_state_host.argtypes = [vp, vp, ip]
     L.rbc2d_get_fields_host.argtypes = [vp, vp]
     L.rbc2d_get_info_host.argtypes = [vp, vp, vp]
+    L.rbc2d_set_wrappers.argtypes = [vp, C.POINTER(Rbc2dWrappers)]
+    L.rbc2d_get_cell_dist_host.argtypes = [vp, vp]
     L.rbc2d_launch_count.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ip), C.POINTER(ip)]
     L.rbc2d_last_step_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     if L.rbc_abi_version() != 1:
@@ -252,6 +265,30 @@ class Sim2D:
             return {k: np.zeros(s, d) for k, (s, d) in shapes.items()}
         t = self.torch
         return {k: t.zeros(s, dtype=getattr(t, np.dtype(d).name)).pin_memory().numpy() for k, (s, d) in shapes.items()}
+
+    def set_wrappers(self, *, normalize_obs: bool = False, u_limit: float = 1.3, maxval: float = 1.0, clip: bool = False,
+                     normalize_reward: bool = False, shaping_weight: Optional[float] = None):
+        """Fuse the reference wrappers into the step epilogue (`src/rbc_gym/wrappers/`), in the order of
+        `example/run_wrapped.py`: RBCNormalizeObservation -> RBCNormalizeReward -> RBCRewardShaping."""
+        w = Rbc2dWrappers()
+        w.normalize_obs, w.obs_clip, w.obs_maxval = int(normalize_obs), int(clip), float(maxval)
+        lo = [1.0, -u_limit, -u_limit, -u_limit]                       # rbc_normalize_observation.py:45-57
+        hi = [2.0 + self.cfg.heater_limit, u_limit, u_limit, u_limit]
+        for c in range(4):
+            w.obs_lo[c], w.obs_hi[c] = lo[c], hi[c]
+        w.normalize_reward = int(normalize_reward)
+        w.reward_scale = 0.1 * self.ra ** 0.4                          # rbc_normalize_reward.py:19-25 (2D)
+        w.shaping = int(shaping_weight is not None)
+        w.shaping_weight = float(shaping_weight or 0.0)
+        self._check(self._L.rbc2d_set_wrappers(self._h, C.byref(w)))
+        self.wrappers = w
+
+    def cell_dist(self) -> np.ndarray:
+        """`info["cell_dist"]` of the last step (`rbc_reward_shaping.py:61-66`), `[B]` float64."""
+        out = np.empty(self.B, np.float64)
+        self._use_current_stream()
+        self._check(self._L.rbc2d_get_cell_dist_host(self._h, _np_ptr(out)))
+        return out
 
     def observe(self):
         """`get_observation` + `get_nusselt` of the current state without stepping."""

@@ -77,6 +77,14 @@ struct Consts {
     double kappa_d, dt_action, episode_length;
     int obs_nz, obs_nx;          // sensors (8, 48)
     int channels;                // 3, or 5 with pressure
+    // wrappers fused into the epilogue (src/rbc_gym/wrappers/), applied in the order of example/run_wrapped.py:
+    // RBCNormalizeObservation -> RBCNormalizeReward -> RBCRewardShaping
+    int wrap_obs, obs_clip;      // rbc_normalize_observation.py:64-74
+    float obs_lo[4], obs_hi[4], obs_maxval;
+    int wrap_reward;             // rbc_normalize_reward.py:27-32: (r + s)/(s - 1)
+    double reward_scale;
+    int wrap_shaping;            // rbc_reward_shaping.py:53-140: (1-w) r + w (pi - cd)/pi
+    double shaping_weight;
 };
 
 // tables in global memory, staged to shared memory by the CTA
@@ -102,6 +110,7 @@ struct EnvIO {
     int* truncated;           // [B]
     int* nan_flag;            // [B]
     Real* pressure;           // [B][2][NZ][NX] (pHY', pNHS) or nullptr
+    double* cell_dist;        // [B] Benard-cell distance (info["cell_dist"]) or nullptr
 };
 
 // everything one CTA needs while it owns an environment
@@ -770,6 +779,53 @@ RBC_HD void phase_store_state(int tid, const Real* sm, Real* g)
 }
 
 // ------------------------------------------------------------------------------------------
+// RBCRewardShaping.compute_cell_distances (rbc_reward_shaping.py:86-140) on the mid-height row of w:
+// scipy.signal.find_peaks(uy, height=1e-3) (strict local maxima, plateaus -> midpoint, end points never
+// peaks), then for every pair of peaks the periodic distance on linspace(0, 2 pi, NX, endpoint=False), set to
+// 0 when uy > 0 everywhere between the two peaks; result = max over pairs (0 with fewer than 2 peaks).
+// Serial (one thread): ~NX steps, negligible next to an action step.
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+RBC_HD double cell_distance(const Real* uy)
+{
+    const double PI = 3.14159265358979323846;
+    int peaks[NX / 2 + 1];
+    int np = 0;
+    int i = 1;
+    const int imax = NX - 1;
+    while (i < imax) {
+        if (uy[i - 1] < uy[i]) {
+            int ahead = i + 1;
+            while (ahead < imax && uy[ahead] == uy[i]) ++ahead;
+            if (uy[ahead] < uy[i]) {
+                const int mid = (i + ahead - 1) / 2;
+                if ((double)uy[mid] >= 0.001) peaks[np++] = mid;
+                i = ahead;
+            }
+        }
+        ++i;
+    }
+    if (np <= 1) return 0.0;
+    double best = 0.0;
+    for (int a = 0; a < np; ++a)
+        for (int b = a + 1; b < np; ++b) {
+            const double xa = peaks[a] * (2 * PI / NX), xb = peaks[b] * (2 * PI / NX);
+            const double d1 = fabs(xb - xa), d2 = 2 * PI - d1;
+            double d = d1 < d2 ? d1 : d2;
+            bool pos = true;
+            if (d1 < d2) {
+                for (int q = peaks[a]; q < peaks[b]; ++q) pos = pos && (uy[q] > Real(0));
+            } else {
+                for (int q = peaks[b]; q < NX; ++q) pos = pos && (uy[q] > Real(0));
+                for (int q = 0; q < peaks[a]; ++q) pos = pos && (uy[q] > Real(0));
+            }
+            if (pos) d = 0.0;
+            if (d > best) best = d;
+        }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------
 // one action step of one environment (the whole of step_simulation + observation + reward)
 // ------------------------------------------------------------------------------------------
 template <typename Real, bool SPLIT, bool NXT_GLOBAL>
@@ -839,12 +895,25 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
         for (int q = tid; q < 3 * nobs; q += NT) {
             const int ch = q / nobs, zo = (q % nobs) / C.obs_nx, xo = q % C.obs_nx;
             const int off = (ch == 0 ? OFF_B : (ch == 1 ? OFF_U : OFF_W));
-            ob[q] = (float)cur[off + (zo * oz) * SX + xo * ox];
+            float v = (float)cur[off + (zo * oz) * SX + xo * ox];
+            if (C.wrap_obs) {
+                v = C.obs_maxval * (2.0f * (v - C.obs_lo[ch]) / (C.obs_hi[ch] - C.obs_lo[ch]) - 1.0f);
+                if (C.obs_clip) v = fminf(fmaxf(v, -C.obs_maxval), C.obs_maxval);
+            }
+            ob[q] = v;
         }
         if (tid == 0) {
+            double rew = -nu_o;                                        // rbc2D.py:198-200
+            if (C.wrap_reward) rew = (rew + C.reward_scale) / (C.reward_scale - 1.0);
+            if (C.wrap_shaping || io.cell_dist != nullptr) {
+                const double PI = 3.14159265358979323846;
+                const double cd = cell_distance(cur + OFF_W + (NZ / 2 - 1) * SX);
+                if (io.cell_dist != nullptr) io.cell_dist[env] = cd;
+                if (C.wrap_shaping) rew = (1.0 - C.shaping_weight) * rew + C.shaping_weight * ((PI - cd) / PI);
+            }
             io.nu_state[env] = nu_s;
             io.nu_obs[env] = nu_o;
-            io.reward[env] = (float)(-nu_o);
+            io.reward[env] = (float)rew;
             io.nan_flag[env] = fin[6] > 0 ? 1 : 0;
             if (F.advance_clock) {
                 const double tn = io.t[env] + C.dt_action;
@@ -902,8 +971,17 @@ struct HostConfig {
     double ra, pr, lx, lz, b_top, heater_limit, dt_action, dt_solver, episode_length;
     int heaters, obs_nz, obs_nx, channels;
 };
+// optional fused wrappers (all off by default)
+struct HostWrappers {
+    int normalize_obs = 0, obs_clip = 0;
+    float obs_lo[4] = {0, 0, 0, 0}, obs_hi[4] = {1, 1, 1, 1}, obs_maxval = 1.0f;
+    int normalize_reward = 0;
+    double reward_scale = 2.0;
+    int shaping = 0;
+    double shaping_weight = 0.0;
+};
 template <typename Real>
-inline Consts<Real> make_consts(const HostConfig& h)
+inline Consts<Real> make_consts(const HostConfig& h, const HostWrappers& w = HostWrappers())
 {
     Consts<Real> C;
     const double dx = h.lx / NX, dz = h.lz / NZ;
@@ -917,6 +995,10 @@ inline Consts<Real> make_consts(const HostConfig& h)
     C.heaters = h.heaters; C.heater_limit = h.heater_limit; C.lx = h.lx; C.dx = dx;
     C.kappa_d = kappa; C.dt_action = h.dt_action; C.episode_length = h.episode_length;
     C.obs_nz = h.obs_nz; C.obs_nx = h.obs_nx; C.channels = h.channels;
+    C.wrap_obs = w.normalize_obs; C.obs_clip = w.obs_clip; C.obs_maxval = w.obs_maxval;
+    for (int c = 0; c < 4; ++c) { C.obs_lo[c] = w.obs_lo[c]; C.obs_hi[c] = w.obs_hi[c]; }
+    C.wrap_reward = w.normalize_reward; C.reward_scale = w.reward_scale;
+    C.wrap_shaping = w.shaping; C.shaping_weight = w.shaping_weight;
     return C;
 }
 // mode index of spectral word t of a row after fft_untangle

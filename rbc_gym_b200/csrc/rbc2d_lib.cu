@@ -144,6 +144,8 @@ __global__ void rbc2d_get_fields_kernel(const Real* state, double* out, size_t t
 struct rbc2d_sim {
     rbc2d_config cfg;
     HostConfig hc;
+    HostWrappers wr;
+    double* cell_dist = nullptr;
     int B = 0, channels = 3, grid = 0, n_ep = 0;
     size_t smem = 0, real_size = 4;
     cudaStream_t stream = nullptr;
@@ -191,7 +193,7 @@ template <typename Real, bool SPLIT>
 static int launch_env(rbc2d_sim* s, const float* actions, float* obs, float* reward, double* nu_s, double* nu_o, int* trunc,
                       int* nan, const int* env_ids, int n, RunFlags F, bool time_it)
 {
-    Consts<Real> C = make_consts<Real>(s->hc);
+    Consts<Real> C = make_consts<Real>(s->hc, s->wr);
     Tables<Real> T{(const Real*)s->tinv, (const Real*)s->tw48, (const Real*)s->tw96,
                    (Real)((s->hc.lz / NZ) * (s->hc.lz / NZ) / 48.0)};
     EnvIO<Real> io;
@@ -206,6 +208,7 @@ static int launch_env(rbc2d_sim* s, const float* actions, float* obs, float* rew
     io.truncated = trunc ? trunc : s->trunc;
     io.nan_flag = nan ? nan : s->nan;
     io.pressure = (Real*)s->pressure;
+    io.cell_dist = s->cell_dist;
     const int grid = n < s->grid ? n : s->grid;
     if (grid <= 0) return 0;
     if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
@@ -292,6 +295,7 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
     ALLOC(s->obs, B * nobs * sizeof(float));
     ALLOC(s->reward, B * sizeof(float));
     ALLOC(s->actions, B * (size_t)cfg->heaters * sizeof(float));
+    ALLOC(s->cell_dist, B * sizeof(double));
 #undef ALLOC
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
         rbc2d_destroy(s);
@@ -306,7 +310,7 @@ int rbc2d_destroy(rbc2d_sim* s)
     if (!s) return 0;
     cudaSetDevice(s->cfg.device);
     void* ptrs[] = {s->state, s->gm, s->nxt, s->pressure, s->tinv, s->tw48, s->tw96, s->bank, s->t, s->nu_s, s->nu_o,
-                    s->step, s->trunc, s->nan, s->obs, s->reward, s->actions};
+                    s->step, s->trunc, s->nan, s->obs, s->reward, s->actions, s->cell_dist};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -417,6 +421,32 @@ int rbc2d_step_host(rbc2d_sim* s, const float* actions, float* obs, float* rewar
     if (nu_o) CK(cudaMemcpyAsync(nu_o, s->nu_o, B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (trunc) CK(cudaMemcpyAsync(trunc, s->trunc, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     if (nan) CK(cudaMemcpyAsync(nan, s->nan, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int rbc2d_set_wrappers(rbc2d_sim* s, const rbc2d_wrappers* w)
+{
+    if (!s) return fail("null handle");
+    s->wr = HostWrappers();
+    if (!w) return 0;
+    if (w->normalize_obs) {
+        for (int c = 0; c < 4; ++c)
+            if (!(w->obs_hi[c] > w->obs_lo[c])) return fail("rbc2d_set_wrappers: obs_hi must exceed obs_lo");
+    }
+    if (w->normalize_reward && w->reward_scale == 1.0) return fail("rbc2d_set_wrappers: reward_scale must differ from 1");
+    s->wr.normalize_obs = w->normalize_obs; s->wr.obs_clip = w->obs_clip; s->wr.obs_maxval = w->obs_maxval;
+    for (int c = 0; c < 4; ++c) { s->wr.obs_lo[c] = w->obs_lo[c]; s->wr.obs_hi[c] = w->obs_hi[c]; }
+    s->wr.normalize_reward = w->normalize_reward; s->wr.reward_scale = w->reward_scale;
+    s->wr.shaping = w->shaping; s->wr.shaping_weight = w->shaping_weight;
+    return 0;
+}
+
+int rbc2d_get_cell_dist_host(rbc2d_sim* s, double* out)
+{
+    if (!s || !out) return fail("rbc2d_get_cell_dist_host: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpyAsync(out, s->cell_dist, s->B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return 0;
 }

@@ -1,0 +1,155 @@
+"""The reference's wrappers (`src/rbc_gym/wrappers/`) for the single-environment API, plus the pure functions
+they are made of.  The batched/vector path applies the same arithmetic fused into the CUDA step epilogue
+(`Sim2D.set_wrappers`); these classes are the drop-in for code that wraps one `gym.Env`."""
+from __future__ import annotations
+
+import logging
+from typing import Any, Dict, Tuple
+
+import numpy as np
+
+from . import spaces
+from .envs.rbc2d import RBCField
+
+
+# --------------------------------------------------------------------------------------- pure functions
+def find_peaks_height(x: np.ndarray, height: float) -> np.ndarray:
+    """`scipy.signal.find_peaks(x, height=height)[0]` without scipy: strict local maxima, plateaus give their
+    midpoint, the first and last samples are never peaks."""
+    x = np.asarray(x)
+    peaks, i, imax = [], 1, len(x) - 1
+    while i < imax:
+        if x[i - 1] < x[i]:
+            ahead = i + 1
+            while ahead < imax and x[ahead] == x[i]:
+                ahead += 1
+            if x[ahead] < x[i]:
+                mid = (i + ahead - 1) // 2
+                if x[mid] >= height:
+                    peaks.append(mid)
+                i = ahead
+        i += 1
+    return np.asarray(peaks, dtype=np.int64)
+
+
+def cell_distance(state: np.ndarray, size_state=(64, 96), use_avg: bool = False) -> float:
+    """`RBCRewardShaping.compute_cell_distances` (`rbc_reward_shaping.py:86-140`)."""
+    if use_avg:
+        uy = state[RBCField.UY].mean(axis=0)
+    else:
+        uy = state[RBCField.UY][int(size_state[0] / 2) - 1]
+    peaks = find_peaks_height(uy, 0.001)
+    domain_x = np.linspace(0, 2 * np.pi, size_state[1], endpoint=False)
+    if len(peaks) <= 1:
+        return 0
+    distances = []
+    for i in range(len(peaks)):
+        for j in range(i + 1, len(peaks)):
+            dist1 = np.abs(domain_x[peaks[j]] - domain_x[peaks[i]])
+            dist2 = 2 * np.pi - dist1
+            d = min(dist1, dist2)
+            if dist1 < dist2:
+                if np.all(uy[peaks[i]:peaks[j]] > 0):
+                    d = 0
+            else:
+                if np.all(uy[peaks[j]:] > 0) and np.all(uy[:peaks[i]] > 0):
+                    d = 0
+            distances.append(d)
+    return float(np.max(distances))
+
+
+def shape_reward(reward: float, cell_distances: float, w: float) -> float:
+    """`RBCRewardShaping.__apply_reward_shaping` (`rbc_reward_shaping.py:68-84`)."""
+    return (1 - w) * reward + w * ((-cell_distances + np.pi) / np.pi)
+
+
+def normalize_reward(reward: float, ra: float, dims: int = 2) -> float:
+    """`RBCNormalizeReward.reward` (`rbc_normalize_reward.py:6-32`): Nu ~ s Ra^a, 2D s=0.1 a=0.4, 3D s=0.22 a=0.27."""
+    s, a = (0.1, 0.4) if dims == 2 else (0.22, 0.27)
+    scale = s * (ra ** a)
+    return (reward + scale) / (scale - 1)
+
+
+def normalize_observation(obs: np.ndarray, heater_limit: float, temperature_difference=(1, 2), maxval=1, u_limit=1.3,
+                          clip: bool = False) -> np.ndarray:
+    """`RBCNormalizeObservation.observation` (`rbc_normalize_observation.py:64-74`); modifies and returns `obs`."""
+    min_vals = [temperature_difference[0], -u_limit, -u_limit, -u_limit]
+    max_vals = [temperature_difference[1] + heater_limit, u_limit, u_limit, u_limit]
+    for c in range(obs.shape[0]):
+        obs[c] = maxval * (2 * (obs[c] - min_vals[c]) / (max_vals[c] - min_vals[c]) - 1)
+    if clip:
+        obs = np.clip(obs, -maxval, maxval)
+    return obs
+
+
+# --------------------------------------------------------------------------------------- wrapper classes
+class RBCNormalizeObservation(spaces.ObservationWrapper):
+    """Normalize the observation to approximately lie in range [-1, 1] (`rbc_normalize_observation.py:10-81`)."""
+
+    def __init__(self, env, heater_limit: float, maxval: int = 1, u_limit: int | None = 1.3, eps: float = 0.3, clip: bool = False):
+        spaces.ObservationWrapper.__init__(self, env)
+        self.heater_limit, self.clip, self.maxval, self.excursion_eps = heater_limit, clip, maxval, eps
+        T = env.unwrapped.temperature_difference
+        if u_limit is None:
+            if getattr(env.unwrapped, "is_3d", False):
+                u_limit = self._get_u_limit_3d(env.unwrapped.ra)
+            else:
+                raise ValueError("u_limit must be provided for 2D RBC.")
+        self.min_vals = [T[0], -u_limit, -u_limit, -u_limit]
+        self.max_vals = [T[1] + heater_limit, u_limit, u_limit, u_limit]
+        limit = maxval * (1 + eps)
+        self.observation_space = spaces.Box(low=-limit, high=limit, shape=env.observation_space.shape, dtype=np.float32)
+
+    def observation(self, obs) -> Any:
+        for c in range(obs.shape[0]):
+            obs[c] = self.maxval * (2 * (obs[c] - self.min_vals[c]) / (self.max_vals[c] - self.min_vals[c]) - 1)
+        if self.clip:
+            obs = np.clip(obs, -self.maxval, self.maxval)
+        if np.any(np.abs(obs) > (1 + self.excursion_eps) * self.maxval):
+            print(f"Warning: observation exceeds maxval {self.maxval}, namely: {np.max(np.abs(obs))} is the max observed value.")
+        return obs
+
+    @staticmethod
+    def _get_u_limit_3d(ra):
+        w_inf, Ra_c, n = 0.96549382, 654.37063331, 1.06741877      # rbc_normalize_observation.py:77-81
+        return w_inf * ra ** n / (ra ** n + Ra_c ** n)
+
+
+class RBCNormalizeReward(spaces.RewardWrapper):
+    """Normalize the reward to ~[0, 1] (`rbc_normalize_reward.py:6-32`)."""
+
+    def __init__(self, env):
+        spaces.RewardWrapper.__init__(self, env)
+        ra = env.unwrapped.ra
+        s, a = (0.22, 0.27) if getattr(env.unwrapped, "is_3d", False) else (0.1, 0.4)
+        self.scale = s * (ra ** a)
+
+    def reward(self, reward):
+        return (reward + self.scale) / (self.scale - 1)
+
+
+class RBCRewardShaping(spaces.Wrapper):
+    """Shape the reward with the distance of the Benard cells (`rbc_reward_shaping.py:10-155`; the matplotlib
+    debug plotting of the reference is not reproduced)."""
+
+    def __init__(self, env, shaping_weight: float, debug_cell_dist: bool = False):
+        spaces.Wrapper.__init__(self, env)
+        self.logger = logging.getLogger(__name__)
+        self.shaping_weight = shaping_weight
+        self.debug_cell_dist = debug_cell_dist
+        self.size_state = env.unwrapped.state_shape
+
+    def reset(self, seed: int | None = None, options: Dict[str, Any] | None = None) -> Tuple[Any, Dict[str, Any]]:
+        return self.env.reset(seed=seed, options=options)
+
+    def step(self, action):
+        obs, reward, closed, truncated, info = self.env.step(action)
+        cd = self.compute_cell_distances(info["state"])
+        reward = shape_reward(reward, cd, self.shaping_weight)
+        if np.isnan(reward):
+            self.logger.error("Reward is NaN")
+        info["cell_dist"] = cd
+        return obs, reward, closed, truncated, info
+
+    def compute_cell_distances(self, state, use_avg=False) -> float:
+        return cell_distance(state, self.size_state, use_avg)

@@ -16,6 +16,12 @@ class HostConfig(C.Structure):
                [(n, C.c_int) for n in ("heaters", "obs_nz", "obs_nx", "channels")]
 
 
+class HostWrappers(C.Structure):
+    _fields_ = [("normalize_obs", C.c_int), ("obs_clip", C.c_int), ("obs_lo", C.c_float * 4), ("obs_hi", C.c_float * 4),
+                ("obs_maxval", C.c_float), ("normalize_reward", C.c_int), ("reward_scale", C.c_double), ("shaping", C.c_int),
+                ("shaping_weight", C.c_double)]
+
+
 def build():
     srcs = [_HERE / "emu_rbc2d.cpp", _ROOT / "rbc_gym_b200" / "csrc" / "rbc2d_core.h"]
     if not _SO.exists() or _SO.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
@@ -24,7 +30,7 @@ def build():
 
 
 def step(state, actions, ra, dt_action, precision=64, split=False, nxt_global=False, dt_solver=0.03,
-         obs=(8, 48), heaters=12, heater_limit=0.75, episode_length=300.0, pressure=False, t0=None):
+         obs=(8, 48), heaters=12, heater_limit=0.75, episode_length=300.0, pressure=False, t0=None, wrappers=None):
     """state: [B, 18528] (b,u,w flattened) in the given precision; returns dict."""
     lib = C.CDLL(str(build()))
     B = state.shape[0]
@@ -40,10 +46,11 @@ def step(state, actions, ra, dt_action, precision=64, split=False, nxt_global=Fa
     sc, tr, nf = np.ones(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
     pr = np.zeros((B, 2, 64, 96), dt) if pressure else None
     vp = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
-    rc = lib.emu_rbc2d_step(C.byref(h), precision, int(split), int(nxt_global), B, vp(st), vp(a), vp(ob), vp(rew), vp(nus), vp(nuo),
+    cd = np.zeros(B)
+    rc = lib.emu_rbc2d_step(C.byref(h), C.byref(wrappers) if wrappers is not None else None, vp(cd), precision, int(split), int(nxt_global), B, vp(st), vp(a), vp(ob), vp(rew), vp(nus), vp(nuo),
                             vp(t), vp(sc), vp(tr), vp(nf), vp(pr))
     assert rc == 0
-    return dict(state=st, obs=ob, reward=rew, nu_state=nus, nu_obs=nuo, t=t, step=sc, truncated=tr, nan=nf, pressure=pr)
+    return dict(state=st, obs=ob, reward=rew, nu_state=nus, nu_obs=nuo, t=t, step=sc, truncated=tr, nan=nf, pressure=pr, cell_dist=cd)
 
 
 def pack(b, u, w):

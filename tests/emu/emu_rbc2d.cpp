@@ -8,16 +8,16 @@
 using namespace rbc2d;
 
 template <typename Real, bool SPLIT>
-static void run(const HostConfig& h, int B, Real* state, const float* actions, float* obs, float* reward,
+static void run(const HostConfig& h, const HostWrappers& wr, double* cell_dist, int B, Real* state, const float* actions, float* obs, float* reward,
                 double* nu_state, double* nu_obs, double* t, int* step_count, int* truncated, int* nan_flag,
                 Real* pressure, bool nxt_global)
 {
-    Consts<Real> C = make_consts<Real>(h);
+    Consts<Real> C = make_consts<Real>(h, wr);
     std::vector<double> tinv_d(NZ * NX), tw48_d(96), tw96_d(96);
     build_tables_host(h.lx, h.lz, tinv_d.data(), tw48_d.data(), tw96_d.data());
     std::vector<Real> tinv(tinv_d.begin(), tinv_d.end()), tw48(tw48_d.begin(), tw48_d.end()), tw96(tw96_d.begin(), tw96_d.end());
     Tables<Real> T{tinv.data(), tw48.data(), tw96.data(), (Real)((h.lz / NZ) * (h.lz / NZ) / 48.0)};
-    EnvIO<Real> io{state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, pressure};
+    EnvIO<Real> io{state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, pressure, cell_dist};
     std::vector<Real> s0(NS_SM), s1(NS_SM), R(NR), Tb(NX), mid(2 * NX), gm(2 * NSTATE);
     std::vector<double> red(NRED * NT);
     Ctx<Real> X{s0.data(), s1.data(), R.data(), Tb.data(), mid.data(), tw48.data(), tw96.data(), gm.data(), tinv.data(), red.data()};
@@ -28,16 +28,18 @@ static void run(const HostConfig& h, int B, Real* state, const float* actions, f
     }
 }
 
-extern "C" int emu_rbc2d_step(const HostConfig* h, int precision, int split, int nxt_global, int B, void* state,
+extern "C" int emu_rbc2d_step(const HostConfig* h, const HostWrappers* wp, double* cell_dist, int precision, int split, int nxt_global, int B, void* state,
                               const float* actions, float* obs, float* reward, double* nu_state, double* nu_obs, double* t,
                               int* step_count, int* truncated, int* nan_flag, void* pressure)
 {
+    HostWrappers wr;
+    if (wp) wr = *wp;
     if (precision == 64) {
-        if (split) run<double, true>(*h, B, (double*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (double*)pressure, nxt_global);
-        else run<double, false>(*h, B, (double*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (double*)pressure, nxt_global);
+        if (split) run<double, true>(*h, wr, cell_dist, B, (double*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (double*)pressure, nxt_global);
+        else run<double, false>(*h, wr, cell_dist, B, (double*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (double*)pressure, nxt_global);
     } else if (precision == 32) {
-        if (split) run<float, true>(*h, B, (float*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (float*)pressure, nxt_global);
-        else run<float, false>(*h, B, (float*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (float*)pressure, nxt_global);
+        if (split) run<float, true>(*h, wr, cell_dist, B, (float*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (float*)pressure, nxt_global);
+        else run<float, false>(*h, wr, cell_dist, B, (float*)state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, (float*)pressure, nxt_global);
     } else return -1;
     return 0;
 }

@@ -1,0 +1,152 @@
+"""API-surface tests of the environment classes on a GPU (SURVEY §8a a8/a11/a12/a14, §8b "surface kept")."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from pathlib import Path  # noqa: E402
+
+from oracle import oracle as O  # noqa: E402
+
+ROOT = Path(__file__).resolve().parent.parent
+CKPT = str(ROOT / "data/checkpoints/train/ckpt_ra100000.h5")
+
+
+def test_single_env_reference_api(ckpt_ra1e5):
+    import rbc_gym_b200 as R
+    env = R.make(rayleigh_number=100_000, heater_duration=0.3, checkpoint=CKPT, checkpoint_idx=7, render_mode="rgb_array")
+    assert env.action_space.shape == (12,) and env.observation_space.shape == (3, 8, 48)
+    assert env.observation_space.low[0, 0, 0] == 1 and env.observation_space.high[0, 0, 0] == np.float32(2.75)
+    assert env.episode_steps == 1000 and env.temperature_difference == [1, 2] and env.state_shape == [64, 96]
+    obs, info = env.reset(seed=3)
+    assert obs.shape == (3, 8, 48) and obs.dtype == np.float32
+    assert set(info) == {"t", "step", "nusselt_state", "nusselt_obs", "state"}
+    assert info["t"] == 0.0 and info["step"] == 1 and info["state"].shape == (3, 64, 96) and info["state"].dtype == np.float32
+    c = ckpt_ra1e5
+    np.testing.assert_array_equal(info["state"], O.state_channels(c.b[7], c.u[7], c.w[7]).astype(np.float32))
+    P = O.make_params(1e5)
+    ns, no = O.nusselt_state_obs(P, c.b[7], c.u[7], c.w[7])
+    assert info["nusselt_state"] == pytest.approx(ns, rel=1e-12) and info["nusselt_obs"] == pytest.approx(no, rel=1e-12)
+    a = np.linspace(-1, 1, 12).astype(np.float32)
+    obs, reward, terminated, truncated, info = env.step(a)
+    r = O.step(P, c.b[7], c.u[7], c.w[7], a.astype(np.float64), O.substep_schedule(0.3))
+    ns, no = O.nusselt_state_obs(P, r["b"], r["u"], r["w"])
+    assert isinstance(reward, float) and reward == pytest.approx(-no, rel=1e-9)
+    assert terminated is False and truncated is False and info["t"] == pytest.approx(0.3) and info["step"] == 2
+    np.testing.assert_allclose(info["state"][0], r["b"], atol=2e-7)
+    img = env.render()
+    assert img.shape == (64, 96, 3) and img.dtype == np.uint8
+    with pytest.warns(UserWarning):
+        env.step(None)                                                     # zero action + warning (rbc2D.py:164-166)
+    env.close()
+
+
+def test_single_env_truncation_errors_and_noise_init():
+    import rbc_gym_b200 as R
+    env = R.make(rayleigh_number=10_000, heater_duration=0.06, episode_length=0.1)
+    with pytest.raises(RuntimeError):
+        env.step(np.zeros(12, np.float32))                                 # not initialised (rbc_sim2D_api.jl:79-81)
+    obs, info = env.reset(seed=42)                                         # noise init + projection (set!)
+    st = info["state"]
+    assert 1.0 <= st[0].min() and st[0].max() <= 2.0 and abs(st[0].mean() - 1.5) < 0.01
+    obs2, info2 = env.reset(seed=42)
+    np.testing.assert_array_equal(info2["state"], st)                      # seeded reset is reproducible
+    _, _, _, tr1, _ = env.step(env.action_space.sample())
+    _, _, _, tr2, i2 = env.step(env.action_space.sample())
+    assert (tr1, tr2) == (False, True) and i2["t"] >= 0.1
+    env.close()
+    bad = R.make(checkpoint="/nonexistent/ckpt.h5")
+    with pytest.raises(FileNotFoundError):
+        bad.reset()
+    bad.close()
+
+
+def test_single_env_nan_raises_like_reference(ckpt_ra1e5):
+    import rbc_gym_b200 as R
+    from rbc_gym_b200 import backend
+    env = R.make(rayleigh_number=100_000, heater_duration=0.03, checkpoint=CKPT, checkpoint_idx=0, precision=32)
+    env.reset()
+    f = backend.pack_fields(ckpt_ra1e5.b[:1], ckpt_ra1e5.u[:1], ckpt_ra1e5.w[:1])
+    f[0, 77] = np.nan
+    env.sim.reset_from_fields(f, project=False)
+    with pytest.raises(RuntimeError, match="probably NaN values"):
+        env.step(np.zeros(12, np.float32))
+    env.close()
+
+
+def test_python_wrappers_compose_like_run_wrapped():
+    import rbc_gym_b200 as R
+    from rbc_gym_b200 import wrappers as W
+    base = R.make(rayleigh_number=100_000, heater_duration=0.3, checkpoint=CKPT, checkpoint_idx=2)
+    env = W.RBCRewardShaping(W.RBCNormalizeReward(W.RBCNormalizeObservation(base, heater_limit=base.unwrapped.heater_limit)), 0.1)
+    obs, info = env.reset(seed=0)
+    assert env.observation_space.shape == (3, 8, 48) and abs(obs).max() <= 1.3
+    obs, reward, term, trunc, info = env.step(np.zeros(12, np.float32))
+    assert "cell_dist" in info and 0 <= info["cell_dist"] <= np.pi
+    raw = -info["nusselt_obs"]
+    assert reward == pytest.approx(W.shape_reward(W.normalize_reward(raw, 100_000), info["cell_dist"], 0.1), rel=1e-12)
+    env.close()
+
+
+def test_fused_wrappers_on_device_match_python(ckpt_ra1e5):
+    import torch
+    from rbc_gym_b200 import backend, wrappers as W
+    eps = [0, 7, 16, 3, 11]
+    acts = np.random.default_rng(2).uniform(-1, 1, (5, 12)).astype(np.float32)
+    sims = []
+    for fused in (False, True):
+        s = backend.Sim2D(5, ra=1e5, dt_action=0.3, precision=32)
+        s.load_checkpoints(ckpt_ra1e5)
+        s.reset_from_checkpoints(torch.tensor(eps, dtype=torch.int32))
+        if fused:
+            s.set_wrappers(normalize_obs=True, normalize_reward=True, shaping_weight=0.1)
+        s.step(torch.from_numpy(acts).cuda())
+        sims.append(s)
+    plain, fused = sims
+    st = plain.get_state().cpu().numpy()
+    cd = fused.cell_dist()
+    for j in range(5):
+        ref_cd = W.cell_distance(st[j])
+        assert cd[j] == pytest.approx(ref_cd, abs=1e-12)
+        r = W.shape_reward(W.normalize_reward(-plain.nu_obs[j].item(), 1e5), ref_cd, 0.1)
+        assert fused.reward[j].item() == pytest.approx(r, rel=1e-6)
+        np.testing.assert_allclose(fused.obs[j].cpu().numpy(), W.normalize_observation(plain.obs[j].cpu().numpy().copy(), 0.75),
+                                   rtol=2e-6, atol=2e-7)
+    plain.close(); fused.close()
+
+
+@pytest.mark.parametrize("mode", ["next_step", "same_step"])
+def test_vector_env_autoreset_semantics(mode):
+    import torch
+    from rbc_gym_b200.envs import RBCVectorEnv2D
+    n = 6
+    env = RBCVectorEnv2D(n, rayleigh_number=100_000, heater_duration=0.06, episode_length=0.1, checkpoint=CKPT,
+                         autoreset_mode=mode, seed=5, precision=32)
+    obs0, info0 = env.reset()
+    assert obs0.shape == (n, 3, 8, 48) and obs0.is_cuda
+    reset_obs = obs0.clone()
+    a = torch.zeros(n, 12, device="cuda")
+    o1, r1, te1, tr1, _ = env.step(a)
+    assert not tr1.any() and not te1.any()
+    o2, r2, te2, tr2, i2 = env.step(a)
+    assert tr2.all()
+    if mode == "same_step":
+        assert "final_obs" in i2 and not torch.equal(i2["final_obs"], o2)
+        # the returned observation is already the reset observation of the next episode (a new random checkpoint)
+        t, step = env.sim.info()
+        assert np.all(t == 0) and np.all(step == 1)
+        o3, r3, _, tr3, _ = env.step(a)
+        assert not tr3.any() and (r3 != 0).all()
+    else:
+        t, _ = env.sim.info()
+        assert np.all(t > 0.1)
+        o3, r3, _, tr3, _ = env.step(a)                  # this call only resets (gymnasium NEXT_STEP)
+        assert not tr3.any() and (r3 == 0).all()
+        t, step = env.sim.info()
+        assert np.all(t == 0) and np.all(step == 1)
+    # checkpoint draws are keyed by (seed, global env id, episode): the same env ids elsewhere draw the same episodes
+    env2 = RBCVectorEnv2D(3, rayleigh_number=100_000, heater_duration=0.06, episode_length=0.1, checkpoint=CKPT,
+                          autoreset_mode=mode, seed=5, precision=32, env_id_offset=3)
+    o, _ = env2.reset()
+    assert torch.equal(o, reset_obs[3:6])
+    env.close(); env2.close()
