@@ -115,7 +115,8 @@ int rbc2d_step_host(rbc2d_sim* sim, const float* actions_host, float* obs_host, 
 
 /* Enable/disable the fused wrappers (NULL = all off).  Takes effect from the next step/observe. */
 int rbc2d_set_wrappers(rbc2d_sim* sim, const rbc2d_wrappers* w);
-/* info["cell_dist"] of the last step (rbc_reward_shaping.py:61-66), [B] float64. */
+/* info["cell_dist"] of the last step (rbc_reward_shaping.py:61-66), [B] float64; computed only while
+ * shaping is enabled (use shaping_weight = 0 to get the diagnostic without changing the reward). */
 int rbc2d_get_cell_dist_host(rbc2d_sim* sim, double* out_host);
 
 /* get_observation / get_nusselt without stepping (what reset() returns). */

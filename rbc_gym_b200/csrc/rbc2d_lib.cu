@@ -208,7 +208,7 @@ static int launch_env(rbc2d_sim* s, const float* actions, float* obs, float* rew
     io.truncated = trunc ? trunc : s->trunc;
     io.nan_flag = nan ? nan : s->nan;
     io.pressure = (Real*)s->pressure;
-    io.cell_dist = s->cell_dist;
+    io.cell_dist = s->wr.shaping ? s->cell_dist : nullptr;   // the peak scan runs only when reward shaping is on
     const int grid = n < s->grid ? n : s->grid;
     if (grid <= 0) return 0;
     if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
