@@ -1,0 +1,48 @@
+"""Checkpoint generation: the reference's `simulate_2d_rb` (`src/rbc_gym/sim/rbc_sim2D.jl:14-72`, arguments in
+`scripts/create_checkpoints_2D.sh:18-20`) as one batched on-device spin-up.
+
+For each of `random_inits` episodes: noise initialisation (kick 0.02), `duration / delta_t_snap` runs of
+`delta_t_snap` time units with zero action (bottom T = 2), NaN check per snapshot, final `b, u, w` written to a
+reference-compatible HDF5 file (`h5lite.write_checkpoint`).  All episodes advance together as one batch.
+Julia's RNG streams cannot be reproduced, so files are statistically — not bitwise — equivalent to the
+reference's; episode i is seeded with `seed + i + 1` like `Random.seed!(seed + i)` (1-based i).
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+from . import backend
+from .envs.rbc2d import noise_initial_fields
+from .h5lite import write_checkpoint
+
+
+def simulate_2d_rb(directory, seed: int = 42, random_inits: int = 20, ra: float = 1e5, pr: float = 0.7, random_kick: float = 0.02,
+                   delta_t: float = 0.03, delta_t_snap: float = 0.3, duration: float = 600.0, precision: int = 64, device: int = 0,
+                   progress=None):
+    import torch
+
+    n = int(random_inits)
+    sim = backend.Sim2D(n, ra=float(ra), dt_action=float(delta_t_snap), pr=pr, dt_solver=delta_t, episode_length=1e30,
+                        precision=precision, device=device)
+    fields = np.concatenate([noise_initial_fields(np.random.default_rng(seed + i + 1), kick=random_kick) for i in range(n)])
+    sim.reset_from_fields(fields, project=True)
+    zero = torch.zeros((n, sim.heaters), device=sim.device)
+    total = int(duration // delta_t_snap)
+    for it in range(total):
+        *_, nan = sim.step(zero)
+        if (it % 100 == 99 or it == total - 1) and bool(nan.any()):
+            raise RuntimeError("[ERROR] NaN values found!")             # rbc_sim2D.jl:196-199
+        if progress and it % 200 == 0:
+            progress(it, total)
+    b, u, w = backend.split_fields(sim.fields())
+    _, nus, nuo = sim.observe()
+    stats = {"nu_state": nus.cpu().numpy().copy(), "nu_obs": nuo.cpu().numpy().copy()}
+    sim.close()
+    directory = Path(directory)
+    directory.mkdir(parents=True, exist_ok=True)
+    ra_tag = int(ra) if float(ra).is_integer() else ra
+    path = directory / f"ckpt_ra{ra_tag}.h5"                            # rbc_sim2D.jl:36
+    write_checkpoint(path, b, u, w, start_seed=seed)
+    return path, stats

@@ -150,3 +150,25 @@ def test_vector_env_autoreset_semantics(mode):
     o, _ = env2.reset()
     assert torch.equal(o, reset_obs[3:6])
     env.close(); env2.close()
+
+
+def test_checkpoint_generator_reaches_reference_fixed_point(tmp_path):
+    """Spin-up from noise at Ra = 1e4 (the generator of the reference's fixtures, `rbc_sim2D.jl:14-72`): the flow
+    must settle on the reference's near-fixed point — the band spanned by its 40 Ra=1e4 checkpoints widened by
+    the residual oscillation amplitude — and the file must read back bit-identically."""
+    from rbc_gym_b200.checkpoints import simulate_2d_rb
+    from rbc_gym_b200.h5lite import load_checkpoint_2d
+    path, stats = simulate_2d_rb(tmp_path, seed=42, random_inits=4, ra=1e4, duration=600.0, precision=64)
+    assert path.name == "ckpt_ra10000.h5"
+    c = load_checkpoint_2d(path)
+    assert c.num_episodes == 4 and c.start_seed == 42 and c.b.shape == (4, 64, 96) and c.w.shape == (4, 65, 96)
+    P = O.make_params(1e4)
+    for e in range(4):
+        ns, no = O.nusselt_state_obs(P, c.b[e], c.u[e], c.w[e])
+        assert ns == pytest.approx(stats["nu_state"][e], rel=1e-12)
+        assert 3.997490 - 3e-4 <= ns <= 3.997789 + 3e-4, ns
+        assert 4.192437 - 3e-4 <= no <= 4.192916 + 3e-4, no
+        assert 0.0974366 - 2e-6 <= O.kinetic_energy(c.u[e], c.w[e]) <= 0.0974397 + 2e-6
+    dx, dz = 2 * np.pi / 96, 2 / 64
+    div = (np.roll(c.u, -1, axis=-1) - c.u) / dx + (c.w[:, 1:] - c.w[:, :-1]) / dz
+    assert np.abs(div).max() < 1e-13
