@@ -139,6 +139,53 @@ int rbc2d_launch_count(const rbc2d_sim* sim, int64_t* launches, int32_t* grid, i
  * synchronises). */
 int rbc2d_last_step_kernel_ms(rbc2d_sim* sim, float* ms);
 
+/* ------------------------------------------------------------------------------------------------
+ * 3D environment (rbc_gym/RayleighBenardConvection3D-v0): replaces the juliacall functions of
+ * src/rbc_gym/sim/rbc_sim3D_api.jl — initialize_simulation :17-72, step_simulation :77-101,
+ * get_state :106-121, get_info :126-129, get_nusselt :134-159, shutdown_simulation :164-171 —
+ * called from src/rbc_gym/envs/rbc3D.py:145-245.  Same conventions as the 2D entry points.
+ *   state / observation  [B][4][nz][ny][nx] float32 = (b,u,v,w) in the Python layout (rbc3D.py:229-232)
+ *   action               [B][heaters][heaters] float32, action[i][j] <-> patch i along x, j along y
+ *                        (rbc3D.py:206 passes the array un-transposed; rbc_sim3D.jl:131-141)
+ *   fields (raw)         [B][3*nx*ny*nz + nx*ny*(nz+1)] float64: b,u,v [nz][ny][nx], w [nz+1][ny][nx]
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct rbc3d_config {
+    int32_t num_envs;
+    int32_t nx, ny, nz;        /* grid = state_shape[::-1]; this build supports 32 x 32 x 16            */
+    int32_t heaters;           /* patches per side (8)                                                  */
+    double heater_limit;       /* 0.9                                                                   */
+    double ra, pr;
+    double lx, ly, lz;         /* L = domain[::-1] = [4 pi, 4 pi, 2]                                    */
+    double b_min, b_max;       /* T_diff = [1, 2]                                                       */
+    double heater_duration;    /* dt, in free-fall units (0.125)                                        */
+    double dt_solver;          /* in free-fall units (0.01); simulation dt = dt_solver * lz^2           */
+    double episode_length;     /* compared with the simulation time, which advances heater_duration*lz^2 */
+    int32_t precision;         /* 32 | 64                                                               */
+    int32_t split;             /* 1: hydrostatic-pressure split like Oceananigans, 0: buoyancy in G_w   */
+    int32_t device;
+} rbc3d_config;
+
+typedef struct rbc3d_sim rbc3d_sim;
+
+int rbc3d_create(const rbc3d_config* cfg, rbc3d_sim** out);
+int rbc3d_destroy(rbc3d_sim* sim);                          /* shutdown_simulation */
+int rbc3d_set_stream(rbc3d_sim* sim, void* cuda_stream);
+int rbc3d_state_values_per_env(const rbc3d_sim* sim);
+/* checkpoint bank [n_episodes][values_per_env] float64 (3D_ckpt_ra*.h5 read on the host; rbc_sim3D.jl:181-199) */
+int rbc3d_load_checkpoints(rbc3d_sim* sim, const double* fields_host, int32_t n_episodes);
+int rbc3d_reset_from_checkpoints_dev(rbc3d_sim* sim, const int32_t* env_ids_dev, const int32_t* ckpt_idx_dev, int32_t n);
+int rbc3d_reset_from_fields_host(rbc3d_sim* sim, const int32_t* env_ids_host, const double* fields_host, int32_t n, int32_t project);
+/* step_simulation + get_state + get_nusselt fused; obs may be NULL (skips the 262 KB/env observation write) */
+int rbc3d_step_dev(rbc3d_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, double* nusselt_dev,
+                   int32_t* truncated_dev, int32_t* nan_dev);
+int rbc3d_step_host(rbc3d_sim* sim, const float* actions_host, float* obs_host, float* reward_host, double* nusselt_host,
+                    int32_t* truncated_host, int32_t* nan_host);
+int rbc3d_observe_dev(rbc3d_sim* sim, float* obs_dev, double* nusselt_dev);
+int rbc3d_get_fields_host(rbc3d_sim* sim, double* fields_host);
+int rbc3d_get_info_host(rbc3d_sim* sim, double* t_host, int32_t* step_host);
+int rbc3d_launch_count(const rbc3d_sim* sim, int64_t* launches, int32_t* grid, int32_t* smem_bytes);
+int rbc3d_last_step_kernel_ms(rbc3d_sim* sim, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,359 @@
+/*
+ * rbc3d_oracle.c — CPU fp64 restatement of the RBC-Gym 3D simulation step.
+ *
+ * TEST INFRASTRUCTURE ONLY (same rules as rbc2d_oracle.c).
+ *
+ * Restates (reference = /root/reference):
+ *   - step_simulation / run!, preprocess_action, bottom_T(x,y,t)   src/rbc_gym/sim/rbc_sim3D_api.jl:77-101,
+ *                                                                  src/rbc_gym/sim/rbc_sim3D.jl:111-141
+ *   - model configuration (same NonhydrostaticModel / UpwindBiasedFifthOrder / RK3 as 2D, grid
+ *     (Periodic, Periodic, Bounded))                               src/rbc_gym/sim/rbc_sim3D.jl:99-166
+ *   - get_state, get_nusselt                                       src/rbc_gym/sim/rbc_sim3D_api.jl:106-159
+ * The arithmetic of run! is Oceananigans.jl 0.92.0 (not in the tree); the scheme is the 2D one of SURVEY.md 8a
+ * with a second periodic direction: v at y-faces (the "south" face of cell j), the extra fluxes Vc, Vu, Uv, Vv,
+ * Wv, Vw built by the same centred-4 advecting velocity / upwind-5 reconstruction rules.
+ *
+ * PARITY PIN: the reference's 3D checkpoint files are missing from the mount (.MISSING_LARGE_BLOBS), so this
+ * oracle is pinned (tests/test_oracle3d.py) to the fixture-pinned 2D oracle: a y-invariant state (v = 0) must
+ * evolve exactly like the 2D oracle, and so must its x<->y transposed twin (which exercises every y-direction
+ * code path); plus exact known answers (conduction state, Nu = 1, heater patches).  Against Julia: UNPINNED.
+ *
+ * Layout (C order, x fastest):  b,u,v: [nz][ny][nx];  w: [nz+1][ny][nx].
+ *   u(i,j,k) x-face left of cell i;  v(i,j,k) y-face "south" of cell j;  w(i,j,k) z-face below cell k.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "oracle_stencils.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+typedef struct {
+    int nx, ny, nz;
+    double lx, ly, lz;       /* 4 pi, 4 pi, 2 (rbc_sim3D_api.jl:17) */
+    double nu, kappa;        /* sqrt(Pr/Ra), 1/sqrt(Pr Ra) (rbc_sim3D_api.jl:37-38) */
+    double b_top, delta_b;   /* T_diff = [1, 2] */
+    int heaters;             /* 8 x 8 patches */
+    double heater_limit;     /* 0.9 */
+    int split_phy;
+} rbc3d_params;
+
+/* preprocess_action (rbc_sim3D.jl:111-128): T[i][j] = (min_b + db) + (a - mean)/K * limit, K = max(1, max|a - mean|).
+ * action[i*heaters + j] <-> patch i along x, j along y (rbc3D.py passes the array un-transposed). */
+void rbc3d_oracle_preprocess_action(const rbc3d_params *P, const double *action, double *T)
+{
+    const int n = P->heaters * P->heaters;
+    double mean = 0.0, K = 1.0;
+    for (int q = 0; q < n; ++q) mean += action[q];
+    mean /= n;
+    for (int q = 0; q < n; ++q) { double d = fabs(action[q] - mean); if (d > K) K = d; }
+    for (int q = 0; q < n; ++q) T[q] = (P->b_top + P->delta_b) + ((action[q] - mean) / K) * P->heater_limit;
+}
+
+/* bottom_T (rbc_sim3D.jl:131-141) at cell centres -> Tb[j][i] */
+void rbc3d_oracle_heater_profile(const rbc3d_params *P, const double *action, double *Tb)
+{
+    const int h = P->heaters;
+    double *T = (double *)malloc((size_t)h * h * 8);
+    rbc3d_oracle_preprocess_action(P, action, T);
+    const double dx = P->lx / P->nx, dy = P->ly / P->ny;
+    for (int j = 0; j < P->ny; ++j)
+        for (int i = 0; i < P->nx; ++i) {
+            int pi = (int)floor((i + 0.5) * dx / P->lx * h), pj = (int)floor((j + 0.5) * dy / P->ly * h);
+            if (pi < 0) pi = 0; if (pi > h - 1) pi = h - 1;
+            if (pj < 0) pj = 0; if (pj > h - 1) pj = h - 1;
+            Tb[(size_t)j * P->nx + i] = T[(size_t)pi * h + pj];
+        }
+    free(T);
+}
+
+#define H3 3
+typedef struct {
+    int nx, ny, nz, px, py;
+    long sy, sz;
+    double *bp, *up, *vp, *wp, *phy;       /* padded in x and y (halo 3, periodic) */
+    double *G[4], *G0[4];                  /* b,u,v,w tendencies (unpadded; w has nz+1 levels) */
+    double *rhs, *p, *Tb;
+    double *fr, *fi, *gr, *gi;             /* spectral scratch */
+} work3_t;
+
+static work3_t *w3_new(int nx, int ny, int nz)
+{
+    work3_t *W = (work3_t *)calloc(1, sizeof(work3_t));
+    W->nx = nx; W->ny = ny; W->nz = nz; W->px = nx + 2 * H3; W->py = ny + 2 * H3;
+    W->sy = W->px; W->sz = (long)W->px * W->py;
+    const size_t np = (size_t)W->sz * (nz + 1), n = (size_t)nx * ny * nz, nw = (size_t)nx * ny * (nz + 1);
+    W->bp = calloc(np, 8); W->up = calloc(np, 8); W->vp = calloc(np, 8); W->wp = calloc(np, 8); W->phy = calloc(np, 8);
+    for (int f = 0; f < 4; ++f) { W->G[f] = calloc(nw, 8); W->G0[f] = calloc(nw, 8); }
+    W->rhs = calloc(n, 8); W->p = calloc(n, 8); W->Tb = calloc((size_t)nx * ny, 8);
+    W->fr = calloc(n, 8); W->fi = calloc(n, 8); W->gr = calloc(n, 8); W->gi = calloc(n, 8);
+    return W;
+}
+static void w3_free(work3_t *W)
+{
+    free(W->bp); free(W->up); free(W->vp); free(W->wp); free(W->phy);
+    for (int f = 0; f < 4; ++f) { free(W->G[f]); free(W->G0[f]); }
+    free(W->rhs); free(W->p); free(W->Tb); free(W->fr); free(W->fi); free(W->gr); free(W->gi); free(W);
+}
+static void pad3(const work3_t *W, double *dst, const double *src, int levels)
+{
+    const int nx = W->nx, ny = W->ny;
+    for (int k = 0; k < levels; ++k)
+        for (int j = -H3; j < ny + H3; ++j) {
+            const int js = ((j % ny) + ny) % ny;
+            double *d = dst + (size_t)k * W->sz + (size_t)(j + H3) * W->sy + H3;
+            const double *s = src + ((size_t)k * ny + js) * nx;
+            for (int i = -H3; i < nx + H3; ++i) d[i] = s[((i % nx) + nx) % nx];
+        }
+}
+
+static void tendencies3(const rbc3d_params *P, work3_t *W, const double *b, const double *u, const double *v, const double *w)
+{
+    const int nx = P->nx, ny = P->ny, nz = P->nz;
+    const long sx = 1, sy = W->sy, sz = W->sz;
+    const double idx = nx / P->lx, idy = ny / P->ly, idz = nz / P->lz, dz = P->lz / nz;
+    pad3(W, W->bp, b, nz); pad3(W, W->up, u, nz); pad3(W, W->vp, v, nz); pad3(W, W->wp, w, nz + 1);
+#define AT(A, i, j, k) A[(size_t)(k) * sz + (size_t)((j) + H3) * sy + (i) + H3]
+#define B(i, j, k) AT(W->bp, i, j, k)
+#define U(i, j, k) AT(W->up, i, j, k)
+#define V(i, j, k) AT(W->vp, i, j, k)
+#define Wf(i, j, k) AT(W->wp, i, j, k)
+#define PH(i, j, k) AT(W->phy, i, j, k)
+    if (P->split_phy)
+        for (int j = -1; j < ny; ++j)
+            for (int i = -1; i < nx; ++i) {
+                double gh = 2 * P->b_top - B(i, j, nz - 1);
+                PH(i, j, nz - 1) = -0.5 * (B(i, j, nz - 1) + gh) * dz;
+                for (int k = nz - 2; k >= 0; --k) PH(i, j, k) = PH(i, j, k + 1) - 0.5 * (B(i, j, k) + B(i, j, k + 1)) * dz;
+            }
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const size_t q = ((size_t)k * ny + j) * nx + i;
+                const int of1 = (k + 1 <= nz - 1) ? ord_up_face(k + 1, nz) : 0, of0 = (k >= 1) ? ord_up_face(k, nz) : 0;
+                /* ---------------- tracer ---------------- */
+                {
+                    double Fx0 = upwind(U(i, j, k), up5L(&B(i, j, k), sx), up5R(&B(i, j, k), sx));
+                    double Fx1 = upwind(U(i + 1, j, k), up5L(&B(i + 1, j, k), sx), up5R(&B(i + 1, j, k), sx));
+                    double Fy0 = upwind(V(i, j, k), up5L(&B(i, j, k), sy), up5R(&B(i, j, k), sy));
+                    double Fy1 = upwind(V(i, j + 1, k), up5L(&B(i, j + 1, k), sy), up5R(&B(i, j + 1, k), sy));
+                    double Fz0 = of0 ? upwind(Wf(i, j, k), upL(&B(i, j, k), sz, of0), upR(&B(i, j, k), sz, of0)) : 0.0;
+                    double Fz1 = of1 ? upwind(Wf(i, j, k + 1), upL(&B(i, j, k + 1), sz, of1), upR(&B(i, j, k + 1), sz, of1)) : 0.0;
+                    double bdn = (k == 0) ? 2 * W->Tb[(size_t)j * nx + i] - B(i, j, 0) : B(i, j, k - 1);
+                    double bup = (k == nz - 1) ? 2 * P->b_top - B(i, j, nz - 1) : B(i, j, k + 1);
+                    double lap = (B(i + 1, j, k) - 2 * B(i, j, k) + B(i - 1, j, k)) * idx * idx +
+                                 (B(i, j + 1, k) - 2 * B(i, j, k) + B(i, j - 1, k)) * idy * idy + (bup - 2 * B(i, j, k) + bdn) * idz * idz;
+                    W->G[0][q] = -((Fx1 - Fx0) * idx + (Fy1 - Fy0) * idy + (Fz1 - Fz0) * idz) + P->kappa * lap;
+                }
+                /* ---------------- u at (x-face i, j, k) ---------------- */
+                {
+                    double F0 = upwind(ce4(&U(i, j, k), sx), up5L(&U(i, j, k), sx), up5R(&U(i, j, k), sx));
+                    double F1 = upwind(ce4(&U(i + 1, j, k), sx), up5L(&U(i + 1, j, k), sx), up5R(&U(i + 1, j, k), sx));
+                    /* Vu at (x-face i, y-face j): v interpolated in x, u reconstructed in y */
+                    double G0 = upwind(ce4(&V(i, j, k), sx), up5L(&U(i, j, k), sy), up5R(&U(i, j, k), sy));
+                    double G1 = upwind(ce4(&V(i, j + 1, k), sx), up5L(&U(i, j + 1, k), sy), up5R(&U(i, j + 1, k), sy));
+                    double H0 = of0 ? upwind(ce4(&Wf(i, j, k), sx), upL(&U(i, j, k), sz, of0), upR(&U(i, j, k), sz, of0)) : 0.0;
+                    double H1 = of1 ? upwind(ce4(&Wf(i, j, k + 1), sx), upL(&U(i, j, k + 1), sz, of1), upR(&U(i, j, k + 1), sz, of1)) : 0.0;
+                    double dn = (k == 0) ? -U(i, j, 0) : U(i, j, k - 1), up = (k == nz - 1) ? -U(i, j, nz - 1) : U(i, j, k + 1);
+                    double lap = (U(i + 1, j, k) - 2 * U(i, j, k) + U(i - 1, j, k)) * idx * idx +
+                                 (U(i, j + 1, k) - 2 * U(i, j, k) + U(i, j - 1, k)) * idy * idy + (up - 2 * U(i, j, k) + dn) * idz * idz;
+                    double g = -((F1 - F0) * idx + (G1 - G0) * idy + (H1 - H0) * idz) + P->nu * lap;
+                    if (P->split_phy) g -= (PH(i, j, k) - PH(i - 1, j, k)) * idx;
+                    W->G[1][q] = g;
+                }
+                /* ---------------- v at (i, y-face j, k) ---------------- */
+                {
+                    /* Uv at (x-face i, y-face j): u interpolated in y, v reconstructed in x */
+                    double F0 = upwind(ce4(&U(i, j, k), sy), up5L(&V(i, j, k), sx), up5R(&V(i, j, k), sx));
+                    double F1 = upwind(ce4(&U(i + 1, j, k), sy), up5L(&V(i + 1, j, k), sx), up5R(&V(i + 1, j, k), sx));
+                    double G0 = upwind(ce4(&V(i, j, k), sy), up5L(&V(i, j, k), sy), up5R(&V(i, j, k), sy));
+                    double G1 = upwind(ce4(&V(i, j + 1, k), sy), up5L(&V(i, j + 1, k), sy), up5R(&V(i, j + 1, k), sy));
+                    double H0 = of0 ? upwind(ce4(&Wf(i, j, k), sy), upL(&V(i, j, k), sz, of0), upR(&V(i, j, k), sz, of0)) : 0.0;
+                    double H1 = of1 ? upwind(ce4(&Wf(i, j, k + 1), sy), upL(&V(i, j, k + 1), sz, of1), upR(&V(i, j, k + 1), sz, of1)) : 0.0;
+                    double dn = (k == 0) ? -V(i, j, 0) : V(i, j, k - 1), up = (k == nz - 1) ? -V(i, j, nz - 1) : V(i, j, k + 1);
+                    double lap = (V(i + 1, j, k) - 2 * V(i, j, k) + V(i - 1, j, k)) * idx * idx +
+                                 (V(i, j + 1, k) - 2 * V(i, j, k) + V(i, j - 1, k)) * idy * idy + (up - 2 * V(i, j, k) + dn) * idz * idz;
+                    double g = -((F1 - F0) * idx + (G1 - G0) * idy + (H1 - H0) * idz) + P->nu * lap;
+                    if (P->split_phy) g -= (PH(i, j, k) - PH(i, j - 1, k)) * idy;
+                    W->G[2][q] = g;
+                }
+                /* ---------------- w at (i, j, z-face k), interior faces ---------------- */
+                if (k >= 1) {
+                    const int oc = ord_ce_face(k, nz);
+                    double F0 = upwind(cen(&U(i, j, k), sz, oc), up5L(&Wf(i, j, k), sx), up5R(&Wf(i, j, k), sx));
+                    double F1 = upwind(cen(&U(i + 1, j, k), sz, oc), up5L(&Wf(i + 1, j, k), sx), up5R(&Wf(i + 1, j, k), sx));
+                    double G0 = upwind(cen(&V(i, j, k), sz, oc), up5L(&Wf(i, j, k), sy), up5R(&Wf(i, j, k), sy));
+                    double G1 = upwind(cen(&V(i, j + 1, k), sz, oc), up5L(&Wf(i, j + 1, k), sy), up5R(&Wf(i, j + 1, k), sy));
+                    const int o0 = ord_up_cen(k - 1, nz), c0 = ord_ce_cen(k - 1, nz), o1 = ord_up_cen(k, nz), c1 = ord_ce_cen(k, nz);
+                    double H0 = upwind(cen(&Wf(i, j, k), sz, c0), upL(&Wf(i, j, k), sz, o0), upR(&Wf(i, j, k), sz, o0));
+                    double H1 = upwind(cen(&Wf(i, j, k + 1), sz, c1), upL(&Wf(i, j, k + 1), sz, o1), upR(&Wf(i, j, k + 1), sz, o1));
+                    double lap = (Wf(i + 1, j, k) - 2 * Wf(i, j, k) + Wf(i - 1, j, k)) * idx * idx +
+                                 (Wf(i, j + 1, k) - 2 * Wf(i, j, k) + Wf(i, j - 1, k)) * idy * idy +
+                                 (Wf(i, j, k + 1) - 2 * Wf(i, j, k) + Wf(i, j, k - 1)) * idz * idz;
+                    double g = -((F1 - F0) * idx + (G1 - G0) * idy + (H1 - H0) * idz) + P->nu * lap;
+                    if (!P->split_phy) g += 0.5 * (B(i, j, k - 1) + B(i, j, k));
+                    W->G[3][q] = g;
+                } else {
+                    W->G[3][q] = 0.0;
+                }
+            }
+    for (size_t q = 0; q < (size_t)nx * ny; ++q) W->G[3][(size_t)nz * nx * ny + q] = 0.0;
+#undef AT
+#undef B
+#undef U
+#undef V
+#undef Wf
+#undef PH
+}
+
+/* plain DFT along one axis of a [nz][ny][nx] complex array (n up to 64: O(n^2) is fine for the oracle) */
+static void dft_axis(int nx, int ny, int nz, int axis, const double *ar, const double *ai, double *br, double *bi, int sign)
+{
+    const int n = axis == 0 ? nx : ny;
+    const long st = axis == 0 ? 1 : nx;
+    double *c = (double *)malloc(n * 8), *s = (double *)malloc(n * 8);
+    for (int q = 0; q < n; ++q) { c[q] = cos(2 * M_PI * q / n); s[q] = sign * sin(2 * M_PI * q / n); }
+    for (int k = 0; k < nz; ++k)
+        for (int o = 0; o < (axis == 0 ? ny : nx); ++o) {
+            const size_t base = (size_t)k * nx * ny + (axis == 0 ? (size_t)o * nx : (size_t)o);
+            for (int m = 0; m < n; ++m) {
+                double sr = 0, si = 0;
+                for (int q = 0; q < n; ++q) {
+                    const int t = (int)(((long)m * q) % n);
+                    const double xr = ar[base + q * st], xi = ai ? ai[base + q * st] : 0.0;
+                    sr += xr * c[t] - xi * s[t];
+                    si += xr * s[t] + xi * c[t];
+                }
+                br[base + m * st] = sr; bi[base + m * st] = si;
+            }
+        }
+    free(c); free(s);
+}
+
+static void poisson3(const rbc3d_params *P, work3_t *W)
+{
+    const int nx = P->nx, ny = P->ny, nz = P->nz;
+    const double dx = P->lx / nx, dy = P->ly / ny, dz = P->lz / nz;
+    const size_t pl = (size_t)nx * ny;
+    dft_axis(nx, ny, nz, 0, W->rhs, NULL, W->fr, W->fi, -1);
+    dft_axis(nx, ny, nz, 1, W->fr, W->fi, W->gr, W->gi, -1);
+    double *cp = (double *)malloc(nz * 8), *dr = (double *)malloc(nz * 8), *di = (double *)malloc(nz * 8);
+    for (int my = 0; my < ny; ++my)
+        for (int mx = 0; mx < nx; ++mx) {
+            const double sxv = 2 * sin(M_PI * mx / nx) / dx, syv = 2 * sin(M_PI * my / ny) / dy, lam = (sxv * sxv + syv * syv) * dz * dz;
+            const size_t o = (size_t)my * nx + mx;
+            for (int k = 0; k < nz; ++k) {
+                double diag = -(2.0 + lam);
+                if (k == 0 || k == nz - 1) diag += 1.0;
+                if (mx == 0 && my == 0 && k == 0) diag -= 1.0;
+                const double fr = W->gr[k * pl + o] * dz * dz, fi = W->gi[k * pl + o] * dz * dz;
+                if (k == 0) { cp[0] = 1.0 / diag; dr[0] = fr / diag; di[0] = fi / diag; }
+                else { double den = diag - cp[k - 1]; cp[k] = 1.0 / den; dr[k] = (fr - dr[k - 1]) / den; di[k] = (fi - di[k - 1]) / den; }
+            }
+            W->gr[(nz - 1) * pl + o] = dr[nz - 1]; W->gi[(nz - 1) * pl + o] = di[nz - 1];
+            for (int k = nz - 2; k >= 0; --k) {
+                W->gr[k * pl + o] = dr[k] - cp[k] * W->gr[(k + 1) * pl + o];
+                W->gi[k * pl + o] = di[k] - cp[k] * W->gi[(k + 1) * pl + o];
+            }
+        }
+    free(cp); free(dr); free(di);
+    double mr = 0.0;
+    for (int k = 0; k < nz; ++k) mr += W->gr[k * pl];
+    mr /= nz;
+    for (int k = 0; k < nz; ++k) { W->gr[k * pl] -= mr; W->gi[k * pl] = 0.0; }
+    dft_axis(nx, ny, nz, 1, W->gr, W->gi, W->fr, W->fi, +1);
+    dft_axis(nx, ny, nz, 0, W->fr, W->fi, W->gr, W->gi, +1);
+    for (size_t q = 0; q < pl * nz; ++q) W->p[q] = W->gr[q] / ((double)nx * ny);
+}
+
+static void project3(const rbc3d_params *P, work3_t *W, double *u, double *v, double *w, double dtau)
+{
+    const int nx = P->nx, ny = P->ny, nz = P->nz;
+    const double dx = P->lx / nx, dy = P->ly / ny, dz = P->lz / nz;
+#define Q(i, j, k) (((size_t)(k) * ny + (j)) * nx + (i))
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const int ip = (i + 1) % nx, jp = (j + 1) % ny;
+                W->rhs[Q(i, j, k)] = ((u[Q(ip, j, k)] - u[Q(i, j, k)]) / dx + (v[Q(i, jp, k)] - v[Q(i, j, k)]) / dy +
+                                      (w[Q(i, j, k + 1)] - w[Q(i, j, k)]) / dz) / dtau;
+            }
+    poisson3(P, W);
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const int im = (i + nx - 1) % nx, jm = (j + ny - 1) % ny;
+                u[Q(i, j, k)] -= dtau * (W->p[Q(i, j, k)] - W->p[Q(im, j, k)]) / dx;
+                v[Q(i, j, k)] -= dtau * (W->p[Q(i, j, k)] - W->p[Q(i, jm, k)]) / dy;
+                if (k >= 1) w[Q(i, j, k)] -= dtau * (W->p[Q(i, j, k)] - W->p[Q(i, j, k - 1)]) / dz;
+            }
+#undef Q
+}
+
+static void rk3_step3(const rbc3d_params *P, work3_t *W, double *b, double *u, double *v, double *w, double dt)
+{
+    static const double gam[3] = {8.0 / 15.0, 5.0 / 12.0, 3.0 / 4.0};
+    static const double zet[3] = {0.0, -17.0 / 60.0, -5.0 / 12.0};
+    const size_t n = (size_t)P->nx * P->ny * P->nz, pl = (size_t)P->nx * P->ny;
+    for (int s = 0; s < 3; ++s) {
+        tendencies3(P, W, b, u, v, w);
+        const double g = gam[s], z = zet[s];
+        for (size_t q = 0; q < n; ++q) {
+            b[q] += dt * (g * W->G[0][q] + z * W->G0[0][q]);
+            u[q] += dt * (g * W->G[1][q] + z * W->G0[1][q]);
+            v[q] += dt * (g * W->G[2][q] + z * W->G0[2][q]);
+        }
+        for (size_t q = pl; q < n; ++q) w[q] += dt * (g * W->G[3][q] + z * W->G0[3][q]);
+        project3(P, W, u, v, w, (g + z) * dt);
+        for (int f = 0; f < 4; ++f) { double *t = W->G0[f]; W->G0[f] = W->G[f]; W->G[f] = t; }
+    }
+}
+
+/* One action step: step_simulation (rbc_sim3D_api.jl:77-101) with the substep schedule dts[nsub] in simulation
+ * time units (dt_solver * t_ff each, last one clipped).  Returns 1 if NaNs are present. */
+int rbc3d_oracle_step(const rbc3d_params *P, double *b, double *u, double *v, double *w, const double *action, int nsub,
+                      const double *dts)
+{
+    work3_t *W = w3_new(P->nx, P->ny, P->nz);
+    rbc3d_oracle_heater_profile(P, action, W->Tb);
+    for (int s = 0; s < nsub; ++s) rk3_step3(P, W, b, u, v, w, dts[s]);
+    int bad = 0;
+    const size_t n = (size_t)P->nx * P->ny * P->nz;
+    for (size_t q = 0; q < n; ++q) if (isnan(b[q]) || isnan(u[q]) || isnan(v[q]) || isnan(w[q])) { bad = 1; break; }
+    w3_free(W);
+    return bad;
+}
+
+void rbc3d_oracle_tendencies(const rbc3d_params *P, const double *b, const double *u, const double *v, const double *w,
+                             const double *action, double *Gb, double *Gu, double *Gv, double *Gw)
+{
+    work3_t *W = w3_new(P->nx, P->ny, P->nz);
+    rbc3d_oracle_heater_profile(P, action, W->Tb);
+    tendencies3(P, W, b, u, v, w);
+    const size_t n = (size_t)P->nx * P->ny * P->nz, nw = (size_t)P->nx * P->ny * (P->nz + 1);
+    memcpy(Gb, W->G[0], n * 8); memcpy(Gu, W->G[1], n * 8); memcpy(Gv, W->G[2], n * 8); memcpy(Gw, W->G[3], nw * 8);
+    w3_free(W);
+}
+
+void rbc3d_oracle_project(const rbc3d_params *P, double *u, double *v, double *w)
+{
+    work3_t *W = w3_new(P->nx, P->ny, P->nz);
+    project3(P, W, u, v, w, 1.0);
+    w3_free(W);
+}
+
+/* get_nusselt (rbc_sim3D_api.jl:134-159): Nu = 1 + mean((b - T_cond(z)) * w) / kappa, T_cond = (1 - z) db + min_b at
+ * z = (k + 1/2)/nz (unit height!), w = bottom-face values of the nz cell layers. */
+double rbc3d_oracle_nusselt(const rbc3d_params *P, const double *b, const double *w)
+{
+    const size_t pl = (size_t)P->nx * P->ny;
+    double acc = 0.0;
+    for (int k = 0; k < P->nz; ++k) {
+        const double dzu = 1.0 / P->nz, z = dzu / 2 + k * dzu, Tc = (1 - z) * P->delta_b + P->b_top;
+        for (size_t q = 0; q < pl; ++q) acc += (b[k * pl + q] - Tc) * w[k * pl + q];
+    }
+    return 1 + (acc / (double)(pl * P->nz)) / P->kappa;
+}

@@ -22,6 +22,23 @@ DEFAULT_KWARGS_2D = {                      # src/rbc_gym/__init__.py:7-18
 }
 
 
+ENV_ID_3D = "rbc_gym/RayleighBenardConvection3D-v0"
+DEFAULT_KWARGS_3D = {                      # src/rbc_gym/__init__.py:24-37
+    "rayleigh_number": 500,
+    "prandtl_number": 0.7,
+    "domain": [2, 4 * 3.141592653589793, 4 * 3.141592653589793],
+    "state_shape": (16, 32, 32),
+    "temperature_difference": [1, 2],
+    "heater_segments": 8,
+    "heater_limit": 0.9,
+    "heater_duration": 0.125,
+    "episode_length": 300,
+    "checkpoint": None,
+    "use_gpu": True,
+    "render_mode": None,
+}
+
+
 def register_envs() -> bool:
     """Register the reference's gym ids against this backend (no-op without gymnasium)."""
     if not spaces.HAVE_GYMNASIUM:
@@ -29,17 +46,22 @@ def register_envs() -> bool:
     from gymnasium.envs.registration import register, registry
     if ENV_ID_2D not in registry:
         register(id=ENV_ID_2D, entry_point="rbc_gym_b200.envs:RayleighBenardConvection2DEnv", kwargs=dict(DEFAULT_KWARGS_2D))
+    if ENV_ID_3D not in registry:
+        register(id=ENV_ID_3D, entry_point="rbc_gym_b200.envs:RayleighBenardConvection3DEnv", kwargs=dict(DEFAULT_KWARGS_3D))
     return True
 
 
 def make(env_id: str = ENV_ID_2D, **kwargs):
     """`gym.make` stand-in usable without gymnasium: builds the env with the registered default kwargs."""
-    if env_id != ENV_ID_2D:
+    from .envs import RayleighBenardConvection2DEnv, RayleighBenardConvection3DEnv
+    if env_id == ENV_ID_2D:
+        cls, kw = RayleighBenardConvection2DEnv, dict(DEFAULT_KWARGS_2D)
+    elif env_id == ENV_ID_3D:
+        cls, kw = RayleighBenardConvection3DEnv, dict(DEFAULT_KWARGS_3D)
+    else:
         raise ValueError(f"unknown environment id {env_id!r}")
-    from .envs import RayleighBenardConvection2DEnv
-    kw = dict(DEFAULT_KWARGS_2D)
     kw.update(kwargs)
-    return RayleighBenardConvection2DEnv(**kw)
+    return cls(**kw)
 
 
 register_envs()

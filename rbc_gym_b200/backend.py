@@ -50,6 +50,18 @@ class Rbc2dWrappers(C.Structure):
     ]
 
 
+class Rbc3dConfig(C.Structure):
+    """Mirror of ``rbc3d_config`` (include/rbc_b200.h)."""
+
+    _fields_ = [
+        ("num_envs", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("heaters", C.c_int32),
+        ("heater_limit", C.c_double), ("ra", C.c_double), ("pr", C.c_double),
+        ("lx", C.c_double), ("ly", C.c_double), ("lz", C.c_double), ("b_min", C.c_double), ("b_max", C.c_double),
+        ("heater_duration", C.c_double), ("dt_solver", C.c_double), ("episode_length", C.c_double),
+        ("precision", C.c_int32), ("split", C.c_int32), ("device", C.c_int32),
+    ]
+
+
 # every symbol include/rbc_b200.h declares; tests check that the built library exports them all
 ABI_SYMBOLS = (
     "rbc_abi_version", "rbc_last_error", "rbc2d_create", "rbc2d_destroy", "rbc2d_set_stream", "rbc2d_num_envs",
@@ -57,6 +69,9 @@ ABI_SYMBOLS = (
     "rbc2d_reset_from_fields_host", "rbc2d_step_dev", "rbc2d_step_host", "rbc2d_observe_dev", "rbc2d_observe_host",
     "rbc2d_get_state_dev", "rbc2d_get_state_host", "rbc2d_get_fields_host", "rbc2d_get_info_host",
     "rbc2d_launch_count", "rbc2d_last_step_kernel_ms", "rbc2d_set_wrappers", "rbc2d_get_cell_dist_host",
+    "rbc3d_create", "rbc3d_destroy", "rbc3d_set_stream", "rbc3d_state_values_per_env", "rbc3d_load_checkpoints",
+    "rbc3d_reset_from_checkpoints_dev", "rbc3d_reset_from_fields_host", "rbc3d_step_dev", "rbc3d_step_host",
+    "rbc3d_observe_dev", "rbc3d_get_fields_host", "rbc3d_get_info_host", "rbc3d_launch_count", "rbc3d_last_step_kernel_ms",
 )
 
 _lib = None
@@ -109,6 +124,20 @@ def load_library(build_if_missing: bool = True):
     L.rbc2d_get_cell_dist_host.argtypes = [vp, vp]
     L.rbc2d_launch_count.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ip), C.POINTER(ip)]
     L.rbc2d_last_step_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.rbc3d_create.argtypes = [C.POINTER(Rbc3dConfig), C.POINTER(vp)]
+    L.rbc3d_destroy.argtypes = [vp]
+    L.rbc3d_set_stream.argtypes = [vp, vp]
+    L.rbc3d_state_values_per_env.argtypes = [vp]
+    L.rbc3d_load_checkpoints.argtypes = [vp, vp, ip]
+    L.rbc3d_reset_from_checkpoints_dev.argtypes = [vp, vp, vp, ip]
+    L.rbc3d_reset_from_fields_host.argtypes = [vp, vp, vp, ip, ip]
+    L.rbc3d_step_dev.argtypes = [vp] * 7
+    L.rbc3d_step_host.argtypes = [vp] * 7
+    L.rbc3d_observe_dev.argtypes = [vp] * 3
+    L.rbc3d_get_fields_host.argtypes = [vp, vp]
+    L.rbc3d_get_info_host.argtypes = [vp, vp, vp]
+    L.rbc3d_launch_count.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ip), C.POINTER(ip)]
+    L.rbc3d_last_step_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     if L.rbc_abi_version() != 1:
         raise BackendUnavailable("librbc_b200.so ABI version mismatch; rebuild with `python -m rbc_gym_b200.build`")
     _lib = L
@@ -342,3 +371,150 @@ def pack_fields(b, u, w) -> np.ndarray:
     b, u, w = (np.asarray(a, dtype=np.float64) for a in (b, u, w))
     B = b.shape[0]
     return np.concatenate([b.reshape(B, -1), u.reshape(B, -1), w.reshape(B, -1)], axis=1)
+
+
+# ============================================================================================ 3D
+NX3, NY3, NZ3 = 32, 32, 16
+NC3 = NX3 * NY3 * NZ3
+NSTATE3 = 3 * NC3 + NX3 * NY3 * (NZ3 + 1)
+
+
+class Sim3D:
+    """A batch of B independent 3D RBC environments on one GPU (`rbc3d_sim` handle): the batched form of
+    `rbc_sim3D_api.jl` (`initialize_simulation`, `step_simulation`, `get_state`, `get_info`, `get_nusselt`)."""
+
+    def __init__(self, num_envs: int, ra: float = 2500, *, pr: float = 0.7, domain=(2.0, 4 * math.pi, 4 * math.pi),
+                 state_shape=(16, 32, 32), temperature_difference=(1.0, 2.0), heaters: int = 8, heater_limit: float = 0.9,
+                 heater_duration: float = 0.125, dt_solver: float = 0.01, episode_length: float = 300.0, precision: int = 32,
+                 split: bool = True, device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise BackendUnavailable("rbc_gym_b200 needs a CUDA device (there is no CPU fallback)")
+        self._L = load_library()
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.B, self.heaters, self.precision = int(num_envs), int(heaters), int(precision)
+        self.state_shape = tuple(int(x) for x in state_shape)
+        nz, ny, nx = self.state_shape
+        lz, ly, lx = (float(x) for x in domain)                       # rbc3D.py:173 passes L = domain[::-1]
+        self.ra, self.pr = float(ra), float(pr)
+        self.kappa = 1.0 / math.sqrt(self.pr * self.ra)
+        self.t_ff = lz * lz
+        self.nsub = len(substep_schedule(heater_duration * self.t_ff, dt_solver * self.t_ff))
+        self.cfg = Rbc3dConfig(self.B, nx, ny, nz, self.heaters, float(heater_limit), self.ra, self.pr, lx, ly, lz,
+                               float(temperature_difference[0]), float(temperature_difference[1]), float(heater_duration),
+                               float(dt_solver), float(episode_length), self.precision, int(bool(split)), device)
+        h = C.c_void_p()
+        self._h = None
+        self._check(self._L.rbc3d_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+        f32, f64, i32 = torch.float32, torch.float64, torch.int32
+        self.obs = torch.zeros((self.B, 4, nz, ny, nx), dtype=f32, device=self.device)
+        self.reward = torch.zeros(self.B, dtype=f32, device=self.device)
+        self.nusselt = torch.zeros(self.B, dtype=f64, device=self.device)
+        self.truncated = torch.zeros(self.B, dtype=i32, device=self.device)
+        self.nan = torch.zeros(self.B, dtype=i32, device=self.device)
+        self.n_episodes = 0
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RuntimeError(f"rbc_b200: {self._L.rbc_last_error().decode()}")
+
+    def _use_current_stream(self):
+        self._check(self._L.rbc3d_set_stream(self._h, C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rbc3d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_checkpoints(self, fields: np.ndarray) -> int:
+        """Upload a bank `[n_ep, 66560]` float64 (b,u,v,w in checkpoint layout)."""
+        f = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1, NSTATE3)
+        self._use_current_stream()
+        self._check(self._L.rbc3d_load_checkpoints(self._h, _np_ptr(f), f.shape[0]))
+        self.n_episodes = f.shape[0]
+        return self.n_episodes
+
+    def reset_from_checkpoints(self, ckpt_idx, env_ids=None):
+        t = self.torch
+        idx = t.as_tensor(ckpt_idx, dtype=t.int32, device=self.device).contiguous()
+        ids = None if env_ids is None else t.as_tensor(env_ids, dtype=t.int32, device=self.device).contiguous()
+        n = self.B if ids is None else int(ids.numel())
+        self._use_current_stream()
+        self._check(self._L.rbc3d_reset_from_checkpoints_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
+                                                            C.c_void_p(idx.data_ptr()), n))
+
+    def reset_from_fields(self, fields: np.ndarray, env_ids: Optional[Sequence[int]] = None, project: bool = True):
+        f = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1, NSTATE3)
+        ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
+        self._use_current_stream()
+        self._check(self._L.rbc3d_reset_from_fields_host(self._h, _np_ptr(ids), _np_ptr(f), f.shape[0], int(project)))
+
+    def step(self, actions, want_obs: bool = True):
+        """actions `[B, heaters, heaters]` float32 CUDA tensor -> (obs, reward, nusselt, truncated, nan)."""
+        t = self.torch
+        a = t.as_tensor(actions, dtype=t.float32, device=self.device).contiguous()
+        if a.shape != (self.B, self.heaters, self.heaters):
+            # rbc_sim3D.jl:115-117: "Action size does not match the number of actuators"
+            raise RuntimeError(f"Action size does not match the number of actuators. Expected {(self.heaters, self.heaters)}, "
+                               f"got {tuple(a.shape[1:])}.")
+        self._use_current_stream()
+        p = lambda x: C.c_void_p(x.data_ptr())
+        self._check(self._L.rbc3d_step_dev(self._h, p(a), p(self.obs) if want_obs else None, p(self.reward), p(self.nusselt),
+                                           p(self.truncated), p(self.nan)))
+        return self.obs, self.reward, self.nusselt, self.truncated, self.nan
+
+    def step_host(self, actions: np.ndarray, out: dict) -> dict:
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        self._use_current_stream()
+        self._check(self._L.rbc3d_step_host(self._h, _np_ptr(a), _np_ptr(out.get("obs")), _np_ptr(out["reward"]),
+                                            _np_ptr(out["nusselt"]), _np_ptr(out["truncated"]), _np_ptr(out["nan"])))
+        return out
+
+    def observe(self):
+        self._use_current_stream()
+        p = lambda x: C.c_void_p(x.data_ptr())
+        self._check(self._L.rbc3d_observe_dev(self._h, p(self.obs), p(self.nusselt)))
+        return self.obs, self.nusselt
+
+    def fields(self) -> np.ndarray:
+        out = np.empty((self.B, NSTATE3), np.float64)
+        self._use_current_stream()
+        self._check(self._L.rbc3d_get_fields_host(self._h, _np_ptr(out)))
+        return out
+
+    def info(self):
+        t = np.empty(self.B, np.float64)
+        s = np.empty(self.B, np.int32)
+        self._use_current_stream()
+        self._check(self._L.rbc3d_get_info_host(self._h, _np_ptr(t), _np_ptr(s)))
+        return t, s
+
+    def launch_info(self):
+        n, g, s = C.c_int64(), C.c_int32(), C.c_int32()
+        self._check(self._L.rbc3d_launch_count(self._h, C.byref(n), C.byref(g), C.byref(s)))
+        return {"launches": n.value, "grid": g.value, "smem_bytes": s.value}
+
+    def last_step_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._L.rbc3d_last_step_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+
+def split_fields3(fields: np.ndarray):
+    B = fields.shape[0]
+    shp = (B, NZ3, NY3, NX3)
+    return (fields[:, :NC3].reshape(shp), fields[:, NC3:2 * NC3].reshape(shp), fields[:, 2 * NC3:3 * NC3].reshape(shp),
+            fields[:, 3 * NC3:].reshape(B, NZ3 + 1, NY3, NX3))
+
+
+def pack_fields3(b, u, v, w) -> np.ndarray:
+    return np.concatenate([np.asarray(x, dtype=np.float64).reshape(np.shape(x)[0], -1) for x in (b, u, v, w)], axis=1)

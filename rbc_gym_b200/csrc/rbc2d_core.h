@@ -34,12 +34,13 @@
 #define RBC_RESTRICT __restrict__
 
 #if defined(__CUDA_ARCH__)
-#define RBC_PHASE(...) { const int tid = threadIdx.x; __VA_ARGS__ } __syncthreads();
+#define RBC_PHASE_N(NTHREADS, ...) { const int tid = threadIdx.x; __VA_ARGS__ } __syncthreads();
 #define RBC_UNROLL _Pragma("unroll")
 #else
-#define RBC_PHASE(...) for (int tid = 0; tid < rbc2d::NT; ++tid) { __VA_ARGS__ }
+#define RBC_PHASE_N(NTHREADS, ...) for (int tid = 0; tid < (NTHREADS); ++tid) { __VA_ARGS__ }
 #define RBC_UNROLL
 #endif
+#define RBC_PHASE(...) RBC_PHASE_N(rbc2d::NT, __VA_ARGS__)
 
 namespace rbc2d {
 
@@ -249,8 +250,7 @@ RBC_HD void phase_phy(int tid, const Consts<Real>& C, const Real* cb, Real* phy)
 // ------------------------------------------------------------------------------------------
 template <typename Real, bool SPLIT>
 RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTRICT c, Real* RBC_RESTRICT n,
-                           const Real* RBC_RESTRICT phy, const Real* RBC_RESTRICT Tb, const Real* RBC_RESTRICT gm_in,
-                           Real* RBC_RESTRICT gm_out, Real dt, Real gam, Real zet, bool use_gm)
+                           const Real* RBC_RESTRICT phy, const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm)
 {
     const int i = tid % NX, s = tid / NX, k0 = s * RS;
     const Real* RBC_RESTRICT cb = c + OFF_B;

@@ -12,6 +12,7 @@
 
 #include "../../include/rbc_b200.h"
 #include "rbc2d_core.h"
+#include "rbc_common.h"
 
 using namespace rbc2d;
 
@@ -19,13 +20,8 @@ using namespace rbc2d;
 // error plumbing
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static int fail(const std::string& m) { g_err = m; return -1; }
-#define CK(call)                                                                                    \
-    do {                                                                                            \
-        cudaError_t e_ = (call);                                                                    \
-        if (e_ != cudaSuccess)                                                                      \
-            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                        \
-    } while (0)
+int rbc_fail(const std::string& m) { g_err = m; return -1; }
+static int fail(const std::string& m) { return rbc_fail(m); }
 
 // ------------------------------------------------------------------------------------------
 // kernels

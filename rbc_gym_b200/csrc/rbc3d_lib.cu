@@ -1,0 +1,354 @@
+// rbc3d_lib.cu — sm_100a kernel wrapper + C ABI of the 3D environment (rbc3d_* in include/rbc_b200.h).
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rbc_b200.h"
+#include "rbc3d_core.h"
+#include "rbc_common.h"
+
+using namespace rbc3d;
+
+template <typename Real>
+struct Smem3 {
+    static constexpr size_t R = 0;
+    static constexpr size_t Tb = R + sizeof(Real) * NR;
+    static constexpr size_t red = Tb + sizeof(Real) * NCOL;
+    static constexpr size_t total = red + sizeof(double) * 2 * NT;
+    static_assert(Tb % 16 == 0 && red % 16 == 0, "alignment");
+    static_assert(total <= 232448, "exceeds the shared memory a CTA can opt into");
+};
+
+template <typename Real, bool SPLIT>
+__global__ void __launch_bounds__(NT, 1)
+rbc3d_env_kernel(Consts3<Real> C, EnvIO3<Real> io, Real* buf_all, Real* gm_all, const Real* tinv, Real thomas_scale,
+                 const int* env_ids, int n, RunFlags3 F)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    using L = Smem3<Real>;
+    Ctx3<Real> X;
+    X.bufA = buf_all + (size_t)blockIdx.x * 2 * NSTATE;
+    X.bufB = X.bufA + NSTATE;
+    X.gm = gm_all + (size_t)blockIdx.x * 2 * NG;
+    X.R = reinterpret_cast<Real*>(smem + L::R);
+    X.Tb = reinterpret_cast<Real*>(smem + L::Tb);
+    X.red = reinterpret_cast<double*>(smem + L::red);
+    X.tinv = tinv;
+    X.thomas_scale = thomas_scale;
+    for (int q = threadIdx.x; q < NR; q += NT) X.R[q] = Real(0);
+    __syncthreads();
+    for (int j = blockIdx.x; j < n; j += gridDim.x) {
+        const int env = env_ids ? env_ids[j] : j;
+        env_action_step3<Real, SPLIT>(C, io, X, env, F);
+    }
+}
+
+template <typename Real>
+__global__ void rbc3d_set_fields_kernel(Real* state, const double* fields, const int* env_ids, const int* src_idx, int n, int n_src,
+                                        double* t, int* step, int* trunc, int* nan)
+{
+    for (int j = blockIdx.y; j < n; j += gridDim.y) {
+        const int env = env_ids ? env_ids[j] : j;
+        int sidx = src_idx ? src_idx[j] : j;
+        sidx = sidx < 0 ? 0 : (sidx >= n_src ? n_src - 1 : sidx);
+        const double* src = fields + (size_t)sidx * NSTATE;
+        Real* dst = state + (size_t)env * NSTATE;
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < NSTATE; q += gridDim.x * blockDim.x) dst[q] = (Real)src[q];
+        if (blockIdx.x == 0 && threadIdx.x == 0) { t[env] = 0.0; step[env] = 1; trunc[env] = 0; nan[env] = 0; }
+    }
+}
+
+template <typename Real>
+__global__ void rbc3d_get_fields_kernel(const Real* state, double* out, size_t total)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x)
+        out[q] = (double)state[q];
+}
+
+struct rbc3d_sim {
+    rbc3d_config cfg;
+    HostConfig3 hc;
+    int B = 0, grid = 0, n_ep = 0;
+    size_t smem = 0, rs = 4;
+    cudaStream_t stream = nullptr;
+    void *state = nullptr, *buf = nullptr, *gm = nullptr, *tinv = nullptr;
+    double *bank = nullptr, *t = nullptr, *nu = nullptr;
+    int *step = nullptr, *trunc = nullptr, *nan = nullptr;
+    float *obs = nullptr, *reward = nullptr, *actions = nullptr;
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+template <typename Real, bool SPLIT>
+static int prepare3(rbc3d_sim* s)
+{
+    auto k = rbc3d_env_kernel<Real, SPLIT>;
+    s->smem = Smem3<Real>::total;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    int per_sm = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, s->smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->cfg.device));
+    if (per_sm < 1) return rbc_fail("3D step kernel does not fit on an SM");
+    s->grid = per_sm * sms;
+    std::vector<double> tv((size_t)NZ * NCOL);
+    build_tables3_host(s->hc.lx, s->hc.ly, s->hc.lz, tv.data());
+    std::vector<Real> tr(tv.begin(), tv.end());
+    CK(cudaMalloc(&s->tinv, tr.size() * sizeof(Real)));
+    CK(cudaMemcpy(s->tinv, tr.data(), tr.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+template <typename Real, bool SPLIT>
+static int launch3(rbc3d_sim* s, const float* actions, float* obs, float* reward, double* nu, int* trunc, int* nan, const int* env_ids,
+                   int n, RunFlags3 F, bool time_it, bool want_obs)
+{
+    Consts3<Real> C = make_consts3<Real>(s->hc);
+    EnvIO3<Real> io;
+    io.state = (Real*)s->state;
+    io.actions = actions ? actions : s->actions;
+    io.obs = want_obs ? (obs ? obs : s->obs) : nullptr;
+    io.reward = reward ? reward : s->reward;
+    io.nusselt = nu ? nu : s->nu;
+    io.t = s->t; io.step_count = s->step;
+    io.truncated = trunc ? trunc : s->trunc;
+    io.nan_flag = nan ? nan : s->nan;
+    const int grid = n < s->grid ? n : s->grid;
+    if (grid <= 0) return 0;
+    if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
+    rbc3d_env_kernel<Real, SPLIT><<<grid, NT, s->smem, s->stream>>>(C, io, (Real*)s->buf, (Real*)s->gm, (const Real*)s->tinv,
+                                                                   (Real)((s->hc.lz / NZ) * (s->hc.lz / NZ) / 512.0), env_ids, n, F);
+    CK(cudaGetLastError());
+    if (time_it) { CK(cudaEventRecord(s->ev1, s->stream)); s->timed = true; }
+    s->launches += 1;
+    return 0;
+}
+
+static int dispatch3(rbc3d_sim* s, const float* actions, float* obs, float* reward, double* nu, int* trunc, int* nan, const int* env_ids,
+                     int n, RunFlags3 F, bool time_it, bool want_obs = true)
+{
+    const bool f32 = s->cfg.precision == 32, split = s->cfg.split != 0;
+    if (f32) return split ? launch3<float, true>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs)
+                          : launch3<float, false>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs);
+    return split ? launch3<double, true>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs)
+                 : launch3<double, false>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs);
+}
+
+extern "C" {
+
+int rbc3d_create(const rbc3d_config* cfg, rbc3d_sim** out)
+{
+    if (!cfg || !out) return rbc_fail("rbc3d_create: null argument");
+    *out = nullptr;
+    if (cfg->nx != NX || cfg->ny != NY || cfg->nz != NZ) return rbc_fail("rbc3d_create: this build supports a 32 x 32 x 16 grid only");
+    if (cfg->num_envs < 1) return rbc_fail("rbc3d_create: num_envs must be >= 1");
+    if (cfg->precision != 32 && cfg->precision != 64) return rbc_fail("rbc3d_create: precision must be 32 or 64");
+    if (cfg->heaters < 1 || cfg->heaters > MAX_HEATERS) return rbc_fail("rbc3d_create: heaters must be in 1..16");
+    if (!(cfg->ra > 0) || !(cfg->pr > 0) || !(cfg->heater_duration > 0) || !(cfg->dt_solver > 0))
+        return rbc_fail("rbc3d_create: ra, pr, heater_duration, dt_solver must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return rbc_fail("rbc3d_create: no CUDA device available (this backend has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return rbc_fail("rbc3d_create: bad device ordinal");
+    CK(cudaSetDevice(cfg->device));
+    rbc3d_sim* s = new rbc3d_sim();
+    s->cfg = *cfg;
+    s->B = cfg->num_envs;
+    s->rs = cfg->precision == 32 ? 4 : 8;
+    s->hc = HostConfig3{cfg->ra, cfg->pr, cfg->lx, cfg->ly, cfg->lz, cfg->b_min, cfg->b_max - cfg->b_min, cfg->heater_limit,
+                        cfg->heater_duration, cfg->dt_solver, cfg->episode_length, cfg->heaters};
+    const bool f32 = cfg->precision == 32, split = cfg->split != 0;
+    int rc = f32 ? (split ? prepare3<float, true>(s) : prepare3<float, false>(s))
+                 : (split ? prepare3<double, true>(s) : prepare3<double, false>(s));
+    if (rc) { rbc3d_destroy(s); return rc; }
+    const size_t B = s->B, rs = s->rs;
+#define ALLOC3(ptr, bytes)                                                                      \
+    do {                                                                                        \
+        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                   \
+        if (e_ != cudaSuccess) {                                                                \
+            std::string m = std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_);      \
+            rbc3d_destroy(s);                                                                   \
+            return rbc_fail(m);                                                                 \
+        }                                                                                       \
+        cudaMemset((ptr), 0, (bytes));                                                          \
+    } while (0)
+    ALLOC3(s->state, B * NSTATE * rs);
+    ALLOC3(s->buf, (size_t)s->grid * 2 * NSTATE * rs);
+    ALLOC3(s->gm, (size_t)s->grid * 2 * NG * rs);
+    ALLOC3(s->t, B * sizeof(double));
+    ALLOC3(s->nu, B * sizeof(double));
+    ALLOC3(s->step, B * sizeof(int));
+    ALLOC3(s->trunc, B * sizeof(int));
+    ALLOC3(s->nan, B * sizeof(int));
+    ALLOC3(s->reward, B * sizeof(float));
+    ALLOC3(s->actions, B * (size_t)cfg->heaters * cfg->heaters * sizeof(float));
+#undef ALLOC3
+    if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
+        rbc3d_destroy(s);
+        return rbc_fail("cudaEventCreate failed");
+    }
+    *out = s;
+    return 0;
+}
+
+int rbc3d_destroy(rbc3d_sim* s)
+{
+    if (!s) return 0;
+    cudaSetDevice(s->cfg.device);
+    void* ptrs[] = {s->state, s->buf, s->gm, s->tinv, s->bank, s->t, s->nu, s->step, s->trunc, s->nan, s->obs, s->reward, s->actions};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+    return 0;
+}
+
+int rbc3d_set_stream(rbc3d_sim* s, void* stream)
+{
+    if (!s) return rbc_fail("null handle");
+    s->stream = (cudaStream_t)stream;
+    return 0;
+}
+int rbc3d_state_values_per_env(const rbc3d_sim* s) { return s ? NSTATE : -1; }
+
+int rbc3d_load_checkpoints(rbc3d_sim* s, const double* fields_host, int32_t n_episodes)
+{
+    if (!s || !fields_host || n_episodes < 1) return rbc_fail("rbc3d_load_checkpoints: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    if (s->bank) { cudaFree(s->bank); s->bank = nullptr; }
+    CK(cudaMalloc((void**)&s->bank, (size_t)n_episodes * NSTATE * sizeof(double)));
+    CK(cudaMemcpyAsync(s->bank, fields_host, (size_t)n_episodes * NSTATE * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->n_ep = n_episodes;
+    return 0;
+}
+
+static int set_fields3(rbc3d_sim* s, const double* dfields, const int* env_ids_dev, const int* src_idx_dev, int n, int n_src)
+{
+    dim3 grid(16, n < 2048 ? n : 2048);
+    if (s->cfg.precision == 32)
+        rbc3d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, dfields, env_ids_dev, src_idx_dev, n, n_src, s->t, s->step, s->trunc, s->nan);
+    else
+        rbc3d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, dfields, env_ids_dev, src_idx_dev, n, n_src, s->t, s->step, s->trunc, s->nan);
+    CK(cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
+int rbc3d_reset_from_checkpoints_dev(rbc3d_sim* s, const int32_t* env_ids, const int32_t* ckpt_idx, int32_t n)
+{
+    if (!s || !ckpt_idx) return rbc_fail("rbc3d_reset_from_checkpoints_dev: bad argument");
+    if (!s->bank) return rbc_fail("rbc3d_reset_from_checkpoints_dev: no checkpoint bank loaded");
+    CK(cudaSetDevice(s->cfg.device));
+    if (!env_ids) n = s->B;
+    if (n <= 0) return 0;
+    return set_fields3(s, s->bank, env_ids, ckpt_idx, n, s->n_ep);
+}
+
+int rbc3d_reset_from_fields_host(rbc3d_sim* s, const int32_t* env_ids_host, const double* fields, int32_t n, int32_t project)
+{
+    if (!s || !fields || n < 1 || n > s->B) return rbc_fail("rbc3d_reset_from_fields_host: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    double* dfields = nullptr;
+    int* dids = nullptr;
+    CK(cudaMalloc((void**)&dfields, (size_t)n * NSTATE * sizeof(double)));
+    CK(cudaMemcpyAsync(dfields, fields, (size_t)n * NSTATE * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (env_ids_host) {
+        CK(cudaMalloc((void**)&dids, n * sizeof(int)));
+        CK(cudaMemcpyAsync(dids, env_ids_host, n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    }
+    int rc = set_fields3(s, dfields, dids, nullptr, n, n);
+    if (!rc && project) {
+        RunFlags3 F{0, 1, 0};
+        rc = dispatch3(s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dids, n, F, false, false);
+    }
+    cudaStreamSynchronize(s->stream);
+    cudaFree(dfields);
+    if (dids) cudaFree(dids);
+    return rc;
+}
+
+int rbc3d_step_dev(rbc3d_sim* s, const float* actions, float* obs, float* reward, double* nusselt, int32_t* trunc, int32_t* nan)
+{
+    if (!s || !actions) return rbc_fail("rbc3d_step_dev: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    Consts3<float> tmp = make_consts3<float>(s->hc);
+    RunFlags3 F{tmp.nsub, 0, 1};
+    return dispatch3(s, actions, obs, reward, nusselt, trunc, nan, nullptr, s->B, F, true, obs != nullptr);
+}
+
+int rbc3d_step_host(rbc3d_sim* s, const float* actions, float* obs, float* reward, double* nusselt, int32_t* trunc, int32_t* nan)
+{
+    if (!s || !actions) return rbc_fail("rbc3d_step_host: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    const size_t B = s->B, na = (size_t)s->cfg.heaters * s->cfg.heaters, nobs = 4 * (size_t)NC;
+    if (obs && !s->obs) CK(cudaMalloc((void**)&s->obs, B * nobs * sizeof(float)));
+    CK(cudaMemcpyAsync(s->actions, actions, B * na * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    int rc = rbc3d_step_dev(s, s->actions, obs ? s->obs : nullptr, s->reward, s->nu, s->trunc, s->nan);
+    if (rc) return rc;
+    if (obs) CK(cudaMemcpyAsync(obs, s->obs, B * nobs * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (reward) CK(cudaMemcpyAsync(reward, s->reward, B * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (nusselt) CK(cudaMemcpyAsync(nusselt, s->nu, B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (trunc) CK(cudaMemcpyAsync(trunc, s->trunc, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (nan) CK(cudaMemcpyAsync(nan, s->nan, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int rbc3d_observe_dev(rbc3d_sim* s, float* obs, double* nusselt)
+{
+    if (!s) return rbc_fail("null handle");
+    CK(cudaSetDevice(s->cfg.device));
+    RunFlags3 F{0, 0, 0};
+    return dispatch3(s, nullptr, obs, nullptr, nusselt, nullptr, nullptr, nullptr, s->B, F, false, obs != nullptr);
+}
+
+int rbc3d_get_fields_host(rbc3d_sim* s, double* out)
+{
+    if (!s || !out) return rbc_fail("rbc3d_get_fields_host: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    const size_t total = (size_t)s->B * NSTATE;
+    double* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, total * sizeof(double)));
+    if (s->cfg.precision == 32) rbc3d_get_fields_kernel<float><<<148 * 8, 256, 0, s->stream>>>((const float*)s->state, tmp, total);
+    else rbc3d_get_fields_kernel<double><<<148 * 8, 256, 0, s->stream>>>((const double*)s->state, tmp, total);
+    s->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, total * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return rbc_fail(std::string("rbc3d_get_fields_host: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int rbc3d_get_info_host(rbc3d_sim* s, double* t, int32_t* step)
+{
+    if (!s) return rbc_fail("null handle");
+    CK(cudaSetDevice(s->cfg.device));
+    if (t) CK(cudaMemcpyAsync(t, s->t, s->B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (step) CK(cudaMemcpyAsync(step, s->step, s->B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int rbc3d_launch_count(const rbc3d_sim* s, int64_t* launches, int32_t* grid, int32_t* smem_bytes)
+{
+    if (!s) return rbc_fail("null handle");
+    if (launches) *launches = s->launches;
+    if (grid) *grid = s->B < s->grid ? s->B : s->grid;
+    if (smem_bytes) *smem_bytes = (int32_t)s->smem;
+    return 0;
+}
+
+int rbc3d_last_step_kernel_ms(rbc3d_sim* s, float* ms)
+{
+    if (!s || !ms) return rbc_fail("rbc3d_last_step_kernel_ms: bad argument");
+    if (!s->timed) return rbc_fail("rbc3d_last_step_kernel_ms: no step has been launched");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaEventSynchronize(s->ev1));
+    CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    return 0;
+}
+
+}  // extern "C"

@@ -282,6 +282,19 @@ def load_checkpoint_2d(path) -> Checkpoint2D:
     return Checkpoint2D(arrs["b"], arrs["u"], arrs["w"], n, int(f.attrs.get("start_seed", 0)))
 
 
+def load_checkpoint_3d(path) -> np.ndarray:
+    """Read a `3D_ckpt_ra*.h5` (datasets b,u,v,w with Julia dims (n_ep, Nx, Ny, Nz|Nz+1), written at
+    `rbc_sim3D.jl:57-65`) into a bank `[n_ep, 3*Nx*Ny*Nz + Nx*Ny*(Nz+1)]` float64 with fields laid out [z][y][x]."""
+    f = read_file(path)
+    parts = []
+    for name in ("b", "u", "v", "w"):
+        a = f.datasets[name]                                   # HDF5 order: (Nz|Nz+1, Ny, Nx, n_ep)
+        if a.ndim != 4:
+            raise H5FormatError(f"dataset {name}: expected 4 dims, got {a.shape}")
+        parts.append(np.ascontiguousarray(np.moveaxis(a, 3, 0), dtype=np.float64).reshape(a.shape[3], -1))
+    return np.concatenate(parts, axis=1)
+
+
 # --------------------------------------------------------------------------------------
 # writer (same on-disk structure as the reference files; SURVEY §8a-a10)
 # --------------------------------------------------------------------------------------

@@ -23,10 +23,49 @@ class HostWrappers(C.Structure):
 
 
 def build():
-    srcs = [_HERE / "emu_rbc2d.cpp", _ROOT / "rbc_gym_b200" / "csrc" / "rbc2d_core.h"]
+    csrc = _ROOT / "rbc_gym_b200" / "csrc"
+    srcs = [_HERE / "emu_rbc2d.cpp", _HERE / "emu_rbc3d.cpp", csrc / "rbc2d_core.h", csrc / "rbc3d_core.h"]
     if not _SO.exists() or _SO.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", str(_SO), str(srcs[0])], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", str(_SO), str(srcs[0]), str(srcs[1])],
+                       check=True)
     return _SO
+
+
+class HostConfig3(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("ra", "pr", "lx", "ly", "lz", "b_top", "delta_b", "heater_limit", "heater_duration",
+                                          "dt_solver", "episode_length")] + [("heaters", C.c_int)]
+
+
+def step3(state, actions, ra, precision=64, split=False, heater_duration=0.125, dt_solver=0.01, heaters=8, heater_limit=0.9,
+          episode_length=300.0, project_first=False, nsub=-1, t0=None):
+    """state: [B, 66560] (b,u,v,w flattened, each [z][y][x]); actions [B, 8, 8]."""
+    lib = C.CDLL(str(build()))
+    B = state.shape[0]
+    dt = np.float64 if precision == 64 else np.float32
+    st = np.array(state, dtype=dt, order="C")
+    h = HostConfig3(ra, 0.7, 4 * math.pi, 4 * math.pi, 2.0, 1.0, 1.0, heater_limit, heater_duration, dt_solver, episode_length, heaters)
+    a = np.ascontiguousarray(actions, dtype=np.float32)
+    ob = np.zeros((B, 4, 16, 32, 32), np.float32)
+    rew = np.zeros(B, np.float32)
+    nu = np.zeros(B)
+    t = np.zeros(B) if t0 is None else np.array(t0, dtype=np.float64)
+    sc, tr, nf = np.ones(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    rc = lib.emu_rbc3d_step(C.byref(h), precision, int(split), B, vp(st), vp(a), vp(ob), vp(rew), vp(nu), vp(t), vp(sc), vp(tr), vp(nf),
+                            int(project_first), nsub)
+    assert rc == 0
+    return dict(state=st, obs=ob, reward=rew, nusselt=nu, t=t, step=sc, truncated=tr, nan=nf)
+
+
+def pack3(b, u, v, w):
+    return np.concatenate([x.reshape(x.shape[0], -1) for x in (b, u, v, w)], axis=1)
+
+
+def unpack3(st):
+    B = st.shape[0]
+    n = 16 * 32 * 32
+    return (st[:, :n].reshape(B, 16, 32, 32), st[:, n:2 * n].reshape(B, 16, 32, 32), st[:, 2 * n:3 * n].reshape(B, 16, 32, 32),
+            st[:, 3 * n:].reshape(B, 17, 32, 32))
 
 
 def step(state, actions, ra, dt_action, precision=64, split=False, nxt_global=False, dt_solver=0.03,
