@@ -15,7 +15,8 @@ import numpy as np
 
 from . import backend
 from .envs.rbc2d import noise_initial_fields
-from .h5lite import write_checkpoint
+from .envs.rbc3d import noise_initial_fields_3d
+from .h5lite import write_checkpoint, write_checkpoint_3d
 
 
 def simulate_2d_rb(directory, seed: int = 42, random_inits: int = 20, ra: float = 1e5, pr: float = 0.7, random_kick: float = 0.02,
@@ -45,4 +46,34 @@ def simulate_2d_rb(directory, seed: int = 42, random_inits: int = 20, ra: float 
     ra_tag = int(ra) if float(ra).is_integer() else ra
     path = directory / f"ckpt_ra{ra_tag}.h5"                            # rbc_sim2D.jl:36
     write_checkpoint(path, b, u, w, start_seed=seed)
+    return path, stats
+
+
+def simulate_3d_rb(directory, seed: int = 42, random_inits: int = 20, ra: float = 2500, pr: float = 0.7, random_kick: float = 0.2,
+                   delta_t: float = 0.01, delta_t_snap: float = 0.25, duration: float = 200.0, precision: int = 64, device: int = 0):
+    """3D twin (`src/rbc_gym/sim/rbc_sim3D.jl:13-96`, arguments in `scripts/create_checkpoints_3D.sh`): the reference's 3D
+    checkpoint files are missing from the mount, this regenerates statistically equivalent ones on the device.
+    Times are in free-fall units like the reference's 3D API (`dt_solver`, `heater_duration`)."""
+    import torch
+
+    n = int(random_inits)
+    sim = backend.Sim3D(n, ra=float(ra), pr=pr, heater_duration=float(delta_t_snap), dt_solver=delta_t, episode_length=1e30,
+                        precision=precision, device=device)
+    fields = np.concatenate([noise_initial_fields_3d(np.random.default_rng(seed + i + 1), kick=random_kick) for i in range(n)])
+    sim.reset_from_fields(fields, project=True)
+    zero = torch.zeros((n, sim.heaters, sim.heaters), device=sim.device)
+    total = int(duration // delta_t_snap)
+    for it in range(total):
+        *_, nan = sim.step(zero, want_obs=False)
+        if (it % 50 == 49 or it == total - 1) and bool(nan.any()):
+            raise RuntimeError("[ERROR] NaN values found!")
+    b, u, v, w = backend.split_fields3(sim.fields())
+    _, nu = sim.observe()
+    stats = {"nusselt": nu.cpu().numpy().copy()}
+    sim.close()
+    directory = Path(directory)
+    directory.mkdir(parents=True, exist_ok=True)
+    ra_tag = int(ra) if float(ra).is_integer() else ra
+    path = directory / f"3D_ckpt_ra{ra_tag}.h5"
+    write_checkpoint_3d(path, b, u, v, w, start_seed=seed)
     return path, stats

@@ -286,6 +286,8 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         Ww_lo = upwind5(centred4(wz[1], wz[2], wz[3], wz[4]), wz);
     }
     const Real tb = Tb[i];
+    const Real kdx = C.kappa * C.idx2, kdz = C.kappa * C.idz2, ndx = C.nu * C.idx2, ndz = C.nu * C.idz2;
+    const Real dtg = dt * gam, dtz = dt * zet;
 
     // previous-stage tendencies live in per-CTA global slabs [field][r][tid] (coalesced; one slab is read,
     // the other written, so loads never alias stores).  They are fetched one row ahead so their L2 latency
@@ -325,8 +327,8 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         const Real Fzb_hi = top ? Real(0) : upwind_ord(wz[4], bz + 1, o_face_hi);
         const Real bdn = bot ? (Real(2) * tb - bz[3]) : bz[2];
         const Real bup = top ? (Real(2) * C.b_top - bz[3]) : bz[4];
-        const Real Gb = -((Fx1 - Fx0) * C.idx + (Fzb_hi - Fzb_lo) * C.idz) +
-                        C.kappa * ((bx[4] - Real(2) * bx[3] + bx[2]) * C.idx2 + (bup - Real(2) * bz[3] + bdn) * C.idz2);
+        const Real Gb = (Fx0 - Fx1) * C.idx + (Fzb_lo - Fzb_hi) * C.idz + (bx[4] - Real(2) * bx[3] + bx[2]) * kdx +
+                        (bup - Real(2) * bz[3] + bdn) * kdz;
 
         // ---- u ----
         const Real F0 = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);          // centre i-1
@@ -334,8 +336,8 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         const Real Wu_hi = top ? Real(0) : upwind_ord(centred4(wxn[1], wxn[2], wxn[3], wxn[4]), uz + 1, o_face_hi);
         const Real udn = bot ? -uz[3] : uz[2];
         const Real uup = top ? -uz[3] : uz[4];
-        Real Gu = -((F1 - F0) * C.idx + (Wu_hi - Wu_lo) * C.idz) +
-                  C.nu * ((ux[4] - Real(2) * ux[3] + ux[2]) * C.idx2 + (uup - Real(2) * uz[3] + udn) * C.idz2);
+        Real Gu = (F0 - F1) * C.idx + (Wu_lo - Wu_hi) * C.idz + (ux[4] - Real(2) * ux[3] + ux[2]) * ndx +
+                  (uup - Real(2) * uz[3] + udn) * ndz;
         if (SPLIT) Gu -= (phy[k * RSTR + i] - phy[k * RSTR + col[2]]) * C.idx;
 
         // ---- w (face k; face 0 is the wall) ----
@@ -344,8 +346,8 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         const Real Fw0 = upwind5(ut0, wxr);
         const Real Fw1 = upwind5(ut1, wxr + 1);
         const Real Ww_hi = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen), wz + 1, o_up_cen);
-        Real Gw = -((Fw1 - Fw0) * C.idx + (Ww_hi - Ww_lo) * C.idz) +
-                  C.nu * ((wxr[4] - Real(2) * wxr[3] + wxr[2]) * C.idx2 + (wz[4] - Real(2) * wz[3] + wz[2]) * C.idz2);
+        Real Gw = (Fw0 - Fw1) * C.idx + (Ww_lo - Ww_hi) * C.idz + (wxr[4] - Real(2) * wxr[3] + wxr[2]) * ndx +
+                  (wz[4] - Real(2) * wz[3] + wz[2]) * ndz;
         if (!SPLIT) Gw += Real(0.5) * (bz[2] + bz[3]);
         if (bot) Gw = Real(0);
 
@@ -353,9 +355,9 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         gm_out[(0 * RS + r) * NT + tid] = Gb;
         gm_out[(1 * RS + r) * NT + tid] = Gu;
         gm_out[(2 * RS + r) * NT + tid] = Gw;
-        n[OFF_B + k * SX + i] = bz[3] + dt * (gam * Gb + zet * gb0);
-        n[OFF_U + k * SX + i] = uz[3] + dt * (gam * Gu + zet * gu0);
-        n[OFF_W + k * SX + i] = bot ? Real(0) : wz[3] + dt * (gam * Gw + zet * gw0);
+        n[OFF_B + k * SX + i] = bz[3] + dtg * Gb + dtz * gb0;
+        n[OFF_U + k * SX + i] = uz[3] + dtg * Gu + dtz * gu0;
+        n[OFF_W + k * SX + i] = bot ? Real(0) : wz[3] + dtg * Gw + dtz * gw0;
 
         // ---- slide ----
         Fzb_lo = Fzb_hi; Wu_lo = Wu_hi; Ww_lo = Ww_hi;

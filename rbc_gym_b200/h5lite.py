@@ -336,23 +336,17 @@ def _object_header(messages) -> bytes:
     return struct.pack("<BxHII4x", 1, len(messages), 1, len(body)) + body
 
 
-def write_checkpoint(path, b: np.ndarray, u: np.ndarray, w: np.ndarray, start_seed: int) -> None:
-    """Write arrays ``[ep, z, x]`` as a reference-compatible `ckpt_ra*.h5`.
+def write_h5(path, datasets: Dict[str, np.ndarray], attrs: Dict[str, int]) -> None:
+    """Write little-endian f64 datasets (given in HDF5/C dimension order) and scalar i64 root attributes with the
+    structure of the reference files: superblock v0, v1 object headers, link messages, v3 attributes, contiguous
+    layout, data starting at 0x800."""
+    payload = {k: np.ascontiguousarray(a, dtype="<f8") for k, a in datasets.items()}
+    names = list(payload)
+    base, data_start = 0x60, 0x800
 
-    Datasets ``b,u,w`` get HDF5 dims ``(Nz|Nz+1, 1, Nx, n_ep)`` of little-endian f64, contiguous;
-    root attributes ``num_episodes`` and ``start_seed`` are scalar i64 (`rbc_sim2D.jl:39-43`).
-    """
-    b, u, w = (np.asarray(a, dtype="<f8") for a in (b, u, w))
-    n_ep = b.shape[0]
-    arrays = {"b": b, "u": u, "w": w}
-    payload = {k: np.ascontiguousarray(np.transpose(a, (1, 2, 0))[:, None, :, :]) for k, a in arrays.items()}
-
-    base = 0x60
-    data_start = 0x800
-    # dataset headers are fixed-size: dataspace(8+8+32+32=80) datatype(8+24) fill(8+8) layout(8+24) = 168 + 16 hdr
     def ds_header(arr: np.ndarray, addr: int) -> bytes:
         lay = struct.pack("<BBQQ", 3, 1, addr, arr.nbytes)
-        fill = struct.pack("<BBBB", 2, 2, 2, 1)  # v2, alloc early... matches reference bytes 02 02 02 01
+        fill = struct.pack("<BBBB", 2, 2, 2, 1)
         return _object_header([
             _msg(0x01, _ds_simple(arr.shape)),
             _msg(0x03, _dt_f64(), flags=1),
@@ -360,41 +354,50 @@ def write_checkpoint(path, b: np.ndarray, u: np.ndarray, w: np.ndarray, start_se
             _msg(0x08, lay),
         ])
 
-    hdrs, addrs, off = {}, {}, data_start
-    for k in ("b", "u", "w"):
+    addrs, off = {}, data_start
+    for k in names:
         addrs[k] = off
         off += payload[k].nbytes
     eof = off
+    root_msgs_fixed = [_msg(0x0C, _attr_v3_scalar_i64(k, int(v))) for k, v in attrs.items()]
 
-    # lay out: root header at 0x60, then dataset headers, all before data_start
-    root_msgs_fixed = [
-        _msg(0x0C, _attr_v3_scalar_i64("num_episodes", n_ep)),
-        _msg(0x0C, _attr_v3_scalar_i64("start_seed", int(start_seed))),
-    ]
-    link_len = len(_msg(0x06, struct.pack("<BBB", 1, 0x10, 1) + b"\x01" + b"b" + struct.pack("<Q", 0)))
-    root_len = 16 + sum(len(m) for m in root_msgs_fixed) + 3 * link_len
+    def link(name: str, addr: int) -> bytes:
+        nm = name.encode()
+        return _msg(0x06, struct.pack("<BBB", 1, 0x10, 1) + bytes([len(nm)]) + nm + struct.pack("<Q", addr))
+
+    root_len = 16 + sum(len(m) for m in root_msgs_fixed) + sum(len(link(k, 0)) for k in names)
     p = _pad8(base + root_len)
-    ds_addr = {}
-    for k in ("b", "u", "w"):
+    ds_addr, hdrs = {}, {}
+    for k in names:
         ds_addr[k] = p
         hdrs[k] = ds_header(payload[k], addrs[k])
         p = _pad8(p + len(hdrs[k]))
     if p > data_start:
         raise H5FormatError("header region overflow")
-    links = [
-        _msg(0x06, struct.pack("<BBB", 1, 0x10, 1) + b"\x01" + k.encode() + struct.pack("<Q", ds_addr[k]))
-        for k in ("b", "u", "w")
-    ]
-    root = _object_header(root_msgs_fixed + links)
-
+    root = _object_header(root_msgs_fixed + [link(k, ds_addr[k]) for k in names])
     sb = _SIG + bytes([0, 0, 0, 0, 0, 8, 8, 0]) + struct.pack("<HHI", 4, 16, 0)
     sb += struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
-    # root symbol table entry: link name offset, object header addr, cache type 0, reserved, scratch
     sb += struct.pack("<QQII16x", 0, base, 0, 0)
     buf = bytearray(eof)
     buf[: len(sb)] = sb
     buf[base : base + len(root)] = root
-    for k in ("b", "u", "w"):
+    for k in names:
         buf[ds_addr[k] : ds_addr[k] + len(hdrs[k])] = hdrs[k]
         buf[addrs[k] : addrs[k] + payload[k].nbytes] = payload[k].tobytes()
     Path(path).write_bytes(bytes(buf))
+
+
+def write_checkpoint(path, b: np.ndarray, u: np.ndarray, w: np.ndarray, start_seed: int) -> None:
+    """Write 2D arrays ``[ep, z, x]`` as a reference-compatible `ckpt_ra*.h5`: datasets ``b,u,w`` with HDF5 dims
+    ``(Nz|Nz+1, 1, Nx, n_ep)``, root attributes ``num_episodes`` and ``start_seed`` (`rbc_sim2D.jl:39-43`).  The data
+    section is byte-identical to what the reference writes for the same arrays; header bytes differ in layout only."""
+    arrays = {k: np.asarray(a, dtype="<f8") for k, a in (("b", b), ("u", u), ("w", w))}
+    write_h5(path, {k: np.transpose(a, (1, 2, 0))[:, None, :, :] for k, a in arrays.items()},
+             {"num_episodes": arrays["b"].shape[0], "start_seed": int(start_seed)})
+
+
+def write_checkpoint_3d(path, b, u, v, w, start_seed: int) -> None:
+    """Write 3D arrays ``[ep, z, y, x]`` as `3D_ckpt_ra*.h5` (`rbc_sim3D.jl:57-65`): HDF5 dims ``(Nz|Nz+1, Ny, Nx, n_ep)``."""
+    arrays = {k: np.asarray(a, dtype="<f8") for k, a in (("b", b), ("u", u), ("v", v), ("w", w))}
+    write_h5(path, {k: np.moveaxis(a, 0, 3) for k, a in arrays.items()},
+             {"num_episodes": arrays["b"].shape[0], "start_seed": int(start_seed)})
