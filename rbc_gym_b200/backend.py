@@ -180,6 +180,9 @@ class Sim2D:
         self.B = int(num_envs)
         self.obs_shape = (int(obs_shape[0]), int(obs_shape[1]))
         self.state_shape = (int(state_shape[0]), int(state_shape[1]))
+        self.nz, self.nx = self.state_shape
+        self.ncell = self.nx * self.nz
+        self.nstate = 2 * self.ncell + self.nx * (self.nz + 1)
         self.heaters = int(heaters)
         self.channels = 5 if pressure else 3
         self.precision = int(precision)
@@ -252,8 +255,8 @@ class Sim2D:
                                                             C.c_void_p(idx.data_ptr()), n))
 
     def reset_from_fields(self, fields: np.ndarray, env_ids: Optional[Sequence[int]] = None, project: bool = True):
-        """Reset from explicit `[n, 18528]` float64 fields (b,u,w); `project` mirrors Oceananigans' `set!`."""
-        f = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1, NSTATE)
+        """Reset from explicit `[n, 2*nx*nz + nx*(nz+1)]` float64 fields (b,u,w); `project` mirrors Oceananigans' `set!`."""
+        f = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1, self.nstate)
         ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
         self._use_current_stream()
         self._check(self._L.rbc2d_reset_from_fields_host(self._h, _np_ptr(ids), _np_ptr(f), f.shape[0], int(project)))
@@ -329,14 +332,14 @@ class Sim2D:
     def get_state(self, channels: Optional[int] = None):
         """`get_state` in the Python layout: float32 CUDA tensor `[B, C, Nz, Nx]`."""
         ch = self.channels if channels is None else int(channels)
-        out = self.torch.empty((self.B, ch, NZ, NX), dtype=self.torch.float32, device=self.device)
+        out = self.torch.empty((self.B, ch, self.nz, self.nx), dtype=self.torch.float32, device=self.device)
         self._use_current_stream()
         self._check(self._L.rbc2d_get_state_dev(self._h, C.c_void_p(out.data_ptr()), ch))
         return out
 
     def fields(self) -> np.ndarray:
-        """Raw (b,u,w) in checkpoint layout `[B, 18528]` float64 on the host."""
-        out = np.empty((self.B, NSTATE), np.float64)
+        """Raw (b,u,w) in checkpoint layout `[B, 2*nx*nz + nx*(nz+1)]` float64 on the host."""
+        out = np.empty((self.B, self.nstate), np.float64)
         self._use_current_stream()
         self._check(self._L.rbc2d_get_fields_host(self._h, _np_ptr(out)))
         return out
@@ -360,11 +363,12 @@ class Sim2D:
         return ms.value
 
 
-def split_fields(fields: np.ndarray):
-    """`[B, 18528]` -> b[B,64,96], u[B,64,96], w[B,65,96]."""
+def split_fields(fields: np.ndarray, shape=(NZ, NX)):
+    """`[B, nstate]` -> b[B,nz,nx], u[B,nz,nx], w[B,nz+1,nx] (default grid 64 x 96: `[B, 18528]`)."""
     B = fields.shape[0]
-    return (fields[:, :NCELL].reshape(B, NZ, NX), fields[:, NCELL:2 * NCELL].reshape(B, NZ, NX),
-            fields[:, 2 * NCELL:].reshape(B, NZ + 1, NX))
+    nz, nx = shape
+    nc = nz * nx
+    return (fields[:, :nc].reshape(B, nz, nx), fields[:, nc:2 * nc].reshape(B, nz, nx), fields[:, 2 * nc:].reshape(B, nz + 1, nx))
 
 
 def pack_fields(b, u, w) -> np.ndarray:

@@ -12,6 +12,7 @@
 
 #include "../../include/rbc_b200.h"
 #include "rbc2d_core.h"
+#include "rbc2dx_api.h"
 #include "rbc_common.h"
 
 using namespace rbc2d;
@@ -85,9 +86,10 @@ rbc2d_env_kernel(Consts<Real> C, Tables<Real> T, EnvIO<Real> io, Real* gm_all, R
 }
 
 // state[env_ids[j]] <- bank[ckpt_idx[j]] (fp64 -> Real); clock reset (initialize_simulation, rbc_sim2D_api.jl:66-68)
+// (the small kernels below take the grid as run-time arguments: they serve every registered grid)
 template <typename Real>
 __global__ void rbc2d_reset_kernel(Real* state, const double* bank, const int* env_ids, const int* ckpt_idx, int n, int n_ep,
-                                   double* t, int* step, int* trunc, int* nan)
+                                   double* t, int* step, int* trunc, int* nan, int NSTATE)
 {
     for (int j = blockIdx.y; j < n; j += gridDim.y) {
         const int env = env_ids ? env_ids[j] : j;
@@ -102,7 +104,7 @@ __global__ void rbc2d_reset_kernel(Real* state, const double* bank, const int* e
 
 template <typename Real>
 __global__ void rbc2d_set_fields_kernel(Real* state, const double* fields, const int* env_ids, int n, double* t, int* step,
-                                        int* trunc, int* nan)
+                                        int* trunc, int* nan, int NSTATE)
 {
     for (int j = blockIdx.y; j < n; j += gridDim.y) {
         const int env = env_ids ? env_ids[j] : j;
@@ -115,8 +117,9 @@ __global__ void rbc2d_set_fields_kernel(Real* state, const double* fields, const
 
 // get_state (rbc_sim2D_api.jl:102-118 + rbc2D.py:184-189): [B][C][NZ][NX] float32; w channel = faces 0..NZ-1
 template <typename Real>
-__global__ void rbc2d_get_state_kernel(const Real* state, const Real* pressure, float* out, int B, int channels)
+__global__ void rbc2d_get_state_kernel(const Real* state, const Real* pressure, float* out, int B, int channels, int NCELL, int NSTATE)
 {
+    const int GOFF_B = 0, GOFF_U = NCELL, GOFF_W = 2 * NCELL;
     const size_t per = (size_t)channels * NCELL, total = per * B;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
         const int env = (int)(q / per), r = (int)(q % per), ch = r / NCELL, c = r % NCELL;
@@ -143,6 +146,8 @@ struct rbc2d_sim {
     HostWrappers wr;
     double* cell_dist = nullptr;
     int B = 0, channels = 3, grid = 0, n_ep = 0;
+    int nx = NX, nz = NZ, ncell = NCELL, nwf = NWF, nstate = NSTATE;   // grid of this handle
+    rbc2dx_api::Plan* plan = nullptr;                                  // cluster kernels for grids other than 96 x 64
     size_t smem = 0, real_size = 4;
     cudaStream_t stream = nullptr;
     void *state = nullptr, *gm = nullptr, *nxt = nullptr, *pressure = nullptr;
@@ -219,6 +224,27 @@ static int dispatch_env(rbc2d_sim* s, const float* actions, float* obs, float* r
                         int* nan, const int* env_ids, int n, RunFlags F, bool time_it)
 {
     const bool f32 = s->cfg.precision == 32, split = s->cfg.pressure != 0;
+    if (s->plan) {
+        rbc2dx_api::IoRaw io;
+        io.state = s->state;
+        io.actions = actions ? actions : s->actions;
+        io.obs = obs ? obs : s->obs;
+        io.reward = reward ? reward : s->reward;
+        io.nu_state = nu_s ? nu_s : s->nu_s;
+        io.nu_obs = nu_o ? nu_o : s->nu_o;
+        io.t = s->t;
+        io.step_count = s->step;
+        io.truncated = trunc ? trunc : s->trunc;
+        io.nan_flag = nan ? nan : s->nan;
+        io.cell_dist = s->wr.shaping ? s->cell_dist : nullptr;
+        if (n <= 0) return 0;
+        if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
+        int rc = rbc2dx_api::launch(s->plan, s->hc, s->wr, io, env_ids, n, F, s->stream);
+        if (rc) return rc;
+        if (time_it) { CK(cudaEventRecord(s->ev1, s->stream)); s->timed = true; }
+        s->launches += 1;
+        return 0;
+    }
     if (f32) return split ? launch_env<float, true>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it)
                           : launch_env<float, false>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it);
     return split ? launch_env<double, true>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it)
@@ -237,11 +263,14 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
 {
     if (!cfg || !out) return fail("rbc2d_create: null argument");
     *out = nullptr;
-    if (cfg->nx != NX || cfg->nz != NZ) return fail("rbc2d_create: this build supports a 96 x 64 grid only");
+    const bool dedicated = (cfg->nx == NX && cfg->nz == NZ) && !(rbc2dx_api::supported(cfg->nx, cfg->nz) && !cfg->pressure);
+    if (!dedicated && !rbc2dx_api::supported(cfg->nx, cfg->nz))
+        return fail("rbc2d_create: registered grids are 96 x 64 and 192 x 128");
+    if (!dedicated && cfg->pressure) return fail("rbc2d_create: pressure channels are available on the 96 x 64 grid only");
     if (cfg->num_envs < 1) return fail("rbc2d_create: num_envs must be >= 1");
     if (cfg->precision != 32 && cfg->precision != 64) return fail("rbc2d_create: precision must be 32 or 64");
     if (cfg->heaters < 1 || cfg->heaters > MAX_HEATERS) return fail("rbc2d_create: heaters must be in 1..32");
-    if (cfg->obs_nx < 1 || cfg->obs_nz < 2 || NX % cfg->obs_nx || NZ % cfg->obs_nz)
+    if (cfg->obs_nx < 1 || cfg->obs_nz < 2 || cfg->nx % cfg->obs_nx || cfg->nz % cfg->obs_nz)
         return fail("rbc2d_create: sensors must divide the grid (and obs_nz >= 2)");
     if (!(cfg->ra > 0) || !(cfg->pr > 0) || !(cfg->dt_action > 0) || !(cfg->dt_solver > 0))
         return fail("rbc2d_create: ra, pr, dt_action, dt_solver must be positive");
@@ -256,17 +285,26 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
     s->B = cfg->num_envs;
     s->channels = cfg->pressure ? 5 : 3;
     s->real_size = cfg->precision == 32 ? 4 : 8;
+    s->nx = cfg->nx; s->nz = cfg->nz; s->ncell = cfg->nx * cfg->nz; s->nwf = cfg->nx * (cfg->nz + 1); s->nstate = 2 * s->ncell + s->nwf;
     s->hc = HostConfig{cfg->ra, cfg->pr, 2.0 * 3.14159265358979323846, 2.0, 1.0, cfg->heater_limit, cfg->dt_action,
                        cfg->dt_solver, cfg->episode_length, cfg->heaters, cfg->obs_nz, cfg->obs_nx, s->channels};
     int rc;
     const bool f32 = cfg->precision == 32, split = cfg->pressure != 0;
-    rc = f32 ? upload_tables<float>(s) : upload_tables<double>(s);
-    if (rc) { rbc2d_destroy(s); return rc; }
-    if (f32) rc = split ? prepare_kernel<float, true>(s) : prepare_kernel<float, false>(s);
-    else rc = split ? prepare_kernel<double, true>(s) : prepare_kernel<double, false>(s);
-    if (rc) { rbc2d_destroy(s); return rc; }
+    if (dedicated) {
+        rc = f32 ? upload_tables<float>(s) : upload_tables<double>(s);
+        if (rc) { rbc2d_destroy(s); return rc; }
+        if (f32) rc = split ? prepare_kernel<float, true>(s) : prepare_kernel<float, false>(s);
+        else rc = split ? prepare_kernel<double, true>(s) : prepare_kernel<double, false>(s);
+        if (rc) { rbc2d_destroy(s); return rc; }
+    } else {
+        rc = rbc2dx_api::create(cfg->nx, cfg->nz, cfg->precision, cfg->device, s->hc.lx, s->hc.lz, &s->plan);
+        if (rc) { rbc2d_destroy(s); return rc; }
+        s->smem = rbc2dx_api::smem_bytes(s->plan);
+        s->grid = rbc2dx_api::grid_ctas(s->plan, 1 << 30);
+    }
 
     const size_t B = s->B, rs = s->real_size;
+    const size_t NSTATE = s->nstate, NCELL = s->ncell;
     const size_t nobs = (size_t)s->channels * cfg->obs_nz * cfg->obs_nx;
 #define ALLOC(ptr, bytes)                                                         \
     do {                                                                          \
@@ -279,8 +317,10 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
         cudaMemset((ptr), 0, (bytes));                                            \
     } while (0)
     ALLOC(s->state, B * NSTATE * rs);
-    ALLOC(s->gm, (size_t)s->grid * 2 * NSTATE * rs);
-    if (!f32) ALLOC(s->nxt, (size_t)s->grid * NS_SM * rs);
+    if (dedicated) {
+        ALLOC(s->gm, (size_t)s->grid * 2 * NSTATE * rs);
+        if (!f32) ALLOC(s->nxt, (size_t)s->grid * NS_SM * rs);
+    }
     if (split) ALLOC(s->pressure, B * 2 * NCELL * rs);
     ALLOC(s->t, B * sizeof(double));
     ALLOC(s->nu_s, B * sizeof(double));
@@ -310,6 +350,7 @@ int rbc2d_destroy(rbc2d_sim* s)
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    rbc2dx_api::destroy(s->plan);
     delete s;
     return 0;
 }
@@ -321,12 +362,13 @@ int rbc2d_set_stream(rbc2d_sim* s, void* stream)
     return 0;
 }
 int rbc2d_num_envs(const rbc2d_sim* s) { return s ? s->B : -1; }
-int rbc2d_state_values_per_env(const rbc2d_sim* s) { return s ? NSTATE : -1; }
+int rbc2d_state_values_per_env(const rbc2d_sim* s) { return s ? s->nstate : -1; }
 
 int rbc2d_load_checkpoints(rbc2d_sim* s, const double* b, const double* u, const double* w, int32_t n_ep)
 {
     if (!s || !b || !u || !w || n_ep < 1) return fail("rbc2d_load_checkpoints: bad argument");
     CK(cudaSetDevice(s->cfg.device));
+    const size_t NSTATE = s->nstate, NCELL = s->ncell, NWF = s->nwf, GOFF_B = 0, GOFF_U = NCELL, GOFF_W = 2 * NCELL;
     if (s->bank) { cudaFree(s->bank); s->bank = nullptr; }
     CK(cudaMalloc((void**)&s->bank, (size_t)n_ep * NSTATE * sizeof(double)));
     for (int e = 0; e < n_ep; ++e) {
@@ -349,9 +391,9 @@ int rbc2d_reset_from_checkpoints_dev(rbc2d_sim* s, const int32_t* env_ids, const
     if (n <= 0) return 0;
     dim3 grid(8, n < 4096 ? n : 4096);
     if (s->cfg.precision == 32)
-        rbc2d_reset_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, s->bank, env_ids, ckpt_idx, n, s->n_ep, s->t, s->step, s->trunc, s->nan);
+        rbc2d_reset_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, s->bank, env_ids, ckpt_idx, n, s->n_ep, s->t, s->step, s->trunc, s->nan, s->nstate);
     else
-        rbc2d_reset_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, s->bank, env_ids, ckpt_idx, n, s->n_ep, s->t, s->step, s->trunc, s->nan);
+        rbc2d_reset_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, s->bank, env_ids, ckpt_idx, n, s->n_ep, s->t, s->step, s->trunc, s->nan, s->nstate);
     CK(cudaGetLastError());
     s->launches += 1;
     if (s->cfg.pressure) {   // set! projects and leaves pNHS; pHY' follows from b
@@ -367,6 +409,7 @@ int rbc2d_reset_from_fields_host(rbc2d_sim* s, const int32_t* env_ids_host, cons
     CK(cudaSetDevice(s->cfg.device));
     double* dfields = nullptr;
     int* dids = nullptr;
+    const size_t NSTATE = s->nstate;
     CK(cudaMalloc((void**)&dfields, (size_t)n * NSTATE * sizeof(double)));
     CK(cudaMemcpyAsync(dfields, fields, (size_t)n * NSTATE * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     if (env_ids_host) {
@@ -375,9 +418,9 @@ int rbc2d_reset_from_fields_host(rbc2d_sim* s, const int32_t* env_ids_host, cons
     }
     dim3 grid(8, n < 4096 ? n : 4096);
     if (s->cfg.precision == 32)
-        rbc2d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, dfields, dids, n, s->t, s->step, s->trunc, s->nan);
+        rbc2d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, dfields, dids, n, s->t, s->step, s->trunc, s->nan, s->nstate);
     else
-        rbc2d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, dfields, dids, n, s->t, s->step, s->trunc, s->nan);
+        rbc2d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, dfields, dids, n, s->t, s->step, s->trunc, s->nan, s->nstate);
     CK(cudaGetLastError());
     s->launches += 1;
     int rc = 0;
@@ -477,9 +520,9 @@ int rbc2d_get_state_dev(rbc2d_sim* s, float* out, int32_t channels)
     CK(cudaSetDevice(s->cfg.device));
     const int blocks = 148 * 8;
     if (s->cfg.precision == 32)
-        rbc2d_get_state_kernel<float><<<blocks, 256, 0, s->stream>>>((const float*)s->state, (const float*)s->pressure, out, s->B, channels);
+        rbc2d_get_state_kernel<float><<<blocks, 256, 0, s->stream>>>((const float*)s->state, (const float*)s->pressure, out, s->B, channels, s->ncell, s->nstate);
     else
-        rbc2d_get_state_kernel<double><<<blocks, 256, 0, s->stream>>>((const double*)s->state, (const double*)s->pressure, out, s->B, channels);
+        rbc2d_get_state_kernel<double><<<blocks, 256, 0, s->stream>>>((const double*)s->state, (const double*)s->pressure, out, s->B, channels, s->ncell, s->nstate);
     CK(cudaGetLastError());
     s->launches += 1;
     return 0;
@@ -490,7 +533,7 @@ int rbc2d_get_state_host(rbc2d_sim* s, float* out, int32_t channels)
     if (!s || !out) return fail("rbc2d_get_state_host: bad argument");
     CK(cudaSetDevice(s->cfg.device));
     float* tmp = nullptr;
-    const size_t bytes = (size_t)s->B * channels * NCELL * sizeof(float);
+    const size_t bytes = (size_t)s->B * channels * s->ncell * sizeof(float);
     CK(cudaMalloc((void**)&tmp, bytes));
     int rc = rbc2d_get_state_dev(s, tmp, channels);
     if (!rc) {
@@ -506,7 +549,7 @@ int rbc2d_get_fields_host(rbc2d_sim* s, double* out)
 {
     if (!s || !out) return fail("rbc2d_get_fields_host: bad argument");
     CK(cudaSetDevice(s->cfg.device));
-    const size_t total = (size_t)s->B * NSTATE;
+    const size_t total = (size_t)s->B * s->nstate;
     double* tmp = nullptr;
     CK(cudaMalloc((void**)&tmp, total * sizeof(double)));
     if (s->cfg.precision == 32) rbc2d_get_fields_kernel<float><<<148 * 8, 256, 0, s->stream>>>((const float*)s->state, tmp, total);
@@ -534,7 +577,7 @@ int rbc2d_launch_count(const rbc2d_sim* s, int64_t* launches, int32_t* grid, int
 {
     if (!s) return fail("null handle");
     if (launches) *launches = s->launches;
-    if (grid) *grid = s->B < s->grid ? s->B : s->grid;
+    if (grid) *grid = s->plan ? rbc2dx_api::grid_ctas(s->plan, s->B) : (s->B < s->grid ? s->B : s->grid);
     if (smem_bytes) *smem_bytes = (int32_t)s->smem;
     return 0;
 }

@@ -22,13 +22,24 @@ class HostWrappers(C.Structure):
                 ("shaping_weight", C.c_double)]
 
 
+_SOX = _HERE / "libemu_rbc2dx.so"
+
+
+def _compile(so, cpps, deps):
+    if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in list(cpps) + list(deps)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", str(so), *map(str, cpps)], check=True)
+    return so
+
+
 def build():
     csrc = _ROOT / "rbc_gym_b200" / "csrc"
-    srcs = [_HERE / "emu_rbc2d.cpp", _HERE / "emu_rbc3d.cpp", csrc / "rbc2d_core.h", csrc / "rbc3d_core.h"]
-    if not _SO.exists() or _SO.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", str(_SO), str(srcs[0]), str(srcs[1])],
-                       check=True)
-    return _SO
+    return _compile(_SO, [_HERE / "emu_rbc2d.cpp", _HERE / "emu_rbc3d.cpp"], [csrc / "rbc2d_core.h", csrc / "rbc3d_core.h"])
+
+
+def build_x():
+    """The cluster kernel for generic grids (rbc2dx_core.h), emulated."""
+    csrc = _ROOT / "rbc_gym_b200" / "csrc"
+    return _compile(_SOX, [_HERE / "emu_rbc2dx.cpp"], [csrc / "rbc2d_core.h", csrc / "rbc2dx_core.h"])
 
 
 class HostConfig3(C.Structure):
@@ -99,3 +110,36 @@ def pack(b, u, w):
 def unpack(st):
     B = st.shape[0]
     return st[:, :6144].reshape(B, 64, 96), st[:, 6144:12288].reshape(B, 64, 96), st[:, 12288:].reshape(B, 65, 96)
+
+
+def stepx(state, actions, ra, dt_action, nx=96, nz=64, cl=1, precision=64, nxt_global=False, dt_solver=0.03, obs=(8, 48), heaters=12,
+          heater_limit=0.75, episode_length=300.0, t0=None, wrappers=None, project_first=False, nsub=-1):
+    """One action step through the emulated CLUSTER kernel (rbc2dx_core.h): grid nx x nz split over `cl` CTAs.
+    state: [B, 2*nx*nz + nx*(nz+1)] (b,u,w flattened)."""
+    lib = C.CDLL(str(build_x()))
+    B = state.shape[0]
+    dt = np.float64 if precision == 64 else np.float32
+    st = np.array(state, dtype=dt, order="C")
+    h = HostConfig(ra, 0.7, 2 * math.pi, 2.0, 1.0, heater_limit, dt_action, dt_solver, episode_length, heaters, obs[0], obs[1], 3)
+    a = np.ascontiguousarray(actions, dtype=np.float32)
+    ob = np.zeros((B, 3, obs[0], obs[1]), np.float32)
+    rew = np.zeros(B, np.float32)
+    nus, nuo = np.zeros(B), np.zeros(B)
+    t = np.zeros(B) if t0 is None else np.array(t0, dtype=np.float64)
+    sc, tr, nf = np.ones(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
+    cd = np.zeros(B)
+    rc = lib.emu_rbc2dx_step(C.byref(h), C.byref(wrappers) if wrappers is not None else None, vp(cd), nx, nz, cl, precision, int(nxt_global), B,
+                             vp(st), vp(a), vp(ob), vp(rew), vp(nus), vp(nuo), vp(t), vp(sc), vp(tr), vp(nf), int(project_first), nsub)
+    assert rc == 0, rc
+    return dict(state=st, obs=ob, reward=rew, nu_state=nus, nu_obs=nuo, t=t, step=sc, truncated=tr, nan=nf, cell_dist=cd)
+
+
+def packx(b, u, w):
+    return pack(b, u, w)
+
+
+def unpackx(st, nx, nz):
+    B = st.shape[0]
+    n = nx * nz
+    return st[:, :n].reshape(B, nz, nx), st[:, n:2 * n].reshape(B, nz, nx), st[:, 2 * n:].reshape(B, nz + 1, nx)

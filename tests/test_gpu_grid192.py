@@ -1,0 +1,150 @@
+"""Config 3 (192 x 128, Ra=1e6, dt_solver=0.015) on the GPU: the thread-block-cluster kernel (one cluster per
+environment, slabs in distributed shared memory) through the C ABI against the fp64 oracle.
+
+Tolerances as for the 96 x 64 grid: rel-L2 per field after one action step <= 1e-10 (fp64), <= 1e-5 (fp32)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+from tests.gridstates import smooth_state  # noqa: E402
+
+NX, NZ, RA, DTS = 192, 128, 1e6, 0.015
+
+
+def rel(x, y):
+    return np.linalg.norm(x - y) / np.linalg.norm(y)
+
+
+@pytest.fixture(scope="module")
+def B():
+    from rbc_gym_b200 import backend
+    return backend
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-10), (32, 1e-5)])
+def test_one_action_step_192x128_matches_oracle(B, precision, tol):
+    import torch
+    P = O.make_params(RA, nx=NX, nz=NZ, split_phy=False)
+    states = [smooth_state(NX, NZ, seed=s) for s in (0, 1, 2)]
+    rng = np.random.default_rng(7)
+    acts = rng.uniform(-1, 1, (3, 12)).astype(np.float32)
+    acts[2] = 0
+    dt = 0.1                                                  # 6 x 0.015 + 0.01: 7 RK3 steps, clipped last step
+    sim = B.Sim2D(3, ra=RA, dt_action=dt, dt_solver=DTS, state_shape=(NZ, NX), obs_shape=(8, 48), precision=precision)
+    sim.reset_from_fields(np.concatenate([B.pack_fields(b[None], u[None], w[None]) for b, u, w in states]), project=False)
+    obs, rew, nus, nuo, trunc, nan = sim.step(torch.from_numpy(acts).cuda())
+    b, u, w = B.split_fields(sim.fields(), (NZ, NX))
+    t, step = sim.info()
+    assert np.all(t == dt) and np.all(step == 2) and not nan.any().item() and not trunc.any().item()
+    for j, (b0, u0, w0) in enumerate(states):
+        r = O.step(P, b0, u0, w0, acts[j].astype(np.float64), O.substep_schedule(dt, DTS))
+        assert rel(b[j], r["b"]) < tol and rel(u[j], r["u"]) < tol and rel(w[j], r["w"]) < tol
+        ns, no = O.nusselt_state_obs(P, r["b"], r["u"], r["w"])
+        nu_tol = 1e-8 if precision == 64 else 2e-3
+        assert nus[j].item() == pytest.approx(ns, abs=nu_tol) and nuo[j].item() == pytest.approx(no, abs=nu_tol)
+        assert rew[j].item() == pytest.approx(-no, abs=max(nu_tol, 1e-4))
+        ref_obs = O.observe(O.state_channels(r["b"], r["u"], r["w"]))
+        np.testing.assert_allclose(obs[j].cpu().numpy(), ref_obs, rtol=0, atol=2e-7 if precision == 64 else 1e-5)
+    st = sim.get_state().cpu().numpy()
+    assert st.shape == (3, 3, NZ, NX)
+    np.testing.assert_allclose(st[0, 2], w[0, :-1], rtol=0, atol=1e-6)
+    info = sim.launch_info()
+    assert info["grid"] == 3 * (4 if precision == 32 else 8)   # one cluster per environment
+    sim.close()
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_more_envs_than_clusters_is_replica_exact_192(B, precision):
+    import torch
+    n = 90                                                    # > 33 resident clusters of 4 (or 16 of 8)
+    base = [smooth_state(NX, NZ, seed=s) for s in (0, 1, 2)]
+    fields = np.concatenate([B.pack_fields(*(a[None] for a in base[i % 3])) for i in range(n)])
+    sim = B.Sim2D(n, ra=RA, dt_action=0.045, dt_solver=DTS, state_shape=(NZ, NX), precision=precision)
+    sim.reset_from_fields(fields, project=False)
+    acts = np.stack([np.cos(2 * np.pi * np.arange(12) / 12) * ((i % 3) / 2.0) for i in range(n)]).astype(np.float32)
+    obs, rew, *_ = sim.step(torch.from_numpy(acts).cuda())
+    f = sim.fields()
+    r = rew.cpu().numpy()
+    for i in range(3, n):
+        assert np.array_equal(f[i], f[i % 3]) and r[i] == r[i % 3]
+    sim.close()
+
+
+def test_config3_env_noise_init_wrappers_rollout(B):
+    """Config 3 end to end: the reference env class at doubled resolution, noise initialisation (kick 0.01, seed 42)
+    projected on the device, NormalizeReward + reward shaping fused, a short fp32 rollout that stays solenoidal."""
+    import torch
+    from rbc_gym_b200.envs.rbc2d import noise_initial_fields
+    from rbc_gym_b200 import wrappers as W
+    nenv = 8
+    sim = B.Sim2D(nenv, ra=RA, dt_action=0.3, dt_solver=DTS, state_shape=(NZ, NX), precision=32)
+    rng = np.random.default_rng(42)
+    sim.reset_from_fields(np.concatenate([noise_initial_fields(rng, (NZ, NX), kick=0.01) for _ in range(nenv)]), project=True)
+    b, u, w = B.split_fields(sim.fields(), (NZ, NX))
+    dx, dz = 2 * np.pi / NX, 2.0 / NZ
+    div = (np.roll(u, -1, axis=-1) - u) / dx + (w[:, 1:] - w[:, :-1]) / dz
+    assert np.abs(div).max() < 5e-5 and np.all(w[:, 0] == 0) and np.all(w[:, -1] == 0)
+    sim.set_wrappers(normalize_obs=True, normalize_reward=True, shaping_weight=0.1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for _ in range(3):
+        a = torch.rand((nenv, 12), device="cuda", generator=g) * 2 - 1
+        obs, rew, nus, nuo, trunc, nan = sim.step(a)
+    assert not nan.any().item()
+    state = sim.get_state().cpu().numpy()
+    cds = sim.cell_dist()
+    for j in range(nenv):
+        cd = W.cell_distance(state[j], size_state=(NZ, NX))
+        assert cds[j] == pytest.approx(cd, abs=1e-9)
+        r = W.shape_reward(W.normalize_reward(float(-nuo[j].item()), RA), cd, 0.1)
+        assert rew[j].item() == pytest.approx(r, rel=1e-5, abs=1e-6)
+    b, u, w = B.split_fields(sim.fields(), (NZ, NX))
+    div = (np.roll(u, -1, axis=-1) - u) / dx + (w[:, 1:] - w[:, :-1]) / dz
+    assert np.abs(div).max() < 1e-4
+    sim.close()
+
+
+def test_env_class_at_192x128(B):
+    from rbc_gym_b200.envs.rbc2d import RayleighBenardConvection2DEnv
+    env = RayleighBenardConvection2DEnv(rayleigh_number=1_000_000, state_shape=[NZ, NX], observation_shape=[8, 48],
+                                        heater_duration=0.15, dt_solver=DTS, precision=64)
+    obs, info = env.reset(seed=42)
+    assert obs.shape == (3, 8, 48) and info["state"].shape == (3, NZ, NX)
+    obs, reward, terminated, truncated, info = env.step(env.action_space.sample())
+    assert np.isfinite(reward) and info["t"] == pytest.approx(0.15) and not truncated
+    assert info["nusselt_obs"] == pytest.approx(-reward)
+    env.close()
+
+
+def test_unregistered_grid_and_pressure_are_rejected(B):
+    with pytest.raises(RuntimeError, match="registered grids"):
+        B.Sim2D(1, ra=1e5, state_shape=(100, 200))
+    with pytest.raises(RuntimeError, match="pressure"):
+        B.Sim2D(1, ra=1e5, state_shape=(NZ, NX), pressure=True)
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-12), (32, 2e-6)])
+def test_cluster_kernel_on_96x64_agrees_with_dedicated_kernel(B, ckpt_ra1e5, precision, tol):
+    """RBC_B200_CLUSTER=1 routes the 96 x 64 grid through the 2-CTA cluster kernel: same results as the one-CTA kernel."""
+    import torch
+    c = ckpt_ra1e5
+    acts = np.random.default_rng(3).uniform(-1, 1, (4, 12)).astype(np.float32)
+    out = []
+    for flag in ("0", "1"):
+        os.environ["RBC_B200_CLUSTER"] = flag
+        try:
+            sim = B.Sim2D(4, ra=1e5, dt_action=0.3, precision=precision)
+        finally:
+            os.environ.pop("RBC_B200_CLUSTER", None)
+        sim.load_checkpoints(c)
+        sim.reset_from_checkpoints(torch.tensor([0, 7, 3, 16], dtype=torch.int32))
+        _, rew, nus, nuo, *_ = sim.step(torch.from_numpy(acts).cuda())
+        out.append((sim.fields(), nus.cpu().numpy(), nuo.cpu().numpy(), sim.launch_info()["grid"]))
+        sim.close()
+    assert out[0][3] == 4 and out[1][3] == 8
+    assert rel(out[1][0], out[0][0]) < tol
+    np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-9 if precision == 64 else 1e-4)
+    np.testing.assert_allclose(out[1][2], out[0][2], rtol=1e-9 if precision == 64 else 1e-4)

@@ -1,0 +1,107 @@
+"""The cluster kernel for generic 2D grids (rbc_gym_b200/csrc/rbc2dx_core.h) compiled for the host and run
+as a sequential emulator of a thread-block cluster (CTAs one after the other inside every phase, remote
+shared memory = another slice of one arena), checked against the fp64 oracle.  Exercises the slab
+decomposition, halo pushes, the SPIKE-partitioned tridiagonal solve, the N1 x N2 FFT and the cross-CTA
+reductions; the `-m gpu` tests repeat the comparison on the device (tests/test_gpu_grid192.py)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from rbc_gym_b200 import wrappers as W
+from tests.emu import emu
+from tests.gridstates import smooth_state
+
+
+def rel(x, y):
+    return np.linalg.norm(x - y) / np.linalg.norm(y)
+
+
+COS = np.cos(2 * np.pi * np.arange(12) / 12).astype(np.float32)
+
+
+@pytest.mark.parametrize("cl", [1, 2, 4])
+@pytest.mark.parametrize("nxt_global", [False, True])
+def test_96x64_any_cluster_size_matches_oracle(ckpt_ra1e5, cl, nxt_global):
+    c = ckpt_ra1e5
+    eps, acts = [0, 7], np.stack([COS, np.linspace(-1, 1, 12).astype(np.float32)])
+    e = emu.stepx(emu.pack(c.b[eps], c.u[eps], c.w[eps]), acts, 1e5, 0.09, cl=cl, precision=64, nxt_global=nxt_global)
+    b, u, w = emu.unpackx(e["state"], 96, 64)
+    P = O.make_params(1e5, split_phy=False)
+    for j, ep in enumerate(eps):
+        r = O.step(P, c.b[ep], c.u[ep], c.w[ep], acts[j].astype(np.float64), O.substep_schedule(0.09))
+        assert rel(b[j], r["b"]) < 1e-13 and rel(u[j], r["u"]) < 1e-13 and rel(w[j], r["w"]) < 1e-13
+        ns, no = O.nusselt_state_obs(P, r["b"], r["u"], r["w"])
+        assert e["nu_state"][j] == pytest.approx(ns, abs=1e-10) and e["nu_obs"][j] == pytest.approx(no, abs=1e-10)
+        np.testing.assert_array_equal(e["obs"][j], O.observe(O.state_channels(r["b"], r["u"], r["w"])).astype(np.float32))
+    assert np.all(e["nan"] == 0) and np.all(e["t"] == 0.09) and np.all(e["step"] == 2)
+
+
+@pytest.mark.parametrize("nx,nz,cl,obs", [(192, 128, 4, (8, 48)), (192, 128, 8, (16, 96)), (128, 64, 2, (8, 64))])
+def test_other_grids_match_oracle(nx, nz, cl, obs):
+    """config 3's grid (192 x 128, Ra=1e6, dt_solver=0.015: the heater's cubic blends fire) and a power-of-two
+    width (4 x 16 FFT split), fp64 to round-off and fp32 within the stated tolerance."""
+    ra, dts = 1e6, 0.015
+    P = O.make_params(ra, nx=nx, nz=nz, split_phy=False)
+    b, u, w = smooth_state(nx, nz)
+    act = np.random.default_rng(1).uniform(-1, 1, 12).astype(np.float32)
+    if nx == 192:
+        Tb = O.heater_profile(P, act)
+        assert len(np.unique(np.round(Tb, 12))) > 12           # not piecewise constant: blends active
+    dt = 3 * dts + dts / 3
+    r = O.step(P, b, u, w, act.astype(np.float64), O.substep_schedule(dt, dts))
+    ns, no = O.nusselt_state_obs(P, r["b"], r["u"], r["w"], obs)
+    st = emu.pack(b[None], u[None], w[None])
+    for precision, nxt_global, tol in ((64, False, 1e-13), (64, True, 1e-13), (32, False, 2e-6)):
+        e = emu.stepx(st, act[None], ra, dt, nx=nx, nz=nz, cl=cl, precision=precision, nxt_global=nxt_global, dt_solver=dts, obs=obs)
+        bb, uu, ww = emu.unpackx(e["state"].astype(np.float64), nx, nz)
+        assert rel(bb[0], r["b"]) < tol and rel(uu[0], r["u"]) < tol and rel(ww[0], r["w"]) < tol
+        assert e["nu_state"][0] == pytest.approx(ns, abs=1e-9 if precision == 64 else 1e-3)
+        assert e["nu_obs"][0] == pytest.approx(no, abs=1e-9 if precision == 64 else 1e-3)
+        ref_obs = O.observe(O.state_channels(r["b"], r["u"], r["w"]), obs).astype(np.float32)
+        np.testing.assert_allclose(e["obs"][0], ref_obs, rtol=0, atol=0 if precision == 64 else 2e-6)
+        assert e["nan"][0] == 0 and e["step"][0] == 2
+
+
+def test_set_projection_of_noise_init_192():
+    """reset-from-noise path: project_first (Oceananigans set!) through the SPIKE solve == the oracle projection."""
+    nx, nz = 192, 128
+    rng = np.random.default_rng(42)
+    u = 0.01 * rng.standard_normal((nz, nx))
+    w = 0.01 * rng.standard_normal((nz + 1, nx))
+    w[0] = 0
+    w[-1] = 0
+    b = np.ones((nz, nx)) * 1.5
+    P = O.make_params(1e6, nx=nx, nz=nz, split_phy=False)
+    up, wp, _ = O.project(P, u, w)
+    e = emu.stepx(emu.pack(b[None], u[None], w[None]), np.zeros((1, 12), np.float32), 1e6, 0.015, nx=nx, nz=nz, cl=4, precision=64,
+                  dt_solver=0.015, project_first=True, nsub=0)
+    _, uu, ww = emu.unpackx(e["state"], nx, nz)
+    assert rel(uu[0], up) < 1e-12 and rel(ww[0], wp) < 1e-12
+    div = (np.roll(uu[0], -1, axis=-1) - uu[0]) / (2 * np.pi / nx) + (ww[0, 1:] - ww[0, :-1]) / (2 / nz)
+    assert np.abs(div).max() < 1e-12
+
+
+def test_cluster_flags_and_fused_wrappers_192():
+    nx, nz, ra, dts = 192, 128, 1e6, 0.015
+    b, u, w = smooth_state(nx, nz, seed=3)
+    st = np.repeat(emu.pack(b[None], u[None], w[None]), 2, axis=0)
+    st[1, nx * 100 + 17] = np.nan                          # a NaN in the slab of cluster rank 3
+    acts = np.random.default_rng(5).uniform(-1, 1, (2, 12)).astype(np.float32)
+    e = emu.stepx(st, acts, ra, 2 * dts, nx=nx, nz=nz, cl=4, precision=64, dt_solver=dts, t0=[299.98, 0.0])
+    assert list(e["nan"]) == [0, 1] and list(e["truncated"]) == [1, 0]
+    wr = emu.HostWrappers()
+    wr.normalize_obs, wr.obs_clip, wr.obs_maxval = 1, 0, 1.0
+    for ch, (lo, hi) in enumerate([(1.0, 2.75), (-1.3, 1.3), (-1.3, 1.3), (-1.3, 1.3)]):
+        wr.obs_lo[ch], wr.obs_hi[ch] = lo, hi
+    wr.normalize_reward, wr.reward_scale = 1, 0.1 * ra ** 0.4
+    wr.shaping, wr.shaping_weight = 1, 0.1
+    plain = emu.stepx(st[:1], acts[:1], ra, 2 * dts, nx=nx, nz=nz, cl=4, precision=64, dt_solver=dts)
+    fused = emu.stepx(st[:1], acts[:1], ra, 2 * dts, nx=nx, nz=nz, cl=4, precision=64, dt_solver=dts, wrappers=wr)
+    np.testing.assert_array_equal(fused["state"], plain["state"])
+    bb, uu, ww = emu.unpackx(plain["state"], nx, nz)
+    state = np.stack([bb[0], uu[0], ww[0, :-1]]).astype(np.float32)
+    cd = W.cell_distance(state, size_state=(nz, nx))
+    assert fused["cell_dist"][0] == pytest.approx(cd, abs=1e-12) and cd > 0
+    rwd = W.shape_reward(W.normalize_reward(float(-plain["nu_obs"][0]), ra), cd, 0.1)
+    assert fused["reward"][0] == pytest.approx(rwd, rel=1e-6)
+    np.testing.assert_allclose(fused["obs"][0], W.normalize_observation(plain["obs"][0].copy(), 0.75), rtol=2e-6, atol=2e-7)
