@@ -11,8 +11,9 @@
 // shared memory:
 //   * stencil halos    — pushed into the neighbours' halo rows by the thread that produces the value
 //                        (b* and the shared w* face during the tendency march, u and w after the pressure
-//                        correction), fire-and-forget remote stores, made visible by the cluster barrier
-//                        that ends the phase;
+//                        correction) with st.async: fire-and-forget remote stores that complete a transaction
+//                        count on an mbarrier of the RECEIVING CTA, which waits on its own barrier just before it
+//                        consumes the rows — no cluster-wide barrier and no memory fence in the stage loop;
 //   * the z-tridiagonal Poisson solve — SPIKE partitioning: every CTA solves its own NZL-row block with the
 //                        two-sided Thomas sweep, the 2*CL block-end values are exchanged, each CTA applies the
 //                        pre-inverted reduced system (host, fp64) and corrects its block with the two
@@ -20,7 +21,9 @@
 //                        below the slab, which is inverse-transformed locally (idle FFT lanes), so the
 //                        pressure correction needs no further exchange;
 //   * the epilogue reductions (Nusselt numbers, NaN flag).
-// The x-direction (FFT, upwind stencils) never leaves the CTA.  3 cluster barriers per RK3 stage.
+// The x-direction (FFT, upwind stencils) never leaves the CTA.  In fp32 mode the stage loop has no cluster
+// barrier at all (three mbarrier waits per stage, usually already complete); the fp64 validation mode keeps
+// its predicted state in global memory and synchronises with three cluster barriers per stage instead.
 //
 // Plain C++ shared between nvcc and g++ like rbc2d_core.h: tests/emu runs the CTAs of a cluster one after
 // the other inside every phase, with "remote" pointers resolved inside one host arena.
@@ -91,7 +94,7 @@ template <typename Real>
 struct CtxX {
     unsigned char* base;        // device: this CTA's dynamic shared memory; host: arena of rank 0
     size_t arena_stride;        // host: bytes between the arenas of consecutive ranks (device: unused)
-    unsigned o_s0, o_s1, o_R, o_Tb, o_mid, o_ends, o_twN, o_tw2, o_red, o_fin, o_cfin;
+    unsigned o_s0, o_s1, o_R, o_Tb, o_mid, o_ends, o_twN, o_tw2, o_red, o_fin, o_cfin, o_bars;
     Real* gm;                   // global: [CL][2][NLOC] stage tendencies of this cluster (ping-pong slabs)
     Real* nxt_g;                // global: [CL][NS_SM] predicted state (fp64 mode) or nullptr
     // global tables, [CL] blocks each (build_tables_host)
@@ -118,6 +121,9 @@ __device__ __forceinline__ T* peer_ptr(const unsigned char*, size_t, T* p, int /
 }
 #define RBX_PHASE_L(G, ...) { const int tid = threadIdx.x; const int rank = my_rank; unsigned char* const smb = X.base; (void)rank; (void)smb; __VA_ARGS__ } RBX_SYNC_LOCAL;
 #define RBX_PHASE_C(G, ...) { const int tid = threadIdx.x; const int rank = my_rank; unsigned char* const smb = X.base; (void)rank; (void)smb; __VA_ARGS__ } RBX_SYNC_CLUSTER(G);
+// a phase whose cross-CTA stores are tracked by the receivers' mbarriers (ASYNCF) needs only the CTA barrier
+#define RBX_PHASE_X(G, ASYNCF, ...) { const int tid = threadIdx.x; const int rank = my_rank; unsigned char* const smb = X.base; (void)rank; (void)smb; __VA_ARGS__ } \
+    do { if (ASYNCF) __syncthreads(); else RBX_SYNC_CLUSTER(G); } while (0);
 #else
 template <typename T>
 inline T* peer_ptr(const unsigned char*, size_t stride, T* p, int my, int to)
@@ -127,6 +133,107 @@ inline T* peer_ptr(const unsigned char*, size_t stride, T* p, int my, int to)
 #define RBX_PHASE_L(G, ...) for (int rank = 0; rank < G::CL; ++rank) { unsigned char* const smb = X.base + rank * X.arena_stride; (void)smb; \
         for (int tid = 0; tid < G::NT; ++tid) { __VA_ARGS__ } }
 #define RBX_PHASE_C(G, ...) RBX_PHASE_L(G, __VA_ARGS__)
+#define RBX_PHASE_X(G, ASYNCF, ...) RBX_PHASE_L(G, __VA_ARGS__)
+#endif
+
+// ------------------------------------------------------------------------------------------
+// cross-CTA stores.  A PeerBuf names a buffer of another CTA of the cluster:
+//   host emulator      : a pointer into that rank's arena;
+//   device, barrier mode: a generic pointer (DSMEM through map_shared_rank, or the peer's global scratch);
+//   device, async mode  : the shared::cluster address of the buffer and of the receiver's mbarrier; every
+//                         store is a st.async that completes sizeof(Real) bytes on that mbarrier.
+// Channels (one pair of mbarriers each, alternating with the use count so that consecutive uses never share
+// a barrier): W = the w* face from the slab above, E = block-end values of the tridiagonal solve, H = halo rows.
+// ------------------------------------------------------------------------------------------
+enum { CH_W = 0, CH_E = 1, CH_H = 2, NCHAN = 3 };
+struct SyncState { unsigned n[NCHAN]; };              // uses of each channel so far (identical on all CTAs)
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned a, unsigned r)
+{
+    unsigned o;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(o) : "r"(a), "r"(r));
+    return o;
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void st_async(unsigned addr, float v, unsigned bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_async(unsigned addr, double v, unsigned bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(addr), "l"(__double_as_longlong(v)), "r"(bar) : "memory");
+}
+#endif
+
+template <typename Real>
+struct PeerBuf {
+    Real* p;            // nullptr: there is no such peer
+    unsigned addr, bar; // async mode only
+};
+// peer `to`'s copy of the shared-memory region at byte offset data_off; stores complete on its barrier at bar_off
+template <bool ASYNC, typename Real>
+RBC_HD PeerBuf<Real> make_peer(const CtxX<Real>& X, unsigned char* smb, unsigned data_off, unsigned bar_off, int my, int to, bool exists)
+{
+    PeerBuf<Real> pb;
+    pb.p = nullptr; pb.addr = 0; pb.bar = 0;
+    if (!exists) return pb;
+    Real* lp = reinterpret_cast<Real*>(smb + data_off);
+#if defined(__CUDA_ARCH__)
+    if (ASYNC) {
+        pb.addr = mapa_u32(smem_u32(lp), (unsigned)to);
+        pb.bar = mapa_u32(smem_u32(smb + bar_off), (unsigned)to);
+        pb.p = lp;                                           // non-null marker only
+    } else {
+        pb.p = cooperative_groups::this_cluster().map_shared_rank(lp, to);
+    }
+    (void)my; (void)X;
+#else
+    (void)bar_off;
+    pb.p = peer_ptr(X.base, X.arena_stride, lp, my, to);
+#endif
+    return pb;
+}
+template <bool ASYNC, typename Real>
+RBC_HD void peer_store(const PeerBuf<Real>& pb, int idx, Real v)
+{
+#if defined(__CUDA_ARCH__)
+    if (ASYNC) st_async(pb.addr + (unsigned)idx * (unsigned)sizeof(Real), v, pb.bar);
+    else pb.p[idx] = v;
+#else
+    pb.p[idx] = v;
+#endif
+}
+// byte offset of the mbarrier serving use number n of channel ch
+RBC_HD unsigned bar_off(unsigned o_bars, int ch, unsigned n) { return o_bars + (unsigned)(ch * 2 + (int)(n & 1u)) * 8u; }
+
+#if defined(__CUDA_ARCH__)
+#define RBX_ASYNC(G, NXTG) (G::CL > 1 && !(NXTG))
+// consumer side: thread 0 arms the barrier with the bytes this CTA is about to receive, everybody waits for them
+#define RBX_WAIT(ch, cnt, bytes)                                                        \
+    do {                                                                                \
+        const unsigned nbytes_ = (unsigned)(bytes);                                     \
+        if (nbytes_ > 0) {                                                              \
+            const unsigned bar_ = smem_u32(X.base + bar_off(X.o_bars, (ch), (cnt)));    \
+            if (threadIdx.x == 0) mbar_expect_tx(bar_, nbytes_);                        \
+            mbar_wait(bar_, ((cnt) >> 1) & 1u);                                         \
+        }                                                                               \
+    } while (0)
+#else
+#define RBX_ASYNC(G, NXTG) false
+#define RBX_WAIT(ch, cnt, bytes) do { (void)(bytes); } while (0)
 #endif
 
 template <typename G> RBC_HD int wrapx(int i) { return i < 0 ? i + G::NX : (i >= G::NX ? i - G::NX : i); }
@@ -170,10 +277,10 @@ RBC_HD void phase_store_state(int tid, int rank, const Real* RBC_RESTRICT sm, Re
 // arithmetic in the same order).  Halo rows make every window load unconditional; b* rows and the w* face
 // that the neighbouring slabs need before the next barrier are pushed into their buffers as they are made.
 // ------------------------------------------------------------------------------------------
-template <typename G, typename Real>
+template <typename G, bool ASYNC, typename Real>
 RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real* RBC_RESTRICT c, Real* RBC_RESTRICT n,
-                           Real* n_below, Real* n_above, const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out,
-                           Real dt, Real gam, Real zet, bool use_gm)
+                           const PeerBuf<Real>& below_h, const PeerBuf<Real>& below_w, const PeerBuf<Real>& above_h,
+                           const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm)
 {
     constexpr int NX = G::NX, NZ = G::NZ, SX = G::SX, RS = G::RS, NT = G::NT, NZL = G::NZL, H = G::HALO;
     const int i = tid % NX, s = tid / NX, lk0 = s * RS, kg0 = rank * NZL + lk0;
@@ -273,11 +380,11 @@ RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real*
         n[G::OFF_W + lr * SX + i] = wn;
         // halo pushes (b is final after this phase; the w* face shared with the slab below feeds its divergence)
         if (G::CL > 1) {
-            if (lk < H && n_below != nullptr) {
-                n_below[G::OFF_B + (NZL + H + lk) * SX + i] = bn;
-                if (lk == 0) n_below[G::OFF_W + (NZL + H) * SX + i] = wn;
+            if (lk < H && below_h.p != nullptr) {
+                peer_store<ASYNC>(below_h, G::OFF_B + (NZL + H + lk) * SX + i, bn);
+                if (lk == 0) peer_store<ASYNC>(below_w, G::OFF_W + (NZL + H) * SX + i, wn);
             }
-            if (lk >= NZL - H && n_above != nullptr) n_above[G::OFF_B + (lk - NZL + H) * SX + i] = bn;
+            if (lk >= NZL - H && above_h.p != nullptr) peer_store<ASYNC>(above_h, G::OFF_B + (lk - NZL + H) * SX + i, bn);
         }
 
         // ---- slide ----
@@ -501,8 +608,9 @@ RBC_HD void phase_thomas_sweep(int tid, Real* RBC_RESTRICT R, const Real* RBC_RE
     }
     mid[tid] = d;
 }
-template <typename G, typename Real>
-RBC_HD void phase_thomas_back(int tid, Real* RBC_RESTRICT R, const Real* RBC_RESTRICT tinv, const Real* RBC_RESTRICT mid, Real* RBC_RESTRICT ends)
+template <typename G, bool ASYNC, typename Real>
+RBC_HD void phase_thomas_back(int tid, int rank, Real* RBC_RESTRICT R, const Real* RBC_RESTRICT tinv, const Real* RBC_RESTRICT mid,
+                              Real* RBC_RESTRICT ends, const PeerBuf<Real>* peers)
 {
     constexpr int NX = G::NX, M = G::NZL, MH = M / 2, RSTR = G::RSTR;
     if (tid >= 2 * NX) return;
@@ -534,23 +642,27 @@ RBC_HD void phase_thomas_back(int tid, Real* RBC_RESTRICT R, const Real* RBC_RES
             }
         }
     }
-    ends[tid] = pv;                                   // ends[t] = y(0), ends[NX + t] = y(M-1)
+    // block-end values y(0) (slot t) and y(M-1) (slot NX + t) of this rank, to every CTA of the cluster
+    ends[rank * 2 * NX + tid] = pv;
+    if (G::CL > 1) {
+        RBC_UNROLL
+        for (int j = 0; j < G::CL; ++j)
+            if (j != rank) peer_store<ASYNC>(peers[j], rank * 2 * NX + tid, pv);
+    }
 }
 template <typename G, typename Real>
-RBC_HD void phase_spike_correct(int tid, int rank, const CtxX<Real>& X, unsigned char* smb, Real* RBC_RESTRICT R)
+RBC_HD void phase_spike_correct(int tid, int rank, const CtxX<Real>& X, const Real* RBC_RESTRICT ends, Real* RBC_RESTRICT R)
 {
     constexpr int NX = G::NX, M = G::NZL, MH = M / 2, RSTR = G::RSTR, CL = G::CL;
     if (tid >= 2 * NX) return;
     const int t = tid % NX;
     const bool hi = tid >= NX;
-    Real* my_ends = reinterpret_cast<Real*>(smb + X.o_ends);
     const Real* cl = X.cxl + (size_t)rank * 2 * CL * NX + t;
     const Real* cr = X.cxr + (size_t)rank * 2 * CL * NX + t;
     Real xl = Real(0), xr = Real(0);
     RBC_UNROLL
     for (int j = 0; j < CL; ++j) {
-        const Real* e = (j == rank) ? my_ends : peer_ptr(X.base, X.arena_stride, my_ends, rank, j);
-        const Real e0 = e[t], e1 = e[NX + t];
+        const Real e0 = ends[j * 2 * NX + t], e1 = ends[j * 2 * NX + NX + t];
         xl += cl[(2 * j) * NX] * e0 + cl[(2 * j + 1) * NX] * e1;
         xr += cr[(2 * j) * NX] * e0 + cr[(2 * j + 1) * NX] * e1;
     }
@@ -572,8 +684,8 @@ RBC_HD void phase_spike_correct(int tid, int rank, const CtxX<Real>& X, unsigned
 // ------------------------------------------------------------------------------------------
 // phase: pressure correction of the slab + push of the corrected halo rows to the neighbouring slabs
 // ------------------------------------------------------------------------------------------
-template <typename G, typename Real>
-RBC_HD void phase_correct(int tid, int rank, const Consts<Real>& C, Real* RBC_RESTRICT p, Real* p_below, Real* p_above,
+template <typename G, bool ASYNC, typename Real>
+RBC_HD void phase_correct(int tid, int rank, const Consts<Real>& C, Real* RBC_RESTRICT p, const PeerBuf<Real>& below, const PeerBuf<Real>& above,
                           const Real* RBC_RESTRICT R)
 {
     constexpr int NX = G::NX, SX = G::SX, RS = G::RS, RSTR = G::RSTR, NZL = G::NZL, H = G::HALO;
@@ -598,13 +710,13 @@ RBC_HD void phase_correct(int tid, int rank, const Consts<Real>& C, Real* RBC_RE
         pu[(lk + H) * SX + i] = un;
         if (k >= 1) pw[(lk + H) * SX + i] = wn;
         if (G::CL > 1) {
-            if (lk < H && p_below != nullptr) {
-                p_below[G::OFF_U + (NZL + H + lk) * SX + i] = un;
-                p_below[G::OFF_W + (NZL + H + lk) * SX + i] = wn;
+            if (lk < H && below.p != nullptr) {
+                peer_store<ASYNC>(below, G::OFF_U + (NZL + H + lk) * SX + i, un);
+                peer_store<ASYNC>(below, G::OFF_W + (NZL + H + lk) * SX + i, wn);
             }
-            if (lk >= NZL - H && p_above != nullptr) {
-                p_above[G::OFF_U + (lk - NZL + H) * SX + i] = un;
-                p_above[G::OFF_W + (lk - NZL + H) * SX + i] = wn;
+            if (lk >= NZL - H && above.p != nullptr) {
+                peer_store<ASYNC>(above, G::OFF_U + (lk - NZL + H) * SX + i, un);
+                peer_store<ASYNC>(above, G::OFF_W + (lk - NZL + H) * SX + i, wn);
             }
         }
     }
@@ -659,10 +771,16 @@ RBC_HD double cell_distance(const Real* uy)
 #define RBX_PTR(off) reinterpret_cast<Real*>(smb + (off))
 
 template <typename G, typename Real, bool NXT_GLOBAL>
-RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, int my_rank)
+RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, int my_rank, SyncState& S, bool after_tendency)
 {
     (void)my_rank;
-    constexpr int NZL = G::NZL, NT = G::NT, N1 = G::N1, N2 = G::N2, CL = G::CL;
+    constexpr int NZL = G::NZL, NT = G::NT, NX = G::NX, N1 = G::N1, N2 = G::N2, CL = G::CL;
+    constexpr bool ASYNC = RBX_ASYNC(G, NXT_GLOBAL);
+    constexpr unsigned ROWB = NX * sizeof(Real);           // bytes of one pushed row
+    if (ASYNC && after_tendency) {                         // the w* face on top of the slab, pushed by the slab above
+        RBX_WAIT(CH_W, S.n[CH_W], (my_rank < CL - 1) ? ROWB : 0u);
+    }
+    if (after_tendency) S.n[CH_W] += 1;
     RBX_PHASE_L(G,
         for (int item = tid; item < N1 * NZL; item += NT)
             fft_passA_fwd_div<G>(item, C, RBX_PTR(o_p), (const Real*)nullptr, RBX_PTR(X.o_R), RBX_PTR(X.o_twN));
@@ -671,9 +789,20 @@ RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, in
         for (int item = tid; item < (N2 / 2) * NZL; item += NT)
             fft_passB_fwd_untangle<G>(item / NZL, RBX_PTR(X.o_R) + (item % NZL) * G::RSTR, RBX_PTR(X.o_tw2));
     )
-    RBX_PHASE_L(G, phase_thomas_sweep<G>(tid, RBX_PTR(X.o_R), X.tinv + (size_t)rank * NZL * G::NX, RBX_PTR(X.o_mid), X.thomas_scale);)
-    RBX_PHASE_C(G, phase_thomas_back<G>(tid, RBX_PTR(X.o_R), X.tinv + (size_t)rank * NZL * G::NX, RBX_PTR(X.o_mid), RBX_PTR(X.o_ends));)
-    if (CL > 1) { RBX_PHASE_L(G, phase_spike_correct<G>(tid, rank, X, smb, RBX_PTR(X.o_R));) }
+    RBX_PHASE_L(G, phase_thomas_sweep<G>(tid, RBX_PTR(X.o_R), X.tinv + (size_t)rank * NZL * NX, RBX_PTR(X.o_mid), X.thomas_scale);)
+    const unsigned o_ends = X.o_ends + (S.n[CH_E] & 1u) * (unsigned)(CL * 2 * NX * sizeof(Real));     // double-buffered by use parity
+    RBX_PHASE_X(G, ASYNC,
+        PeerBuf<Real> peers[CL];
+        RBC_UNROLL
+        for (int j = 0; j < CL; ++j)
+            peers[j] = make_peer<ASYNC, Real>(X, smb, o_ends, bar_off(X.o_bars, CH_E, S.n[CH_E]), rank, j, j != rank);
+        phase_thomas_back<G, ASYNC>(tid, rank, RBX_PTR(X.o_R), X.tinv + (size_t)rank * NZL * NX, RBX_PTR(X.o_mid), RBX_PTR(o_ends), peers);
+    )
+    if (CL > 1) {
+        if (ASYNC) { RBX_WAIT(CH_E, S.n[CH_E], (unsigned)(CL - 1) * 2u * ROWB); }
+        RBX_PHASE_L(G, phase_spike_correct<G>(tid, rank, X, RBX_PTR(o_ends), RBX_PTR(X.o_R));)
+    }
+    S.n[CH_E] += 1;
     // inverse transforms; the extra row NZL (pressure row below the slab) rides on otherwise idle lanes
     RBX_PHASE_L(G,
         constexpr int NB = (N2 / 2) * NZL;
@@ -691,21 +820,29 @@ RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, in
             else fft_passA_inv<G, Real>(item - NA, RBX_PTR(X.o_R) + NZL * G::RSTR);
         }
     )
-    RBX_PHASE_C(G,
-        Real* P = RBX_PTR(o_p);
-        Real* below = (CL > 1 && rank > 0) ? peer_ptr(X.base, X.arena_stride, P, rank, rank - 1) : nullptr;
-        Real* above = (CL > 1 && rank < CL - 1) ? peer_ptr(X.base, X.arena_stride, P, rank, rank + 1) : nullptr;
-        phase_correct<G>(tid, rank, C, P, below, above, RBX_PTR(X.o_R));
+    RBX_PHASE_X(G, ASYNC,
+        const unsigned hb = bar_off(X.o_bars, CH_H, S.n[CH_H]);
+        const PeerBuf<Real> below = make_peer<ASYNC, Real>(X, smb, o_p, hb, rank, rank - 1, CL > 1 && rank > 0);
+        const PeerBuf<Real> above = make_peer<ASYNC, Real>(X, smb, o_p, hb, rank, rank + 1, CL > 1 && rank < CL - 1);
+        phase_correct<G, ASYNC>(tid, rank, C, RBX_PTR(o_p), below, above, RBX_PTR(X.o_R));
     )
+    if (ASYNC) {
+        // halo rows for the next tendency: 3 rows each of u and w (this phase) and, after a tendency, of b*, per neighbour
+        const unsigned nbrs = (my_rank > 0 ? 1u : 0u) + (my_rank < CL - 1 ? 1u : 0u);
+        RBX_WAIT(CH_H, S.n[CH_H], nbrs * (after_tendency ? 9u : 6u) * ROWB);
+    }
+    S.n[CH_H] += 1;
 }
 
 // ------------------------------------------------------------------------------------------
 // one action step of one environment, executed by all CTAs of the cluster
 // ------------------------------------------------------------------------------------------
 template <typename G, typename Real, bool NXT_GLOBAL>
-RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, const RunFlags& F, int my_rank)
+RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, const RunFlags& F, int my_rank,
+                            SyncState& S)
 {
     (void)my_rank;
+    constexpr bool ASYNC = RBX_ASYNC(G, NXT_GLOBAL);
     constexpr int NX = G::NX, NZ = G::NZ, NZL = G::NZL, NT = G::NT, CL = G::CL, SX = G::SX, H = G::HALO, NRED = G::NRED, NFIN = G::NFIN;
     const Real gam[3] = {Real(8.0 / 15.0), Real(5.0 / 12.0), Real(3.0 / 4.0)};
     const Real zet[3] = {Real(0), Real(-17.0 / 60.0), Real(-5.0 / 12.0)};
@@ -716,26 +853,31 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
         if (tid < NX) RBX_PTR(X.o_Tb)[tid] = (Real)rbc2d::heater_T(C, io.actions + (size_t)env * C.heaters, (tid + 0.5) * C.dx);
     )
     unsigned o_cur = X.o_s0, o_nxt = X.o_s1;               // fp64 mode: o_s1 is unused, the predicted state is global
-    if (F.project_first) project<G, Real, NXT_GLOBAL>(C, X, o_cur, my_rank);
+    if (F.project_first) project<G, Real, NXT_GLOBAL>(C, X, o_cur, my_rank, S, false);
     for (int sub = 0; sub < F.nsub; ++sub) {
         const Real dt = (sub == F.nsub - 1) ? C.dt_last : C.dt_full;
         for (int stage = 0; stage < 3; ++stage) {
             const int in_slab = (stage & 1) ? 0 : 1, out_slab = 1 - in_slab;
-            RBX_PHASE_C(G,
+            RBX_PHASE_X(G, ASYNC,
                 Real* cur = RBX_PTR(o_cur);
-                Real* nxt; Real* below; Real* above;
+                Real* nxt;
+                PeerBuf<Real> below_h; PeerBuf<Real> below_w; PeerBuf<Real> above_h;
                 if (NXT_GLOBAL) {
                     nxt = X.nxt_g + (size_t)rank * G::NS_SM;
-                    below = rank > 0 ? nxt - G::NS_SM : nullptr;
-                    above = rank < CL - 1 ? nxt + G::NS_SM : nullptr;
+                    below_h.p = rank > 0 ? nxt - G::NS_SM : nullptr; below_h.addr = 0; below_h.bar = 0;
+                    above_h.p = rank < CL - 1 ? nxt + G::NS_SM : nullptr; above_h.addr = 0; above_h.bar = 0;
+                    below_w = below_h;
                 } else {
                     nxt = RBX_PTR(o_nxt);
-                    below = (CL > 1 && rank > 0) ? peer_ptr(X.base, X.arena_stride, nxt, rank, rank - 1) : nullptr;
-                    above = (CL > 1 && rank < CL - 1) ? peer_ptr(X.base, X.arena_stride, nxt, rank, rank + 1) : nullptr;
+                    const unsigned hb = bar_off(X.o_bars, CH_H, S.n[CH_H]);
+                    const unsigned wb = bar_off(X.o_bars, CH_W, S.n[CH_W]);
+                    below_h = make_peer<ASYNC, Real>(X, smb, o_nxt, hb, rank, rank - 1, CL > 1 && rank > 0);
+                    below_w = make_peer<ASYNC, Real>(X, smb, o_nxt, wb, rank, rank - 1, CL > 1 && rank > 0);
+                    above_h = make_peer<ASYNC, Real>(X, smb, o_nxt, hb, rank, rank + 1, CL > 1 && rank < CL - 1);
                 }
                 Real* gmr = X.gm + (size_t)rank * 2 * G::NLOC;
-                phase_tendency<G>(tid, rank, C, cur, nxt, below, above, RBX_PTR(X.o_Tb), gmr + in_slab * G::NLOC, gmr + out_slab * G::NLOC,
-                                  dt, gam[stage], zet[stage], stage > 0);
+                phase_tendency<G, ASYNC>(tid, rank, C, cur, nxt, below_h, below_w, above_h, RBX_PTR(X.o_Tb), gmr + in_slab * G::NLOC,
+                                         gmr + out_slab * G::NLOC, dt, gam[stage], zet[stage], stage > 0);
             )
             unsigned o_p;
             if (NXT_GLOBAL) {
@@ -744,7 +886,7 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
             } else {
                 o_p = o_nxt; o_nxt = o_cur; o_cur = o_p;
             }
-            project<G, Real, NXT_GLOBAL>(C, X, o_p, my_rank);
+            project<G, Real, NXT_GLOBAL>(C, X, o_p, my_rank, S, true);
         }
     }
 
@@ -1002,14 +1144,15 @@ struct SmemLayoutX {
     static constexpr size_t Tb = al(cfin + sizeof(double) * G::NFIN);
     static constexpr size_t mid = al(Tb + sizeof(Real) * G::NX);
     static constexpr size_t ends = al(mid + sizeof(Real) * 2 * G::NX);
-    static constexpr size_t twN = al(ends + sizeof(Real) * 2 * G::NX);
+    static constexpr size_t bars = al(ends + sizeof(Real) * 2 * G::CL * 2 * G::NX);     // ends: [2 parities][CL ranks][2 NX]
+    static constexpr size_t twN = al(bars + 8 * 2 * NCHAN);
     static constexpr size_t tw2 = al(twN + sizeof(Real) * 2 * G::NH);
     static constexpr size_t total = al(tw2 + sizeof(Real) * 2 * G::NH);
     template <typename Ctx>
     static void fill(Ctx& X)
     {
         X.o_s0 = (unsigned)s0; X.o_s1 = (unsigned)s1; X.o_R = (unsigned)R; X.o_red = kRedSeparate ? (unsigned)red : ~0u; X.o_fin = (unsigned)fin;
-        X.o_cfin = (unsigned)cfin; X.o_Tb = (unsigned)Tb; X.o_mid = (unsigned)mid; X.o_ends = (unsigned)ends;
+        X.o_cfin = (unsigned)cfin; X.o_Tb = (unsigned)Tb; X.o_mid = (unsigned)mid; X.o_ends = (unsigned)ends; X.o_bars = (unsigned)bars;
         X.o_twN = (unsigned)twN; X.o_tw2 = (unsigned)tw2;
     }
 };

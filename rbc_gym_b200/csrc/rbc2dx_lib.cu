@@ -38,11 +38,19 @@ rbc2dx_env_kernel(Consts<Real> C, EnvIO<Real> io, CtxX<Real> Xg, const int* env_
     }
     Real* R = reinterpret_cast<Real*>(smem + L::R);
     for (int q = threadIdx.x; q < G::NR; q += G::NT) R[q] = Real(0);
+    if (G::CL > 1 && !NXTG && threadIdx.x == 0) {
+        // receive barriers of the three push channels (two per channel, alternating): one arrival = the local expect_tx
+        for (int b = 0; b < 2 * NCHAN; ++b) mbar_init(smem_u32(smem + L::bars + 8 * b), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     // every CTA of the cluster must be resident and initialised before the first remote store
+    __syncthreads();
     RBX_SYNC_CLUSTER(G);
+    SyncState S;
+    for (int c = 0; c < NCHAN; ++c) S.n[c] = 0;
     for (int j = cluster_id; j < n; j += n_clusters) {
         const int env = env_ids ? env_ids[j] : j;
-        env_action_step<G, Real, NXTG>(C, io, X, env, F, my_rank);
+        env_action_step<G, Real, NXTG>(C, io, X, env, F, my_rank, S);
     }
 }
 

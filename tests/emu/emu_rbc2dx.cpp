@@ -51,7 +51,8 @@ static void run(const HostConfig& h, const HostWrappers& wr, double* cell_dist, 
     }
     EnvIO<Real> io{state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, nullptr, cell_dist};
     RunFlags F{nsub >= 0 ? nsub : C.nsub, project_first, 1};
-    for (int e = 0; e < B; ++e) env_action_step<G, Real, NXTG>(C, io, X, e, F, 0);
+    SyncState S{};
+    for (int e = 0; e < B; ++e) env_action_step<G, Real, NXTG>(C, io, X, e, F, 0, S);
 }
 
 #define ARGS *h, wr, cell_dist, B

@@ -1,11 +1,14 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep of the env kernel: key raw metrics + samples/instructions per source function.
-Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [envs_in_launch]"""
+Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [envs_in_launch [stages_per_env [cells_per_env [core_header]]]]"""
 import collections, csv, io, re, subprocess, sys
 from pathlib import Path
 
 rep = sys.argv[1]
 envs = int(sys.argv[2]) if len(sys.argv) > 2 else 592
+stages_per_env = int(sys.argv[3]) if len(sys.argv) > 3 else 102      # RK3 stages per env action step
+cells = int(sys.argv[4]) if len(sys.argv) > 4 else 6144               # cells per env
+core = sys.argv[5] if len(sys.argv) > 5 else "rbc2d_core.h"           # source file whose functions are attributed
 ROOT = Path(__file__).resolve().parent.parent
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -20,9 +23,9 @@ keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum"]
 for k in keys:
     if k in M: print(f"{k:75s} {M[k][0]:>18s} {M[k][1]}")
-stages = envs * 102
+stages = envs * stages_per_env
 print(f"per stage: cycles {g('sm__cycles_elapsed.avg') * 148 / stages:.0f}  warp-instr {g('smsp__inst_executed.sum') / stages:.0f} "
-      f"(thread-instr/cell {g('smsp__inst_executed.sum') / stages * 32 / 6144:.1f})  smem wavefronts {g('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum') / stages:.0f} "
+      f"(thread-instr/cell {g('smsp__inst_executed.sum') / stages * 32 / cells:.1f})  smem wavefronts {g('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum') / stages:.0f} "
       f"conflicts {g('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum') / stages:.0f}")
 print(f"dram bytes per env-step: read {g('dram__bytes_read.sum') * (1e6 if M['dram__bytes_read.sum'][1]=='Mbyte' else 1) / envs:.0f} write {g('dram__bytes_write.sum') * (1e6 if M['dram__bytes_write.sum'][1]=='Mbyte' else 1) / envs:.0f}")
 for k, (v, u) in M.items():
@@ -35,7 +38,7 @@ hdr = rows[2]
 iS, iI = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
 ci = {h: i for i, h in enumerate(hdr)}
 stallcols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-lines = (ROOT / "rbc_gym_b200/csrc/rbc2d_core.h").read_text().split("\n")
+lines = (ROOT / "rbc_gym_b200/csrc" / core).read_text().split("\n")
 linefunc, cur = {}, None
 for n, l in enumerate(lines, 1):
     m = re.match(r"^RBC_HD\s+[\w<>:]+\s+(\w+)\(", l)
@@ -46,7 +49,7 @@ curfile = ""
 for r in rows:
     if r and r[0] == "File Path": curfile = r[1]; continue
     if len(r) < len(hdr) or not r[0].isdigit(): continue
-    f = linefunc.get(int(r[0]), "?") if curfile.endswith("rbc2d_core.h") else Path(curfile).name
+    f = linefunc.get(int(r[0]), "?") if curfile.endswith("/" + core) else Path(curfile).name
     s_, ins = int(r[iS] or 0), int(r[iI] or 0)
     agg[f][0] += s_; agg[f][1] += ins
     for c in stallcols:
