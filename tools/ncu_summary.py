@@ -50,7 +50,10 @@ for r in rows:
     if r and r[0] == "File Path": curfile = r[1]; continue
     if len(r) < len(hdr) or not r[0].isdigit(): continue
     f = linefunc.get(int(r[0]), "?") if curfile.endswith("/" + core) else Path(curfile).name
-    s_, ins = int(r[iS] or 0), int(r[iI] or 0)
+    try:
+        s_, ins = int(r[iS] or 0), int(r[iI] or 0)
+    except ValueError:          # a source line whose quotes broke the CSV row (inline asm)
+        continue
     agg[f][0] += s_; agg[f][1] += ins
     for c in stallcols:
         v = r[ci[c]]
