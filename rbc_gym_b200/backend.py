@@ -390,7 +390,11 @@ class Sim3D:
     def __init__(self, num_envs: int, ra: float = 2500, *, pr: float = 0.7, domain=(2.0, 4 * math.pi, 4 * math.pi),
                  state_shape=(16, 32, 32), temperature_difference=(1.0, 2.0), heaters: int = 8, heater_limit: float = 0.9,
                  heater_duration: float = 0.125, dt_solver: float = 0.01, episode_length: float = 300.0, precision: int = 32,
-                 split: bool = True, device: int = 0):
+                 split: bool = False, device: int = 0):
+        """`split=True` carries Oceananigans' hydrostatic-pressure anomaly explicitly (buoyancy through pHY'); the default adds
+        the buoyancy to G_w instead.  The two differ by a discrete gradient that the projection removes, so velocities and b
+        agree to round-off (oracle test), and the 3D state exposes no pressure channel.  fp32 + `split=False` runs the tiled
+        kernel (shared-memory tile per half domain)."""
         import torch
 
         if not torch.cuda.is_available():

@@ -145,6 +145,18 @@ inline T* peer_ptr(const unsigned char*, size_t stride, T* p, int my, int to)
 // Channels (one pair of mbarriers each, alternating with the use count so that consecutive uses never share
 // a barrier): W = the w* face from the slab above, E = block-end values of the tridiagonal solve, H = halo rows.
 // ------------------------------------------------------------------------------------------
+//
+// Why no cluster barrier is needed (stage s, buffers ping-pong A/B, barriers alternate with the use count):
+//   * a CTA starts the tendency of stage s+1 only after wait H(s), i.e. after BOTH neighbours finished their
+//     correct(s); it reaches thomas_back(s) only after its own tendency(s); it passes wait E(s) only after ALL
+//     CTAs ran thomas_back(s).  Hence, when a CTA pushes b*/w* in tendency(s) into a neighbour's `nxt` halos,
+//     that neighbour has passed thomas_back(s-1) (we waited E(s-1)) and no longer reads that buffer (it was its
+//     `cur` in tendency(s-1)); when a CTA pushes corrected u,w (and overwrites the shared w* face) in correct(s),
+//     the neighbour has passed thomas_back(s) (we waited E(s)) and therefore its pass A of stage s.
+//   * ends[parity] slot of rank r in CTA q is rewritten by r in thomas_back(s+2); r got there through wait E(s+1),
+//     so q ran thomas_back(s+1), which follows its spike_correct(s) — the last reader of the slot.
+//   * barrier (ch, parity) is re-used by pushes of use n+2; a producer two uses ahead would have needed the
+//     consumer's own pushes of use n+1, which the consumer issues only after completing its wait of use n.
 enum { CH_W = 0, CH_E = 1, CH_H = 2, NCHAN = 3 };
 struct SyncState { unsigned n[NCHAN]; };              // uses of each channel so far (identical on all CTAs)
 

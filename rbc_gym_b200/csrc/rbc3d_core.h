@@ -19,6 +19,13 @@
 // real-FFT split), then one thread transforms one 32-point complex column in y; the z direction is 1024
 // independent tridiagonal systems of length 16 per environment (two per thread), then the inverses.
 //
+//
+// Tiled variant (fp32 throughput mode, buoyancy in G_w): the tendency phase runs in two halves of 16 rows (y).
+// For each half the CTA first copies the 22 rows it touches (16 + 3 halo rows per side, periodic wrap) of all
+// levels of b,u,v,w into shared memory (183 KB, aliasing the Poisson scratch that is dead during this phase);
+// the march then takes every stencil value — its own column and the x/y neighbours — from that tile, so the only
+// global traffic of the march is the previous tendencies in and the new tendencies + predicted state out.
+//
 // Shared with nvcc and g++ (tests/emu) exactly like rbc2d_core.h.
 #pragma once
 #include "rbc2d_core.h"
@@ -54,6 +61,9 @@ constexpr int RX = 34;                          // padded row of the Poisson scr
 constexpr int RP = NY * RX;                     //  walk the banks two at a time for 64-bit accesses)
 constexpr int NR = NZ * RP;
 constexpr int MAX_HEATERS = 16;
+// shared-memory tile of the tiled tendency phase: TROWS rows of all levels of b,u,v (NZ planes each) and w (NZ+1)
+constexpr int THALF = NY / 2, TROWS = THALF + 6, TPL = TROWS * NX;
+constexpr int NTILE = (3 * NZ + NZ + 1) * TPL;  // 45 760 values
 
 template <typename Real>
 struct Consts3 {
@@ -87,6 +97,7 @@ struct Ctx3 {
     Real* bufB;
     Real* gm;                 // global, per CTA: two tendency slabs (2 x NG)
     Real* R;                  // shared: Poisson scratch / pHY' [NZ][NY][RX]
+    Real* tile;               // shared (tiled variant): NTILE values, aliases R; nullptr otherwise
     Real* Tb;                 // shared: bottom wall temperature per column (NCOL)
     double* red;              // shared: NT doubles x 2 for the epilogue reductions
     const Real* tinv;         // global: Thomas pivots [NZ][NY][NX]
@@ -155,20 +166,27 @@ RBC_HD void phase_phy3(int tid, const Consts3<Real>& C, const Real* cb, Real* ph
 // ------------------------------------------------------------------------------------------
 // phase: tendencies + RK3 substep; reads `cur`, writes the predicted state `nxt`, stores G for the next stage
 // ------------------------------------------------------------------------------------------
-template <typename Real, bool SPLIT>
-RBC_HD void phase_tendency3(int tid, const Consts3<Real>& C, const Real* cur, Real* nxt, const Real* RBC_RESTRICT phy,
-                            const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm)
+template <typename Real, bool SPLIT, bool TILE>
+RBC_HD void tendency3_column(const Consts3<Real>& C, const Real* RBC_RESTRICT src, Real* nxt, const Real* RBC_RESTRICT phy,
+                             const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm,
+                             const int i, const int j, const int jl)
 {
-    for (int q = 0; q < NCOL / NT; ++q) {
-        const int c = tid + q * NT, i = c % NX, j = c / NX;
+    // `src` is the environment's state in global memory (level stride NCOL, rows wrap periodically) or the
+    // shared-memory tile of this half (level stride TPL, tile row = jl + 3 + dj, no wrap needed)
+    constexpr int LS = TILE ? TPL : NCOL;
+    constexpr int SB = 0, SU = NZ * LS, SV = 2 * NZ * LS, SW = 3 * NZ * LS;
+    auto rowoff = [&](int dj) { return TILE ? (jl + 3 + dj) * NX : wrapn(j + dj, NY) * NX; };
+    {
+        const int c = j * NX + i;                          // global column (outputs, tendency slabs, Tb)
+        const int cs = rowoff(0) + i;                      // the same column in `src`
         int xo[7], yo[7];
         RBC_UNROLL
-        for (int d = 0; d < 7; ++d) { xo[d] = j * NX + wrapn(i + d - 3, NX); yo[d] = wrapn(j + d - 3, NY) * NX + i; }
+        for (int d = 0; d < 7; ++d) { xo[d] = rowoff(0) + wrapn(i + d - 3, NX); yo[d] = rowoff(d - 3) + i; }
         const int c_ip = xo[4], c_jp = yo[4];          // columns (i+1, j) and (i, j+1)
         // u(i+1, j-2..j+1) and v(i-2..i+1, j+1) columns for the mixed fluxes Uv(i+1) and Vu(j+1)
-        const int ip = wrapn(i + 1, NX), jp = wrapn(j + 1, NY);
-        const int cu0 = wrapn(j - 2, NY) * NX + ip, cu1 = wrapn(j - 1, NY) * NX + ip, cu3 = jp * NX + ip;
-        const int cv0 = jp * NX + wrapn(i - 2, NX), cv1 = jp * NX + wrapn(i - 1, NX), cv3 = cu3;
+        const int ip = wrapn(i + 1, NX);
+        const int cu0 = rowoff(-2) + ip, cu1 = rowoff(-1) + ip, cu3 = rowoff(1) + ip;
+        const int cv0 = rowoff(1) + wrapn(i - 2, NX), cv1 = rowoff(1) + wrapn(i - 1, NX), cv3 = cu3;
 
         // own-column windows: index jj <-> level k-3+jj
         Real bz[7], uz[7], vz[7], wz[7], u1z[4], v1z[4], wx[7], wy[7];
@@ -176,19 +194,19 @@ RBC_HD void phase_tendency3(int tid, const Consts3<Real>& C, const Real* cur, Re
         for (int jj = 0; jj < 7; ++jj) {
             const int k = jj - 3;
             const bool ok = k >= 0;
-            bz[jj] = ok ? cur[GB + k * NCOL + c] : Real(0);
-            uz[jj] = ok ? cur[GU + k * NCOL + c] : Real(0);
-            vz[jj] = ok ? cur[GV + k * NCOL + c] : Real(0);
-            wz[jj] = ok ? cur[GW + k * NCOL + c] : Real(0);
+            bz[jj] = ok ? src[SB + k * LS + cs] : Real(0);
+            uz[jj] = ok ? src[SU + k * LS + cs] : Real(0);
+            vz[jj] = ok ? src[SV + k * LS + cs] : Real(0);
+            wz[jj] = ok ? src[SW + k * LS + cs] : Real(0);
         }
         RBC_UNROLL
         for (int jj = 0; jj < 4; ++jj) {
             const int k = jj - 2;
-            u1z[jj] = k >= 0 ? cur[GU + k * NCOL + c_ip] : Real(0);
-            v1z[jj] = k >= 0 ? cur[GV + k * NCOL + c_jp] : Real(0);
+            u1z[jj] = k >= 0 ? src[SU + k * LS + c_ip] : Real(0);
+            v1z[jj] = k >= 0 ? src[SV + k * LS + c_jp] : Real(0);
         }
         RBC_UNROLL
-        for (int d = 0; d < 7; ++d) { wx[d] = cur[GW + xo[d]]; wy[d] = cur[GW + yo[d]]; }     // wall face 0
+        for (int d = 0; d < 7; ++d) { wx[d] = src[SW + xo[d]]; wy[d] = src[SW + yo[d]]; }     // wall face 0
         Real Fzb_lo = Real(0), Wu_lo = Real(0), Wv_lo = Real(0), Ww_lo = Real(0);
         const Real tb = Tb[c];
         Real gn[4] = {Real(0), Real(0), Real(0), Real(0)};
@@ -204,10 +222,10 @@ RBC_HD void phase_tendency3(int tid, const Consts3<Real>& C, const Real* cur, Re
                 RBC_UNROLL
                 for (int f = 0; f < 4; ++f) gn[f] = gm_in[f * NC + (k + 1) * NCOL + c];
             }
-            const Real* lb = cur + GB + k * NCOL;
-            const Real* lu = cur + GU + k * NCOL;
-            const Real* lv = cur + GV + k * NCOL;
-            const Real* lwn = cur + GW + (k + 1) * NCOL;       // face k+1 <= NZ always exists
+            const Real* lb = src + SB + k * LS;
+            const Real* lu = src + SU + k * LS;
+            const Real* lv = src + SV + k * LS;
+            const Real* lwn = src + SW + (k + 1) * LS;         // face k+1 <= NZ always exists
             Real bx[7], by[7], ux[7], uy[7], vx[7], vy[7], wxn[7], wyn[7];
             RBC_UNROLL
             for (int d = 0; d < 7; ++d) {
@@ -289,14 +307,14 @@ RBC_HD void phase_tendency3(int tid, const Consts3<Real>& C, const Real* cur, Re
             RBC_UNROLL
             for (int jj = 0; jj < 6; ++jj) { bz[jj] = bz[jj + 1]; uz[jj] = uz[jj + 1]; vz[jj] = vz[jj + 1]; wz[jj] = wz[jj + 1]; }
             const int kn = k + 4;
-            bz[6] = (kn < NZ) ? cur[GB + kn * NCOL + c] : Real(0);
-            uz[6] = (kn < NZ) ? cur[GU + kn * NCOL + c] : Real(0);
-            vz[6] = (kn < NZ) ? cur[GV + kn * NCOL + c] : Real(0);
-            wz[6] = (kn <= NZ) ? cur[GW + kn * NCOL + c] : Real(0);
+            bz[6] = (kn < NZ) ? src[SB + kn * LS + cs] : Real(0);
+            uz[6] = (kn < NZ) ? src[SU + kn * LS + cs] : Real(0);
+            vz[6] = (kn < NZ) ? src[SV + kn * LS + cs] : Real(0);
+            wz[6] = (kn <= NZ) ? src[SW + kn * LS + cs] : Real(0);
             RBC_UNROLL
             for (int jj = 0; jj < 3; ++jj) { u1z[jj] = u1z[jj + 1]; v1z[jj] = v1z[jj + 1]; }
-            u1z[3] = (k + 2 < NZ) ? cur[GU + (k + 2) * NCOL + c_ip] : Real(0);
-            v1z[3] = (k + 2 < NZ) ? cur[GV + (k + 2) * NCOL + c_jp] : Real(0);
+            u1z[3] = (k + 2 < NZ) ? src[SU + (k + 2) * LS + c_ip] : Real(0);
+            v1z[3] = (k + 2 < NZ) ? src[SV + (k + 2) * LS + c_jp] : Real(0);
             RBC_UNROLL
             for (int d = 0; d < 7; ++d) { wx[d] = wxn[d]; wy[d] = wyn[d]; }
         };
@@ -308,6 +326,36 @@ RBC_HD void phase_tendency3(int tid, const Consts3<Real>& C, const Real* cur, Re
         }
         nxt[GW + NZ * NCOL + c] = Real(0);               // top wall face
     }
+}
+
+
+// global variant: each thread marches its two columns straight from the state in global memory (through L1)
+template <typename Real, bool SPLIT>
+RBC_HD void phase_tendency3(int tid, const Consts3<Real>& C, const Real* cur, Real* nxt, const Real* RBC_RESTRICT phy,
+                            const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm)
+{
+    for (int q = 0; q < NCOL / NT; ++q) {
+        const int c = tid + q * NT;
+        tendency3_column<Real, SPLIT, false>(C, cur, nxt, phy, Tb, gm_in, gm_out, dt, gam, zet, use_gm, c % NX, c / NX, 0);
+    }
+}
+// tiled variant: copy the rows half h touches into shared memory, then march from the tile
+template <typename Real>
+RBC_HD void phase_load_tile3(int tid, const Real* RBC_RESTRICT cur, Real* RBC_RESTRICT tile, int h)
+{
+    for (int q = tid; q < NTILE; q += NT) {
+        const int p = q / TPL, rem = q % TPL, tr = rem / NX, i = rem % NX;
+        const int f = p < 3 * NZ ? p / NZ : 3, lev = p - f * NZ;
+        const int j = wrapn(h * THALF - 3 + tr, NY);
+        tile[q] = cur[f * NC + lev * NCOL + j * NX + i];
+    }
+}
+template <typename Real, bool SPLIT>
+RBC_HD void phase_tendency3_tile(int tid, const Consts3<Real>& C, const Real* tile, Real* nxt, const Real* RBC_RESTRICT phy,
+                                 const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm, int h)
+{
+    const int i = tid % NX, jl = tid / NX;                 // NT = 512 = 32 columns x 16 rows of the half
+    tendency3_column<Real, SPLIT, true>(C, tile, nxt, phy, Tb, gm_in, gm_out, dt, gam, zet, use_gm, i, h * THALF + jl, jl);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -508,9 +556,10 @@ RBC_HD void project3(const Consts3<Real>& C, const Ctx3<Real>& X, Real* p)
 // ------------------------------------------------------------------------------------------
 // one action step of one 3D environment
 // ------------------------------------------------------------------------------------------
-template <typename Real, bool SPLIT>
+template <typename Real, bool SPLIT, bool TILED = false>
 RBC_HD void env_action_step3(const Consts3<Real>& C, const EnvIO3<Real>& io, const Ctx3<Real>& X, int env, const RunFlags3& F)
 {
+    static_assert(!(TILED && SPLIT), "the tile aliases the scratch that holds pHY' in split mode");
     const Real gam[3] = {Real(8.0 / 15.0), Real(5.0 / 12.0), Real(3.0 / 4.0)};
     const Real zet[3] = {Real(0), Real(-17.0 / 60.0), Real(-5.0 / 12.0)};
     Real* st = io.state + (size_t)env * NSTATE;
@@ -530,7 +579,14 @@ RBC_HD void env_action_step3(const Consts3<Real>& C, const EnvIO3<Real>& io, con
             if (SPLIT) { RBC3_PHASE(phase_phy3(tid, C, cur + GB, X.R);) }
             const Real* gin = X.gm + ((stage & 1) ? 0 : NG);
             Real* gout = X.gm + ((stage & 1) ? NG : 0);
-            RBC3_PHASE((phase_tendency3<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, gin, gout, dt, gam[stage], zet[stage], stage > 0));)
+            if (TILED) {
+                for (int h = 0; h < 2; ++h) {
+                    RBC3_PHASE(phase_load_tile3(tid, cur, X.tile, h);)
+                    RBC3_PHASE((phase_tendency3_tile<Real, false>(tid, C, X.tile, nxt, X.R, X.Tb, gin, gout, dt, gam[stage], zet[stage], stage > 0, h));)
+                }
+            } else {
+                RBC3_PHASE((phase_tendency3<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, gin, gout, dt, gam[stage], zet[stage], stage > 0));)
+            }
             project3(C, X, nxt);
             cur = nxt;
             nxt = (cur == X.bufA) ? X.bufB : X.bufA;

@@ -10,28 +10,29 @@
 
 using namespace rbc3d;
 
-template <typename Real>
+template <typename Real, bool TILED>
 struct Smem3 {
-    static constexpr size_t R = 0;
-    static constexpr size_t Tb = R + sizeof(Real) * NR;
+    static constexpr size_t R = 0;                       // the tile of the tiled tendency phase aliases the Poisson scratch
+    static constexpr size_t Tb = R + sizeof(Real) * ((TILED && NTILE > NR) ? NTILE : NR);
     static constexpr size_t red = Tb + sizeof(Real) * NCOL;
     static constexpr size_t total = red + sizeof(double) * 2 * NT;
     static_assert(Tb % 16 == 0 && red % 16 == 0, "alignment");
     static_assert(total <= 232448, "exceeds the shared memory a CTA can opt into");
 };
 
-template <typename Real, bool SPLIT>
+template <typename Real, bool SPLIT, bool TILED>
 __global__ void __launch_bounds__(NT, 1)
 rbc3d_env_kernel(Consts3<Real> C, EnvIO3<Real> io, Real* buf_all, Real* gm_all, const Real* tinv, Real thomas_scale,
                  const int* env_ids, int n, RunFlags3 F)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    using L = Smem3<Real>;
+    using L = Smem3<Real, TILED>;
     Ctx3<Real> X;
     X.bufA = buf_all + (size_t)blockIdx.x * 2 * NSTATE;
     X.bufB = X.bufA + NSTATE;
     X.gm = gm_all + (size_t)blockIdx.x * 2 * NG;
     X.R = reinterpret_cast<Real*>(smem + L::R);
+    X.tile = TILED ? X.R : nullptr;
     X.Tb = reinterpret_cast<Real*>(smem + L::Tb);
     X.red = reinterpret_cast<double*>(smem + L::red);
     X.tinv = tinv;
@@ -40,7 +41,7 @@ rbc3d_env_kernel(Consts3<Real> C, EnvIO3<Real> io, Real* buf_all, Real* gm_all, 
     __syncthreads();
     for (int j = blockIdx.x; j < n; j += gridDim.x) {
         const int env = env_ids ? env_ids[j] : j;
-        env_action_step3<Real, SPLIT>(C, io, X, env, F);
+        env_action_step3<Real, SPLIT, TILED>(C, io, X, env, F);
     }
 }
 
@@ -81,11 +82,16 @@ struct rbc3d_sim {
     bool timed = false;
 };
 
+// fp32 without the hydrostatic split runs the tiled tendency phase (the fp64 tile would not fit next to the scratch)
+template <typename Real, bool SPLIT>
+struct UseTile { static constexpr bool value = sizeof(Real) == 4 && !SPLIT; };
+
 template <typename Real, bool SPLIT>
 static int prepare3(rbc3d_sim* s)
 {
-    auto k = rbc3d_env_kernel<Real, SPLIT>;
-    s->smem = Smem3<Real>::total;
+    constexpr bool TILED = UseTile<Real, SPLIT>::value;
+    auto k = rbc3d_env_kernel<Real, SPLIT, TILED>;
+    s->smem = Smem3<Real, TILED>::total;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
     int per_sm = 0, sms = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, s->smem));
@@ -117,7 +123,7 @@ static int launch3(rbc3d_sim* s, const float* actions, float* obs, float* reward
     const int grid = n < s->grid ? n : s->grid;
     if (grid <= 0) return 0;
     if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
-    rbc3d_env_kernel<Real, SPLIT><<<grid, NT, s->smem, s->stream>>>(C, io, (Real*)s->buf, (Real*)s->gm, (const Real*)s->tinv,
+    rbc3d_env_kernel<Real, SPLIT, UseTile<Real, SPLIT>::value><<<grid, NT, s->smem, s->stream>>>(C, io, (Real*)s->buf, (Real*)s->gm, (const Real*)s->tinv,
                                                                    (Real)((s->hc.lz / NZ) * (s->hc.lz / NZ) / 512.0), env_ids, n, F);
     CK(cudaGetLastError());
     if (time_it) { CK(cudaEventRecord(s->ev1, s->stream)); s->timed = true; }

@@ -62,7 +62,7 @@ def step3(state, actions, ra, precision=64, split=False, heater_duration=0.125, 
     t = np.zeros(B) if t0 is None else np.array(t0, dtype=np.float64)
     sc, tr, nf = np.ones(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
     vp = lambda x: x.ctypes.data_as(C.c_void_p)
-    rc = lib.emu_rbc3d_step(C.byref(h), precision, int(split), B, vp(st), vp(a), vp(ob), vp(rew), vp(nu), vp(t), vp(sc), vp(tr), vp(nf),
+    rc = lib.emu_rbc3d_step(C.byref(h), precision, 2 if split == "tiled" else int(split), B, vp(st), vp(a), vp(ob), vp(rew), vp(nu), vp(t), vp(sc), vp(tr), vp(nf),
                             int(project_first), nsub)
     assert rc == 0
     return dict(state=st, obs=ob, reward=rew, nusselt=nu, t=t, step=sc, truncated=tr, nan=nf)

@@ -12,14 +12,16 @@ def rel(x, y):
     return np.linalg.norm(x - y) / np.linalg.norm(y)
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("precision,tol", [(64, 1e-10), (32, 1e-5)])
-def test_3d_action_step_matches_oracle(precision, tol):
+def test_3d_action_step_matches_oracle(precision, tol, split):
+    """split=False + fp32 is the tiled throughput kernel; the other three combinations run the global-memory kernel."""
     import torch
     from rbc_gym_b200 import backend
-    P = O3.make_params(5e3)
+    P = O3.make_params(5e3, split_phy=split)
     states = [random_state(P, s) for s in (1, 2, 3)]
     acts = np.random.default_rng(9).uniform(-1, 1, (3, 8, 8)).astype(np.float32)
-    sim = backend.Sim3D(3, ra=5e3, precision=precision)
+    sim = backend.Sim3D(3, ra=5e3, precision=precision, split=split)
     sim.reset_from_fields(np.concatenate([backend.pack_fields3(*(x[None] for x in st)) for st in states]), project=False)
     obs, rew, nu, trunc, nan = sim.step(torch.from_numpy(acts).cuda())
     b, u, v, w = backend.split_fields3(sim.fields())

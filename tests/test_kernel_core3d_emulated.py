@@ -12,9 +12,10 @@ def rel(x, y):
     return np.linalg.norm(x - y) / np.linalg.norm(y)
 
 
-@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("split", [False, True, "tiled"])
 def test_emulated_3d_kernel_matches_oracle(split):
-    P = O3.make_params(5e3, split_phy=split)
+    # "tiled": the tendency phase marches from a shared-memory tile per half of the domain (fp32 throughput path)
+    P = O3.make_params(5e3, split_phy=(split is True))
     b, u, v, w = random_state(P, 1)
     a = np.random.default_rng(2).uniform(-1, 1, (8, 8)).astype(np.float32)
     r = O3.step(P, b, u, v, w, a.astype(np.float64), O3.substep_schedule())
