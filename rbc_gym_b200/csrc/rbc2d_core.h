@@ -36,9 +36,11 @@
 #if defined(__CUDA_ARCH__)
 #define RBC_PHASE_N(NTHREADS, ...) { const int tid = threadIdx.x; __VA_ARGS__ } __syncthreads();
 #define RBC_UNROLL _Pragma("unroll")
+#define RBC_NOUNROLL _Pragma("unroll 1")
 #else
 #define RBC_PHASE_N(NTHREADS, ...) for (int tid = 0; tid < (NTHREADS); ++tid) { __VA_ARGS__ }
 #define RBC_UNROLL
+#define RBC_NOUNROLL
 #endif
 #define RBC_PHASE(...) RBC_PHASE_N(rbc2d::NT, __VA_ARGS__)
 

@@ -319,7 +319,9 @@ RBC_HD void tendency3_column(const Consts3<Real>& C, const Real* RBC_RESTRICT sr
             for (int d = 0; d < 7; ++d) { wx[d] = wxn[d]; wy[d] = wyn[d]; }
         };
 
-        RBC_UNROLL
+        // The level loop is deliberately NOT unrolled: one interior body and one wall body (with run-time order
+        // selection) keep the march inside the instruction cache; the sliding windows cost ~45 register moves per level.
+        RBC_NOUNROLL
         for (int k = 0; k < NZ; ++k) {
             if (k >= 2 && k <= NZ - 4) level(BoolTag<false>{}, k);
             else level(BoolTag<true>{}, k);
@@ -341,13 +343,33 @@ RBC_HD void phase_tendency3(int tid, const Consts3<Real>& C, const Real* cur, Re
 }
 // tiled variant: copy the rows half h touches into shared memory, then march from the tile
 template <typename Real>
+struct alignas(4 * sizeof(Real)) Vec4 {
+    Real v[4];
+};
+template <typename Real>
 RBC_HD void phase_load_tile3(int tid, const Real* RBC_RESTRICT cur, Real* RBC_RESTRICT tile, int h)
 {
-    for (int q = tid; q < NTILE; q += NT) {
-        const int p = q / TPL, rem = q % TPL, tr = rem / NX, i = rem % NX;
-        const int f = p < 3 * NZ ? p / NZ : 3, lev = p - f * NZ;
-        const int j = wrapn(h * THALF - 3 + tr, NY);
-        tile[q] = cur[f * NC + lev * NCOL + j * NX + i];
+    // 4 values per access (rows are 32 values, 128-byte aligned in both layouts), 4 independent loads in flight
+    constexpr int NV = NTILE / 4, VPL = TPL / 4, VROW = NX / 4;
+    const Vec4<Real>* src = reinterpret_cast<const Vec4<Real>*>(cur);
+    Vec4<Real>* dst = reinterpret_cast<Vec4<Real>*>(tile);
+    for (int q0 = tid; q0 < NV; q0 += 4 * NT) {
+        Vec4<Real> val[4];
+        RBC_UNROLL
+        for (int a = 0; a < 4; ++a) {
+            const int q = q0 + a * NT;
+            if (q < NV) {
+                const int p = q / VPL, rem = q % VPL, tr = rem / VROW, i4 = rem % VROW;
+                const int f = p < 3 * NZ ? p / NZ : 3, lev = p - f * NZ;
+                const int j = wrapn(h * THALF - 3 + tr, NY);
+                val[a] = src[(f * NC + lev * NCOL + j * NX) / 4 + i4];
+            }
+        }
+        RBC_UNROLL
+        for (int a = 0; a < 4; ++a) {
+            const int q = q0 + a * NT;
+            if (q < NV) dst[q] = val[a];
+        }
     }
 }
 template <typename Real, bool SPLIT>
