@@ -114,13 +114,65 @@ def cpu_reference_rate(sample_env_steps: int, threads: int):
     return n / el, el
 
 
+def secondary_configs(device: int):
+    """Side measurements of the other BASELINE.json configs on this GPU (not the headline; 2 timed steps each):
+    config 3 = 2D 192x128 Ra=1e6 dt_solver=0.015 (cluster kernel), config 4 = 3D 32x32x16 Ra=1e4 (13 RK3 steps)."""
+    import torch
+    from rbc_gym_b200 import backend
+    from rbc_gym_b200.envs import noise_initial_fields_3d
+    from rbc_gym_b200.envs.rbc2d import noise_initial_fields
+    out = {}
+    peak, _ = hbm_peak()
+
+    def timed(step_fn, n_steps=2):
+        step_fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            step_fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n_steps
+
+    try:
+        B3 = 1056
+        sim = backend.Sim2D(B3, ra=1e6, dt_action=1.0, dt_solver=0.015, state_shape=(128, 192), precision=32, device=device)
+        rng = np.random.default_rng(42)
+        base = np.concatenate([noise_initial_fields(rng, (128, 192), kick=0.01) for _ in range(8)])
+        sim.reset_from_fields(np.tile(base, (B3 // 8, 1)), project=True)
+        a = torch.rand((B3, 12), device=f"cuda:{device}") * 2 - 1
+        ms = timed(lambda: sim.step(a))
+        alg = sim.nsub * 10 * sim.nstate * 4
+        out["config3_2d_192x128_ra1e6"] = {"env_steps_per_s": B3 / ms * 1e3, "envs": B3, "rk3_steps": sim.nsub, "ms_per_step": ms,
+                                           "streaming_equiv_GBps": B3 / ms * 1e3 * alg / 1e9, "frac_of_hbm_peak": B3 / ms * 1e3 * alg / 1e9 / peak,
+                                           "kernel": "rbc2dx_env_kernel<192x128,cl4,f32>", "launch": sim.launch_info()}
+        sim.close()
+    except Exception as e:  # a side measurement must never take the headline down
+        out["config3_2d_192x128_ra1e6"] = {"error": str(e)[:200]}
+    try:
+        B4 = 1184
+        sim = backend.Sim3D(B4, ra=1e4, precision=32, device=device)
+        rng = np.random.default_rng(0)
+        base = np.concatenate([noise_initial_fields_3d(rng, kick=0.05) for _ in range(8)])
+        sim.reset_from_fields(base[np.arange(B4) % 8], project=True)
+        a = torch.rand((B4, 8, 8), device=f"cuda:{device}") * 2 - 1
+        ms = timed(lambda: sim.step(a, want_obs=False))
+        alg = 13 * 10 * 66560 * 4
+        out["config4_3d_32x32x16_ra1e4"] = {"env_steps_per_s": B4 / ms * 1e3, "envs": B4, "rk3_steps": 13, "ms_per_step": ms,
+                                            "streaming_equiv_GBps": B4 / ms * 1e3 * alg / 1e9, "frac_of_hbm_peak": B4 / ms * 1e3 * alg / 1e9 / peak,
+                                            "kernel": "rbc3d_env_kernel<float, tiled>", "launch": sim.launch_info()}
+        sim.close()
+    except Exception as e:
+        out["config4_3d_32x32x16_ra1e4"] = {"error": str(e)[:200]}
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port; Julia cannot run here),
     all host threads, each step a bounded sample of the workload."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_step = max(threads * 2, 16)
+    per_step = max(threads * 8, 64)                       # a bounded sample: well under a second of CPU work per step on 16 cores
     rates = []
     for _ in range(args.warmup):
         cpu_reference_rate(threads, threads)
@@ -155,6 +207,8 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work of the cpu_baseline sample")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config 3 / config 4 side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -253,6 +307,9 @@ def main():
     h2d = B * sim.heaters * 4
     d2h = sum(v.nbytes for v in out.values())
 
+    secondary = None
+    if rank == 0 and not args.no_secondary:
+        secondary = secondary_configs(local_rank)
     if rank == 0:
         real_bytes = args.precision // 8
         per_env = algorithmic_bytes_per_env_step(sim.nsub, real_bytes)
@@ -269,7 +326,9 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n = max(4 * threads, 32)
+            r0, _ = cpu_reference_rate(2 * threads, threads)            # calibrate, then ~10 s of CPU work
+            n = int(min(max(args.cpu_seconds * r0, 4 * threads), 20000))
+            n -= n % threads
             rate, el = cpu_reference_rate(n, threads)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{n} env action-steps of the same workload (oracle fp64 C port, {threads} threads, {el:.1f} s)"}
@@ -293,6 +352,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "episode_stats": totals,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     sim.close()
