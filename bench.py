@@ -69,11 +69,13 @@ class ClockSampler:
             return
         def pump():
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self) -> dict:
+    def stop(self, t_begin: float = 0.0, t_end: float = float("inf")) -> dict:
+        """Summary of the samples that arrived inside [t_begin, t_end] (the timed region); nvidia-smi takes a few
+        hundred ms to start, so the sampler is launched before the warm-up and the region is cut out afterwards."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -83,7 +85,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if ts < t_begin or ts > t_end:
+                continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for n, v in zip(names, r[5:9]):
@@ -252,6 +256,9 @@ def main():
 
     # ---------------- device-resident throughput (`value`) ----------------
     # untimed pre-warm: bring the SM clock up from idle (120 MHz) before the W warm-up steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     t_pre = time.perf_counter()
     while time.perf_counter() - t_pre < 1.0:
         sim.step(actions[0])
@@ -262,10 +269,8 @@ def main():
         stats.accumulate(o_[1], o_[3], o_[2], o_[5])       # also warms torch's lazily loaded reduction kernels
     stats = EpisodeStats(dev)
     kernel_ms = []
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    t_region0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = sim.launch_info()["launches"]
     e0.record()
@@ -276,7 +281,7 @@ def main():
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
     launches = sim.launch_info()["launches"] - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.time()) if rank == 0 else None
     # per-launch duration of the dominant kernel, measured by the library's own CUDA events on the launch stream
     for i in range(3):
         sim.step(actions[W + (i % K)])

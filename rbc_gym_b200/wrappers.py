@@ -153,3 +153,96 @@ class RBCRewardShaping(spaces.Wrapper):
 
     def compute_cell_distances(self, state, use_avg=False) -> float:
         return cell_distance(state, self.size_state, use_avg)
+
+
+# --------------------------------------------------------------------------------------- observation plumbing
+class FlattenObservation(spaces.ObservationWrapper):
+    """`gymnasium.wrappers.FlattenObservation` as used by `example/run_wrapped.py:20`: (C, H, W) -> (C*H*W,)."""
+
+    def __init__(self, env):
+        spaces.ObservationWrapper.__init__(self, env)
+        sp = env.observation_space
+        self.observation_space = spaces.Box(low=np.asarray(sp.low).reshape(-1), high=np.asarray(sp.high).reshape(-1),
+                                            shape=(int(np.prod(sp.shape)),), dtype=np.float32)
+
+    def observation(self, obs):
+        return np.asarray(obs).reshape(-1)
+
+
+class FrameStackObservation(spaces.Wrapper):
+    """`gymnasium.wrappers.FrameStackObservation(env, stack_size)` (`example/run_wrapped.py:22`): the last
+    `stack_size` observations, oldest first; after `reset` the stack is padded with the reset observation
+    (`padding_type="reset"`, gymnasium's default) or zeros (`"zero"`)."""
+
+    def __init__(self, env, stack_size: int, padding_type: str = "reset"):
+        spaces.Wrapper.__init__(self, env)
+        if stack_size < 1:
+            raise ValueError("stack_size must be >= 1")
+        if padding_type not in ("reset", "zero"):
+            raise ValueError("padding_type must be 'reset' or 'zero'")
+        self.stack_size, self.padding_type = int(stack_size), padding_type
+        sp = env.observation_space
+        self.observation_space = spaces.Box(low=np.repeat(np.asarray(sp.low)[None], stack_size, axis=0),
+                                            high=np.repeat(np.asarray(sp.high)[None], stack_size, axis=0),
+                                            shape=(stack_size, *sp.shape), dtype=np.float32)
+        self._frames = None
+
+    def reset(self, seed: int | None = None, options: Dict[str, Any] | None = None):
+        obs, info = self.env.reset(seed=seed, options=options)
+        pad = obs if self.padding_type == "reset" else np.zeros_like(obs)
+        self._frames = np.stack([pad] * (self.stack_size - 1) + [obs])
+        return self._frames.copy(), info
+
+    def step(self, action):
+        obs, reward, terminated, truncated, info = self.env.step(action)
+        self._frames = np.concatenate([self._frames[1:], np.asarray(obs)[None]])
+        return self._frames.copy(), reward, terminated, truncated, info
+
+
+class VectorFrameStack:
+    """Flatten + frame-stack for the on-device vector env (`RBCVectorEnv2D`): a ring buffer `[num_envs, k, ...]` of CUDA
+    tensors that never leaves the GPU.  Environments that were (auto-)reset restart their stack from the reset observation.
+
+    Wraps any object with the vector-env surface (`reset`, `step`, `num_envs`); `flatten=True` additionally flattens
+    each frame like `FlattenObservation` does in `example/run_wrapped.py:19-22`."""
+
+    def __init__(self, venv, stack_size: int = 4, flatten: bool = True, padding_type: str = "reset"):
+        if padding_type not in ("reset", "zero"):
+            raise ValueError("padding_type must be 'reset' or 'zero'")
+        self.venv, self.k, self.flatten, self.padding_type = venv, int(stack_size), bool(flatten), padding_type
+        self.num_envs = venv.num_envs
+        self._buf = None
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.venv, name)
+
+    def _frame(self, obs):
+        return obs.reshape(obs.shape[0], -1) if self.flatten else obs
+
+    def _restart(self, frame, rows):
+        pad = frame[rows] if self.padding_type == "reset" else frame[rows] * 0
+        self._buf[rows] = pad.unsqueeze(1).expand(-1, self.k, *pad.shape[1:])
+        self._buf[rows, -1] = frame[rows]
+
+    def reset(self, seed=None, options=None):
+        obs, info = self.venv.reset(seed=seed, options=options)
+        f = self._frame(obs)
+        self._buf = f.new_zeros((f.shape[0], self.k, *f.shape[1:]))
+        self._restart(f, slice(None))
+        return self._buf.clone(), info
+
+    def step(self, actions):
+        was_pending = getattr(self.venv, "_pending", None)
+        was_pending = None if was_pending is None else was_pending.clone()
+        obs, reward, terminated, truncated, info = self.venv.step(actions)
+        f = self._frame(obs)
+        self._buf = self._buf.roll(-1, dims=1)
+        self._buf[:, -1] = f
+        mode = getattr(self.venv, "autoreset_mode", "disabled")
+        if mode == "same_step" and bool(truncated.any()):          # obs of truncated envs is already the reset observation
+            self._restart(f, truncated.nonzero().flatten())
+        elif mode == "next_step" and was_pending is not None and bool(was_pending.any()):
+            self._restart(f, was_pending.nonzero().flatten())      # this call reset them: obs is the reset observation
+        return self._buf.clone(), reward, terminated, truncated, info

@@ -63,3 +63,68 @@ def test_fused_epilogue_matches_python_wrappers(ckpt_ra1e5, precision):
         assert fused["reward"][j] == pytest.approx(r, rel=1e-6)
         np.testing.assert_allclose(fused["obs"][j], W.normalize_observation(plain["obs"][j].copy(), 0.75), rtol=2e-6, atol=2e-7)
     assert np.ptp(fused["cell_dist"]) > 0            # the four flows are not all alike
+
+
+class _FakeEnv:
+    """Minimal env producing obs = step counter, to check the stacking order without a GPU."""
+
+    def __init__(self):
+        from rbc_gym_b200 import spaces
+        self.observation_space = spaces.Box(-np.inf, np.inf, shape=(2, 3), dtype=np.float32)
+        self.action_space = spaces.Box(-1, 1, shape=(1,), dtype=np.float32)
+        self.n = 0
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def reset(self, seed=None, options=None):
+        self.n = 10
+        return np.full((2, 3), self.n, np.float32), {}
+
+    def step(self, action):
+        self.n += 1
+        return np.full((2, 3), self.n, np.float32), -1.0, False, False, {}
+
+
+def test_flatten_and_frame_stack_follow_gymnasium_semantics():
+    env = W.FrameStackObservation(W.FlattenObservation(_FakeEnv()), 4)
+    assert env.observation_space.shape == (4, 6)
+    obs, _ = env.reset()
+    assert obs.shape == (4, 6) and np.all(obs == 10)                     # padding_type="reset"
+    for _ in range(2):
+        obs, *_ = env.step(None)
+    assert [row[0] for row in obs] == [10, 10, 11, 12]                   # oldest first
+    envz = W.FrameStackObservation(_FakeEnv(), 3, padding_type="zero")
+    obs, _ = envz.reset()
+    assert obs.shape == (3, 2, 3) and np.all(obs[:2] == 0) and np.all(obs[2] == 10)
+
+
+class _FakeVec:
+    """CPU stand-in with the vector-env surface and SAME_STEP autoreset: env e truncates when its counter hits 3."""
+
+    def __init__(self, n=3):
+        import torch
+        self.torch, self.num_envs, self.autoreset_mode = torch, n, "same_step"
+        self.c = torch.zeros(n)
+
+    def reset(self, seed=None, options=None):
+        self.c = self.torch.arange(self.num_envs, dtype=self.torch.float32)
+        return self.c.reshape(-1, 1, 1).expand(-1, 2, 2).clone(), {}
+
+    def step(self, actions):
+        self.c = self.c + 1
+        trunc = self.c == 3
+        self.c = self.torch.where(trunc, self.torch.full_like(self.c, 100.0), self.c)    # reset obs = 100
+        return self.c.reshape(-1, 1, 1).expand(-1, 2, 2).clone(), self.c * 0, trunc & False, trunc, {}
+
+
+def test_vector_frame_stack_ring_buffer_restarts_on_autoreset():
+    v = W.VectorFrameStack(_FakeVec(3), stack_size=3, flatten=True)
+    obs, _ = v.reset()
+    assert obs.shape == (3, 3, 4) and obs[2, :, 0].tolist() == [2, 2, 2]
+    obs, _, _, trunc, _ = v.step(None)
+    assert trunc.tolist() == [False, False, True]
+    assert obs[0, :, 0].tolist() == [0, 0, 1] and obs[2, :, 0].tolist() == [100, 100, 100]   # env 2 restarted its stack
+    obs, *_ = v.step(None)
+    assert obs[0, :, 0].tolist() == [0, 1, 2] and obs[2, :, 0].tolist() == [100, 100, 101]
