@@ -1,0 +1,71 @@
+"""Long-horizon statistics of the fp32 throughput mode (north star: "time-averaged Nu over long horizons must agree
+statistically"), against the numbers the reference's own shipped data pin and against the fp64
+validation mode of the same kernels."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tests.conftest import ROOT  # noqa: E402
+
+
+def kinetic_energy(u, w):
+    return 0.5 * np.mean(u * u, axis=(1, 2)) + 0.5 * np.mean(w * w, axis=(1, 2))
+
+
+def test_ra1e5_limit_cycle_fp32_reproduces_phase_portrait(ckpt_ra1e5):
+    """Train episode 0 sits on the two-roll-pair limit cycle (period ~5.88): with zero action the fp32 rollout must trace
+    the cycle's range/mean (Nu_state in [2.977, 10.580], mean 6.81, KE in [0.127347, 0.143461]) and stay on top of the
+    fp64 rollout for three periods."""
+    import torch
+    from rbc_gym_b200 import backend
+    sims = {p: backend.Sim2D(1, ra=1e5, dt_action=0.3, precision=p) for p in (32, 64)}
+    series = {32: [], 64: []}
+    ke = []
+    for p, sim in sims.items():
+        sim.load_checkpoints(ckpt_ra1e5)
+        sim.reset_from_checkpoints(torch.tensor([0], dtype=torch.int32))
+    zero = torch.zeros((1, 12), device="cuda")
+    for _ in range(60):                                            # 18 time units ~ 3 periods
+        for p, sim in sims.items():
+            _, _, nus, _, _, nan = sim.step(zero)
+            assert not nan.any().item()
+            series[p].append(nus.item())
+        b, u, w = backend.split_fields(sims[32].fields())
+        ke.append(kinetic_energy(u, w)[0])
+    n32, n64 = np.array(series[32]), np.array(series[64])
+    assert 2.9 < n32.min() < 3.4 and 10.0 < n32.max() < 10.7
+    assert abs(n32[:59].mean() - 6.81) < 0.25                      # 59 samples x 0.3 = 17.7 ~ 3 x 5.88
+    assert 0.1272 < min(ke) and max(ke) < 0.1436
+    assert np.abs(n32 - n64).max() < 0.02                          # no phase drift between the two arithmetic modes
+    for sim in sims.values():
+        sim.close()
+
+
+def test_ra1e6_long_time_average_within_ensemble_error():
+    """Chaotic regime (Ra = 1e6 on the 96 x 64 grid): the 20 train checkpoints are 20 samples of the attractor with
+    Nu_state = 14.615 +- 6.534.  Time-averaging 100 time units of 20 zero-action fp32 rollouts must land within two
+    standard errors of that ensemble mean, and next to the fp64 average of the same rollouts."""
+    import torch
+    from rbc_gym_b200 import backend
+    from rbc_gym_b200.h5lite import load_checkpoint_2d
+    c = load_checkpoint_2d(ROOT / "data/checkpoints/train/ckpt_ra1000000.h5")
+    means = {}
+    for p in (32, 64):
+        sim = backend.Sim2D(20, ra=1e6, dt_action=1.0, precision=p)
+        sim.load_checkpoints(c)
+        sim.reset_from_checkpoints(torch.arange(20, dtype=torch.int32))
+        zero = torch.zeros((20, 12), device="cuda")
+        acc = []
+        for step in range(150):
+            _, _, nus, _, _, nan = sim.step(zero)
+            if step >= 50:
+                acc.append(nus.cpu().numpy())
+        assert not nan.any().item()
+        means[p] = float(np.mean(acc))
+        b, u, w = backend.split_fields(sim.fields())
+        assert np.abs(w).max() < 1.5 and b.max() < 2.1 and b.min() > 0.9       # still a physical state
+        sim.close()
+    se = 6.534 / np.sqrt(20)
+    assert abs(means[32] - 14.615) < 2 * se, means
+    assert abs(means[32] - means[64]) < 1.0, means
