@@ -221,6 +221,58 @@ RBC_HD Real centred_ord(Real a, Real b, Real c, Real d, int ord)
 {
     return ord == 4 ? centred4(a, b, c, d) : (b + c) * Real(0.5);
 }
+// ------------------------------------------------------------------------------------------
+// Two reconstructions at once.  The march is issue-bound, and on sm_100a two fp32 operations on a register pair
+// issue as ONE instruction (FFMA2 / FMUL2 / FADD2, same FMA-pipe throughput, half the issue slots).  Fluxes come in
+// natural pairs with identical coefficients (the two x-faces of a cell, two of the three z-faces), so the fp32
+// device path evaluates them packed: the selects write straight into adjacent registers and the coefficients are
+// broadcast immediates, i.e. no packing moves (checked in SASS).  Same operations in the same order as the scalar
+// functions; every other instantiation (fp64, host emulator) simply calls the scalar functions twice.
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+struct Pair {
+    Real a, b;
+};
+template <typename Real>
+RBC_HD Pair<Real> upwind5_pair(Real v0, const Real* w0, Real v1, const Real* w1)
+{
+    return {upwind5(v0, w0), upwind5(v1, w1)};
+}
+template <typename Real>
+RBC_HD Pair<Real> centred4_pair(Real a0, Real b0, Real c0, Real d0, Real a1, Real b1, Real c1, Real d1)
+{
+    return {centred4(a0, b0, c0, d0), centred4(a1, b1, c1, d1)};
+}
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+template <>
+__device__ __forceinline__ Pair<float> upwind5_pair<float>(float v0, const float* w0, float v1, const float* w1)
+{
+    const bool p0 = v0 > 0.f, p1 = v1 > 0.f;
+    const float2 x0 = make_float2(p0 ? w0[0] : w0[5], p1 ? w1[0] : w1[5]);
+    const float2 x1 = make_float2(p0 ? w0[1] : w0[4], p1 ? w1[1] : w1[4]);
+    const float2 x2 = make_float2(p0 ? w0[2] : w0[3], p1 ? w1[2] : w1[3]);
+    const float2 x3 = make_float2(p0 ? w0[3] : w0[2], p1 ? w1[3] : w1[2]);
+    const float2 x4 = make_float2(p0 ? w0[4] : w0[1], p1 ? w1[4] : w1[1]);
+    const float k0 = float(2.0 / 60.0), k1 = float(-13.0 / 60.0), k2 = float(47.0 / 60.0), k3 = float(27.0 / 60.0), k4 = float(-3.0 / 60.0);
+    float2 phi = __fmul2_rn(make_float2(k0, k0), x0);
+    phi = __ffma2_rn(make_float2(k1, k1), x1, phi);
+    phi = __ffma2_rn(make_float2(k2, k2), x2, phi);
+    phi = __ffma2_rn(make_float2(k3, k3), x3, phi);
+    phi = __ffma2_rn(make_float2(k4, k4), x4, phi);
+    const float2 f = __fmul2_rn(make_float2(v0, v1), phi);
+    return {f.x, f.y};
+}
+template <>
+__device__ __forceinline__ Pair<float> centred4_pair<float>(float a0, float b0, float c0, float d0, float a1, float b1, float c1, float d1)
+{
+    const float2 in = __fadd2_rn(make_float2(b0, b1), make_float2(c0, c1));
+    const float2 out = __fadd2_rn(make_float2(a0, a1), make_float2(d0, d1));
+    const float h = float(7.0 / 12.0), q = float(-1.0 / 12.0);
+    const float2 r = __ffma2_rn(make_float2(q, q), out, __fmul2_rn(make_float2(h, h), in));
+    return {r.x, r.y};
+}
+#endif
+
 // wall-order rules (0-based), SURVEY 8a: centres->z-face kf, and z-faces->centre kc
 RBC_HD int ord_up_face(int kf) { return (kf >= 3 && kf <= NZ - 3) ? 5 : ((kf == 2 || kf == NZ - 2) ? 3 : 1); }
 RBC_HD int ord_ce_face(int kf) { return (kf >= 2 && kf <= NZ - 2) ? 4 : 2; }
@@ -323,19 +375,40 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         const int o_up_cen = EDGE ? ord_up_cen(k) : 5;
         const int o_ce_cen = EDGE ? ord_ce_cen(k) : 4;
 
+        // x- and z-face fluxes.  Interior rows evaluate them in pairs (see upwind5_pair); wall rows keep the scalar,
+        // order-selecting forms.
+        Real Fx0, Fx1, F0, F1, Fw0, Fw1, Fzb_hi, Wu_hi, Ww_hi;
+        if (!EDGE) {
+            const Pair<Real> fx = upwind5_pair(ux[3], bx, ux[4], bx + 1);
+            const Pair<Real> ua = centred4_pair(ux[1], ux[2], ux[3], ux[4], ux[2], ux[3], ux[4], ux[5]);
+            const Pair<Real> fu = upwind5_pair(ua.a, ux, ua.b, ux + 1);
+            const Pair<Real> ut = centred4_pair(uz[1], uz[2], uz[3], uz[4], u1z[0], u1z[1], u1z[2], u1z[3]);
+            const Pair<Real> fw = upwind5_pair(ut.a, wxr, ut.b, wxr + 1);
+            const Pair<Real> wa = centred4_pair(wxn[1], wxn[2], wxn[3], wxn[4], wz[2], wz[3], wz[4], wz[5]);
+            const Pair<Real> fz = upwind5_pair(wa.a, uz + 1, wa.b, wz + 1);
+            Fx0 = fx.a; Fx1 = fx.b; F0 = fu.a; F1 = fu.b; Fw0 = fw.a; Fw1 = fw.b; Wu_hi = fz.a; Ww_hi = fz.b;
+            Fzb_hi = upwind5(wz[4], bz + 1);
+        } else {
+            Fx0 = upwind5(ux[3], bx);
+            Fx1 = upwind5(ux[4], bx + 1);
+            F0 = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);          // centre i-1
+            F1 = upwind5(centred4(ux[2], ux[3], ux[4], ux[5]), ux + 1);      // centre i
+            const Real ut0 = centred_ord(uz[1], uz[2], uz[3], uz[4], o_ce_face);        // x-face i,   z-face k
+            const Real ut1 = centred_ord(u1z[0], u1z[1], u1z[2], u1z[3], o_ce_face);    // x-face i+1, z-face k
+            Fw0 = upwind5(ut0, wxr);
+            Fw1 = upwind5(ut1, wxr + 1);
+            Fzb_hi = top ? Real(0) : upwind_ord(wz[4], bz + 1, o_face_hi);
+            Wu_hi = top ? Real(0) : upwind_ord(centred4(wxn[1], wxn[2], wxn[3], wxn[4]), uz + 1, o_face_hi);
+            Ww_hi = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen), wz + 1, o_up_cen);
+        }
+
         // ---- tracer ----
-        const Real Fx0 = upwind5(ux[3], bx);
-        const Real Fx1 = upwind5(ux[4], bx + 1);
-        const Real Fzb_hi = top ? Real(0) : upwind_ord(wz[4], bz + 1, o_face_hi);
         const Real bdn = bot ? (Real(2) * tb - bz[3]) : bz[2];
         const Real bup = top ? (Real(2) * C.b_top - bz[3]) : bz[4];
         const Real Gb = (Fx0 - Fx1) * C.idx + (Fzb_lo - Fzb_hi) * C.idz + (bx[4] - Real(2) * bx[3] + bx[2]) * kdx +
                         (bup - Real(2) * bz[3] + bdn) * kdz;
 
         // ---- u ----
-        const Real F0 = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);          // centre i-1
-        const Real F1 = upwind5(centred4(ux[2], ux[3], ux[4], ux[5]), ux + 1);      // centre i
-        const Real Wu_hi = top ? Real(0) : upwind_ord(centred4(wxn[1], wxn[2], wxn[3], wxn[4]), uz + 1, o_face_hi);
         const Real udn = bot ? -uz[3] : uz[2];
         const Real uup = top ? -uz[3] : uz[4];
         Real Gu = (F0 - F1) * C.idx + (Wu_lo - Wu_hi) * C.idz + (ux[4] - Real(2) * ux[3] + ux[2]) * ndx +
@@ -343,11 +416,6 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         if (SPLIT) Gu -= (phy[k * RSTR + i] - phy[k * RSTR + col[2]]) * C.idx;
 
         // ---- w (face k; face 0 is the wall) ----
-        const Real ut0 = centred_ord(uz[1], uz[2], uz[3], uz[4], o_ce_face);        // x-face i,   z-face k
-        const Real ut1 = centred_ord(u1z[0], u1z[1], u1z[2], u1z[3], o_ce_face);    // x-face i+1, z-face k
-        const Real Fw0 = upwind5(ut0, wxr);
-        const Real Fw1 = upwind5(ut1, wxr + 1);
-        const Real Ww_hi = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen), wz + 1, o_up_cen);
         Real Gw = (Fw0 - Fw1) * C.idx + (Ww_lo - Ww_hi) * C.idz + (wxr[4] - Real(2) * wxr[3] + wxr[2]) * ndx +
                   (wz[4] - Real(2) * wz[3] + wz[2]) * ndz;
         if (!SPLIT) Gw += Real(0.5) * (bz[2] + bz[3]);
