@@ -21,13 +21,16 @@ from .h5lite import write_checkpoint, write_checkpoint_3d
 
 def simulate_2d_rb(directory, seed: int = 42, random_inits: int = 20, ra: float = 1e5, pr: float = 0.7, random_kick: float = 0.02,
                    delta_t: float = 0.03, delta_t_snap: float = 0.3, duration: float = 600.0, precision: int = 64, device: int = 0,
-                   progress=None):
+                   progress=None, state_shape=(64, 96)):
+    """`state_shape` = (Nz, Nx): any registered grid, e.g. (128, 192) with `delta_t=0.015` for config 3 — the reference
+    ships 96 x 64 files only (`N = [96, 64]` default, `rbc_sim2D.jl:17`)."""
     import torch
 
     n = int(random_inits)
+    shape = (int(state_shape[0]), int(state_shape[1]))
     sim = backend.Sim2D(n, ra=float(ra), dt_action=float(delta_t_snap), pr=pr, dt_solver=delta_t, episode_length=1e30,
-                        precision=precision, device=device)
-    fields = np.concatenate([noise_initial_fields(np.random.default_rng(seed + i + 1), kick=random_kick) for i in range(n)])
+                        precision=precision, device=device, state_shape=shape)
+    fields = np.concatenate([noise_initial_fields(np.random.default_rng(seed + i + 1), shape, kick=random_kick) for i in range(n)])
     sim.reset_from_fields(fields, project=True)
     zero = torch.zeros((n, sim.heaters), device=sim.device)
     total = int(duration // delta_t_snap)
@@ -37,14 +40,15 @@ def simulate_2d_rb(directory, seed: int = 42, random_inits: int = 20, ra: float 
             raise RuntimeError("[ERROR] NaN values found!")             # rbc_sim2D.jl:196-199
         if progress and it % 200 == 0:
             progress(it, total)
-    b, u, w = backend.split_fields(sim.fields())
+    b, u, w = backend.split_fields(sim.fields(), shape)
     _, nus, nuo = sim.observe()
     stats = {"nu_state": nus.cpu().numpy().copy(), "nu_obs": nuo.cpu().numpy().copy()}
     sim.close()
     directory = Path(directory)
     directory.mkdir(parents=True, exist_ok=True)
     ra_tag = int(ra) if float(ra).is_integer() else ra
-    path = directory / f"ckpt_ra{ra_tag}.h5"                            # rbc_sim2D.jl:36
+    grid_tag = "" if shape == (64, 96) else f"_{shape[1]}x{shape[0]}"
+    path = directory / f"ckpt_ra{ra_tag}{grid_tag}.h5"                  # rbc_sim2D.jl:36 (grid tag for non-default grids)
     write_checkpoint(path, b, u, w, start_seed=seed)
     return path, stats
 

@@ -148,3 +148,27 @@ def test_cluster_kernel_on_96x64_agrees_with_dedicated_kernel(B, ckpt_ra1e5, pre
     assert rel(out[1][0], out[0][0]) < tol
     np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-9 if precision == 64 else 1e-4)
     np.testing.assert_allclose(out[1][2], out[0][2], rtol=1e-9 if precision == 64 else 1e-4)
+
+
+def test_checkpoint_generator_and_reset_at_192x128(B, tmp_path):
+    """Config 3 has no shipped checkpoints: the generator spins up 192 x 128 episodes on the device, writes the reference's
+    HDF5 layout, and the env resets from the file exactly (fp64 round trip through the file and the device bank)."""
+    import torch
+    from rbc_gym_b200.checkpoints import simulate_2d_rb
+    from rbc_gym_b200.h5lite import load_checkpoint_2d
+    from rbc_gym_b200.envs.rbc2d import RayleighBenardConvection2DEnv
+    path, stats = simulate_2d_rb(tmp_path / "train", seed=42, random_inits=3, ra=RA, delta_t=DTS, delta_t_snap=0.3, duration=3.0,
+                                 state_shape=(NZ, NX))
+    assert path.name == "ckpt_ra1000000_192x128.h5" and np.all(np.isfinite(stats["nu_state"]))
+    c = load_checkpoint_2d(path)
+    assert c.shape == (NZ, NX) and c.num_episodes == 3 and c.start_seed == 42
+    dx, dz = 2 * np.pi / NX, 2.0 / NZ
+    div = (np.roll(c.u, -1, axis=-1) - c.u) / dx + (c.w[:, 1:] - c.w[:, :-1]) / dz
+    assert np.abs(div).max() < 1e-11                                     # fp64 spin-up: discretely solenoidal
+    env = RayleighBenardConvection2DEnv(rayleigh_number=1_000_000, state_shape=[NZ, NX], heater_duration=0.15, dt_solver=DTS,
+                                        checkpoint=str(path), checkpoint_idx=1, precision=64)
+    obs, info = env.reset(seed=0)
+    b, u, w = B.split_fields(env.sim.fields(), (NZ, NX))
+    assert np.array_equal(b[0], c.b[1]) and np.array_equal(u[0], c.u[1]) and np.array_equal(w[0], c.w[1])
+    np.testing.assert_array_equal(obs[0], c.b[1][::16, ::4].astype(np.float32))
+    env.close()
