@@ -94,7 +94,7 @@ template <typename Real>
 struct CtxX {
     unsigned char* base;        // device: this CTA's dynamic shared memory; host: arena of rank 0
     size_t arena_stride;        // host: bytes between the arenas of consecutive ranks (device: unused)
-    unsigned o_s0, o_s1, o_R, o_Tb, o_mid, o_ends, o_twN, o_tw2, o_red, o_fin, o_cfin, o_bars;
+    unsigned o_s0, o_s1, o_R, o_Tb, o_mid, o_ends, o_twN, o_tw2, o_red, o_fin, o_cfin, o_bars, o_tinv;   // o_R / o_tinv == ~0u: see project()
     Real* gm;                   // global: [CL][2][NLOC] stage tendencies of this cluster (ping-pong slabs)
     Real* nxt_g;                // global: [CL][NS_SM] predicted state (fp64 mode) or nullptr
     // global tables, [CL] blocks each (build_tables_host)
@@ -783,9 +783,21 @@ RBC_HD double cell_distance(const Real* uy)
 #define RBX_PTR(off) reinterpret_cast<Real*>(smb + (off))
 
 template <typename G, typename Real, bool NXT_GLOBAL>
-RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, int my_rank, SyncState& S, bool after_tendency)
+RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, unsigned o_dead, int my_rank, SyncState& S, bool after_tendency)
 {
     (void)my_rank;
+    // Poisson scratch: with two on-chip state buffers the one that is dead during the projection (the old state)
+    // provides it — its u rows, which no neighbour writes before this CTA has finished correct() (b*/w* pushes of the
+    // next tendency only touch b halo rows and one w row).  The shared memory saved holds this rank's Thomas pivots.
+    const unsigned o_R = NXT_GLOBAL ? X.o_R : o_dead + (unsigned)(G::OFF_U * sizeof(Real));
+#if defined(__CUDA_ARCH__)
+    const Real* tinv_l;
+    if (NXT_GLOBAL) tinv_l = X.tinv + (size_t)my_rank * G::NZL * G::NX;
+    else tinv_l = reinterpret_cast<const Real*>(X.base + X.o_tinv);
+#define RBX_TINV(rank) tinv_l
+#else
+#define RBX_TINV(rank) (X.tinv + (size_t)(rank) * G::NZL * G::NX)
+#endif
     constexpr int NZL = G::NZL, NT = G::NT, NX = G::NX, N1 = G::N1, N2 = G::N2, CL = G::CL;
     constexpr bool ASYNC = RBX_ASYNC(G, NXT_GLOBAL);
     constexpr unsigned ROWB = NX * sizeof(Real);           // bytes of one pushed row
@@ -795,24 +807,24 @@ RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, in
     if (after_tendency) S.n[CH_W] += 1;
     RBX_PHASE_L(G,
         for (int item = tid; item < N1 * NZL; item += NT)
-            fft_passA_fwd_div<G>(item, C, RBX_PTR(o_p), (const Real*)nullptr, RBX_PTR(X.o_R), RBX_PTR(X.o_twN));
+            fft_passA_fwd_div<G>(item, C, RBX_PTR(o_p), (const Real*)nullptr, RBX_PTR(o_R), RBX_PTR(X.o_twN));
     )
     RBX_PHASE_L(G,
         for (int item = tid; item < (N2 / 2) * NZL; item += NT)
-            fft_passB_fwd_untangle<G>(item / NZL, RBX_PTR(X.o_R) + (item % NZL) * G::RSTR, RBX_PTR(X.o_tw2));
+            fft_passB_fwd_untangle<G>(item / NZL, RBX_PTR(o_R) + (item % NZL) * G::RSTR, RBX_PTR(X.o_tw2));
     )
-    RBX_PHASE_L(G, phase_thomas_sweep<G>(tid, RBX_PTR(X.o_R), X.tinv + (size_t)rank * NZL * NX, RBX_PTR(X.o_mid), X.thomas_scale);)
+    RBX_PHASE_L(G, phase_thomas_sweep<G>(tid, RBX_PTR(o_R), RBX_TINV(rank), RBX_PTR(X.o_mid), X.thomas_scale);)
     const unsigned o_ends = X.o_ends + (S.n[CH_E] & 1u) * (unsigned)(CL * 2 * NX * sizeof(Real));     // double-buffered by use parity
     RBX_PHASE_X(G, ASYNC,
         PeerBuf<Real> peers[CL];
         RBC_UNROLL
         for (int j = 0; j < CL; ++j)
             peers[j] = make_peer<ASYNC, Real>(X, smb, o_ends, bar_off(X.o_bars, CH_E, S.n[CH_E]), rank, j, j != rank);
-        phase_thomas_back<G, ASYNC>(tid, rank, RBX_PTR(X.o_R), X.tinv + (size_t)rank * NZL * NX, RBX_PTR(X.o_mid), RBX_PTR(o_ends), peers);
+        phase_thomas_back<G, ASYNC>(tid, rank, RBX_PTR(o_R), RBX_TINV(rank), RBX_PTR(X.o_mid), RBX_PTR(o_ends), peers);
     )
     if (CL > 1) {
         if (ASYNC) { RBX_WAIT(CH_E, S.n[CH_E], (unsigned)(CL - 1) * 2u * ROWB); }
-        RBX_PHASE_L(G, phase_spike_correct<G>(tid, rank, X, RBX_PTR(o_ends), RBX_PTR(X.o_R));)
+        RBX_PHASE_L(G, phase_spike_correct<G>(tid, rank, X, RBX_PTR(o_ends), RBX_PTR(o_R));)
     }
     S.n[CH_E] += 1;
     // inverse transforms; the extra row NZL (pressure row below the slab) rides on otherwise idle lanes
@@ -820,23 +832,23 @@ RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, in
         constexpr int NB = (N2 / 2) * NZL;
         constexpr int NBX = (CL > 1) ? NB + N2 / 2 : NB;
         for (int item = tid; item < NBX; item += NT) {
-            if (item < NB) fft_passB_inv_tangle<G>(item / NZL, RBX_PTR(X.o_R) + (item % NZL) * G::RSTR, RBX_PTR(X.o_twN), RBX_PTR(X.o_tw2));
-            else fft_passB_inv_tangle<G>(item - NB, RBX_PTR(X.o_R) + NZL * G::RSTR, RBX_PTR(X.o_twN), RBX_PTR(X.o_tw2));
+            if (item < NB) fft_passB_inv_tangle<G>(item / NZL, RBX_PTR(o_R) + (item % NZL) * G::RSTR, RBX_PTR(X.o_twN), RBX_PTR(X.o_tw2));
+            else fft_passB_inv_tangle<G>(item - NB, RBX_PTR(o_R) + NZL * G::RSTR, RBX_PTR(X.o_twN), RBX_PTR(X.o_tw2));
         }
     )
     RBX_PHASE_L(G,
         constexpr int NA = N1 * NZL;
         constexpr int NAX = (CL > 1) ? NA + N1 : NA;
         for (int item = tid; item < NAX; item += NT) {
-            if (item < NA) fft_passA_inv<G, Real>(item / NZL, RBX_PTR(X.o_R) + (item % NZL) * G::RSTR);
-            else fft_passA_inv<G, Real>(item - NA, RBX_PTR(X.o_R) + NZL * G::RSTR);
+            if (item < NA) fft_passA_inv<G, Real>(item / NZL, RBX_PTR(o_R) + (item % NZL) * G::RSTR);
+            else fft_passA_inv<G, Real>(item - NA, RBX_PTR(o_R) + NZL * G::RSTR);
         }
     )
     RBX_PHASE_X(G, ASYNC,
         const unsigned hb = bar_off(X.o_bars, CH_H, S.n[CH_H]);
         const PeerBuf<Real> below = make_peer<ASYNC, Real>(X, smb, o_p, hb, rank, rank - 1, CL > 1 && rank > 0);
         const PeerBuf<Real> above = make_peer<ASYNC, Real>(X, smb, o_p, hb, rank, rank + 1, CL > 1 && rank < CL - 1);
-        phase_correct<G, ASYNC>(tid, rank, C, RBX_PTR(o_p), below, above, RBX_PTR(X.o_R));
+        phase_correct<G, ASYNC>(tid, rank, C, RBX_PTR(o_p), below, above, RBX_PTR(o_R));
     )
     if (ASYNC) {
         // halo rows for the next tendency: 3 rows each of u and w (this phase) and, after a tendency, of b*, per neighbour
@@ -865,7 +877,7 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
         if (tid < NX) RBX_PTR(X.o_Tb)[tid] = (Real)rbc2d::heater_T(C, io.actions + (size_t)env * C.heaters, (tid + 0.5) * C.dx);
     )
     unsigned o_cur = X.o_s0, o_nxt = X.o_s1;               // fp64 mode: o_s1 is unused, the predicted state is global
-    if (F.project_first) project<G, Real, NXT_GLOBAL>(C, X, o_cur, my_rank, S, false);
+    if (F.project_first) project<G, Real, NXT_GLOBAL>(C, X, o_cur, o_nxt, my_rank, S, false);
     for (int sub = 0; sub < F.nsub; ++sub) {
         const Real dt = (sub == F.nsub - 1) ? C.dt_last : C.dt_full;
         for (int stage = 0; stage < 3; ++stage) {
@@ -898,7 +910,7 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
             } else {
                 o_p = o_nxt; o_nxt = o_cur; o_cur = o_p;
             }
-            project<G, Real, NXT_GLOBAL>(C, X, o_p, my_rank, S, true);
+            project<G, Real, NXT_GLOBAL>(C, X, o_p, NXT_GLOBAL ? o_p : o_nxt, my_rank, S, true);
         }
     }
 
@@ -1148,8 +1160,12 @@ struct SmemLayoutX {
     static constexpr size_t al(size_t x) { return (x + 15) & ~(size_t)15; }
     static constexpr size_t s0 = 0;
     static constexpr size_t s1 = al(s0 + sizeof(Real) * G::NS_SM);
+    // fp64 (one on-chip state buffer): separate Poisson scratch; fp32: the scratch aliases the dead buffer and the
+    // space holds this rank's Thomas pivots instead
     static constexpr size_t R = NXT_GLOBAL ? s1 : al(s1 + sizeof(Real) * G::NS_SM);
-    static constexpr size_t red = al(R + sizeof(Real) * G::NR);
+    static constexpr size_t tinv = R;
+    static constexpr size_t red = al(R + (NXT_GLOBAL ? sizeof(Real) * G::NR : sizeof(Real) * G::NZL * G::NX));
+    static_assert(NXT_GLOBAL || G::LR >= G::NZL + 1, "the scratch must fit the u rows of a state buffer");
     static constexpr bool kRedSeparate = NXT_GLOBAL || sizeof(double) * G::NRED * G::NT > sizeof(Real) * G::NS_SM;
     static constexpr size_t fin = al(red + (kRedSeparate ? sizeof(double) * G::NRED * G::NT : 0));
     static constexpr size_t cfin = al(fin + sizeof(double) * G::NRED * 16);
@@ -1163,7 +1179,7 @@ struct SmemLayoutX {
     template <typename Ctx>
     static void fill(Ctx& X)
     {
-        X.o_s0 = (unsigned)s0; X.o_s1 = (unsigned)s1; X.o_R = (unsigned)R; X.o_red = kRedSeparate ? (unsigned)red : ~0u; X.o_fin = (unsigned)fin;
+        X.o_s0 = (unsigned)s0; X.o_s1 = (unsigned)s1; X.o_R = NXT_GLOBAL ? (unsigned)R : ~0u; X.o_tinv = NXT_GLOBAL ? ~0u : (unsigned)tinv; X.o_red = kRedSeparate ? (unsigned)red : ~0u; X.o_fin = (unsigned)fin;
         X.o_cfin = (unsigned)cfin; X.o_Tb = (unsigned)Tb; X.o_mid = (unsigned)mid; X.o_ends = (unsigned)ends; X.o_bars = (unsigned)bars;
         X.o_twN = (unsigned)twN; X.o_tw2 = (unsigned)tw2;
     }

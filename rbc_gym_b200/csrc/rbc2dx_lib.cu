@@ -36,8 +36,14 @@ rbc2dx_env_kernel(Consts<Real> C, EnvIO<Real> io, CtxX<Real> Xg, const int* env_
         Real* s1 = reinterpret_cast<Real*>(smem + L::s1);
         for (int q = threadIdx.x; q < G::NS_SM; q += G::NT) s1[q] = Real(0);
     }
-    Real* R = reinterpret_cast<Real*>(smem + L::R);
-    for (int q = threadIdx.x; q < G::NR; q += G::NT) R[q] = Real(0);
+    if (NXTG) {
+        Real* R = reinterpret_cast<Real*>(smem + L::R);
+        for (int q = threadIdx.x; q < G::NR; q += G::NT) R[q] = Real(0);
+    } else {                                             // this rank's Thomas pivots stay on-chip
+        Real* tv = reinterpret_cast<Real*>(smem + L::tinv);
+        const Real* src = Xg.tinv + (size_t)my_rank * G::NZL * G::NX;
+        for (int q = threadIdx.x; q < G::NZL * G::NX; q += G::NT) tv[q] = src[q];
+    }
     if (G::CL > 1 && !NXTG && threadIdx.x == 0) {
         // receive barriers of the three push channels (two per channel, alternating): one arrival = the local expect_tx
         for (int b = 0; b < 2 * NCHAN; ++b) mbar_init(smem_u32(smem + L::bars + 8 * b), 1);
