@@ -349,10 +349,25 @@ struct alignas(4 * sizeof(Real)) Vec4 {
 template <typename Real>
 RBC_HD void phase_load_tile3(int tid, const Real* RBC_RESTRICT cur, Real* RBC_RESTRICT tile, int h)
 {
-    // 4 values per access (rows are 32 values, 128-byte aligned in both layouts), 4 independent loads in flight
+    // 16 bytes per access (rows are 32 values, 128-byte aligned in both layouts)
     constexpr int NV = NTILE / 4, VPL = TPL / 4, VROW = NX / 4;
     const Vec4<Real>* src = reinterpret_cast<const Vec4<Real>*>(cur);
     Vec4<Real>* dst = reinterpret_cast<Vec4<Real>*>(tile);
+#if defined(__CUDA_ARCH__)
+    if (sizeof(Real) == 4) {
+        // asynchronous global->shared copies (LDGSTS): no register staging, all ~22 copies of a thread in flight at once
+        const unsigned dbase = (unsigned)__cvta_generic_to_shared(dst);
+        for (int q = tid; q < NV; q += NT) {
+            const int p = q / VPL, rem = q % VPL, tr = rem / VROW, i4 = rem % VROW;
+            const int f = p < 3 * NZ ? p / NZ : 3, lev = p - f * NZ;
+            const int j = wrapn(h * THALF - 3 + tr, NY);
+            const Vec4<Real>* g = src + (f * NC + lev * NCOL + j * NX) / 4 + i4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dbase + (unsigned)q * 16u), "l"(g) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
+#endif
     for (int q0 = tid; q0 < NV; q0 += 4 * NT) {
         Vec4<Real> val[4];
         RBC_UNROLL
