@@ -95,7 +95,7 @@ template <typename Real>
 struct Ctx3 {
     Real* bufA;               // global, per CTA: predicted-state ping-pong buffers (NSTATE each)
     Real* bufB;
-    Real* gm;                 // global, per CTA: two tendency slabs (2 x NG)
+    Real* gm;                 // global, per CTA: the tendency slab (NG), updated in place
     Real* R;                  // shared: Poisson scratch / pHY' [NZ][NY][RX]
     Real* tile;               // shared (tiled variant): NTILE values, aliases R; nullptr otherwise
     Real* Tb;                 // shared: bottom wall temperature per column (NCOL)
@@ -614,8 +614,10 @@ RBC_HD void env_action_step3(const Consts3<Real>& C, const EnvIO3<Real>& io, con
         const Real dt = (sub == F.nsub - 1) ? C.dt_last : C.dt_full;
         for (int stage = 0; stage < 3; ++stage, ++stage_no) {
             if (SPLIT) { RBC3_PHASE(phase_phy3(tid, C, cur + GB, X.R);) }
-            const Real* gin = X.gm + ((stage & 1) ? 0 : NG);
-            Real* gout = X.gm + ((stage & 1) ? NG : 0);
+            // one tendency slab, updated in place: every (column, level) entry is read (previous stage) and then
+            // rewritten by the same thread, which halves the per-CTA footprint of the slabs in L2
+            const Real* gin = X.gm;
+            Real* gout = X.gm;
             if (TILED) {
                 for (int h = 0; h < 2; ++h) {
                     RBC3_PHASE(phase_load_tile3(tid, cur, X.tile, h);)

@@ -30,7 +30,7 @@ rbc3d_env_kernel(Consts3<Real> C, EnvIO3<Real> io, Real* buf_all, Real* gm_all, 
     Ctx3<Real> X;
     X.bufA = buf_all + (size_t)blockIdx.x * 2 * NSTATE;
     X.bufB = X.bufA + NSTATE;
-    X.gm = gm_all + (size_t)blockIdx.x * 2 * NG;
+    X.gm = gm_all + (size_t)blockIdx.x * NG;
     X.R = reinterpret_cast<Real*>(smem + L::R);
     X.tile = TILED ? X.R : nullptr;
     X.Tb = reinterpret_cast<Real*>(smem + L::Tb);
@@ -181,7 +181,7 @@ int rbc3d_create(const rbc3d_config* cfg, rbc3d_sim** out)
     } while (0)
     ALLOC3(s->state, B * NSTATE * rs);
     ALLOC3(s->buf, (size_t)s->grid * 2 * NSTATE * rs);
-    ALLOC3(s->gm, (size_t)s->grid * 2 * NG * rs);
+    ALLOC3(s->gm, (size_t)s->grid * NG * rs);
     ALLOC3(s->t, B * sizeof(double));
     ALLOC3(s->nu, B * sizeof(double));
     ALLOC3(s->step, B * sizeof(int));

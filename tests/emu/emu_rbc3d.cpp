@@ -12,7 +12,7 @@ static void run3(const HostConfig3& h, int B, Real* state, const float* actions,
     std::vector<double> tinv_d((size_t)NZ * NCOL);
     build_tables3_host(h.lx, h.ly, h.lz, tinv_d.data());
     std::vector<Real> tinv(tinv_d.begin(), tinv_d.end());
-    std::vector<Real> bufA(NSTATE), bufB(NSTATE), gm(2 * NG), R(NTILE > NR ? NTILE : NR), Tb(NCOL);   // the tile aliases the scratch
+    std::vector<Real> bufA(NSTATE), bufB(NSTATE), gm(NG), R(NTILE > NR ? NTILE : NR), Tb(NCOL);   // the tile aliases the scratch
     std::vector<double> red(2 * NT);
     EnvIO3<Real> io{state, actions, obs, reward, nusselt, t, step_count, truncated, nan_flag};
     Ctx3<Real> X{bufA.data(), bufB.data(), gm.data(), R.data(), TILED ? R.data() : nullptr, Tb.data(), red.data(), tinv.data(),
