@@ -468,8 +468,11 @@ RBC_HD void phase_copy(int tid, const Real* src, Real* dst, int nvals)
 // ------------------------------------------------------------------------------------------
 // small complex DFTs (SIGN = -1 forward, +1 inverse), natural in/out order
 // ------------------------------------------------------------------------------------------
+// aligned to its own size: every complex number in shared memory sits on a 2*sizeof(Real) boundary, and saying so lets
+// the compiler emit one 64-/128-bit access even where it cannot prove the alignment of a run-time offset (without it
+// the cluster kernel's FFT passes issued two 32-bit accesses with a 2-way bank conflict each)
 template <typename Real>
-struct cx {
+struct alignas(2 * sizeof(Real)) cx {
     Real re, im;
 };
 template <typename Real> RBC_HD cx<Real> cadd(cx<Real> a, cx<Real> b) { return {a.re + b.re, a.im + b.im}; }
