@@ -41,7 +41,7 @@ stallcols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 lines = (ROOT / "rbc_gym_b200/csrc" / core).read_text().split("\n")
 linefunc, cur = {}, None
 for n, l in enumerate(lines, 1):
-    m = re.match(r"^RBC_HD\s+[\w<>:]+\s+(\w+)\(", l)
+    m = re.match(r"^(?:template\s*<[^>]*>\s*)?(?:RBC_HD|__device__ __forceinline__|inline)\s+[\w<>:,\s\*&]+?\s+(\w+)(?:<[^>]*>)?\(", l)
     if m: cur = m.group(1)
     linefunc[n] = cur
 agg = collections.defaultdict(lambda: [0, 0, collections.Counter()])
