@@ -782,6 +782,17 @@ RBC_HD double cell_distance(const Real* uy)
 // ------------------------------------------------------------------------------------------
 #define RBX_PTR(off) reinterpret_cast<Real*>(smb + (off))
 
+// Thomas pivots of this rank's block: the on-chip copy (fp32 device path) or the global table
+template <typename G, typename Real, bool NXT_GLOBAL>
+RBC_HD const Real* local_tinv(const CtxX<Real>& X, unsigned char* smb, int rank)
+{
+#if defined(__CUDA_ARCH__)
+    if (!NXT_GLOBAL) return reinterpret_cast<const Real*>(smb + X.o_tinv);
+#endif
+    (void)smb;
+    return X.tinv + (size_t)rank * G::NZL * G::NX;
+}
+
 template <typename G, typename Real, bool NXT_GLOBAL>
 RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, unsigned o_dead, int my_rank, SyncState& S, bool after_tendency)
 {
@@ -790,14 +801,7 @@ RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, un
     // provides it — its u rows, which no neighbour writes before this CTA has finished correct() (b*/w* pushes of the
     // next tendency only touch b halo rows and one w row).  The shared memory saved holds this rank's Thomas pivots.
     const unsigned o_R = NXT_GLOBAL ? X.o_R : o_dead + (unsigned)(G::OFF_U * sizeof(Real));
-#if defined(__CUDA_ARCH__)
-    const Real* tinv_l;
-    if (NXT_GLOBAL) tinv_l = X.tinv + (size_t)my_rank * G::NZL * G::NX;
-    else tinv_l = reinterpret_cast<const Real*>(X.base + X.o_tinv);
-#define RBX_TINV(rank) tinv_l
-#else
-#define RBX_TINV(rank) (X.tinv + (size_t)(rank) * G::NZL * G::NX)
-#endif
+
     constexpr int NZL = G::NZL, NT = G::NT, NX = G::NX, N1 = G::N1, N2 = G::N2, CL = G::CL;
     constexpr bool ASYNC = RBX_ASYNC(G, NXT_GLOBAL);
     constexpr unsigned ROWB = NX * sizeof(Real);           // bytes of one pushed row
@@ -813,14 +817,14 @@ RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, un
         for (int item = tid; item < (N2 / 2) * NZL; item += NT)
             fft_passB_fwd_untangle<G>(item / NZL, RBX_PTR(o_R) + (item % NZL) * G::RSTR, RBX_PTR(X.o_tw2));
     )
-    RBX_PHASE_L(G, phase_thomas_sweep<G>(tid, RBX_PTR(o_R), RBX_TINV(rank), RBX_PTR(X.o_mid), X.thomas_scale);)
+    RBX_PHASE_L(G, phase_thomas_sweep<G>(tid, RBX_PTR(o_R), local_tinv<G, Real, NXT_GLOBAL>(X, smb, rank), RBX_PTR(X.o_mid), X.thomas_scale);)
     const unsigned o_ends = X.o_ends + (S.n[CH_E] & 1u) * (unsigned)(CL * 2 * NX * sizeof(Real));     // double-buffered by use parity
     RBX_PHASE_X(G, ASYNC,
         PeerBuf<Real> peers[CL];
         RBC_UNROLL
         for (int j = 0; j < CL; ++j)
             peers[j] = make_peer<ASYNC, Real>(X, smb, o_ends, bar_off(X.o_bars, CH_E, S.n[CH_E]), rank, j, j != rank);
-        phase_thomas_back<G, ASYNC>(tid, rank, RBX_PTR(o_R), RBX_TINV(rank), RBX_PTR(X.o_mid), RBX_PTR(o_ends), peers);
+        phase_thomas_back<G, ASYNC>(tid, rank, RBX_PTR(o_R), local_tinv<G, Real, NXT_GLOBAL>(X, smb, rank), RBX_PTR(X.o_mid), RBX_PTR(o_ends), peers);
     )
     if (CL > 1) {
         if (ASYNC) { RBX_WAIT(CH_E, S.n[CH_E], (unsigned)(CL - 1) * 2u * ROWB); }
