@@ -127,6 +127,11 @@ int rbc2d_observe_host(rbc2d_sim* sim, float* obs_host, double* nu_state_host, d
 int rbc2d_get_state_dev(rbc2d_sim* sim, float* out_dev, int32_t channels);
 int rbc2d_get_state_host(rbc2d_sim* sim, float* out_host, int32_t channels);
 
+/* render("rgb_array") for the whole batch on the device (rbc2D.py:214-261 renders one env on the host with matplotlib's
+ * turbo colormap): temperature channel -> turbo RGB, vmin = 1, vmax = 2 + heater_limit, origin at the top left like the
+ * reference image.  out_dev: [B][nz][nx][3] uint8.  The colormap is the 7-term polynomial fit of turbo (|error| <= 1/255). */
+int rbc2d_render_rgb_dev(rbc2d_sim* sim, uint8_t* out_dev);
+
 /* Raw fields in checkpoint layout [B][2*nx*nz + nx*(nz+1)] float64 (for parity tests / checkpoint writing). */
 int rbc2d_get_fields_host(rbc2d_sim* sim, double* fields_host);
 

@@ -68,7 +68,7 @@ ABI_SYMBOLS = (
     "rbc2d_state_values_per_env", "rbc2d_load_checkpoints", "rbc2d_reset_from_checkpoints_dev",
     "rbc2d_reset_from_fields_host", "rbc2d_step_dev", "rbc2d_step_host", "rbc2d_observe_dev", "rbc2d_observe_host",
     "rbc2d_get_state_dev", "rbc2d_get_state_host", "rbc2d_get_fields_host", "rbc2d_get_info_host",
-    "rbc2d_launch_count", "rbc2d_last_step_kernel_ms", "rbc2d_set_wrappers", "rbc2d_get_cell_dist_host",
+    "rbc2d_launch_count", "rbc2d_last_step_kernel_ms", "rbc2d_set_wrappers", "rbc2d_get_cell_dist_host", "rbc2d_render_rgb_dev",
     "rbc3d_create", "rbc3d_destroy", "rbc3d_set_stream", "rbc3d_state_values_per_env", "rbc3d_load_checkpoints",
     "rbc3d_reset_from_checkpoints_dev", "rbc3d_reset_from_fields_host", "rbc3d_step_dev", "rbc3d_step_host",
     "rbc3d_observe_dev", "rbc3d_get_fields_host", "rbc3d_get_info_host", "rbc3d_launch_count", "rbc3d_last_step_kernel_ms",
@@ -122,6 +122,7 @@ def load_library(build_if_missing: bool = True):
     L.rbc2d_get_info_host.argtypes = [vp, vp, vp]
     L.rbc2d_set_wrappers.argtypes = [vp, C.POINTER(Rbc2dWrappers)]
     L.rbc2d_get_cell_dist_host.argtypes = [vp, vp]
+    L.rbc2d_render_rgb_dev.argtypes = [vp, vp]
     L.rbc2d_launch_count.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ip), C.POINTER(ip)]
     L.rbc2d_last_step_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.rbc3d_create.argtypes = [C.POINTER(Rbc3dConfig), C.POINTER(vp)]
@@ -335,6 +336,13 @@ class Sim2D:
         out = self.torch.empty((self.B, ch, self.nz, self.nx), dtype=self.torch.float32, device=self.device)
         self._use_current_stream()
         self._check(self._L.rbc2d_get_state_dev(self._h, C.c_void_p(out.data_ptr()), ch))
+        return out
+
+    def render_rgb(self):
+        """`render("rgb_array")` for every environment, on the device: uint8 CUDA tensor `[B, Nz, Nx, 3]`, origin top left."""
+        out = self.torch.empty((self.B, self.nz, self.nx, 3), dtype=self.torch.uint8, device=self.device)
+        self._use_current_stream()
+        self._check(self._L.rbc2d_render_rgb_dev(self._h, C.c_void_p(out.data_ptr())))
         return out
 
     def fields(self) -> np.ndarray:

@@ -130,6 +130,24 @@ __global__ void rbc2d_get_state_kernel(const Real* state, const Real* pressure, 
     }
 }
 
+// render("rgb_array"): b -> turbo RGB (polynomial fit, same coefficients as rbc_gym_b200/colormap.py), flipped in z
+template <typename Real>
+__global__ void rbc2d_render_kernel(const Real* state, uint8_t* out, int B, int nx, int nz, int NSTATE, float vmin, float inv_range)
+{
+    const size_t ncell = (size_t)nx * nz, total = ncell * B;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int env = (int)(q / ncell), c = (int)(q % ncell), row = c / nx, i = c % nx;
+        const float v = (float)state[(size_t)env * NSTATE + (size_t)(nz - 1 - row) * nx + i];
+        const float x = fminf(fmaxf((v - vmin) * inv_range, 0.0f), 1.0f);
+        const float r = 0.13572138f + x * (4.61539260f + x * (-42.66032258f + x * (132.13108234f + x * (-152.94239396f + x * 59.28637943f))));
+        const float g = 0.09140261f + x * (2.19418839f + x * (4.84296658f + x * (-14.18503333f + x * (4.27729857f + x * 2.82956604f))));
+        const float b = 0.10667330f + x * (12.64194608f + x * (-60.58204836f + x * (110.36276771f + x * (-89.90310912f + x * 27.34824973f))));
+        out[3 * q + 0] = (uint8_t)(fminf(fmaxf(r, 0.0f), 1.0f) * 255.0f);
+        out[3 * q + 1] = (uint8_t)(fminf(fmaxf(g, 0.0f), 1.0f) * 255.0f);
+        out[3 * q + 2] = (uint8_t)(fminf(fmaxf(b, 0.0f), 1.0f) * 255.0f);
+    }
+}
+
 template <typename Real>
 __global__ void rbc2d_get_fields_kernel(const Real* state, double* out, size_t total)
 {
@@ -543,6 +561,20 @@ int rbc2d_get_state_host(rbc2d_sim* s, float* out, int32_t channels)
     }
     cudaFree(tmp);
     return rc;
+}
+
+int rbc2d_render_rgb_dev(rbc2d_sim* s, uint8_t* out)
+{
+    if (!s || !out) return fail("rbc2d_render_rgb_dev: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    const float vmin = 1.0f, inv = 1.0f / (float)(1.0 + s->cfg.heater_limit);      // vmin=1, vmax=2+limit (rbc2D.py:244-249)
+    if (s->cfg.precision == 32)
+        rbc2d_render_kernel<float><<<148 * 8, 256, 0, s->stream>>>((const float*)s->state, out, s->B, s->nx, s->nz, s->nstate, vmin, inv);
+    else
+        rbc2d_render_kernel<double><<<148 * 8, 256, 0, s->stream>>>((const double*)s->state, out, s->B, s->nx, s->nz, s->nstate, vmin, inv);
+    CK(cudaGetLastError());
+    s->launches += 1;
+    return 0;
 }
 
 int rbc2d_get_fields_host(rbc2d_sim* s, double* out)

@@ -138,5 +138,10 @@ class RBCVectorEnv2D:
     def get_state(self):
         return self.sim.get_state()
 
+    def render(self):
+        """`rgb_array` frames of all environments as one uint8 CUDA tensor `[num_envs, Nz, Nx, 3]` (e.g. for logging videos
+        like `example/run_wandb.py:25-59` without a host round trip per frame)."""
+        return self.sim.render_rgb()
+
     def close(self):
         self.sim.close()

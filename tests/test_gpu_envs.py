@@ -172,3 +172,21 @@ def test_checkpoint_generator_reaches_reference_fixed_point(tmp_path):
     dx, dz = 2 * np.pi / 96, 2 / 64
     div = (np.roll(c.u, -1, axis=-1) - c.u) / dx + (c.w[:, 1:] - c.w[:, :-1]) / dz
     assert np.abs(div).max() < 1e-13
+
+
+def test_device_render_matches_host_colormap(ckpt_ra1e5):
+    """rbc2d_render_rgb_dev (whole batch on the device) against the host-side turbo map the single env renders with."""
+    import torch
+    from rbc_gym_b200.colormap import turbo
+    from rbc_gym_b200.envs import RBCVectorEnv2D
+    env = RBCVectorEnv2D(5, rayleigh_number=100_000, heater_duration=0.3, checkpoint=CKPT, precision=32)
+    env.reset(seed=1)
+    env.step(torch.rand((5, 12), device="cuda") * 2 - 1)
+    img = env.render().cpu().numpy()
+    assert img.shape == (5, 64, 96, 3) and img.dtype == np.uint8
+    state = env.get_state().cpu().numpy()
+    ref = turbo(state[:, 0, ::-1, :], vmin=1, vmax=2.75)                 # flipped: origin at the top left (rbc2D.py:239-241)
+    assert np.abs(img.astype(int) - ref.astype(int)).max() <= 1           # fp32 vs fp64 polynomial: at most one level
+    assert img[:, -1].mean() > img[:, 0].mean() - 255                     # sanity: image has structure
+    assert img.std() > 10
+    env.close()
