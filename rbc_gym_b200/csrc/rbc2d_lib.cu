@@ -283,7 +283,7 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
     *out = nullptr;
     const bool dedicated = (cfg->nx == NX && cfg->nz == NZ) && !(rbc2dx_api::supported(cfg->nx, cfg->nz) && !cfg->pressure);
     if (!dedicated && !rbc2dx_api::supported(cfg->nx, cfg->nz))
-        return fail("rbc2d_create: registered grids are 96 x 64 and 192 x 128");
+        return fail("rbc2d_create: registered grids are 96 x 64, 128 x 64 and 192 x 128");
     if (!dedicated && cfg->pressure) return fail("rbc2d_create: pressure channels are available on the 96 x 64 grid only");
     if (cfg->num_envs < 1) return fail("rbc2d_create: num_envs must be >= 1");
     if (cfg->precision != 32 && cfg->precision != 64) return fail("rbc2d_create: precision must be 32 or 64");

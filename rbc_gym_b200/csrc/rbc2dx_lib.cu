@@ -171,6 +171,7 @@ static bool force_cluster()
 int supported(int nx, int nz)
 {
     if (nx == 192 && nz == 128) return 1;
+    if (nx == 128 && nz == 64) return 1;
     if (nx == 96 && nz == 64 && force_cluster()) return 1;
     return 0;
 }
@@ -186,6 +187,10 @@ int create(int nx, int nz, int precision, int device, double lx, double lz, Plan
         // fp32: 4 CTAs x 32 rows, both state buffers on-chip; fp64: 8 CTAs x 16 rows, predicted state in global memory
         if (precision == 32) rc = create_impl<Grid<192, 128, 4, 2>, float, false>(p, "rbc2dx_env_kernel<192x128,cl4,f32>");
         else rc = create_impl<Grid<192, 128, 8, 2>, double, true>(p, "rbc2dx_env_kernel<192x128,cl8,f64>");
+    } else if (nx == 128 && nz == 64) {
+        // a power-of-two width: 64-point complex FFT = 4 x 16; 2 CTAs x 32 rows, 256 threads = 128 columns x 2 strips
+        if (precision == 32) rc = create_impl<Grid<128, 64, 2, 2, 4>, float, false>(p, "rbc2dx_env_kernel<128x64,cl2,f32>");
+        else rc = create_impl<Grid<128, 64, 2, 2, 4>, double, true>(p, "rbc2dx_env_kernel<128x64,cl2,f64>");
     } else if (nx == 96 && nz == 64) {
         if (precision == 32) rc = create_impl<Grid<96, 64, 2, 4>, float, false>(p, "rbc2dx_env_kernel<96x64,cl2,f32>");
         else rc = create_impl<Grid<96, 64, 2, 4>, double, true>(p, "rbc2dx_env_kernel<96x64,cl2,f64>");

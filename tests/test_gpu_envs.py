@@ -190,3 +190,31 @@ def test_device_render_matches_host_colormap(ckpt_ra1e5):
     assert img[:, -1].mean() > img[:, 0].mean() - 255                     # sanity: image has structure
     assert img.std() > 10
     env.close()
+
+
+def test_config1_run_2d_example(ckpt_ra1e4):
+    """BASELINE config 1 = example/run_2D.py: the registered defaults (Ra=1e4, heater_duration 1.5) with pressure=True and the
+    full grid as observation, random actions; fp64 env against the oracle in hydrostatic-split mode for two action steps."""
+    import rbc_gym_b200 as R
+    c = ckpt_ra1e4
+    env = R.make(R.ENV_ID_2D, pressure=True, observation_shape=[64, 96], checkpoint=str(ROOT / "data/checkpoints/test/ckpt_ra10000.h5"),
+                 checkpoint_idx=4)
+    assert env.ra == 10_000 and env.heater_duration == 1.5 and env.episode_steps == 200
+    assert env.observation_space.shape == (5, 64, 96) and env.action_space.shape == (12,)
+    obs, info = env.reset(seed=0)
+    assert obs.shape == (5, 64, 96) and info["state"].shape == (5, 64, 96)
+    P = O.make_params(1e4, split_phy=True)
+    b, u, w = c.b[4], c.u[4], c.w[4]
+    env.action_space.seed(5)
+    for n in range(2):
+        a = env.action_space.sample()
+        obs, reward, terminated, truncated, info = env.step(a)
+        r = O.step(P, b, u, w, a.astype(np.float64), O.substep_schedule(1.5), want_pressure=True)
+        b, u, w = r["b"], r["u"], r["w"]
+        ref = np.stack([b, u, w[:-1], r["phy"], r["pnhs"]]).astype(np.float32)
+        np.testing.assert_allclose(obs, ref, rtol=0, atol=2e-6)              # full-grid sensors: obs == state, 5 channels
+        np.testing.assert_array_equal(obs, info["state"])
+        ns, no = O.nusselt_state_obs(P, b, u, w, (64, 96))
+        assert info["nusselt_obs"] == pytest.approx(no, rel=1e-9) and info["nusselt_state"] == pytest.approx(ns, rel=1e-9)
+        assert reward == pytest.approx(-no, rel=1e-9) and info["t"] == pytest.approx(1.5 * (n + 1)) and not truncated
+    env.close()

@@ -172,3 +172,24 @@ def test_checkpoint_generator_and_reset_at_192x128(B, tmp_path):
     assert np.array_equal(b[0], c.b[1]) and np.array_equal(u[0], c.u[1]) and np.array_equal(w[0], c.w[1])
     np.testing.assert_array_equal(obs[0], c.b[1][::16, ::4].astype(np.float32))
     env.close()
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-10), (32, 1e-5)])
+def test_power_of_two_grid_128x64_matches_oracle(B, precision, tol):
+    """A second registered cluster grid (128 x 64: 4 x 16 FFT split, 2 CTAs per environment, 256 threads per CTA)."""
+    import torch
+    nx, nz = 128, 64
+    P = O.make_params(1e5, nx=nx, nz=nz, split_phy=False)
+    states = [smooth_state(nx, nz, seed=s) for s in (5, 6)]
+    acts = np.random.default_rng(11).uniform(-1, 1, (2, 12)).astype(np.float32)
+    sim = B.Sim2D(2, ra=1e5, dt_action=0.2, dt_solver=0.03, state_shape=(nz, nx), obs_shape=(8, 64), precision=precision)
+    sim.reset_from_fields(np.concatenate([B.pack_fields(b[None], u[None], w[None]) for b, u, w in states]), project=False)
+    obs, rew, nus, nuo, trunc, nan = sim.step(torch.from_numpy(acts).cuda())
+    b, u, w = B.split_fields(sim.fields(), (nz, nx))
+    assert not nan.any().item() and sim.launch_info()["grid"] == 4
+    for j, (b0, u0, w0) in enumerate(states):
+        r = O.step(P, b0, u0, w0, acts[j].astype(np.float64), O.substep_schedule(0.2, 0.03))
+        assert rel(b[j], r["b"]) < tol and rel(u[j], r["u"]) < tol and rel(w[j], r["w"]) < tol
+        ns, no = O.nusselt_state_obs(P, r["b"], r["u"], r["w"], (8, 64))
+        assert nuo[j].item() == pytest.approx(no, abs=1e-8 if precision == 64 else 2e-3)
+    sim.close()
