@@ -37,10 +37,12 @@
 #define RBC_PHASE_N(NTHREADS, ...) { const int tid = threadIdx.x; __VA_ARGS__ } __syncthreads();
 #define RBC_UNROLL _Pragma("unroll")
 #define RBC_NOUNROLL _Pragma("unroll 1")
+#define RBC_UNROLL2 _Pragma("unroll 2")
 #else
 #define RBC_PHASE_N(NTHREADS, ...) for (int tid = 0; tid < (NTHREADS); ++tid) { __VA_ARGS__ }
 #define RBC_UNROLL
 #define RBC_NOUNROLL
+#define RBC_UNROLL2
 #endif
 #define RBC_PHASE(...) RBC_PHASE_N(rbc2d::NT, __VA_ARGS__)
 

@@ -319,13 +319,15 @@ RBC_HD void tendency3_column(const Consts3<Real>& C, const Real* RBC_RESTRICT sr
             for (int d = 0; d < 7; ++d) { wx[d] = wxn[d]; wy[d] = wyn[d]; }
         };
 
-        // The level loop is deliberately NOT unrolled: one interior body and one wall body (with run-time order
-        // selection) keep the march inside the instruction cache; the sliding windows cost ~45 register moves per level.
+        // The level loop is deliberately NOT fully unrolled: a wall body (run-time order selection) and the interior body
+        // unrolled twice keep the march inside the instruction cache; the sliding windows cost ~45 register moves per level,
+        // half of which the two-fold unrolling renames away (measured: rolled 59.1 k, x2 61.3 k, x4 58.1 k env-steps/s).
         RBC_NOUNROLL
-        for (int k = 0; k < NZ; ++k) {
-            if (k >= 2 && k <= NZ - 4) level(BoolTag<false>{}, k);
-            else level(BoolTag<true>{}, k);
-        }
+        for (int k = 0; k < 2; ++k) level(BoolTag<true>{}, k);
+        RBC_UNROLL2
+        for (int k = 2; k <= NZ - 4; ++k) level(BoolTag<false>{}, k);
+        RBC_NOUNROLL
+        for (int k = NZ - 3; k < NZ; ++k) level(BoolTag<true>{}, k);
         nxt[GW + NZ * NCOL + c] = Real(0);               // top wall face
     }
 }
