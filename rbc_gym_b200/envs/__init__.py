@@ -1,6 +1,6 @@
 from .rbc2d import RBCField, RayleighBenardConvection2DEnv, noise_initial_fields
 from .rbc3d import RayleighBenardConvection3DEnv, noise_initial_fields_3d
-from .vector import RBCVectorEnv2D
+from .vector import RBCVectorEnv2D, RBCVectorEnv3D
 
-__all__ = ["RBCField", "RayleighBenardConvection2DEnv", "RayleighBenardConvection3DEnv", "RBCVectorEnv2D",
+__all__ = ["RBCField", "RayleighBenardConvection2DEnv", "RayleighBenardConvection3DEnv", "RBCVectorEnv2D", "RBCVectorEnv3D",
            "noise_initial_fields", "noise_initial_fields_3d"]

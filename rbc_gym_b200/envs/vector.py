@@ -145,3 +145,103 @@ class RBCVectorEnv2D:
 
     def close(self):
         self.sim.close()
+
+
+class RBCVectorEnv3D:
+    """The 3D twin: B independent `RayleighBenardConvection3D-v0` environments as one on-device batch — what
+    `SubprocVecEnv([make_env(i, ...) for i in range(n_envs)])` of `experiments/run_sarl.py:130-153` becomes.
+
+    Observations are the full state `(num_envs, 4, Nz, Ny, Nx)` float32 CUDA tensors (`rbc3D.py:229-232`), actions
+    `(num_envs, 8, 8)` in [-1, 1] with `action[:, i, j]` <-> patch i along x, j along y, reward = -Nu, `info["nusselt"]`.
+    Resets come from a `3D_ckpt_ra*.h5` bank (device gather) or from the noise initialisation; autoreset as in the 2D class."""
+
+    def __init__(self, num_envs: int, rayleigh_number: float = 2500, prandtl_number: float = 0.7, domain=(2, 4 * np.pi, 4 * np.pi),
+                 state_shape=(16, 32, 32), temperature_difference=(1, 2), heater_segments: int = 8, heater_limit: float = 0.9,
+                 heater_duration: float = 0.125, episode_length: float = 300, dt_solver: float = 0.01, checkpoint: Optional[str] = None,
+                 precision: int = 32, device: int = 0, autoreset_mode: str = "next_step", seed: int = 0, env_id_offset: int = 0):
+        import torch
+
+        if autoreset_mode not in ("next_step", "same_step", "disabled"):
+            raise ValueError("autoreset_mode must be next_step, same_step or disabled")
+        self.torch = torch
+        self.num_envs = int(num_envs)
+        self.is_3d = True
+        self.ra, self.episode_length = rayleigh_number, episode_length
+        self.state_shape, self.domain = tuple(state_shape), tuple(domain)
+        self.temperature_difference = list(temperature_difference)
+        self.heater_segments, self.heater_limit, self.heater_duration = heater_segments, heater_limit, heater_duration
+        self.checkpoint, self.autoreset_mode = checkpoint, autoreset_mode
+        self.sim = backend.Sim3D(self.num_envs, ra=float(rayleigh_number), pr=float(prandtl_number), domain=self.domain,
+                                 state_shape=self.state_shape, temperature_difference=tuple(temperature_difference),
+                                 heaters=heater_segments, heater_limit=heater_limit, heater_duration=heater_duration, dt_solver=dt_solver,
+                                 episode_length=float(episode_length), precision=precision, device=device)
+        self.device = self.sim.device
+        self.single_action_space = spaces.Box(-1, 1, shape=(heater_segments, heater_segments), dtype=np.float32)
+        self.single_observation_space = spaces.Box(-np.inf, np.inf, shape=(4, *self.state_shape), dtype=np.float32)
+        self.action_space = spaces.Box(-1, 1, shape=(self.num_envs, heater_segments, heater_segments), dtype=np.float32)
+        self.observation_space = spaces.Box(-np.inf, np.inf, shape=(self.num_envs, 4, *self.state_shape), dtype=np.float32)
+        if checkpoint:
+            from ..h5lite import load_checkpoint_3d
+            self.sim.load_checkpoints(load_checkpoint_3d(checkpoint))
+        self.env_ids = torch.arange(env_id_offset, env_id_offset + self.num_envs, device=self.device, dtype=torch.int64)
+        self.seed = int(seed)
+        self._episode = torch.zeros(self.num_envs, dtype=torch.int64, device=self.device)
+        self._pending = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        self.episode_return = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+
+    _draw_checkpoints = RBCVectorEnv2D._draw_checkpoints
+
+    def _reset_envs(self, ids, ckpt_idx=None):
+        t = self.torch
+        if ids.numel() == 0:
+            return
+        if self.sim.n_episodes == 0:
+            from .rbc3d import noise_initial_fields_3d
+            rng = np.random.default_rng([self.seed, int(self._episode.max().item())])
+            T = self.temperature_difference
+            fields = np.concatenate([noise_initial_fields_3d(rng, self.state_shape, min_b=T[0], delta_b=T[1] - T[0], lz=float(self.domain[0]))
+                                     for _ in range(ids.numel())])
+            self.sim.reset_from_fields(fields, env_ids=ids.cpu().numpy(), project=True)
+        else:
+            idx = self._draw_checkpoints(ids) if ckpt_idx is None else t.as_tensor(ckpt_idx, dtype=t.int32, device=self.device)
+            self.sim.reset_from_checkpoints(idx, env_ids=ids.to(t.int32))
+        self._episode[ids] += 1
+        self.episode_return[ids] = 0
+
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        t = self.torch
+        if seed is not None:
+            self.seed = int(seed)
+        self._episode.zero_()
+        self._reset_envs(t.arange(self.num_envs, device=self.device), None if not options else options.get("checkpoint_idx"))
+        self._pending.zero_()
+        obs, nu = self.sim.observe()
+        return obs, {"nusselt": nu}
+
+    def step(self, actions):
+        t = self.torch
+        pend = self._pending
+        have_pending = self.autoreset_mode == "next_step" and bool(pend.any())
+        obs, rew, nu, trunc, nan = self.sim.step(actions)
+        bad = nan.to(t.bool) & ~pend if have_pending else nan.to(t.bool)
+        if bool(bad.any()):
+            raise RuntimeError("Error in simulation step, probably NaN values")    # rbc3D.py:207-212
+        truncated, reward, info = trunc.to(t.bool), rew, {"nusselt": nu}
+        if have_pending:
+            self._reset_envs(pend.nonzero().flatten())
+            obs, nu = self.sim.observe()
+            info = {"nusselt": nu}
+            reward = rew.clone()
+            reward[pend] = 0
+            truncated = truncated & ~pend
+        self.episode_return += reward.to(t.float64)
+        if self.autoreset_mode == "same_step" and bool(truncated.any()):
+            info["final_obs"] = obs.clone()
+            info["final_info"] = {"nusselt": nu.clone(), "episode_return": self.episode_return.clone()}
+            self._reset_envs(truncated.nonzero().flatten())
+            obs, _ = self.sim.observe()
+        self._pending = truncated.clone() if self.autoreset_mode == "next_step" else t.zeros_like(truncated)
+        return obs, reward, t.zeros_like(truncated), truncated, info
+
+    def close(self):
+        self.sim.close()

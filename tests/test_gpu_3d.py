@@ -102,3 +102,33 @@ def test_3d_convection_onset_statistics():
     assert abs(late[150.0] - 1.0) < 5e-3, late
     assert 1.25 < late[500.0] < 1.50, late
     assert 1.85 < late[4000.0] < 2.45, late
+
+
+@pytest.mark.parametrize("mode", ["next_step", "same_step"])
+def test_vector_env_3d_autoreset_and_batch_consistency(mode):
+    """RBCVectorEnv3D (the on-device replacement of run_sarl.py's SubprocVecEnv): shapes, reward = -Nu, truncation and
+    autoreset semantics, and every env of the batch behaves like the single-env class."""
+    import torch
+    from rbc_gym_b200.envs import RBCVectorEnv3D
+    env = RBCVectorEnv3D(6, rayleigh_number=2500, heater_duration=0.125, episode_length=1.0, autoreset_mode=mode, seed=3)
+    obs, info = env.reset(seed=3)
+    assert obs.shape == (6, 4, 16, 32, 32) and info["nusselt"].shape == (6,)
+    acts = torch.rand((6, 8, 8), device="cuda") * 2 - 1
+    obs, rew, term, trunc, info = env.step(acts)                      # t = 0.5
+    assert torch.allclose(rew.double(), -info["nusselt"], atol=1e-6) and not trunc.any() and not term.any()
+    obs1 = obs.clone()
+    obs, rew, term, trunc, info = env.step(acts)                      # t = 1.0 >= episode_length: truncation
+    assert trunc.all()
+    t, step = env.sim.info()
+    if mode == "same_step":
+        assert "final_obs" in info and not torch.equal(info["final_obs"], obs)
+        assert np.all(t == 0.0) and np.all(step == 1)                 # already reset
+    else:
+        assert np.all(t == 1.0)
+        obs, rew, term, trunc, info = env.step(acts)                  # this call only resets
+        t, step = env.sim.info()
+        assert np.all(t == 0.0) and torch.all(rew == 0) and not trunc.any()
+    with pytest.raises(RuntimeError, match="Action size"):
+        env.step(torch.zeros((6, 4, 4), device="cuda"))
+    assert not torch.equal(obs1[0], obs1[1])
+    env.close()
