@@ -193,3 +193,30 @@ def test_power_of_two_grid_128x64_matches_oracle(B, precision, tol):
         ns, no = O.nusselt_state_obs(P, r["b"], r["u"], r["w"], (8, 64))
         assert nuo[j].item() == pytest.approx(no, abs=1e-8 if precision == 64 else 2e-3)
     sim.close()
+
+
+def test_config3_full_batch_properties(B):
+    """Config 3 at bench size (1056 envs = 32 per resident cluster): size-independent properties after an action step —
+    discretely solenoidal, impenetrable walls, zero net vertical mass flux, bounded temperature, replica-exactness."""
+    import torch
+    from rbc_gym_b200.envs.rbc2d import noise_initial_fields
+    n = 1056
+    rng = np.random.default_rng(1)
+    base = np.concatenate([noise_initial_fields(rng, (NZ, NX), kick=0.05) for _ in range(4)])
+    sim = B.Sim2D(n, ra=RA, dt_action=0.3, dt_solver=DTS, state_shape=(NZ, NX), precision=32)
+    sim.reset_from_fields(np.tile(base, (n // 4, 1)), project=True)
+    acts = torch.from_numpy(np.tile(np.random.default_rng(2).uniform(-1, 1, (4, 12)).astype(np.float32), (n // 4, 1))).cuda()
+    for _ in range(2):
+        obs, rew, nus, nuo, trunc, nan = sim.step(acts)
+    assert not nan.any().item() and torch.isfinite(rew).all().item()
+    f = sim.fields()
+    b, u, w = B.split_fields(f, (NZ, NX))
+    dx, dz = 2 * np.pi / NX, 2.0 / NZ
+    div = (np.roll(u, -1, axis=-1) - u) / dx + (w[:, 1:] - w[:, :-1]) / dz
+    assert np.abs(div).max() < 1e-4
+    assert np.all(w[:, 0] == 0) and np.all(w[:, -1] == 0)
+    assert np.abs(w.sum(axis=-1)).max() < 1e-3                        # no net mass flux through any horizontal plane
+    assert b.min() > 0.2 and b.max() < 2.8
+    for i in range(4, n):
+        assert np.array_equal(f[i], f[i % 4])
+    sim.close()
