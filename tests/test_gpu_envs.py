@@ -218,3 +218,32 @@ def test_config1_run_2d_example(ckpt_ra1e4):
         assert info["nusselt_obs"] == pytest.approx(no, rel=1e-9) and info["nusselt_state"] == pytest.approx(ns, rel=1e-9)
         assert reward == pytest.approx(-no, rel=1e-9) and info["t"] == pytest.approx(1.5 * (n + 1)) and not truncated
     env.close()
+
+
+def test_full_episode_rollout_4096_envs_autoreset():
+    """Config 2 as SURVEY 8d describes it: 4096 envs reset from the train checkpoints, U(-1,1) actions, one full episode of
+    300 action steps (dt = 1) so that the auto-reset fires exactly once at the end; nothing may blow up on the way."""
+    import torch
+    from rbc_gym_b200.envs import RBCVectorEnv2D
+    n = 4096
+    env = RBCVectorEnv2D(n, rayleigh_number=100_000, heater_duration=1.0, episode_length=300, checkpoint=CKPT, precision=32,
+                         autoreset_mode="same_step", seed=11)
+    obs, info = env.reset(seed=11)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    n_trunc, rew_sum, nu_max = 0, 0.0, 0.0
+    for step in range(300):
+        a = torch.rand((n, 12), device="cuda", generator=g) * 2 - 1
+        obs, rew, term, trunc, info = env.step(a)
+        n_trunc += int(trunc.sum().item())
+        if step % 50 == 49 or step == 299:
+            assert torch.isfinite(rew).all().item() and torch.isfinite(obs).all().item()
+            rew_sum += float(rew.mean().item())
+            nu_max = max(nu_max, float(info["nusselt_state"].max().item()))
+    assert n_trunc == n                                           # every env truncated exactly once, at step 300
+    t, stepc = env.sim.info()
+    assert np.all(t == 0.0) and np.all(stepc == 1)                # SAME_STEP autoreset already happened
+    assert "final_obs" in info and info["final_info"]["episode_return"].shape == (n,)
+    assert -12.0 < rew_sum / 7 < -3.0 and nu_max < 40.0           # Ra=1e5 with random heating: Nu_obs ~ 5-9
+    ret = info["final_info"]["episode_return"].cpu().numpy()
+    assert np.all(np.isfinite(ret)) and -300 * 12 < ret.min() and ret.max() < -300 * 2
+    env.close()
