@@ -479,15 +479,14 @@ RBC_HD void dftn(cx<Real>* x)
 // item = group * ROWS + row: lanes walk consecutive rows (conflict-free 64-bit accesses on padded rows).
 // ------------------------------------------------------------------------------------------
 template <typename G, typename Real>
-RBC_HD void fft_passA_fwd_div(int item, const Consts<Real>& C, const Real* RBC_RESTRICT p, const Real* RBC_RESTRICT w_top_remote,
-                              Real* RBC_RESTRICT R, const Real* RBC_RESTRICT twN)
+RBC_HD void fft_passA_fwd_div(int item, const Consts<Real>& C, const Real* RBC_RESTRICT p, Real* RBC_RESTRICT R,
+                              const Real* RBC_RESTRICT twN)
 {
     constexpr int N1 = G::N1, N2 = G::N2, SX = G::SX, H = G::HALO;
     const int n1 = item / G::NZL, row = item % G::NZL;
     const Real* pu = p + G::OFF_U + (row + H) * SX;
     const Real* pw0 = p + G::OFF_W + (row + H) * SX;
     const Real* pw1 = pw0 + SX;
-    (void)w_top_remote;
     cx<Real> a[N2];
     RBC_UNROLL
     for (int n2 = 0; n2 < N2; ++n2) {
@@ -811,7 +810,7 @@ RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, un
     if (after_tendency) S.n[CH_W] += 1;
     RBX_PHASE_L(G,
         for (int item = tid; item < N1 * NZL; item += NT)
-            fft_passA_fwd_div<G>(item, C, RBX_PTR(o_p), (const Real*)nullptr, RBX_PTR(o_R), RBX_PTR(X.o_twN));
+            fft_passA_fwd_div<G>(item, C, RBX_PTR(o_p), RBX_PTR(o_R), RBX_PTR(X.o_twN));
     )
     RBX_PHASE_L(G,
         for (int item = tid; item < (N2 / 2) * NZL; item += NT)
