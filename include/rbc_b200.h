@@ -99,6 +99,9 @@ int rbc2d_reset_from_checkpoints_dev(rbc2d_sim* sim, const int32_t* env_ids_dev,
  * the environments (NULL = the first n). */
 int rbc2d_reset_from_fields_host(rbc2d_sim* sim, const int32_t* env_ids_host, const double* fields_host, int32_t n,
                                  int32_t project);
+/* Same with everything already on the device (e.g. noise fields drawn by a device generator): no host round trip, no
+ * synchronisation.  env_ids_dev may be NULL (= the first n environments). */
+int rbc2d_reset_from_fields_dev(rbc2d_sim* sim, const int32_t* env_ids_dev, const double* fields_dev, int32_t n, int32_t project);
 
 /* step_simulation for the whole batch + get_observation + get_nusselt + truncation, fused.
  *   actions      [B][heaters] float32 in [-1,1]

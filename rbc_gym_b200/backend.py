@@ -66,7 +66,7 @@ class Rbc3dConfig(C.Structure):
 ABI_SYMBOLS = (
     "rbc_abi_version", "rbc_last_error", "rbc2d_create", "rbc2d_destroy", "rbc2d_set_stream", "rbc2d_num_envs",
     "rbc2d_state_values_per_env", "rbc2d_load_checkpoints", "rbc2d_reset_from_checkpoints_dev",
-    "rbc2d_reset_from_fields_host", "rbc2d_step_dev", "rbc2d_step_host", "rbc2d_observe_dev", "rbc2d_observe_host",
+    "rbc2d_reset_from_fields_host", "rbc2d_reset_from_fields_dev", "rbc2d_step_dev", "rbc2d_step_host", "rbc2d_observe_dev", "rbc2d_observe_host",
     "rbc2d_get_state_dev", "rbc2d_get_state_host", "rbc2d_get_fields_host", "rbc2d_get_info_host",
     "rbc2d_launch_count", "rbc2d_last_step_kernel_ms", "rbc2d_set_wrappers", "rbc2d_get_cell_dist_host", "rbc2d_render_rgb_dev",
     "rbc3d_create", "rbc3d_destroy", "rbc3d_set_stream", "rbc3d_state_values_per_env", "rbc3d_load_checkpoints",
@@ -112,6 +112,7 @@ def load_library(build_if_missing: bool = True):
     L.rbc2d_load_checkpoints.argtypes = [vp, vp, vp, vp, ip]
     L.rbc2d_reset_from_checkpoints_dev.argtypes = [vp, vp, vp, ip]
     L.rbc2d_reset_from_fields_host.argtypes = [vp, vp, vp, ip, ip]
+    L.rbc2d_reset_from_fields_dev.argtypes = [vp, vp, vp, ip, ip]
     L.rbc2d_step_dev.argtypes = [vp] * 8
     L.rbc2d_step_host.argtypes = [vp] * 8
     L.rbc2d_observe_dev.argtypes = [vp] * 4
@@ -261,6 +262,32 @@ class Sim2D:
         ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
         self._use_current_stream()
         self._check(self._L.rbc2d_reset_from_fields_host(self._h, _np_ptr(ids), _np_ptr(f), f.shape[0], int(project)))
+
+    def reset_from_fields_dev(self, fields, env_ids=None, project: bool = True):
+        """`reset_from_fields` with float64 CUDA tensors `[n, nstate]` (and int32 CUDA `env_ids`): nothing touches the host."""
+        t = self.torch
+        f = t.as_tensor(fields, dtype=t.float64, device=self.device).reshape(-1, self.nstate).contiguous()
+        ids = None if env_ids is None else t.as_tensor(env_ids, dtype=t.int32, device=self.device).contiguous()
+        if ids is not None and ids.numel() != f.shape[0]:
+            raise ValueError("env_ids must have one entry per field row")
+        self._use_current_stream()
+        self._check(self._L.rbc2d_reset_from_fields_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
+                                                       C.c_void_p(f.data_ptr()), f.shape[0], int(project)))
+
+    def noise_reset(self, env_ids=None, kick: float = 0.01, generator=None):
+        """`initialize_model` (`rbc_sim2D.jl:163-171`) for many environments on the device: u, w = kick*randn,
+        b = clamp(min_b + (Lz - z) db/2 + kick*randn, min_b, min_b + db), walls impenetrable, then the `set!` projection."""
+        t = self.torch
+        n = self.B if env_ids is None else int(t.as_tensor(env_ids).numel())
+        nz, nx = self.nz, self.nx
+        z = (t.arange(nz, device=self.device, dtype=t.float64) + 0.5) * (2.0 / nz)
+        rn = lambda *shape: t.randn(shape, device=self.device, dtype=t.float64, generator=generator)
+        b = t.clamp(1.0 + (2.0 - z)[None, :, None] * 0.5 + kick * rn(n, nz, nx), 1.0, 2.0)
+        u = kick * rn(n, nz, nx)
+        w = kick * rn(n, nz + 1, nx)
+        w[:, 0] = 0.0
+        w[:, -1] = 0.0
+        self.reset_from_fields_dev(t.cat([b.reshape(n, -1), u.reshape(n, -1), w.reshape(n, -1)], dim=1), env_ids, project=True)
 
     # ------------------------------------------------------------------ step / observe
     def step(self, actions):

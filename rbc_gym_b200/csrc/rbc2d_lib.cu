@@ -452,6 +452,24 @@ int rbc2d_reset_from_fields_host(rbc2d_sim* s, const int32_t* env_ids_host, cons
     return rc;
 }
 
+int rbc2d_reset_from_fields_dev(rbc2d_sim* s, const int32_t* env_ids, const double* fields, int32_t n, int32_t project)
+{
+    if (!s || !fields || n < 1 || n > s->B) return fail("rbc2d_reset_from_fields_dev: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    dim3 grid(8, n < 4096 ? n : 4096);
+    if (s->cfg.precision == 32)
+        rbc2d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, fields, env_ids, n, s->t, s->step, s->trunc, s->nan, s->nstate);
+    else
+        rbc2d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, fields, env_ids, n, s->t, s->step, s->trunc, s->nan, s->nstate);
+    CK(cudaGetLastError());
+    s->launches += 1;
+    if (project || s->cfg.pressure) {
+        RunFlags F{0, 1, 0};
+        return dispatch_env(s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, env_ids, n, F, false);
+    }
+    return 0;
+}
+
 int rbc2d_step_dev(rbc2d_sim* s, const float* actions, float* obs, float* reward, double* nu_s, double* nu_o, int32_t* trunc,
                    int32_t* nan)
 {

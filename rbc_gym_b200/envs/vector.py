@@ -76,10 +76,10 @@ class RBCVectorEnv2D:
         if ids.numel() == 0:
             return
         if self.sim.n_episodes == 0:
-            from .rbc2d import noise_initial_fields
-            rng = np.random.default_rng([self.seed, int(self._episode.max().item())])
-            fields = np.concatenate([noise_initial_fields(rng, tuple(self.state_shape)) for _ in range(ids.numel())])
-            self.sim.reset_from_fields(fields, env_ids=ids.cpu().numpy(), project=True)
+            # noise initialisation drawn and projected on the device (a per-call generator keyed by seed and episode)
+            gen = t.Generator(device=self.device)
+            gen.manual_seed(self.seed * 1_000_003 + int(self._episode.max().item()))
+            self.sim.noise_reset(ids.to(t.int32), kick=0.01, generator=gen)
         else:
             idx = self._draw_checkpoints(ids) if ckpt_idx is None else t.as_tensor(ckpt_idx, dtype=t.int32, device=self.device)
             self.sim.reset_from_checkpoints(idx, env_ids=ids.to(t.int32))

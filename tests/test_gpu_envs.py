@@ -247,3 +247,28 @@ def test_full_episode_rollout_4096_envs_autoreset():
     ret = info["final_info"]["episode_return"].cpu().numpy()
     assert np.all(np.isfinite(ret)) and -300 * 12 < ret.min() and ret.max() < -300 * 2
     env.close()
+
+
+def test_device_noise_reset_matches_reference_initialisation():
+    """`Sim2D.noise_reset`: initialize_model (rbc_sim2D.jl:163-171) drawn on the device + the set! projection, no host trip."""
+    import torch
+    from rbc_gym_b200 import backend
+    sim = backend.Sim2D(64, ra=1e5, dt_action=0.3, precision=64)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    sim.noise_reset(kick=0.01, generator=gen)
+    b, u, w = backend.split_fields(sim.fields())
+    dx, dz = 2 * np.pi / 96, 2.0 / 64
+    div = (np.roll(u, -1, axis=-1) - u) / dx + (w[:, 1:] - w[:, :-1]) / dz
+    assert np.abs(div).max() < 1e-12 and np.all(w[:, 0] == 0) and np.all(w[:, -1] == 0)
+    z = (np.arange(64) + 0.5) * dz
+    resid = b - (1 + (2 - z)[None, :, None] / 2)
+    assert b.min() >= 1.0 and b.max() <= 2.0 and abs(resid[:, 2:-2].std() - 0.01) < 5e-4       # kick 0.01 away from the clamp
+    assert 0.004 < u.std() < 0.011 and not np.array_equal(b[0], b[1])
+    t, step = sim.info()
+    assert np.all(t == 0) and np.all(step == 1)
+    ids = torch.tensor([3, 9], dtype=torch.int32)
+    before = sim.fields()
+    sim.noise_reset(ids, kick=0.01, generator=gen)                       # partial reset leaves the others untouched
+    after = sim.fields()
+    assert not np.array_equal(after[3], before[3]) and np.array_equal(after[4], before[4])
+    sim.close()
