@@ -183,6 +183,7 @@ int rbc3d_state_values_per_env(const rbc3d_sim* sim);
 int rbc3d_load_checkpoints(rbc3d_sim* sim, const double* fields_host, int32_t n_episodes);
 int rbc3d_reset_from_checkpoints_dev(rbc3d_sim* sim, const int32_t* env_ids_dev, const int32_t* ckpt_idx_dev, int32_t n);
 int rbc3d_reset_from_fields_host(rbc3d_sim* sim, const int32_t* env_ids_host, const double* fields_host, int32_t n, int32_t project);
+int rbc3d_reset_from_fields_dev(rbc3d_sim* sim, const int32_t* env_ids_dev, const double* fields_dev, int32_t n, int32_t project);
 /* step_simulation + get_state + get_nusselt fused; obs may be NULL (skips the 262 KB/env observation write) */
 int rbc3d_step_dev(rbc3d_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, double* nusselt_dev,
                    int32_t* truncated_dev, int32_t* nan_dev);

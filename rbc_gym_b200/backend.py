@@ -70,7 +70,7 @@ ABI_SYMBOLS = (
     "rbc2d_get_state_dev", "rbc2d_get_state_host", "rbc2d_get_fields_host", "rbc2d_get_info_host",
     "rbc2d_launch_count", "rbc2d_last_step_kernel_ms", "rbc2d_set_wrappers", "rbc2d_get_cell_dist_host", "rbc2d_render_rgb_dev",
     "rbc3d_create", "rbc3d_destroy", "rbc3d_set_stream", "rbc3d_state_values_per_env", "rbc3d_load_checkpoints",
-    "rbc3d_reset_from_checkpoints_dev", "rbc3d_reset_from_fields_host", "rbc3d_step_dev", "rbc3d_step_host",
+    "rbc3d_reset_from_checkpoints_dev", "rbc3d_reset_from_fields_host", "rbc3d_reset_from_fields_dev", "rbc3d_step_dev", "rbc3d_step_host",
     "rbc3d_observe_dev", "rbc3d_get_fields_host", "rbc3d_get_info_host", "rbc3d_launch_count", "rbc3d_last_step_kernel_ms",
 )
 
@@ -133,6 +133,7 @@ def load_library(build_if_missing: bool = True):
     L.rbc3d_load_checkpoints.argtypes = [vp, vp, ip]
     L.rbc3d_reset_from_checkpoints_dev.argtypes = [vp, vp, vp, ip]
     L.rbc3d_reset_from_fields_host.argtypes = [vp, vp, vp, ip, ip]
+    L.rbc3d_reset_from_fields_dev.argtypes = [vp, vp, vp, ip, ip]
     L.rbc3d_step_dev.argtypes = [vp] * 7
     L.rbc3d_step_host.argtypes = [vp] * 7
     L.rbc3d_observe_dev.argtypes = [vp] * 3
@@ -500,6 +501,24 @@ class Sim3D:
         ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
         self._use_current_stream()
         self._check(self._L.rbc3d_reset_from_fields_host(self._h, _np_ptr(ids), _np_ptr(f), f.shape[0], int(project)))
+
+    def noise_reset(self, env_ids=None, kick: float = 0.01, generator=None):
+        """`initialize_model` (`rbc_sim3D.jl:169-178`) drawn and projected on the device for all or the listed environments."""
+        t = self.torch
+        ids = None if env_ids is None else t.as_tensor(env_ids, dtype=t.int32, device=self.device).contiguous()
+        n = self.B if ids is None else int(ids.numel())
+        nz, ny, nx = self.state_shape
+        lz, b0, db = float(self.cfg.lz), float(self.cfg.b_min), float(self.cfg.b_max - self.cfg.b_min)
+        z = (t.arange(nz, device=self.device, dtype=t.float64) + 0.5) * (lz / nz)
+        rn = lambda *shape: t.randn(shape, device=self.device, dtype=t.float64, generator=generator)
+        b = t.clamp(b0 + (lz - z)[None, :, None, None] * db / 2 + kick * rn(n, nz, ny, nx), b0, b0 + db)
+        u, v, w = kick * rn(n, nz, ny, nx), kick * rn(n, nz, ny, nx), kick * rn(n, nz + 1, ny, nx)
+        w[:, 0] = 0.0
+        w[:, -1] = 0.0
+        f = t.cat([x.reshape(n, -1) for x in (b, u, v, w)], dim=1).contiguous()
+        self._use_current_stream()
+        self._check(self._L.rbc3d_reset_from_fields_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
+                                                       C.c_void_p(f.data_ptr()), n, 1))
 
     def step(self, actions, want_obs: bool = True):
         """actions `[B, heaters, heaters]` float32 CUDA tensor -> (obs, reward, nusselt, truncated, nan)."""

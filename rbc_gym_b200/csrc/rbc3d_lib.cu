@@ -275,6 +275,18 @@ int rbc3d_reset_from_fields_host(rbc3d_sim* s, const int32_t* env_ids_host, cons
     return rc;
 }
 
+int rbc3d_reset_from_fields_dev(rbc3d_sim* s, const int32_t* env_ids, const double* fields, int32_t n, int32_t project)
+{
+    if (!s || !fields || n < 1 || n > s->B) return rbc_fail("rbc3d_reset_from_fields_dev: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    int rc = set_fields3(s, fields, env_ids, nullptr, n, n);
+    if (!rc && project) {
+        RunFlags3 F{0, 1, 0};
+        rc = dispatch3(s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, env_ids, n, F, false, false);
+    }
+    return rc;
+}
+
 int rbc3d_step_dev(rbc3d_sim* s, const float* actions, float* obs, float* reward, double* nusselt, int32_t* trunc, int32_t* nan)
 {
     if (!s || !actions) return rbc_fail("rbc3d_step_dev: bad argument");

@@ -196,12 +196,9 @@ class RBCVectorEnv3D:
         if ids.numel() == 0:
             return
         if self.sim.n_episodes == 0:
-            from .rbc3d import noise_initial_fields_3d
-            rng = np.random.default_rng([self.seed, int(self._episode.max().item())])
-            T = self.temperature_difference
-            fields = np.concatenate([noise_initial_fields_3d(rng, self.state_shape, min_b=T[0], delta_b=T[1] - T[0], lz=float(self.domain[0]))
-                                     for _ in range(ids.numel())])
-            self.sim.reset_from_fields(fields, env_ids=ids.cpu().numpy(), project=True)
+            gen = t.Generator(device=self.device)
+            gen.manual_seed(self.seed * 1_000_003 + int(self._episode.max().item()))
+            self.sim.noise_reset(ids.to(t.int32), kick=0.01, generator=gen)
         else:
             idx = self._draw_checkpoints(ids) if ckpt_idx is None else t.as_tensor(ckpt_idx, dtype=t.int32, device=self.device)
             self.sim.reset_from_checkpoints(idx, env_ids=ids.to(t.int32))
