@@ -146,6 +146,9 @@ int rbc2d_launch_count(const rbc2d_sim* sim, int64_t* launches, int32_t* grid, i
 /* Device time of the most recent step kernel in milliseconds (CUDA events on the handle's stream;
  * synchronises). */
 int rbc2d_last_step_kernel_ms(rbc2d_sim* sim, float* ms);
+/* Device times of the last n step kernels (n <= 64), oldest first, from the same per-launch CUDA events; returns the number
+ * written (<= n) or <0.  Lets a benchmark average over every launch of its timed region without synchronising inside it. */
+int rbc2d_step_kernel_ms_history(rbc2d_sim* sim, float* ms_out, int32_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * 3D environment (rbc_gym/RayleighBenardConvection3D-v0): replaces the juliacall functions of

@@ -68,7 +68,7 @@ ABI_SYMBOLS = (
     "rbc2d_state_values_per_env", "rbc2d_load_checkpoints", "rbc2d_reset_from_checkpoints_dev",
     "rbc2d_reset_from_fields_host", "rbc2d_reset_from_fields_dev", "rbc2d_step_dev", "rbc2d_step_host", "rbc2d_observe_dev", "rbc2d_observe_host",
     "rbc2d_get_state_dev", "rbc2d_get_state_host", "rbc2d_get_fields_host", "rbc2d_get_info_host",
-    "rbc2d_launch_count", "rbc2d_last_step_kernel_ms", "rbc2d_set_wrappers", "rbc2d_get_cell_dist_host", "rbc2d_render_rgb_dev",
+    "rbc2d_launch_count", "rbc2d_last_step_kernel_ms", "rbc2d_step_kernel_ms_history", "rbc2d_set_wrappers", "rbc2d_get_cell_dist_host", "rbc2d_render_rgb_dev",
     "rbc3d_create", "rbc3d_destroy", "rbc3d_set_stream", "rbc3d_state_values_per_env", "rbc3d_load_checkpoints",
     "rbc3d_reset_from_checkpoints_dev", "rbc3d_reset_from_fields_host", "rbc3d_reset_from_fields_dev", "rbc3d_step_dev", "rbc3d_step_host",
     "rbc3d_observe_dev", "rbc3d_get_fields_host", "rbc3d_get_info_host", "rbc3d_launch_count", "rbc3d_last_step_kernel_ms",
@@ -126,6 +126,7 @@ def load_library(build_if_missing: bool = True):
     L.rbc2d_render_rgb_dev.argtypes = [vp, vp]
     L.rbc2d_launch_count.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ip), C.POINTER(ip)]
     L.rbc2d_last_step_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.rbc2d_step_kernel_ms_history.argtypes = [vp, C.POINTER(C.c_float), ip]
     L.rbc3d_create.argtypes = [C.POINTER(Rbc3dConfig), C.POINTER(vp)]
     L.rbc3d_destroy.argtypes = [vp]
     L.rbc3d_set_stream.argtypes = [vp, vp]
@@ -397,6 +398,14 @@ class Sim2D:
         ms = C.c_float()
         self._check(self._L.rbc2d_last_step_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def step_kernel_ms_history(self, n: int):
+        """Device times (ms) of the last `n` step kernels (n <= 64), oldest first, from the library's per-launch CUDA events."""
+        buf = (C.c_float * n)()
+        got = self._L.rbc2d_step_kernel_ms_history(self._h, buf, n)
+        if got < 0:
+            self._check(got)
+        return [buf[i] for i in range(got)]
 
 
 def split_fields(fields: np.ndarray, shape=(NZ, NX)):

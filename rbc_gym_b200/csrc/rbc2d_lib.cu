@@ -175,8 +175,11 @@ struct rbc2d_sim {
     int *step = nullptr, *trunc = nullptr, *nan = nullptr;
     float *obs = nullptr, *reward = nullptr, *actions = nullptr;
     int64_t launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timed = false;
+    // CUDA events around the step kernel on the launch stream: a ring of the last kRing step launches, so that a
+    // benchmark can read every launch of its timed region afterwards without synchronising inside it
+    static constexpr int kRing = 64;
+    cudaEvent_t ev0[kRing] = {}, ev1[kRing] = {};
+    int64_t timed_launches = 0;
 };
 
 template <typename Real>
@@ -230,10 +233,11 @@ static int launch_env(rbc2d_sim* s, const float* actions, float* obs, float* rew
     io.cell_dist = s->wr.shaping ? s->cell_dist : nullptr;   // the peak scan runs only when reward shaping is on
     const int grid = n < s->grid ? n : s->grid;
     if (grid <= 0) return 0;
-    if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
+    const int slot = (int)(s->timed_launches % rbc2d_sim::kRing);
+    if (time_it) CK(cudaEventRecord(s->ev0[slot], s->stream));
     rbc2d_env_kernel<Real, SPLIT><<<grid, NT, s->smem, s->stream>>>(C, T, io, (Real*)s->gm, (Real*)s->nxt, env_ids, n, F);
     CK(cudaGetLastError());
-    if (time_it) { CK(cudaEventRecord(s->ev1, s->stream)); s->timed = true; }
+    if (time_it) { CK(cudaEventRecord(s->ev1[slot], s->stream)); s->timed_launches += 1; }
     s->launches += 1;
     return 0;
 }
@@ -256,10 +260,11 @@ static int dispatch_env(rbc2d_sim* s, const float* actions, float* obs, float* r
         io.nan_flag = nan ? nan : s->nan;
         io.cell_dist = s->wr.shaping ? s->cell_dist : nullptr;
         if (n <= 0) return 0;
-        if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
+        const int slot = (int)(s->timed_launches % rbc2d_sim::kRing);
+        if (time_it) CK(cudaEventRecord(s->ev0[slot], s->stream));
         int rc = rbc2dx_api::launch(s->plan, s->hc, s->wr, io, env_ids, n, F, s->stream);
         if (rc) return rc;
-        if (time_it) { CK(cudaEventRecord(s->ev1, s->stream)); s->timed = true; }
+        if (time_it) { CK(cudaEventRecord(s->ev1[slot], s->stream)); s->timed_launches += 1; }
         s->launches += 1;
         return 0;
     }
@@ -351,10 +356,11 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
     ALLOC(s->actions, B * (size_t)cfg->heaters * sizeof(float));
     ALLOC(s->cell_dist, B * sizeof(double));
 #undef ALLOC
-    if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
-        rbc2d_destroy(s);
-        return fail("cudaEventCreate failed");
-    }
+    for (int i = 0; i < rbc2d_sim::kRing; ++i)
+        if (cudaEventCreate(&s->ev0[i]) != cudaSuccess || cudaEventCreate(&s->ev1[i]) != cudaSuccess) {
+            rbc2d_destroy(s);
+            return fail("cudaEventCreate failed");
+        }
     *out = s;
     return 0;
 }
@@ -366,8 +372,10 @@ int rbc2d_destroy(rbc2d_sim* s)
     void* ptrs[] = {s->state, s->gm, s->nxt, s->pressure, s->tinv, s->tw48, s->tw96, s->bank, s->t, s->nu_s, s->nu_o,
                     s->step, s->trunc, s->nan, s->obs, s->reward, s->actions, s->cell_dist};
     for (void* p : ptrs) if (p) cudaFree(p);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
+    for (int i = 0; i < rbc2d_sim::kRing; ++i) {
+        if (s->ev0[i]) cudaEventDestroy(s->ev0[i]);
+        if (s->ev1[i]) cudaEventDestroy(s->ev1[i]);
+    }
     rbc2dx_api::destroy(s->plan);
     delete s;
     return 0;
@@ -635,11 +643,22 @@ int rbc2d_launch_count(const rbc2d_sim* s, int64_t* launches, int32_t* grid, int
 int rbc2d_last_step_kernel_ms(rbc2d_sim* s, float* ms)
 {
     if (!s || !ms) return fail("rbc2d_last_step_kernel_ms: bad argument");
-    if (!s->timed) return fail("rbc2d_last_step_kernel_ms: no step has been launched");
+    return rbc2d_step_kernel_ms_history(s, ms, 1) == 1 ? 0 : -1;
+}
+
+int rbc2d_step_kernel_ms_history(rbc2d_sim* s, float* ms, int32_t n)
+{
+    if (!s || !ms || n < 1) return fail("rbc2d_step_kernel_ms_history: bad argument");
+    if (s->timed_launches < 1) return fail("rbc2d_step_kernel_ms_history: no step has been launched");
     CK(cudaSetDevice(s->cfg.device));
-    CK(cudaEventSynchronize(s->ev1));
-    CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
-    return 0;
+    int64_t have = s->timed_launches < rbc2d_sim::kRing ? s->timed_launches : rbc2d_sim::kRing;
+    if (n > have) n = (int32_t)have;
+    for (int32_t i = 0; i < n; ++i) {                      // oldest of the requested launches first
+        const int slot = (int)((s->timed_launches - n + i) % rbc2d_sim::kRing);
+        CK(cudaEventSynchronize(s->ev1[slot]));
+        CK(cudaEventElapsedTime(&ms[i], s->ev0[slot], s->ev1[slot]));
+    }
+    return n;
 }
 
 }  // extern "C"
