@@ -16,7 +16,12 @@
  * PARITY PIN: the reference's 3D checkpoint files are missing from the mount (.MISSING_LARGE_BLOBS), so this
  * oracle is pinned (tests/test_oracle3d.py) to the fixture-pinned 2D oracle: a y-invariant state (v = 0) must
  * evolve exactly like the 2D oracle, and so must its x<->y transposed twin (which exercises every y-direction
- * code path); plus exact known answers (conduction state, Nu = 1, heater patches).  Against Julia: UNPINNED.
+ * code path); plus exact known answers (conduction state, Nu = 1, heater patches).  Against Julia output the pin
+ * is statistical: run with the protocol and resolution of the reference's experiments/flowstats/flowstats_ra.py
+ * (64 x 64 x 32) it reproduces the Julia-produced Nusselt series of flowstats_ra.pkl — linear growth rates within
+ * 2 %, first-burst time and height, saturated means within one standard deviation at Ra = 500, 4000, 16000
+ * (tools/oracle3d_flowstats.py, tests/golden/oracle3d_flowstats_64x64x32.json, tests/test_oracle3d_flowstats.py).
+ * Field-by-field against Julia: UNPINNED (no 3D fields from the reference are available).
  *
  * Layout (C order, x fastest):  b,u,v: [nz][ny][nx];  w: [nz+1][ny][nx].
  *   u(i,j,k) x-face left of cell i;  v(i,j,k) y-face "south" of cell j;  w(i,j,k) z-face below cell k.
