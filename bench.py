@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=18.0, help="CPU work of the cpu_baseline sample")
     ap.add_argument("--no-secondary", action="store_true", help="skip the config 3 / config 4 side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
