@@ -124,7 +124,6 @@ def secondary_configs(device: int):
     import torch
     from rbc_gym_b200 import backend
     from rbc_gym_b200.envs import noise_initial_fields_3d
-    from rbc_gym_b200.envs.rbc2d import noise_initial_fields
     out = {}
     peak, _ = hbm_peak()
 
@@ -140,9 +139,9 @@ def secondary_configs(device: int):
     try:
         B3 = 1056
         sim = backend.Sim2D(B3, ra=1e6, dt_action=1.0, dt_solver=0.015, state_shape=(128, 192), precision=32, device=device)
-        rng = np.random.default_rng(42)
-        base = np.concatenate([noise_initial_fields(rng, (128, 192), kick=0.01) for _ in range(8)])
-        sim.reset_from_fields(np.tile(base, (B3 // 8, 1)), project=True)
+        from rbc_gym_b200.checkpoints import developed_states_2d
+        base = developed_states_2d(16, 1e6, (128, 192), dt_solver=0.015, spin_up=40, device=device)   # fp64 spin-up, ~1 s
+        sim.reset_from_fields(np.tile(base, (B3 // 16, 1)), project=False)
         a = torch.rand((B3, 12), device=f"cuda:{device}") * 2 - 1
         ms = timed(lambda: sim.step(a))
         alg = sim.nsub * 10 * sim.nstate * 4

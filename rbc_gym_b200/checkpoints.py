@@ -81,3 +81,29 @@ def simulate_3d_rb(directory, seed: int = 42, random_inits: int = 20, ra: float 
     path = directory / f"3D_ckpt_ra{ra_tag}.h5"
     write_checkpoint_3d(path, b, u, v, w, start_seed=seed)
     return path, stats
+
+
+def developed_states_2d(n_states: int, ra: float, state_shape=(64, 96), dt_solver: float = 0.03, spin_up: float = 40.0, seed: int = 42,
+                        device: int = 0) -> np.ndarray:
+    """`n_states` statistically developed flows `[n, nstate]` (float64) for grids without shipped checkpoints: noise
+    initialisation + `spin_up` time units of zero-action evolution in the fp64 validation mode.
+
+    fp64 on purpose: from the conduction state the first plumes overshoot (at Ra = 1e6 on 192 x 128: Nu > 100, max|w| ~ 1.7,
+    i.e. CFL ~ 1.6 at dt_solver = 0.015), and at CFL > 1.5 the RK3 / 5th-order-upwind scheme amplifies grid-scale round-off by
+    ~1.5x per step for a few dozen steps.  A 1e-16 seed survives that burst (as in the reference, which is fp64), a 1e-7 seed
+    does not always (1 fp32 environment in ~1000 ends with the NaN flag set); developed flows have max|w| ~ 1.1."""
+    import torch
+
+    shape = (int(state_shape[0]), int(state_shape[1]))
+    sim = backend.Sim2D(int(n_states), ra=float(ra), dt_action=1.0, dt_solver=dt_solver, episode_length=1e30, precision=64,
+                        device=device, state_shape=shape)
+    gen = torch.Generator(device=sim.device).manual_seed(seed)
+    sim.noise_reset(kick=0.01, generator=gen)
+    zero = torch.zeros((sim.B, sim.heaters), device=sim.device)
+    for _ in range(int(round(spin_up))):
+        *_, nan = sim.step(zero)
+    if bool(nan.any()):
+        raise RuntimeError("[ERROR] NaN values found!")
+    f = sim.fields()
+    sim.close()
+    return f

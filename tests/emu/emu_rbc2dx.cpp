@@ -78,12 +78,16 @@ extern "C" int emu_rbc2dx_step(const HostConfig* h, const HostWrappers* wp, doub
     using G96_4 = Grid<96, 64, 4, 4>;
     using G192_4 = Grid<192, 128, 4, 2>;
     using G192_8 = Grid<192, 128, 8, 2>;
+    using G192_1 = Grid<192, 128, 1, 2>;          // host-only: the whole grid in one "CTA" (plain two-sided Thomas, no SPIKE)
+    using G192_2 = Grid<192, 128, 2, 2>;
     using G128_2 = Grid<128, 64, 2, 2, 4>;
     if (nx == 96 && nz == 64 && cl == 1) DISPATCH(G96_1);
     if (nx == 96 && nz == 64 && cl == 2) DISPATCH(G96_2);
     if (nx == 96 && nz == 64 && cl == 4) DISPATCH(G96_4);
     if (nx == 192 && nz == 128 && cl == 4) DISPATCH(G192_4);
     if (nx == 192 && nz == 128 && cl == 8) DISPATCH(G192_8);
+    if (nx == 192 && nz == 128 && cl == 1) DISPATCH(G192_1);
+    if (nx == 192 && nz == 128 && cl == 2) DISPATCH(G192_2);
     if (nx == 128 && nz == 64 && cl == 2) DISPATCH(G128_2);
     return -2;
 }
