@@ -27,11 +27,14 @@ class RBCVectorEnv2D:
     def __init__(self, num_envs: int, rayleigh_number: float = 10_000, episode_length: float = 300, observation_shape=(8, 48),
                  state_shape=(64, 96), heater_segments: int = 12, heater_limit: float = 0.75, heater_duration: float = 1.5,
                  pressure: bool = False, checkpoint: Optional[str] = None, dt_solver: float = 0.03, precision: int = 32,
-                 device: int = 0, autoreset_mode: str = "next_step", seed: int = 0, env_id_offset: int = 0):
+                 device: int = 0, autoreset_mode: str = "next_step", seed: int = 0, env_id_offset: int = 0, nan_policy: str = "raise"):
         import torch
 
         if autoreset_mode not in ("next_step", "same_step", "disabled"):
             raise ValueError("autoreset_mode must be next_step, same_step or disabled")
+        if nan_policy not in ("raise", "reset"):
+            raise ValueError("nan_policy must be raise or reset")
+        self.nan_policy = nan_policy      # "raise": the reference's RuntimeError; "reset": re-initialise only the failed envs
         self.torch = torch
         self.num_envs = int(num_envs)
         self.ra = rayleigh_number
@@ -108,11 +111,23 @@ class RBCVectorEnv2D:
         have_pending = self.autoreset_mode == "next_step" and bool(pend.any())
         obs, rew, nus, nuo, trunc, nan = self.sim.step(actions)
         bad = nan.to(t.bool) & ~pend if have_pending else nan.to(t.bool)
-        if bool(bad.any()):
-            raise RuntimeError("Error in simulation step, probably NaN values")   # rbc2D.py:170-171
         truncated = trunc.to(t.bool)
         reward = rew
         info = self._info(nus, nuo)
+        already_reset = None
+        if bool(bad.any()):
+            if self.nan_policy == "raise":
+                raise RuntimeError("Error in simulation step, probably NaN values")   # rbc2D.py:170-171
+            # a batch of thousands should not die with one environment: re-initialise the failed ones, zero their reward,
+            # report them as truncated and in info["nan_reset"]
+            self._reset_envs(bad.nonzero().flatten())
+            obs, nus, nuo = self.sim.observe()
+            info = self._info(nus, nuo)
+            reward = rew.clone()
+            reward[bad] = 0
+            truncated = truncated | bad
+            info["nan_reset"] = bad
+            already_reset = bad
         if have_pending:
             # gymnasium NEXT_STEP semantics: for an env that truncated on the previous call this call only resets
             # it — the action is ignored, reward 0, and the returned observation is the reset observation.
@@ -121,17 +136,22 @@ class RBCVectorEnv2D:
             obs, nus, nuo = self.sim.observe()
             reward = rew.clone()
             reward[pend] = 0
+            if already_reset is not None:
+                reward[already_reset] = 0
             truncated = truncated & ~pend
         self.episode_return += reward.to(t.float64)
-        if self.autoreset_mode == "same_step" and bool(truncated.any()):
+        to_reset = truncated if already_reset is None else truncated & ~already_reset
+        if self.autoreset_mode == "same_step" and bool(to_reset.any()):
             # SB3 semantics: reset inside the truncating step; terminal observation kept in info["final_obs"]
-            ids = truncated.nonzero().flatten()
+            ids = to_reset.nonzero().flatten()
             info["final_obs"] = obs.clone()
             info["final_info"] = {"nusselt_state": nus.clone(), "nusselt_obs": nuo.clone(),
                                   "episode_return": self.episode_return.clone()}
             self._reset_envs(ids)
             obs, _, _ = self.sim.observe()
         self._pending = truncated.clone() if self.autoreset_mode == "next_step" else t.zeros_like(truncated)
+        if already_reset is not None:
+            self._pending &= ~already_reset
         terminated = t.zeros_like(truncated)
         return obs, reward, terminated, truncated, info
 

@@ -272,3 +272,37 @@ def test_device_noise_reset_matches_reference_initialisation():
     after = sim.fields()
     assert not np.array_equal(after[3], before[3]) and np.array_equal(after[4], before[4])
     sim.close()
+
+
+@pytest.mark.parametrize("mode", ["next_step", "same_step"])
+def test_vector_env_nan_policy(mode):
+    """One failed environment: nan_policy="raise" is the reference's RuntimeError; "reset" re-initialises only that env,
+    reports it (truncated + info["nan_reset"], reward 0) and the rest of the batch carries on."""
+    import torch
+    from rbc_gym_b200 import backend
+    from rbc_gym_b200.envs import RBCVectorEnv2D
+
+    def poison(env, e):
+        f = env.sim.fields()
+        f[e, 1000] = np.nan
+        env.sim.reset_from_fields(f[e:e + 1], env_ids=[e], project=False)
+
+    env = RBCVectorEnv2D(6, rayleigh_number=100_000, heater_duration=0.15, checkpoint=CKPT, autoreset_mode=mode, nan_policy="raise")
+    env.reset(seed=0)
+    poison(env, 2)
+    with pytest.raises(RuntimeError, match="probably NaN"):
+        env.step(torch.zeros((6, 12), device="cuda"))
+    env.close()
+    env = RBCVectorEnv2D(6, rayleigh_number=100_000, heater_duration=0.15, checkpoint=CKPT, autoreset_mode=mode, nan_policy="reset")
+    env.reset(seed=0)
+    poison(env, 2)
+    obs, rew, term, trunc, info = env.step(torch.zeros((6, 12), device="cuda"))
+    assert info["nan_reset"].tolist() == [False, False, True, False, False, False]
+    assert trunc.tolist() == [False, False, True, False, False, False] and rew[2].item() == 0 and torch.isfinite(obs).all()
+    t, step = env.sim.info()
+    assert t[2] == 0.0 and step[2] == 1 and np.all(np.delete(t, 2) == pytest.approx(0.15))
+    obs, rew, term, trunc, info = env.step(torch.zeros((6, 12), device="cuda"))        # everybody steps normally again
+    assert not trunc.any() and "nan_reset" not in info and torch.isfinite(rew).all() and (rew != 0).all()
+    t, step = env.sim.info()
+    assert t[2] == pytest.approx(0.15) and t[0] == pytest.approx(0.30)
+    env.close()
