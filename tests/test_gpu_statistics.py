@@ -69,3 +69,29 @@ def test_ra1e6_long_time_average_within_ensemble_error():
     se = 6.534 / np.sqrt(20)
     assert abs(means[32] - 14.615) < 2 * se, means
     assert abs(means[32] - means[64]) < 1.0, means
+
+
+def test_config3_fp32_long_time_average_matches_fp64_and_the_coarse_grid_ensemble():
+    """Config 3 (192 x 128, Ra = 1e6): 32 developed flows advanced for 60 time units with zero action in fp32 and in fp64.
+    The time-averaged Nusselt numbers of the two arithmetic modes must agree within the sampling error, and sit near the
+    reference's 96 x 64 ensemble at the same Ra (14.6 +- 6.5 over 20 states) — the doubled resolution changes the mean a little."""
+    import torch
+    from rbc_gym_b200 import backend
+    from rbc_gym_b200.checkpoints import developed_states_2d
+    base = developed_states_2d(32, 1e6, (128, 192), dt_solver=0.015, spin_up=40, seed=7)
+    means, stds = {}, {}
+    for p in (32, 64):
+        sim = backend.Sim2D(32, ra=1e6, dt_action=1.0, dt_solver=0.015, state_shape=(128, 192), precision=p)
+        sim.reset_from_fields(base, project=False)
+        zero = torch.zeros((32, 12), device="cuda")
+        acc = []
+        for _ in range(60):
+            _, _, nus, _, _, nan = sim.step(zero)
+            acc.append(nus.cpu().numpy().copy())
+        assert not nan.any().item()
+        acc = np.array(acc)
+        means[p], stds[p] = float(acc.mean()), float(acc.mean(axis=0).std())
+        sim.close()
+    se = max(stds.values()) / np.sqrt(32)
+    assert abs(means[32] - means[64]) < 4 * se + 0.3, (means, stds)
+    assert 9.0 < means[32] < 21.0, means
