@@ -1000,22 +1000,26 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
             }
         }
     )
-    if (io.pressure != nullptr && (F.nsub > 0 || F.project_first)) {
+    if (io.pressure != nullptr) {
         // pressure channels of get_state (rbc_sim2D_api.jl:114-115): pHY' from the final b (as the
-        // last update_state! leaves it) and pNHS = phi / dtau of the last stage, zero-mean gauge.
+        // last update_state! leaves it) and pNHS = phi / dtau of the last stage, zero-mean gauge.  They are refreshed
+        // whenever the state changed (step, or the set! projection of a reset) and kept per environment, so that an
+        // observe-only launch (what reset() returns) emits the channels from the stored fields.
         Real* pr = io.pressure + (size_t)env * 2 * NCELL;
-        RBC_PHASE(
-            double acc = 0;
-            for (int q = tid; q < NCELL; q += NT) acc += (double)X.R[(q / NX) * RSTR + (q % NX)];
-            red[tid] = acc;
-        )
-        RBC_PHASE(if (tid == 0) fin[11] = sum_serial(red, NT) / (double)NCELL;)
-        RBC_PHASE(
-            for (int q = tid; q < NCELL; q += NT)
-                pr[NCELL + q] = (Real)(((double)X.R[(q / NX) * RSTR + (q % NX)] - fin[11]) / (double)last_dtau);
-        )
-        RBC_PHASE(phase_phy(tid, C, cur + OFF_B, X.R);)
-        RBC_PHASE(for (int q = tid; q < NCELL; q += NT) pr[q] = X.R[(q / NX) * RSTR + (q % NX)];)
+        if (F.nsub > 0 || F.project_first) {
+            RBC_PHASE(
+                double acc = 0;
+                for (int q = tid; q < NCELL; q += NT) acc += (double)X.R[(q / NX) * RSTR + (q % NX)];
+                red[tid] = acc;
+            )
+            RBC_PHASE(if (tid == 0) fin[11] = sum_serial(red, NT) / (double)NCELL;)
+            RBC_PHASE(
+                for (int q = tid; q < NCELL; q += NT)
+                    pr[NCELL + q] = (Real)(((double)X.R[(q / NX) * RSTR + (q % NX)] - fin[11]) / (double)last_dtau);
+            )
+            RBC_PHASE(phase_phy(tid, C, cur + OFF_B, X.R);)
+            RBC_PHASE(for (int q = tid; q < NCELL; q += NT) pr[q] = X.R[(q / NX) * RSTR + (q % NX)];)
+        }
         if (C.channels == 5) {
             RBC_PHASE(
                 float* ob = io.obs + (size_t)env * C.channels * nobs;
