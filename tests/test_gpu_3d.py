@@ -160,3 +160,33 @@ def test_3d_flowstats_protocol_reproduces_julia_series_at_ra500():
         assert nus[:60, e].max() == pytest.approx(1.417, rel=0.02)
         assert nus[50:, e].mean() == pytest.approx(1.4035, abs=0.02)
     sim.close()
+
+
+def test_sb3_vecenv_facade_over_the_3d_batch():
+    """What `experiments/run_sarl.py:130-153` builds (SubprocVecEnv of Monitor + RBCNormalizeObservation 3D envs), as one
+    on-device batch behind the SB3 VecEnv contract: numpy in/out, reset inside the truncating step, terminal_observation,
+    TimeLimit.truncated, Monitor's episode record, the `nusselt` key NusseltCallback reads."""
+    from rbc_gym_b200 import wrappers as W
+    from rbc_gym_b200.envs import RBCSB3VecEnv, RBCVectorEnv3D
+    venv = RBCVectorEnv3D(4, rayleigh_number=2500, heater_duration=0.125, episode_length=1.0, autoreset_mode="same_step", seed=1)
+    env = RBCSB3VecEnv(venv)
+    assert env.num_envs == 4 and env.observation_space.shape == (4, 16, 32, 32) and env.action_space.shape == (8, 8)
+    assert float(env.observation_space.high.max()) == pytest.approx(1.3)
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (4, 4, 16, 32, 32) and obs.dtype == np.float32
+    raw = venv.sim.obs.cpu().numpy()
+    ref = W.normalize_observation(raw[0].copy(), 0.9, u_limit=W.RBCNormalizeObservation._get_u_limit_3d(2500))
+    np.testing.assert_allclose(obs[0], ref, rtol=1e-5, atol=1e-6)
+    acts = np.random.default_rng(0).uniform(-1, 1, (4, 8, 8)).astype(np.float32)
+    obs, rew, dones, infos = env.step(acts)
+    assert rew.shape == (4,) and not dones.any() and set(infos[0]) == {"nusselt", "t", "step"} and infos[0]["nusselt"] == pytest.approx(-rew[0], rel=1e-5)
+    ret = rew.astype(np.float64).copy()
+    env.step_async(acts)
+    obs, rew, dones, infos = env.step_wait()                               # t = 1.0 >= episode_length
+    ret += rew
+    assert dones.all() and all(i["TimeLimit.truncated"] for i in infos)
+    assert infos[2]["terminal_observation"].shape == (4, 16, 32, 32) and not np.array_equal(infos[2]["terminal_observation"], obs[2])
+    assert infos[1]["episode"]["l"] == 2 and infos[1]["episode"]["r"] == pytest.approx(ret[1], rel=1e-5)
+    assert all(i["t"] == 0.0 and i["step"] == 1 for i in infos)            # already reset: the returned obs is the reset observation
+    assert env.get_attr("ra") == [2500] * 4 and env.env_is_wrapped(object) == [False] * 4
+    env.close()
