@@ -162,10 +162,15 @@ static int create_impl(Plan* p, const char* name)
     return 0;
 }
 
-static bool force_cluster()
+// RBC_B200_CLUSTER=1: 96 x 64 through the 2-CTA cluster kernel; =0c1: through the same generic code as a single CTA
+// (cluster size 1) — both for cross-validation and for measuring what the generic code costs against the dedicated kernel
+static int force_cluster()
 {
     const char* e = std::getenv("RBC_B200_CLUSTER");
-    return e && e[0] == '1';
+    if (!e) return 0;
+    if (e[0] == '1') return 2;
+    if (e[0] == 'g') return 1;
+    return 0;
 }
 
 int supported(int nx, int nz)
@@ -191,6 +196,9 @@ int create(int nx, int nz, int precision, int device, double lx, double lz, Plan
         // a power-of-two width: 64-point complex FFT = 4 x 16; 2 CTAs x 32 rows, 256 threads = 128 columns x 2 strips
         if (precision == 32) rc = create_impl<Grid<128, 64, 2, 2, 4>, float, false>(p, "rbc2dx_env_kernel<128x64,cl2,f32>");
         else rc = create_impl<Grid<128, 64, 2, 2, 4>, double, true>(p, "rbc2dx_env_kernel<128x64,cl2,f64>");
+    } else if (nx == 96 && nz == 64 && force_cluster() == 1) {
+        if (precision == 32) rc = create_impl<Grid<96, 64, 1, 4>, float, false>(p, "rbc2dx_env_kernel<96x64,cl1,f32>");
+        else rc = rbc_fail("rbc2dx: the single-CTA generic variant is built for fp32 only");
     } else if (nx == 96 && nz == 64) {
         if (precision == 32) rc = create_impl<Grid<96, 64, 2, 4>, float, false>(p, "rbc2dx_env_kernel<96x64,cl2,f32>");
         else rc = create_impl<Grid<96, 64, 2, 4>, double, true>(p, "rbc2dx_env_kernel<96x64,cl2,f64>");

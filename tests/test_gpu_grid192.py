@@ -126,14 +126,15 @@ def test_unregistered_grid_and_pressure_are_rejected(B):
         B.Sim2D(1, ra=1e5, state_shape=(NZ, NX), pressure=True)
 
 
-@pytest.mark.parametrize("precision,tol", [(64, 1e-12), (32, 2e-6)])
-def test_cluster_kernel_on_96x64_agrees_with_dedicated_kernel(B, ckpt_ra1e5, precision, tol):
-    """RBC_B200_CLUSTER=1 routes the 96 x 64 grid through the 2-CTA cluster kernel: same results as the one-CTA kernel."""
+@pytest.mark.parametrize("precision,tol,flag,ctas", [(64, 1e-12, "1", 8), (32, 2e-6, "1", 8), (32, 2e-6, "g", 4)])
+def test_cluster_kernel_on_96x64_agrees_with_dedicated_kernel(B, ckpt_ra1e5, precision, tol, flag, ctas):
+    """RBC_B200_CLUSTER=1 routes the 96 x 64 grid through the 2-CTA cluster kernel, =g through the same generic code as one
+    CTA per environment: same results as the dedicated one-CTA kernel."""
     import torch
     c = ckpt_ra1e5
     acts = np.random.default_rng(3).uniform(-1, 1, (4, 12)).astype(np.float32)
     out = []
-    for flag in ("0", "1"):
+    for flag in ("0", flag):
         os.environ["RBC_B200_CLUSTER"] = flag
         try:
             sim = B.Sim2D(4, ra=1e5, dt_action=0.3, precision=precision)
@@ -144,7 +145,7 @@ def test_cluster_kernel_on_96x64_agrees_with_dedicated_kernel(B, ckpt_ra1e5, pre
         _, rew, nus, nuo, *_ = sim.step(torch.from_numpy(acts).cuda())
         out.append((sim.fields(), nus.cpu().numpy(), nuo.cpu().numpy(), sim.launch_info()["grid"]))
         sim.close()
-    assert out[0][3] == 4 and out[1][3] == 8
+    assert out[0][3] == 4 and out[1][3] == ctas
     assert rel(out[1][0], out[0][0]) < tol
     np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-9 if precision == 64 else 1e-4)
     np.testing.assert_allclose(out[1][2], out[0][2], rtol=1e-9 if precision == 64 else 1e-4)
