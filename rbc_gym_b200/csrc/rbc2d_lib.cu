@@ -259,6 +259,7 @@ static int dispatch_env(rbc2d_sim* s, const float* actions, float* obs, float* r
         io.truncated = trunc ? trunc : s->trunc;
         io.nan_flag = nan ? nan : s->nan;
         io.cell_dist = s->wr.shaping ? s->cell_dist : nullptr;
+        io.pressure = s->pressure;
         if (n <= 0) return 0;
         const int slot = (int)(s->timed_launches % rbc2d_sim::kRing);
         if (time_it) CK(cudaEventRecord(s->ev0[slot], s->stream));
@@ -286,10 +287,9 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
 {
     if (!cfg || !out) return fail("rbc2d_create: null argument");
     *out = nullptr;
-    const bool dedicated = (cfg->nx == NX && cfg->nz == NZ) && !(rbc2dx_api::supported(cfg->nx, cfg->nz) && !cfg->pressure);
+    const bool dedicated = (cfg->nx == NX && cfg->nz == NZ) && !rbc2dx_api::supported(cfg->nx, cfg->nz);
     if (!dedicated && !rbc2dx_api::supported(cfg->nx, cfg->nz))
         return fail("rbc2d_create: registered grids are 96 x 64, 128 x 64 and 192 x 128");
-    if (!dedicated && cfg->pressure) return fail("rbc2d_create: pressure channels are available on the 96 x 64 grid only");
     if (cfg->num_envs < 1) return fail("rbc2d_create: num_envs must be >= 1");
     if (cfg->precision != 32 && cfg->precision != 64) return fail("rbc2d_create: precision must be 32 or 64");
     if (cfg->heaters < 1 || cfg->heaters > MAX_HEATERS) return fail("rbc2d_create: heaters must be in 1..32");
@@ -320,7 +320,7 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
         else rc = split ? prepare_kernel<double, true>(s) : prepare_kernel<double, false>(s);
         if (rc) { rbc2d_destroy(s); return rc; }
     } else {
-        rc = rbc2dx_api::create(cfg->nx, cfg->nz, cfg->precision, cfg->device, s->hc.lx, s->hc.lz, &s->plan);
+        rc = rbc2dx_api::create(cfg->nx, cfg->nz, cfg->precision, split ? 1 : 0, cfg->device, s->hc.lx, s->hc.lz, &s->plan);
         if (rc) { rbc2d_destroy(s); return rc; }
         s->smem = rbc2dx_api::smem_bytes(s->plan);
         s->grid = rbc2dx_api::grid_ctas(s->plan, 1 << 30);

@@ -22,12 +22,13 @@ struct IoRaw {
     int* truncated;
     int* nan_flag;
     double* cell_dist;
+    void* pressure;      // [B][2][NZ][NX] in the plan's precision (split mode), else nullptr
 };
 
 // 1 when a cluster kernel is registered for this grid.  `force_cluster` (env RBC_B200_CLUSTER=1) also routes the
 // 96 x 64 grid through the cluster kernel (2 CTAs per environment) for cross-validation and measurement.
 int supported(int nx, int nz);
-int create(int nx, int nz, int precision, int device, double lx, double lz, Plan** out);   // 0 or -1 (rbc_fail)
+int create(int nx, int nz, int precision, int split, int device, double lx, double lz, Plan** out);   // 0 or -1 (rbc_fail); split: pressure channels
 void destroy(Plan* p);
 int launch(Plan* p, const rbc2d::HostConfig& hc, const rbc2d::HostWrappers& wr, const IoRaw& io, const int* env_ids, int n,
            rbc2d::RunFlags F, cudaStream_t stream);

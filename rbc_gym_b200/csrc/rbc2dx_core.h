@@ -94,7 +94,7 @@ template <typename Real>
 struct CtxX {
     unsigned char* base;        // device: this CTA's dynamic shared memory; host: arena of rank 0
     size_t arena_stride;        // host: bytes between the arenas of consecutive ranks (device: unused)
-    unsigned o_s0, o_s1, o_R, o_Tb, o_mid, o_ends, o_twN, o_tw2, o_red, o_fin, o_cfin, o_bars, o_tinv;   // o_R / o_tinv == ~0u: see project()
+    unsigned o_s0, o_s1, o_R, o_Tb, o_mid, o_ends, o_twN, o_tw2, o_red, o_fin, o_cfin, o_bars, o_tinv, o_phs;   // o_R / o_tinv == ~0u: see project(); o_phs: split mode only
     Real* gm;                   // global: [CL][2][NLOC] stage tendencies of this cluster (ping-pong slabs)
     Real* nxt_g;                // global: [CL][NS_SM] predicted state (fp64 mode) or nullptr
     // global tables, [CL] blocks each (build_tables_host)
@@ -143,7 +143,8 @@ inline T* peer_ptr(const unsigned char*, size_t stride, T* p, int my, int to)
 //   device, async mode  : the shared::cluster address of the buffer and of the receiver's mbarrier; every
 //                         store is a st.async that completes sizeof(Real) bytes on that mbarrier.
 // Channels (one pair of mbarriers each, alternating with the use count so that consecutive uses never share
-// a barrier): W = the w* face from the slab above, E = block-end values of the tridiagonal solve, H = halo rows.
+// a barrier): W = the w* face from the slab above, E = block-end values of the tridiagonal solve, H = halo rows,
+// P = column totals of the hydrostatic pressure integral from the slabs above (split mode only).
 // ------------------------------------------------------------------------------------------
 //
 // Why no cluster barrier is needed (stage s, buffers ping-pong A/B, barriers alternate with the use count):
@@ -157,7 +158,7 @@ inline T* peer_ptr(const unsigned char*, size_t stride, T* p, int my, int to)
 //     so q ran thomas_back(s+1), which follows its spike_correct(s) — the last reader of the slot.
 //   * barrier (ch, parity) is re-used by pushes of use n+2; a producer two uses ahead would have needed the
 //     consumer's own pushes of use n+1, which the consumer issues only after completing its wait of use n.
-enum { CH_W = 0, CH_E = 1, CH_H = 2, NCHAN = 3 };
+enum { CH_W = 0, CH_E = 1, CH_H = 2, CH_P = 3, NCHAN = 4 };   // CH_P: column sums of the hydrostatic pressure (split mode)
 struct SyncState { unsigned n[NCHAN]; };              // uses of each channel so far (identical on all CTAs)
 
 #if defined(__CUDACC__)
@@ -289,10 +290,10 @@ RBC_HD void phase_store_state(int tid, int rank, const Real* RBC_RESTRICT sm, Re
 // arithmetic in the same order).  Halo rows make every window load unconditional; b* rows and the w* face
 // that the neighbouring slabs need before the next barrier are pushed into their buffers as they are made.
 // ------------------------------------------------------------------------------------------
-template <typename G, bool ASYNC, typename Real>
+template <typename G, bool ASYNC, bool SPLIT, typename Real>
 RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real* RBC_RESTRICT c, Real* RBC_RESTRICT n,
                            const PeerBuf<Real>& below_h, const PeerBuf<Real>& below_w, const PeerBuf<Real>& above_h,
-                           const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm)
+                           const Real* RBC_RESTRICT phy, const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm)
 {
     constexpr int NX = G::NX, NZ = G::NZ, SX = G::SX, RS = G::RS, NT = G::NT, NZL = G::NZL, H = G::HALO;
     const int i = tid % NX, s = tid / NX, lk0 = s * RS, kg0 = rank * NZL + lk0;
@@ -367,8 +368,9 @@ RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real*
         const Real Wu_hi = top ? Real(0) : upwind_ord(centred4(wxn[1], wxn[2], wxn[3], wxn[4]), uz + 1, o_face_hi);
         const Real udn = bot ? -uz[3] : uz[2];
         const Real uup = top ? -uz[3] : uz[4];
-        const Real Gu = (F0 - F1) * C.idx + (Wu_lo - Wu_hi) * C.idz + (ux[4] - Real(2) * ux[3] + ux[2]) * ndx +
-                        (uup - Real(2) * uz[3] + udn) * ndz;
+        Real Gu = (F0 - F1) * C.idx + (Wu_lo - Wu_hi) * C.idz + (ux[4] - Real(2) * ux[3] + ux[2]) * ndx +
+                  (uup - Real(2) * uz[3] + udn) * ndz;
+        if (SPLIT) Gu -= (phy[lk * G::RSTR + i] - phy[lk * G::RSTR + col[2]]) * C.idx;
 
         // ---- w (face k; face 0 is the wall) ----
         const Real ut0 = centred_ord(uz[1], uz[2], uz[3], uz[4], o_ce_face);
@@ -378,7 +380,7 @@ RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real*
         const Real Ww_hi = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen), wz + 1, o_up_cen);
         Real Gw = (Fw0 - Fw1) * C.idx + (Ww_lo - Ww_hi) * C.idz + (wxr[4] - Real(2) * wxr[3] + wxr[2]) * ndx +
                   (wz[4] - Real(2) * wz[3] + wz[2]) * ndz;
-        Gw += Real(0.5) * (bz[2] + bz[3]);
+        if (!SPLIT) Gw += Real(0.5) * (bz[2] + bz[3]);
         if (bot) Gw = Real(0);
 
         // ---- RK3 substep ----
@@ -430,6 +432,42 @@ template <typename Real>
 RBC_HD void phase_copy(int tid, int nt, const Real* src, Real* dst, int nvals)
 {
     for (int q = tid; q < nvals; q += nt) dst[q] = src[q];
+}
+
+// ------------------------------------------------------------------------------------------
+// split mode (pressure channels requested): the hydrostatic pressure anomaly pHY' of the slab — the column
+// integral of b from the top wall, as in rbc2d_core.h phase_phy.  Every CTA integrates its own rows starting
+// from zero and sends its column totals to the slabs below; adding the totals of the slabs above then gives
+// the absolute values.  `phy` is the Poisson scratch (free during the tendency), `tot` is [CL][NX].
+// ------------------------------------------------------------------------------------------
+template <typename G, bool ASYNC, typename Real>
+RBC_HD void phase_phy_local(int tid, int rank, const Consts<Real>& C, const Real* RBC_RESTRICT cb, Real* RBC_RESTRICT phy,
+                            const PeerBuf<Real>* peers)
+{
+    constexpr int NX = G::NX, NZL = G::NZL, SX = G::SX, H = G::HALO, RSTR = G::RSTR;
+    if (tid >= NX) return;
+    const Real dz = Real(1) / C.idz;
+    Real above = cb[(NZL - 1 + H) * SX + tid];
+    const Real over = (rank == G::CL - 1) ? (Real(2) * C.b_top - above) : cb[(NZL + H) * SX + tid];
+    Real acc = -Real(0.5) * (above + over) * dz;
+    phy[(NZL - 1) * RSTR + tid] = acc;
+    for (int lk = NZL - 2; lk >= 0; --lk) {
+        const Real bk = cb[(lk + H) * SX + tid];
+        acc = acc - Real(0.5) * (bk + above) * dz;
+        phy[lk * RSTR + tid] = acc;
+        above = bk;
+    }
+    for (int j = 0; j < rank; ++j) peer_store<ASYNC>(peers[j], rank * NX + tid, acc);
+}
+template <typename G, typename Real>
+RBC_HD void phase_phy_offset(int tid, int rank, const Real* RBC_RESTRICT tot, Real* RBC_RESTRICT phy)
+{
+    constexpr int NX = G::NX, RS = G::RS, RSTR = G::RSTR;
+    if (rank == G::CL - 1) return;
+    const int i = tid % NX, s = tid / NX;
+    Real off = Real(0);
+    for (int j = G::CL - 1; j > rank; --j) off += tot[j * NX + i];
+    for (int r = 0; r < RS; ++r) phy[(s * RS + r) * RSTR + i] += off;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -782,24 +820,25 @@ RBC_HD double cell_distance(const Real* uy)
 #define RBX_PTR(off) reinterpret_cast<Real*>(smb + (off))
 
 // Thomas pivots of this rank's block: the on-chip copy (fp32 device path) or the global table
-template <typename G, typename Real, bool NXT_GLOBAL>
+template <typename G, typename Real, bool TINV_GLOBAL>
 RBC_HD const Real* local_tinv(const CtxX<Real>& X, unsigned char* smb, int rank)
 {
 #if defined(__CUDA_ARCH__)
-    if (!NXT_GLOBAL) return reinterpret_cast<const Real*>(smb + X.o_tinv);
+    if (!TINV_GLOBAL) return reinterpret_cast<const Real*>(smb + X.o_tinv);
 #endif
     (void)smb;
     return X.tinv + (size_t)rank * G::NZL * G::NX;
 }
 
-template <typename G, typename Real, bool NXT_GLOBAL>
+template <typename G, typename Real, bool NXT_GLOBAL, bool SPLIT>
 RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, unsigned o_dead, int my_rank, SyncState& S, bool after_tendency)
 {
     (void)my_rank;
+    constexpr bool OWN_R = NXT_GLOBAL || SPLIT;            // split mode keeps the scratch (it outlives the projection: pHY', pNHS)
     // Poisson scratch: with two on-chip state buffers the one that is dead during the projection (the old state)
     // provides it — its u rows, which no neighbour writes before this CTA has finished correct() (b*/w* pushes of the
     // next tendency only touch b halo rows and one w row).  The shared memory saved holds this rank's Thomas pivots.
-    const unsigned o_R = NXT_GLOBAL ? X.o_R : o_dead + (unsigned)(G::OFF_U * sizeof(Real));
+    const unsigned o_R = OWN_R ? X.o_R : o_dead + (unsigned)(G::OFF_U * sizeof(Real));
 
     constexpr int NZL = G::NZL, NT = G::NT, NX = G::NX, N1 = G::N1, N2 = G::N2, CL = G::CL;
     constexpr bool ASYNC = RBX_ASYNC(G, NXT_GLOBAL);
@@ -816,14 +855,14 @@ RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, un
         for (int item = tid; item < (N2 / 2) * NZL; item += NT)
             fft_passB_fwd_untangle<G>(item / NZL, RBX_PTR(o_R) + (item % NZL) * G::RSTR, RBX_PTR(X.o_tw2));
     )
-    RBX_PHASE_L(G, phase_thomas_sweep<G>(tid, RBX_PTR(o_R), local_tinv<G, Real, NXT_GLOBAL>(X, smb, rank), RBX_PTR(X.o_mid), X.thomas_scale);)
+    RBX_PHASE_L(G, phase_thomas_sweep<G>(tid, RBX_PTR(o_R), local_tinv<G, Real, OWN_R>(X, smb, rank), RBX_PTR(X.o_mid), X.thomas_scale);)
     const unsigned o_ends = X.o_ends + (S.n[CH_E] & 1u) * (unsigned)(CL * 2 * NX * sizeof(Real));     // double-buffered by use parity
     RBX_PHASE_X(G, ASYNC,
         PeerBuf<Real> peers[CL];
         RBC_UNROLL
         for (int j = 0; j < CL; ++j)
             peers[j] = make_peer<ASYNC, Real>(X, smb, o_ends, bar_off(X.o_bars, CH_E, S.n[CH_E]), rank, j, j != rank);
-        phase_thomas_back<G, ASYNC>(tid, rank, RBX_PTR(o_R), local_tinv<G, Real, NXT_GLOBAL>(X, smb, rank), RBX_PTR(X.o_mid), RBX_PTR(o_ends), peers);
+        phase_thomas_back<G, ASYNC>(tid, rank, RBX_PTR(o_R), local_tinv<G, Real, OWN_R>(X, smb, rank), RBX_PTR(X.o_mid), RBX_PTR(o_ends), peers);
     )
     if (CL > 1) {
         if (ASYNC) { RBX_WAIT(CH_E, S.n[CH_E], (unsigned)(CL - 1) * 2u * ROWB); }
@@ -864,7 +903,28 @@ RBC_HD void project(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_p, un
 // ------------------------------------------------------------------------------------------
 // one action step of one environment, executed by all CTAs of the cluster
 // ------------------------------------------------------------------------------------------
+// split mode: pHY' of the slab state at byte offset o_state into the Poisson scratch (two phases and one exchange)
 template <typename G, typename Real, bool NXT_GLOBAL>
+RBC_HD void hydrostatic(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_state, int my_rank, SyncState& S)
+{
+    (void)my_rank;
+    constexpr bool ASYNC = RBX_ASYNC(G, NXT_GLOBAL);
+    constexpr int CL = G::CL;
+    RBX_PHASE_X(G, ASYNC,
+        PeerBuf<Real> peers[CL];
+        RBC_UNROLL
+        for (int j = 0; j < CL; ++j)
+            peers[j] = make_peer<ASYNC, Real>(X, smb, X.o_phs, bar_off(X.o_bars, CH_P, S.n[CH_P]), rank, j, j < rank);
+        phase_phy_local<G, ASYNC>(tid, rank, C, RBX_PTR(o_state) + G::OFF_B, RBX_PTR(X.o_R), peers);
+    )
+    if (CL > 1) {
+        if (ASYNC) { RBX_WAIT(CH_P, S.n[CH_P], (unsigned)(CL - 1 - my_rank) * (unsigned)(G::NX * sizeof(Real))); }
+        RBX_PHASE_L(G, phase_phy_offset<G>(tid, rank, RBX_PTR(X.o_phs), RBX_PTR(X.o_R));)
+    }
+    S.n[CH_P] += 1;
+}
+
+template <typename G, typename Real, bool NXT_GLOBAL, bool SPLIT = false>
 RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, const RunFlags& F, int my_rank,
                             SyncState& S)
 {
@@ -880,11 +940,13 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
         if (tid < NX) RBX_PTR(X.o_Tb)[tid] = (Real)rbc2d::heater_T(C, io.actions + (size_t)env * C.heaters, (tid + 0.5) * C.dx);
     )
     unsigned o_cur = X.o_s0, o_nxt = X.o_s1;               // fp64 mode: o_s1 is unused, the predicted state is global
-    if (F.project_first) project<G, Real, NXT_GLOBAL>(C, X, o_cur, o_nxt, my_rank, S, false);
+    Real last_dtau = Real(1);                              // set! projects with dtau = 1
+    if (F.project_first) project<G, Real, NXT_GLOBAL, SPLIT>(C, X, o_cur, o_nxt, my_rank, S, false);
     for (int sub = 0; sub < F.nsub; ++sub) {
         const Real dt = (sub == F.nsub - 1) ? C.dt_last : C.dt_full;
         for (int stage = 0; stage < 3; ++stage) {
             const int in_slab = (stage & 1) ? 0 : 1, out_slab = 1 - in_slab;
+            if (SPLIT) hydrostatic<G, Real, NXT_GLOBAL>(C, X, o_cur, my_rank, S);
             RBX_PHASE_X(G, ASYNC,
                 Real* cur = RBX_PTR(o_cur);
                 Real* nxt;
@@ -903,7 +965,7 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
                     above_h = make_peer<ASYNC, Real>(X, smb, o_nxt, hb, rank, rank + 1, CL > 1 && rank < CL - 1);
                 }
                 Real* gmr = X.gm + (size_t)rank * 2 * G::NLOC;
-                phase_tendency<G, ASYNC>(tid, rank, C, cur, nxt, below_h, below_w, above_h, RBX_PTR(X.o_Tb), gmr + in_slab * G::NLOC,
+                phase_tendency<G, ASYNC, SPLIT>(tid, rank, C, cur, nxt, below_h, below_w, above_h, SPLIT ? RBX_PTR(X.o_R) : nullptr, RBX_PTR(X.o_Tb), gmr + in_slab * G::NLOC,
                                          gmr + out_slab * G::NLOC, dt, gam[stage], zet[stage], stage > 0);
             )
             unsigned o_p;
@@ -913,13 +975,49 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
             } else {
                 o_p = o_nxt; o_nxt = o_cur; o_cur = o_p;
             }
-            project<G, Real, NXT_GLOBAL>(C, X, o_p, NXT_GLOBAL ? o_p : o_nxt, my_rank, S, true);
+            project<G, Real, NXT_GLOBAL, SPLIT>(C, X, o_p, NXT_GLOBAL ? o_p : o_nxt, my_rank, S, true);
+            last_dtau = (gam[stage] + zet[stage]) * dt;
         }
     }
 
     // ---- epilogue: NaN check, observation, Nusselt numbers, reward, bookkeeping ----
     const int oz = NZ / C.obs_nz, ox = NX / C.obs_nx, nobs = C.obs_nz * C.obs_nx;
     const unsigned o_red = (X.o_red != ~0u) ? X.o_red : o_nxt;   // fp32: the dead state buffer when it is large enough
+    if (SPLIT && io.pressure != nullptr && (F.nsub > 0 || F.project_first)) {
+        // pressure fields of get_state (rbc_sim2D_api.jl:114-115), kept per environment as in rbc2d_core.h:
+        // pNHS = phi / dtau of the last stage in the zero-mean gauge (the mean needs the whole cluster), then
+        // pHY' recomputed from the final b
+        Real* pr = io.pressure + (size_t)env * 2 * G::NCELL;
+        RBX_PHASE_L(G,
+            double* red = reinterpret_cast<double*>(smb + o_red);
+            const Real* R = RBX_PTR(X.o_R);
+            double acc = 0;
+            for (int q = tid; q < NZL * NX; q += NT) acc += (double)R[(q / NX) * G::RSTR + (q % NX)];
+            red[tid] = acc;
+        )
+        RBX_PHASE_C(G,
+            if (tid == 0) {
+                const double* red = reinterpret_cast<const double*>(smb + o_red);
+                double acc = 0;
+                for (int e = 0; e < NT; ++e) acc += red[e];
+                reinterpret_cast<double*>(smb + X.o_cfin)[NRED + 1] = acc;
+            }
+        )
+        RBX_PHASE_L(G,
+            double* mine = reinterpret_cast<double*>(smb + X.o_cfin);
+            double tot = 0;
+            for (int j = 0; j < CL; ++j) tot += (j == rank) ? mine[NRED + 1] : peer_ptr(X.base, X.arena_stride, mine, rank, j)[NRED + 1];
+            const double mean = tot / (double)G::NCELL;
+            const Real* R = RBX_PTR(X.o_R);
+            for (int q = tid; q < NZL * NX; q += NT)
+                pr[G::NCELL + rank * NZL * NX + q] = (Real)(((double)R[(q / NX) * G::RSTR + (q % NX)] - mean) / (double)last_dtau);
+        )
+        hydrostatic<G, Real, NXT_GLOBAL>(C, X, o_cur, my_rank, S);
+        RBX_PHASE_L(G,
+            const Real* R = RBX_PTR(X.o_R);
+            for (int q = tid; q < NZL * NX; q += NT) pr[rank * NZL * NX + q] = R[(q / NX) * G::RSTR + (q % NX)];
+        )
+    }
     RBX_PHASE_L(G,
         // per-thread partial sums over the thread's strip (get_nusselt, rbc_sim2D_api.jl:142-163):
         //  0: sum b w   1: same on the sensor grid   2..5: sum_x b on rows 0, 1, NZ-2, NZ-1
@@ -993,6 +1091,15 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
                 if (C.obs_clip) v = fminf(fmaxf(v, -C.obs_maxval), C.obs_maxval);
             }
             ob[q] = v;
+        }
+        if (SPLIT && io.pressure != nullptr && C.channels == 5) {     // also on observe-only launches, from the stored fields
+            const Real* pr = io.pressure + (size_t)env * 2 * G::NCELL;
+            for (int q = tid; q < 2 * nobs; q += NT) {
+                const int ch = q / nobs; const int zo = (q % nobs) / C.obs_nx; const int xo = q % C.obs_nx;
+                const int k = zo * oz;
+                if (k / NZL != rank) continue;
+                ob[3 * nobs + q] = (float)pr[(size_t)ch * G::NCELL + k * NX + xo * ox];
+            }
         }
         if (rank == 0 && tid == 0) {
             double* my = reinterpret_cast<double*>(smb + X.o_cfin);
@@ -1158,17 +1265,18 @@ inline void build_tables_host(double lx, double lz, const HostTables& T)
 }
 
 // shared-memory layout of one CTA (bytes); identical on the device and in the host emulator
-template <typename G, typename Real, bool NXT_GLOBAL>
+template <typename G, typename Real, bool NXT_GLOBAL, bool SPLIT = false>
 struct SmemLayoutX {
     static constexpr size_t al(size_t x) { return (x + 15) & ~(size_t)15; }
+    static constexpr bool OWN_R = NXT_GLOBAL || SPLIT;
     static constexpr size_t s0 = 0;
     static constexpr size_t s1 = al(s0 + sizeof(Real) * G::NS_SM);
-    // fp64 (one on-chip state buffer): separate Poisson scratch; fp32: the scratch aliases the dead buffer and the
-    // space holds this rank's Thomas pivots instead
+    // fp64 (one on-chip state buffer) and split mode: separate Poisson scratch; otherwise the scratch aliases the dead
+    // buffer and the space holds this rank's Thomas pivots instead
     static constexpr size_t R = NXT_GLOBAL ? s1 : al(s1 + sizeof(Real) * G::NS_SM);
     static constexpr size_t tinv = R;
-    static constexpr size_t red = al(R + (NXT_GLOBAL ? sizeof(Real) * G::NR : sizeof(Real) * G::NZL * G::NX));
-    static_assert(NXT_GLOBAL || G::LR >= G::NZL + 1, "the scratch must fit the u rows of a state buffer");
+    static constexpr size_t red = al(R + (OWN_R ? sizeof(Real) * G::NR : sizeof(Real) * G::NZL * G::NX));
+    static_assert(OWN_R || G::LR >= G::NZL + 1, "the scratch must fit the u rows of a state buffer");
     static constexpr bool kRedSeparate = NXT_GLOBAL || sizeof(double) * G::NRED * G::NT > sizeof(Real) * G::NS_SM;
     static constexpr size_t fin = al(red + (kRedSeparate ? sizeof(double) * G::NRED * G::NT : 0));
     static constexpr size_t cfin = al(fin + sizeof(double) * G::NRED * 16);
@@ -1176,15 +1284,22 @@ struct SmemLayoutX {
     static constexpr size_t mid = al(Tb + sizeof(Real) * G::NX);
     static constexpr size_t ends = al(mid + sizeof(Real) * 2 * G::NX);
     static constexpr size_t bars = al(ends + sizeof(Real) * 2 * G::CL * 2 * G::NX);     // ends: [2 parities][CL ranks][2 NX]
-    static constexpr size_t twN = al(bars + 8 * 2 * NCHAN);
+    // split mode: [CL ranks][NX] column totals of the hydrostatic integral.  With a separate reduction scratch they live
+    // inside it, past the NT doubles the pNHS mean uses: the scratch is otherwise idle until the final reductions, which
+    // start after the last hydrostatic phase
+    static constexpr bool kPhsInRed = SPLIT && kRedSeparate;
+    static constexpr size_t phs = kPhsInRed ? red + 4096 : al(bars + 8 * 2 * NCHAN);
+    static_assert(!kPhsInRed || (sizeof(double) * G::NT <= 4096 && 4096 + sizeof(Real) * G::CL * G::NX <= sizeof(double) * G::NRED * G::NT),
+                  "column totals do not fit the reduction scratch");
+    static constexpr size_t twN = al(bars + 8 * 2 * NCHAN + ((SPLIT && !kPhsInRed) ? sizeof(Real) * G::CL * G::NX : 0));
     static constexpr size_t tw2 = al(twN + sizeof(Real) * 2 * G::NH);
     static constexpr size_t total = al(tw2 + sizeof(Real) * 2 * G::NH);
     template <typename Ctx>
     static void fill(Ctx& X)
     {
-        X.o_s0 = (unsigned)s0; X.o_s1 = (unsigned)s1; X.o_R = NXT_GLOBAL ? (unsigned)R : ~0u; X.o_tinv = NXT_GLOBAL ? ~0u : (unsigned)tinv; X.o_red = kRedSeparate ? (unsigned)red : ~0u; X.o_fin = (unsigned)fin;
+        X.o_s0 = (unsigned)s0; X.o_s1 = (unsigned)s1; X.o_R = OWN_R ? (unsigned)R : ~0u; X.o_tinv = OWN_R ? ~0u : (unsigned)tinv; X.o_red = kRedSeparate ? (unsigned)red : ~0u; X.o_fin = (unsigned)fin;
         X.o_cfin = (unsigned)cfin; X.o_Tb = (unsigned)Tb; X.o_mid = (unsigned)mid; X.o_ends = (unsigned)ends; X.o_bars = (unsigned)bars;
-        X.o_twN = (unsigned)twN; X.o_tw2 = (unsigned)tw2;
+        X.o_phs = SPLIT ? (unsigned)phs : ~0u; X.o_twN = (unsigned)twN; X.o_tw2 = (unsigned)tw2;
     }
 };
 

@@ -113,26 +113,28 @@ def unpack(st):
 
 
 def stepx(state, actions, ra, dt_action, nx=96, nz=64, cl=1, precision=64, nxt_global=False, dt_solver=0.03, obs=(8, 48), heaters=12,
-          heater_limit=0.75, episode_length=300.0, t0=None, wrappers=None, project_first=False, nsub=-1):
+          heater_limit=0.75, episode_length=300.0, t0=None, wrappers=None, project_first=False, nsub=-1, split=False):
     """One action step through the emulated CLUSTER kernel (rbc2dx_core.h): grid nx x nz split over `cl` CTAs.
-    state: [B, 2*nx*nz + nx*(nz+1)] (b,u,w flattened)."""
+    state: [B, 2*nx*nz + nx*(nz+1)] (b,u,w flattened).  split=True: pressure-split mode with the two pressure channels."""
     lib = C.CDLL(str(build_x()))
     B = state.shape[0]
     dt = np.float64 if precision == 64 else np.float32
     st = np.array(state, dtype=dt, order="C")
-    h = HostConfig(ra, 0.7, 2 * math.pi, 2.0, 1.0, heater_limit, dt_action, dt_solver, episode_length, heaters, obs[0], obs[1], 3)
+    ch = 5 if split else 3
+    h = HostConfig(ra, 0.7, 2 * math.pi, 2.0, 1.0, heater_limit, dt_action, dt_solver, episode_length, heaters, obs[0], obs[1], ch)
     a = np.ascontiguousarray(actions, dtype=np.float32)
-    ob = np.zeros((B, 3, obs[0], obs[1]), np.float32)
+    ob = np.zeros((B, ch, obs[0], obs[1]), np.float32)
     rew = np.zeros(B, np.float32)
     nus, nuo = np.zeros(B), np.zeros(B)
     t = np.zeros(B) if t0 is None else np.array(t0, dtype=np.float64)
     sc, tr, nf = np.ones(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    pr = np.zeros((B, 2, nz, nx), dt) if split else None
     vp = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
     cd = np.zeros(B)
     rc = lib.emu_rbc2dx_step(C.byref(h), C.byref(wrappers) if wrappers is not None else None, vp(cd), nx, nz, cl, precision, int(nxt_global), B,
-                             vp(st), vp(a), vp(ob), vp(rew), vp(nus), vp(nuo), vp(t), vp(sc), vp(tr), vp(nf), int(project_first), nsub)
+                             vp(st), vp(a), vp(ob), vp(rew), vp(nus), vp(nuo), vp(t), vp(sc), vp(tr), vp(nf), int(project_first), nsub, int(split), vp(pr))
     assert rc == 0, rc
-    return dict(state=st, obs=ob, reward=rew, nu_state=nus, nu_obs=nuo, t=t, step=sc, truncated=tr, nan=nf, cell_dist=cd)
+    return dict(state=st, obs=ob, reward=rew, nu_state=nus, nu_obs=nuo, t=t, step=sc, truncated=tr, nan=nf, cell_dist=cd, pressure=pr)
 
 
 def packx(b, u, w):

@@ -9,12 +9,12 @@
 
 using namespace rbc2dx;
 
-template <typename G, typename Real, bool NXTG>
+template <typename G, typename Real, bool NXTG, bool SPLIT>
 static void run(const HostConfig& h, const HostWrappers& wr, double* cell_dist, int B, Real* state, const float* actions, float* obs,
                 float* reward, double* nu_state, double* nu_obs, double* t, int* step_count, int* truncated, int* nan_flag,
-                int project_first, int nsub)
+                int project_first, int nsub, Real* pressure)
 {
-    using L = SmemLayoutX<G, Real, NXTG>;
+    using L = SmemLayoutX<G, Real, NXTG, SPLIT>;
     Consts<Real> C = make_consts<G, Real>(h, wr);
     std::vector<double> td(table_doubles<G>());
     HostTables T;
@@ -49,27 +49,32 @@ static void run(const HostConfig& h, const HostWrappers& wr, double* cell_dist, 
         std::memcpy(arena.data() + r * L::total + X.o_twN, X.twN, sizeof(Real) * 2 * G::NH);
         std::memcpy(arena.data() + r * L::total + X.o_tw2, X.tw2, sizeof(Real) * 2 * G::NH);
     }
-    EnvIO<Real> io{state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, nullptr, cell_dist};
+    EnvIO<Real> io{state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, SPLIT ? pressure : nullptr, cell_dist};
     RunFlags F{nsub >= 0 ? nsub : C.nsub, project_first, 1};
     SyncState S{};
-    for (int e = 0; e < B; ++e) env_action_step<G, Real, NXTG>(C, io, X, e, F, 0, S);
+    for (int e = 0; e < B; ++e) env_action_step<G, Real, NXTG, SPLIT>(C, io, X, e, F, 0, S);
 }
 
 #define ARGS *h, wr, cell_dist, B
 #define TAIL actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, project_first, nsub
+#define DISPATCH2(GT, RT, NG)                                                                     \
+    do {                                                                                          \
+        if (split) run<GT, RT, NG, true>(ARGS, (RT*)state, TAIL, (RT*)pressure);                   \
+        else run<GT, RT, NG, false>(ARGS, (RT*)state, TAIL, (RT*)nullptr);                         \
+        return 0;                                                                                 \
+    } while (0)
 #define DISPATCH(GT)                                                                              \
     do {                                                                                          \
-        if (precision == 64 && nxt_global) run<GT, double, true>(ARGS, (double*)state, TAIL);     \
-        else if (precision == 64) run<GT, double, false>(ARGS, (double*)state, TAIL);             \
-        else if (precision == 32 && nxt_global) run<GT, float, true>(ARGS, (float*)state, TAIL);  \
-        else if (precision == 32) run<GT, float, false>(ARGS, (float*)state, TAIL);               \
+        if (precision == 64 && nxt_global) DISPATCH2(GT, double, true);                           \
+        else if (precision == 64) DISPATCH2(GT, double, false);                                   \
+        else if (precision == 32 && nxt_global) DISPATCH2(GT, float, true);                       \
+        else if (precision == 32) DISPATCH2(GT, float, false);                                    \
         else return -1;                                                                           \
-        return 0;                                                                                 \
     } while (0)
 
 extern "C" int emu_rbc2dx_step(const HostConfig* h, const HostWrappers* wp, double* cell_dist, int nx, int nz, int cl, int precision,
                                int nxt_global, int B, void* state, const float* actions, float* obs, float* reward, double* nu_state,
-                               double* nu_obs, double* t, int* step_count, int* truncated, int* nan_flag, int project_first, int nsub)
+                               double* nu_obs, double* t, int* step_count, int* truncated, int* nan_flag, int project_first, int nsub, int split, void* pressure)
 {
     HostWrappers wr;
     if (wp) wr = *wp;

@@ -119,11 +119,90 @@ def test_env_class_at_192x128(B):
     env.close()
 
 
-def test_unregistered_grid_and_pressure_are_rejected(B):
+def test_unregistered_grid_is_rejected(B):
     with pytest.raises(RuntimeError, match="registered grids"):
         B.Sim2D(1, ra=1e5, state_shape=(100, 200))
-    with pytest.raises(RuntimeError, match="pressure"):
-        B.Sim2D(1, ra=1e5, state_shape=(NZ, NX), pressure=True)
+
+
+@pytest.mark.parametrize("nx,nz,precision,tol,ptol", [(192, 128, 64, 1e-10, 1e-8), (192, 128, 32, 1e-5, 5e-3), (128, 64, 64, 1e-10, 1e-8),
+                                                      (128, 64, 32, 1e-5, 5e-3)])
+def test_pressure_channels_on_cluster_grids_match_oracle(B, nx, nz, precision, tol, ptol):
+    """Pressure-split mode of the cluster kernel: the hydrostatic column integral and the zero-mean gauge of pNHS cross the
+    CTAs of the cluster.  State, both pressure fields (get_state channels 3-4) and their sensor sub-sample against the
+    oracle's split scheme; more environments than resident clusters."""
+    import torch
+    n = 40
+    P = O.make_params(RA, nx=nx, nz=nz, split_phy=True)
+    states = [smooth_state(nx, nz, seed=s) for s in (0, 1)]
+    acts = np.random.default_rng(11).uniform(-1, 1, (2, 12)).astype(np.float32)
+    dt = 3 * DTS + 0.005
+    sim = B.Sim2D(n, ra=RA, dt_action=dt, dt_solver=DTS, state_shape=(nz, nx), obs_shape=(8, 48 if nx == 192 else 64), precision=precision,
+                  pressure=True)
+    sim.reset_from_fields(np.concatenate([B.pack_fields(*(a[None] for a in states[i % 2])) for i in range(n)]), project=False)
+    obs, *_ = sim.step(torch.from_numpy(acts[np.arange(n) % 2]).cuda())
+    st = sim.get_state().cpu().numpy()
+    assert st.shape == (n, 5, nz, nx) and obs.shape[1] == 5
+    b, u, w = B.split_fields(sim.fields(), (nz, nx))
+    oz, ox = nz // 8, nx // obs.shape[3]
+    for j in (0, 1, n - 2, n - 1):
+        b0, u0, w0 = states[j % 2]
+        r = O.step(P, b0, u0, w0, acts[j % 2].astype(np.float64), O.substep_schedule(dt, DTS), want_pressure=True)
+        assert rel(b[j], r["b"]) < tol and rel(u[j], r["u"]) < tol and rel(w[j], r["w"]) < tol
+        assert rel(st[j, 3], r["phy"]) < max(tol, 1e-6) and rel(st[j, 4], r["pnhs"]) < max(ptol, 1e-6)   # get_state is fp32
+        np.testing.assert_array_equal(obs[j, 3:].cpu().numpy(), st[j, 3:, ::oz, ::ox])
+    sim.close()
+
+
+def test_pressure_at_reset_on_192x128(B):
+    """reset in pressure mode: the set! projection (dtau = 1) leaves pNHS, pHY' follows from b; reset()'s observation
+    carries the channels from the stored fields (observe-only launch)."""
+    rng = np.random.default_rng(5)
+    u = 0.01 * rng.standard_normal((NZ, NX))
+    w = 0.01 * rng.standard_normal((NZ + 1, NX))
+    w[0] = 0
+    w[-1] = 0
+    b = 1.5 - 0.5 * (np.arange(NZ)[:, None] + 0.5) / NZ + 0.01 * rng.standard_normal((NZ, NX))
+    P = O.make_params(RA, nx=NX, nz=NZ, split_phy=True)
+    up, wp, phi = O.project(P, u, w)
+    sim = B.Sim2D(2, ra=RA, dt_action=0.045, dt_solver=DTS, state_shape=(NZ, NX), precision=64, pressure=True)
+    sim.reset_from_fields(np.concatenate([B.pack_fields(b[None], u[None], w[None])] * 2), project=True)
+    st = sim.get_state().cpu().numpy()
+    assert rel(st[1, 4], phi - phi.mean()) < 1e-5
+    dz = 2.0 / NZ
+    phy = np.empty((NZ, NX))
+    phy[-1] = -0.5 * (b[-1] + (2 * 1.0 - b[-1])) * dz
+    for k in range(NZ - 2, -1, -1):
+        phy[k] = phy[k + 1] - 0.5 * (b[k] + b[k + 1]) * dz
+    assert rel(st[1, 3], phy) < 1e-6
+    obs = sim.observe()[0].cpu().numpy()
+    np.testing.assert_array_equal(obs[1, 3:], st[1, 3:, ::16, ::4])
+    sim.close()
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-12), (32, 2e-6)])
+def test_generic_split_kernel_on_96x64_agrees_with_dedicated_split_kernel(B, ckpt_ra1e5, precision, tol):
+    import torch
+    c = ckpt_ra1e5
+    acts = np.random.default_rng(4).uniform(-1, 1, (4, 12)).astype(np.float32)
+    out = []
+    for flag in ("0", "g"):
+        os.environ["RBC_B200_CLUSTER"] = flag
+        try:
+            sim = B.Sim2D(4, ra=1e5, dt_action=0.3, precision=precision, pressure=True)
+        finally:
+            os.environ.pop("RBC_B200_CLUSTER", None)
+        sim.load_checkpoints(c)
+        sim.reset_from_checkpoints(torch.tensor([0, 7, 3, 16], dtype=torch.int32))
+        obs0 = sim.observe()[0].cpu().numpy()
+        obs, *_ = sim.step(torch.from_numpy(acts).cuda())
+        out.append((sim.fields(), sim.get_state().cpu().numpy(), obs.cpu().numpy(), obs0, sim.launch_info()["grid"]))
+        sim.close()
+    assert out[0][4] == 4 and out[1][4] == (4 if precision == 32 else 8)
+    assert rel(out[1][0], out[0][0]) < tol
+    for ch in (3, 4):
+        assert rel(out[1][1][:, ch], out[0][1][:, ch]) < max(tol * 500, 1e-6)
+        assert rel(out[1][3][:, ch], out[0][3][:, ch]) < max(tol * 500, 1e-6)
+        assert rel(out[1][2][:, ch], out[0][2][:, ch]) < max(tol * 500, 1e-6)
 
 
 @pytest.mark.parametrize("precision,tol,flag,ctas", [(64, 1e-12, "1", 8), (32, 2e-6, "1", 8), (32, 2e-6, "g", 4)])

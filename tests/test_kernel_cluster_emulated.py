@@ -105,3 +105,54 @@ def test_cluster_flags_and_fused_wrappers_192():
     rwd = W.shape_reward(W.normalize_reward(float(-plain["nu_obs"][0]), ra), cd, 0.1)
     assert fused["reward"][0] == pytest.approx(rwd, rel=1e-6)
     np.testing.assert_allclose(fused["obs"][0], W.normalize_observation(plain["obs"][0].copy(), 0.75), rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize("nx,nz,cl,nxt_global,obs", [(96, 64, 1, False, (8, 48)), (96, 64, 2, False, (8, 48)), (96, 64, 4, True, (8, 48)),
+                                                     (192, 128, 4, False, (8, 48)), (192, 128, 8, True, (16, 96)), (128, 64, 2, False, (8, 64))])
+def test_pressure_split_mode_matches_oracle(nx, nz, cl, nxt_global, obs):
+    """pressure-split mode on every cluster size: the hydrostatic column integral crosses the slabs (column totals sent
+    downwards), pNHS needs a cluster-wide mean; state and both pressure fields against the oracle's split scheme."""
+    ra, dts = 1e6, 0.015
+    P = O.make_params(ra, nx=nx, nz=nz, split_phy=True)
+    b, u, w = smooth_state(nx, nz)
+    act = np.random.default_rng(3).uniform(-1, 1, 12).astype(np.float32)
+    dt = 2 * dts + dts / 3
+    r = O.step(P, b, u, w, act.astype(np.float64), O.substep_schedule(dt, dts), want_pressure=True)
+    st = emu.pack(b[None], u[None], w[None])
+    for precision, tol, ptol in ((64, 1e-13, 1e-10), (32, 2e-6, 2e-3)):
+        if precision == 32 and nxt_global:
+            continue
+        e = emu.stepx(st, act[None], ra, dt, nx=nx, nz=nz, cl=cl, precision=precision, nxt_global=nxt_global, dt_solver=dts, obs=obs, split=True)
+        bb, uu, ww = emu.unpackx(e["state"].astype(np.float64), nx, nz)
+        assert rel(bb[0], r["b"]) < tol and rel(uu[0], r["u"]) < tol and rel(ww[0], r["w"]) < tol
+        pr = e["pressure"][0].astype(np.float64)
+        assert rel(pr[0], r["phy"]) < max(tol, 1e-13) * 10
+        assert rel(pr[1], r["pnhs"]) < ptol
+        oz, ox = nz // obs[0], nx // obs[1]
+        np.testing.assert_array_equal(e["obs"][0, 3], e["pressure"][0, 0, ::oz, ::ox].astype(np.float32))
+        np.testing.assert_array_equal(e["obs"][0, 4], e["pressure"][0, 1, ::oz, ::ox].astype(np.float32))
+        assert e["nan"][0] == 0
+
+
+def test_pressure_split_set_projection_192():
+    """reset path in split mode: the set! projection (dtau = 1) leaves pNHS, pHY' follows from b."""
+    nx, nz = 192, 128
+    rng = np.random.default_rng(7)
+    u = 0.01 * rng.standard_normal((nz, nx))
+    w = 0.01 * rng.standard_normal((nz + 1, nx))
+    w[0] = 0
+    w[-1] = 0
+    b = 1.5 - 0.5 * (np.arange(nz)[:, None] + 0.5) / nz + 0.01 * rng.standard_normal((nz, nx))
+    P = O.make_params(1e6, nx=nx, nz=nz, split_phy=True)
+    up, wp, phi = O.project(P, u, w)
+    e = emu.stepx(emu.pack(b[None], u[None], w[None]), np.zeros((1, 12), np.float32), 1e6, 0.015, nx=nx, nz=nz, cl=4, precision=64,
+                  dt_solver=0.015, project_first=True, nsub=0, split=True)
+    _, uu, ww = emu.unpackx(e["state"], nx, nz)
+    assert rel(uu[0], up) < 1e-12 and rel(ww[0], wp) < 1e-12
+    assert rel(e["pressure"][0, 1], phi - phi.mean()) < 1e-10
+    dz = 2.0 / nz
+    phy = np.empty((nz, nx))
+    phy[-1] = -0.5 * (b[-1] + (2 * 1.0 - b[-1])) * dz
+    for k in range(nz - 2, -1, -1):
+        phy[k] = phy[k + 1] - 0.5 * (b[k] + b[k + 1]) * dz
+    assert rel(e["pressure"][0, 0], phy) < 1e-12
