@@ -131,6 +131,7 @@ struct Ctx {
     Real* gm;        // global: two slabs (2 x NSTATE) of stage tendencies of this CTA, used ping-pong
     const Real* tinv; // Thomas pivots [NZ][NX]: shared copy (fp32) or the global table (fp64)
     double* red;     // shared: NRED*NT doubles for the epilogue reductions (fp64 mode; fp32 aliases s0/s1)
+    Real* E;         // shared: NE left fluxes of the warps' first columns (phase_edge_fluxes); fp64 mode: inside `red`
 };
 
 // what one kernel launch does with each environment it visits
@@ -301,23 +302,85 @@ RBC_HD void phase_phy(int tid, const Consts<Real>& C, const Real* cb, Real* phy)
 }
 
 // ------------------------------------------------------------------------------------------
+// The x-direction fluxes of a cell are shared with its neighbours: the flux through the right face of column i is
+// the flux through the left face of column i+1.  Each thread therefore evaluates only the three LEFT fluxes of its
+// cell (tracer flux at x-face i, u-momentum flux at x-centre i-1, w-momentum flux at (x-face i, z-face k)) and takes
+// the right ones from lane+1 with a warp shuffle.  Lane 31 has no lane+1: its right fluxes belong to column
+// 32(w+1) mod NX, and those are evaluated for all rows by an otherwise idle-lane prologue (phase_edge_fluxes) into
+// a small shared-memory table E[flux][row][warp column].  One third of the upwind reconstructions of the march go away.
+// ------------------------------------------------------------------------------------------
+constexpr int NEDGE = NX / 32;                       // columns 0, 32, 64
+constexpr int NE = 3 * NZ * NEDGE;                   // table size
+
+template <typename Real>
+RBC_HD void left_fluxes(const Real* RBC_RESTRICT c, int i, int k, bool want_bu, bool want_w, Real& fb, Real& fu, Real& fw)
+{
+    const Real* RBC_RESTRICT cb = c + OFF_B + k * SX;
+    const Real* RBC_RESTRICT cu = c + OFF_U + k * SX;
+    const Real* RBC_RESTRICT cw = c + OFF_W + k * SX;
+    int col[6];
+    RBC_UNROLL
+    for (int j = 0; j < 6; ++j) col[j] = wrapx(i - 3 + j);
+    if (want_bu) {
+        Real bx[6], ux[6];
+        RBC_UNROLL
+        for (int j = 0; j < 6; ++j) { bx[j] = cb[col[j]]; ux[j] = cu[col[j]]; }
+        fb = upwind5(ux[3], bx);
+        fu = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);
+    }
+    if (want_w) {
+        Real wx[6], uz[4];
+        RBC_UNROLL
+        for (int j = 0; j < 6; ++j) wx[j] = cw[col[j]];
+        RBC_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            const int kk = k - 2 + j;
+            uz[j] = (kk >= 0 && kk < NZ) ? c[OFF_U + kk * SX + i] : Real(0);
+        }
+        fw = upwind5(centred_ord(uz[0], uz[1], uz[2], uz[3], ord_ce_face(k)), wx);
+    }
+}
+
+// prologue of the march: left fluxes of the first column of every warp, all rows.  Threads 0..191 do the tracer and u
+// fluxes of (row, warp column), threads 192..383 the w flux.
+template <typename Real>
+RBC_HD void phase_edge_fluxes(int tid, const Real* RBC_RESTRICT c, Real* RBC_RESTRICT E)
+{
+    const int item = tid % (NZ * NEDGE), half = tid / (NZ * NEDGE);
+    if (half > 1) return;
+    const int k = item % NZ, ci = item / NZ;
+    Real fb = Real(0), fu = Real(0), fw = Real(0);
+    left_fluxes(c, ci * 32, k, half == 0, half == 1, fb, fu, fw);
+    if (half == 0) {
+        E[(0 * NZ + k) * NEDGE + ci] = fb;
+        E[(1 * NZ + k) * NEDGE + ci] = fu;
+    } else {
+        E[(2 * NZ + k) * NEDGE + ci] = fw;
+    }
+}
+static_assert(NT >= 2 * NZ * NEDGE, "the edge-flux prologue needs one thread per (row, warp column, half)");
+
+// ------------------------------------------------------------------------------------------
 // phase: tendencies + RK3 substep for one strip.  Reads the current state `c`, writes the
 // predicted state `n` (U* = U + dt (gam G + zet G-)), stores G into the CTA's G- slab.
 // ------------------------------------------------------------------------------------------
 template <typename Real, bool SPLIT>
 RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTRICT c, Real* RBC_RESTRICT n,
-                           const Real* RBC_RESTRICT phy, const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm)
+                           const Real* RBC_RESTRICT phy, const Real* RBC_RESTRICT Tb, const Real* RBC_RESTRICT E, const Real* gm_in, Real* gm_out,
+                           Real dt, Real gam, Real zet, bool use_gm)
 {
     const int i = tid % NX, s = tid / NX, k0 = s * RS;
     const Real* RBC_RESTRICT cb = c + OFF_B;
     const Real* RBC_RESTRICT cu = c + OFF_U;
     const Real* RBC_RESTRICT cw = c + OFF_W;
-    int col[7];
+    int col[6];
     RBC_UNROLL
-    for (int j = 0; j < 7; ++j) col[j] = wrapx(i - 3 + j);
+    for (int j = 0; j < 6; ++j) col[j] = wrapx(i - 3 + j);
+    const bool last_lane = (i & 31) == 31;
+    const int eci = ((i + 1) % NX) / 32;                 // table column of lane 31's right neighbour
 
     // sliding windows of the own column; index j <-> row k-3+j
-    Real bz[7], uz[7], wz[7], u1z[4], wxr[7];
+    Real bz[7], uz[7], wz[7], wxr[6];
     RBC_UNROLL
     for (int j = 0; j < 7; ++j) {
         const int k = k0 - 3 + j;
@@ -327,12 +390,7 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         wz[j] = (k >= 0 && k <= NZ) ? cw[k * SX + i] : Real(0);
     }
     RBC_UNROLL
-    for (int j = 0; j < 4; ++j) {                      // u(i+1, k-2 .. k+1)
-        const int k = k0 - 2 + j;
-        u1z[j] = (k >= 0 && k < NZ) ? cu[k * SX + col[4]] : Real(0);
-    }
-    RBC_UNROLL
-    for (int j = 0; j < 7; ++j) wxr[j] = cw[k0 * SX + col[j]];   // w(i-3..i+3, face k0)
+    for (int j = 0; j < 6; ++j) wxr[j] = cw[k0 * SX + col[j]];   // w(i-3..i+2, face k0)
 
     // fluxes through the strip's lower boundary (carried afterwards)
     Real Fzb_lo = Real(0), Wu_lo = Real(0), Ww_lo = Real(0);
@@ -363,11 +421,11 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
             gnu = gm_in[(1 * RS + r + 1) * NT + tid];
             gnw = gm_in[(2 * RS + r + 1) * NT + tid];
         }
-        Real bx[7], ux[7], wxn[7];
+        Real bx[6], ux[6], wxn[6];
         RBC_UNROLL
-        for (int j = 0; j < 7; ++j) {
+        for (int j = 0; j < 6; ++j) {
             bx[j] = (j == 3) ? bz[3] : cb[k * SX + col[j]];
-            ux[j] = (j == 3) ? uz[3] : ((j == 4) ? u1z[2] : cu[k * SX + col[j]]);
+            ux[j] = (j == 3) ? uz[3] : cu[k * SX + col[j]];
             wxn[j] = (j == 3) ? wz[4] : cw[(k + 1) * SX + col[j]];      // face k+1 <= NZ always valid
         }
         const bool top = EDGE && (k == NZ - 1);
@@ -377,32 +435,44 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         const int o_up_cen = EDGE ? ord_up_cen(k) : 5;
         const int o_ce_cen = EDGE ? ord_ce_cen(k) : 4;
 
-        // x- and z-face fluxes.  Interior rows evaluate them in pairs (see upwind5_pair); wall rows keep the scalar,
-        // order-selecting forms.
-        Real Fx0, Fx1, F0, F1, Fw0, Fw1, Fzb_hi, Wu_hi, Ww_hi;
+        // left x-fluxes and upper z-fluxes.  Interior rows evaluate them in pairs (see upwind5_pair); wall rows keep the
+        // scalar, order-selecting forms.
+        Real Fx0, F0, Fw0, Fzb_hi, Wu_hi, Ww_hi;
         if (!EDGE) {
-            const Pair<Real> fx = upwind5_pair(ux[3], bx, ux[4], bx + 1);
-            const Pair<Real> ua = centred4_pair(ux[1], ux[2], ux[3], ux[4], ux[2], ux[3], ux[4], ux[5]);
-            const Pair<Real> fu = upwind5_pair(ua.a, ux, ua.b, ux + 1);
-            const Pair<Real> ut = centred4_pair(uz[1], uz[2], uz[3], uz[4], u1z[0], u1z[1], u1z[2], u1z[3]);
-            const Pair<Real> fw = upwind5_pair(ut.a, wxr, ut.b, wxr + 1);
+            const Pair<Real> ce = centred4_pair(ux[1], ux[2], ux[3], ux[4], uz[1], uz[2], uz[3], uz[4]);   // u~ at centre i-1; u at (x-face i, z-face k)
+            const Pair<Real> fxu = upwind5_pair(ux[3], bx, ce.a, ux);
+            const Pair<Real> fwz = upwind5_pair(ce.b, wxr, wz[4], bz + 1);
             const Pair<Real> wa = centred4_pair(wxn[1], wxn[2], wxn[3], wxn[4], wz[2], wz[3], wz[4], wz[5]);
             const Pair<Real> fz = upwind5_pair(wa.a, uz + 1, wa.b, wz + 1);
-            Fx0 = fx.a; Fx1 = fx.b; F0 = fu.a; F1 = fu.b; Fw0 = fw.a; Fw1 = fw.b; Wu_hi = fz.a; Ww_hi = fz.b;
-            Fzb_hi = upwind5(wz[4], bz + 1);
+            Fx0 = fxu.a; F0 = fxu.b; Fw0 = fwz.a; Fzb_hi = fwz.b; Wu_hi = fz.a; Ww_hi = fz.b;
         } else {
             Fx0 = upwind5(ux[3], bx);
-            Fx1 = upwind5(ux[4], bx + 1);
             F0 = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);          // centre i-1
-            F1 = upwind5(centred4(ux[2], ux[3], ux[4], ux[5]), ux + 1);      // centre i
-            const Real ut0 = centred_ord(uz[1], uz[2], uz[3], uz[4], o_ce_face);        // x-face i,   z-face k
-            const Real ut1 = centred_ord(u1z[0], u1z[1], u1z[2], u1z[3], o_ce_face);    // x-face i+1, z-face k
-            Fw0 = upwind5(ut0, wxr);
-            Fw1 = upwind5(ut1, wxr + 1);
+            Fw0 = upwind5(centred_ord(uz[1], uz[2], uz[3], uz[4], o_ce_face), wxr);   // x-face i, z-face k
             Fzb_hi = top ? Real(0) : upwind_ord(wz[4], bz + 1, o_face_hi);
             Wu_hi = top ? Real(0) : upwind_ord(centred4(wxn[1], wxn[2], wxn[3], wxn[4]), uz + 1, o_face_hi);
             Ww_hi = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen), wz + 1, o_up_cen);
         }
+        // right x-fluxes = the neighbour's left ones
+        Real Fx1, F1, Fw1;
+#if defined(__CUDA_ARCH__)
+        Fx1 = __shfl_down_sync(0xffffffffu, Fx0, 1);
+        F1 = __shfl_down_sync(0xffffffffu, F0, 1);
+        Fw1 = __shfl_down_sync(0xffffffffu, Fw0, 1);
+        if (last_lane) {
+            Fx1 = E[(0 * NZ + k) * NEDGE + eci];
+            F1 = E[(1 * NZ + k) * NEDGE + eci];
+            Fw1 = E[(2 * NZ + k) * NEDGE + eci];
+        }
+#else
+        if (last_lane) {
+            Fx1 = E[(0 * NZ + k) * NEDGE + eci];
+            F1 = E[(1 * NZ + k) * NEDGE + eci];
+            Fw1 = E[(2 * NZ + k) * NEDGE + eci];
+        } else {
+            left_fluxes(c, i + 1, k, true, true, Fx1, F1, Fw1);
+        }
+#endif
 
         // ---- tracer ----
         const Real bdn = bot ? (Real(2) * tb - bz[3]) : bz[2];
@@ -439,10 +509,8 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         bz[6] = (kn < NZ) ? cb[kn * SX + i] : Real(0);
         uz[6] = (kn < NZ) ? cu[kn * SX + i] : Real(0);
         wz[6] = (kn <= NZ) ? cw[kn * SX + i] : Real(0);
-        u1z[0] = u1z[1]; u1z[1] = u1z[2]; u1z[2] = u1z[3];
-        u1z[3] = (k + 2 < NZ) ? cu[(k + 2) * SX + col[4]] : Real(0);
         RBC_UNROLL
-        for (int j = 0; j < 7; ++j) wxr[j] = wxn[j];
+        for (int j = 0; j < 6; ++j) wxr[j] = wxn[j];
     };
 
     RBC_UNROLL
@@ -928,7 +996,8 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
             if (SPLIT) { RBC_PHASE(phase_phy(tid, C, cur + OFF_B, X.R);) }
             const Real* gin = X.gm + ((stage & 1) ? 0 : NSTATE);      // stage s reads what stage s-1 wrote
             Real* gout = X.gm + ((stage & 1) ? NSTATE : 0);
-            RBC_PHASE((phase_tendency<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, gin, gout, dt, gam[stage], zet[stage], stage > 0));)
+            RBC_PHASE(phase_edge_fluxes(tid, cur, X.E);)
+            RBC_PHASE((phase_tendency<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, X.E, gin, gout, dt, gam[stage], zet[stage], stage > 0));)
             Real* P;
             if (NXT_GLOBAL) {
                 RBC_PHASE(phase_copy(tid, nxt, cur, NS_SM);)

@@ -43,7 +43,10 @@ struct SmemLayout {
     static constexpr size_t mid = Tb + sizeof(Real) * NX;
     static constexpr size_t tw48 = mid + sizeof(Real) * 2 * NX;
     static constexpr size_t tw96 = tw48 + sizeof(Real) * 96;
-    static constexpr size_t total = tw96 + sizeof(Real) * 96;
+    // left fluxes of the warps' first columns (phase_edge_fluxes): fp64 mode keeps them in the reduction scratch, idle until the epilogue
+    static constexpr size_t edge = kNxtGlobal ? red : tw96 + sizeof(Real) * 96;
+    static constexpr size_t total = tw96 + sizeof(Real) * 96 + (kNxtGlobal ? 0 : sizeof(Real) * NE);
+    static_assert(!kNxtGlobal || sizeof(Real) * NE <= sizeof(double) * NRED * NT, "edge-flux table must fit the reduction scratch");
     static_assert(total <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
     static constexpr size_t kAlign = 2 * sizeof(Real);     // one complex number per shared-memory access
     static_assert(s1 % kAlign == 0 && R % kAlign == 0 && tinv % kAlign == 0 && red % 8 == 0 && Tb % kAlign == 0, "alignment");
@@ -65,6 +68,7 @@ rbc2d_env_kernel(Consts<Real> C, Tables<Real> T, EnvIO<Real> io, Real* gm_all, R
     X.red = reinterpret_cast<double*>(smem + L::red);
     X.Tb = reinterpret_cast<Real*>(smem + L::Tb);
     X.mid = reinterpret_cast<Real*>(smem + L::mid);
+    X.E = reinterpret_cast<Real*>(smem + L::edge);
     X.tw48 = reinterpret_cast<Real*>(smem + L::tw48);
     X.tw96 = reinterpret_cast<Real*>(smem + L::tw96);
     X.gm = gm_all + (size_t)blockIdx.x * 2 * NSTATE;

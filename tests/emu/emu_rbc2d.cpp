@@ -20,7 +20,8 @@ static void run(const HostConfig& h, const HostWrappers& wr, double* cell_dist, 
     EnvIO<Real> io{state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, pressure, cell_dist};
     std::vector<Real> s0(NS_SM), s1(NS_SM), R(NR), Tb(NX), mid(2 * NX), gm(2 * NSTATE);
     std::vector<double> red(NRED * NT);
-    Ctx<Real> X{s0.data(), s1.data(), R.data(), Tb.data(), mid.data(), tw48.data(), tw96.data(), gm.data(), tinv.data(), red.data()};
+    std::vector<Real> E(NE);
+    Ctx<Real> X{s0.data(), s1.data(), R.data(), Tb.data(), mid.data(), tw48.data(), tw96.data(), gm.data(), tinv.data(), red.data(), E.data()};
     RunFlags F{C.nsub, 0, 1};
     for (int e = 0; e < B; ++e) {
         if (nxt_global) env_action_step<Real, SPLIT, true>(C, T, io, X, e, F);
