@@ -80,6 +80,7 @@ struct Grid {
     static constexpr int NR = (NZL + 1) * RSTR;          // Poisson scratch: NZL rows + the pressure row below the slab
     static constexpr int NRED = 11;                      // partial sums per thread in the epilogue
     static constexpr int NFIN = 16;                      // per-CTA totals exchanged through DSMEM
+    static constexpr int NEDGE = NX / 32, NE = 3 * NZL * NEDGE;   // left fluxes of the warps' first columns (phase_edge_fluxes)
     static_assert(NZ % CL == 0 && NZL % NSTRIP == 0, "slabs and strips must tile the grid");
     static_assert(RS >= 4, "a strip must be at least 4 rows (full-order fluxes at strip boundaries)");
     static_assert(NZL % 8 == 0, "two-sided Thomas sweeps the block in chunks of 4 rows from both ends");
@@ -94,7 +95,7 @@ template <typename Real>
 struct CtxX {
     unsigned char* base;        // device: this CTA's dynamic shared memory; host: arena of rank 0
     size_t arena_stride;        // host: bytes between the arenas of consecutive ranks (device: unused)
-    unsigned o_s0, o_s1, o_R, o_Tb, o_mid, o_ends, o_twN, o_tw2, o_red, o_fin, o_cfin, o_bars, o_tinv, o_phs;   // o_R / o_tinv == ~0u: see project(); o_phs: split mode only
+    unsigned o_s0, o_s1, o_R, o_Tb, o_mid, o_ends, o_twN, o_tw2, o_red, o_fin, o_cfin, o_bars, o_tinv, o_phs, o_edge;   // o_R / o_tinv == ~0u: see project(); o_phs: split mode only
     Real* gm;                   // global: [CL][2][NLOC] stage tendencies of this cluster (ping-pong slabs)
     Real* nxt_g;                // global: [CL][NS_SM] predicted state (fp64 mode) or nullptr
     // global tables, [CL] blocks each (build_tables_host)
@@ -286,6 +287,56 @@ RBC_HD void phase_store_state(int tid, int rank, const Real* RBC_RESTRICT sm, Re
 }
 
 // ------------------------------------------------------------------------------------------
+// shared x-fluxes (see rbc2d_core.h left_fluxes / phase_edge_fluxes): every thread evaluates the three LEFT fluxes of
+// its cell and takes the right ones from lane+1; lane 31 reads those of the next warp's first column from a table
+// filled by this prologue.  Local row lk of the slab, on-chip row lk + HALO; the u window may reach into the halo rows
+// (zero beyond the walls, like every window of the march).
+// ------------------------------------------------------------------------------------------
+template <typename G, typename Real>
+RBC_HD void left_fluxes(const Real* RBC_RESTRICT c, int i, int lk, int kg, bool want_bu, bool want_w, Real& fb, Real& fu, Real& fw)
+{
+    constexpr int SX = G::SX, H = G::HALO;
+    const Real* RBC_RESTRICT cb = c + G::OFF_B + (lk + H) * SX;
+    const Real* RBC_RESTRICT cu = c + G::OFF_U + (lk + H) * SX;
+    const Real* RBC_RESTRICT cw = c + G::OFF_W + (lk + H) * SX;
+    int col[6];
+    RBC_UNROLL
+    for (int j = 0; j < 6; ++j) col[j] = wrapx<G>(i - 3 + j);
+    if (want_bu) {
+        Real bx[6], ux[6];
+        RBC_UNROLL
+        for (int j = 0; j < 6; ++j) { bx[j] = cb[col[j]]; ux[j] = cu[col[j]]; }
+        fb = upwind5(ux[3], bx);
+        fu = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);
+    }
+    if (want_w) {
+        Real wx[6], uz[4];
+        RBC_UNROLL
+        for (int j = 0; j < 6; ++j) wx[j] = cw[col[j]];
+        RBC_UNROLL
+        for (int j = 0; j < 4; ++j) uz[j] = c[G::OFF_U + (lk + H - 2 + j) * SX + i];
+        fw = upwind5(centred_ord(uz[0], uz[1], uz[2], uz[3], ord_ce_face<G>(kg)), wx);
+    }
+}
+template <typename G, typename Real>
+RBC_HD void phase_edge_fluxes(int tid, int rank, const Real* RBC_RESTRICT c, Real* RBC_RESTRICT E)
+{
+    constexpr int NZL = G::NZL, NEDGE = G::NEDGE;
+    for (int q = tid; q < 2 * NZL * NEDGE; q += G::NT) {
+        const int item = q % (NZL * NEDGE), half = q / (NZL * NEDGE);
+        const int lk = item % NZL, ci = item / NZL;
+        Real fb = Real(0), fu = Real(0), fw = Real(0);
+        left_fluxes<G>(c, ci * 32, lk, rank * NZL + lk, half == 0, half == 1, fb, fu, fw);
+        if (half == 0) {
+            E[(0 * NZL + lk) * NEDGE + ci] = fb;
+            E[(1 * NZL + lk) * NEDGE + ci] = fu;
+        } else {
+            E[(2 * NZL + lk) * NEDGE + ci] = fw;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // phase: tendencies + RK3 substep of one strip of the slab (see rbc2d_core.h phase_tendency; same
 // arithmetic in the same order).  Halo rows make every window load unconditional; b* rows and the w* face
 // that the neighbouring slabs need before the next barrier are pushed into their buffers as they are made.
@@ -293,19 +344,22 @@ RBC_HD void phase_store_state(int tid, int rank, const Real* RBC_RESTRICT sm, Re
 template <typename G, bool ASYNC, bool SPLIT, typename Real>
 RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real* RBC_RESTRICT c, Real* RBC_RESTRICT n,
                            const PeerBuf<Real>& below_h, const PeerBuf<Real>& below_w, const PeerBuf<Real>& above_h,
-                           const Real* RBC_RESTRICT phy, const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm)
+                           const Real* RBC_RESTRICT phy, const Real* RBC_RESTRICT Tb, const Real* RBC_RESTRICT E, const Real* gm_in, Real* gm_out,
+                           Real dt, Real gam, Real zet, bool use_gm)
 {
-    constexpr int NX = G::NX, NZ = G::NZ, SX = G::SX, RS = G::RS, NT = G::NT, NZL = G::NZL, H = G::HALO;
+    constexpr int NX = G::NX, NZ = G::NZ, SX = G::SX, RS = G::RS, NT = G::NT, NZL = G::NZL, H = G::HALO, NEDGE = G::NEDGE;
     const int i = tid % NX, s = tid / NX, lk0 = s * RS, kg0 = rank * NZL + lk0;
+    const bool last_lane = (i & 31) == 31;
+    const int eci = ((i + 1) % NX) / 32;                 // table column of lane 31's right neighbour
     const Real* RBC_RESTRICT cb = c + G::OFF_B;
     const Real* RBC_RESTRICT cu = c + G::OFF_U;
     const Real* RBC_RESTRICT cw = c + G::OFF_W;
-    int col[7];
+    int col[6];
     RBC_UNROLL
-    for (int j = 0; j < 7; ++j) col[j] = wrapx<G>(i - 3 + j);
+    for (int j = 0; j < 6; ++j) col[j] = wrapx<G>(i - 3 + j);
 
     // sliding windows of the own column; index j <-> local row lk0 - 3 + j (on-chip row lk0 + j)
-    Real bz[7], uz[7], wz[7], u1z[4], wxr[7];
+    Real bz[7], uz[7], wz[7], wxr[6];
     RBC_UNROLL
     for (int j = 0; j < 7; ++j) {
         bz[j] = cb[(lk0 + j) * SX + i];
@@ -313,9 +367,7 @@ RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real*
         wz[j] = cw[(lk0 + j) * SX + i];
     }
     RBC_UNROLL
-    for (int j = 0; j < 4; ++j) u1z[j] = cu[(lk0 + 1 + j) * SX + col[4]];        // u(i+1, k-2 .. k+1)
-    RBC_UNROLL
-    for (int j = 0; j < 7; ++j) wxr[j] = cw[(lk0 + H) * SX + col[j]];            // w(i-3..i+3, face k0)
+    for (int j = 0; j < 6; ++j) wxr[j] = cw[(lk0 + H) * SX + col[j]];            // w(i-3..i+2, face k0)
 
     Real Fzb_lo = Real(0), Wu_lo = Real(0), Ww_lo = Real(0);
     if (kg0 >= 1) {                                       // strip boundaries are interior faces: full order
@@ -339,11 +391,11 @@ RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real*
             gnu = gm_in[(1 * RS + r + 1) * NT + tid];
             gnw = gm_in[(2 * RS + r + 1) * NT + tid];
         }
-        Real bx[7], ux[7], wxn[7];
+        Real bx[6], ux[6], wxn[6];
         RBC_UNROLL
-        for (int j = 0; j < 7; ++j) {
+        for (int j = 0; j < 6; ++j) {
             bx[j] = (j == 3) ? bz[3] : cb[lr * SX + col[j]];
-            ux[j] = (j == 3) ? uz[3] : ((j == 4) ? u1z[2] : cu[lr * SX + col[j]]);
+            ux[j] = (j == 3) ? uz[3] : cu[lr * SX + col[j]];
             wxn[j] = (j == 3) ? wz[4] : cw[(lr + 1) * SX + col[j]];
         }
         const bool top = EDGE && (k == NZ - 1);
@@ -353,9 +405,31 @@ RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real*
         const int o_up_cen = EDGE ? ord_up_cen<G>(k) : 5;
         const int o_ce_cen = EDGE ? ord_ce_cen<G>(k) : 4;
 
-        // ---- tracer ----
+        // left x-fluxes; the right ones are the neighbour's left ones
         const Real Fx0 = upwind5(ux[3], bx);
-        const Real Fx1 = upwind5(ux[4], bx + 1);
+        const Real F0 = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);
+        const Real Fw0 = upwind5(centred_ord(uz[1], uz[2], uz[3], uz[4], o_ce_face), wxr);
+        Real Fx1, F1, Fw1;
+#if defined(__CUDA_ARCH__)
+        Fx1 = __shfl_down_sync(0xffffffffu, Fx0, 1);
+        F1 = __shfl_down_sync(0xffffffffu, F0, 1);
+        Fw1 = __shfl_down_sync(0xffffffffu, Fw0, 1);
+        if (last_lane) {
+            Fx1 = E[(0 * NZL + lk) * NEDGE + eci];
+            F1 = E[(1 * NZL + lk) * NEDGE + eci];
+            Fw1 = E[(2 * NZL + lk) * NEDGE + eci];
+        }
+#else
+        if (last_lane) {
+            Fx1 = E[(0 * NZL + lk) * NEDGE + eci];
+            F1 = E[(1 * NZL + lk) * NEDGE + eci];
+            Fw1 = E[(2 * NZL + lk) * NEDGE + eci];
+        } else {
+            left_fluxes<G>(c, i + 1, lk, k, true, true, Fx1, F1, Fw1);
+        }
+#endif
+
+        // ---- tracer ----
         const Real Fzb_hi = top ? Real(0) : upwind_ord(wz[4], bz + 1, o_face_hi);
         const Real bdn = bot ? (Real(2) * tb - bz[3]) : bz[2];
         const Real bup = top ? (Real(2) * C.b_top - bz[3]) : bz[4];
@@ -363,8 +437,6 @@ RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real*
                         (bup - Real(2) * bz[3] + bdn) * kdz;
 
         // ---- u ----
-        const Real F0 = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);
-        const Real F1 = upwind5(centred4(ux[2], ux[3], ux[4], ux[5]), ux + 1);
         const Real Wu_hi = top ? Real(0) : upwind_ord(centred4(wxn[1], wxn[2], wxn[3], wxn[4]), uz + 1, o_face_hi);
         const Real udn = bot ? -uz[3] : uz[2];
         const Real uup = top ? -uz[3] : uz[4];
@@ -373,10 +445,6 @@ RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real*
         if (SPLIT) Gu -= (phy[lk * G::RSTR + i] - phy[lk * G::RSTR + col[2]]) * C.idx;
 
         // ---- w (face k; face 0 is the wall) ----
-        const Real ut0 = centred_ord(uz[1], uz[2], uz[3], uz[4], o_ce_face);
-        const Real ut1 = centred_ord(u1z[0], u1z[1], u1z[2], u1z[3], o_ce_face);
-        const Real Fw0 = upwind5(ut0, wxr);
-        const Real Fw1 = upwind5(ut1, wxr + 1);
         const Real Ww_hi = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen), wz + 1, o_up_cen);
         Real Gw = (Fw0 - Fw1) * C.idx + (Ww_lo - Ww_hi) * C.idz + (wxr[4] - Real(2) * wxr[3] + wxr[2]) * ndx +
                   (wz[4] - Real(2) * wz[3] + wz[2]) * ndz;
@@ -409,10 +477,8 @@ RBC_HD void phase_tendency(int tid, int rank, const Consts<Real>& C, const Real*
             bz[6] = cb[(lr + 4) * SX + i];
             uz[6] = cu[(lr + 4) * SX + i];
             wz[6] = cw[(lr + 4) * SX + i];
-            u1z[0] = u1z[1]; u1z[1] = u1z[2]; u1z[2] = u1z[3];
-            u1z[3] = cu[(lr + 2) * SX + col[4]];
             RBC_UNROLL
-            for (int j = 0; j < 7; ++j) wxr[j] = wxn[j];
+            for (int j = 0; j < 6; ++j) wxr[j] = wxn[j];
         }
     };
 
@@ -947,6 +1013,7 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
         for (int stage = 0; stage < 3; ++stage) {
             const int in_slab = (stage & 1) ? 0 : 1, out_slab = 1 - in_slab;
             if (SPLIT) hydrostatic<G, Real, NXT_GLOBAL>(C, X, o_cur, my_rank, S);
+            RBX_PHASE_L(G, phase_edge_fluxes<G>(tid, rank, RBX_PTR(o_cur), RBX_PTR(X.o_edge));)
             RBX_PHASE_X(G, ASYNC,
                 Real* cur = RBX_PTR(o_cur);
                 Real* nxt;
@@ -965,7 +1032,7 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
                     above_h = make_peer<ASYNC, Real>(X, smb, o_nxt, hb, rank, rank + 1, CL > 1 && rank < CL - 1);
                 }
                 Real* gmr = X.gm + (size_t)rank * 2 * G::NLOC;
-                phase_tendency<G, ASYNC, SPLIT>(tid, rank, C, cur, nxt, below_h, below_w, above_h, SPLIT ? RBX_PTR(X.o_R) : nullptr, RBX_PTR(X.o_Tb), gmr + in_slab * G::NLOC,
+                phase_tendency<G, ASYNC, SPLIT>(tid, rank, C, cur, nxt, below_h, below_w, above_h, SPLIT ? RBX_PTR(X.o_R) : nullptr, RBX_PTR(X.o_Tb), RBX_PTR(X.o_edge), gmr + in_slab * G::NLOC,
                                          gmr + out_slab * G::NLOC, dt, gam[stage], zet[stage], stage > 0);
             )
             unsigned o_p;
@@ -1293,13 +1360,14 @@ struct SmemLayoutX {
                   "column totals do not fit the reduction scratch");
     static constexpr size_t twN = al(bars + 8 * 2 * NCHAN + ((SPLIT && !kPhsInRed) ? sizeof(Real) * G::CL * G::NX : 0));
     static constexpr size_t tw2 = al(twN + sizeof(Real) * 2 * G::NH);
-    static constexpr size_t total = al(tw2 + sizeof(Real) * 2 * G::NH);
+    static constexpr size_t edge = al(tw2 + sizeof(Real) * 2 * G::NH);
+    static constexpr size_t total = al(edge + sizeof(Real) * G::NE);
     template <typename Ctx>
     static void fill(Ctx& X)
     {
         X.o_s0 = (unsigned)s0; X.o_s1 = (unsigned)s1; X.o_R = OWN_R ? (unsigned)R : ~0u; X.o_tinv = OWN_R ? ~0u : (unsigned)tinv; X.o_red = kRedSeparate ? (unsigned)red : ~0u; X.o_fin = (unsigned)fin;
         X.o_cfin = (unsigned)cfin; X.o_Tb = (unsigned)Tb; X.o_mid = (unsigned)mid; X.o_ends = (unsigned)ends; X.o_bars = (unsigned)bars;
-        X.o_phs = SPLIT ? (unsigned)phs : ~0u; X.o_twN = (unsigned)twN; X.o_tw2 = (unsigned)tw2;
+        X.o_phs = SPLIT ? (unsigned)phs : ~0u; X.o_twN = (unsigned)twN; X.o_tw2 = (unsigned)tw2; X.o_edge = (unsigned)edge;
     }
 };
 

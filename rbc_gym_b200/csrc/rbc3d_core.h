@@ -166,6 +166,22 @@ RBC_HD void phase_phy3(int tid, const Consts3<Real>& C, const Real* cb, Real* ph
 // ------------------------------------------------------------------------------------------
 // phase: tendencies + RK3 substep; reads `cur`, writes the predicted state `nxt`, stores G for the next stage
 // ------------------------------------------------------------------------------------------
+// The x-direction flux through the right face of column i is the flux through the left face of column i+1, and with
+// NX = 32 the x-neighbours of a cell are the neighbouring lanes of its warp (periodic): on the device every thread
+// evaluates only the left fluxes and takes the right ones from lane+1 with a shuffle — 4 of the 20 upwind
+// reconstructions per cell, the u(i+1, .) windows and their loads go away.  The host emulator (threads run one after
+// the other) evaluates both faces; the arithmetic is identical.
+#if defined(__CUDA_ARCH__)
+#define RBC3_SHARE_X 1
+template <typename Real>
+__device__ __forceinline__ Real from_next_lane(Real v) { return __shfl_sync(0xffffffffu, v, (threadIdx.x + 1) & 31); }
+#else
+#define RBC3_SHARE_X 0
+template <typename Real>
+inline Real from_next_lane(Real v) { return v; }
+#endif
+static_assert(NX == 32, "x-flux sharing maps one x-row of cells onto one warp");
+
 template <typename Real, bool SPLIT, bool TILE>
 RBC_HD void tendency3_column(const Consts3<Real>& C, const Real* RBC_RESTRICT src, Real* nxt, const Real* RBC_RESTRICT phy,
                              const Real* RBC_RESTRICT Tb, const Real* gm_in, Real* gm_out, Real dt, Real gam, Real zet, bool use_gm,
@@ -248,7 +264,7 @@ RBC_HD void tendency3_column(const Consts3<Real>& C, const Real* RBC_RESTRICT sr
             const int oc_cen = EDGE ? o_ce_cen(k) : 4;
 
             // ---- tracer ----
-            const Real Fx0 = upwind5(ux[3], bx), Fx1 = upwind5(ux[4], bx + 1);
+            const Real Fx0 = upwind5(ux[3], bx), Fx1 = RBC3_SHARE_X ? from_next_lane(Fx0) : upwind5(ux[4], bx + 1);
             const Real Fy0 = upwind5(vy[3], by), Fy1 = upwind5(vy[4], by + 1);
             const Real Fzb_hi = top ? Real(0) : upwind_ord(wz[4], bz + 1, of_hi);
             const Real bdn = bot ? (Real(2) * tb - bz[3]) : bz[2];
@@ -258,7 +274,7 @@ RBC_HD void tendency3_column(const Consts3<Real>& C, const Real* RBC_RESTRICT sr
                                        (bup - Real(2) * bz[3] + bdn) * C.idz2);
             // ---- u at (x-face i, j, k) ----
             const Real uF0 = upwind5(centred4(ux[1], ux[2], ux[3], ux[4]), ux);
-            const Real uF1 = upwind5(centred4(ux[2], ux[3], ux[4], ux[5]), ux + 1);
+            const Real uF1 = RBC3_SHARE_X ? from_next_lane(uF0) : upwind5(centred4(ux[2], ux[3], ux[4], ux[5]), ux + 1);
             const Real uG0 = upwind5(centred4(vx[1], vx[2], vx[3], vx[4]), uy);          // (x-face i, y-face j)
             const Real uG1 = upwind5(centred4(vc0, vc1, vc2, vc3), uy + 1);              // (x-face i, y-face j+1)
             const Real Wu_hi = top ? Real(0) : upwind_ord(centred4(wxn[1], wxn[2], wxn[3], wxn[4]), uz + 1, of_hi);
@@ -268,7 +284,7 @@ RBC_HD void tendency3_column(const Consts3<Real>& C, const Real* RBC_RESTRICT sr
                               (uup - Real(2) * uz[3] + udn) * C.idz2);
             // ---- v at (i, y-face j, k) ----
             const Real vF0 = upwind5(centred4(uy[1], uy[2], uy[3], uy[4]), vx);          // (x-face i,   y-face j)
-            const Real vF1 = upwind5(centred4(uc0, uc1, uc2, uc3), vx + 1);              // (x-face i+1, y-face j)
+            const Real vF1 = RBC3_SHARE_X ? from_next_lane(vF0) : upwind5(centred4(uc0, uc1, uc2, uc3), vx + 1);   // (x-face i+1, y-face j)
             const Real vG0 = upwind5(centred4(vy[1], vy[2], vy[3], vy[4]), vy);
             const Real vG1 = upwind5(centred4(vy[2], vy[3], vy[4], vy[5]), vy + 1);
             const Real Wv_hi = top ? Real(0) : upwind_ord(centred4(wyn[1], wyn[2], wyn[3], wyn[4]), vz + 1, of_hi);
@@ -285,7 +301,7 @@ RBC_HD void tendency3_column(const Consts3<Real>& C, const Real* RBC_RESTRICT sr
             // ---- w at (i, j, z-face k); face 0 is the wall ----
             const Real ut0 = centred_ord(uz[1], uz[2], uz[3], uz[4], oc_face), ut1 = centred_ord(u1z[0], u1z[1], u1z[2], u1z[3], oc_face);
             const Real vt0 = centred_ord(vz[1], vz[2], vz[3], vz[4], oc_face), vt1 = centred_ord(v1z[0], v1z[1], v1z[2], v1z[3], oc_face);
-            const Real wF0 = upwind5(ut0, wx), wF1 = upwind5(ut1, wx + 1);
+            const Real wF0 = upwind5(ut0, wx), wF1 = RBC3_SHARE_X ? from_next_lane(wF0) : upwind5(ut1, wx + 1);
             const Real wG0 = upwind5(vt0, wy), wG1 = upwind5(vt1, wy + 1);
             const Real Ww_hi = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], oc_cen), wz + 1, ou_cen);
             Real Gw = -((wF1 - wF0) * C.idx + (wG1 - wG0) * C.idy + (Ww_hi - Ww_lo) * C.idz) +
