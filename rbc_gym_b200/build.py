@@ -40,6 +40,20 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Build the library if a source is newer than it.  Safe to call from several processes at once (one rank per GPU
+    under torchrun): the check and the build run under an exclusive file lock, objects and the library are written to
+    temporary names and renamed into place, so no process can ever dlopen a half-written file."""
+    import fcntl
+    OBJ_DIR.mkdir(exist_ok=True)
+    with open(OBJ_DIR / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
     if not force and not needs_build():
         return LIB
     base = [find_nvcc(), *NVCC_FLAGS]
@@ -49,29 +63,34 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     host = shutil.which("g++")
     if host:
         base += ["-ccbin", host]
-    OBJ_DIR.mkdir(exist_ok=True)
     newest_header = max(p.stat().st_mtime for p in HEADERS)
 
     def compile_one(src: Path) -> Path:
         obj = OBJ_DIR / (src.stem + ".o")
         if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, newest_header):
             return obj
-        cmd = base + ["-c", "-o", str(obj), str(src)]
+        tmp = obj.with_suffix(f".{os.getpid()}.tmp.o")
+        cmd = base + ["-c", "-o", str(tmp), str(src)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
         if res.returncode != 0:
+            tmp.unlink(missing_ok=True)
             raise RuntimeError(f"nvcc failed ({res.returncode}): {' '.join(cmd)}")
+        os.replace(tmp, obj)
         return obj
 
     # one translation unit per kernel family, compiled concurrently (the unrolled kernels take ~30-60 s each)
     with ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = base + ["-shared", "-o", str(LIB), *map(str, objs)]
+    tmp_lib = LIB.with_suffix(f".{os.getpid()}.tmp.so")
+    cmd = base + ["-shared", "-o", str(tmp_lib), *map(str, objs)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
+        tmp_lib.unlink(missing_ok=True)
         raise RuntimeError(f"nvcc link failed ({res.returncode}): {' '.join(cmd)}")
+    os.replace(tmp_lib, LIB)
     return LIB
 
 
