@@ -312,7 +312,7 @@ RBC_HD void tendency3_column(const Consts3<Real>& C, const Real* RBC_RESTRICT sr
 
             // ---- RK3 substep ----
             const int o = k * NCOL + c;
-            gm_out[0 * NC + o] = Gb; gm_out[1 * NC + o] = Gu; gm_out[2 * NC + o] = Gv; gm_out[3 * NC + o] = Gw;
+            if (gm_out != nullptr) { gm_out[0 * NC + o] = Gb; gm_out[1 * NC + o] = Gu; gm_out[2 * NC + o] = Gv; gm_out[3 * NC + o] = Gw; }   // last stage: never read
             nxt[GB + o] = bz[3] + dt * (gam * Gb + zet * g0[0]);
             nxt[GU + o] = uz[3] + dt * (gam * Gu + zet * g0[1]);
             nxt[GV + o] = vz[3] + dt * (gam * Gv + zet * g0[2]);
@@ -639,10 +639,10 @@ RBC_HD void env_action_step3(const Consts3<Real>& C, const EnvIO3<Real>& io, con
             if (TILED) {
                 for (int h = 0; h < 2; ++h) {
                     RBC3_PHASE(phase_load_tile3(tid, cur, X.tile, h);)
-                    RBC3_PHASE((phase_tendency3_tile<Real, false>(tid, C, X.tile, nxt, X.R, X.Tb, gin, gout, dt, gam[stage], zet[stage], stage > 0, h));)
+                    RBC3_PHASE((phase_tendency3_tile<Real, false>(tid, C, X.tile, nxt, X.R, X.Tb, gin, stage < 2 ? gout : nullptr, dt, gam[stage], zet[stage], stage > 0, h));)
                 }
             } else {
-                RBC3_PHASE((phase_tendency3<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, gin, gout, dt, gam[stage], zet[stage], stage > 0));)
+                RBC3_PHASE((phase_tendency3<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, gin, stage < 2 ? gout : nullptr, dt, gam[stage], zet[stage], stage > 0));)
             }
             project3(C, X, nxt);
             cur = nxt;
