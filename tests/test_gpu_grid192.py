@@ -119,6 +119,22 @@ def test_env_class_at_192x128(B):
     env.close()
 
 
+def test_env_class_at_192x128_with_pressure_channels(B):
+    """`pressure=True` (rbc2D.py:57,94-97: two unbounded extra channels) on the config-3 grid."""
+    from rbc_gym_b200.envs.rbc2d import RayleighBenardConvection2DEnv
+    env = RayleighBenardConvection2DEnv(rayleigh_number=1_000_000, state_shape=[NZ, NX], observation_shape=[8, 48],
+                                        heater_duration=0.15, dt_solver=DTS, pressure=True)
+    obs, info = env.reset(seed=42)
+    assert obs.shape == (5, 8, 48) and info["state"].shape == (5, NZ, NX) and env.observation_space.shape == (5, 8, 48)
+    obs, reward, terminated, truncated, info = env.step(env.action_space.sample())
+    assert obs.shape == (5, 8, 48) and np.all(np.isfinite(obs)) and np.isfinite(reward)
+    st = info["state"]
+    np.testing.assert_array_equal(obs[3:], st[3:, ::16, ::4])
+    assert abs(st[4].mean()) < 1e-4                              # pNHS in the zero-mean gauge
+    assert np.all(np.diff(st[3].mean(axis=1)) > 0)               # pHY' integrates b > 0 downwards from the top wall
+    env.close()
+
+
 def test_unregistered_grid_is_rejected(B):
     with pytest.raises(RuntimeError, match="registered grids"):
         B.Sim2D(1, ra=1e5, state_shape=(100, 200))
