@@ -184,6 +184,7 @@ struct rbc2d_sim {
     static constexpr int kRing = 64;
     cudaEvent_t ev0[kRing] = {}, ev1[kRing] = {};
     int64_t timed_launches = 0;
+    HostPipe pipe;                                                     // rbc2d_step_host
 };
 
 template <typename Real>
@@ -277,6 +278,27 @@ static int dispatch_env(rbc2d_sim* s, const float* actions, float* obs, float* r
                           : launch_env<float, false>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it);
     return split ? launch_env<double, true>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it)
                  : launch_env<double, false>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it);
+}
+
+int rbc_pipe_prepare(HostPipe* p, int B)
+{
+    if (p->copy && p->n == B) return 0;
+    rbc_pipe_destroy(p);
+    CK(cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking));
+    for (int c = 0; c < HostPipe::kMaxChunks; ++c) CK(cudaEventCreateWithFlags(&p->done[c], cudaEventDisableTiming));
+    std::vector<int> h(B);
+    for (int i = 0; i < B; ++i) h[i] = i;
+    CK(cudaMalloc((void**)&p->iota, (size_t)B * sizeof(int)));
+    CK(cudaMemcpy(p->iota, h.data(), (size_t)B * sizeof(int), cudaMemcpyHostToDevice));
+    p->n = B;
+    return 0;
+}
+void rbc_pipe_destroy(HostPipe* p)
+{
+    if (p->copy) cudaStreamDestroy(p->copy);
+    for (int c = 0; c < HostPipe::kMaxChunks; ++c) if (p->done[c]) cudaEventDestroy(p->done[c]);
+    if (p->iota) cudaFree(p->iota);
+    *p = HostPipe();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -381,6 +403,7 @@ int rbc2d_destroy(rbc2d_sim* s)
         if (s->ev1[i]) cudaEventDestroy(s->ev1[i]);
     }
     rbc2dx_api::destroy(s->plan);
+    rbc_pipe_destroy(&s->pipe);
     delete s;
     return 0;
 }
@@ -500,14 +523,34 @@ int rbc2d_step_host(rbc2d_sim* s, const float* actions, float* obs, float* rewar
     const size_t B = s->B;
     const size_t nobs = (size_t)s->channels * s->cfg.obs_nz * s->cfg.obs_nx;
     CK(cudaMemcpyAsync(s->actions, actions, B * s->cfg.heaters * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    int rc = rbc2d_step_dev(s, s->actions, s->obs, s->reward, s->nu_s, s->nu_o, s->trunc, s->nan);
+    // chunks of whole waves of the persistent grid; the copy stream drains chunk c while chunk c+1 computes
+    const int lanes = s->plan ? rbc2dx_api::grid_ctas(s->plan, 1 << 30) / rbc2dx_api::cluster_size(s->plan) : s->grid;
+    int len[HostPipe::kMaxChunks];
+    const int nch = rbc_pipe_chunks(s->B, lanes, len);
+    int rc = rbc_pipe_prepare(&s->pipe, s->B);
     if (rc) return rc;
-    if (obs) CK(cudaMemcpyAsync(obs, s->obs, B * nobs * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    if (reward) CK(cudaMemcpyAsync(reward, s->reward, B * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    if (nu_s) CK(cudaMemcpyAsync(nu_s, s->nu_s, B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    if (nu_o) CK(cudaMemcpyAsync(nu_o, s->nu_o, B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    if (trunc) CK(cudaMemcpyAsync(trunc, s->trunc, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    if (nan) CK(cudaMemcpyAsync(nan, s->nan, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    Consts<float> tmp = make_consts<float>(s->hc);
+    RunFlags F{tmp.nsub, 0, 1};
+    const int slot = (int)(s->timed_launches % rbc2d_sim::kRing);
+    CK(cudaEventRecord(s->ev0[slot], s->stream));             // the step's kernel time = span of its chunks
+    size_t off = 0;
+    for (int c = 0; c < nch; ++c) {
+        const size_t n = (size_t)len[c];
+        rc = dispatch_env(s, s->actions, s->obs, s->reward, s->nu_s, s->nu_o, s->trunc, s->nan, s->pipe.iota + off, (int)n, F, false);
+        if (rc) return rc;
+        if (c == nch - 1) { CK(cudaEventRecord(s->ev1[slot], s->stream)); s->timed_launches += 1; }
+        CK(cudaEventRecord(s->pipe.done[c], s->stream));
+        CK(cudaStreamWaitEvent(s->pipe.copy, s->pipe.done[c], 0));
+        cudaStream_t cs = s->pipe.copy;
+        if (obs) CK(cudaMemcpyAsync(obs + off * nobs, s->obs + off * nobs, n * nobs * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        if (reward) CK(cudaMemcpyAsync(reward + off, s->reward + off, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        if (nu_s) CK(cudaMemcpyAsync(nu_s + off, s->nu_s + off, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+        if (nu_o) CK(cudaMemcpyAsync(nu_o + off, s->nu_o + off, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+        if (trunc) CK(cudaMemcpyAsync(trunc + off, s->trunc + off, n * sizeof(int), cudaMemcpyDeviceToHost, cs));
+        if (nan) CK(cudaMemcpyAsync(nan + off, s->nan + off, n * sizeof(int), cudaMemcpyDeviceToHost, cs));
+        off += n;
+    }
+    CK(cudaStreamSynchronize(s->pipe.copy));
     CK(cudaStreamSynchronize(s->stream));
     return 0;
 }

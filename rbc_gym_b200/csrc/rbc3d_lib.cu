@@ -80,6 +80,7 @@ struct rbc3d_sim {
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    HostPipe pipe;                   // rbc3d_step_host
 };
 
 // fp32 without the hydrostatic split runs the tiled tendency phase (the fp64 tile would not fit next to the scratch)
@@ -206,6 +207,7 @@ int rbc3d_destroy(rbc3d_sim* s)
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    rbc_pipe_destroy(&s->pipe);
     delete s;
     return 0;
 }
@@ -303,13 +305,32 @@ int rbc3d_step_host(rbc3d_sim* s, const float* actions, float* obs, float* rewar
     const size_t B = s->B, na = (size_t)s->cfg.heaters * s->cfg.heaters, nobs = 4 * (size_t)NC;
     if (obs && !s->obs) CK(cudaMalloc((void**)&s->obs, B * nobs * sizeof(float)));
     CK(cudaMemcpyAsync(s->actions, actions, B * na * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    int rc = rbc3d_step_dev(s, s->actions, obs ? s->obs : nullptr, s->reward, s->nu, s->trunc, s->nan);
+    // chunks of whole waves of the persistent grid; the copy stream drains chunk c (262 KB of observation per environment)
+    // while chunk c+1 computes
+    int len[HostPipe::kMaxChunks];
+    const int nch = rbc_pipe_chunks(s->B, s->grid, len);
+    int rc = rbc_pipe_prepare(&s->pipe, s->B);
     if (rc) return rc;
-    if (obs) CK(cudaMemcpyAsync(obs, s->obs, B * nobs * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    if (reward) CK(cudaMemcpyAsync(reward, s->reward, B * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    if (nusselt) CK(cudaMemcpyAsync(nusselt, s->nu, B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    if (trunc) CK(cudaMemcpyAsync(trunc, s->trunc, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    if (nan) CK(cudaMemcpyAsync(nan, s->nan, B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    Consts3<float> tmp = make_consts3<float>(s->hc);
+    RunFlags3 F{tmp.nsub, 0, 1};
+    CK(cudaEventRecord(s->ev0, s->stream));
+    size_t off = 0;
+    for (int c = 0; c < nch; ++c) {
+        const size_t n = (size_t)len[c];
+        rc = dispatch3(s, s->actions, obs ? s->obs : nullptr, s->reward, s->nu, s->trunc, s->nan, s->pipe.iota + off, (int)n, F, false, obs != nullptr);
+        if (rc) return rc;
+        if (c == nch - 1) { CK(cudaEventRecord(s->ev1, s->stream)); s->timed = true; }
+        CK(cudaEventRecord(s->pipe.done[c], s->stream));
+        CK(cudaStreamWaitEvent(s->pipe.copy, s->pipe.done[c], 0));
+        cudaStream_t cs = s->pipe.copy;
+        if (obs) CK(cudaMemcpyAsync(obs + off * nobs, s->obs + off * nobs, n * nobs * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        if (reward) CK(cudaMemcpyAsync(reward + off, s->reward + off, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        if (nusselt) CK(cudaMemcpyAsync(nusselt + off, s->nu + off, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+        if (trunc) CK(cudaMemcpyAsync(trunc + off, s->trunc + off, n * sizeof(int), cudaMemcpyDeviceToHost, cs));
+        if (nan) CK(cudaMemcpyAsync(nan + off, s->nan + off, n * sizeof(int), cudaMemcpyDeviceToHost, cs));
+        off += n;
+    }
+    CK(cudaStreamSynchronize(s->pipe.copy));
     CK(cudaStreamSynchronize(s->stream));
     return 0;
 }

@@ -55,6 +55,31 @@ def test_3d_batch_larger_than_grid_is_replica_exact():
     sim.close()
 
 
+def test_3d_host_step_in_overlapped_chunks_equals_device_step():
+    """rbc3d_step_host: chunks of whole waves, observations (262 KB per environment) copied out on a second stream while the
+    next chunk computes; same outputs as the device-buffer step."""
+    import torch
+    from rbc_gym_b200 import backend
+    P = O3.make_params(2500)
+    base = [backend.pack_fields3(*(x[None] for x in random_state(P, s))) for s in (4, 5, 6)]
+    n = 450                                                   # 4 waves of 148 CTAs
+    fields = np.concatenate([base[i % 3] for i in range(n)])
+    acts = np.random.default_rng(3).uniform(-1, 1, (n, 8, 8)).astype(np.float32)
+    sims = [backend.Sim3D(n, ra=2500, heater_duration=0.02, precision=32) for _ in range(2)]
+    for sim in sims:
+        sim.reset_from_fields(fields, project=False)
+    obs, rew, nu, tr, nan = sims[0].step(torch.from_numpy(acts).cuda())
+    out = {"obs": np.zeros((n, 4, 16, 32, 32), np.float32), "reward": np.zeros(n, np.float32), "nusselt": np.zeros(n),
+           "truncated": np.zeros(n, np.int32), "nan": np.zeros(n, np.int32)}
+    sims[1].step_host(acts, out)
+    np.testing.assert_array_equal(out["obs"], obs.cpu().numpy())
+    np.testing.assert_array_equal(out["reward"], rew.cpu().numpy())
+    np.testing.assert_array_equal(out["nusselt"], nu.cpu().numpy())
+    assert np.array_equal(sims[0].fields(), sims[1].fields())
+    for sim in sims:
+        sim.close()
+
+
 def test_3d_env_reference_api():
     import rbc_gym_b200 as R
     env = R.make(R.ENV_ID_3D, rayleigh_number=2500)

@@ -316,3 +316,23 @@ def test_config3_full_batch_properties(B):
     for i in range(4, n):
         assert np.array_equal(f[i], f[i % 4])
     sim.close()
+
+
+def test_host_step_in_overlapped_chunks_on_the_cluster_grid(B):
+    """Three waves of resident clusters -> three chunks; host-buffer step == device-buffer step."""
+    import torch
+    n = 90
+    base = [smooth_state(NX, NZ, seed=s) for s in (0, 1, 2)]
+    fields = np.concatenate([B.pack_fields(*(a[None] for a in base[i % 3])) for i in range(n)])
+    acts = np.random.default_rng(2).uniform(-1, 1, (n, 12)).astype(np.float32)
+    sims = [B.Sim2D(n, ra=RA, dt_action=0.045, dt_solver=DTS, state_shape=(NZ, NX)) for _ in range(2)]
+    for sim in sims:
+        sim.reset_from_fields(fields, project=False)
+    obs, rew, nus, nuo, *_ = sims[0].step(torch.from_numpy(acts).cuda())
+    out = sims[1].step_host(acts)
+    np.testing.assert_array_equal(out["obs"], obs.cpu().numpy())
+    np.testing.assert_array_equal(out["reward"], rew.cpu().numpy())
+    np.testing.assert_array_equal(out["nu_obs"], nuo.cpu().numpy())
+    assert np.array_equal(sims[0].fields(), sims[1].fields())
+    for sim in sims:
+        sim.close()

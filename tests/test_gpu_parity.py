@@ -138,6 +138,35 @@ def test_host_buffer_entry_point_equals_device_entry_point(B, ckpt_ra1e5):
     s1.close(); s2.close()
 
 
+def test_host_step_in_overlapped_chunks_equals_device_step(B, ckpt_ra1e5):
+    """rbc2d_step_host launches a multi-wave batch in chunks of whole waves and copies each chunk out on a second stream
+    while the next one computes: same outputs as the single device-buffer launch, over two consecutive steps, into pinned
+    buffers; the step's kernel time spans the chunks."""
+    import torch
+    n = 700                                                   # 5 waves of 148 CTAs -> 4 chunks
+    eps = [i % 20 for i in range(n)]
+    rng = np.random.default_rng(5)
+    s1 = make_sim(B, n, ckpt_ra1e5, eps, ra=1e5, dt_action=0.09, precision=32)
+    s2 = make_sim(B, n, ckpt_ra1e5, eps, ra=1e5, dt_action=0.09, precision=32)
+    out = s2.alloc_host_outputs(pinned=True)
+    for _ in range(2):
+        acts = rng.uniform(-1, 1, (n, 12)).astype(np.float32)
+        obs, rew, nus, nuo, tr, nan = s1.step(torch.from_numpy(acts).cuda())
+        s2.step_host(acts, out)
+        np.testing.assert_array_equal(out["obs"], obs.cpu().numpy())
+        np.testing.assert_array_equal(out["reward"], rew.cpu().numpy())
+        np.testing.assert_array_equal(out["nu_state"], nus.cpu().numpy())
+        np.testing.assert_array_equal(out["nu_obs"], nuo.cpu().numpy())
+        np.testing.assert_array_equal(out["truncated"], tr.cpu().numpy())
+        np.testing.assert_array_equal(out["nan"], nan.cpu().numpy())
+    assert np.array_equal(s1.fields(), s2.fields())
+    t1, c1 = s1.info()
+    t2, c2 = s2.info()
+    assert np.array_equal(t1, t2) and np.array_equal(c1, c2)
+    assert 0.0 < s2.last_step_kernel_ms() < 10 * s1.last_step_kernel_ms() + 1.0
+    s1.close(); s2.close()
+
+
 def test_reset_observe_and_state_layout(B, ckpt_ra1e5):
     import torch
     c = ckpt_ra1e5
