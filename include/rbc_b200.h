@@ -110,7 +110,10 @@ int rbc2d_reset_from_fields_dev(rbc2d_sim* sim, const int32_t* env_ids_dev, cons
  *   nu_state/obs [B] float64                         (info["nusselt_state"], info["nusselt_obs"])
  *   truncated    [B] int32: t >= episode_length      (rbc2D.py:178-180)
  *   nan          [B] int32: step_contains_NaNs       (rbc_sim2D.jl:223-228)
- * Any output pointer may be NULL except obs. */
+ * Any output pointer may be NULL except obs.
+ * The _host variant copies the actions in and every requested output out inside the call and returns when they have
+ * landed; the batch runs in wave-aligned chunks whose outputs are copied on a second stream while the next chunk
+ * computes (page-locked host buffers make that overlap effective; pageable ones work, serialised by the driver). */
 int rbc2d_step_dev(rbc2d_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, double* nu_state_dev,
                    double* nu_obs_dev, int32_t* truncated_dev, int32_t* nan_dev);
 int rbc2d_step_host(rbc2d_sim* sim, const float* actions_host, float* obs_host, float* reward_host, double* nu_state_host,
