@@ -406,8 +406,11 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
     // previous-stage tendencies live in per-CTA global slabs [field][r][tid] (coalesced; one slab is read,
     // the other written, so loads never alias stores).  They are fetched one row ahead so their L2 latency
     // hides behind a whole row of arithmetic (stage 1 has zet = 0 and must not read).
-    Real gnb = Real(0), gnu = Real(0), gnw = Real(0);
-    if (use_gm) { gnb = gm_in[(0 * RS) * NT + tid]; gnu = gm_in[(1 * RS) * NT + tid]; gnw = gm_in[(2 * RS) * NT + tid]; }
+    Real gnb = Real(0), gnu = Real(0), gnw = Real(0), gmb = Real(0), gmu = Real(0), gmw = Real(0);   // rows r and r+1
+    if (use_gm) {
+        gnb = gm_in[(0 * RS) * NT + tid]; gnu = gm_in[(1 * RS) * NT + tid]; gnw = gm_in[(2 * RS) * NT + tid];
+        gmb = gm_in[(0 * RS + 1) * NT + tid]; gmu = gm_in[(1 * RS + 1) * NT + tid]; gmw = gm_in[(2 * RS + 1) * NT + tid];
+    }
 
     // One row of the march.  EDGE = false is the interior fast path (rows 2..60: all stencils at full order,
     // no wall ghosts) with every order decision resolved at compile time; EDGE = true handles rows
@@ -416,10 +419,11 @@ RBC_HD void phase_tendency(int tid, const Consts<Real>& C, const Real* RBC_RESTR
         constexpr bool EDGE = decltype(edge_tag)::value;
         const int k = k0 + r;
         const Real gb0 = gnb, gu0 = gnu, gw0 = gnw;
-        if (r + 1 < RS && use_gm) {
-            gnb = gm_in[(0 * RS + r + 1) * NT + tid];
-            gnu = gm_in[(1 * RS + r + 1) * NT + tid];
-            gnw = gm_in[(2 * RS + r + 1) * NT + tid];
+        gnb = gmb; gnu = gmu; gnw = gmw;
+        if (r + 2 < RS && use_gm) {                          // two rows ahead
+            gmb = gm_in[(0 * RS + r + 2) * NT + tid];
+            gmu = gm_in[(1 * RS + r + 2) * NT + tid];
+            gmw = gm_in[(2 * RS + r + 2) * NT + tid];
         }
         Real bx[6], ux[6], wxn[6];
         RBC_UNROLL
