@@ -25,8 +25,11 @@
  * PARITY PIN: the reference has no tests and cannot be executed here (no Julia).  The oracle
  * is pinned by the reference's shipped checkpoint files (produced by the real Julia sim):
  * discrete divergence-freeness under this staggering, the Ra=1e4 fixed-point band, the
- * near-wall tracer residual and the Ra=1e5 limit cycle (tests/test_oracle_fixtures.py), plus
- * the survey's cross-check table.  Against Julia output itself parity is UNPINNED.
+ * near-wall tracer residual (tests/test_oracle_fixtures.py), the Ra=1e5 limit cycle — all 34
+ * two-roll-pair states of the train/val/test files within 0.0075 sigma of this oracle's own
+ * trajectory in (Nu_state, KE, Nu_obs) space, the 6 one-roll-pair states inside their branch's
+ * band (tests/test_oracle_limit_cycle.py) — plus the survey's cross-check table.  Step-by-step
+ * against Julia output itself parity is UNPINNED (no Julia step output exists to compare with).
  *
  * Index conventions (0-based, C order, x fastest):
  *   b[k*nx+i]  cell centre (i,k), k = 0 bottom .. nz-1 top
