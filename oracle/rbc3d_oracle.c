@@ -214,28 +214,52 @@ static void tendencies3(const rbc3d_params *P, work3_t *W, const double *b, cons
 #undef PH
 }
 
-/* plain DFT along one axis of a [nz][ny][nx] complex array (n up to 64: O(n^2) is fine for the oracle) */
+/* DFT of one line of n complex values (stride st), out of place.  Power-of-two lengths use the textbook recursive
+ * radix-2 decimation in time (the flowstats protocol runs this oracle for 14 x 300 samples at 64 x 64 x 32), any other
+ * length the defining O(n^2) sum; the two agree to round-off (tests/test_oracle3d.py). */
+static void dft_line(int n, const double *xr, const double *xi, long st, double *yr, double *yi, const double *c, const double *s,
+                     int tw_stride)
+{
+    if (n == 1) { yr[0] = xr[0]; yi[0] = xi ? xi[0] : 0.0; return; }
+    if (n % 2 == 0) {
+        const int h = n / 2;
+        dft_line(h, xr, xi, 2 * st, yr, yi, c, s, 2 * tw_stride);                                  /* even samples */
+        dft_line(h, xr + st, xi ? xi + st : NULL, 2 * st, yr + h, yi + h, c, s, 2 * tw_stride);     /* odd samples  */
+        for (int m = 0; m < h; ++m) {
+            const double wr = c[m * tw_stride], wi = s[m * tw_stride];
+            const double orr = yr[h + m] * wr - yi[h + m] * wi, oi = yr[h + m] * wi + yi[h + m] * wr;
+            const double er = yr[m], ei = yi[m];
+            yr[m] = er + orr; yi[m] = ei + oi;
+            yr[h + m] = er - orr; yi[h + m] = ei - oi;
+        }
+        return;
+    }
+    for (int m = 0; m < n; ++m) {
+        double sr = 0, si = 0;
+        for (int q = 0; q < n; ++q) {
+            const int t = (int)(((long)m * q) % n) * tw_stride;
+            const double ar = xr[q * st], ai = xi ? xi[q * st] : 0.0;
+            sr += ar * c[t] - ai * s[t];
+            si += ar * s[t] + ai * c[t];
+        }
+        yr[m] = sr; yi[m] = si;
+    }
+}
+
+/* DFT along one axis of a [nz][ny][nx] complex array */
 static void dft_axis(int nx, int ny, int nz, int axis, const double *ar, const double *ai, double *br, double *bi, int sign)
 {
     const int n = axis == 0 ? nx : ny;
     const long st = axis == 0 ? 1 : nx;
-    double *c = (double *)malloc(n * 8), *s = (double *)malloc(n * 8);
+    double *c = (double *)malloc(n * 8), *s = (double *)malloc(n * 8), *yr = (double *)malloc(n * 8), *yi = (double *)malloc(n * 8);
     for (int q = 0; q < n; ++q) { c[q] = cos(2 * M_PI * q / n); s[q] = sign * sin(2 * M_PI * q / n); }
     for (int k = 0; k < nz; ++k)
         for (int o = 0; o < (axis == 0 ? ny : nx); ++o) {
             const size_t base = (size_t)k * nx * ny + (axis == 0 ? (size_t)o * nx : (size_t)o);
-            for (int m = 0; m < n; ++m) {
-                double sr = 0, si = 0;
-                for (int q = 0; q < n; ++q) {
-                    const int t = (int)(((long)m * q) % n);
-                    const double xr = ar[base + q * st], xi = ai ? ai[base + q * st] : 0.0;
-                    sr += xr * c[t] - xi * s[t];
-                    si += xr * s[t] + xi * c[t];
-                }
-                br[base + m * st] = sr; bi[base + m * st] = si;
-            }
+            dft_line(n, ar + base, ai ? ai + base : NULL, st, yr, yi, c, s, 1);
+            for (int m = 0; m < n; ++m) { br[base + m * st] = yr[m]; bi[base + m * st] = yi[m]; }
         }
-    free(c); free(s);
+    free(c); free(s); free(yr); free(yi);
 }
 
 static void poisson3(const rbc3d_params *P, work3_t *W)

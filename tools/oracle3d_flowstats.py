@@ -2,9 +2,10 @@
 """Golden-vector generator: the 3D CPU oracle run like the reference's `experiments/flowstats/flowstats_ra.py:27-36`
 (64 x 64 x 32 grid, dt_solver 0.005, heater_duration 0.25 -> one sample per time unit, zero action, noise initialisation
 with kick 0.01), so that its Nusselt series can be compared with the Julia-produced `flowstats_ra.pkl` at the SAME
-resolution.  Test infrastructure (oracle only; no GPU).  One process per Rayleigh number, ~28 s of one core per sample.
+resolution.  Test infrastructure (oracle only; no GPU).  One process per Rayleigh number, ~9 s of one core per sample.
 
-    python tools/oracle3d_flowstats.py --ra 500 4000 16000 --samples 100 --out tests/golden/oracle3d_flowstats_64x64x32.json
+    python tools/oracle3d_flowstats.py --ra 500 750 1000 1500 2000 4000 8000 16000 32000 64000 128000 256000 512000 1000000 \
+        --samples 300 --seed 1000 --procs 7 --out tests/golden/oracle3d_flowstats_64x64x32.json
 """
 import argparse
 import json
@@ -52,12 +53,14 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--ra", type=float, nargs="+", default=[500, 4000, 16000])
     ap.add_argument("--samples", type=int, default=100)
-    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--seed", type=int, default=42, help="seed of the first Rayleigh number; the i-th one uses seed + i (one noise "
+                    "realisation per run, like the reference, whose env draws a fresh seed per reset)")
+    ap.add_argument("--procs", type=int, default=0)
     ap.add_argument("--out", default="tests/golden/oracle3d_flowstats_64x64x32.json")
     ap.add_argument("--log", default="")
     a = ap.parse_args()
-    with mp.Pool(len(a.ra)) as pool:
-        res = dict(pool.map(run, [(ra, a.samples, a.seed, a.log) for ra in a.ra]))
+    with mp.Pool(a.procs or len(a.ra)) as pool:
+        res = dict(pool.map(run, [(ra, a.samples, a.seed + i, a.log) for i, ra in enumerate(a.ra)], chunksize=1))
     meta = {"grid": [32, 64, 64], "dt_solver": 0.005, "heater_duration": 0.25, "kick": 0.01, "samples": a.samples,
             "generator": "tools/oracle3d_flowstats.py", "note": "CPU oracle (oracle/rbc3d_oracle.c), one sample per time unit"}
     Path(a.out).write_text(json.dumps({"meta": meta, "runs": res}, indent=0))
