@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RBC_B200_ABI_VERSION 1
+#define RBC_B200_ABI_VERSION 2
 
 /* Configuration = the keyword arguments of initialize_simulation (rbc_sim2D_api.jl:17) plus the
  * constants that the Julia API hard-codes (rbc_sim2D_api.jl:28-41), made explicit. */
@@ -119,6 +119,64 @@ int rbc2d_step_dev(rbc2d_sim* sim, const float* actions_dev, float* obs_dev, flo
 int rbc2d_step_host(rbc2d_sim* sim, const float* actions_host, float* obs_host, float* reward_host, double* nu_state_host,
                     double* nu_obs_host, int32_t* truncated_host, int32_t* nan_host);
 
+/* ------------------------------------------------------------------------------------------------
+ * Vector-environment step: what the reference gets from gymnasium's / SB3's vector wrappers around one process per
+ * env (gym.make_vec(..., vectorization_mode="async"), example/run_vectorized.py:11-31; SubprocVecEnv,
+ * experiments/run_sarl.py:130-153) — auto-reset of truncated environments, episode returns, terminal observations —
+ * fused into the ONE kernel launch that steps the batch.  Resets gather a uniformly drawn episode of the checkpoint
+ * bank (rbc_sim2D.jl:176-177); the draw is rbc_checkpoint_draw(seed, env_id_offset + env, episode counter), so it does
+ * not depend on how environments are sharded over GPUs.
+ *   mode 0  disabled: flags and episode returns only
+ *   mode 1  next_step (gymnasium 1.1.1 default): an environment that truncated is re-initialised by the NEXT call —
+ *           that call ignores its action, does not march it, returns the reset observation, reward 0, truncated 0
+ *   mode 2  same_step (SB3): re-initialised inside the truncating call; obs is the reset observation, the terminal
+ *           observation / Nusselt numbers / episode return go to the final_* outputs (rows of truncated envs only)
+ *   nan_reset != 0: an environment whose fields contain NaNs is re-initialised inside the call in either mode, reported
+ *           truncated with reward 0 (the reference raises instead, rbc2D.py:170-171; the count of such events is kept
+ *           in a device counter the caller can poll without synchronising the step)
+ * Without a checkpoint bank (noise initialisation) nothing is reset in the kernel: the flags are reported and the caller
+ * resets with rbc2d_reset_from_fields_dev.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct rbc_autoreset {
+    int32_t mode;
+    int32_t nan_reset;
+    int64_t seed;
+    int64_t env_id_offset;
+} rbc_autoreset;
+
+/* Outputs of a vector step; device pointers, any may be NULL except obs (final_* are only written in mode 2 / NaN resets). */
+typedef struct rbc2d_vec_out {
+    float* obs;              /* [B][C][obs_nz][obs_nx]                                   */
+    float* reward;           /* [B]                                                      */
+    double* nu_state;        /* [B] info["nusselt_state"]                                */
+    double* nu_obs;          /* [B] info["nusselt_obs"]                                  */
+    int32_t* truncated;      /* [B]                                                      */
+    int32_t* nan;            /* [B] step_contains_NaNs of this call                      */
+    double* t;               /* [B] info["t"]   (rbc2D.py:202-212)                       */
+    int32_t* step;           /* [B] info["step"]                                         */
+    double* episode_return;  /* [B] running return of the current episode                */
+    float* final_obs;        /* [B][C][obs_nz][obs_nx]                                   */
+    double* final_nu_state;  /* [B]                                                      */
+    double* final_nu_obs;    /* [B]                                                      */
+    double* final_return;    /* [B] return of the episode that just ended                */
+} rbc2d_vec_out;
+
+int32_t rbc_checkpoint_draw(int64_t seed, int64_t global_env, int64_t episode, int32_t n_episodes);
+int rbc2d_set_autoreset(rbc2d_sim* sim, const rbc_autoreset* cfg);
+/* reset(): every environment starts episode 0 from bank[ckpt_idx_dev[env]] (NULL: from its own draw); returns and pending
+ * flags are cleared.  Needs a checkpoint bank. */
+int rbc2d_vec_reset_dev(rbc2d_sim* sim, const int32_t* ckpt_idx_dev);
+/* Counts one episode start for every environment without touching the fields (after the caller re-initialised them itself,
+ * e.g. the noise initialisation through rbc2d_reset_from_fields_dev): episode counter += 1 for the listed environments
+ * (NULL = all), return := 0, pending := 0. */
+int rbc2d_vec_mark_reset_dev(rbc2d_sim* sim, const int32_t* env_ids_dev, int32_t n);
+int rbc2d_vec_step_dev(rbc2d_sim* sim, const float* actions_dev, const rbc2d_vec_out* out);
+/* Number of environments that reported NaNs in vector steps since the last call with clear != 0 (synchronises the stream). */
+int rbc2d_vec_nan_count(rbc2d_sim* sim, int32_t clear, int64_t* count);
+/* Same counter copied to a caller-provided (pinned) host int32 without synchronising: the value is valid once the stream
+ * has passed this point (poll it one step late for a deferred, sync-free NaN check). */
+int rbc2d_vec_nan_count_async(rbc2d_sim* sim, int32_t* count_host_pinned);
+
 /* Enable/disable the fused wrappers (NULL = all off).  Takes effect from the next step/observe. */
 int rbc2d_set_wrappers(rbc2d_sim* sim, const rbc2d_wrappers* w);
 /* info["cell_dist"] of the last step (rbc_reward_shaping.py:61-66), [B] float64; computed only while
@@ -195,6 +253,27 @@ int rbc3d_step_dev(rbc3d_sim* sim, const float* actions_dev, float* obs_dev, flo
                    int32_t* truncated_dev, int32_t* nan_dev);
 int rbc3d_step_host(rbc3d_sim* sim, const float* actions_host, float* obs_host, float* reward_host, double* nusselt_host,
                     int32_t* truncated_host, int32_t* nan_host);
+/* Vector-environment step of the 3D batch: same semantics as rbc2d_vec_step_dev (what SubprocVecEnv + Monitor give
+ * experiments/run_sarl.py:130-153).  final_obs is [B][4][nz][ny][nx] — pass NULL to skip the terminal observations. */
+typedef struct rbc3d_vec_out {
+    float* obs;              /* [B][4][nz][ny][nx] or NULL                               */
+    float* reward;           /* [B]                                                      */
+    double* nusselt;         /* [B] info["nusselt"]                                      */
+    int32_t* truncated;
+    int32_t* nan;
+    double* t;               /* [B] info["t"] (rbc3D.py:241-245)                         */
+    int32_t* step;           /* [B] info["step"]                                         */
+    double* episode_return;
+    float* final_obs;
+    double* final_nusselt;
+    double* final_return;
+} rbc3d_vec_out;
+int rbc3d_set_autoreset(rbc3d_sim* sim, const rbc_autoreset* cfg);
+int rbc3d_vec_reset_dev(rbc3d_sim* sim, const int32_t* ckpt_idx_dev);
+int rbc3d_vec_mark_reset_dev(rbc3d_sim* sim, const int32_t* env_ids_dev, int32_t n);
+int rbc3d_vec_step_dev(rbc3d_sim* sim, const float* actions_dev, const rbc3d_vec_out* out);
+int rbc3d_vec_nan_count(rbc3d_sim* sim, int32_t clear, int64_t* count);
+int rbc3d_vec_nan_count_async(rbc3d_sim* sim, int32_t* count_host_pinned);
 int rbc3d_observe_dev(rbc3d_sim* sim, float* obs_dev, double* nusselt_dev);
 int rbc3d_get_fields_host(rbc3d_sim* sim, double* fields_host);
 int rbc3d_get_info_host(rbc3d_sim* sim, double* t_host, int32_t* step_host);

@@ -62,6 +62,28 @@ class Rbc3dConfig(C.Structure):
     ]
 
 
+class RbcAutoreset(C.Structure):
+    """Mirror of ``rbc_autoreset`` (include/rbc_b200.h)."""
+
+    _fields_ = [("mode", C.c_int32), ("nan_reset", C.c_int32), ("seed", C.c_int64), ("env_id_offset", C.c_int64)]
+
+
+class Rbc2dVecOut(C.Structure):
+    """Mirror of ``rbc2d_vec_out`` (include/rbc_b200.h): device pointers."""
+
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "reward", "nu_state", "nu_obs", "truncated", "nan", "t", "step", "episode_return",
+                                          "final_obs", "final_nu_state", "final_nu_obs", "final_return")]
+
+
+class Rbc3dVecOut(C.Structure):
+    """Mirror of ``rbc3d_vec_out`` (include/rbc_b200.h): device pointers."""
+
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "reward", "nusselt", "truncated", "nan", "t", "step", "episode_return",
+                                          "final_obs", "final_nusselt", "final_return")]
+
+
+AUTORESET_MODES = {"disabled": 0, "next_step": 1, "same_step": 2}
+
 # every symbol include/rbc_b200.h declares; tests check that the built library exports them all
 ABI_SYMBOLS = (
     "rbc_abi_version", "rbc_last_error", "rbc2d_create", "rbc2d_destroy", "rbc2d_set_stream", "rbc2d_num_envs",
@@ -72,7 +94,11 @@ ABI_SYMBOLS = (
     "rbc3d_create", "rbc3d_destroy", "rbc3d_set_stream", "rbc3d_state_values_per_env", "rbc3d_load_checkpoints",
     "rbc3d_reset_from_checkpoints_dev", "rbc3d_reset_from_fields_host", "rbc3d_reset_from_fields_dev", "rbc3d_step_dev", "rbc3d_step_host",
     "rbc3d_observe_dev", "rbc3d_get_fields_host", "rbc3d_get_info_host", "rbc3d_launch_count", "rbc3d_last_step_kernel_ms",
+    "rbc_checkpoint_draw", "rbc2d_set_autoreset", "rbc2d_vec_reset_dev", "rbc2d_vec_mark_reset_dev", "rbc2d_vec_step_dev",
+    "rbc2d_vec_nan_count", "rbc2d_vec_nan_count_async", "rbc3d_set_autoreset", "rbc3d_vec_reset_dev", "rbc3d_vec_mark_reset_dev",
+    "rbc3d_vec_step_dev", "rbc3d_vec_nan_count", "rbc3d_vec_nan_count_async",
 )
+ABI_VERSION = 2
 
 _lib = None
 
@@ -93,11 +119,10 @@ def load_library(build_if_missing: bool = True):
     if build_if_missing and _build.needs_build():
         try:
             _build.build()
-        except Exception as e:  # no nvcc and no prebuilt library: fail loudly
-            if not _build.LIB.exists():
-                raise BackendUnavailable(
-                    f"{_build.LIB} is missing and could not be built ({e}); run `python -m rbc_gym_b200.build`"
-                ) from e
+        except Exception as e:  # a stale library must never be loaded silently: its struct layouts or kernels may differ
+            raise BackendUnavailable(
+                f"{_build.LIB} is missing or older than its sources and could not be rebuilt ({e}); "
+                "run `python -m rbc_gym_b200.build`") from e
     if not _build.LIB.exists():
         raise BackendUnavailable(f"{_build.LIB} is missing; run `python -m rbc_gym_b200.build`")
     L = C.CDLL(str(_build.LIB))
@@ -142,8 +167,18 @@ def load_library(build_if_missing: bool = True):
     L.rbc3d_get_info_host.argtypes = [vp, vp, vp]
     L.rbc3d_launch_count.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ip), C.POINTER(ip)]
     L.rbc3d_last_step_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
-    if L.rbc_abi_version() != 1:
-        raise BackendUnavailable("librbc_b200.so ABI version mismatch; rebuild with `python -m rbc_gym_b200.build`")
+    L.rbc_checkpoint_draw.argtypes = [C.c_int64, C.c_int64, C.c_int64, ip]
+    L.rbc_checkpoint_draw.restype = ip
+    for dim, out_t in (("2d", Rbc2dVecOut), ("3d", Rbc3dVecOut)):
+        getattr(L, f"rbc{dim}_set_autoreset").argtypes = [vp, C.POINTER(RbcAutoreset)]
+        getattr(L, f"rbc{dim}_vec_reset_dev").argtypes = [vp, vp]
+        getattr(L, f"rbc{dim}_vec_mark_reset_dev").argtypes = [vp, vp, ip]
+        getattr(L, f"rbc{dim}_vec_step_dev").argtypes = [vp, vp, C.POINTER(out_t)]
+        getattr(L, f"rbc{dim}_vec_nan_count").argtypes = [vp, ip, C.POINTER(C.c_int64)]
+        getattr(L, f"rbc{dim}_vec_nan_count_async").argtypes = [vp, vp]
+    if L.rbc_abi_version() != ABI_VERSION:
+        raise BackendUnavailable(f"librbc_b200.so has ABI version {L.rbc_abi_version()}, this package needs {ABI_VERSION}; "
+                                 "rebuild with `python -m rbc_gym_b200.build`")
     _lib = L
     return L
 
@@ -254,6 +289,9 @@ class Sim2D:
         n = self.B if ids is None else int(ids.numel())
         if idx.numel() != n:
             raise ValueError("ckpt_idx must have one entry per environment being reset")
+        self._validate_indices(idx, self.n_episodes, "checkpoint_idx")
+        if ids is not None:
+            self._validate_indices(ids, self.B, "env_ids")
         self._use_current_stream()
         self._check(self._L.rbc2d_reset_from_checkpoints_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
                                                             C.c_void_p(idx.data_ptr()), n))
@@ -262,6 +300,8 @@ class Sim2D:
         """Reset from explicit `[n, 2*nx*nz + nx*(nz+1)]` float64 fields (b,u,w); `project` mirrors Oceananigans' `set!`."""
         f = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1, self.nstate)
         ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
+        if ids is not None and (ids.size != f.shape[0] or (ids.size and (ids.min() < 0 or ids.max() >= self.B))):
+            raise IndexError(f"env_ids must list {f.shape[0]} environments in [0, {self.B})")
         self._use_current_stream()
         self._check(self._L.rbc2d_reset_from_fields_host(self._h, _np_ptr(ids), _np_ptr(f), f.shape[0], int(project)))
 
@@ -272,6 +312,8 @@ class Sim2D:
         ids = None if env_ids is None else t.as_tensor(env_ids, dtype=t.int32, device=self.device).contiguous()
         if ids is not None and ids.numel() != f.shape[0]:
             raise ValueError("env_ids must have one entry per field row")
+        if ids is not None:
+            self._validate_indices(ids, self.B, "env_ids")
         self._use_current_stream()
         self._check(self._L.rbc2d_reset_from_fields_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
                                                        C.c_void_p(f.data_ptr()), f.shape[0], int(project)))
@@ -327,6 +369,76 @@ class Sim2D:
             return {k: np.zeros(s, d) for k, (s, d) in shapes.items()}
         t = self.torch
         return {k: t.zeros(s, dtype=getattr(t, np.dtype(d).name)).pin_memory().numpy() for k, (s, d) in shapes.items()}
+
+    # ------------------------------------------------------------------ fused vector-env step
+    def set_autoreset(self, mode: str = "next_step", nan_reset: bool = False, seed: int = 0, env_id_offset: int = 0):
+        """Configure the vector-env semantics fused into the step kernel (`rbc2d_set_autoreset`)."""
+        self._check(self._L.rbc2d_set_autoreset(self._h, C.byref(RbcAutoreset(AUTORESET_MODES[mode], int(nan_reset), int(seed), int(env_id_offset)))))
+        self.autoreset_mode = mode
+
+    def _vec_buffers(self):
+        if getattr(self, "_vec", None) is None:
+            t = self.torch
+            f32, f64, i32 = t.float32, t.float64, t.int32
+            mk = lambda shape, dt: t.zeros(shape, dtype=dt, device=self.device)
+            v = {"t": mk(self.B, f64), "step": mk(self.B, i32), "episode_return": mk(self.B, f64),
+                 "final_obs": mk((self.B, self.channels, *self.obs_shape), f32), "final_nu_state": mk(self.B, f64),
+                 "final_nu_obs": mk(self.B, f64), "final_return": mk(self.B, f64)}
+            out = Rbc2dVecOut(*[C.c_void_p(x.data_ptr()) for x in (self.obs, self.reward, self.nu_state, self.nu_obs, self.truncated,
+                                                                  self.nan, v["t"], v["step"], v["episode_return"], v["final_obs"],
+                                                                  v["final_nu_state"], v["final_nu_obs"], v["final_return"])])
+            self._vec, self._vec_out = v, out
+        return self._vec
+
+    def vec_reset(self, ckpt_idx=None):
+        """`reset()` of the whole batch from the checkpoint bank: episode 0 of every environment (its own draw, or `ckpt_idx`)."""
+        t = self.torch
+        idx = None if ckpt_idx is None else t.as_tensor(ckpt_idx, dtype=t.int32, device=self.device).contiguous()
+        if idx is not None:
+            self._validate_indices(idx, self.n_episodes, "checkpoint_idx", self.B)
+        self._use_current_stream()
+        self._check(self._L.rbc2d_vec_reset_dev(self._h, None if idx is None else C.c_void_p(idx.data_ptr())))
+
+    def vec_mark_reset(self, env_ids=None):
+        """Episode bookkeeping for environments the caller re-initialised itself (noise initialisation)."""
+        t = self.torch
+        ids = None if env_ids is None else t.as_tensor(env_ids, dtype=t.int32, device=self.device).contiguous()
+        self._use_current_stream()
+        self._check(self._L.rbc2d_vec_mark_reset_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
+                                                    self.B if ids is None else int(ids.numel())))
+
+    def vec_step(self, actions):
+        """One vector-env step in ONE kernel launch: march, observation, reward, truncation AND the auto-reset of the configured
+        mode.  Returns (obs, reward, nu_state, nu_obs, truncated, nan, extras) — handle-owned tensors that the next call
+        overwrites; `extras` holds t, step, episode_return and the final_* outputs."""
+        t = self.torch
+        a = t.as_tensor(actions, dtype=t.float32, device=self.device).contiguous()
+        if a.shape != (self.B, self.heaters):
+            raise ValueError(f"actions must have shape {(self.B, self.heaters)}, got {tuple(a.shape)}")
+        v = self._vec_buffers()
+        self._use_current_stream()
+        self._check(self._L.rbc2d_vec_step_dev(self._h, C.c_void_p(a.data_ptr()), C.byref(self._vec_out)))
+        return self.obs, self.reward, self.nu_state, self.nu_obs, self.truncated, self.nan, v
+
+    def vec_nan_count(self, clear: bool = False) -> int:
+        """Environments that reported NaNs in vector steps since the counter was cleared (synchronises)."""
+        n = C.c_int64()
+        self._use_current_stream()
+        self._check(self._L.rbc2d_vec_nan_count(self._h, int(clear), C.byref(n)))
+        return n.value
+
+    def vec_nan_count_async(self, pinned_int32):
+        """Enqueue a copy of the NaN counter into a pinned int32 host tensor (no synchronisation)."""
+        self._use_current_stream()
+        self._check(self._L.rbc2d_vec_nan_count_async(self._h, C.c_void_p(pinned_int32.data_ptr())))
+
+    def _validate_indices(self, idx, upper: int, what: str, expect_n: Optional[int] = None):
+        """Raise like the reference would (Julia BoundsError on a bad checkpoint index) instead of clamping or writing out of
+        bounds.  One small reduction + host read; resets are off the hot path."""
+        if expect_n is not None and int(idx.numel()) != expect_n:
+            raise ValueError(f"{what} must have {expect_n} entries, got {int(idx.numel())}")
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= upper):
+            raise IndexError(f"{what} out of range [0, {upper})")
 
     def set_wrappers(self, *, normalize_obs: bool = False, u_limit: float = 1.3, maxval: float = 1.0, clip: bool = False,
                      normalize_reward: bool = False, shaping_weight: Optional[float] = None):
@@ -501,6 +613,9 @@ class Sim3D:
         idx = t.as_tensor(ckpt_idx, dtype=t.int32, device=self.device).contiguous()
         ids = None if env_ids is None else t.as_tensor(env_ids, dtype=t.int32, device=self.device).contiguous()
         n = self.B if ids is None else int(ids.numel())
+        self._validate_indices(idx, self.n_episodes, "checkpoint_idx", n)
+        if ids is not None:
+            self._validate_indices(ids, self.B, "env_ids")
         self._use_current_stream()
         self._check(self._L.rbc3d_reset_from_checkpoints_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
                                                             C.c_void_p(idx.data_ptr()), n))
@@ -528,6 +643,65 @@ class Sim3D:
         self._use_current_stream()
         self._check(self._L.rbc3d_reset_from_fields_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
                                                        C.c_void_p(f.data_ptr()), n, 1))
+
+    # ------------------------------------------------------------------ fused vector-env step
+    _validate_indices = Sim2D._validate_indices
+
+    def set_autoreset(self, mode: str = "next_step", nan_reset: bool = False, seed: int = 0, env_id_offset: int = 0):
+        self._check(self._L.rbc3d_set_autoreset(self._h, C.byref(RbcAutoreset(AUTORESET_MODES[mode], int(nan_reset), int(seed), int(env_id_offset)))))
+        self.autoreset_mode = mode
+
+    def _vec_buffers(self, want_final_obs: bool):
+        t = self.torch
+        if getattr(self, "_vec", None) is None:
+            mk = lambda shape, dt: t.zeros(shape, dtype=dt, device=self.device)
+            self._vec = {"t": mk(self.B, t.float64), "step": mk(self.B, t.int32), "episode_return": mk(self.B, t.float64),
+                         "final_nusselt": mk(self.B, t.float64), "final_return": mk(self.B, t.float64), "final_obs": None}
+        v = self._vec
+        if want_final_obs and v["final_obs"] is None:
+            v["final_obs"] = t.zeros_like(self.obs)
+        return v
+
+    def vec_reset(self, ckpt_idx=None):
+        t = self.torch
+        idx = None if ckpt_idx is None else t.as_tensor(ckpt_idx, dtype=t.int32, device=self.device).contiguous()
+        if idx is not None:
+            self._validate_indices(idx, self.n_episodes, "checkpoint_idx", self.B)
+        self._use_current_stream()
+        self._check(self._L.rbc3d_vec_reset_dev(self._h, None if idx is None else C.c_void_p(idx.data_ptr())))
+
+    def vec_mark_reset(self, env_ids=None):
+        t = self.torch
+        ids = None if env_ids is None else t.as_tensor(env_ids, dtype=t.int32, device=self.device).contiguous()
+        self._use_current_stream()
+        self._check(self._L.rbc3d_vec_mark_reset_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
+                                                    self.B if ids is None else int(ids.numel())))
+
+    def vec_step(self, actions, want_obs: bool = True, want_final_obs: bool = True):
+        """One vector-env step of the 3D batch in one launch (`rbc3d_vec_step_dev`); see `Sim2D.vec_step`."""
+        t = self.torch
+        a = t.as_tensor(actions, dtype=t.float32, device=self.device).contiguous()
+        if a.shape != (self.B, self.heaters, self.heaters):
+            raise RuntimeError(f"Action size does not match the number of actuators. Expected {(self.heaters, self.heaters)}, "
+                               f"got {tuple(a.shape[1:])}.")
+        v = self._vec_buffers(want_final_obs and want_obs)
+        p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
+        out = Rbc3dVecOut(p(self.obs) if want_obs else None, p(self.reward), p(self.nusselt), p(self.truncated), p(self.nan), p(v["t"]),
+                          p(v["step"]), p(v["episode_return"]), p(v["final_obs"]) if (want_obs and want_final_obs) else None,
+                          p(v["final_nusselt"]), p(v["final_return"]))
+        self._use_current_stream()
+        self._check(self._L.rbc3d_vec_step_dev(self._h, C.c_void_p(a.data_ptr()), C.byref(out)))
+        return self.obs, self.reward, self.nusselt, self.truncated, self.nan, v
+
+    def vec_nan_count(self, clear: bool = False) -> int:
+        n = C.c_int64()
+        self._use_current_stream()
+        self._check(self._L.rbc3d_vec_nan_count(self._h, int(clear), C.byref(n)))
+        return n.value
+
+    def vec_nan_count_async(self, pinned_int32):
+        self._use_current_stream()
+        self._check(self._L.rbc3d_vec_nan_count_async(self._h, C.c_void_p(pinned_int32.data_ptr())))
 
     def step(self, actions, want_obs: bool = True):
         """actions `[B, heaters, heaters]` float32 CUDA tensor -> (obs, reward, nusselt, truncated, nan)."""

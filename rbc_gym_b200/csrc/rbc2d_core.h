@@ -32,6 +32,12 @@
 #define RBC_HD inline
 #endif
 #define RBC_RESTRICT __restrict__
+// out-of-line on the device: code that runs once per environment visit and must not share the register budget of the march
+#if defined(__CUDACC__)
+#define RBC_HD_COLD __host__ __device__ __noinline__
+#else
+#define RBC_HD_COLD inline
+#endif
 
 #if defined(__CUDA_ARCH__)
 #define RBC_PHASE_N(NTHREADS, ...) { const int tid = threadIdx.x; __VA_ARGS__ } __syncthreads();
@@ -101,6 +107,39 @@ struct Tables {
     Real thomas_scale;  // dz^2 / 48
 };
 
+// ------------------------------------------------------------------------------------------
+// Vector-environment semantics fused into the step kernel: what gymnasium's / SB3's vector wrappers do around the
+// reference's one-process-per-env setup (example/run_vectorized.py:11-31, experiments/run_sarl.py:130-153) — auto-reset
+// of truncated environments from the device checkpoint bank, episode returns, terminal observations — happens inside
+// the launch that steps the batch.  mode < 0: plain batched step (no vector semantics).
+// ------------------------------------------------------------------------------------------
+struct VecIO {
+    int mode = -1;                 // 0 disabled (flags + returns only), 1 next_step (gymnasium 1.1.1), 2 same_step (SB3)
+    int nan_reset = 0;             // 1: an environment with NaNs is re-initialised inside the step (truncated, reward 0)
+    const double* bank = nullptr;  // [n_ep][NSTATE] fp64 checkpoint bank
+    int n_ep = 0;
+    unsigned long long seed = 0, id_offset = 0;   // checkpoint draw = hash(seed, id_offset + env, episode) mod n_ep
+    int* pending = nullptr;        // [B] next_step: truncated on the previous call, this call only resets
+    long long* episode = nullptr;  // [B] resets so far (the counter that keys the draw)
+    double* ep_return = nullptr;   // [B] running episode return
+    float* final_obs = nullptr;    // [B][obs...] terminal observation of environments reset inside this step
+    double* final_nu_a = nullptr;  // [B] terminal nusselt_state (2D) / nusselt (3D)
+    double* final_nu_b = nullptr;  // [B] terminal nusselt_obs (2D)
+    double* final_return = nullptr;  // [B] return of the episode that ended
+    int* nan_count = nullptr;      // one counter: environments that reported NaNs since it was last cleared
+};
+
+// Episode index for global environment g at episode counter e (same arithmetic as the 64-bit tensor expression the
+// Python vector env used before the fusion, so sharded and unsharded runs draw alike)
+RBC_HD int checkpoint_draw(unsigned long long seed, unsigned long long g, unsigned long long e, int n_ep)
+{
+    const unsigned long long M63 = 0x7FFFFFFFFFFFFFFFull;
+    unsigned long long x = (g * 0x9E3779B97F4A7C15ull + e * 0xC2B2AE3D27D4EB4Full + seed * 0x165667B19E3779F9ull) & M63;
+    x = ((x ^ (x >> 31)) * 0x7FB5D329728EA185ull) & M63;
+    x = x ^ (x >> 27);
+    return (int)(x % (unsigned long long)n_ep);
+}
+
 template <typename Real>
 struct EnvIO {
     // per-environment global arrays, indexed by env
@@ -116,6 +155,7 @@ struct EnvIO {
     int* nan_flag;            // [B]
     Real* pressure;           // [B][2][NZ][NX] (pHY', pNHS) or nullptr
     double* cell_dist;        // [B] Benard-cell distance (info["cell_dist"]) or nullptr
+    VecIO vec;                // fused auto-reset (off by default)
 };
 
 // everything one CTA needs while it owns an environment
@@ -921,6 +961,12 @@ RBC_HD void phase_load_state(int tid, const Real* g, Real* sm)
 {
     for (int q = tid; q < NSTATE; q += NT) sm[(q / NX) * SX + (q % NX)] = g[q];
 }
+// checkpoint bank (fp64, compact) -> on-chip state: the gather + cast of a reset (initialize_from_checkpoint, rbc_sim2D.jl:173-186)
+template <typename Real>
+RBC_HD void phase_load_bank(int tid, const double* g, Real* sm)
+{
+    for (int q = tid; q < NSTATE; q += NT) sm[(q / NX) * SX + (q % NX)] = (Real)g[q];
+}
 template <typename Real>
 RBC_HD void phase_store_state(int tid, const Real* sm, Real* g)
 {
@@ -975,48 +1021,21 @@ RBC_HD double cell_distance(const Real* uy)
 }
 
 // ------------------------------------------------------------------------------------------
-// one action step of one environment (the whole of step_simulation + observation + reward)
+// epilogue of an action step: NaN check, observation, Nusselt numbers, reward, clock / truncation and the fused
+// vector-env bookkeeping.  Runs once per environment visit, and a second time (second_pass) when the environment is
+// re-initialised from the checkpoint bank inside the same launch.  Returns whether such a reset is due.
 // ------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define RBC_COUNT_ONE(p) atomicAdd((p), 1)
+#else
+#define RBC_COUNT_ONE(p) (*(p) += 1)
+#endif
 template <typename Real, bool SPLIT, bool NXT_GLOBAL>
-RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const EnvIO<Real>& io, const Ctx<Real>& X, int env,
-                            const RunFlags& F)
+RBC_HD_COLD bool env_epilogue(const Consts<Real>& C, const EnvIO<Real>& io, const Ctx<Real>& X, int env, const Real* cur, double* red,
+                         const RunFlags& F, bool state_changed, Real last_dtau, double t_old, int pend, bool second_pass)
 {
-    const Real gam[3] = {Real(8.0 / 15.0), Real(5.0 / 12.0), Real(3.0 / 4.0)};
-    const Real zet[3] = {Real(0), Real(-17.0 / 60.0), Real(-5.0 / 12.0)};
+    const VecIO& V = io.vec;
     Real* st = io.state + (size_t)env * NSTATE;
-
-    // load the environment, evaluate the heater profile for this action
-    RBC_PHASE(
-        phase_load_state(tid, st, X.s0);
-        if (tid < NX) X.Tb[tid] = (Real)heater_T(C, io.actions + (size_t)env * C.heaters, (tid + 0.5) * C.dx);
-    )
-    Real* cur = X.s0;
-    Real* nxt = X.s1;
-    Real last_dtau = Real(1);
-    if (F.project_first) project(C, X, cur, T.thomas_scale);
-    for (int sub = 0; sub < F.nsub; ++sub) {
-        const Real dt = (sub == F.nsub - 1) ? C.dt_last : C.dt_full;
-        for (int stage = 0; stage < 3; ++stage) {
-            if (SPLIT) { RBC_PHASE(phase_phy(tid, C, cur + OFF_B, X.R);) }
-            const Real* gin = X.gm + ((stage & 1) ? 0 : NSTATE);      // stage s reads what stage s-1 wrote
-            Real* gout = X.gm + ((stage & 1) ? NSTATE : 0);
-            RBC_PHASE(phase_edge_fluxes(tid, cur, X.E);)
-            RBC_PHASE((phase_tendency<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, X.E, gin, gout, dt, gam[stage], zet[stage], stage > 0));)
-            Real* P;
-            if (NXT_GLOBAL) {
-                RBC_PHASE(phase_copy(tid, nxt, cur, NS_SM);)
-                P = cur;
-            } else {
-                P = nxt; nxt = cur; cur = P;
-            }
-            project(C, X, P, T.thomas_scale);
-            last_dtau = (gam[stage] + zet[stage]) * dt;
-        }
-    }
-
-    // ---- epilogue: NaN check, observation, Nusselt numbers, reward, bookkeeping ----
-    // the reduction scratch aliases the dead second state buffer when that one is on-chip
-    double* red = NXT_GLOBAL ? X.red : reinterpret_cast<double*>(nxt);
     const int oz = NZ / C.obs_nz, ox = NX / C.obs_nx, nobs = C.obs_nz * C.obs_nx;
     double nu_s = 0, nu_o = 0;
     RBC_PHASE(phase_reduce_partials(tid, C, cur, red);)
@@ -1038,10 +1057,17 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
         const double go = (1.5 * om1 - 0.5 * om2 + 0.5 * o1 - 1.5 * o0) / C.obs_nz;
         nu_o = (q1o - kap * go) / dbH;
     }
+    // decisions every thread takes alike (fin is shared; t_old / pend were read before the march)
+    const bool vec = V.mode >= 0 && F.advance_clock;
+    const bool bad = fin[6] > 0;
+    const bool stepping = F.advance_clock && !pend && !second_pass;
+    const bool trunc_now = stepping && (t_old + C.dt_action >= C.episode_length);
+    const bool bad_reset = vec && stepping && V.nan_reset && bad;
+    const bool do_reset = vec && stepping && V.bank != nullptr && ((V.mode == 2 && trunc_now) || bad_reset);
+    float* ob = ((do_reset && V.final_obs != nullptr) ? V.final_obs : io.obs) + (size_t)env * C.channels * nobs;
     RBC_PHASE(
         // store the state back and emit the observation (strided sub-sample, channel-major)
-        if (F.nsub > 0 || F.project_first) phase_store_state(tid, cur, st);
-        float* ob = io.obs + (size_t)env * C.channels * nobs;
+        if (state_changed && !do_reset) phase_store_state(tid, cur, st);
         for (int q = tid; q < 3 * nobs; q += NT) {
             const int ch = q / nobs, zo = (q % nobs) / C.obs_nx, xo = q % C.obs_nx;
             const int off = (ch == 0 ? OFF_B : (ch == 1 ? OFF_U : OFF_W));
@@ -1053,23 +1079,62 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
             ob[q] = v;
         }
         if (tid == 0) {
-            double rew = -nu_o;                                        // rbc2D.py:198-200
-            if (C.wrap_reward) rew = (rew + C.reward_scale) / (C.reward_scale - 1.0);
-            if (C.wrap_shaping || io.cell_dist != nullptr) {
-                const double PI = 3.14159265358979323846;
-                const double cd = cell_distance(cur + OFF_W + (NZ / 2 - 1) * SX);
-                if (io.cell_dist != nullptr) io.cell_dist[env] = cd;
-                if (C.wrap_shaping) rew = (1.0 - C.shaping_weight) * rew + C.shaping_weight * ((PI - cd) / PI);
-            }
-            io.nu_state[env] = nu_s;
-            io.nu_obs[env] = nu_o;
-            io.reward[env] = (float)rew;
-            io.nan_flag[env] = fin[6] > 0 ? 1 : 0;
-            if (F.advance_clock) {
-                const double tn = io.t[env] + C.dt_action;
-                io.t[env] = tn;
-                io.step_count[env] += 1;
-                io.truncated[env] = tn >= C.episode_length ? 1 : 0;
+            if (second_pass) {
+                // the environment was re-initialised inside this step: its new observation is already out, the
+                // Nusselt outputs follow the new state (the terminal ones went to final_*), the clock restarts
+                io.nu_state[env] = nu_s;
+                io.nu_obs[env] = nu_o;
+                io.t[env] = 0.0;
+                io.step_count[env] = 1;
+                V.episode[env] += 1;
+                V.ep_return[env] = 0.0;
+                if (V.pending != nullptr) V.pending[env] = 0;
+            } else {
+                double rew = -nu_o;                                        // rbc2D.py:198-200
+                if (C.wrap_reward) rew = (rew + C.reward_scale) / (C.reward_scale - 1.0);
+                if (C.wrap_shaping || io.cell_dist != nullptr) {
+                    const double PI = 3.14159265358979323846;
+                    const double cd = cell_distance(cur + OFF_W + (NZ / 2 - 1) * SX);
+                    if (io.cell_dist != nullptr) io.cell_dist[env] = cd;
+                    if (C.wrap_shaping) rew = (1.0 - C.shaping_weight) * rew + C.shaping_weight * ((PI - cd) / PI);
+                }
+                io.nan_flag[env] = bad ? 1 : 0;
+                if (pend) {
+                    // gymnasium NEXT_STEP: this call only resets the environment (action ignored, reward 0)
+                    io.nu_state[env] = nu_s;
+                    io.nu_obs[env] = nu_o;
+                    io.reward[env] = 0.0f;
+                    io.truncated[env] = 0;
+                    io.t[env] = 0.0;
+                    io.step_count[env] = 1;
+                    V.episode[env] += 1;
+                    V.ep_return[env] = 0.0;
+                    V.pending[env] = 0;
+                } else {
+                    if (bad_reset) rew = 0.0;
+                    if (bad && vec && V.nan_count != nullptr) RBC_COUNT_ONE(V.nan_count);
+                    io.reward[env] = (float)rew;
+                    const double ret = vec ? V.ep_return[env] + (double)(float)rew : 0.0;
+                    if (do_reset) {
+                        if (V.final_nu_a != nullptr) V.final_nu_a[env] = nu_s;
+                        if (V.final_nu_b != nullptr) V.final_nu_b[env] = nu_o;
+                        if (V.final_return != nullptr) V.final_return[env] = ret;
+                        io.truncated[env] = 1;
+                    } else {
+                        io.nu_state[env] = nu_s;
+                        io.nu_obs[env] = nu_o;
+                        if (F.advance_clock) {
+                            const double tn = t_old + C.dt_action;
+                            io.t[env] = tn;
+                            io.step_count[env] += 1;
+                            io.truncated[env] = (trunc_now || bad_reset) ? 1 : 0;
+                        }
+                        if (vec) {
+                            V.ep_return[env] = ret;
+                            if (V.pending != nullptr) V.pending[env] = (V.mode == 1 && trunc_now && V.bank != nullptr) ? 1 : 0;
+                        }
+                    }
+                }
             }
         }
     )
@@ -1079,7 +1144,7 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
         // whenever the state changed (step, or the set! projection of a reset) and kept per environment, so that an
         // observe-only launch (what reset() returns) emits the channels from the stored fields.
         Real* pr = io.pressure + (size_t)env * 2 * NCELL;
-        if (F.nsub > 0 || F.project_first) {
+        if (state_changed) {
             RBC_PHASE(
                 double acc = 0;
                 for (int q = tid; q < NCELL; q += NT) acc += (double)X.R[(q / NX) * RSTR + (q % NX)];
@@ -1095,13 +1160,77 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
         }
         if (C.channels == 5) {
             RBC_PHASE(
-                float* ob = io.obs + (size_t)env * C.channels * nobs;
                 for (int q = tid; q < 2 * nobs; q += NT) {
                     const int ch = q / nobs, zo = (q % nobs) / C.obs_nx, xo = q % C.obs_nx;
                     ob[3 * nobs + q] = (float)pr[ch * NCELL + (zo * oz) * NX + xo * ox];
                 }
             )
         }
+    }
+    return do_reset;
+}
+
+// ------------------------------------------------------------------------------------------
+// one action step of one environment (the whole of step_simulation + observation + reward)
+// ------------------------------------------------------------------------------------------
+template <typename Real, bool SPLIT, bool NXT_GLOBAL>
+RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const EnvIO<Real>& io, const Ctx<Real>& X, int env,
+                            const RunFlags& F)
+{
+    const Real gam[3] = {Real(8.0 / 15.0), Real(5.0 / 12.0), Real(3.0 / 4.0)};
+    const Real zet[3] = {Real(0), Real(-17.0 / 60.0), Real(-5.0 / 12.0)};
+    Real* st = io.state + (size_t)env * NSTATE;
+    const VecIO& V = io.vec;
+    // fused vector-env semantics: an environment that truncated on the previous call (next_step mode) is only
+    // re-initialised by this one — gather from the checkpoint bank instead of loading its state, no march
+    const int pend = (V.mode == 1 && V.bank != nullptr && F.advance_clock) ? V.pending[env] : 0;
+    const double t_old = io.t[env];
+    const int nsub = pend ? 0 : F.nsub;
+    const bool project_first = pend ? SPLIT : (F.project_first != 0);
+
+    // load the environment, evaluate the heater profile for this action
+    if (pend) {
+        const double* src = V.bank + (size_t)checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * NSTATE;
+        RBC_PHASE(phase_load_bank(tid, src, X.s0);)
+    } else {
+        RBC_PHASE(
+            phase_load_state(tid, st, X.s0);
+            if (tid < NX) X.Tb[tid] = (Real)heater_T(C, io.actions + (size_t)env * C.heaters, (tid + 0.5) * C.dx);
+        )
+    }
+    Real* cur = X.s0;
+    Real* nxt = X.s1;
+    Real last_dtau = Real(1);
+    if (project_first) project(C, X, cur, T.thomas_scale);
+    for (int sub = 0; sub < nsub; ++sub) {
+        const Real dt = (sub == nsub - 1) ? C.dt_last : C.dt_full;
+        for (int stage = 0; stage < 3; ++stage) {
+            if (SPLIT) { RBC_PHASE(phase_phy(tid, C, cur + OFF_B, X.R);) }
+            const Real* gin = X.gm + ((stage & 1) ? 0 : NSTATE);      // stage s reads what stage s-1 wrote
+            Real* gout = X.gm + ((stage & 1) ? NSTATE : 0);
+            RBC_PHASE(phase_edge_fluxes(tid, cur, X.E);)
+            RBC_PHASE((phase_tendency<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, X.E, gin, gout, dt, gam[stage], zet[stage], stage > 0));)
+            Real* P;
+            if (NXT_GLOBAL) {
+                RBC_PHASE(phase_copy(tid, nxt, cur, NS_SM);)
+                P = cur;
+            } else {
+                P = nxt; nxt = cur; cur = P;
+            }
+            project(C, X, P, T.thomas_scale);
+            last_dtau = (gam[stage] + zet[stage]) * dt;
+        }
+    }
+
+    // the reduction scratch aliases the dead second state buffer when that one is on-chip
+    double* red = NXT_GLOBAL ? X.red : reinterpret_cast<double*>(nxt);
+    const bool changed = nsub > 0 || project_first || pend;
+    if (env_epilogue<Real, SPLIT, NXT_GLOBAL>(C, io, X, env, cur, red, F, changed, last_dtau, t_old, pend, false)) {
+        // same_step auto-reset (or a NaN reset): terminal outputs went to final_*; gather the next episode's start
+        const double* src = V.bank + (size_t)checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * NSTATE;
+        RBC_PHASE(phase_load_bank(tid, src, cur);)
+        if (SPLIT) project(C, X, cur, T.thomas_scale);
+        env_epilogue<Real, SPLIT, NXT_GLOBAL>(C, io, X, env, cur, red, F, true, Real(1), t_old, 0, true);
     }
 }
 

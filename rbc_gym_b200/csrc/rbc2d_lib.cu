@@ -93,12 +93,14 @@ rbc2d_env_kernel(Consts<Real> C, Tables<Real> T, EnvIO<Real> io, Real* gm_all, R
 // (the small kernels below take the grid as run-time arguments: they serve every registered grid)
 template <typename Real>
 __global__ void rbc2d_reset_kernel(Real* state, const double* bank, const int* env_ids, const int* ckpt_idx, int n, int n_ep,
-                                   double* t, int* step, int* trunc, int* nan, int NSTATE)
+                                   double* t, int* step, int* trunc, int* nan, int NSTATE, int B)
 {
+    // indices are validated by the caller (the Python facade raises IndexError like the reference's BoundsError); an entry
+    // that is out of range anyway is skipped rather than allowed to touch another environment or read past the bank
     for (int j = blockIdx.y; j < n; j += gridDim.y) {
         const int env = env_ids ? env_ids[j] : j;
-        int ep = ckpt_idx[j];
-        ep = ep < 0 ? 0 : (ep >= n_ep ? n_ep - 1 : ep);
+        const int ep = ckpt_idx[j];
+        if (env < 0 || env >= B || ep < 0 || ep >= n_ep) continue;
         const double* src = bank + (size_t)ep * NSTATE;
         Real* dst = state + (size_t)env * NSTATE;
         for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < NSTATE; q += gridDim.x * blockDim.x) dst[q] = (Real)src[q];
@@ -108,10 +110,11 @@ __global__ void rbc2d_reset_kernel(Real* state, const double* bank, const int* e
 
 template <typename Real>
 __global__ void rbc2d_set_fields_kernel(Real* state, const double* fields, const int* env_ids, int n, double* t, int* step,
-                                        int* trunc, int* nan, int NSTATE)
+                                        int* trunc, int* nan, int NSTATE, int B)
 {
     for (int j = blockIdx.y; j < n; j += gridDim.y) {
         const int env = env_ids ? env_ids[j] : j;
+        if (env < 0 || env >= B) continue;
         const double* src = fields + (size_t)j * NSTATE;
         Real* dst = state + (size_t)env * NSTATE;
         for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < NSTATE; q += gridDim.x * blockDim.x) dst[q] = (Real)src[q];
@@ -185,7 +188,31 @@ struct rbc2d_sim {
     cudaEvent_t ev0[kRing] = {}, ev1[kRing] = {};
     int64_t timed_launches = 0;
     HostPipe pipe;                                                     // rbc2d_step_host
+    // fused vector-env state (rbc2d_set_autoreset / rbc2d_vec_step_dev)
+    rbc_autoreset ar = {0, 0, 0, 0};
+    int* pending = nullptr;
+    long long* episode = nullptr;
+    double* ep_return = nullptr;
+    int* nan_count = nullptr;
 };
+
+// the kernel-side view of the handle's vector-env state for one launch; `out` supplies the caller's final_* buffers
+static VecIO make_vec(const rbc2d_sim* s, const rbc2d_vec_out* out)
+{
+    VecIO v;
+    v.mode = s->ar.mode;
+    v.nan_reset = s->ar.nan_reset;
+    v.bank = s->bank;
+    v.n_ep = s->n_ep;
+    v.seed = (unsigned long long)s->ar.seed;
+    v.id_offset = (unsigned long long)s->ar.env_id_offset;
+    v.pending = s->pending;
+    v.episode = s->episode;
+    v.ep_return = s->ep_return;
+    v.nan_count = s->nan_count;
+    if (out) { v.final_obs = out->final_obs; v.final_nu_a = out->final_nu_state; v.final_nu_b = out->final_nu_obs; v.final_return = out->final_return; }
+    return v;
+}
 
 template <typename Real>
 static int upload_tables(rbc2d_sim* s)
@@ -218,7 +245,7 @@ static int prepare_kernel(rbc2d_sim* s)
 
 template <typename Real, bool SPLIT>
 static int launch_env(rbc2d_sim* s, const float* actions, float* obs, float* reward, double* nu_s, double* nu_o, int* trunc,
-                      int* nan, const int* env_ids, int n, RunFlags F, bool time_it)
+                      int* nan, const int* env_ids, int n, RunFlags F, bool time_it, const VecIO& vec)
 {
     Consts<Real> C = make_consts<Real>(s->hc, s->wr);
     Tables<Real> T{(const Real*)s->tinv, (const Real*)s->tw48, (const Real*)s->tw96,
@@ -236,6 +263,7 @@ static int launch_env(rbc2d_sim* s, const float* actions, float* obs, float* rew
     io.nan_flag = nan ? nan : s->nan;
     io.pressure = (Real*)s->pressure;
     io.cell_dist = s->wr.shaping ? s->cell_dist : nullptr;   // the peak scan runs only when reward shaping is on
+    io.vec = vec;
     const int grid = n < s->grid ? n : s->grid;
     if (grid <= 0) return 0;
     const int slot = (int)(s->timed_launches % rbc2d_sim::kRing);
@@ -248,7 +276,7 @@ static int launch_env(rbc2d_sim* s, const float* actions, float* obs, float* rew
 }
 
 static int dispatch_env(rbc2d_sim* s, const float* actions, float* obs, float* reward, double* nu_s, double* nu_o, int* trunc,
-                        int* nan, const int* env_ids, int n, RunFlags F, bool time_it)
+                        int* nan, const int* env_ids, int n, RunFlags F, bool time_it, const VecIO& vec = VecIO())
 {
     const bool f32 = s->cfg.precision == 32, split = s->cfg.pressure != 0;
     if (s->plan) {
@@ -265,6 +293,7 @@ static int dispatch_env(rbc2d_sim* s, const float* actions, float* obs, float* r
         io.nan_flag = nan ? nan : s->nan;
         io.cell_dist = s->wr.shaping ? s->cell_dist : nullptr;
         io.pressure = s->pressure;
+        io.vec = vec;
         if (n <= 0) return 0;
         const int slot = (int)(s->timed_launches % rbc2d_sim::kRing);
         if (time_it) CK(cudaEventRecord(s->ev0[slot], s->stream));
@@ -274,10 +303,10 @@ static int dispatch_env(rbc2d_sim* s, const float* actions, float* obs, float* r
         s->launches += 1;
         return 0;
     }
-    if (f32) return split ? launch_env<float, true>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it)
-                          : launch_env<float, false>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it);
-    return split ? launch_env<double, true>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it)
-                 : launch_env<double, false>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it);
+    if (f32) return split ? launch_env<float, true>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it, vec)
+                          : launch_env<float, false>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it, vec);
+    return split ? launch_env<double, true>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it, vec)
+                 : launch_env<double, false>(s, actions, obs, reward, nu_s, nu_o, trunc, nan, env_ids, n, F, time_it, vec);
 }
 
 int rbc_pipe_prepare(HostPipe* p, int B)
@@ -381,6 +410,10 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
     ALLOC(s->reward, B * sizeof(float));
     ALLOC(s->actions, B * (size_t)cfg->heaters * sizeof(float));
     ALLOC(s->cell_dist, B * sizeof(double));
+    ALLOC(s->pending, B * sizeof(int));
+    ALLOC(s->episode, B * sizeof(long long));
+    ALLOC(s->ep_return, B * sizeof(double));
+    ALLOC(s->nan_count, sizeof(int));
 #undef ALLOC
     for (int i = 0; i < rbc2d_sim::kRing; ++i)
         if (cudaEventCreate(&s->ev0[i]) != cudaSuccess || cudaEventCreate(&s->ev1[i]) != cudaSuccess) {
@@ -396,7 +429,8 @@ int rbc2d_destroy(rbc2d_sim* s)
     if (!s) return 0;
     cudaSetDevice(s->cfg.device);
     void* ptrs[] = {s->state, s->gm, s->nxt, s->pressure, s->tinv, s->tw48, s->tw96, s->bank, s->t, s->nu_s, s->nu_o,
-                    s->step, s->trunc, s->nan, s->obs, s->reward, s->actions, s->cell_dist};
+                    s->step, s->trunc, s->nan, s->obs, s->reward, s->actions, s->cell_dist, s->pending, s->episode, s->ep_return,
+                    s->nan_count};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < rbc2d_sim::kRing; ++i) {
         if (s->ev0[i]) cudaEventDestroy(s->ev0[i]);
@@ -444,9 +478,9 @@ int rbc2d_reset_from_checkpoints_dev(rbc2d_sim* s, const int32_t* env_ids, const
     if (n <= 0) return 0;
     dim3 grid(8, n < 4096 ? n : 4096);
     if (s->cfg.precision == 32)
-        rbc2d_reset_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, s->bank, env_ids, ckpt_idx, n, s->n_ep, s->t, s->step, s->trunc, s->nan, s->nstate);
+        rbc2d_reset_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, s->bank, env_ids, ckpt_idx, n, s->n_ep, s->t, s->step, s->trunc, s->nan, s->nstate, s->B);
     else
-        rbc2d_reset_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, s->bank, env_ids, ckpt_idx, n, s->n_ep, s->t, s->step, s->trunc, s->nan, s->nstate);
+        rbc2d_reset_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, s->bank, env_ids, ckpt_idx, n, s->n_ep, s->t, s->step, s->trunc, s->nan, s->nstate, s->B);
     CK(cudaGetLastError());
     s->launches += 1;
     if (s->cfg.pressure) {   // set! projects and leaves pNHS; pHY' follows from b
@@ -471,9 +505,9 @@ int rbc2d_reset_from_fields_host(rbc2d_sim* s, const int32_t* env_ids_host, cons
     }
     dim3 grid(8, n < 4096 ? n : 4096);
     if (s->cfg.precision == 32)
-        rbc2d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, dfields, dids, n, s->t, s->step, s->trunc, s->nan, s->nstate);
+        rbc2d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, dfields, dids, n, s->t, s->step, s->trunc, s->nan, s->nstate, s->B);
     else
-        rbc2d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, dfields, dids, n, s->t, s->step, s->trunc, s->nan, s->nstate);
+        rbc2d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, dfields, dids, n, s->t, s->step, s->trunc, s->nan, s->nstate, s->B);
     CK(cudaGetLastError());
     s->launches += 1;
     int rc = 0;
@@ -493,9 +527,9 @@ int rbc2d_reset_from_fields_dev(rbc2d_sim* s, const int32_t* env_ids, const doub
     CK(cudaSetDevice(s->cfg.device));
     dim3 grid(8, n < 4096 ? n : 4096);
     if (s->cfg.precision == 32)
-        rbc2d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, fields, env_ids, n, s->t, s->step, s->trunc, s->nan, s->nstate);
+        rbc2d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, fields, env_ids, n, s->t, s->step, s->trunc, s->nan, s->nstate, s->B);
     else
-        rbc2d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, fields, env_ids, n, s->t, s->step, s->trunc, s->nan, s->nstate);
+        rbc2d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, fields, env_ids, n, s->t, s->step, s->trunc, s->nan, s->nstate, s->B);
     CK(cudaGetLastError());
     s->launches += 1;
     if (project || s->cfg.pressure) {
@@ -552,6 +586,119 @@ int rbc2d_step_host(rbc2d_sim* s, const float* actions, float* obs, float* rewar
     }
     CK(cudaStreamSynchronize(s->pipe.copy));
     CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int32_t rbc_checkpoint_draw(int64_t seed, int64_t global_env, int64_t episode, int32_t n_episodes)
+{
+    if (n_episodes < 1) return -1;
+    return checkpoint_draw((unsigned long long)seed, (unsigned long long)global_env, (unsigned long long)episode, n_episodes);
+}
+
+int rbc2d_set_autoreset(rbc2d_sim* s, const rbc_autoreset* cfg)
+{
+    if (!s || !cfg) return fail("rbc2d_set_autoreset: bad argument");
+    if (cfg->mode < 0 || cfg->mode > 2) return fail("rbc2d_set_autoreset: mode must be 0 (disabled), 1 (next_step) or 2 (same_step)");
+    s->ar = *cfg;
+    return 0;
+}
+
+// episode bookkeeping of a reset that the caller (or rbc2d_vec_reset_dev) performed on the fields
+__global__ void rbc_vec_mark_kernel(const int* env_ids, int n, long long* episode, double* ep_return, int* pending, int restart)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int env = env_ids ? env_ids[j] : j;
+        episode[env] = restart ? 1 : episode[env] + 1;
+        ep_return[env] = 0.0;
+        pending[env] = 0;
+    }
+}
+// ckpt_idx[env] = draw(seed, offset + env, episode 0)
+__global__ void rbc_vec_draw_kernel(int* idx, int n, unsigned long long seed, unsigned long long offset, int n_ep)
+{
+    for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < n; env += gridDim.x * blockDim.x)
+        idx[env] = checkpoint_draw(seed, offset + (unsigned long long)env, 0ull, n_ep);
+}
+
+}  // extern "C"
+int rbc_vec_mark(cudaStream_t stream, const int* env_ids, int n, long long* episode, double* ep_return, int* pending, int restart)
+{
+    if (n <= 0) return 0;
+    rbc_vec_mark_kernel<<<(n + 255) / 256, 256, 0, stream>>>(env_ids, n, episode, ep_return, pending, restart);
+    CK(cudaGetLastError());
+    return 0;
+}
+int rbc_vec_draw(cudaStream_t stream, int* idx, int n, unsigned long long seed, unsigned long long offset, int n_ep)
+{
+    rbc_vec_draw_kernel<<<(n + 255) / 256, 256, 0, stream>>>(idx, n, seed, offset, n_ep);
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" {
+
+int rbc2d_vec_mark_reset_dev(rbc2d_sim* s, const int32_t* env_ids, int32_t n)
+{
+    if (!s) return fail("null handle");
+    CK(cudaSetDevice(s->cfg.device));
+    if (!env_ids) n = s->B;
+    s->launches += 1;
+    return rbc_vec_mark(s->stream, env_ids, n, s->episode, s->ep_return, s->pending, 0);
+}
+
+int rbc2d_vec_reset_dev(rbc2d_sim* s, const int32_t* ckpt_idx)
+{
+    if (!s) return fail("null handle");
+    if (!s->bank) return fail("rbc2d_vec_reset_dev: no checkpoint bank loaded");
+    CK(cudaSetDevice(s->cfg.device));
+    if (!ckpt_idx) {
+        // the draw of episode 0, into the pending array (idle until the mark kernel below clears it)
+        int rcd = rbc_vec_draw(s->stream, s->pending, s->B, (unsigned long long)s->ar.seed, (unsigned long long)s->ar.env_id_offset, s->n_ep);
+        if (rcd) return rcd;
+        s->launches += 1;
+        ckpt_idx = s->pending;
+    }
+    int rc = rbc2d_reset_from_checkpoints_dev(s, nullptr, ckpt_idx, s->B);
+    if (rc) return rc;
+    rc = rbc_vec_mark(s->stream, nullptr, s->B, s->episode, s->ep_return, s->pending, 1);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(s->nan_count, 0, sizeof(int), s->stream));
+    s->launches += 1;
+    return 0;
+}
+
+int rbc2d_vec_step_dev(rbc2d_sim* s, const float* actions, const rbc2d_vec_out* out)
+{
+    if (!s || !actions || !out || !out->obs) return fail("rbc2d_vec_step_dev: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    Consts<float> tmp = make_consts<float>(s->hc);
+    RunFlags F{tmp.nsub, 0, 1};
+    int rc = dispatch_env(s, actions, out->obs, out->reward, out->nu_state, out->nu_obs, out->truncated, out->nan, nullptr, s->B, F, true,
+                          make_vec(s, out));
+    if (rc) return rc;
+    // info["t"], info["step"], running returns: plain device copies on the same stream, no synchronisation
+    if (out->t) CK(cudaMemcpyAsync(out->t, s->t, (size_t)s->B * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    if (out->step) CK(cudaMemcpyAsync(out->step, s->step, (size_t)s->B * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+    if (out->episode_return) CK(cudaMemcpyAsync(out->episode_return, s->ep_return, (size_t)s->B * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
+
+int rbc2d_vec_nan_count(rbc2d_sim* s, int32_t clear, int64_t* count)
+{
+    if (!s || !count) return fail("rbc2d_vec_nan_count: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, s->nan_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (clear) CK(cudaMemsetAsync(s->nan_count, 0, sizeof(int), s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *count = h;
+    return 0;
+}
+
+int rbc2d_vec_nan_count_async(rbc2d_sim* s, int32_t* count_host)
+{
+    if (!s || !count_host) return fail("rbc2d_vec_nan_count_async: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpyAsync(count_host, s->nan_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     return 0;
 }
 

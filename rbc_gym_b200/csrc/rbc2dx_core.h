@@ -261,8 +261,8 @@ template <typename G> RBC_HD int ord_ce_cen(int kc) { return (kc >= 1 && kc <= G
 // ------------------------------------------------------------------------------------------
 // phase: load the slab (with halos) of one environment from the checkpoint layout in global memory
 // ------------------------------------------------------------------------------------------
-template <typename G, typename Real>
-RBC_HD void phase_load_state(int tid, int rank, const Real* RBC_RESTRICT g, Real* RBC_RESTRICT sm)
+template <typename G, typename Real, typename Src>
+RBC_HD void phase_load_state(int tid, int rank, const Src* RBC_RESTRICT g, Real* RBC_RESTRICT sm)
 {
     const int k0 = rank * G::NZL - G::HALO;
     for (int q = tid; q < 3 * G::LR * G::NX; q += G::NT) {
@@ -270,7 +270,7 @@ RBC_HD void phase_load_state(int tid, int rank, const Real* RBC_RESTRICT g, Real
         const int k = k0 + lr;
         const int kmax = (f == 2) ? G::NZ : G::NZ - 1;
         const int goff = (f == 0) ? G::GOFF_B : (f == 1 ? G::GOFF_U : G::GOFF_W);
-        sm[f * G::LR * G::SX + lr * G::SX + i] = (k >= 0 && k <= kmax) ? g[goff + k * G::NX + i] : Real(0);
+        sm[f * G::LR * G::SX + lr * G::SX + i] = (k >= 0 && k <= kmax) ? (Real)g[goff + k * G::NX + i] : Real(0);
     }
 }
 template <typename G, typename Real>
@@ -990,67 +990,36 @@ RBC_HD void hydrostatic(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_s
     S.n[CH_P] += 1;
 }
 
-template <typename G, typename Real, bool NXT_GLOBAL, bool SPLIT = false>
-RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, const RunFlags& F, int my_rank,
-                            SyncState& S)
+// sum over the CTAs of the cluster of entry `idx` of their cfin blocks (valid after the cluster barrier that follows the
+// phase writing them); every thread of every CTA gets the same value
+template <typename G, typename Real>
+RBC_HD double cluster_cfin_sum(const CtxX<Real>& X, int my_rank, int idx)
+{
+    double tot = 0;
+#if defined(__CUDA_ARCH__)
+    double* mine = reinterpret_cast<double*>(X.base + X.o_cfin);
+    for (int j = 0; j < G::CL; ++j) tot += (j == my_rank) ? mine[idx] : peer_ptr(X.base, X.arena_stride, mine, my_rank, j)[idx];
+#else
+    (void)my_rank;
+    for (int j = 0; j < G::CL; ++j) tot += reinterpret_cast<const double*>(X.base + j * X.arena_stride + X.o_cfin)[idx];
+#endif
+    return tot;
+}
+
+// epilogue of an action step (see rbc2d::env_epilogue): runs once per environment visit, and again (second_pass) after an
+// in-launch re-initialisation from the checkpoint bank.  Returns whether such a reset is due.
+template <typename G, typename Real, bool NXT_GLOBAL, bool SPLIT>
+RBC_HD_COLD bool env_epilogue(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, const RunFlags& F, int my_rank,
+                              SyncState& S, unsigned o_cur, unsigned o_nxt, Real last_dtau, bool state_changed, double t_old, int pend,
+                              bool second_pass)
 {
     (void)my_rank;
-    constexpr bool ASYNC = RBX_ASYNC(G, NXT_GLOBAL);
     constexpr int NX = G::NX, NZ = G::NZ, NZL = G::NZL, NT = G::NT, CL = G::CL, SX = G::SX, H = G::HALO, NRED = G::NRED, NFIN = G::NFIN;
-    const Real gam[3] = {Real(8.0 / 15.0), Real(5.0 / 12.0), Real(3.0 / 4.0)};
-    const Real zet[3] = {Real(0), Real(-17.0 / 60.0), Real(-5.0 / 12.0)};
+    const rbc2d::VecIO& V = io.vec;
     Real* st = io.state + (size_t)env * G::NSTATE;
-
-    RBX_PHASE_L(G,
-        phase_load_state<G>(tid, rank, st, RBX_PTR(X.o_s0));
-        if (tid < NX) RBX_PTR(X.o_Tb)[tid] = (Real)rbc2d::heater_T(C, io.actions + (size_t)env * C.heaters, (tid + 0.5) * C.dx);
-    )
-    unsigned o_cur = X.o_s0, o_nxt = X.o_s1;               // fp64 mode: o_s1 is unused, the predicted state is global
-    Real last_dtau = Real(1);                              // set! projects with dtau = 1
-    if (F.project_first) project<G, Real, NXT_GLOBAL, SPLIT>(C, X, o_cur, o_nxt, my_rank, S, false);
-    for (int sub = 0; sub < F.nsub; ++sub) {
-        const Real dt = (sub == F.nsub - 1) ? C.dt_last : C.dt_full;
-        for (int stage = 0; stage < 3; ++stage) {
-            const int in_slab = (stage & 1) ? 0 : 1, out_slab = 1 - in_slab;
-            if (SPLIT) hydrostatic<G, Real, NXT_GLOBAL>(C, X, o_cur, my_rank, S);
-            RBX_PHASE_L(G, phase_edge_fluxes<G>(tid, rank, RBX_PTR(o_cur), RBX_PTR(X.o_edge));)
-            RBX_PHASE_X(G, ASYNC,
-                Real* cur = RBX_PTR(o_cur);
-                Real* nxt;
-                PeerBuf<Real> below_h; PeerBuf<Real> below_w; PeerBuf<Real> above_h;
-                if (NXT_GLOBAL) {
-                    nxt = X.nxt_g + (size_t)rank * G::NS_SM;
-                    below_h.p = rank > 0 ? nxt - G::NS_SM : nullptr; below_h.addr = 0; below_h.bar = 0;
-                    above_h.p = rank < CL - 1 ? nxt + G::NS_SM : nullptr; above_h.addr = 0; above_h.bar = 0;
-                    below_w = below_h;
-                } else {
-                    nxt = RBX_PTR(o_nxt);
-                    const unsigned hb = bar_off(X.o_bars, CH_H, S.n[CH_H]);
-                    const unsigned wb = bar_off(X.o_bars, CH_W, S.n[CH_W]);
-                    below_h = make_peer<ASYNC, Real>(X, smb, o_nxt, hb, rank, rank - 1, CL > 1 && rank > 0);
-                    below_w = make_peer<ASYNC, Real>(X, smb, o_nxt, wb, rank, rank - 1, CL > 1 && rank > 0);
-                    above_h = make_peer<ASYNC, Real>(X, smb, o_nxt, hb, rank, rank + 1, CL > 1 && rank < CL - 1);
-                }
-                Real* gmr = X.gm + (size_t)rank * 2 * G::NLOC;
-                phase_tendency<G, ASYNC, SPLIT>(tid, rank, C, cur, nxt, below_h, below_w, above_h, SPLIT ? RBX_PTR(X.o_R) : nullptr, RBX_PTR(X.o_Tb), RBX_PTR(X.o_edge), gmr + in_slab * G::NLOC,
-                                         gmr + out_slab * G::NLOC, dt, gam[stage], zet[stage], stage > 0);
-            )
-            unsigned o_p;
-            if (NXT_GLOBAL) {
-                RBX_PHASE_L(G, phase_copy(tid, NT, X.nxt_g + (size_t)rank * G::NS_SM, RBX_PTR(o_cur), G::NS_SM);)
-                o_p = o_cur;
-            } else {
-                o_p = o_nxt; o_nxt = o_cur; o_cur = o_p;
-            }
-            project<G, Real, NXT_GLOBAL, SPLIT>(C, X, o_p, NXT_GLOBAL ? o_p : o_nxt, my_rank, S, true);
-            last_dtau = (gam[stage] + zet[stage]) * dt;
-        }
-    }
-
-    // ---- epilogue: NaN check, observation, Nusselt numbers, reward, bookkeeping ----
     const int oz = NZ / C.obs_nz, ox = NX / C.obs_nx, nobs = C.obs_nz * C.obs_nx;
     const unsigned o_red = (X.o_red != ~0u) ? X.o_red : o_nxt;   // fp32: the dead state buffer when it is large enough
-    if (SPLIT && io.pressure != nullptr && (F.nsub > 0 || F.project_first)) {
+    if (SPLIT && io.pressure != nullptr && state_changed) {
         // pressure fields of get_state (rbc_sim2D_api.jl:114-115), kept per environment as in rbc2d_core.h:
         // pNHS = phi / dtau of the last stage in the zero-mean gauge (the mean needs the whole cluster), then
         // pHY' recomputed from the final b
@@ -1143,10 +1112,17 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
             cfin[NRED] = cd;
         }
     )
+    // decisions every thread of every CTA takes alike (cfin blocks are complete: cluster barrier above)
+    const bool vec = V.mode >= 0 && F.advance_clock;
+    const bool stepping = F.advance_clock && !pend && !second_pass;
+    const bool trunc_now = stepping && (t_old + C.dt_action >= C.episode_length);
+    const bool bad_reset = vec && stepping && V.nan_reset && cluster_cfin_sum<G>(X, my_rank, 6) > 0;
+    const bool do_reset = vec && stepping && V.bank != nullptr && ((V.mode == 2 && trunc_now) || bad_reset);
+    float* const ob_base = ((do_reset && V.final_obs != nullptr) ? V.final_obs : io.obs) + (size_t)env * C.channels * nobs;
     RBX_PHASE_C(G,
         const Real* cur = RBX_PTR(o_cur);
-        if (F.nsub > 0 || F.project_first) phase_store_state<G>(tid, rank, cur, st);
-        float* ob = io.obs + (size_t)env * C.channels * nobs;
+        if (state_changed && !do_reset) phase_store_state<G>(tid, rank, cur, st);
+        float* ob = ob_base;
         for (int q = tid; q < 3 * nobs; q += NT) {
             const int ch = q / nobs; const int zo = (q % nobs) / C.obs_nx; const int xo = q % C.obs_nx;
             const int k = zo * oz;
@@ -1189,21 +1165,136 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
             if (C.wrap_shaping || io.cell_dist != nullptr) {
                 const double PI = 3.14159265358979323846;
                 const double cd = tot[NRED];
-                if (io.cell_dist != nullptr) io.cell_dist[env] = cd;
+                if (io.cell_dist != nullptr && !second_pass) io.cell_dist[env] = cd;
                 if (C.wrap_shaping) rew = (1.0 - C.shaping_weight) * rew + C.shaping_weight * ((PI - cd) / PI);
             }
-            io.nu_state[env] = nu_s;
-            io.nu_obs[env] = nu_o;
-            io.reward[env] = (float)rew;
-            io.nan_flag[env] = tot[6] > 0 ? 1 : 0;
-            if (F.advance_clock) {
-                const double tn = io.t[env] + C.dt_action;
-                io.t[env] = tn;
-                io.step_count[env] += 1;
-                io.truncated[env] = tn >= C.episode_length ? 1 : 0;
+            const bool bad = tot[6] > 0;
+            if (second_pass) {
+                io.nu_state[env] = nu_s;
+                io.nu_obs[env] = nu_o;
+                io.t[env] = 0.0;
+                io.step_count[env] = 1;
+                V.episode[env] += 1;
+                V.ep_return[env] = 0.0;
+                if (V.pending != nullptr) V.pending[env] = 0;
+            } else if (pend) {
+                io.nan_flag[env] = bad ? 1 : 0;
+                io.nu_state[env] = nu_s;
+                io.nu_obs[env] = nu_o;
+                io.reward[env] = 0.0f;
+                io.truncated[env] = 0;
+                io.t[env] = 0.0;
+                io.step_count[env] = 1;
+                V.episode[env] += 1;
+                V.ep_return[env] = 0.0;
+                V.pending[env] = 0;
+            } else {
+                io.nan_flag[env] = bad ? 1 : 0;
+                if (bad_reset) rew = 0.0;
+                if (bad && vec && V.nan_count != nullptr) RBC_COUNT_ONE(V.nan_count);
+                io.reward[env] = (float)rew;
+                const double ret = vec ? V.ep_return[env] + (double)(float)rew : 0.0;
+                if (do_reset) {
+                    if (V.final_nu_a != nullptr) V.final_nu_a[env] = nu_s;
+                    if (V.final_nu_b != nullptr) V.final_nu_b[env] = nu_o;
+                    if (V.final_return != nullptr) V.final_return[env] = ret;
+                    io.truncated[env] = 1;
+                } else {
+                    io.nu_state[env] = nu_s;
+                    io.nu_obs[env] = nu_o;
+                    if (F.advance_clock) {
+                        const double tn = t_old + C.dt_action;
+                        io.t[env] = tn;
+                        io.step_count[env] += 1;
+                        io.truncated[env] = (trunc_now || bad_reset) ? 1 : 0;
+                    }
+                    if (vec) {
+                        V.ep_return[env] = ret;
+                        if (V.pending != nullptr) V.pending[env] = (V.mode == 1 && trunc_now && V.bank != nullptr) ? 1 : 0;
+                    }
+                }
             }
         }
     )
+    return do_reset;
+}
+
+template <typename G, typename Real, bool NXT_GLOBAL, bool SPLIT = false>
+RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, const RunFlags& F, int my_rank,
+                            SyncState& S)
+{
+    (void)my_rank;
+    constexpr bool ASYNC = RBX_ASYNC(G, NXT_GLOBAL);
+    constexpr int NX = G::NX, NZ = G::NZ, NZL = G::NZL, NT = G::NT, CL = G::CL, SX = G::SX, H = G::HALO, NRED = G::NRED, NFIN = G::NFIN;
+    const Real gam[3] = {Real(8.0 / 15.0), Real(5.0 / 12.0), Real(3.0 / 4.0)};
+    const Real zet[3] = {Real(0), Real(-17.0 / 60.0), Real(-5.0 / 12.0)};
+    Real* st = io.state + (size_t)env * G::NSTATE;
+    const rbc2d::VecIO& V = io.vec;
+    // fused vector-env semantics (rbc2d_core.h): a pending environment is only re-initialised from the checkpoint bank
+    const int pend = (V.mode == 1 && V.bank != nullptr && F.advance_clock) ? V.pending[env] : 0;
+    const double t_old = io.t[env];
+    const int nsub = pend ? 0 : F.nsub;
+    const bool project_first = pend ? SPLIT : (F.project_first != 0);
+
+    if (pend) {
+        const double* src = V.bank + (size_t)rbc2d::checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * G::NSTATE;
+        RBX_PHASE_L(G, phase_load_state<G>(tid, rank, src, RBX_PTR(X.o_s0));)
+    } else {
+        RBX_PHASE_L(G,
+            phase_load_state<G>(tid, rank, st, RBX_PTR(X.o_s0));
+            if (tid < NX) RBX_PTR(X.o_Tb)[tid] = (Real)rbc2d::heater_T(C, io.actions + (size_t)env * C.heaters, (tid + 0.5) * C.dx);
+        )
+    }
+    unsigned o_cur = X.o_s0, o_nxt = X.o_s1;               // fp64 mode: o_s1 is unused, the predicted state is global
+    Real last_dtau = Real(1);                              // set! projects with dtau = 1
+    if (project_first) project<G, Real, NXT_GLOBAL, SPLIT>(C, X, o_cur, o_nxt, my_rank, S, false);
+    for (int sub = 0; sub < nsub; ++sub) {
+        const Real dt = (sub == nsub - 1) ? C.dt_last : C.dt_full;
+        for (int stage = 0; stage < 3; ++stage) {
+            const int in_slab = (stage & 1) ? 0 : 1, out_slab = 1 - in_slab;
+            if (SPLIT) hydrostatic<G, Real, NXT_GLOBAL>(C, X, o_cur, my_rank, S);
+            RBX_PHASE_L(G, phase_edge_fluxes<G>(tid, rank, RBX_PTR(o_cur), RBX_PTR(X.o_edge));)
+            RBX_PHASE_X(G, ASYNC,
+                Real* cur = RBX_PTR(o_cur);
+                Real* nxt;
+                PeerBuf<Real> below_h; PeerBuf<Real> below_w; PeerBuf<Real> above_h;
+                if (NXT_GLOBAL) {
+                    nxt = X.nxt_g + (size_t)rank * G::NS_SM;
+                    below_h.p = rank > 0 ? nxt - G::NS_SM : nullptr; below_h.addr = 0; below_h.bar = 0;
+                    above_h.p = rank < CL - 1 ? nxt + G::NS_SM : nullptr; above_h.addr = 0; above_h.bar = 0;
+                    below_w = below_h;
+                } else {
+                    nxt = RBX_PTR(o_nxt);
+                    const unsigned hb = bar_off(X.o_bars, CH_H, S.n[CH_H]);
+                    const unsigned wb = bar_off(X.o_bars, CH_W, S.n[CH_W]);
+                    below_h = make_peer<ASYNC, Real>(X, smb, o_nxt, hb, rank, rank - 1, CL > 1 && rank > 0);
+                    below_w = make_peer<ASYNC, Real>(X, smb, o_nxt, wb, rank, rank - 1, CL > 1 && rank > 0);
+                    above_h = make_peer<ASYNC, Real>(X, smb, o_nxt, hb, rank, rank + 1, CL > 1 && rank < CL - 1);
+                }
+                Real* gmr = X.gm + (size_t)rank * 2 * G::NLOC;
+                phase_tendency<G, ASYNC, SPLIT>(tid, rank, C, cur, nxt, below_h, below_w, above_h, SPLIT ? RBX_PTR(X.o_R) : nullptr, RBX_PTR(X.o_Tb), RBX_PTR(X.o_edge), gmr + in_slab * G::NLOC,
+                                         gmr + out_slab * G::NLOC, dt, gam[stage], zet[stage], stage > 0);
+            )
+            unsigned o_p;
+            if (NXT_GLOBAL) {
+                RBX_PHASE_L(G, phase_copy(tid, NT, X.nxt_g + (size_t)rank * G::NS_SM, RBX_PTR(o_cur), G::NS_SM);)
+                o_p = o_cur;
+            } else {
+                o_p = o_nxt; o_nxt = o_cur; o_cur = o_p;
+            }
+            project<G, Real, NXT_GLOBAL, SPLIT>(C, X, o_p, NXT_GLOBAL ? o_p : o_nxt, my_rank, S, true);
+            last_dtau = (gam[stage] + zet[stage]) * dt;
+        }
+    }
+
+    const bool changed = nsub > 0 || project_first || pend;
+    if (env_epilogue<G, Real, NXT_GLOBAL, SPLIT>(C, io, X, env, F, my_rank, S, o_cur, o_nxt, last_dtau, changed, t_old, pend, false)) {
+        // same_step auto-reset (or a NaN reset): terminal outputs went to final_*; gather the next episode's start
+        const double* src = V.bank + (size_t)rbc2d::checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * G::NSTATE;
+        RBX_PHASE_L(G, phase_load_state<G>(tid, rank, src, RBX_PTR(o_cur));)
+        if (SPLIT) project<G, Real, NXT_GLOBAL, SPLIT>(C, X, o_cur, o_nxt, my_rank, S, false);
+        env_epilogue<G, Real, NXT_GLOBAL, SPLIT>(C, io, X, env, F, my_rank, S, o_cur, o_nxt, Real(1), true, t_old, 0, true);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

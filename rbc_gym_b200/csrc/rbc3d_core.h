@@ -89,6 +89,7 @@ struct EnvIO3 {
     int* step_count;
     int* truncated;
     int* nan_flag;
+    rbc2d::VecIO vec;         // fused vector-env semantics (rbc2d_core.h); final_nu_a = terminal nusselt, final_obs [B][4][NZ][NY][NX]
 };
 
 template <typename Real>
@@ -609,47 +610,15 @@ RBC_HD void project3(const Consts3<Real>& C, const Ctx3<Real>& X, Real* p)
 }
 
 // ------------------------------------------------------------------------------------------
-// one action step of one 3D environment
+// epilogue of a 3D action step: write back, observation (= get_state), Nusselt number, NaN flag, clock and the fused
+// vector-env bookkeeping (see rbc2d::env_epilogue).  Returns whether an in-launch re-initialisation is due.
 // ------------------------------------------------------------------------------------------
-template <typename Real, bool SPLIT, bool TILED = false>
-RBC_HD void env_action_step3(const Consts3<Real>& C, const EnvIO3<Real>& io, const Ctx3<Real>& X, int env, const RunFlags3& F)
+template <typename Real>
+RBC_HD_COLD bool env_epilogue3(const Consts3<Real>& C, const EnvIO3<Real>& io, const Ctx3<Real>& X, int env, const Real* cur, const RunFlags3& F,
+                               double t_old, int pend, bool second_pass)
 {
-    static_assert(!(TILED && SPLIT), "the tile aliases the scratch that holds pHY' in split mode");
-    const Real gam[3] = {Real(8.0 / 15.0), Real(5.0 / 12.0), Real(3.0 / 4.0)};
-    const Real zet[3] = {Real(0), Real(-17.0 / 60.0), Real(-5.0 / 12.0)};
+    const rbc2d::VecIO& V = io.vec;
     Real* st = io.state + (size_t)env * NSTATE;
-    RBC3_PHASE(
-        for (int q = 0; q < NCOL / NT; ++q) {
-            const int c = tid + q * NT;
-            X.Tb[c] = (Real)heater_T3(C, io.actions + (size_t)env * C.heaters * C.heaters, c % NX, c / NX);
-        }
-    )
-    if (F.project_first) project3(C, X, st);
-    Real* cur = st;                        // stage 1 reads the environment's own array, then A <-> B ping-pong
-    Real* nxt = X.bufA;
-    int stage_no = 0;
-    for (int sub = 0; sub < F.nsub; ++sub) {
-        const Real dt = (sub == F.nsub - 1) ? C.dt_last : C.dt_full;
-        for (int stage = 0; stage < 3; ++stage, ++stage_no) {
-            if (SPLIT) { RBC3_PHASE(phase_phy3(tid, C, cur + GB, X.R);) }
-            // one tendency slab, updated in place: every (column, level) entry is read (previous stage) and then
-            // rewritten by the same thread, which halves the per-CTA footprint of the slabs in L2
-            const Real* gin = X.gm;
-            Real* gout = X.gm;
-            if (TILED) {
-                for (int h = 0; h < 2; ++h) {
-                    RBC3_PHASE(phase_load_tile3(tid, cur, X.tile, h);)
-                    RBC3_PHASE((phase_tendency3_tile<Real, false>(tid, C, X.tile, nxt, X.R, X.Tb, gin, stage < 2 ? gout : nullptr, dt, gam[stage], zet[stage], stage > 0, h));)
-                }
-            } else {
-                RBC3_PHASE((phase_tendency3<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, gin, stage < 2 ? gout : nullptr, dt, gam[stage], zet[stage], stage > 0));)
-            }
-            project3(C, X, nxt);
-            cur = nxt;
-            nxt = (cur == X.bufA) ? X.bufB : X.bufA;
-        }
-    }
-    // ---- epilogue: write back, observation (= get_state), Nusselt number, NaN flag, clock ----
     RBC3_PHASE(
         double acc = 0, bad = 0;
         for (int q = 0; q < NCOL / NT; ++q) {
@@ -672,25 +641,125 @@ RBC_HD void env_action_step3(const Consts3<Real>& C, const EnvIO3<Real>& io, con
     double fin3[2];
 #endif
     RBC3_PHASE(if (tid < 2) fin3[tid] = sum_serial(X.red + tid * NT, NT);)
+    const bool vec = V.mode >= 0 && F.advance_clock;
+    const bool bad = fin3[1] > 0;
+    const bool stepping = F.advance_clock && !pend && !second_pass;
+    const bool trunc_now = stepping && (t_old + C.dt_action >= C.episode_length);
+    const bool bad_reset = vec && stepping && V.nan_reset && bad;
+    const bool do_reset = vec && stepping && V.bank != nullptr && ((V.mode == 2 && trunc_now) || bad_reset);
+    float* const ob_base = (do_reset && V.final_obs != nullptr) ? V.final_obs : io.obs;
     RBC3_PHASE(
-        if (cur != st) { for (int q = tid; q < NSTATE; q += NT) st[q] = cur[q]; }
-        if (io.obs != nullptr) {
-            float* ob = io.obs + (size_t)env * 4 * NC;
+        if (cur != st && !do_reset) { for (int q = tid; q < NSTATE; q += NT) st[q] = cur[q]; }
+        if (ob_base != nullptr && !(do_reset && V.final_obs == nullptr)) {
+            float* ob = ob_base + (size_t)env * 4 * NC;
             for (int q = tid; q < 4 * NC; q += NT) ob[q] = (float)cur[q];        // b,u,v and w faces 0..NZ-1 are contiguous
         }
         if (tid == 0) {
             const double nu = 1.0 + (fin3[0] / (double)NC) / C.kappa_d;
-            io.nusselt[env] = nu;
-            io.reward[env] = (float)(-nu);
-            io.nan_flag[env] = fin3[1] > 0 ? 1 : 0;
-            if (F.advance_clock) {
-                const double tn = io.t[env] + C.dt_action;
-                io.t[env] = tn;
-                io.step_count[env] += 1;
-                io.truncated[env] = tn >= C.episode_length ? 1 : 0;
+            if (second_pass) {
+                io.nusselt[env] = nu;
+                io.t[env] = 0.0;
+                io.step_count[env] = 1;
+                V.episode[env] += 1;
+                V.ep_return[env] = 0.0;
+                if (V.pending != nullptr) V.pending[env] = 0;
+            } else if (pend) {
+                io.nusselt[env] = nu;
+                io.reward[env] = 0.0f;
+                io.nan_flag[env] = bad ? 1 : 0;
+                io.truncated[env] = 0;
+                io.t[env] = 0.0;
+                io.step_count[env] = 1;
+                V.episode[env] += 1;
+                V.ep_return[env] = 0.0;
+                V.pending[env] = 0;
+            } else {
+                double rew = -nu;
+                if (bad_reset) rew = 0.0;
+                if (bad && vec && V.nan_count != nullptr) RBC_COUNT_ONE(V.nan_count);
+                io.reward[env] = (float)rew;
+                io.nan_flag[env] = bad ? 1 : 0;
+                const double ret = vec ? V.ep_return[env] + (double)(float)rew : 0.0;
+                if (do_reset) {
+                    if (V.final_nu_a != nullptr) V.final_nu_a[env] = nu;
+                    if (V.final_return != nullptr) V.final_return[env] = ret;
+                    io.truncated[env] = 1;
+                } else {
+                    io.nusselt[env] = nu;
+                    if (F.advance_clock) {
+                        const double tn = t_old + C.dt_action;
+                        io.t[env] = tn;
+                        io.step_count[env] += 1;
+                        io.truncated[env] = (trunc_now || bad_reset) ? 1 : 0;
+                    }
+                    if (vec) {
+                        V.ep_return[env] = ret;
+                        if (V.pending != nullptr) V.pending[env] = (V.mode == 1 && trunc_now && V.bank != nullptr) ? 1 : 0;
+                    }
+                }
             }
         }
     )
+    return do_reset;
+}
+
+// ------------------------------------------------------------------------------------------
+// one action step of one 3D environment
+// ------------------------------------------------------------------------------------------
+template <typename Real, bool SPLIT, bool TILED = false>
+RBC_HD void env_action_step3(const Consts3<Real>& C, const EnvIO3<Real>& io, const Ctx3<Real>& X, int env, const RunFlags3& F)
+{
+    static_assert(!(TILED && SPLIT), "the tile aliases the scratch that holds pHY' in split mode");
+    const Real gam[3] = {Real(8.0 / 15.0), Real(5.0 / 12.0), Real(3.0 / 4.0)};
+    const Real zet[3] = {Real(0), Real(-17.0 / 60.0), Real(-5.0 / 12.0)};
+    Real* st = io.state + (size_t)env * NSTATE;
+    const rbc2d::VecIO& V = io.vec;
+    // fused vector-env semantics: a pending environment (next_step mode) is only re-initialised from the checkpoint bank
+    const int pend = (V.mode == 1 && V.bank != nullptr && F.advance_clock) ? V.pending[env] : 0;
+    const double t_old = io.t[env];
+    const int nsub = pend ? 0 : F.nsub;
+    if (pend) {
+        const double* src = V.bank + (size_t)rbc2d::checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * NSTATE;
+        RBC3_PHASE(for (int q = tid; q < NSTATE; q += NT) st[q] = (Real)src[q];)
+    } else {
+        RBC3_PHASE(
+            for (int q = 0; q < NCOL / NT; ++q) {
+                const int c = tid + q * NT;
+                X.Tb[c] = (Real)heater_T3(C, io.actions + (size_t)env * C.heaters * C.heaters, c % NX, c / NX);
+            }
+        )
+    }
+    if (F.project_first && !pend) project3(C, X, st);
+    Real* cur = st;                        // stage 1 reads the environment's own array, then A <-> B ping-pong
+    Real* nxt = X.bufA;
+    int stage_no = 0;
+    for (int sub = 0; sub < nsub; ++sub) {
+        const Real dt = (sub == nsub - 1) ? C.dt_last : C.dt_full;
+        for (int stage = 0; stage < 3; ++stage, ++stage_no) {
+            if (SPLIT) { RBC3_PHASE(phase_phy3(tid, C, cur + GB, X.R);) }
+            // one tendency slab, updated in place: every (column, level) entry is read (previous stage) and then
+            // rewritten by the same thread, which halves the per-CTA footprint of the slabs in L2
+            const Real* gin = X.gm;
+            Real* gout = X.gm;
+            if (TILED) {
+                for (int h = 0; h < 2; ++h) {
+                    RBC3_PHASE(phase_load_tile3(tid, cur, X.tile, h);)
+                    RBC3_PHASE((phase_tendency3_tile<Real, false>(tid, C, X.tile, nxt, X.R, X.Tb, gin, stage < 2 ? gout : nullptr, dt, gam[stage], zet[stage], stage > 0, h));)
+                }
+            } else {
+                RBC3_PHASE((phase_tendency3<Real, SPLIT>(tid, C, cur, nxt, X.R, X.Tb, gin, stage < 2 ? gout : nullptr, dt, gam[stage], zet[stage], stage > 0));)
+            }
+            project3(C, X, nxt);
+            cur = nxt;
+            nxt = (cur == X.bufA) ? X.bufB : X.bufA;
+        }
+    }
+    if (env_epilogue3(C, io, X, env, cur, F, t_old, pend, false)) {
+        // same_step auto-reset (or a NaN reset): terminal outputs went to final_*; gather the next episode's start
+        const double* src = V.bank + (size_t)rbc2d::checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * NSTATE;
+        RBC3_PHASE(for (int q = tid; q < NSTATE; q += NT) st[q] = (Real)src[q];)
+        env_epilogue3(C, io, X, env, st, F, t_old, 0, true);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

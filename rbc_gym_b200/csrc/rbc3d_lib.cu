@@ -47,12 +47,13 @@ rbc3d_env_kernel(Consts3<Real> C, EnvIO3<Real> io, Real* buf_all, Real* gm_all, 
 
 template <typename Real>
 __global__ void rbc3d_set_fields_kernel(Real* state, const double* fields, const int* env_ids, const int* src_idx, int n, int n_src,
-                                        double* t, int* step, int* trunc, int* nan)
+                                        double* t, int* step, int* trunc, int* nan, int B)
 {
+    // indices are validated by the caller (IndexError in the Python facade); out-of-range entries are skipped, never clamped
     for (int j = blockIdx.y; j < n; j += gridDim.y) {
         const int env = env_ids ? env_ids[j] : j;
-        int sidx = src_idx ? src_idx[j] : j;
-        sidx = sidx < 0 ? 0 : (sidx >= n_src ? n_src - 1 : sidx);
+        const int sidx = src_idx ? src_idx[j] : j;
+        if (env < 0 || env >= B || sidx < 0 || sidx >= n_src) continue;
         const double* src = fields + (size_t)sidx * NSTATE;
         Real* dst = state + (size_t)env * NSTATE;
         for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < NSTATE; q += gridDim.x * blockDim.x) dst[q] = (Real)src[q];
@@ -81,7 +82,30 @@ struct rbc3d_sim {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     HostPipe pipe;                   // rbc3d_step_host
+    // fused vector-env state (rbc3d_set_autoreset / rbc3d_vec_step_dev)
+    rbc_autoreset ar = {0, 0, 0, 0};
+    int* pending = nullptr;
+    long long* episode = nullptr;
+    double* ep_return = nullptr;
+    int* nan_count = nullptr;
 };
+
+static rbc2d::VecIO make_vec3(const rbc3d_sim* s, const rbc3d_vec_out* out)
+{
+    rbc2d::VecIO v;
+    v.mode = s->ar.mode;
+    v.nan_reset = s->ar.nan_reset;
+    v.bank = s->bank;
+    v.n_ep = s->n_ep;
+    v.seed = (unsigned long long)s->ar.seed;
+    v.id_offset = (unsigned long long)s->ar.env_id_offset;
+    v.pending = s->pending;
+    v.episode = s->episode;
+    v.ep_return = s->ep_return;
+    v.nan_count = s->nan_count;
+    if (out) { v.final_obs = out->final_obs; v.final_nu_a = out->final_nusselt; v.final_return = out->final_return; }
+    return v;
+}
 
 // fp32 without the hydrostatic split runs the tiled tendency phase (the fp64 tile would not fit next to the scratch)
 template <typename Real, bool SPLIT>
@@ -109,7 +133,7 @@ static int prepare3(rbc3d_sim* s)
 
 template <typename Real, bool SPLIT>
 static int launch3(rbc3d_sim* s, const float* actions, float* obs, float* reward, double* nu, int* trunc, int* nan, const int* env_ids,
-                   int n, RunFlags3 F, bool time_it, bool want_obs)
+                   int n, RunFlags3 F, bool time_it, bool want_obs, const rbc2d::VecIO& vec)
 {
     Consts3<Real> C = make_consts3<Real>(s->hc);
     EnvIO3<Real> io;
@@ -121,6 +145,7 @@ static int launch3(rbc3d_sim* s, const float* actions, float* obs, float* reward
     io.t = s->t; io.step_count = s->step;
     io.truncated = trunc ? trunc : s->trunc;
     io.nan_flag = nan ? nan : s->nan;
+    io.vec = vec;
     const int grid = n < s->grid ? n : s->grid;
     if (grid <= 0) return 0;
     if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
@@ -133,13 +158,13 @@ static int launch3(rbc3d_sim* s, const float* actions, float* obs, float* reward
 }
 
 static int dispatch3(rbc3d_sim* s, const float* actions, float* obs, float* reward, double* nu, int* trunc, int* nan, const int* env_ids,
-                     int n, RunFlags3 F, bool time_it, bool want_obs = true)
+                     int n, RunFlags3 F, bool time_it, bool want_obs = true, const rbc2d::VecIO& vec = rbc2d::VecIO())
 {
     const bool f32 = s->cfg.precision == 32, split = s->cfg.split != 0;
-    if (f32) return split ? launch3<float, true>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs)
-                          : launch3<float, false>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs);
-    return split ? launch3<double, true>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs)
-                 : launch3<double, false>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs);
+    if (f32) return split ? launch3<float, true>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs, vec)
+                          : launch3<float, false>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs, vec);
+    return split ? launch3<double, true>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs, vec)
+                 : launch3<double, false>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs, vec);
 }
 
 extern "C" {
@@ -190,6 +215,10 @@ int rbc3d_create(const rbc3d_config* cfg, rbc3d_sim** out)
     ALLOC3(s->nan, B * sizeof(int));
     ALLOC3(s->reward, B * sizeof(float));
     ALLOC3(s->actions, B * (size_t)cfg->heaters * cfg->heaters * sizeof(float));
+    ALLOC3(s->pending, B * sizeof(int));
+    ALLOC3(s->episode, B * sizeof(long long));
+    ALLOC3(s->ep_return, B * sizeof(double));
+    ALLOC3(s->nan_count, sizeof(int));
 #undef ALLOC3
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
         rbc3d_destroy(s);
@@ -203,7 +232,8 @@ int rbc3d_destroy(rbc3d_sim* s)
 {
     if (!s) return 0;
     cudaSetDevice(s->cfg.device);
-    void* ptrs[] = {s->state, s->buf, s->gm, s->tinv, s->bank, s->t, s->nu, s->step, s->trunc, s->nan, s->obs, s->reward, s->actions};
+    void* ptrs[] = {s->state, s->buf, s->gm, s->tinv, s->bank, s->t, s->nu, s->step, s->trunc, s->nan, s->obs, s->reward, s->actions, s->pending, s->episode,
+                    s->ep_return, s->nan_count};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -236,9 +266,9 @@ static int set_fields3(rbc3d_sim* s, const double* dfields, const int* env_ids_d
 {
     dim3 grid(16, n < 2048 ? n : 2048);
     if (s->cfg.precision == 32)
-        rbc3d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, dfields, env_ids_dev, src_idx_dev, n, n_src, s->t, s->step, s->trunc, s->nan);
+        rbc3d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, dfields, env_ids_dev, src_idx_dev, n, n_src, s->t, s->step, s->trunc, s->nan, s->B);
     else
-        rbc3d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, dfields, env_ids_dev, src_idx_dev, n, n_src, s->t, s->step, s->trunc, s->nan);
+        rbc3d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, dfields, env_ids_dev, src_idx_dev, n, n_src, s->t, s->step, s->trunc, s->nan, s->B);
     CK(cudaGetLastError());
     s->launches += 1;
     return 0;
@@ -296,6 +326,78 @@ int rbc3d_step_dev(rbc3d_sim* s, const float* actions, float* obs, float* reward
     Consts3<float> tmp = make_consts3<float>(s->hc);
     RunFlags3 F{tmp.nsub, 0, 1};
     return dispatch3(s, actions, obs, reward, nusselt, trunc, nan, nullptr, s->B, F, true, obs != nullptr);
+}
+
+int rbc3d_set_autoreset(rbc3d_sim* s, const rbc_autoreset* cfg)
+{
+    if (!s || !cfg) return rbc_fail("rbc3d_set_autoreset: bad argument");
+    if (cfg->mode < 0 || cfg->mode > 2) return rbc_fail("rbc3d_set_autoreset: mode must be 0 (disabled), 1 (next_step) or 2 (same_step)");
+    s->ar = *cfg;
+    return 0;
+}
+
+int rbc3d_vec_mark_reset_dev(rbc3d_sim* s, const int32_t* env_ids, int32_t n)
+{
+    if (!s) return rbc_fail("null handle");
+    CK(cudaSetDevice(s->cfg.device));
+    if (!env_ids) n = s->B;
+    s->launches += 1;
+    return rbc_vec_mark(s->stream, env_ids, n, s->episode, s->ep_return, s->pending, 0);
+}
+
+int rbc3d_vec_reset_dev(rbc3d_sim* s, const int32_t* ckpt_idx)
+{
+    if (!s) return rbc_fail("null handle");
+    if (!s->bank) return rbc_fail("rbc3d_vec_reset_dev: no checkpoint bank loaded");
+    CK(cudaSetDevice(s->cfg.device));
+    if (!ckpt_idx) {
+        int rcd = rbc_vec_draw(s->stream, s->pending, s->B, (unsigned long long)s->ar.seed, (unsigned long long)s->ar.env_id_offset, s->n_ep);
+        if (rcd) return rcd;
+        s->launches += 1;
+        ckpt_idx = s->pending;
+    }
+    int rc = rbc3d_reset_from_checkpoints_dev(s, nullptr, ckpt_idx, s->B);
+    if (rc) return rc;
+    rc = rbc_vec_mark(s->stream, nullptr, s->B, s->episode, s->ep_return, s->pending, 1);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(s->nan_count, 0, sizeof(int), s->stream));
+    s->launches += 1;
+    return 0;
+}
+
+int rbc3d_vec_step_dev(rbc3d_sim* s, const float* actions, const rbc3d_vec_out* out)
+{
+    if (!s || !actions || !out) return rbc_fail("rbc3d_vec_step_dev: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    Consts3<float> tmp = make_consts3<float>(s->hc);
+    RunFlags3 F{tmp.nsub, 0, 1};
+    int rc = dispatch3(s, actions, out->obs, out->reward, out->nusselt, out->truncated, out->nan, nullptr, s->B, F, true, out->obs != nullptr,
+                       make_vec3(s, out));
+    if (rc) return rc;
+    if (out->t) CK(cudaMemcpyAsync(out->t, s->t, (size_t)s->B * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    if (out->step) CK(cudaMemcpyAsync(out->step, s->step, (size_t)s->B * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+    if (out->episode_return) CK(cudaMemcpyAsync(out->episode_return, s->ep_return, (size_t)s->B * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
+
+int rbc3d_vec_nan_count(rbc3d_sim* s, int32_t clear, int64_t* count)
+{
+    if (!s || !count) return rbc_fail("rbc3d_vec_nan_count: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, s->nan_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (clear) CK(cudaMemsetAsync(s->nan_count, 0, sizeof(int), s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *count = h;
+    return 0;
+}
+
+int rbc3d_vec_nan_count_async(rbc3d_sim* s, int32_t* count_host)
+{
+    if (!s || !count_host) return rbc_fail("rbc3d_vec_nan_count_async: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpyAsync(count_host, s->nan_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    return 0;
 }
 
 int rbc3d_step_host(rbc3d_sim* s, const float* actions, float* obs, float* reward, double* nusselt, int32_t* trunc, int32_t* nan)

@@ -43,3 +43,11 @@ inline int rbc_pipe_chunks(int B, int lanes, int* len /*[kMaxChunks]*/)
     }
     return nch;
 }
+
+// ------------------------------------------------------------------------------------------
+// episode bookkeeping of the fused vector environments (rbc2d_vec_* / rbc3d_vec_*), implemented in rbc2d_lib.cu
+// ------------------------------------------------------------------------------------------
+// episode += 1 (restart: := 1), episode return := 0, pending := 0 for the listed environments (env_ids NULL = the first n)
+int rbc_vec_mark(cudaStream_t stream, const int* env_ids, int n, long long* episode, double* ep_return, int* pending, int restart);
+// idx[env] = checkpoint draw of episode 0 for env = 0..n-1
+int rbc_vec_draw(cudaStream_t stream, int* idx, int n, unsigned long long seed, unsigned long long offset, int n_ep);

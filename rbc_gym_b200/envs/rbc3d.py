@@ -85,7 +85,14 @@ class RayleighBenardConvection3DEnv(spaces.Env):
             import torch
             bank = load_checkpoint_3d(path)
             n = self.sim.load_checkpoints(bank)
-            idx = self.checkpoint_idx if self.checkpoint_idx is not None else int(self.np_random.integers(n))
+            if self.checkpoint_idx is not None:
+                # the reference forwards checkpoint_idx unchanged to Julia, where it is 1-BASED: read(h5, "b")[idx, :, :, :]
+                # (rbc_sim3D.jl:191; experiments/eval_sarl.py:45 passes 1 for the first episode); 0 or > n is a BoundsError there
+                if not 1 <= int(self.checkpoint_idx) <= n:
+                    raise IndexError(f"checkpoint_idx {self.checkpoint_idx} out of range 1..{n} (1-based like the reference's Julia side)")
+                idx = int(self.checkpoint_idx) - 1
+            else:
+                idx = int(self.np_random.integers(n))
             self.sim.reset_from_checkpoints(torch.tensor([idx], dtype=torch.int32))
         else:
             lz = float(self.domain[0])

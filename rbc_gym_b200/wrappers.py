@@ -234,15 +234,17 @@ class VectorFrameStack:
         return self._buf.clone(), info
 
     def step(self, actions):
-        was_pending = getattr(self.venv, "_pending", None)
-        was_pending = None if was_pending is None else was_pending.clone()
         obs, reward, terminated, truncated, info = self.venv.step(actions)
         f = self._frame(obs)
         self._buf = self._buf.roll(-1, dims=1)
         self._buf[:, -1] = f
-        mode = getattr(self.venv, "autoreset_mode", "disabled")
-        if mode == "same_step" and bool(truncated.any()):          # obs of truncated envs is already the reset observation
-            self._restart(f, truncated.nonzero().flatten())
-        elif mode == "next_step" and was_pending is not None and bool(was_pending.any()):
-            self._restart(f, was_pending.nonzero().flatten())      # this call reset them: obs is the reset observation
+        # an environment that was (auto-)reset by this call — inside the truncating step (same_step) or as the whole of this call
+        # (next_step) — reports step == 1 (`rbc_sim2D_api.jl:67-68`); its stack restarts from the reset observation.  A masked
+        # select instead of an index list: no host synchronisation.
+        was_reset = info["step"] == 1
+        pad = f if self.padding_type == "reset" else f * 0
+        fresh = pad.unsqueeze(1).expand(-1, self.k, *pad.shape[1:]).clone()
+        fresh[:, -1] = f
+        mask = was_reset.reshape(-1, *([1] * (self._buf.dim() - 1)))
+        self._buf = self.venv.torch.where(mask, fresh, self._buf)
         return self._buf.clone(), reward, terminated, truncated, info

@@ -103,6 +103,67 @@ def step(state, actions, ra, dt_action, precision=64, split=False, nxt_global=Fa
     return dict(state=st, obs=ob, reward=rew, nu_state=nus, nu_obs=nuo, t=t, step=sc, truncated=tr, nan=nf, pressure=pr, cell_dist=cd)
 
 
+class VecEmu2D:
+    """B environments stepped by the emulated kernel WITH the fused vector-env semantics (`VecIO` in rbc2d_core.h): the CPU
+    twin of `rbc2d_vec_step_dev`.  Holds the per-environment arrays the library handle owns on the device."""
+
+    def __init__(self, B, bank, ra, dt_action, mode, nan_reset=False, seed=0, id_offset=0, precision=32, episode_length=300.0,
+                 dt_solver=0.03, pressure=False, cluster=0):
+        """cluster = CL > 0 runs the emulated CLUSTER kernel (rbc2dx_core.h, 96 x 64 split over CL CTAs) instead of the dedicated one."""
+        self.lib = C.CDLL(str(build()))
+        self.cluster = cluster
+        self.libx = C.CDLL(str(build_x())) if cluster else None
+        self.B, self.mode, self.nan_reset, self.seed, self.id_offset, self.precision = B, mode, int(nan_reset), seed, id_offset, precision
+        self.dtype = np.float64 if precision == 64 else np.float32
+        self.bank = np.ascontiguousarray(bank, dtype=np.float64)
+        self.ch = 5 if pressure else 3
+        self.split = int(pressure)
+        self.h = HostConfig(ra, 0.7, 2 * math.pi, 2.0, 1.0, 0.75, dt_action, dt_solver, episode_length, 12, 8, 48, self.ch)
+        self.state = np.zeros((B, 18528), self.dtype)
+        self.t, self.step_count = np.zeros(B), np.ones(B, np.int32)
+        self.pending, self.episode, self.ep_return = np.zeros(B, np.int32), np.zeros(B, np.int64), np.zeros(B)
+        self.nan_count = np.zeros(1, np.int32)
+        self.pressure = np.zeros((B, 2, 64, 96), self.dtype) if pressure else None
+        self.lib.emu_checkpoint_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
+
+    def draw(self, env, episode):
+        return self.lib.emu_checkpoint_draw(self.seed, self.id_offset + env, episode, self.bank.shape[0])
+
+    def reset(self):
+        for e in range(self.B):
+            self.state[e] = self.bank[self.draw(e, 0)].astype(self.dtype)
+        self.t[:] = 0; self.step_count[:] = 1; self.pending[:] = 0; self.episode[:] = 1; self.ep_return[:] = 0
+
+    def step(self, actions):
+        B = self.B
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        o = dict(obs=np.zeros((B, self.ch, 8, 48), np.float32), reward=np.zeros(B, np.float32), nu_state=np.zeros(B), nu_obs=np.zeros(B),
+                 truncated=np.zeros(B, np.int32), nan=np.zeros(B, np.int32), final_obs=np.zeros((B, self.ch, 8, 48), np.float32),
+                 final_nu_state=np.zeros(B), final_nu_obs=np.zeros(B), final_return=np.zeros(B))
+        vp = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
+        if self.cluster:
+            self.libx.emu_rbc2dx_set_vec(self.mode, self.nan_reset, vp(self.bank), self.bank.shape[0], C.c_uint64(self.seed),
+                                         C.c_uint64(self.id_offset), vp(self.pending), vp(self.episode), vp(self.ep_return),
+                                         vp(o["final_obs"]), vp(o["final_nu_state"]), vp(o["final_nu_obs"]), vp(o["final_return"]),
+                                         vp(self.nan_count))
+            rc = self.libx.emu_rbc2dx_step(C.byref(self.h), None, None, 96, 64, self.cluster, self.precision, int(self.precision == 64), B,
+                                           vp(self.state), vp(a), vp(o["obs"]), vp(o["reward"]), vp(o["nu_state"]), vp(o["nu_obs"]),
+                                           vp(self.t), vp(self.step_count), vp(o["truncated"]), vp(o["nan"]), 0, -1, self.split, vp(self.pressure))
+            self.libx.emu_rbc2dx_set_vec(-1, 0, None, 0, C.c_uint64(0), C.c_uint64(0), None, None, None, None, None, None, None, None)
+            assert rc == 0
+            o.update(t=self.t.copy(), step=self.step_count.copy(), episode_return=self.ep_return.copy())
+            return o
+        rc = self.lib.emu_rbc2d_vec_step(C.byref(self.h), self.precision, self.split, B, vp(self.state), vp(a), vp(o["obs"]), vp(o["reward"]),
+                                         vp(o["nu_state"]), vp(o["nu_obs"]), vp(self.t), vp(self.step_count), vp(o["truncated"]), vp(o["nan"]),
+                                         vp(self.pressure), self.mode, self.nan_reset, vp(self.bank), self.bank.shape[0],
+                                         C.c_uint64(self.seed), C.c_uint64(self.id_offset), vp(self.pending), vp(self.episode),
+                                         vp(self.ep_return), vp(o["final_obs"]), vp(o["final_nu_state"]), vp(o["final_nu_obs"]),
+                                         vp(o["final_return"]), vp(self.nan_count))
+        assert rc == 0
+        o.update(t=self.t.copy(), step=self.step_count.copy(), episode_return=self.ep_return.copy())
+        return o
+
+
 def pack(b, u, w):
     return np.concatenate([b.reshape(b.shape[0], -1), u.reshape(u.shape[0], -1), w.reshape(w.shape[0], -1)], axis=1)
 

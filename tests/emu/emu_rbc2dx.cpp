@@ -9,6 +9,9 @@
 
 using namespace rbc2dx;
 
+// fused vector-env semantics for the next emu_rbc2dx_step call (emu_rbc2dx_set_vec); mode < 0 = plain step
+static rbc2d::VecIO g_vec;
+
 template <typename G, typename Real, bool NXTG, bool SPLIT>
 static void run(const HostConfig& h, const HostWrappers& wr, double* cell_dist, int B, Real* state, const float* actions, float* obs,
                 float* reward, double* nu_state, double* nu_obs, double* t, int* step_count, int* truncated, int* nan_flag,
@@ -49,7 +52,7 @@ static void run(const HostConfig& h, const HostWrappers& wr, double* cell_dist, 
         std::memcpy(arena.data() + r * L::total + X.o_twN, X.twN, sizeof(Real) * 2 * G::NH);
         std::memcpy(arena.data() + r * L::total + X.o_tw2, X.tw2, sizeof(Real) * 2 * G::NH);
     }
-    EnvIO<Real> io{state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, SPLIT ? pressure : nullptr, cell_dist};
+    EnvIO<Real> io{state, actions, obs, reward, nu_state, nu_obs, t, step_count, truncated, nan_flag, SPLIT ? pressure : nullptr, cell_dist, g_vec};
     RunFlags F{nsub >= 0 ? nsub : C.nsub, project_first, 1};
     SyncState S{};
     for (int e = 0; e < B; ++e) env_action_step<G, Real, NXTG, SPLIT>(C, io, X, e, F, 0, S);
@@ -95,4 +98,14 @@ extern "C" int emu_rbc2dx_step(const HostConfig* h, const HostWrappers* wp, doub
     if (nx == 192 && nz == 128 && cl == 2) DISPATCH(G192_2);
     if (nx == 128 && nz == 64 && cl == 2) DISPATCH(G128_2);
     return -2;
+}
+
+extern "C" void emu_rbc2dx_set_vec(int mode, int nan_reset, const double* bank, int n_ep, unsigned long long seed, unsigned long long id_offset,
+                                   int* pending, long long* episode, double* ep_return, float* final_obs, double* final_nu_s,
+                                   double* final_nu_o, double* final_return, int* nan_count)
+{
+    g_vec = rbc2d::VecIO();
+    g_vec.mode = mode; g_vec.nan_reset = nan_reset; g_vec.bank = bank; g_vec.n_ep = n_ep; g_vec.seed = seed; g_vec.id_offset = id_offset;
+    g_vec.pending = pending; g_vec.episode = episode; g_vec.ep_return = ep_return; g_vec.final_obs = final_obs;
+    g_vec.final_nu_a = final_nu_s; g_vec.final_nu_b = final_nu_o; g_vec.final_return = final_return; g_vec.nan_count = nan_count;
 }

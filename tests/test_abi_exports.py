@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(backend.ABI_SYMBOLS), declared ^ set(backend.ABI_SYMBOLS)
     for sym in declared:
         assert hasattr(L, sym), f"{sym} not exported"
-    assert L.rbc_abi_version() == 1
+    assert L.rbc_abi_version() == backend.ABI_VERSION == 2
 
 
 def test_config_struct_matches_header():
@@ -32,6 +32,14 @@ def test_config_struct_matches_header():
         names += [(n.strip(), typ) for n in decl.split(",")]
     fields = [(n, "int32_t" if t is ctypes.c_int32 else "double") for n, t in backend.Rbc2dConfig._fields_]
     assert names == fields
+
+
+@pytest.mark.parametrize("name,cls", [("rbc_autoreset", "RbcAutoreset"), ("rbc2d_vec_out", "Rbc2dVecOut"), ("rbc3d_vec_out", "Rbc3dVecOut")])
+def test_vector_step_structs_match_header(name, cls):
+    header = (ROOT / "include" / "rbc_b200.h").read_text()
+    body = header[header.index(f"typedef struct {name} {{"):header.index(f"}} {name};")]
+    names = [n.strip() for _, n in re.findall(r"^\s*(int32_t|int64_t|float\*|double\*|int32_t\*)\s+([a-z_]+);", body, flags=re.M)]
+    assert names == [n for n, _ in getattr(backend, cls)._fields_]
 
 
 def test_create_fails_loudly_without_gpu():

@@ -302,7 +302,7 @@ def test_vector_env_nan_policy(mode):
     t, step = env.sim.info()
     assert t[2] == 0.0 and step[2] == 1 and np.all(np.delete(t, 2) == pytest.approx(0.15))
     obs, rew, term, trunc, info = env.step(torch.zeros((6, 12), device="cuda"))        # everybody steps normally again
-    assert not trunc.any() and "nan_reset" not in info and torch.isfinite(rew).all() and (rew != 0).all()
+    assert not trunc.any() and not info["nan_reset"].any() and torch.isfinite(rew).all() and (rew != 0).all()
     t, step = env.sim.info()
     assert t[2] == pytest.approx(0.15) and t[0] == pytest.approx(0.30)
     env.close()

@@ -116,7 +116,8 @@ class _FakeVec:
         self.c = self.c + 1
         trunc = self.c == 3
         self.c = self.torch.where(trunc, self.torch.full_like(self.c, 100.0), self.c)    # reset obs = 100
-        return self.c.reshape(-1, 1, 1).expand(-1, 2, 2).clone(), self.c * 0, trunc & False, trunc, {}
+        # a reset environment reports step == 1 (rbc_sim2D_api.jl:67-68); that is what the ring buffer keys its restart on
+        return self.c.reshape(-1, 1, 1).expand(-1, 2, 2).clone(), self.c * 0, trunc & False, trunc, {"step": self.torch.where(trunc, 1, 2)}
 
 
 def test_vector_frame_stack_ring_buffer_restarts_on_autoreset():

@@ -45,7 +45,8 @@ def build_fake_julia():
                                     t_diff=tuple(T_diff))
             self.t_ff = lz ** 2                                                   # rbc_sim3D_api.jl:43
             self.dt, self.dts = dt, O3.substep_schedule(dt, dt_solver, lz)
-            bank = load_checkpoint_3d(checkpoint_path)[checkpoint_idx]            # the golden episode starts from a checkpoint
+            # Julia indexes the file 1-based: read(h5, "b")[idx, :, :, :] (rbc_sim3D.jl:191)
+            bank = load_checkpoint_3d(checkpoint_path)[checkpoint_idx - 1]        # the golden episode starts from a checkpoint
             nc = nx * ny * nz
             self.b, self.u, self.v = (bank[q * nc:(q + 1) * nc].reshape(nz, ny, nx).copy() for q in range(3))
             self.w = bank[3 * nc:].reshape(nz + 1, ny, nx).copy()
