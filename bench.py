@@ -201,6 +201,40 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def source_hash() -> str:
+    """Hash of the kernel sources the committed ncu figures (profiles/traffic.json) were measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("rbc2d_core.h", "rbc2d_lib.cu"):
+        h.update((ROOT / "rbc_gym_b200" / "csrc" / f).read_bytes())
+    return h.hexdigest()[:16]
+
+
+def ncu_figures():
+    """Per-launch DRAM bytes and fp32 flop of the dominant kernel from the committed ncu capture (tools/gpu_ncu.sh writes
+    profiles/traffic.json with the hash of the sources it ran); a capture of other sources is refused, not reported."""
+    tj = ROOT / "profiles" / "traffic.json"
+    if not tj.exists():
+        return None, None, "no ncu capture committed"
+    try:
+        d = json.loads(tj.read_text())
+    except Exception:
+        return None, None, "unreadable profiles/traffic.json"
+    if d.get("source_hash") != source_hash():
+        return None, None, f"stale: ncu capture is of sources {d.get('source_hash')}, this build is {source_hash()}"
+    return d.get("dram_bytes_per_launch"), d.get("fp32_flop_per_launch"), f"ncu --set full, {d.get('envs_per_launch')} envs per launch"
+
+
+def uniform_actions(torch, step: int, gids, heaters: int, seed: int = 1234):
+    """U(-1,1) actions keyed by (seed, GLOBAL env id, step, heater): rank r of an N-GPU run feeds its environments exactly what
+    the single-GPU run feeds the same global ids, so the runs can be compared bit for bit (slice_checksum)."""
+    from rbc_gym_b200.envs.vector import _as_i64, _mix63, _M63
+    k = torch.arange(heaters, device=gids.device, dtype=torch.int64)[None, :]
+    x = (gids[:, None] * _as_i64(0x9E3779B97F4A7C15) + k * _as_i64(0xC2B2AE3D27D4EB4F) + _as_i64((seed * 1_000_003 + step) * 0x165667B19E3779F9)) & _M63
+    x = _mix63(torch, _mix63(torch, x))
+    return ((x >> 10).to(torch.float64) * (2.0 / (1 << 53)) - 1.0).to(torch.float32)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,7 +245,8 @@ def main():
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=18.0, help="CPU work of the cpu_baseline sample")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the config 3 / config 4 side measurements")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the side measurements (configs 3/4/5, fp64, 300-step episode)")
+    ap.add_argument("--episode-steps", type=int, default=300, help="length of the full-episode leg (auto-reset fires inside it)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -223,9 +258,10 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import hashlib
     import torch
     import torch.distributed as dist
-    from rbc_gym_b200 import backend
+    from rbc_gym_b200.envs import RBCVectorEnv2D
     from rbc_gym_b200.sharding import EpisodeStats, shard_range
 
     if not torch.cuda.is_available():
@@ -238,14 +274,15 @@ def main():
 
     B = args.envs_per_gpu
     lo, hi = shard_range(B * world, world, rank)           # this rank's slice of the global batch
-    sim = backend.Sim2D(B, ra=RA, dt_action=DT_ACTION, dt_solver=DT_SOLVER, precision=args.precision, device=local_rank)
-    n_ep = sim.load_checkpoints(CKPT)
+    # the path RL callers use: the vector environment (auto-reset fused into the step kernel, gymnasium's next_step mode)
+    env = RBCVectorEnv2D(B, rayleigh_number=RA, heater_duration=DT_ACTION, dt_solver=DT_SOLVER, episode_length=300, checkpoint=str(CKPT),
+                         precision=args.precision, device=local_rank, autoreset_mode="next_step", seed=1234, env_id_offset=lo)
+    sim = env.sim
+    n_ep = sim.n_episodes
     gid = torch.arange(lo, hi, device=dev, dtype=torch.int64)
-    sim.reset_from_checkpoints((gid % n_ep).to(torch.int32))
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
+    start_idx = (gid % n_ep).to(torch.int32)               # initial state of env e = episode (e mod 20) of the train file
     K, W = args.steps, args.warmup
-    actions = torch.rand((W + K, B, sim.heaters), device=dev, generator=gen) * 2 - 1
+    actions = torch.stack([uniform_actions(torch, i, gid, sim.heaters) for i in range(W + K)])
     stats = EpisodeStats(dev)
 
     def barrier():
@@ -258,24 +295,24 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    env.reset(options={"checkpoint_idx": start_idx})
     t_pre = time.perf_counter()
     while time.perf_counter() - t_pre < 1.0:
-        sim.step(actions[0])
+        env.step(actions[0])
         torch.cuda.synchronize()
-    sim.reset_from_checkpoints((gid % n_ep).to(torch.int32))
+    env.reset(options={"checkpoint_idx": start_idx})
     for i in range(W):
-        o_ = sim.step(actions[i])
-        stats.accumulate(o_[1], o_[3], o_[2], o_[5])       # also warms torch's lazily loaded reduction kernels
+        o_ = env.step(actions[i])
+        stats.accumulate(o_[1], o_[4]["nusselt_obs"], o_[4]["nusselt_state"], o_[4]["nan"])   # also warms torch's lazily loaded kernels
     stats = EpisodeStats(dev)
-    kernel_ms = []
     barrier()
     t_region0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = sim.launch_info()["launches"]
     e0.record()
     for i in range(K):
-        obs, rew, nus, nuo, trunc, nan = sim.step(actions[W + i])
-        stats.accumulate(rew, nuo, nus, nan)
+        obs, rew, term, trunc, info = env.step(actions[W + i])
+        stats.accumulate(rew, info["nusselt_obs"], info["nusselt_state"], info["nan"])
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
@@ -284,6 +321,9 @@ def main():
     # per-launch duration of the dominant kernel over the timed region: the library records a CUDA event pair around every
     # step kernel on its launch stream (ring of 64); they are read here, after the region, so nothing synchronised inside it
     kernel_ms = sim.step_kernel_ms_history(min(K, 64))
+    # bitwise fingerprint of the first 64 environments of the GLOBAL batch after W + K steps (rank 0 owns them at every N):
+    # equal values on the N = 1 and N = 8 lines prove that sharding does not change a single bit
+    slice_checksum = hashlib.sha256(sim.get_state()[:64].cpu().numpy().tobytes()).hexdigest()[:16] if rank == 0 else None
     tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -295,12 +335,12 @@ def main():
     host_actions = [torch.empty((B, sim.heaters), dtype=torch.float32).pin_memory() for _ in range(K)]
     for i in range(K):
         host_actions[i].copy_(actions[W + i].cpu())
-    out = sim.alloc_host_outputs(pinned=True)
-    sim.step_host(host_actions[0].numpy(), out)
+    out = env.alloc_host_outputs(pinned=True)
+    env.step_host(host_actions[0].numpy(), out)
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        sim.step_host(host_actions[i].numpy(), out)       # H2D actions, kernel, D2H obs/reward/nu/flags, sync
+        env.step_host(host_actions[i].numpy(), out)       # H2D actions, fused vector step, D2H obs/reward/nu/flags/t/step/returns, sync
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     tmax = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
@@ -310,22 +350,98 @@ def main():
     h2d = B * sim.heaters * 4
     d2h = sum(v.nbytes for v in out.values())
 
-    secondary = None
-    if rank == 0 and not args.no_secondary:
-        secondary = secondary_configs(local_rank)
+    # ---------------- side measurements (every rank runs the sharded ones; rank 0 the single-GPU ones) ----------------
+    secondary = {}
+    if not args.no_secondary:
+        def timed_loop(fn, n):
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(n):
+                fn(i)
+            a1.record()
+            barrier()
+            tm = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            return tm.item()
+
+        # (1) one full episode: 300 vector steps from reset, same_step mode, so that the fused auto-reset of every environment
+        #     fires inside the timed region (SURVEY 8d protocol)
+        T = args.episode_steps
+        ep_env = RBCVectorEnv2D(B, rayleigh_number=RA, heater_duration=DT_ACTION, dt_solver=DT_SOLVER, episode_length=T * DT_ACTION,
+                                checkpoint=str(CKPT), precision=args.precision, device=local_rank, autoreset_mode="same_step", seed=1234,
+                                env_id_offset=lo)
+        ep_env.reset(options={"checkpoint_idx": start_idx})
+        n_reset = torch.zeros((), device=dev, dtype=torch.int64)
+        def ep_step(i):
+            nonlocal n_reset
+            o = ep_env.step(uniform_actions(torch, 10_000 + i, gid, sim.heaters))
+            n_reset += o[3].sum()
+        ms = timed_loop(ep_step, T)
+        tot = n_reset.to(torch.float64).reshape(1)
+        if world > 1:
+            dist.all_reduce(tot)
+        secondary["episode_rollout"] = {"env_steps_per_s": world * B * T / (ms * 1e-3), "steps": T, "autoreset_mode": "same_step",
+                                        "environments_auto_reset_inside_the_timed_region": int(tot.item()), "ms_per_step": ms / T,
+                                        "note": "vector env, action generation on the device inside the loop, every env truncates at the last step"}
+        ep_env.close()
+
+        # (2) config 5: a policy in the loop on the same stream (fixed random linear map obs -> 12 actions, tanh), next_step mode
+        Wp = torch.randn((sim.channels * 8 * 48, sim.heaters), device=dev, generator=torch.Generator(device=dev).manual_seed(7)) * 0.05
+        pol = {"obs": env.reset(options={"checkpoint_idx": start_idx})[0]}
+        def pol_step(i):
+            a = torch.tanh(pol["obs"].flatten(1) @ Wp)
+            pol["obs"] = env.step(a)[0]
+        pol_step(0)
+        ms = timed_loop(pol_step, K)
+        secondary["config5_policy_in_loop"] = {"env_steps_per_s": world * B * K / (ms * 1e-3), "global_envs": world * B, "steps": K,
+                                               "policy": "tanh(linear(obs)) on the env's stream, actions never leave the device",
+                                               "ms_per_step": ms / K}
+
+        # (3) end to end INCLUDING info["state"] (the reference returns the full state every step, rbc2D.py:211: 74 KB per env)
+        st_host = torch.empty((B, sim.channels, 64, 96), dtype=torch.float32).pin_memory()
+        def e2e_state(i):
+            env.step_host(host_actions[i % K].numpy(), out)
+            st_host.copy_(sim.get_state(), non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_state(0)
+        barrier()
+        t0 = time.perf_counter()
+        n_s = min(K, 5)
+        for i in range(n_s):
+            e2e_state(i)
+        tm = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        secondary["e2e_with_state"] = {"env_steps_per_s": world * B * n_s / (tm.item() * 1e-3), "d2h_bytes_per_step": d2h + st_host.numel() * 4,
+                                       "steps": n_s}
+        if rank == 0:
+            # (4) the fp64 validation mode (the reference's arithmetic) on the same workload
+            try:
+                e64 = RBCVectorEnv2D(B, rayleigh_number=RA, heater_duration=DT_ACTION, dt_solver=DT_SOLVER, checkpoint=str(CKPT), precision=64,
+                                     device=local_rank, seed=1234, env_id_offset=lo)
+                e64.reset(options={"checkpoint_idx": start_idx})
+                e64.step(actions[0]); torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for i in range(3):
+                    e64.step(actions[1 + i])
+                a1.record(); torch.cuda.synchronize()
+                ms = a0.elapsed_time(a1) / 3
+                secondary["fp64_validation_mode"] = {"env_steps_per_s": B / ms * 1e3, "ms_per_step": ms, "dtype": "f64", "envs": B,
+                                                     "streaming_equiv_GBps": B / ms * 1e3 * algorithmic_bytes_per_env_step(sim.nsub, 8) / 1e9}
+                e64.close()
+            except Exception as e:
+                secondary["fp64_validation_mode"] = {"error": str(e)[:200]}
+            secondary.update(secondary_configs(local_rank))
     if rank == 0:
         real_bytes = args.precision // 8
         per_env = algorithmic_bytes_per_env_step(sim.nsub, real_bytes)
         k_ms = float(np.mean(kernel_ms))
         achieved = per_env * B / (k_ms * 1e-3) / 1e9
         peak, peak_src = hbm_peak()
-        traffic = None
-        tj = ROOT / "profiles" / "traffic.json"
-        if tj.exists():
-            try:
-                traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        traffic, flop, ncu_note = ncu_figures()
         cpu = None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -335,13 +451,13 @@ def main():
             rate, el = cpu_reference_rate(n, threads)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{n} env action-steps of the same workload (oracle fp64 C port, {threads} threads, {el:.1f} s)"}
-        flop_per_env_step = 0.18e9                        # SURVEY §8d estimate (~290 flop / cell-stage)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
             "config": {"workload": "configs[1]: 2D Ra=1e5 96x64 dt=1 (34 RK3 steps / 102 projected stages), "
-                                   f"{B} envs per GPU, reset from train checkpoints, U(-1,1) actions",
+                                   f"{B} envs per GPU, reset from train checkpoints, U(-1,1) actions, through the vector env "
+                                   "(RBCVectorEnv2D.step: auto-reset fused into the step kernel, info t/step/nusselt)",
                        "envs_per_gpu": B, "global_envs": world * B, "parallelism": f"env-sharded x{world}",
                        "l2": "inputs larger than L2 (%.0f MB of state per GPU)" % (B * S_VALUES * real_bytes / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -349,16 +465,20 @@ def main():
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": per_env * B,
                          "note": "algorithmic bytes = stage-streaming formulation (SURVEY 8d); the kernel keeps each env "
                                  "on-chip for the whole action step, so measured DRAM traffic is far below this figure",
-                         "fp32_tflops_est": flop_per_env_step * B / (k_ms * 1e-3) / 1e12},
+                         "ncu": ncu_note,
+                         "fp32_tflops": None if flop is None else flop * (B / 4096.0) / (k_ms * 1e-3) / 1e12},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "rbc2d_vec_step_host: host actions in, obs/reward/nusselt/flags/t/step/returns out; info['state'] "
+                            "(74 KB per env, rbc2D.py:211) is opt-in for the batch: see secondary.e2e_with_state"},
             "gpu_launches": launches,
             "clocks": clocks,
             "episode_stats": totals,
-            "secondary": secondary,
+            "slice_checksum": slice_checksum,
+            "secondary": secondary or None,
         }
         print(json.dumps(line), flush=True)
-    sim.close()
+    env.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -171,6 +171,11 @@ int rbc2d_vec_reset_dev(rbc2d_sim* sim, const int32_t* ckpt_idx_dev);
  * (NULL = all), return := 0, pending := 0. */
 int rbc2d_vec_mark_reset_dev(rbc2d_sim* sim, const int32_t* env_ids_dev, int32_t n);
 int rbc2d_vec_step_dev(rbc2d_sim* sim, const float* actions_dev, const rbc2d_vec_out* out);
+/* The same step through HOST buffers (every pointer of `out` is a host pointer, any may be NULL): actions are copied in,
+ * the requested outputs out, chunk by chunk on a second stream while the next chunk computes; returns when they have landed.
+ * This is the call a caller without device tensors makes once per rollout step — what replaces the pickled pipe traffic of
+ * the process-per-env vector env. */
+int rbc2d_vec_step_host(rbc2d_sim* sim, const float* actions_host, const rbc2d_vec_out* out_host);
 /* Number of environments that reported NaNs in vector steps since the last call with clear != 0 (synchronises the stream). */
 int rbc2d_vec_nan_count(rbc2d_sim* sim, int32_t clear, int64_t* count);
 /* Same counter copied to a caller-provided (pinned) host int32 without synchronising: the value is valid once the stream
@@ -223,7 +228,10 @@ int rbc2d_step_kernel_ms_history(rbc2d_sim* sim, float* ms_out, int32_t n);
  * ------------------------------------------------------------------------------------------------ */
 typedef struct rbc3d_config {
     int32_t num_envs;
-    int32_t nx, ny, nz;        /* grid = state_shape[::-1]; this build supports 32 x 32 x 16            */
+    int32_t nx, ny, nz;        /* grid = state_shape[::-1] (a free kwarg of the reference env, rbc3D.py:43-60): 32 x 32 x 16 runs a
+                                  dedicated one-CTA-per-environment kernel, any other grid with nx, ny powers of two in 8..256 and
+                                  6 <= nz <= 256 (e.g. the 64 x 64 x 32 of experiments/flowstats/flowstats_ra.py:27-36) the
+                                  stage-streaming kernels                                                   */
     int32_t heaters;           /* patches per side (8)                                                  */
     double heater_limit;       /* 0.9                                                                   */
     double ra, pr;
@@ -268,6 +276,9 @@ typedef struct rbc3d_vec_out {
     double* final_nusselt;
     double* final_return;
 } rbc3d_vec_out;
+/* One Rayleigh number per environment (host array [B]; NULL restores cfg.ra): lets one batch sweep the Rayleigh number the way
+ * experiments/flowstats/flowstats_ra.py:27-36 loops over 14 environments.  Stage-streaming kernels only. */
+int rbc3d_set_rayleigh_per_env(rbc3d_sim* sim, const double* ra_host);
 int rbc3d_set_autoreset(rbc3d_sim* sim, const rbc_autoreset* cfg);
 int rbc3d_vec_reset_dev(rbc3d_sim* sim, const int32_t* ckpt_idx_dev);
 int rbc3d_vec_mark_reset_dev(rbc3d_sim* sim, const int32_t* env_ids_dev, int32_t n);

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from pathlib import Path
 from typing import Optional, Sequence, Union
 
@@ -94,9 +95,9 @@ ABI_SYMBOLS = (
     "rbc3d_create", "rbc3d_destroy", "rbc3d_set_stream", "rbc3d_state_values_per_env", "rbc3d_load_checkpoints",
     "rbc3d_reset_from_checkpoints_dev", "rbc3d_reset_from_fields_host", "rbc3d_reset_from_fields_dev", "rbc3d_step_dev", "rbc3d_step_host",
     "rbc3d_observe_dev", "rbc3d_get_fields_host", "rbc3d_get_info_host", "rbc3d_launch_count", "rbc3d_last_step_kernel_ms",
-    "rbc_checkpoint_draw", "rbc2d_set_autoreset", "rbc2d_vec_reset_dev", "rbc2d_vec_mark_reset_dev", "rbc2d_vec_step_dev",
+    "rbc_checkpoint_draw", "rbc2d_set_autoreset", "rbc2d_vec_reset_dev", "rbc2d_vec_mark_reset_dev", "rbc2d_vec_step_dev", "rbc2d_vec_step_host",
     "rbc2d_vec_nan_count", "rbc2d_vec_nan_count_async", "rbc3d_set_autoreset", "rbc3d_vec_reset_dev", "rbc3d_vec_mark_reset_dev",
-    "rbc3d_vec_step_dev", "rbc3d_vec_nan_count", "rbc3d_vec_nan_count_async",
+    "rbc3d_vec_step_dev", "rbc3d_vec_nan_count", "rbc3d_vec_nan_count_async", "rbc3d_set_rayleigh_per_env",
 )
 ABI_VERSION = 2
 
@@ -167,6 +168,7 @@ def load_library(build_if_missing: bool = True):
     L.rbc3d_get_info_host.argtypes = [vp, vp, vp]
     L.rbc3d_launch_count.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ip), C.POINTER(ip)]
     L.rbc3d_last_step_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.rbc3d_set_rayleigh_per_env.argtypes = [vp, vp]
     L.rbc_checkpoint_draw.argtypes = [C.c_int64, C.c_int64, C.c_int64, ip]
     L.rbc_checkpoint_draw.restype = ip
     for dim, out_t in (("2d", Rbc2dVecOut), ("3d", Rbc3dVecOut)):
@@ -174,6 +176,8 @@ def load_library(build_if_missing: bool = True):
         getattr(L, f"rbc{dim}_vec_reset_dev").argtypes = [vp, vp]
         getattr(L, f"rbc{dim}_vec_mark_reset_dev").argtypes = [vp, vp, ip]
         getattr(L, f"rbc{dim}_vec_step_dev").argtypes = [vp, vp, C.POINTER(out_t)]
+        if dim == "2d":
+            L.rbc2d_vec_step_host.argtypes = [vp, vp, C.POINTER(out_t)]
         getattr(L, f"rbc{dim}_vec_nan_count").argtypes = [vp, ip, C.POINTER(C.c_int64)]
         getattr(L, f"rbc{dim}_vec_nan_count_async").argtypes = [vp, vp]
     if L.rbc_abi_version() != ABI_VERSION:
@@ -420,6 +424,34 @@ class Sim2D:
         self._check(self._L.rbc2d_vec_step_dev(self._h, C.c_void_p(a.data_ptr()), C.byref(self._vec_out)))
         return self.obs, self.reward, self.nu_state, self.nu_obs, self.truncated, self.nan, v
 
+    VEC_HOST_KEYS = ("obs", "reward", "nu_state", "nu_obs", "truncated", "nan", "t", "step", "episode_return",
+                     "final_obs", "final_nu_state", "final_nu_obs", "final_return")
+
+    def alloc_vec_host_outputs(self, pinned: bool = True, final: bool = False) -> dict:
+        """Host buffers for `vec_step_host` (page-locked by default so that the copies overlap the kernel)."""
+        obs = (self.B, self.channels, *self.obs_shape)
+        shapes = {"obs": (obs, np.float32), "reward": ((self.B,), np.float32), "nu_state": ((self.B,), np.float64),
+                  "nu_obs": ((self.B,), np.float64), "truncated": ((self.B,), np.int32), "nan": ((self.B,), np.int32),
+                  "t": ((self.B,), np.float64), "step": ((self.B,), np.int32), "episode_return": ((self.B,), np.float64)}
+        if final:
+            shapes.update({"final_obs": (obs, np.float32), "final_nu_state": ((self.B,), np.float64),
+                           "final_nu_obs": ((self.B,), np.float64), "final_return": ((self.B,), np.float64)})
+        t = self.torch
+        if not pinned:
+            return {k: np.zeros(s, d) for k, (s, d) in shapes.items()}
+        return {k: t.zeros(s, dtype=getattr(t, np.dtype(d).name)).pin_memory().numpy() for k, (s, d) in shapes.items()}
+
+    def vec_step_host(self, actions: np.ndarray, out: dict) -> dict:
+        """The vector step through host buffers (`rbc2d_vec_step_host`): H2D of the actions, one fused launch per chunk of whole
+        waves, D2H of every buffer present in `out` overlapped with the next chunk."""
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        if a.shape != (self.B, self.heaters):
+            raise ValueError(f"actions must have shape {(self.B, self.heaters)}, got {a.shape}")
+        o = Rbc2dVecOut(*[_np_ptr(out.get(k)) for k in self.VEC_HOST_KEYS])
+        self._use_current_stream()
+        self._check(self._L.rbc2d_vec_step_host(self._h, _np_ptr(a), C.byref(o)))
+        return out
+
     def vec_nan_count(self, clear: bool = False) -> int:
         """Environments that reported NaNs in vector steps since the counter was cleared (synchronises)."""
         n = C.c_int64()
@@ -562,6 +594,8 @@ class Sim3D:
         self.B, self.heaters, self.precision = int(num_envs), int(heaters), int(precision)
         self.state_shape = tuple(int(x) for x in state_shape)
         nz, ny, nx = self.state_shape
+        self.ncell = nx * ny * nz
+        self.nstate = 3 * self.ncell + nx * ny * (nz + 1)
         lz, ly, lx = (float(x) for x in domain)                       # rbc3D.py:173 passes L = domain[::-1]
         self.ra, self.pr = float(ra), float(pr)
         self.kappa = 1.0 / math.sqrt(self.pr * self.ra)
@@ -600,9 +634,24 @@ class Sim3D:
         except Exception:
             pass
 
+    @property
+    def fused_autoreset(self) -> bool:
+        """The auto-reset is fused into the dedicated 32 x 32 x 16 kernel only; other grids drive resets from the caller."""
+        return self.state_shape == (NZ3, NY3, NX3) and os.environ.get("RBC_B200_3D_GENERIC", "") != "1"
+
+    def set_rayleigh(self, ra_per_env):
+        """One Rayleigh number per environment (`rbc3d_set_rayleigh_per_env`; stage-streaming kernels, i.e. grids other than
+        32 x 32 x 16): a whole Rayleigh sweep like `experiments/flowstats/flowstats_ra.py:27-36` runs as one batch."""
+        ra = np.ascontiguousarray(ra_per_env, dtype=np.float64)
+        if ra.shape != (self.B,):
+            raise ValueError(f"need {self.B} Rayleigh numbers")
+        self._check(self._L.rbc3d_set_rayleigh_per_env(self._h, _np_ptr(ra)))
+        self.ra_per_env = ra
+        self.kappa_per_env = 1.0 / np.sqrt(self.pr * ra)
+
     def load_checkpoints(self, fields: np.ndarray) -> int:
-        """Upload a bank `[n_ep, 66560]` float64 (b,u,v,w in checkpoint layout)."""
-        f = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1, NSTATE3)
+        """Upload a bank `[n_ep, nstate]` float64 (b,u,v,w in checkpoint layout; 66560 values on the registered grid)."""
+        f = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1, self.nstate)
         self._use_current_stream()
         self._check(self._L.rbc3d_load_checkpoints(self._h, _np_ptr(f), f.shape[0]))
         self.n_episodes = f.shape[0]
@@ -621,10 +670,21 @@ class Sim3D:
                                                             C.c_void_p(idx.data_ptr()), n))
 
     def reset_from_fields(self, fields: np.ndarray, env_ids: Optional[Sequence[int]] = None, project: bool = True):
-        f = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1, NSTATE3)
+        f = np.ascontiguousarray(fields, dtype=np.float64).reshape(-1, self.nstate)
         ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
         self._use_current_stream()
         self._check(self._L.rbc3d_reset_from_fields_host(self._h, _np_ptr(ids), _np_ptr(f), f.shape[0], int(project)))
+
+    def reset_from_fields_dev(self, fields, env_ids=None, project: bool = True):
+        """`reset_from_fields` with float64 CUDA tensors `[n, nstate]` (and int32 CUDA `env_ids`): nothing touches the host."""
+        t = self.torch
+        f = t.as_tensor(fields, dtype=t.float64, device=self.device).reshape(-1, self.nstate).contiguous()
+        ids = None if env_ids is None else t.as_tensor(env_ids, dtype=t.int32, device=self.device).contiguous()
+        if ids is not None:
+            self._validate_indices(ids, self.B, "env_ids", f.shape[0])
+        self._use_current_stream()
+        self._check(self._L.rbc3d_reset_from_fields_dev(self._h, None if ids is None else C.c_void_p(ids.data_ptr()),
+                                                       C.c_void_p(f.data_ptr()), f.shape[0], int(project)))
 
     def noise_reset(self, env_ids=None, kick: float = 0.01, generator=None):
         """`initialize_model` (`rbc_sim3D.jl:169-178`) drawn and projected on the device for all or the listed environments."""
@@ -731,7 +791,7 @@ class Sim3D:
         return self.obs, self.nusselt
 
     def fields(self) -> np.ndarray:
-        out = np.empty((self.B, NSTATE3), np.float64)
+        out = np.empty((self.B, self.nstate), np.float64)
         self._use_current_stream()
         self._check(self._L.rbc3d_get_fields_host(self._h, _np_ptr(out)))
         return out
@@ -754,11 +814,13 @@ class Sim3D:
         return ms.value
 
 
-def split_fields3(fields: np.ndarray):
+def split_fields3(fields: np.ndarray, shape=(NZ3, NY3, NX3)):
     B = fields.shape[0]
-    shp = (B, NZ3, NY3, NX3)
-    return (fields[:, :NC3].reshape(shp), fields[:, NC3:2 * NC3].reshape(shp), fields[:, 2 * NC3:3 * NC3].reshape(shp),
-            fields[:, 3 * NC3:].reshape(B, NZ3 + 1, NY3, NX3))
+    nz, ny, nx = shape
+    nc = nz * ny * nx
+    shp = (B, nz, ny, nx)
+    return (fields[:, :nc].reshape(shp), fields[:, nc:2 * nc].reshape(shp), fields[:, 2 * nc:3 * nc].reshape(shp),
+            fields[:, 3 * nc:].reshape(B, nz + 1, ny, nx))
 
 
 def pack_fields3(b, u, v, w) -> np.ndarray:

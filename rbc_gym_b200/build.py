@@ -14,8 +14,8 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "librbc_b200.so"
-SOURCES = [CSRC / "rbc2d_lib.cu", CSRC / "rbc2dx_lib.cu", CSRC / "rbc2dx_split.cu", CSRC / "rbc3d_lib.cu"]
-HEADERS = [CSRC / "rbc2d_core.h", CSRC / "rbc2dx_core.h", CSRC / "rbc2dx_api.h", CSRC / "rbc2dx_kernel.cuh", CSRC / "rbc3d_core.h", CSRC / "rbc_common.h", CSRC.parent.parent / "include" / "rbc_b200.h"]
+SOURCES = [CSRC / "rbc2d_lib.cu", CSRC / "rbc2dx_lib.cu", CSRC / "rbc2dx_split.cu", CSRC / "rbc3d_lib.cu", CSRC / "rbc3dg_lib.cu"]
+HEADERS = [CSRC / "rbc2d_core.h", CSRC / "rbc2dx_core.h", CSRC / "rbc2dx_api.h", CSRC / "rbc2dx_kernel.cuh", CSRC / "rbc3d_core.h", CSRC / "rbc3dg_core.h", CSRC / "rbc3dg_api.h", CSRC / "rbc_common.h", CSRC.parent.parent / "include" / "rbc_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

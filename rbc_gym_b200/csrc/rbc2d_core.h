@@ -1031,10 +1031,15 @@ RBC_HD double cell_distance(const Real* uy)
 #define RBC_COUNT_ONE(p) (*(p) += 1)
 #endif
 template <typename Real, bool SPLIT, bool NXT_GLOBAL>
-RBC_HD_COLD bool env_epilogue(const Consts<Real>& C, const EnvIO<Real>& io, const Ctx<Real>& X, int env, const Real* cur, double* red,
-                         const RunFlags& F, bool state_changed, Real last_dtau, double t_old, int pend, bool second_pass)
+RBC_HD bool env_epilogue(const Consts<Real>& C, const EnvIO<Real>& io, const Ctx<Real>& X, int env, const Real* cur, double* red,
+                         const RunFlags& F, bool state_changed, Real last_dtau, bool second_pass)
 {
     const VecIO& V = io.vec;
+    // re-read here rather than carried in registers across the march; nobody has written them since the launch started
+    // (thread 0 updates them in the last phase of this function, behind several barriers)
+    const int pend = (!second_pass && V.mode == 1 && V.bank != nullptr && F.advance_clock) ? V.pending[env] : 0;
+    const double t_old = io.t[env];
+    state_changed = state_changed || pend;
     Real* st = io.state + (size_t)env * NSTATE;
     const int oz = NZ / C.obs_nz, ox = NX / C.obs_nx, nobs = C.obs_nz * C.obs_nx;
     double nu_s = 0, nu_o = 0;
@@ -1184,7 +1189,6 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
     // fused vector-env semantics: an environment that truncated on the previous call (next_step mode) is only
     // re-initialised by this one — gather from the checkpoint bank instead of loading its state, no march
     const int pend = (V.mode == 1 && V.bank != nullptr && F.advance_clock) ? V.pending[env] : 0;
-    const double t_old = io.t[env];
     const int nsub = pend ? 0 : F.nsub;
     const bool project_first = pend ? SPLIT : (F.project_first != 0);
 
@@ -1224,13 +1228,16 @@ RBC_HD void env_action_step(const Consts<Real>& C, const Tables<Real>& T, const 
 
     // the reduction scratch aliases the dead second state buffer when that one is on-chip
     double* red = NXT_GLOBAL ? X.red : reinterpret_cast<double*>(nxt);
-    const bool changed = nsub > 0 || project_first || pend;
-    if (env_epilogue<Real, SPLIT, NXT_GLOBAL>(C, io, X, env, cur, red, F, changed, last_dtau, t_old, pend, false)) {
-        // same_step auto-reset (or a NaN reset): terminal outputs went to final_*; gather the next episode's start
+    // one inlined copy of the epilogue, run a second time when the environment is re-initialised inside this launch
+    // (same_step auto-reset or a NaN reset: terminal outputs went to final_*, the next episode's start is gathered here)
+    bool changed = nsub > 0 || project_first;
+    RBC_NOUNROLL
+    for (int pass = 0; pass < 2; ++pass) {
+        if (!env_epilogue<Real, SPLIT, NXT_GLOBAL>(C, io, X, env, cur, red, F, changed, last_dtau, pass == 1)) break;
         const double* src = V.bank + (size_t)checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * NSTATE;
         RBC_PHASE(phase_load_bank(tid, src, cur);)
         if (SPLIT) project(C, X, cur, T.thomas_scale);
-        env_epilogue<Real, SPLIT, NXT_GLOBAL>(C, io, X, env, cur, red, F, true, Real(1), t_old, 0, true);
+        changed = true; last_dtau = Real(1);
     }
 }
 

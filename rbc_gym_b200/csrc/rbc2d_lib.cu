@@ -194,6 +194,8 @@ struct rbc2d_sim {
     long long* episode = nullptr;
     double* ep_return = nullptr;
     int* nan_count = nullptr;
+    float* final_obs = nullptr;      // device staging of the final_* outputs of rbc2d_vec_step_host (allocated on first use)
+    double* final_scalars = nullptr;
 };
 
 // the kernel-side view of the handle's vector-env state for one launch; `out` supplies the caller's final_* buffers
@@ -430,7 +432,7 @@ int rbc2d_destroy(rbc2d_sim* s)
     cudaSetDevice(s->cfg.device);
     void* ptrs[] = {s->state, s->gm, s->nxt, s->pressure, s->tinv, s->tw48, s->tw96, s->bank, s->t, s->nu_s, s->nu_o,
                     s->step, s->trunc, s->nan, s->obs, s->reward, s->actions, s->cell_dist, s->pending, s->episode, s->ep_return,
-                    s->nan_count};
+                    s->nan_count, s->final_obs, s->final_scalars};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < rbc2d_sim::kRing; ++i) {
         if (s->ev0[i]) cudaEventDestroy(s->ev0[i]);
@@ -549,10 +551,10 @@ int rbc2d_step_dev(rbc2d_sim* s, const float* actions, float* obs, float* reward
     return dispatch_env(s, actions, obs, reward, nu_s, nu_o, trunc, nan, nullptr, s->B, F, true);
 }
 
-int rbc2d_step_host(rbc2d_sim* s, const float* actions, float* obs, float* reward, double* nu_s, double* nu_o, int32_t* trunc,
-                    int32_t* nan)
+// host-buffer step shared by rbc2d_step_host and rbc2d_vec_step_host: `out` holds HOST pointers; with `vec` the launches carry
+// the fused vector-env semantics and the final_* outputs pass through handle-owned device staging buffers
+static int step_host_impl(rbc2d_sim* s, const float* actions, const rbc2d_vec_out& out, bool vec)
 {
-    if (!s || !actions) return fail("rbc2d_step_host: bad argument");
     CK(cudaSetDevice(s->cfg.device));
     const size_t B = s->B;
     const size_t nobs = (size_t)s->channels * s->cfg.obs_nz * s->cfg.obs_nx;
@@ -563,6 +565,20 @@ int rbc2d_step_host(rbc2d_sim* s, const float* actions, float* obs, float* rewar
     const int nch = rbc_pipe_chunks(s->B, lanes, len);
     int rc = rbc_pipe_prepare(&s->pipe, s->B);
     if (rc) return rc;
+    VecIO V;
+    const bool want_final = vec && (out.final_obs || out.final_nu_state || out.final_nu_obs || out.final_return);
+    if (vec) {
+        if (want_final && !s->final_obs) {
+            CK(cudaMalloc((void**)&s->final_obs, B * nobs * sizeof(float)));
+            CK(cudaMalloc((void**)&s->final_scalars, 3 * B * sizeof(double)));
+        }
+        rbc2d_vec_out dev = {};
+        if (want_final) {
+            dev.final_obs = s->final_obs; dev.final_nu_state = s->final_scalars; dev.final_nu_obs = s->final_scalars + B;
+            dev.final_return = s->final_scalars + 2 * B;
+        }
+        V = make_vec(s, &dev);
+    }
     Consts<float> tmp = make_consts<float>(s->hc);
     RunFlags F{tmp.nsub, 0, 1};
     const int slot = (int)(s->timed_launches % rbc2d_sim::kRing);
@@ -570,23 +586,51 @@ int rbc2d_step_host(rbc2d_sim* s, const float* actions, float* obs, float* rewar
     size_t off = 0;
     for (int c = 0; c < nch; ++c) {
         const size_t n = (size_t)len[c];
-        rc = dispatch_env(s, s->actions, s->obs, s->reward, s->nu_s, s->nu_o, s->trunc, s->nan, s->pipe.iota + off, (int)n, F, false);
+        rc = dispatch_env(s, s->actions, s->obs, s->reward, s->nu_s, s->nu_o, s->trunc, s->nan, s->pipe.iota + off, (int)n, F, false, V);
         if (rc) return rc;
         if (c == nch - 1) { CK(cudaEventRecord(s->ev1[slot], s->stream)); s->timed_launches += 1; }
         CK(cudaEventRecord(s->pipe.done[c], s->stream));
         CK(cudaStreamWaitEvent(s->pipe.copy, s->pipe.done[c], 0));
         cudaStream_t cs = s->pipe.copy;
-        if (obs) CK(cudaMemcpyAsync(obs + off * nobs, s->obs + off * nobs, n * nobs * sizeof(float), cudaMemcpyDeviceToHost, cs));
-        if (reward) CK(cudaMemcpyAsync(reward + off, s->reward + off, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
-        if (nu_s) CK(cudaMemcpyAsync(nu_s + off, s->nu_s + off, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
-        if (nu_o) CK(cudaMemcpyAsync(nu_o + off, s->nu_o + off, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
-        if (trunc) CK(cudaMemcpyAsync(trunc + off, s->trunc + off, n * sizeof(int), cudaMemcpyDeviceToHost, cs));
-        if (nan) CK(cudaMemcpyAsync(nan + off, s->nan + off, n * sizeof(int), cudaMemcpyDeviceToHost, cs));
+#define D2H(dst, src, count, type) if (dst) CK(cudaMemcpyAsync((dst) + off * (count), (src) + off * (count), n * (count) * sizeof(type), cudaMemcpyDeviceToHost, cs))
+        D2H(out.obs, s->obs, nobs, float);
+        D2H(out.reward, s->reward, 1, float);
+        D2H(out.nu_state, s->nu_s, 1, double);
+        D2H(out.nu_obs, s->nu_o, 1, double);
+        D2H(out.truncated, s->trunc, 1, int);
+        D2H(out.nan, s->nan, 1, int);
+        if (vec) {
+            D2H(out.t, s->t, 1, double);
+            D2H(out.step, s->step, 1, int);
+            D2H(out.episode_return, s->ep_return, 1, double);
+            if (want_final) {
+                D2H(out.final_obs, s->final_obs, nobs, float);
+                D2H(out.final_nu_state, s->final_scalars, 1, double);
+                D2H(out.final_nu_obs, s->final_scalars + B, 1, double);
+                D2H(out.final_return, s->final_scalars + 2 * B, 1, double);
+            }
+        }
+#undef D2H
         off += n;
     }
     CK(cudaStreamSynchronize(s->pipe.copy));
     CK(cudaStreamSynchronize(s->stream));
     return 0;
+}
+
+int rbc2d_step_host(rbc2d_sim* s, const float* actions, float* obs, float* reward, double* nu_s, double* nu_o, int32_t* trunc,
+                    int32_t* nan)
+{
+    if (!s || !actions) return fail("rbc2d_step_host: bad argument");
+    rbc2d_vec_out out = {};
+    out.obs = obs; out.reward = reward; out.nu_state = nu_s; out.nu_obs = nu_o; out.truncated = trunc; out.nan = nan;
+    return step_host_impl(s, actions, out, false);
+}
+
+int rbc2d_vec_step_host(rbc2d_sim* s, const float* actions, const rbc2d_vec_out* out)
+{
+    if (!s || !actions || !out) return fail("rbc2d_vec_step_host: bad argument");
+    return step_host_impl(s, actions, *out, true);
 }
 
 int32_t rbc_checkpoint_draw(int64_t seed, int64_t global_env, int64_t episode, int32_t n_episodes)

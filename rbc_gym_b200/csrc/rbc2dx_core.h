@@ -1009,14 +1009,17 @@ RBC_HD double cluster_cfin_sum(const CtxX<Real>& X, int my_rank, int idx)
 // epilogue of an action step (see rbc2d::env_epilogue): runs once per environment visit, and again (second_pass) after an
 // in-launch re-initialisation from the checkpoint bank.  Returns whether such a reset is due.
 template <typename G, typename Real, bool NXT_GLOBAL, bool SPLIT>
-RBC_HD_COLD bool env_epilogue(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, const RunFlags& F, int my_rank,
-                              SyncState& S, unsigned o_cur, unsigned o_nxt, Real last_dtau, bool state_changed, double t_old, int pend,
-                              bool second_pass)
+RBC_HD bool env_epilogue(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, const RunFlags& F, int my_rank,
+                   SyncState& S, unsigned o_cur, unsigned o_nxt, Real last_dtau, bool state_changed, bool second_pass)
 {
     (void)my_rank;
     constexpr int NX = G::NX, NZ = G::NZ, NZL = G::NZL, NT = G::NT, CL = G::CL, SX = G::SX, H = G::HALO, NRED = G::NRED, NFIN = G::NFIN;
     const rbc2d::VecIO& V = io.vec;
     Real* st = io.state + (size_t)env * G::NSTATE;
+    // re-read here rather than carried in registers across the march (see rbc2d::env_epilogue)
+    const int pend = (!second_pass && V.mode == 1 && V.bank != nullptr && F.advance_clock) ? V.pending[env] : 0;
+    const double t_old = io.t[env];
+    state_changed = state_changed || pend;
     const int oz = NZ / C.obs_nz, ox = NX / C.obs_nx, nobs = C.obs_nz * C.obs_nx;
     const unsigned o_red = (X.o_red != ~0u) ? X.o_red : o_nxt;   // fp32: the dead state buffer when it is large enough
     if (SPLIT && io.pressure != nullptr && state_changed) {
@@ -1232,7 +1235,6 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
     const rbc2d::VecIO& V = io.vec;
     // fused vector-env semantics (rbc2d_core.h): a pending environment is only re-initialised from the checkpoint bank
     const int pend = (V.mode == 1 && V.bank != nullptr && F.advance_clock) ? V.pending[env] : 0;
-    const double t_old = io.t[env];
     const int nsub = pend ? 0 : F.nsub;
     const bool project_first = pend ? SPLIT : (F.project_first != 0);
 
@@ -1287,13 +1289,15 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
         }
     }
 
-    const bool changed = nsub > 0 || project_first || pend;
-    if (env_epilogue<G, Real, NXT_GLOBAL, SPLIT>(C, io, X, env, F, my_rank, S, o_cur, o_nxt, last_dtau, changed, t_old, pend, false)) {
-        // same_step auto-reset (or a NaN reset): terminal outputs went to final_*; gather the next episode's start
+    // one inlined copy of the epilogue, run a second time when the environment is re-initialised inside this launch
+    bool changed = nsub > 0 || project_first;
+    RBC_NOUNROLL
+    for (int pass = 0; pass < 2; ++pass) {
+        if (!env_epilogue<G, Real, NXT_GLOBAL, SPLIT>(C, io, X, env, F, my_rank, S, o_cur, o_nxt, last_dtau, changed, pass == 1)) break;
         const double* src = V.bank + (size_t)rbc2d::checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * G::NSTATE;
         RBX_PHASE_L(G, phase_load_state<G>(tid, rank, src, RBX_PTR(o_cur));)
         if (SPLIT) project<G, Real, NXT_GLOBAL, SPLIT>(C, X, o_cur, o_nxt, my_rank, S, false);
-        env_epilogue<G, Real, NXT_GLOBAL, SPLIT>(C, io, X, env, F, my_rank, S, o_cur, o_nxt, Real(1), true, t_old, 0, true);
+        changed = true; last_dtau = Real(1);
     }
 }
 

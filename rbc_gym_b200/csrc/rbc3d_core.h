@@ -614,10 +614,12 @@ RBC_HD void project3(const Consts3<Real>& C, const Ctx3<Real>& X, Real* p)
 // vector-env bookkeeping (see rbc2d::env_epilogue).  Returns whether an in-launch re-initialisation is due.
 // ------------------------------------------------------------------------------------------
 template <typename Real>
-RBC_HD_COLD bool env_epilogue3(const Consts3<Real>& C, const EnvIO3<Real>& io, const Ctx3<Real>& X, int env, const Real* cur, const RunFlags3& F,
-                               double t_old, int pend, bool second_pass)
+RBC_HD bool env_epilogue3(const Consts3<Real>& C, const EnvIO3<Real>& io, const Ctx3<Real>& X, int env, const Real* cur, const RunFlags3& F,
+                          bool second_pass)
 {
     const rbc2d::VecIO& V = io.vec;
+    const int pend = (!second_pass && V.mode == 1 && V.bank != nullptr && F.advance_clock) ? V.pending[env] : 0;
+    const double t_old = io.t[env];
     Real* st = io.state + (size_t)env * NSTATE;
     RBC3_PHASE(
         double acc = 0, bad = 0;
@@ -716,7 +718,6 @@ RBC_HD void env_action_step3(const Consts3<Real>& C, const EnvIO3<Real>& io, con
     const rbc2d::VecIO& V = io.vec;
     // fused vector-env semantics: a pending environment (next_step mode) is only re-initialised from the checkpoint bank
     const int pend = (V.mode == 1 && V.bank != nullptr && F.advance_clock) ? V.pending[env] : 0;
-    const double t_old = io.t[env];
     const int nsub = pend ? 0 : F.nsub;
     if (pend) {
         const double* src = V.bank + (size_t)rbc2d::checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * NSTATE;
@@ -754,11 +755,13 @@ RBC_HD void env_action_step3(const Consts3<Real>& C, const EnvIO3<Real>& io, con
             nxt = (cur == X.bufA) ? X.bufB : X.bufA;
         }
     }
-    if (env_epilogue3(C, io, X, env, cur, F, t_old, pend, false)) {
-        // same_step auto-reset (or a NaN reset): terminal outputs went to final_*; gather the next episode's start
+    // one inlined copy of the epilogue, run a second time when the environment is re-initialised inside this launch
+    RBC_NOUNROLL
+    for (int pass = 0; pass < 2; ++pass) {
+        if (!env_epilogue3(C, io, X, env, cur, F, pass == 1)) break;
         const double* src = V.bank + (size_t)rbc2d::checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * NSTATE;
         RBC3_PHASE(for (int q = tid; q < NSTATE; q += NT) st[q] = (Real)src[q];)
-        env_epilogue3(C, io, X, env, st, F, t_old, 0, true);
+        cur = st;
     }
 }
 

@@ -6,6 +6,7 @@
 
 #include "../../include/rbc_b200.h"
 #include "rbc3d_core.h"
+#include "rbc3dg_api.h"
 #include "rbc_common.h"
 
 using namespace rbc3d;
@@ -47,7 +48,7 @@ rbc3d_env_kernel(Consts3<Real> C, EnvIO3<Real> io, Real* buf_all, Real* gm_all, 
 
 template <typename Real>
 __global__ void rbc3d_set_fields_kernel(Real* state, const double* fields, const int* env_ids, const int* src_idx, int n, int n_src,
-                                        double* t, int* step, int* trunc, int* nan, int B)
+                                        double* t, int* step, int* trunc, int* nan, int B, int NSTATE)
 {
     // indices are validated by the caller (IndexError in the Python facade); out-of-range entries are skipped, never clamped
     for (int j = blockIdx.y; j < n; j += gridDim.y) {
@@ -71,6 +72,8 @@ __global__ void rbc3d_get_fields_kernel(const Real* state, double* out, size_t t
 struct rbc3d_sim {
     rbc3d_config cfg;
     HostConfig3 hc;
+    rbc3dg_api::Plan* plan = nullptr;     // stage-streaming kernels for grids other than 32 x 32 x 16 (rbc3dg_lib.cu)
+    int nstate = NSTATE, ncell = NC;
     int B = 0, grid = 0, n_ep = 0;
     size_t smem = 0, rs = 4;
     cudaStream_t stream = nullptr;
@@ -160,6 +163,24 @@ static int launch3(rbc3d_sim* s, const float* actions, float* obs, float* reward
 static int dispatch3(rbc3d_sim* s, const float* actions, float* obs, float* reward, double* nu, int* trunc, int* nan, const int* env_ids,
                      int n, RunFlags3 F, bool time_it, bool want_obs = true, const rbc2d::VecIO& vec = rbc2d::VecIO())
 {
+    if (s->plan) {
+        if (vec.mode >= 0) return rbc_fail("rbc3d: the fused vector step is available on the 32 x 32 x 16 grid only; drive resets from the caller");
+        rbc3dg_api::IoRaw io;
+        io.state = s->state;
+        io.actions = actions ? actions : s->actions;
+        io.obs = want_obs ? (obs ? obs : s->obs) : nullptr;
+        io.reward = reward ? reward : s->reward;
+        io.nusselt = nu ? nu : s->nu;
+        io.t = s->t; io.step_count = s->step;
+        io.truncated = trunc ? trunc : s->trunc;
+        io.nan_flag = nan ? nan : s->nan;
+        if (n <= 0) return 0;
+        if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
+        int rc = rbc3dg_api::launch(s->plan, io, env_ids, n, F.nsub, F.project_first, F.advance_clock, s->stream, &s->launches);
+        if (rc) return rc;
+        if (time_it) { CK(cudaEventRecord(s->ev1, s->stream)); s->timed = true; }
+        return 0;
+    }
     const bool f32 = s->cfg.precision == 32, split = s->cfg.split != 0;
     if (f32) return split ? launch3<float, true>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs, vec)
                           : launch3<float, false>(s, actions, obs, reward, nu, trunc, nan, env_ids, n, F, time_it, want_obs, vec);
@@ -173,7 +194,10 @@ int rbc3d_create(const rbc3d_config* cfg, rbc3d_sim** out)
 {
     if (!cfg || !out) return rbc_fail("rbc3d_create: null argument");
     *out = nullptr;
-    if (cfg->nx != NX || cfg->ny != NY || cfg->nz != NZ) return rbc_fail("rbc3d_create: this build supports a 32 x 32 x 16 grid only");
+    const char* force = getenv("RBC_B200_3D_GENERIC");
+    const bool dedicated = cfg->nx == NX && cfg->ny == NY && cfg->nz == NZ && !(force && force[0] == '1');
+    if (!dedicated && !rbc3dg_api::supported(cfg->nx, cfg->ny, cfg->nz))
+        return rbc_fail("rbc3d_create: grid must have nx, ny powers of two in 8..256 and 6 <= nz <= 256");
     if (cfg->num_envs < 1) return rbc_fail("rbc3d_create: num_envs must be >= 1");
     if (cfg->precision != 32 && cfg->precision != 64) return rbc_fail("rbc3d_create: precision must be 32 or 64");
     if (cfg->heaters < 1 || cfg->heaters > MAX_HEATERS) return rbc_fail("rbc3d_create: heaters must be in 1..16");
@@ -191,10 +215,24 @@ int rbc3d_create(const rbc3d_config* cfg, rbc3d_sim** out)
     s->hc = HostConfig3{cfg->ra, cfg->pr, cfg->lx, cfg->ly, cfg->lz, cfg->b_min, cfg->b_max - cfg->b_min, cfg->heater_limit,
                         cfg->heater_duration, cfg->dt_solver, cfg->episode_length, cfg->heaters};
     const bool f32 = cfg->precision == 32, split = cfg->split != 0;
-    int rc = f32 ? (split ? prepare3<float, true>(s) : prepare3<float, false>(s))
+    int rc;
+    if (dedicated) {
+        rc = f32 ? (split ? prepare3<float, true>(s) : prepare3<float, false>(s))
                  : (split ? prepare3<double, true>(s) : prepare3<double, false>(s));
+    } else {
+        const rbc3dg::HostConfigG hg{cfg->ra, cfg->pr, cfg->lx, cfg->ly, cfg->lz, cfg->b_min, cfg->b_max - cfg->b_min, cfg->heater_limit,
+                                     cfg->heater_duration, cfg->dt_solver, cfg->episode_length, cfg->heaters};
+        rc = rbc3dg_api::create(hg, cfg->nx, cfg->ny, cfg->nz, cfg->num_envs, cfg->precision, cfg->device, &s->plan);
+        if (!rc) {
+            s->nstate = rbc3dg_api::values_per_env(s->plan);
+            s->ncell = cfg->nx * cfg->ny * cfg->nz;
+            s->smem = rbc3dg_api::smem_bytes(s->plan);
+            s->grid = 1 << 30;                    // no persistent grid: every launch covers the environments it is given
+        }
+    }
     if (rc) { rbc3d_destroy(s); return rc; }
     const size_t B = s->B, rs = s->rs;
+    const size_t NSTATE = s->nstate;              // shadows the compile-time constant of the dedicated kernel from here on
 #define ALLOC3(ptr, bytes)                                                                      \
     do {                                                                                        \
         cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                   \
@@ -206,8 +244,10 @@ int rbc3d_create(const rbc3d_config* cfg, rbc3d_sim** out)
         cudaMemset((ptr), 0, (bytes));                                                          \
     } while (0)
     ALLOC3(s->state, B * NSTATE * rs);
-    ALLOC3(s->buf, (size_t)s->grid * 2 * NSTATE * rs);
-    ALLOC3(s->gm, (size_t)s->grid * NG * rs);
+    if (dedicated) {
+        ALLOC3(s->buf, (size_t)s->grid * 2 * NSTATE * rs);
+        ALLOC3(s->gm, (size_t)s->grid * NG * rs);
+    }
     ALLOC3(s->t, B * sizeof(double));
     ALLOC3(s->nu, B * sizeof(double));
     ALLOC3(s->step, B * sizeof(int));
@@ -237,6 +277,7 @@ int rbc3d_destroy(rbc3d_sim* s)
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    rbc3dg_api::destroy(s->plan);
     rbc_pipe_destroy(&s->pipe);
     delete s;
     return 0;
@@ -248,15 +289,15 @@ int rbc3d_set_stream(rbc3d_sim* s, void* stream)
     s->stream = (cudaStream_t)stream;
     return 0;
 }
-int rbc3d_state_values_per_env(const rbc3d_sim* s) { return s ? NSTATE : -1; }
+int rbc3d_state_values_per_env(const rbc3d_sim* s) { return s ? s->nstate : -1; }
 
 int rbc3d_load_checkpoints(rbc3d_sim* s, const double* fields_host, int32_t n_episodes)
 {
     if (!s || !fields_host || n_episodes < 1) return rbc_fail("rbc3d_load_checkpoints: bad argument");
     CK(cudaSetDevice(s->cfg.device));
     if (s->bank) { cudaFree(s->bank); s->bank = nullptr; }
-    CK(cudaMalloc((void**)&s->bank, (size_t)n_episodes * NSTATE * sizeof(double)));
-    CK(cudaMemcpyAsync(s->bank, fields_host, (size_t)n_episodes * NSTATE * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMalloc((void**)&s->bank, (size_t)n_episodes * s->nstate * sizeof(double)));
+    CK(cudaMemcpyAsync(s->bank, fields_host, (size_t)n_episodes * s->nstate * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     s->n_ep = n_episodes;
     return 0;
@@ -266,9 +307,9 @@ static int set_fields3(rbc3d_sim* s, const double* dfields, const int* env_ids_d
 {
     dim3 grid(16, n < 2048 ? n : 2048);
     if (s->cfg.precision == 32)
-        rbc3d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, dfields, env_ids_dev, src_idx_dev, n, n_src, s->t, s->step, s->trunc, s->nan, s->B);
+        rbc3d_set_fields_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->state, dfields, env_ids_dev, src_idx_dev, n, n_src, s->t, s->step, s->trunc, s->nan, s->B, s->nstate);
     else
-        rbc3d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, dfields, env_ids_dev, src_idx_dev, n, n_src, s->t, s->step, s->trunc, s->nan, s->B);
+        rbc3d_set_fields_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->state, dfields, env_ids_dev, src_idx_dev, n, n_src, s->t, s->step, s->trunc, s->nan, s->B, s->nstate);
     CK(cudaGetLastError());
     s->launches += 1;
     return 0;
@@ -290,8 +331,8 @@ int rbc3d_reset_from_fields_host(rbc3d_sim* s, const int32_t* env_ids_host, cons
     CK(cudaSetDevice(s->cfg.device));
     double* dfields = nullptr;
     int* dids = nullptr;
-    CK(cudaMalloc((void**)&dfields, (size_t)n * NSTATE * sizeof(double)));
-    CK(cudaMemcpyAsync(dfields, fields, (size_t)n * NSTATE * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMalloc((void**)&dfields, (size_t)n * s->nstate * sizeof(double)));
+    CK(cudaMemcpyAsync(dfields, fields, (size_t)n * s->nstate * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     if (env_ids_host) {
         CK(cudaMalloc((void**)&dids, n * sizeof(int)));
         CK(cudaMemcpyAsync(dids, env_ids_host, n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
@@ -326,6 +367,15 @@ int rbc3d_step_dev(rbc3d_sim* s, const float* actions, float* obs, float* reward
     Consts3<float> tmp = make_consts3<float>(s->hc);
     RunFlags3 F{tmp.nsub, 0, 1};
     return dispatch3(s, actions, obs, reward, nusselt, trunc, nan, nullptr, s->B, F, true, obs != nullptr);
+}
+
+int rbc3d_set_rayleigh_per_env(rbc3d_sim* s, const double* ra_host)
+{
+    if (!s) return rbc_fail("null handle");
+    if (!s->plan)
+        return rbc_fail("rbc3d_set_rayleigh_per_env: the dedicated 32 x 32 x 16 kernel takes one Rayleigh number per handle; "
+                        "set RBC_B200_3D_GENERIC=1 to run that grid through the stage-streaming kernels");
+    return rbc3dg_api::set_rayleigh(s->plan, ra_host);
 }
 
 int rbc3d_set_autoreset(rbc3d_sim* s, const rbc_autoreset* cfg)
@@ -404,7 +454,7 @@ int rbc3d_step_host(rbc3d_sim* s, const float* actions, float* obs, float* rewar
 {
     if (!s || !actions) return rbc_fail("rbc3d_step_host: bad argument");
     CK(cudaSetDevice(s->cfg.device));
-    const size_t B = s->B, na = (size_t)s->cfg.heaters * s->cfg.heaters, nobs = 4 * (size_t)NC;
+    const size_t B = s->B, na = (size_t)s->cfg.heaters * s->cfg.heaters, nobs = 4 * (size_t)s->ncell;
     if (obs && !s->obs) CK(cudaMalloc((void**)&s->obs, B * nobs * sizeof(float)));
     CK(cudaMemcpyAsync(s->actions, actions, B * na * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     // chunks of whole waves of the persistent grid; the copy stream drains chunk c (262 KB of observation per environment)
@@ -449,7 +499,7 @@ int rbc3d_get_fields_host(rbc3d_sim* s, double* out)
 {
     if (!s || !out) return rbc_fail("rbc3d_get_fields_host: bad argument");
     CK(cudaSetDevice(s->cfg.device));
-    const size_t total = (size_t)s->B * NSTATE;
+    const size_t total = (size_t)s->B * s->nstate;
     double* tmp = nullptr;
     CK(cudaMalloc((void**)&tmp, total * sizeof(double)));
     if (s->cfg.precision == 32) rbc3d_get_fields_kernel<float><<<148 * 8, 256, 0, s->stream>>>((const float*)s->state, tmp, total);

@@ -6,8 +6,11 @@ every env boots its own Julia runtime and ships pickled numpy arrays through pip
 handle whose observations, rewards and flags are CUDA tensors that never leave the device.
 
 `step()` is ONE kernel launch: the march, the observation / Nusselt / reward epilogue, truncation AND the auto-reset
-run inside `rbc2d_vec_step_dev` / `rbc3d_vec_step_dev` (`VecIO` in `csrc/rbc2d_core.h`), with no host synchronisation
-(except the NaN check of `nan_policy="raise"`, one 4-byte read).  Auto-reset follows the two conventions the
+run inside `rbc2d_vec_step_dev` / `rbc3d_vec_step_dev` (`VecIO` in `csrc/rbc2d_core.h`), with no host synchronisation:
+the reference's NaN error (`rbc2D.py:170-171`) is raised by the call AFTER the failing one by default
+(`nan_policy="raise_deferred"`: the step kernel counts failures on the device, the count is copied to pinned memory behind
+the step and read one call later), `"raise"` reads it in the failing call itself at the price of one host synchronisation per
+step, `"reset"` re-initialises only the failed environments inside the kernel.  Auto-reset follows the two conventions the
 reference's callers rely on:
   "next_step"  gymnasium 1.1.1 default: an env that truncated is reset by the *next* `step` call (its action
                is ignored, it is not marched, reward 0, the reset observation is returned).
@@ -108,7 +111,7 @@ class _VectorBase:
         return _mix63(self.torch, x)
 
     def _use_fused(self) -> bool:
-        return self.fused and self.sim.n_episodes > 0
+        return self.fused and self.sim.n_episodes > 0 and getattr(self.sim, "fused_autoreset", True)
 
     def _sync_fused_config(self):
         self.sim.set_autoreset(self.autoreset_mode, nan_reset=self.nan_policy == "reset", seed=self.seed, env_id_offset=self.env_id_offset)
@@ -145,8 +148,8 @@ class RBCVectorEnv2D(_VectorBase):
     def __init__(self, num_envs: int, rayleigh_number: float = 10_000, episode_length: float = 300, observation_shape=(8, 48),
                  state_shape=(64, 96), heater_segments: int = 12, heater_limit: float = 0.75, heater_duration: float = 1.5,
                  pressure: bool = False, checkpoint: Optional[str] = None, dt_solver: float = 0.03, precision: int = 32,
-                 device: int = 0, autoreset_mode: str = "next_step", seed: int = 0, env_id_offset: int = 0, nan_policy: str = "raise",
-                 info_state: bool = False, copy: bool = True, fused: bool = True):
+                 device: int = 0, autoreset_mode: str = "next_step", seed: int = 0, env_id_offset: int = 0,
+                 nan_policy: str = "raise_deferred", info_state: bool = False, copy: bool = True, fused: bool = True):
         import torch
 
         self.ra = rayleigh_number
@@ -252,6 +255,30 @@ class RBCVectorEnv2D(_VectorBase):
         self._after_fused_step()
         return self._out(obs), self._out(rew), self._terminated, trunc.to(t.bool), info
 
+    def alloc_host_outputs(self, pinned: bool = True):
+        """Page-locked numpy buffers for `step_host` (final_* included in same_step mode / under nan_policy="reset")."""
+        return self.sim.alloc_vec_host_outputs(pinned, final=self.autoreset_mode == "same_step" or self.nan_policy == "reset")
+
+    def step_host(self, actions: np.ndarray, out: Optional[dict] = None):
+        """`step` for callers that live on the host (numpy actions in, numpy results out — what a policy running elsewhere, or
+        the reference's own pipe-based rollout loop, exchanges per step): one call into `rbc2d_vec_step_host`, which overlaps
+        the device-to-host copies of a chunk of environments with the march of the next chunk.  Returns
+        (obs, reward, terminated, truncated, info) as views of `out` (allocate it once with `alloc_host_outputs`)."""
+        if not self._use_fused():
+            raise RuntimeError("step_host needs a checkpoint bank (the fused vector step); call step() with device tensors instead")
+        if out is None:
+            out = self.alloc_host_outputs()
+        self.sim.vec_step_host(actions, out)
+        if self.nan_policy != "reset" and out["nan"].any():
+            raise RuntimeError("Error in simulation step, probably NaN values")      # rbc2D.py:170-171
+        info = {"nusselt_state": out["nu_state"], "nusselt_obs": out["nu_obs"], "t": out["t"], "step": out["step"],
+                "episode_return": out["episode_return"], "nan": out["nan"].astype(bool)}
+        if "final_obs" in out:
+            info["final_obs"] = out["final_obs"]
+            info["final_info"] = {"nusselt_state": out["final_nu_state"], "nusselt_obs": out["final_nu_obs"],
+                                  "episode_return": out["final_return"]}
+        return out["obs"], out["reward"], np.zeros(self.num_envs, bool), out["truncated"].astype(bool), info
+
     def _step_python(self, actions):
         """The same semantics with the resets driven from Python (separate reset + observe launches, host reads of the flags):
         the noise-initialisation path, and the reference the fused kernel is tested against (`fused=False`)."""
@@ -329,7 +356,7 @@ class RBCVectorEnv3D(_VectorBase):
                  state_shape=(16, 32, 32), temperature_difference=(1, 2), heater_segments: int = 8, heater_limit: float = 0.9,
                  heater_duration: float = 0.125, episode_length: float = 300, dt_solver: float = 0.01, checkpoint: Optional[str] = None,
                  precision: int = 32, device: int = 0, autoreset_mode: str = "next_step", seed: int = 0, env_id_offset: int = 0,
-                 nan_policy: str = "raise", copy: bool = False, fused: bool = True):
+                 nan_policy: str = "raise_deferred", copy: bool = False, fused: bool = True):
         import torch
 
         self.is_3d = True

@@ -42,6 +42,33 @@ def build_x():
     return _compile(_SOX, [_HERE / "emu_rbc2dx.cpp"], [csrc / "rbc2d_core.h", csrc / "rbc2dx_core.h"])
 
 
+_SOG = _HERE / "libemu_rbc3dg.so"
+
+
+def build_g():
+    """The stage-streaming 3D kernels for arbitrary grids (rbc3dg_core.h), emulated."""
+    csrc = _ROOT / "rbc_gym_b200" / "csrc"
+    return _compile(_SOG, [_HERE / "emu_rbc3dg.cpp"], [csrc / "rbc2d_core.h", csrc / "rbc3dg_core.h"])
+
+
+def step3g(state, actions, ra, shape, precision=64, heater_duration=0.125, dt_solver=0.01, heaters=8, heater_limit=0.9, project_first=False,
+           nsub=-1, ra_env=None, domain=(2.0, 4 * math.pi, 4 * math.pi)):
+    """state: [B, nstate] (b,u,v,w flattened, each [z][y][x]) on the grid `shape` = (nz, ny, nx); actions [B, 8, 8]."""
+    lib = C.CDLL(str(build_g()))
+    nz, ny, nx = shape
+    B = state.shape[0]
+    dt = np.float64 if precision == 64 else np.float32
+    st = np.array(state, dtype=dt, order="C")
+    h = HostConfig3(ra, 0.7, domain[2], domain[1], domain[0], 1.0, 1.0, heater_limit, heater_duration, dt_solver, 300.0, heaters)
+    a = np.ascontiguousarray(actions, dtype=np.float32)
+    nu, nf = np.zeros(B), np.zeros(B, np.int32)
+    re = None if ra_env is None else np.ascontiguousarray(ra_env, dtype=np.float64)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
+    rc = lib.emu_rbc3dg_step(C.byref(h), nx, ny, nz, precision, B, vp(st), vp(a), vp(re), vp(nu), vp(nf), int(project_first), nsub)
+    assert rc == 0, rc
+    return dict(state=st, nusselt=nu, nan=nf)
+
+
 class HostConfig3(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("ra", "pr", "lx", "ly", "lz", "b_top", "delta_b", "heater_limit", "heater_duration",
                                           "dt_solver", "episode_length")] + [("heaters", C.c_int)]

@@ -95,3 +95,40 @@ def test_config3_fp32_long_time_average_matches_fp64_and_the_coarse_grid_ensembl
     se = max(stds.values()) / np.sqrt(32)
     assert abs(means[32] - means[64]) < 4 * se + 0.3, (means, stds)
     assert 9.0 < means[32] < 21.0, means
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_noise_spinup_ensembles_match_the_reference_checkpoints_at_all_seven_rayleigh_numbers(precision):
+    """The reference's 2D checkpoint files ARE an ensemble experiment: per Rayleigh number 40 independent uncontrolled runs of the
+    Julia simulation from noise (kick 0.02), sampled at t = 600 (`rbc_sim2D.jl:14-72`, `scripts/create_checkpoints_2D.sh:18-20`).
+    The same experiment on the GPU — 128 environments per Rayleigh number, noise initialisation + `set!` projection, 600 action
+    steps of dt = 1 with zero action — must give the same ensemble: mean Nu_state and mean Nu_obs at t = 600 within two
+    standard errors of the difference of the means (Ra = 1e4: every environment inside the fixed-point band), and comparable
+    ensemble widths.  Reference numbers: tests/golden/checkpoint_ensemble_stats.json (tools/make_checkpoint_stats.py)."""
+    import json
+    import torch
+    from rbc_gym_b200 import backend
+    ref = json.loads((ROOT / "tests/golden/checkpoint_ensemble_stats.json").read_text())["states"]
+    n = 128
+    report = {}
+    for ra, rows in ref.items():
+        sim = backend.Sim2D(n, ra=float(ra), dt_action=1.0, precision=precision)
+        sim.noise_reset(kick=0.02, generator=torch.Generator(device="cuda").manual_seed(int(float(ra)) % 9973))
+        zero = torch.zeros((n, 12), device="cuda")
+        for _ in range(600):
+            _, _, nus, nuo, _, nan = sim.step(zero)
+        assert int(nan.sum()) == 0, ra
+        g_s, g_o = nus.cpu().numpy(), nuo.cpu().numpy()
+        r_s, r_o = np.array([r["nu_state"] for r in rows]), np.array([r["nu_obs"] for r in rows])
+        report[ra] = (g_s.mean(), r_s.mean(), g_s.std(), r_s.std())
+        if float(ra) == 1e4:
+            # near-fixed point: band of the 40 reference states widened by the residual oscillation (SURVEY section 4)
+            assert g_s.min() > r_s.min() - 3e-4 and g_s.max() < r_s.max() + 3e-4, (g_s.min(), g_s.max())
+            assert g_o.min() > r_o.min() - 4e-4 and g_o.max() < r_o.max() + 4e-4
+        else:
+            for g, r in ((g_s, r_s), (g_o, r_o)):
+                se = np.sqrt(r.var() / len(r) + g.var() / len(g))
+                assert abs(g.mean() - r.mean()) < 2 * se, (ra, g.mean(), r.mean(), se)
+                assert 0.6 * r.std() < g.std() < 1.6 * r.std(), (ra, g.std(), r.std())
+        sim.close()
+    print({k: tuple(round(float(x), 3) for x in v) for k, v in report.items()})

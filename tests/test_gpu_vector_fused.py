@@ -31,13 +31,12 @@ def test_fused_step_equals_python_driven_autoreset_2d(mode, precision, pressure)
     assert torch.equal(of, op) and torch.equal(inf["nusselt_obs"], inp["nusselt_obs"])
     assert set(inf) >= {"t", "step", "nusselt_state", "nusselt_obs"} and (inf["step"] == 1).all() and (inf["t"] == 0).all()
     g = torch.Generator(device="cuda").manual_seed(3)
-    launches = fused.sim.launch_info()["launches"]
     n_trunc = 0
     for it in range(8):
         a = torch.rand((n, 12), device="cuda", generator=g) * 2 - 1
+        launches = fused.sim.launch_info()["launches"]
         f, p = fused.step(a), plain.step(a)
-        launches += 1
-        assert fused.sim.launch_info()["launches"] == launches           # one kernel launch of ours per vector step
+        assert fused.sim.launch_info()["launches"] == launches + 1       # one kernel launch of ours per vector step
         for k in range(4):
             assert same(f[k], p[k]), (it, k)
         for k in ("nusselt_state", "nusselt_obs", "t", "step", "episode_return", "nan"):
@@ -143,3 +142,28 @@ def test_reset_indices_are_validated():
     with pytest.raises(IndexError):
         sim.reset_from_fields(np.zeros((1, sim.nstate)), env_ids=[-1])
     sim.close()
+
+
+@pytest.mark.parametrize("mode", ["next_step", "same_step"])
+def test_host_buffer_vector_step_equals_device_vector_step(mode):
+    """`rbc2d_vec_step_host` (chunked launches, copies overlapped on a second stream) against `rbc2d_vec_step_dev`."""
+    import torch
+    from rbc_gym_b200.envs import RBCVectorEnv2D
+    n = 700
+    kw = dict(rayleigh_number=100_000, heater_duration=0.09, episode_length=0.27, checkpoint=CKPT, autoreset_mode=mode, seed=8)
+    dev, host = RBCVectorEnv2D(n, **kw), RBCVectorEnv2D(n, **kw)
+    dev.reset(); host.reset()
+    out = host.alloc_host_outputs()
+    rng = np.random.default_rng(2)
+    for it in range(7):
+        a = rng.uniform(-1, 1, (n, 12)).astype(np.float32)
+        d = dev.step(torch.from_numpy(a).cuda())
+        h = host.step_host(a, out)
+        assert np.array_equal(d[0].cpu().numpy(), h[0]) and np.array_equal(d[1].cpu().numpy(), h[1]) and np.array_equal(d[3].cpu().numpy(), h[3])
+        for k in ("nusselt_state", "nusselt_obs", "t", "step", "episode_return"):
+            assert np.array_equal(d[4][k].cpu().numpy(), h[4][k]), (it, k)
+        if mode == "same_step" and h[3].any():
+            m = h[3]
+            assert np.array_equal(d[4]["final_obs"].cpu().numpy()[m], h[4]["final_obs"][m])
+            assert np.array_equal(d[4]["final_info"]["episode_return"].cpu().numpy()[m], h[4]["final_info"]["episode_return"][m])
+    dev.close(); host.close()

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Round-2 GPU check: the whole -m gpu suite, smoke(), the default bench line, the reference arm.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+echo "== pytest -m gpu"
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"
+tail -15 gpurun_out/pytest_gpu.log
+echo "== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -5 gpurun_out/smoke.log
+echo "== bench"
+timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"
+tail -c 3000 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err

@@ -27,7 +27,10 @@ stages = envs * stages_per_env
 print(f"per stage: cycles {g('sm__cycles_elapsed.avg') * 148 / stages:.0f}  warp-instr {g('smsp__inst_executed.sum') / stages:.0f} "
       f"(thread-instr/cell {g('smsp__inst_executed.sum') / stages * 32 / cells:.1f})  smem wavefronts {g('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum') / stages:.0f} "
       f"conflicts {g('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum') / stages:.0f}")
-print(f"dram bytes per env-step: read {g('dram__bytes_read.sum') * (1e6 if M['dram__bytes_read.sum'][1]=='Mbyte' else 1) / envs:.0f} write {g('dram__bytes_write.sum') * (1e6 if M['dram__bytes_write.sum'][1]=='Mbyte' else 1) / envs:.0f}")
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+def gb(k):
+    return g(k) * UNIT[M[k][1]]
+print(f"dram bytes per env-step: read {gb('dram__bytes_read.sum') / envs:.0f} write {gb('dram__bytes_write.sum') / envs:.0f}")
 for k, (v, u) in M.items():
     if "average_warps_issue_stalled" in k and "_per_issue_active" in k and float(v) > 0.05:
         print(f"  stall {k.split('issue_stalled_')[1].split('_per')[0]:22s} {float(v):.3f}")
