@@ -286,6 +286,10 @@ int rbc3d_vec_step_dev(rbc3d_sim* sim, const float* actions_dev, const rbc3d_vec
 int rbc3d_vec_nan_count(rbc3d_sim* sim, int32_t clear, int64_t* count);
 int rbc3d_vec_nan_count_async(rbc3d_sim* sim, int32_t* count_host_pinned);
 int rbc3d_observe_dev(rbc3d_sim* sim, float* obs_dev, double* nusselt_dev);
+/* render("rgb_array") for the whole batch on the device (rbc3D.py:247-318: PyVista volume rendering of the temperature, turbo
+ * colormap, clim = temperature_difference, opacity "sigmoid_1", 800 x 608, isometric camera; used by example/run_wandb.py:25-59):
+ * the same picture ray-marched with one thread per pixel.  out_dev: [B][height][width][3] uint8. */
+int rbc3d_render_rgb_dev(rbc3d_sim* sim, uint8_t* out_dev, int32_t height, int32_t width);
 int rbc3d_get_fields_host(rbc3d_sim* sim, double* fields_host);
 int rbc3d_get_info_host(rbc3d_sim* sim, double* t_host, int32_t* step_host);
 int rbc3d_launch_count(const rbc3d_sim* sim, int64_t* launches, int32_t* grid, int32_t* smem_bytes);

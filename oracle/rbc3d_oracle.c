@@ -16,11 +16,19 @@
  * PARITY PIN: the reference's 3D checkpoint files are missing from the mount (.MISSING_LARGE_BLOBS), so this
  * oracle is pinned (tests/test_oracle3d.py) to the fixture-pinned 2D oracle: a y-invariant state (v = 0) must
  * evolve exactly like the 2D oracle, and so must its x<->y transposed twin (which exercises every y-direction
- * code path); plus exact known answers (conduction state, Nu = 1, heater patches).  Against Julia output the pin
- * is statistical: run with the protocol and resolution of the reference's experiments/flowstats/flowstats_ra.py
- * (64 x 64 x 32) it reproduces the Julia-produced Nusselt series of flowstats_ra.pkl — linear growth rates within
- * 2 %, first-burst time and height, saturated means within one standard deviation at Ra = 500, 4000, 16000
- * (tools/oracle3d_flowstats.py, tests/golden/oracle3d_flowstats_64x64x32.json, tests/test_oracle3d_flowstats.py).
+ * code path); plus exact known answers (conduction state, Nu = 1, heater patches).  Against Julia output the pin is
+ * statistical: run with the protocol and resolution of the reference's experiments/flowstats/flowstats_ra.py (64 x 64 x 32,
+ * all 14 Rayleigh numbers x 300 samples; tools/oracle3d_flowstats.py -> tests/golden/oracle3d_flowstats_64x64x32.json) it
+ * reproduces the Julia-produced Nusselt series of flowstats_ra.pkl (tests/golden/flowstats_julia_64x64x32.json):
+ *   - saturated mean Nu, Ra >= 8000: within 0.2 ... 1.9 % (0.08 ... 0.75 of the Julia series' own standard deviation), mean
+ *     difference +0.4 %, no sign pattern; Ra <= 2000 freezes into noise-selected steady planforms (not comparable run by run);
+ *   - noise level after the set! projection and one time unit: within 10 %;
+ *   - transient growth rate of Nu - 1 (largest local slope): within 1.2 % for Ra <= 4000, but 1.4 ... 2.9 % ABOVE Julia for
+ *     Ra >= 8000.  A 24-seed GPU ensemble (same scheme, seed scatter 0.4 %) puts Julia inside the scatter at Ra = 500 and
+ *     4 ... 7 sigma below the ensemble for Ra >= 16000: a real, unexplained difference in the linear growth of marginally
+ *     resolved modes (it has the opposite Ra signature of any error in nu, kappa, Pr, the buoyancy scale or the domain
+ *     height, which all act most strongly near onset).  tests/test_oracle3d_flowstats.py asserts the
+ *     measured envelope instead of hiding it in a wide tolerance.
  * Field-by-field against Julia: UNPINNED (no 3D fields from the reference are available).
  *
  * Layout (C order, x fastest):  b,u,v: [nz][ny][nx];  w: [nz+1][ny][nx].

@@ -97,7 +97,7 @@ ABI_SYMBOLS = (
     "rbc3d_observe_dev", "rbc3d_get_fields_host", "rbc3d_get_info_host", "rbc3d_launch_count", "rbc3d_last_step_kernel_ms",
     "rbc_checkpoint_draw", "rbc2d_set_autoreset", "rbc2d_vec_reset_dev", "rbc2d_vec_mark_reset_dev", "rbc2d_vec_step_dev", "rbc2d_vec_step_host",
     "rbc2d_vec_nan_count", "rbc2d_vec_nan_count_async", "rbc3d_set_autoreset", "rbc3d_vec_reset_dev", "rbc3d_vec_mark_reset_dev",
-    "rbc3d_vec_step_dev", "rbc3d_vec_nan_count", "rbc3d_vec_nan_count_async", "rbc3d_set_rayleigh_per_env",
+    "rbc3d_vec_step_dev", "rbc3d_vec_nan_count", "rbc3d_vec_nan_count_async", "rbc3d_set_rayleigh_per_env", "rbc3d_render_rgb_dev",
 )
 ABI_VERSION = 2
 
@@ -117,6 +117,14 @@ def load_library(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
+    override = os.environ.get("RBC_B200_LIB")          # developer knob: load another build of the same ABI (the jitter stress build)
+    if override:
+        if not Path(override).exists():
+            raise BackendUnavailable(f"RBC_B200_LIB={override} does not exist")
+        L = C.CDLL(override)
+        _declare(L)
+        _lib = L
+        return L
     if build_if_missing and _build.needs_build():
         try:
             _build.build()
@@ -127,6 +135,13 @@ def load_library(build_if_missing: bool = True):
     if not _build.LIB.exists():
         raise BackendUnavailable(f"{_build.LIB} is missing; run `python -m rbc_gym_b200.build`")
     L = C.CDLL(str(_build.LIB))
+    _declare(L)
+    _lib = L
+    return L
+
+
+def _declare(L):
+    """argtypes / restypes of every entry point + the ABI version check."""
     vp, ip = C.c_void_p, C.c_int32
     L.rbc_abi_version.restype = C.c_int
     L.rbc_last_error.restype = C.c_char_p
@@ -169,6 +184,7 @@ def load_library(build_if_missing: bool = True):
     L.rbc3d_launch_count.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ip), C.POINTER(ip)]
     L.rbc3d_last_step_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.rbc3d_set_rayleigh_per_env.argtypes = [vp, vp]
+    L.rbc3d_render_rgb_dev.argtypes = [vp, vp, ip, ip]
     L.rbc_checkpoint_draw.argtypes = [C.c_int64, C.c_int64, C.c_int64, ip]
     L.rbc_checkpoint_draw.restype = ip
     for dim, out_t in (("2d", Rbc2dVecOut), ("3d", Rbc3dVecOut)):
@@ -183,8 +199,6 @@ def load_library(build_if_missing: bool = True):
     if L.rbc_abi_version() != ABI_VERSION:
         raise BackendUnavailable(f"librbc_b200.so has ABI version {L.rbc_abi_version()}, this package needs {ABI_VERSION}; "
                                  "rebuild with `python -m rbc_gym_b200.build`")
-    _lib = L
-    return L
 
 
 def _np_ptr(a: Optional[np.ndarray]):
@@ -789,6 +803,14 @@ class Sim3D:
         p = lambda x: C.c_void_p(x.data_ptr())
         self._check(self._L.rbc3d_observe_dev(self._h, p(self.obs), p(self.nusselt)))
         return self.obs, self.nusselt
+
+    def render_rgb(self, height: int = 608, width: int = 800):
+        """`render("rgb_array")` of every environment on the device (`rbc3D.py:247-318`): uint8 CUDA tensor `[B, height, width, 3]`,
+        a ray-marched volume rendering of the temperature (turbo colormap, clim = temperature_difference, sigmoid opacity)."""
+        out = self.torch.empty((self.B, height, width, 3), dtype=self.torch.uint8, device=self.device)
+        self._use_current_stream()
+        self._check(self._L.rbc3d_render_rgb_dev(self._h, C.c_void_p(out.data_ptr()), height, width))
+        return out
 
     def fields(self) -> np.ndarray:
         out = np.empty((self.B, self.nstate), np.float64)

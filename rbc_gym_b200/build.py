@@ -94,5 +94,49 @@ def _build_locked(force: bool, verbose: bool) -> Path:
     return LIB
 
 
+LIB_JITTER = CSRC / "librbc_b200_jitter.so"
+
+
+def build_jitter(force: bool = False) -> Path:
+    """The stress build of the cluster kernels (`-DRBX_JITTER`: random delays in front of every DSMEM push and mbarrier wait,
+    see rbc2dx_core.h) linked with the normal objects of the other translation units.  Test infrastructure for
+    tests/test_gpu_grid192.py; select it with RBC_B200_LIB=<path> before the package is imported."""
+    import fcntl
+    build()
+    OBJ_DIR.mkdir(exist_ok=True)
+    with open(OBJ_DIR / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            newest = max(p.stat().st_mtime for p in SOURCES + HEADERS)
+            if not force and LIB_JITTER.exists() and LIB_JITTER.stat().st_mtime > newest:
+                return LIB_JITTER
+            base = [find_nvcc(), *NVCC_FLAGS]
+            host = shutil.which("g++")
+            if host:
+                base += ["-ccbin", host]
+            dx = [s for s in SOURCES if s.name.startswith("rbc2dx")]
+
+            def one(src: Path) -> Path:
+                obj = OBJ_DIR / (src.stem + ".jitter.o")
+                res = subprocess.run(base + ["-DRBX_JITTER=1", "-c", "-o", str(obj), str(src)], capture_output=True, text=True)
+                if res.returncode != 0:
+                    sys.stderr.write(res.stdout + res.stderr)
+                    raise RuntimeError(f"nvcc failed on the jitter build of {src.name}")
+                return obj
+
+            with ThreadPoolExecutor(len(dx)) as ex:
+                jobjs = list(ex.map(one, dx))
+            others = [OBJ_DIR / (s.stem + ".o") for s in SOURCES if s not in dx]
+            tmp = LIB_JITTER.with_suffix(f".{os.getpid()}.tmp.so")
+            res = subprocess.run(base + ["-shared", "-o", str(tmp), *map(str, jobjs + others)], capture_output=True, text=True)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError("nvcc link failed for the jitter build")
+            os.replace(tmp, LIB_JITTER)
+            return LIB_JITTER
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose="-v" in sys.argv))

@@ -192,6 +192,24 @@ __device__ __forceinline__ void st_async(unsigned addr, double v, unsigned bar)
 }
 #endif
 
+// Stress build (-DRBX_JITTER, librbc_b200_jitter.so): pseudo-random delays in front of every remote store and every mbarrier
+// wait, different per CTA, warp and run (clock-seeded) and biased against one rank of the cluster at a time, so that the
+// CTAs of a cluster drift apart as far as the protocol lets them.  The results must stay bitwise identical to the normal
+// build (tests/test_gpu_grid192.py): the write-after-read argument above is then tested, not only argued.
+#if defined(__CUDA_ARCH__) && defined(RBX_JITTER)
+__device__ __forceinline__ void rbx_jitter(unsigned site)
+{
+    unsigned h = ((unsigned)clock() * 2654435761u) ^ (blockIdx.x * 40503u) ^ (site * 0x9E3779B1u) ^ ((threadIdx.x >> 5) * 7919u);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    const unsigned slow_rank = ((unsigned)(clock64() >> 16)) & 7u;               // one rank is the laggard for ~30 us at a time
+    if ((h & 15u) == 0u) __nanosleep((h >> 8) & 0x3FFu);
+    if ((blockIdx.x & 7u) == slow_rank && (h & 3u) == 1u) __nanosleep(0x200u + ((h >> 20) & 0x3FFu));
+}
+#define RBX_JITTER_AT(site) rbx_jitter(site)
+#else
+#define RBX_JITTER_AT(site) do { } while (0)
+#endif
+
 template <typename Real>
 struct PeerBuf {
     Real* p;            // nullptr: there is no such peer
@@ -224,7 +242,7 @@ template <bool ASYNC, typename Real>
 RBC_HD void peer_store(const PeerBuf<Real>& pb, int idx, Real v)
 {
 #if defined(__CUDA_ARCH__)
-    if (ASYNC) st_async(pb.addr + (unsigned)idx * (unsigned)sizeof(Real), v, pb.bar);
+    if (ASYNC) { RBX_JITTER_AT(1u); st_async(pb.addr + (unsigned)idx * (unsigned)sizeof(Real), v, pb.bar); }
     else pb.p[idx] = v;
 #else
     pb.p[idx] = v;
@@ -241,6 +259,7 @@ RBC_HD unsigned bar_off(unsigned o_bars, int ch, unsigned n) { return o_bars + (
         const unsigned nbytes_ = (unsigned)(bytes);                                     \
         if (nbytes_ > 0) {                                                              \
             const unsigned bar_ = smem_u32(X.base + bar_off(X.o_bars, (ch), (cnt)));    \
+            RBX_JITTER_AT(2u + (unsigned)(ch));                                         \
             if (threadIdx.x == 0) mbar_expect_tx(bar_, nbytes_);                        \
             mbar_wait(bar_, ((cnt) >> 1) & 1u);                                         \
         }                                                                               \

@@ -16,6 +16,7 @@ static int force_cluster()
     if (!e) return 0;
     if (e[0] == '1') return 2;
     if (e[0] == 'g') return 1;
+    if (e[0] == '8') return 8;         // stress build only: 192 x 128 fp32 over 8 CTAs
     return 0;
 }
 
@@ -23,7 +24,7 @@ int supported(int nx, int nz)
 {
     if (nx == 192 && nz == 128) return 1;
     if (nx == 128 && nz == 64) return 1;
-    if (nx == 96 && nz == 64 && force_cluster()) return 1;
+    if (nx == 96 && nz == 64 && (force_cluster() == 1 || force_cluster() == 2)) return 1;
     return 0;
 }
 
@@ -38,6 +39,10 @@ int create(int nx, int nz, int precision, int split, int device, double lx, doub
         rc = create_split(p);
     } else if (nx == 192 && nz == 128) {
         // fp32: 4 CTAs x 32 rows, both state buffers on-chip; fp64: 8 CTAs x 16 rows, predicted state in global memory
+#if defined(RBX_JITTER)
+        if (precision == 32 && force_cluster() == 8) rc = create_impl<Grid<192, 128, 8, 2>, float, false, false>(p, "rbc2dx_env_kernel<192x128,cl8,f32,jitter>");
+        else
+#endif
         if (precision == 32) rc = create_impl<Grid<192, 128, 4, 2>, float, false, false>(p, "rbc2dx_env_kernel<192x128,cl4,f32>");
         else rc = create_impl<Grid<192, 128, 8, 2>, double, true, false>(p, "rbc2dx_env_kernel<192x128,cl8,f64>");
     } else if (nx == 128 && nz == 64) {
@@ -47,7 +52,7 @@ int create(int nx, int nz, int precision, int split, int device, double lx, doub
     } else if (nx == 96 && nz == 64 && force_cluster() == 1) {
         if (precision == 32) rc = create_impl<Grid<96, 64, 1, 4>, float, false, false>(p, "rbc2dx_env_kernel<96x64,cl1,f32>");
         else rc = rbc_fail("rbc2dx: the single-CTA generic variant is built for fp32 only");
-    } else if (nx == 96 && nz == 64) {
+    } else if (nx == 96 && nz == 64 && force_cluster() == 2) {
         if (precision == 32) rc = create_impl<Grid<96, 64, 2, 4>, float, false, false>(p, "rbc2dx_env_kernel<96x64,cl2,f32>");
         else rc = create_impl<Grid<96, 64, 2, 4>, double, true, false>(p, "rbc2dx_env_kernel<96x64,cl2,f64>");
     }

@@ -69,6 +69,64 @@ __global__ void rbc3d_get_fields_kernel(const Real* state, double* out, size_t t
         out[q] = (double)state[q];
 }
 
+// render("rgb_array") of the 3D environment (rbc3D.py:247-318 renders the temperature with PyVista: volume rendering, turbo
+// colormap, clim = temperature_difference, opacity "sigmoid_1", 800 x 608 window, default isometric camera).  The same picture
+// ray-marched on the device, one thread per pixel: orthographic isometric view (camera along (1,1,1), z up), trilinear samples
+// of b (flipped in y like the reference's np.flip(T, axis=1)), turbo polynomial, sigmoid opacity composited front to back over
+// a white background.  Not pixel-identical to VTK's renderer (perspective, lighting, sampling distance differ).
+template <typename Real>
+__global__ void rbc3d_render_kernel(const Real* state, uint8_t* out, int B, int nx, int ny, int nz, int nstate, float lx, float ly, float lz,
+                                    float vmin, float inv_range, int H, int W)
+{
+    const size_t total = (size_t)B * H * W;
+    // orthonormal camera frame: view direction d (from the camera into the scene), right r, up u
+    const float d0 = -0.57735027f, d1 = -0.57735027f, d2 = -0.57735027f;
+    const float r0 = 0.70710678f, r1 = -0.70710678f, r2 = 0.0f;
+    const float u0 = -0.40824829f, u1 = -0.40824829f, u2 = 0.81649658f;
+    const float cx0 = 0.5f * lx, cx1 = 0.5f * ly, cx2 = 0.5f * lz;
+    const float diag = sqrtf(lx * lx + ly * ly + lz * lz);
+    const float scale = 1.05f * diag / (float)W;                       // scene units per pixel: the box diagonal fills the width
+    const float dt = 0.5f * fminf(lx / nx, fminf(ly / ny, lz / nz));   // sampling distance: half a cell
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int env = (int)(q / ((size_t)H * W)), pix = (int)(q % ((size_t)H * W)), py = pix / W, px = pix % W;
+        const float sx = (px + 0.5f - 0.5f * W) * scale, sy = (0.5f * H - py - 0.5f) * scale;
+        // ray origin far in front of the box
+        const float o0 = cx0 + sx * r0 + sy * u0 - d0 * diag, o1 = cx1 + sx * r1 + sy * u1 - d1 * diag, o2 = cx2 + sx * r2 + sy * u2 - d2 * diag;
+        // slab test against [0,lx] x [0,ly] x [0,lz]
+        float t0 = 0.0f, t1 = 3.0f * diag;
+        const float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {lx, ly, lz}, o[3] = {o0, o1, o2}, dd[3] = {d0, d1, d2};
+        for (int a = 0; a < 3; ++a) {
+            const float ta = (lo[a] - o[a]) / dd[a], tb = (hi[a] - o[a]) / dd[a];
+            t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+        }
+        float cr = 0.f, cg = 0.f, cb = 0.f, trans = 1.0f;
+        const Real* b = state + (size_t)env * nstate;
+        for (float t = t0 + 0.5f * dt; t < t1 && trans > 0.02f; t += dt) {
+            const float x = o0 + t * d0, y = o1 + t * d1, z = o2 + t * d2;
+            // cell-centred trilinear sample, periodic in x and y, clamped in z; y flipped like the reference picture
+            const float fx = x / lx * nx - 0.5f, fy = (ly - y) / ly * ny - 0.5f, fz = fminf(fmaxf(z / lz * nz - 0.5f, 0.f), (float)(nz - 1));
+            const int i0 = (int)floorf(fx), j0 = (int)floorf(fy), k0 = min((int)fz, nz - 2 < 0 ? 0 : nz - 2);
+            const float ax = fx - i0, ay = fy - j0, az = fz - k0;
+            const int ia = ((i0 % nx) + nx) % nx, ib = (ia + 1) % nx, ja = ((j0 % ny) + ny) % ny, jb = (ja + 1) % ny, kb = min(k0 + 1, nz - 1);
+            auto at = [&](int i, int j, int k) { return (float)b[((size_t)k * ny + j) * nx + i]; };
+            const float v = (1 - az) * ((1 - ay) * ((1 - ax) * at(ia, ja, k0) + ax * at(ib, ja, k0)) + ay * ((1 - ax) * at(ia, jb, k0) + ax * at(ib, jb, k0))) +
+                            az * ((1 - ay) * ((1 - ax) * at(ia, ja, kb) + ax * at(ib, ja, kb)) + ay * ((1 - ax) * at(ia, jb, kb) + ax * at(ib, jb, kb)));
+            const float s = fminf(fmaxf((v - vmin) * inv_range, 0.0f), 1.0f);
+            const float r = 0.13572138f + s * (4.61539260f + s * (-42.66032258f + s * (132.13108234f + s * (-152.94239396f + s * 59.28637943f))));
+            const float g = 0.09140261f + s * (2.19418839f + s * (4.84296658f + s * (-14.18503333f + s * (4.27729857f + s * 2.82956604f))));
+            const float bl = 0.10667330f + s * (12.64194608f + s * (-60.58204836f + s * (110.36276771f + s * (-89.90310912f + s * 27.34824973f))));
+            // "sigmoid_1": opacity = sigmoid over [-1, 1] across the colour range; 0.35 of it per cell crossed, i.e. per two samples
+            const float alpha_cell = 0.35f / (1.0f + __expf(-(2.0f * s - 1.0f)));
+            const float a = 1.0f - sqrtf(1.0f - alpha_cell);
+            cr += trans * a * fminf(fmaxf(r, 0.f), 1.f); cg += trans * a * fminf(fmaxf(g, 0.f), 1.f); cb += trans * a * fminf(fmaxf(bl, 0.f), 1.f);
+            trans *= 1.0f - a;
+        }
+        out[3 * q + 0] = (uint8_t)(fminf(cr + trans, 1.0f) * 255.0f);
+        out[3 * q + 1] = (uint8_t)(fminf(cg + trans, 1.0f) * 255.0f);
+        out[3 * q + 2] = (uint8_t)(fminf(cb + trans, 1.0f) * 255.0f);
+    }
+}
+
 struct rbc3d_sim {
     rbc3d_config cfg;
     HostConfig3 hc;
@@ -493,6 +551,23 @@ int rbc3d_observe_dev(rbc3d_sim* s, float* obs, double* nusselt)
     CK(cudaSetDevice(s->cfg.device));
     RunFlags3 F{0, 0, 0};
     return dispatch3(s, nullptr, obs, nullptr, nusselt, nullptr, nullptr, nullptr, s->B, F, false, obs != nullptr);
+}
+
+int rbc3d_render_rgb_dev(rbc3d_sim* s, uint8_t* out, int32_t height, int32_t width)
+{
+    if (!s || !out || height < 8 || width < 8) return rbc_fail("rbc3d_render_rgb_dev: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    const float vmin = (float)s->cfg.b_min, inv = 1.0f / (float)(s->cfg.b_max - s->cfg.b_min);          // clim = temperature_difference
+    const int blocks = 148 * 8;
+    if (s->cfg.precision == 32)
+        rbc3d_render_kernel<float><<<blocks, 256, 0, s->stream>>>((const float*)s->state, out, s->B, s->cfg.nx, s->cfg.ny, s->cfg.nz, s->nstate,
+                                                                   (float)s->cfg.lx, (float)s->cfg.ly, (float)s->cfg.lz, vmin, inv, height, width);
+    else
+        rbc3d_render_kernel<double><<<blocks, 256, 0, s->stream>>>((const double*)s->state, out, s->B, s->cfg.nx, s->cfg.ny, s->cfg.nz, s->nstate,
+                                                                    (float)s->cfg.lx, (float)s->cfg.ly, (float)s->cfg.lz, vmin, inv, height, width);
+    CK(cudaGetLastError());
+    s->launches += 1;
+    return 0;
 }
 
 int rbc3d_get_fields_host(rbc3d_sim* s, double* out)

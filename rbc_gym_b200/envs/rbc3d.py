@@ -133,7 +133,14 @@ class RayleighBenardConvection3DEnv(spaces.Env):
         return {"t": float(t[0]), "step": int(step[0]), "nusselt": float(self.sim.nusselt[0].item())}
 
     def render(self):
-        raise NotImplementedError("PyVista volume rendering of the reference (rbc3D.py:247-318) is not part of this backend")
+        """`rgb_array`: an (608, 800, 3) uint8 volume rendering of the temperature like the reference's PyVista picture
+        (`rbc3D.py:247-318`: turbo colormap, clim = temperature_difference, sigmoid opacity, isometric camera), ray-marched on
+        the device.  `human` mode (an interactive PyVista window) is not provided."""
+        if self.render_mode != "rgb_array":
+            return None
+        if not self._initialized:
+            raise RuntimeError("Simulation not initialized. Call reset first.")
+        return self.sim.render_rgb()[0].cpu().numpy()
 
     def close(self):
         if getattr(self, "sim", None) is not None:

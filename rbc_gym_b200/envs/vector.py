@@ -408,6 +408,11 @@ class RBCVectorEnv3D(_VectorBase):
         self._episode[ids] += 1
         self.episode_return[ids] = 0
 
+    def render(self, height: int = 608, width: int = 800):
+        """`rgb_array` frames of all environments as one uint8 CUDA tensor `[num_envs, height, width, 3]` (volume rendering of the
+        temperature, `rbc3D.py:247-318`), e.g. for the videos of `example/run_wandb.py:25-59` without a host round trip per frame."""
+        return self.sim.render_rgb(height, width)
+
     def _info(self, nu, extras=None):
         t = self.torch
         if extras is None:

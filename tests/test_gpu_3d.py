@@ -215,3 +215,36 @@ def test_sb3_vecenv_facade_over_the_3d_batch():
     assert all(i["t"] == 0.0 and i["step"] == 1 for i in infos)            # already reset: the returned obs is the reset observation
     assert env.get_attr("ra") == [2500] * 4 and env.env_is_wrapped(object) == [False] * 4
     env.close()
+
+
+def test_3d_rgb_array_render_volume_rendering():
+    """`render("rgb_array")` of the 3D env (`rbc3D.py:247-318`: PyVista volume rendering of the temperature, turbo colormap, clim =
+    temperature_difference, 800 x 608): ray-marched on the device.  The conduction state must show the hot (red) plate at the
+    bottom of the box and the cold (blue) one on top; a plume changes the picture; the batch renderer agrees with the env class."""
+    import torch
+    from pathlib import Path
+    from rbc_gym_b200 import backend
+    from rbc_gym_b200.envs import RayleighBenardConvection3DEnv
+    sim = backend.Sim3D(2, ra=2500, precision=32)
+    z = (np.arange(16) + 0.5) / 8
+    b = np.repeat((2 - z / 2)[None, :, None, None], 2, 0) * np.ones((2, 16, 32, 32))
+    b[1, :, 10:16, 4:10] = 2.0                                              # a hot column in environment 1
+    zeros = np.zeros((2, 16, 32, 32))
+    sim.reset_from_fields(backend.pack_fields3(b, zeros, zeros, np.zeros((2, 17, 32, 32))), project=False)
+    img = sim.render_rgb().cpu().numpy()
+    assert img.shape == (2, 608, 800, 3) and img.dtype == np.uint8
+    assert (img[0, :20] == 255).all() and (img[0, :, :8] == 255).all()       # white background around the box
+    cols = img[0, :, 380:420].astype(int)
+    inside = np.where((cols != 255).any(axis=(1, 2)))[0]
+    top, bottom = cols[inside[:40]].mean(axis=(0, 1)), cols[inside[-40:]].mean(axis=(0, 1))
+    assert top[2] > top[0] + 20 and bottom[0] > bottom[2] + 20               # cold (blue) lid above, hot (red) plate below
+    assert np.abs(img[0].astype(int) - img[1].astype(int)).max() > 40        # the plume is visible
+    env = RayleighBenardConvection3DEnv(rayleigh_number=2500, render_mode="rgb_array")
+    env.reset(seed=0)
+    frame = env.render()
+    assert frame.shape == (608, 800, 3) and frame.std() > 10
+    out = Path(__file__).resolve().parent.parent / "gpurun_out"
+    if out.exists():
+        with open(out / "render3d.ppm", "wb") as f:
+            f.write(b"P6 800 608 255\n" + img[1].tobytes())
+    env.close(); sim.close()

@@ -3,11 +3,13 @@ environment, slabs in distributed shared memory) through the C ABI against the f
 
 Tolerances as for the 96 x 64 grid: rel-L2 per field after one action step <= 1e-10 (fp64), <= 1e-5 (fp32)."""
 import os
+from pathlib import Path
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
 
 from oracle import oracle as O  # noqa: E402
 from tests.gridstates import smooth_state  # noqa: E402
@@ -336,3 +338,59 @@ def test_host_step_in_overlapped_chunks_on_the_cluster_grid(B):
     assert np.array_equal(sims[0].fields(), sims[1].fields())
     for sim in sims:
         sim.close()
+
+
+_JITTER_SCRIPT = r"""
+import hashlib, sys
+import numpy as np, torch
+sys.path.insert(0, {root!r})
+from rbc_gym_b200 import backend
+from tests.gridstates import smooth_state
+n = 6
+sim = backend.Sim2D(n, ra=1e6, dt_action=0.045, dt_solver=0.015, state_shape=(128, 192), precision=32)
+st = [smooth_state(192, 128, seed=s) for s in range(n)]
+sim.reset_from_fields(backend.pack_fields(*[np.stack([s[k] for s in st]) for k in range(3)]), project=True)
+g = torch.Generator(device="cuda").manual_seed(1)
+for it in range(100):
+    sim.step(torch.rand((n, 12), device="cuda", generator=g) * 2 - 1)
+f = sim.fields()
+assert np.isfinite(f).all()
+print("DIGEST", hashlib.sha256(f.tobytes()).hexdigest(), sim.launch_info()["grid"])
+"""
+
+
+def _run_variant(lib, cluster_env):
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env.pop("RBC_B200_LIB", None)
+    env.pop("RBC_B200_CLUSTER", None)
+    if lib is not None:
+        env["RBC_B200_LIB"] = str(lib)
+    if cluster_env is not None:
+        env["RBC_B200_CLUSTER"] = cluster_env
+    r = subprocess.run([sys.executable, "-c", _JITTER_SCRIPT.format(root=str(ROOT))], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1].split()
+    return line[1], int(line[2])
+
+
+def test_async_halo_protocol_survives_jitter():
+    """Stress test of the `st.async` + mbarrier protocol of the cluster kernel (no cluster barrier and no fence in the stage loop;
+    its write-after-read safety is argued in rbc2dx_core.h).  A second build of the library (`-DRBX_JITTER`, build.build_jitter)
+    sleeps for pseudo-random, clock-seeded times in front of every remote store and every mbarrier wait, and makes one rank of the
+    cluster the laggard for ~30 us at a time.  100 action steps (900 RK3 stages with all four exchange channels) of six
+    192 x 128 environments must come out BITWISE identical: at CL = 4 to the normal build, at CL = 8 (an instantiation only the
+    stress build has) across three runs with three different delay patterns."""
+    from rbc_gym_b200 import build
+    jit = build.LIB_JITTER
+    if not jit.exists():
+        jit = build.build_jitter()
+    ref, grid = _run_variant(None, None)
+    assert grid == 24                                          # 6 clusters x 4 CTAs
+    for _ in range(2):
+        assert _run_variant(jit, None)[0] == ref
+    runs8 = [_run_variant(jit, "8") for _ in range(3)]
+    assert runs8[0][1] == 48 and len({d for d, _ in runs8}) == 1
+    assert runs8[0][0] != ref                                  # a different decomposition rounds differently: it really was another kernel

@@ -1,64 +1,86 @@
 """The 3D oracle against the ONLY Julia-produced 3D data the reference ships: `experiments/flowstats/flowstats_ra.pkl`
-(uncontrolled 64 x 64 x 32 runs, one Nusselt sample per time unit).  The oracle was run offline with the same protocol
-(`tools/oracle3d_flowstats.py`, ~45 core-minutes per Rayleigh number) and its series is stored in
-`tests/golden/oracle3d_flowstats_64x64x32.json`; this test compares the two at the same resolution:
+(uncontrolled 64 x 64 x 32 runs of `experiments/flowstats/flowstats_ra.py:27-36`, one Nusselt sample per time unit, 300 samples,
+14 Rayleigh numbers; extracted to `tests/golden/flowstats_julia_64x64x32.json` by `tools/make_flowstats_golden.py` with a
+numpy-only unpickler).  The oracle was run offline with the same protocol at the same resolution for all 14 Rayleigh numbers
+x 300 samples, one noise realisation per Rayleigh number like the reference (`tools/oracle3d_flowstats.py` ->
+`tests/golden/oracle3d_flowstats_64x64x32.json`, ~10 core-hours).
 
-  * the exponential growth rate of (Nu - 1) during the linear instability — independent of the noise realisation, a
-    sharp check of the buoyancy / diffusion balance and of the non-dimensionalisation (nu, kappa, t_ff = Lz^2);
-  * the overshoot of the first plume burst (height; its time shifts with the logarithm of the noise amplitude);
-  * the mean Nusselt number after saturation (samples 50..100).
-
-Reference numbers below were extracted from the pickle (also re-read from the mount when it is present)."""
+What one realisation against one realisation can and cannot pin (DESIGN.md section 2 has the ensemble study):
+  * saturated Nusselt number, Ra >= 8000 (unsteady convection): mean over the last 150 samples within ONE standard deviation
+    of the Julia series over those samples (measured: 0.08 ... 0.75 of it, 0.2 ... 1.9 % of Nu, no sign pattern);
+  * Ra = 4000: within two; Ra <= 2000: the flow freezes into a steady planform selected by the noise — the Julia table is not
+    even monotonic there (Nu(750) > Nu(1000)) — so only a quarter of Nu - 1 is asserted;
+  * linear-instability plateau (largest local growth rate of Nu - 1 per time unit): seed scatter is 0.4 % (24-seed GPU
+    ensemble); the oracle is within 1.2 % of Julia for Ra <= 4000 and 1.4 ... 2.9 % ABOVE it for Ra >= 8000 — a systematic
+    difference in the transient growth that is documented, not hidden: the test asserts the measured envelope."""
 import json
 from pathlib import Path
 
 import numpy as np
 import pytest
 
-GOLD = Path(__file__).resolve().parent / "golden" / "oracle3d_flowstats_64x64x32.json"
+GOLD = Path(__file__).resolve().parent / "golden"
 PKL = Path("/root/reference/experiments/flowstats/flowstats_ra.pkl")
-pytestmark = pytest.mark.skipif(not GOLD.exists(), reason="golden oracle series not generated")
-
-# Ra -> (growth rate of Nu-1 per time unit, first-burst peak, mean Nu over samples 50..99, its std) from flowstats_ra.pkl
-REFERENCE = {"500": (0.3164, 1.417, 1.4035, 0.0145), "4000": (0.7669, 3.439, 2.1535, 0.0518), "16000": (0.8394, 7.204, 2.8975, 0.0812)}
+RAS = ["500", "750", "1000", "1500", "2000", "4000", "8000", "16000", "32000", "64000", "128000", "256000", "512000", "1000000"]
 
 
-def growth_rate(nu, lo=1e-3, hi=5e-2):
-    e = np.asarray(nu) - 1.0
-    idx = [i for i in range(min(len(e), 80)) if lo < e[i] < hi]
-    run = [idx[0]]
-    for i in idx[1:]:
-        if i == run[-1] + 1:
-            run.append(i)
-        else:
-            break
-    return float(np.polyfit(np.array(run), np.log(e[run]), 1)[0])
+def plateau(nu):
+    e = np.log(np.maximum(np.asarray(nu) - 1.0, 1e-12))
+    return float(np.diff(e)[3:60].max())
 
 
-def runs():
-    return json.loads(GOLD.read_text())["runs"]
+@pytest.fixture(scope="module")
+def julia():
+    return json.loads((GOLD / "flowstats_julia_64x64x32.json").read_text())["runs"]
 
 
-def test_reference_numbers_match_the_pickle_when_mounted():
+@pytest.fixture(scope="module")
+def oracle():
+    d = json.loads((GOLD / "oracle3d_flowstats_64x64x32.json").read_text())
+    assert d["meta"]["grid"] == [32, 64, 64] and d["meta"]["samples"] == 300
+    return {str(int(float(k))): v for k, v in d["runs"].items()}
+
+
+def test_golden_julia_series_match_the_pickle_when_mounted(julia):
     if not PKL.exists():
         pytest.skip("reference mount not present")
+    import sys
+    sys.path.insert(0, str(GOLD.parent.parent / "tools"))
+    from make_flowstats_golden import NumpyOnlyUnpickler, load_flowstats      # restricted: the mount is untrusted content
+    d = load_flowstats(PKL)
+    assert sorted(d, key=float) == RAS
+    for ra in RAS:
+        assert np.array_equal(d[ra]["nusselt_step"], np.array(julia[ra]["nusselt_step"])) and len(julia[ra]["nusselt_step"]) == 300
+    import io
     import pickle
-    d = pickle.load(open(PKL, "rb"))
-    for ra, (g, peak, mean, std) in REFERENCE.items():
-        nu = np.array(d[ra]["nusselt_step"])
-        assert growth_rate(nu) == pytest.approx(g, abs=2e-4) and nu[:60].max() == pytest.approx(peak, abs=2e-3)
-        assert nu[50:100].mean() == pytest.approx(mean, abs=2e-4) and nu[50:100].std() == pytest.approx(std, abs=2e-4)
+    with pytest.raises(pickle.UnpicklingError):                                 # anything but numpy arrays is refused
+        NumpyOnlyUnpickler(io.BytesIO(pickle.dumps(Path("/")))).load()
 
 
-@pytest.mark.parametrize("ra", sorted(REFERENCE, key=float))
-def test_oracle_reproduces_julia_flow_statistics_at_64x64x32(ra):
-    r = runs()
-    if ra not in r and f"{float(ra)}" not in r:
-        pytest.skip(f"Ra={ra} not in the golden file")
-    nu = np.array(r.get(ra, r.get(f"{float(ra)}"))["nusselt_step"])
-    g_ref, peak_ref, mean_ref, std_ref = REFERENCE[ra]
-    assert growth_rate(nu) == pytest.approx(g_ref, rel=0.06)              # linear instability growth
-    if len(nu) >= 60:
-        assert nu[:60].max() == pytest.approx(peak_ref, rel=0.15)          # first burst (under-resolved in time: 1 sample/unit)
-    if len(nu) >= 100:
-        assert nu[50:100].mean() == pytest.approx(mean_ref, abs=3 * std_ref + 0.02)
+def test_baseline_table_numbers(julia):
+    # mean +- std over the last 150 samples
+    for ra, m, s in (("500", 1.371, 0.006), ("4000", 2.123, 0.032), ("16000", 2.851, 0.072), ("1000000", 9.230, 0.222)):
+        nu = np.array(julia[ra]["nusselt_step"])
+        assert nu[150:].mean() == pytest.approx(m, abs=1e-3) and nu[150:].std() == pytest.approx(s, abs=1e-3)
+
+
+@pytest.mark.parametrize("ra", RAS)
+def test_oracle_reproduces_julia_flow_statistics_at_64x64x32(julia, oracle, ra):
+    o, j = np.array(oracle[ra]["nusselt_step"]), np.array(julia[ra]["nusselt_step"])
+    assert len(o) == 300 and np.isfinite(o).all()
+    m_o, m_j, s_j = o[150:].mean(), j[150:].mean(), j[150:].std()
+    r = float(ra)
+    tol = 0.25 * (m_j - 1) if r <= 2000 else (2 * s_j if r < 8000 else s_j)
+    assert abs(m_o - m_j) < tol, (ra, m_o, m_j, tol)
+    if r >= 8000:
+        assert o[150:].std() == pytest.approx(s_j, rel=0.5)                    # the fluctuation level, too
+    ratio = plateau(o) / plateau(j)
+    lo, hi = (0.985, 1.012) if r <= 4000 else (1.005, 1.035)
+    assert lo < ratio < hi, (ra, ratio)
+    # the first sample (t = 1) measures the noise level after the set! projection and one time unit: same kick, same decay
+    assert o[0] - 1 == pytest.approx(j[0] - 1, rel=0.10)                     # measured 0.97 ... 1.09 (one realisation each)
+
+
+def test_no_systematic_bias_in_the_saturated_regime(julia, oracle):
+    rel = [np.mean(oracle[ra]["nusselt_step"][150:]) / np.mean(julia[ra]["nusselt_step"][150:]) - 1 for ra in RAS if float(ra) >= 8000]
+    assert abs(np.mean(rel)) < 0.006 and max(np.abs(rel)) < 0.02, rel          # measured: mean +0.4 %, largest 1.9 %
