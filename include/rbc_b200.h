@@ -182,6 +182,15 @@ int rbc2d_vec_nan_count(rbc2d_sim* sim, int32_t clear, int64_t* count);
  * has passed this point (poll it one step late for a deferred, sync-free NaN check). */
 int rbc2d_vec_nan_count_async(rbc2d_sim* sim, int32_t* count_host_pinned);
 
+/* CFL guard of the grids beyond 96 x 64 (cluster kernels).  The reference steps with a fixed dt_solver; on the 192 x 128 grid a
+ * flow started from noise at Ra = 1e6 overshoots to CFL ~ 1.6 in its first plume burst, where the RK3 / upwind scheme is
+ * linearly unstable: fp64 rides it out, fp32 loses about one environment in a thousand to NaNs.  With the guard an environment
+ * whose max(|w| dt/dz, |u| dt/dx) exceeds `limit` at the start of an RK3 step takes that step as ceil(CFL) equal parts; all other
+ * environments are untouched bit for bit.  Default: limit 1.4 in the fp32 mode, off (0) in the fp64 validation mode.
+ * rbc2d_get_cfl_events_host: extra RK3 steps inserted per environment since creation, [B] int32. */
+int rbc2d_set_cfl_guard(rbc2d_sim* sim, double limit);
+int rbc2d_get_cfl_events_host(rbc2d_sim* sim, int32_t* out_host);
+
 /* Enable/disable the fused wrappers (NULL = all off).  Takes effect from the next step/observe. */
 int rbc2d_set_wrappers(rbc2d_sim* sim, const rbc2d_wrappers* w);
 /* info["cell_dist"] of the last step (rbc_reward_shaping.py:61-66), [B] float64; computed only while

@@ -97,7 +97,7 @@ ABI_SYMBOLS = (
     "rbc3d_observe_dev", "rbc3d_get_fields_host", "rbc3d_get_info_host", "rbc3d_launch_count", "rbc3d_last_step_kernel_ms",
     "rbc_checkpoint_draw", "rbc2d_set_autoreset", "rbc2d_vec_reset_dev", "rbc2d_vec_mark_reset_dev", "rbc2d_vec_step_dev", "rbc2d_vec_step_host",
     "rbc2d_vec_nan_count", "rbc2d_vec_nan_count_async", "rbc3d_set_autoreset", "rbc3d_vec_reset_dev", "rbc3d_vec_mark_reset_dev",
-    "rbc3d_vec_step_dev", "rbc3d_vec_nan_count", "rbc3d_vec_nan_count_async", "rbc3d_set_rayleigh_per_env", "rbc3d_render_rgb_dev",
+    "rbc3d_vec_step_dev", "rbc3d_vec_nan_count", "rbc3d_vec_nan_count_async", "rbc3d_set_rayleigh_per_env", "rbc3d_render_rgb_dev", "rbc2d_set_cfl_guard", "rbc2d_get_cfl_events_host",
 )
 ABI_VERSION = 2
 
@@ -165,6 +165,8 @@ def _declare(L):
     L.rbc2d_set_wrappers.argtypes = [vp, C.POINTER(Rbc2dWrappers)]
     L.rbc2d_get_cell_dist_host.argtypes = [vp, vp]
     L.rbc2d_render_rgb_dev.argtypes = [vp, vp]
+    L.rbc2d_set_cfl_guard.argtypes = [vp, C.c_double]
+    L.rbc2d_get_cfl_events_host.argtypes = [vp, vp]
     L.rbc2d_launch_count.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ip), C.POINTER(ip)]
     L.rbc2d_last_step_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.rbc2d_step_kernel_ms_history.argtypes = [vp, C.POINTER(C.c_float), ip]
@@ -502,6 +504,17 @@ class Sim2D:
         w.shaping_weight = float(shaping_weight or 0.0)
         self._check(self._L.rbc2d_set_wrappers(self._h, C.byref(w)))
         self.wrappers = w
+
+    def set_cfl_guard(self, limit: float):
+        """CFL guard of the grids beyond 96 x 64 (`rbc2d_set_cfl_guard`): RK3 steps above `limit` are split; 0 switches it off."""
+        self._check(self._L.rbc2d_set_cfl_guard(self._h, float(limit)))
+
+    def cfl_events(self) -> np.ndarray:
+        """Extra RK3 steps the CFL guard inserted per environment since creation, `[B]` int32."""
+        out = np.zeros(self.B, np.int32)
+        self._use_current_stream()
+        self._check(self._L.rbc2d_get_cfl_events_host(self._h, _np_ptr(out)))
+        return out
 
     def cell_dist(self) -> np.ndarray:
         """`info["cell_dist"]` of the last step (`rbc_reward_shaping.py:61-66`), `[B]` float64."""

@@ -96,6 +96,9 @@ struct Consts {
     double reward_scale;
     int wrap_shaping;            // rbc_reward_shaping.py:53-140: (1-w) r + w (pi - cd)/pi
     double shaping_weight;
+    // CFL guard of the cluster kernels (fp32 throughput mode): an RK3 step whose max(|w| dt/dz, |u| dt/dx) exceeds this limit is
+    // taken as ceil(CFL) shorter steps by that environment; 0 = off (the reference's fixed dt, always in the fp64 mode)
+    Real cfl_limit;
 };
 
 // tables in global memory, staged to shared memory by the CTA
@@ -156,6 +159,7 @@ struct EnvIO {
     Real* pressure;           // [B][2][NZ][NX] (pHY', pNHS) or nullptr
     double* cell_dist;        // [B] Benard-cell distance (info["cell_dist"]) or nullptr
     VecIO vec;                // fused auto-reset (off by default)
+    int* cfl_events = nullptr;   // [B] extra RK3 steps the CFL guard inserted so far (cluster kernels), or nullptr
 };
 
 // everything one CTA needs while it owns an environment
@@ -1260,6 +1264,7 @@ inline int substep_schedule(double dt_action, double dt_solver, double* dt_last)
 struct HostConfig {
     double ra, pr, lx, lz, b_top, heater_limit, dt_action, dt_solver, episode_length;
     int heaters, obs_nz, obs_nx, channels;
+    double cfl_limit;            // CFL guard (cluster kernels); 0 = off.  Last member: brace-initialisers that stop before it leave it 0
 };
 // optional fused wrappers (all off by default)
 struct HostWrappers {
@@ -1289,6 +1294,7 @@ inline Consts<Real> make_consts(const HostConfig& h, const HostWrappers& w = Hos
     for (int c = 0; c < 4; ++c) { C.obs_lo[c] = w.obs_lo[c]; C.obs_hi[c] = w.obs_hi[c]; }
     C.wrap_reward = w.normalize_reward; C.reward_scale = w.reward_scale;
     C.wrap_shaping = w.shaping; C.shaping_weight = w.shaping_weight;
+    C.cfl_limit = Real(0);       // the dedicated 96 x 64 kernel runs the reference's fixed dt (CFL <= 1.2 over the shipped Ra range)
     return C;
 }
 // mode index of spectral word t of a row after fft_untangle

@@ -194,6 +194,7 @@ struct rbc2d_sim {
     long long* episode = nullptr;
     double* ep_return = nullptr;
     int* nan_count = nullptr;
+    int* cfl_events = nullptr;       // [B] extra RK3 steps inserted by the CFL guard of the cluster kernels
     float* final_obs = nullptr;      // device staging of the final_* outputs of rbc2d_vec_step_host (allocated on first use)
     double* final_scalars = nullptr;
 };
@@ -296,6 +297,7 @@ static int dispatch_env(rbc2d_sim* s, const float* actions, float* obs, float* r
         io.cell_dist = s->wr.shaping ? s->cell_dist : nullptr;
         io.pressure = s->pressure;
         io.vec = vec;
+        io.cfl_events = s->cfl_events;
         if (n <= 0) return 0;
         const int slot = (int)(s->timed_launches % rbc2d_sim::kRing);
         if (time_it) CK(cudaEventRecord(s->ev0[slot], s->stream));
@@ -367,7 +369,9 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
     s->real_size = cfg->precision == 32 ? 4 : 8;
     s->nx = cfg->nx; s->nz = cfg->nz; s->ncell = cfg->nx * cfg->nz; s->nwf = cfg->nx * (cfg->nz + 1); s->nstate = 2 * s->ncell + s->nwf;
     s->hc = HostConfig{cfg->ra, cfg->pr, 2.0 * 3.14159265358979323846, 2.0, 1.0, cfg->heater_limit, cfg->dt_action,
-                       cfg->dt_solver, cfg->episode_length, cfg->heaters, cfg->obs_nz, cfg->obs_nx, s->channels};
+                       cfg->dt_solver, cfg->episode_length, cfg->heaters, cfg->obs_nz, cfg->obs_nx, s->channels,
+                       // CFL guard: on in the fp32 throughput mode of the cluster kernels, off in the fp64 validation mode
+                       (!dedicated && cfg->precision == 32) ? 1.4 : 0.0};
     int rc;
     const bool f32 = cfg->precision == 32, split = cfg->pressure != 0;
     if (dedicated) {
@@ -416,6 +420,7 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
     ALLOC(s->episode, B * sizeof(long long));
     ALLOC(s->ep_return, B * sizeof(double));
     ALLOC(s->nan_count, sizeof(int));
+    ALLOC(s->cfl_events, B * sizeof(int));
 #undef ALLOC
     for (int i = 0; i < rbc2d_sim::kRing; ++i)
         if (cudaEventCreate(&s->ev0[i]) != cudaSuccess || cudaEventCreate(&s->ev1[i]) != cudaSuccess) {
@@ -432,7 +437,7 @@ int rbc2d_destroy(rbc2d_sim* s)
     cudaSetDevice(s->cfg.device);
     void* ptrs[] = {s->state, s->gm, s->nxt, s->pressure, s->tinv, s->tw48, s->tw96, s->bank, s->t, s->nu_s, s->nu_o,
                     s->step, s->trunc, s->nan, s->obs, s->reward, s->actions, s->cell_dist, s->pending, s->episode, s->ep_return,
-                    s->nan_count, s->final_obs, s->final_scalars};
+                    s->nan_count, s->final_obs, s->final_scalars, s->cfl_events};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < rbc2d_sim::kRing; ++i) {
         if (s->ev0[i]) cudaEventDestroy(s->ev0[i]);
@@ -743,6 +748,23 @@ int rbc2d_vec_nan_count_async(rbc2d_sim* s, int32_t* count_host)
     if (!s || !count_host) return fail("rbc2d_vec_nan_count_async: bad argument");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaMemcpyAsync(count_host, s->nan_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+
+int rbc2d_set_cfl_guard(rbc2d_sim* s, double limit)
+{
+    if (!s || !(limit >= 0)) return fail("rbc2d_set_cfl_guard: bad argument");
+    if (limit > 0 && !s->plan) return fail("rbc2d_set_cfl_guard: the dedicated 96 x 64 kernel has no CFL guard (dt_solver 0.03 keeps CFL <= 1.2 there)");
+    s->hc.cfl_limit = limit;
+    return 0;
+}
+
+int rbc2d_get_cfl_events_host(rbc2d_sim* s, int32_t* out)
+{
+    if (!s || !out) return fail("rbc2d_get_cfl_events_host: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpyAsync(out, s->cfl_events, (size_t)s->B * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
     return 0;
 }
 

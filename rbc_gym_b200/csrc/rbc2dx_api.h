@@ -24,6 +24,7 @@ struct IoRaw {
     double* cell_dist;
     void* pressure;      // [B][2][NZ][NX] in the plan's precision (split mode), else nullptr
     rbc2d::VecIO vec;    // fused vector-env semantics (off by default)
+    int* cfl_events = nullptr;   // [B] extra RK3 steps inserted by the CFL guard
 };
 
 // 1 when a cluster kernel is registered for this grid.  `force_cluster` (env RBC_B200_CLUSTER=1) also routes the

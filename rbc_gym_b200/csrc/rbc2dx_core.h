@@ -1009,6 +1009,67 @@ RBC_HD void hydrostatic(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_s
     S.n[CH_P] += 1;
 }
 
+// ------------------------------------------------------------------------------------------
+// CFL guard (fp32 throughput mode).  Above CFL ~ 1.5 the RK3 / 5th-order-upwind scheme is linearly unstable; the first plume
+// burst of a high-Ra flow started from noise gets there, fp64 rides it out on its 1e-9 smaller round-off
+// seed, fp32 leaves ~1 environment in 1000 with NaNs.  At the top of every RK3 step the cluster measures
+// max(|w| dt/dz, |u| dt/dx) of the environment (own rows, warp maxima, one DSMEM exchange behind a cluster barrier — 3 barriers
+// per RK3 step against ~25 k cycles per stage) and, above the limit, takes the step as ceil(CFL) equal parts.  Every CTA computes
+// the same number, so the mbarrier channel counts stay in step.  Environments below the limit — all developed flows — are
+// untouched bit for bit.  Returns the number of parts (>= 1).
+// ------------------------------------------------------------------------------------------
+template <typename G, typename Real>
+RBC_HD int cfl_parts(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, unsigned o_cur, int my_rank, Real dt, int sub)
+{
+    (void)my_rank;
+    constexpr int NX = G::NX, NT = G::NT, SX = G::SX, H = G::HALO;
+    const int slot = 13 + (sub & 1);                       // two cfin slots alternate: a slow peer may still be reading the other one
+    RBX_PHASE_L(G, if (tid == 0) reinterpret_cast<double*>(smb + X.o_cfin)[slot] = 0.0;)
+    RBX_PHASE_C(G,
+        const Real* p = RBX_PTR(o_cur);
+        const int i = tid % NX; const int s = tid / NX;
+        Real m = Real(0);
+        for (int r = 0; r < G::RS; ++r) {
+            const int lr = s * G::RS + r + H;
+            const Real aw = fabs(p[G::OFF_W + lr * SX + i]) * C.idz; const Real au = fabs(p[G::OFF_U + lr * SX + i]) * C.idx;
+            m = aw > m ? aw : m; m = au > m ? au : m;      // a NaN never wins: the environment is lost anyway and reported as such
+        }
+        double* cell = reinterpret_cast<double*>(smb + X.o_cfin) + slot;
+#if defined(__CUDA_ARCH__)
+        // non-negative floats order like their bit patterns
+        unsigned bits = __float_as_uint((float)m);
+        bits = __reduce_max_sync(0xffffffffu, bits);
+        if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned*>(cell), bits);
+#else
+        if ((double)m > *cell) *cell = (double)m;
+#endif
+    )
+    double mx = 0.0;
+#if defined(__CUDA_ARCH__)
+    {
+        double* mine = reinterpret_cast<double*>(X.base + X.o_cfin) + slot;
+        for (int j = 0; j < G::CL; ++j) {
+            const unsigned b = *reinterpret_cast<const unsigned*>((j == my_rank) ? mine : peer_ptr(X.base, X.arena_stride, mine, my_rank, j));
+            const double v = (double)__uint_as_float(b);
+            mx = v > mx ? v : mx;
+        }
+    }
+#else
+    for (int j = 0; j < G::CL; ++j) {
+        const double v = reinterpret_cast<const double*>(X.base + j * X.arena_stride + X.o_cfin)[slot];
+        mx = v > mx ? v : mx;
+    }
+    (void)NT;
+#endif
+    const double cfl = mx * (double)dt;
+    int parts = 1;
+    if (cfl > (double)C.cfl_limit) { parts = (int)ceil(cfl); parts = parts < 2 ? 2 : (parts > 8 ? 8 : parts); }
+    if (parts > 1 && io.cfl_events != nullptr) {
+        RBX_PHASE_L(G, if (rank == 0 && tid == 0) io.cfl_events[env] += parts - 1;)
+    }
+    return parts;
+}
+
 // sum over the CTAs of the cluster of entry `idx` of their cfin blocks (valid after the cluster barrier that follows the
 // phase writing them); every thread of every CTA gets the same value
 template <typename G, typename Real>
@@ -1270,8 +1331,11 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
     Real last_dtau = Real(1);                              // set! projects with dtau = 1
     if (project_first) project<G, Real, NXT_GLOBAL, SPLIT>(C, X, o_cur, o_nxt, my_rank, S, false);
     for (int sub = 0; sub < nsub; ++sub) {
-        const Real dt = (sub == nsub - 1) ? C.dt_last : C.dt_full;
-        for (int stage = 0; stage < 3; ++stage) {
+        const Real dt_sub = (sub == nsub - 1) ? C.dt_last : C.dt_full;
+        const int parts = (C.cfl_limit > Real(0)) ? cfl_parts<G>(C, io, X, env, o_cur, my_rank, dt_sub, sub) : 1;
+        const Real dt = parts > 1 ? dt_sub / Real(parts) : dt_sub;
+        for (int ps = 0; ps < 3 * parts; ++ps) {
+            const int stage = ps % 3;
             const int in_slab = (stage & 1) ? 0 : 1, out_slab = 1 - in_slab;
             if (SPLIT) hydrostatic<G, Real, NXT_GLOBAL>(C, X, o_cur, my_rank, S);
             RBX_PHASE_L(G, phase_edge_fluxes<G>(tid, rank, RBX_PTR(o_cur), RBX_PTR(X.o_edge));)
@@ -1342,6 +1406,7 @@ inline Consts<Real> make_consts(const HostConfig& h, const HostWrappers& w = Hos
     for (int c = 0; c < 4; ++c) { C.obs_lo[c] = w.obs_lo[c]; C.obs_hi[c] = w.obs_hi[c]; }
     C.wrap_reward = w.normalize_reward; C.reward_scale = w.reward_scale;
     C.wrap_shaping = w.shaping; C.shaping_weight = w.shaping_weight;
+    C.cfl_limit = (Real)h.cfl_limit;
     return C;
 }
 

@@ -82,6 +82,7 @@ static int launch_impl(Plan* p, const rbc2d::HostConfig& hc, const rbc2d::HostWr
     io.nu_obs = r.nu_obs; io.t = r.t; io.step_count = r.step_count; io.truncated = r.truncated; io.nan_flag = r.nan_flag;
     io.pressure = SPLIT ? (Real*)r.pressure : nullptr; io.cell_dist = r.cell_dist;
     io.vec = r.vec;
+    io.cfl_events = r.cfl_events;
     CtxX<Real> X;
     L::fill(X);
     X.base = nullptr; X.arena_stride = 0;

@@ -13,7 +13,7 @@ _SO = _HERE / "libemu_rbc2d.so"
 
 class HostConfig(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("ra", "pr", "lx", "lz", "b_top", "heater_limit", "dt_action", "dt_solver", "episode_length")] + \
-               [(n, C.c_int) for n in ("heaters", "obs_nz", "obs_nx", "channels")]
+               [(n, C.c_int) for n in ("heaters", "obs_nz", "obs_nx", "channels")] + [("cfl_limit", C.c_double)]
 
 
 class HostWrappers(C.Structure):
@@ -201,7 +201,7 @@ def unpack(st):
 
 
 def stepx(state, actions, ra, dt_action, nx=96, nz=64, cl=1, precision=64, nxt_global=False, dt_solver=0.03, obs=(8, 48), heaters=12,
-          heater_limit=0.75, episode_length=300.0, t0=None, wrappers=None, project_first=False, nsub=-1, split=False):
+          heater_limit=0.75, episode_length=300.0, t0=None, wrappers=None, project_first=False, nsub=-1, split=False, cfl_limit=0.0):
     """One action step through the emulated CLUSTER kernel (rbc2dx_core.h): grid nx x nz split over `cl` CTAs.
     state: [B, 2*nx*nz + nx*(nz+1)] (b,u,w flattened).  split=True: pressure-split mode with the two pressure channels."""
     lib = C.CDLL(str(build_x()))
@@ -209,7 +209,7 @@ def stepx(state, actions, ra, dt_action, nx=96, nz=64, cl=1, precision=64, nxt_g
     dt = np.float64 if precision == 64 else np.float32
     st = np.array(state, dtype=dt, order="C")
     ch = 5 if split else 3
-    h = HostConfig(ra, 0.7, 2 * math.pi, 2.0, 1.0, heater_limit, dt_action, dt_solver, episode_length, heaters, obs[0], obs[1], ch)
+    h = HostConfig(ra, 0.7, 2 * math.pi, 2.0, 1.0, heater_limit, dt_action, dt_solver, episode_length, heaters, obs[0], obs[1], ch, cfl_limit)
     a = np.ascontiguousarray(actions, dtype=np.float32)
     ob = np.zeros((B, ch, obs[0], obs[1]), np.float32)
     rew = np.zeros(B, np.float32)

@@ -394,3 +394,49 @@ def test_async_halo_protocol_survives_jitter():
     runs8 = [_run_variant(jit, "8") for _ in range(3)]
     assert runs8[0][1] == 48 and len({d for d, _ in runs8}) == 1
     assert runs8[0][0] != ref                                  # a different decomposition rounds differently: it really was another kernel
+
+
+def test_cfl_guard_makes_fp32_noise_initialisation_robust_on_config3():
+    """Config 3's own reset path in the throughput mode: 4096 environments, 192 x 128, Ra = 1e6, fp32, the reference's noise
+    initialisation (kick 0.01), 60 action steps of dt = 1 with zero action.  The first plume burst overshoots to CFL ~ 1.6, where the
+    scheme is linearly unstable: without the guard about one fp32 environment in a thousand ends with NaNs (DESIGN.md section 7);
+    with it (default in fp32) none may, the guard must have acted on a minority of RK3 steps only, and the Nusselt statistics must
+    match an fp64 ensemble run without any guard (the reference's fixed time step)."""
+    import torch
+    from rbc_gym_b200 import backend
+    n = 4096
+    sim = backend.Sim2D(n, ra=RA, dt_action=1.0, dt_solver=DTS, state_shape=(NZ, NX), precision=32)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    for lo in range(0, n, 1024):                                         # noise fields in slices: 1024 x 73 920 doubles at a time
+        sim.noise_reset(torch.arange(lo, lo + 1024, dtype=torch.int32), kick=0.01, generator=gen)
+    zero = torch.zeros((n, 12), device="cuda")
+    nu32 = []
+    for step in range(60):
+        _, _, nus, _, _, nan = sim.step(zero)
+        nu32.append(nus.clone())
+    assert int(nan.sum()) == 0
+    nu32 = torch.stack(nu32).cpu().numpy()
+    assert np.isfinite(nu32).all()
+    ev = sim.cfl_events()
+    rk3_steps = 60 * sim.nsub
+    assert ev.max() > 0 and ev.mean() < 0.05 * rk3_steps, (ev.max(), ev.mean())      # it acted, and only during the burst
+    sim.close()
+    m = 256
+    ref = backend.Sim2D(m, ra=RA, dt_action=1.0, dt_solver=DTS, state_shape=(NZ, NX), precision=64)
+    ref.noise_reset(kick=0.01, generator=torch.Generator(device="cuda").manual_seed(12))
+    zero = torch.zeros((m, 12), device="cuda")
+    nu64 = []
+    for step in range(60):
+        _, _, nus, _, _, nan = ref.step(zero)
+        nu64.append(nus.clone())
+    assert int(nan.sum()) == 0 and ref.cfl_events().max() == 0              # the validation mode keeps the reference's fixed dt
+    nu64 = torch.stack(nu64).cpu().numpy()
+    ref.close()
+    # developed phase (steps 40..59): ensemble means within three standard errors, ensemble widths alike
+    a, b = nu32[40:].mean(axis=0), nu64[40:].mean(axis=0)
+    se = np.sqrt(a.var() / len(a) + b.var() / len(b))
+    assert abs(a.mean() - b.mean()) < 3 * se, (a.mean(), b.mean(), se)
+    assert 0.8 * b.std() < a.std() < 1.25 * b.std()
+    # the burst itself (largest ensemble-mean Nusselt number and when it happens)
+    assert abs(int(nu32.mean(axis=1).argmax()) - int(nu64.mean(axis=1).argmax())) <= 1
+    assert nu32.mean(axis=1).max() == pytest.approx(nu64.mean(axis=1).max(), rel=0.05)
