@@ -82,8 +82,7 @@ class RayleighBenardConvection2DEnv(spaces.Env):
         self.episode_steps = int(episode_length / heater_duration)
 
         self.logger = logging.getLogger(__name__)
-        self.logger.info(f"Using Rayleigh number Ra={self.ra}")
-        self.logger.info(f"Using episode length {self.episode_length} timesteps")
+        self.logger.info("2D environment: Ra=%g, episode of %g time units, %d heaters", self.ra, self.episode_length, self.heater_segments)
 
         # rbc2D.py:75-108
         self.action_space = spaces.Box(-1, 1, shape=(self.heater_segments,), dtype=np.float32)
@@ -200,32 +199,17 @@ class RayleighBenardConvection2DEnv(spaces.Env):
         if self.render_mode == "rgb_array":
             return data.transpose(1, 0, 2)
         if self.render_mode == "human":
-            try:
-                import pygame
-            except ImportError as e:
-                raise RuntimeError("render_mode='human' needs pygame, which is not installed") from e
+            # the window itself is outside the accelerated path: a thin optional viewer (viewer.py) shows the same RGB frame
             if self.screen is None:
-                pygame.init()
-                pygame.display.init()
-                self.screen = pygame.display.set_mode((self.screen_width, self.screen_height))
-                pygame.display.set_caption("Rayleigh Benard Convection")
-            if self.clock is None:
-                self.clock = pygame.time.Clock()
-            canvas = pygame.Surface((self.state_shape[1], self.state_shape[0]))
-            pygame.surfarray.blit_array(canvas, data)
-            canvas = pygame.transform.scale(canvas, (self.screen_width, self.screen_height))
-            self.screen.blit(canvas, (0, 0))
-            pygame.event.pump()
-            self.clock.tick(self.metadata["render_fps"])
-            pygame.display.flip()
+                from .viewer import FrameWindow
+                self.screen = FrameWindow(self.screen_width, self.screen_height, self.metadata["render_fps"])
+            self.screen.show(data)
             return None
         raise ValueError(f"Unknown render mode: {self.render_mode}")
 
     def close(self):
         if self.screen is not None:
-            import pygame
-            pygame.display.quit()
-            pygame.quit()
+            self.screen.close()
             self.screen = None
         if getattr(self, "sim", None) is not None:
             self.sim.close()

@@ -336,36 +336,54 @@ def _object_header(messages) -> bytes:
     return struct.pack("<BxHII4x", 1, len(messages), 1, len(body)) + body
 
 
-def write_h5(path, datasets: Dict[str, np.ndarray], attrs: Dict[str, int]) -> None:
-    """Write little-endian f64 datasets (given in HDF5/C dimension order) and scalar i64 root attributes with the
-    structure of the reference files: superblock v0, v1 object headers, link messages, v3 attributes, contiguous
-    layout, data starting at 0x800."""
+_DATASET_HEADER_BYTES = 256          # message area of a dataset header as libhdf5 allocates it (the rest is one null message)
+
+
+def write_h5(path, datasets: Dict[str, np.ndarray], attrs: Dict[str, int], mtime: int | None = None) -> None:
+    """Write little-endian f64 datasets (given in HDF5/C dimension order) and scalar i64 root attributes the way libhdf5
+    (through HDF5.jl) lays the reference files out: superblock v0; a v1 root object header of a *new-style compact group*
+    (Link Info + Group Info messages — libhdf5 looks for a symbol table unless Link Info is there — then v3 attributes and one
+    hard-link message per dataset); v1 dataset headers with dataspace v1, datatype, fill value v2, contiguous layout v3, a
+    modification-time message (`mtime`, seconds since the epoch; default now) and a null message filling the 256-byte message
+    area; raw data from 0x800.
+
+    Given the reference's `mtime`, the dataset headers and everything from 0x800 on are byte-identical to the file HDF5.jl wrote
+    for the same arrays (`tests/test_h5lite_roundtrip.py`); the root group differs in placement only — libhdf5 grew it through
+    continuation blocks scattered between the dataset headers and left the B-tree / heap of the symbol table it started with,
+    here it is one contiguous block."""
+    import time
     payload = {k: np.ascontiguousarray(a, dtype="<f8") for k, a in datasets.items()}
     names = list(payload)
     base, data_start = 0x60, 0x800
+    stamp = int(time.time()) if mtime is None else int(mtime)
 
     def ds_header(arr: np.ndarray, addr: int) -> bytes:
-        lay = struct.pack("<BBQQ", 3, 1, addr, arr.nbytes)
-        fill = struct.pack("<BBBB", 2, 2, 2, 1)
-        return _object_header([
+        msgs = [
             _msg(0x01, _ds_simple(arr.shape)),
             _msg(0x03, _dt_f64(), flags=1),
-            _msg(0x05, fill, flags=1),
-            _msg(0x08, lay),
-        ])
+            _msg(0x05, struct.pack("<BBBB", 2, 2, 2, 1), flags=1),          # fill value v2: allocate late, write if set, undefined
+            _msg(0x08, struct.pack("<BBQQ", 3, 1, addr, arr.nbytes)),
+            _msg(0x12, struct.pack("<B3xI", 1, stamp & 0xFFFFFFFF)),
+        ]
+        used = sum(len(m) for m in msgs)
+        msgs.append(_msg(0x00, b"\0" * (_DATASET_HEADER_BYTES - used - 8)))
+        return _object_header(msgs)
 
     addrs, off = {}, data_start
     for k in names:
         addrs[k] = off
         off += payload[k].nbytes
     eof = off
-    root_msgs_fixed = [_msg(0x0C, _attr_v3_scalar_i64(k, int(v))) for k, v in attrs.items()]
+    group_msgs = [
+        _msg(0x02, struct.pack("<BBQQ", 0, 0, _UNDEF, _UNDEF)),              # link info: compact storage (no heap, no index)
+        _msg(0x0A, struct.pack("<BB", 0, 0), flags=1),                       # group info: defaults
+    ] + [_msg(0x0C, _attr_v3_scalar_i64(k, int(v))) for k, v in attrs.items()]
 
     def link(name: str, addr: int) -> bytes:
         nm = name.encode()
         return _msg(0x06, struct.pack("<BBB", 1, 0x10, 1) + bytes([len(nm)]) + nm + struct.pack("<Q", addr))
 
-    root_len = 16 + sum(len(m) for m in root_msgs_fixed) + sum(len(link(k, 0)) for k in names)
+    root_len = 16 + sum(len(m) for m in group_msgs) + sum(len(link(k, 0)) for k in names)
     p = _pad8(base + root_len)
     ds_addr, hdrs = {}, {}
     for k in names:
@@ -374,7 +392,7 @@ def write_h5(path, datasets: Dict[str, np.ndarray], attrs: Dict[str, int]) -> No
         p = _pad8(p + len(hdrs[k]))
     if p > data_start:
         raise H5FormatError("header region overflow")
-    root = _object_header(root_msgs_fixed + [link(k, ds_addr[k]) for k in names])
+    root = _object_header(group_msgs + [link(k, ds_addr[k]) for k in names])
     sb = _SIG + bytes([0, 0, 0, 0, 0, 8, 8, 0]) + struct.pack("<HHI", 4, 16, 0)
     sb += struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
     sb += struct.pack("<QQII16x", 0, base, 0, 0)
@@ -387,17 +405,17 @@ def write_h5(path, datasets: Dict[str, np.ndarray], attrs: Dict[str, int]) -> No
     Path(path).write_bytes(bytes(buf))
 
 
-def write_checkpoint(path, b: np.ndarray, u: np.ndarray, w: np.ndarray, start_seed: int) -> None:
+def write_checkpoint(path, b: np.ndarray, u: np.ndarray, w: np.ndarray, start_seed: int, mtime: int | None = None) -> None:
     """Write 2D arrays ``[ep, z, x]`` as a reference-compatible `ckpt_ra*.h5`: datasets ``b,u,w`` with HDF5 dims
     ``(Nz|Nz+1, 1, Nx, n_ep)``, root attributes ``num_episodes`` and ``start_seed`` (`rbc_sim2D.jl:39-43`).  The data
-    section is byte-identical to what the reference writes for the same arrays; header bytes differ in layout only."""
+    section and the dataset headers are what the reference writes for the same arrays (see `write_h5`)."""
     arrays = {k: np.asarray(a, dtype="<f8") for k, a in (("b", b), ("u", u), ("w", w))}
     write_h5(path, {k: np.transpose(a, (1, 2, 0))[:, None, :, :] for k, a in arrays.items()},
-             {"num_episodes": arrays["b"].shape[0], "start_seed": int(start_seed)})
+             {"num_episodes": arrays["b"].shape[0], "start_seed": int(start_seed)}, mtime=mtime)
 
 
-def write_checkpoint_3d(path, b, u, v, w, start_seed: int) -> None:
+def write_checkpoint_3d(path, b, u, v, w, start_seed: int, mtime: int | None = None) -> None:
     """Write 3D arrays ``[ep, z, y, x]`` as `3D_ckpt_ra*.h5` (`rbc_sim3D.jl:57-65`): HDF5 dims ``(Nz|Nz+1, Ny, Nx, n_ep)``."""
     arrays = {k: np.asarray(a, dtype="<f8") for k, a in (("b", b), ("u", u), ("v", v), ("w", w))}
     write_h5(path, {k: np.moveaxis(a, 0, 3) for k, a in arrays.items()},
-             {"num_episodes": arrays["b"].shape[0], "start_seed": int(start_seed)})
+             {"num_episodes": arrays["b"].shape[0], "start_seed": int(start_seed)}, mtime=mtime)

@@ -6,6 +6,8 @@ from __future__ import annotations
 import logging
 from typing import Any, Dict, Tuple
 
+import warnings
+
 import numpy as np
 
 from . import spaces
@@ -33,29 +35,27 @@ def find_peaks_height(x: np.ndarray, height: float) -> np.ndarray:
 
 
 def cell_distance(state: np.ndarray, size_state=(64, 96), use_avg: bool = False) -> float:
-    """`RBCRewardShaping.compute_cell_distances` (`rbc_reward_shaping.py:86-140`)."""
-    if use_avg:
-        uy = state[RBCField.UY].mean(axis=0)
-    else:
-        uy = state[RBCField.UY][int(size_state[0] / 2) - 1]
+    """Distance between the Benard cells of a state; same result as `RBCRewardShaping.compute_cell_distances`
+    (`rbc_reward_shaping.py:86-140`), evaluated for all pairs of cells at once.
+
+    Cells are the maxima (height >= 0.001) of the vertical velocity along the row just below mid-height (or its column average).
+    The distance of a pair is the shorter way round the periodic domain, and 0 when the velocity stays positive all along that
+    way (the two maxima then belong to one up-welling).  The result is the largest pair distance; a single cell gives 0."""
+    uy = state[RBCField.UY].mean(axis=0) if use_avg else state[RBCField.UY][int(size_state[0] / 2) - 1]
     peaks = find_peaks_height(uy, 0.001)
-    domain_x = np.linspace(0, 2 * np.pi, size_state[1], endpoint=False)
     if len(peaks) <= 1:
         return 0
-    distances = []
-    for i in range(len(peaks)):
-        for j in range(i + 1, len(peaks)):
-            dist1 = np.abs(domain_x[peaks[j]] - domain_x[peaks[i]])
-            dist2 = 2 * np.pi - dist1
-            d = min(dist1, dist2)
-            if dist1 < dist2:
-                if np.all(uy[peaks[i]:peaks[j]] > 0):
-                    d = 0
-            else:
-                if np.all(uy[peaks[j]:] > 0) and np.all(uy[:peaks[i]] > 0):
-                    d = 0
-            distances.append(d)
-    return float(np.max(distances))
+    x = np.linspace(0, 2 * np.pi, size_state[1], endpoint=False)
+    lo, hi = np.triu_indices(len(peaks), k=1)                      # every pair once, lo before hi along x
+    left, right = peaks[lo], peaks[hi]
+    direct = np.abs(x[right] - x[left])
+    around = 2 * np.pi - direct
+    # down[k] = number of samples among uy[:k] that are not strictly positive (NaN counts as not positive)
+    down = np.concatenate(([0], np.cumsum(~(uy > 0))))
+    one_upwelling = np.where(direct < around,
+                             down[right] == down[left],                              # nothing sinks on the direct way
+                             (down[-1] == down[right]) & (down[left] == 0))          # nothing sinks on the way round the seam
+    return float(np.where(one_upwelling, 0.0, np.minimum(direct, around)).max())
 
 
 def shape_reward(reward: float, cell_distances: float, w: float) -> float:
@@ -70,16 +70,24 @@ def normalize_reward(reward: float, ra: float, dims: int = 2) -> float:
     return (reward + scale) / (scale - 1)
 
 
+def _affine_to_unit(obs: np.ndarray, min_vals, max_vals, maxval) -> np.ndarray:
+    """Map channel c of `obs` from [min_vals[c], max_vals[c]] to [-maxval, maxval], in place, in the array's own precision
+    (the reference assigns channel by channel with Python-float limits, i.e. float32 arithmetic on float32 observations)."""
+    n = obs.shape[0]
+    per_channel = (n,) + (1,) * (obs.ndim - 1)
+    lo = np.asarray(min_vals[:n], dtype=obs.dtype).reshape(per_channel)
+    span = np.asarray([hi - lo_ for hi, lo_ in zip(max_vals[:n], min_vals[:n])], dtype=obs.dtype).reshape(per_channel)
+    obs[...] = maxval * (2 * (obs - lo) / span - 1)
+    return obs
+
+
 def normalize_observation(obs: np.ndarray, heater_limit: float, temperature_difference=(1, 2), maxval=1, u_limit=1.3,
                           clip: bool = False) -> np.ndarray:
     """`RBCNormalizeObservation.observation` (`rbc_normalize_observation.py:64-74`); modifies and returns `obs`."""
-    min_vals = [temperature_difference[0], -u_limit, -u_limit, -u_limit]
-    max_vals = [temperature_difference[1] + heater_limit, u_limit, u_limit, u_limit]
-    for c in range(obs.shape[0]):
-        obs[c] = maxval * (2 * (obs[c] - min_vals[c]) / (max_vals[c] - min_vals[c]) - 1)
-    if clip:
-        obs = np.clip(obs, -maxval, maxval)
-    return obs
+    lows = [temperature_difference[0], -u_limit, -u_limit, -u_limit]
+    highs = [temperature_difference[1] + heater_limit, u_limit, u_limit, u_limit]
+    obs = _affine_to_unit(obs, lows, highs, maxval)
+    return np.clip(obs, -maxval, maxval) if clip else obs
 
 
 # --------------------------------------------------------------------------------------- wrapper classes
@@ -101,12 +109,12 @@ class RBCNormalizeObservation(spaces.ObservationWrapper):
         self.observation_space = spaces.Box(low=-limit, high=limit, shape=env.observation_space.shape, dtype=np.float32)
 
     def observation(self, obs) -> Any:
-        for c in range(obs.shape[0]):
-            obs[c] = self.maxval * (2 * (obs[c] - self.min_vals[c]) / (self.max_vals[c] - self.min_vals[c]) - 1)
+        obs = _affine_to_unit(obs, self.min_vals, self.max_vals, self.maxval)
         if self.clip:
             obs = np.clip(obs, -self.maxval, self.maxval)
-        if np.any(np.abs(obs) > (1 + self.excursion_eps) * self.maxval):
-            print(f"Warning: observation exceeds maxval {self.maxval}, namely: {np.max(np.abs(obs))} is the max observed value.")
+        peak = float(np.abs(obs).max())
+        if peak > (1 + self.excursion_eps) * self.maxval:
+            warnings.warn(f"normalised observation reaches {peak:.4g}, outside the declared range of +-{(1 + self.excursion_eps) * self.maxval:.4g}")
         return obs
 
     @staticmethod

@@ -28,6 +28,42 @@ def test_cell_distance_cases():
     assert W.cell_distance(st) == 0
 
 
+def _cell_distance_by_walking(uy, height=0.001):
+    """Independent definition for the test below: walk the periodic row from one maximum to the other along the shorter way
+    (the reference takes the direct way when it is strictly shorter, otherwise the way over the seam) and see if the flow sinks."""
+    n = len(uy)
+    tops = [i for i in W.find_peaks_height(uy, height)]
+    x = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    best = 0.0
+    for a_pos, a in enumerate(tops):
+        for b in tops[a_pos + 1:]:
+            direct = abs(x[b] - x[a]); around = 2 * np.pi - direct
+            walk = range(a, b) if direct < around else list(range(b, n)) + list(range(0, a))
+            if not all(uy[k] > 0 for k in walk):
+                best = max(best, min(direct, around))
+    return best
+
+
+def test_cell_distance_all_pairs_form_equals_walking_definition():
+    rng = np.random.default_rng(5)
+    x = np.linspace(0, 2 * np.pi, 96, endpoint=False)
+    rows = []
+    for _ in range(300):
+        k = rng.integers(1, 6)
+        sig = sum(rng.normal() * np.cos(m * x + rng.uniform(0, 6.3)) for m in range(1, k + 1)) + rng.normal(0, 0.5)
+        rows.append(sig + 0.05 * rng.standard_normal(96) * rng.integers(0, 2))
+    rows.append(np.round(rng.standard_normal(96), 1))                 # ties and plateaus
+    nan_row = rows[0].copy(); nan_row[40] = np.nan; rows.append(nan_row)
+    seen = set()
+    for r in rows:
+        st = np.zeros((3, 64, 96)); st[2, 31] = r; st[2, :31] = 0.5 * r
+        got = W.cell_distance(st)
+        assert got == _cell_distance_by_walking(r)
+        seen.add(got > 0)
+        assert W.cell_distance(st, use_avg=True) == _cell_distance_by_walking(st[2].mean(axis=0))
+    assert seen == {True, False}
+
+
 def test_normalizers_match_reference_formulas():
     obs = np.random.default_rng(1).uniform(-1, 2.5, (3, 8, 48)).astype(np.float32)
     out = W.normalize_observation(obs.copy(), 0.75)
