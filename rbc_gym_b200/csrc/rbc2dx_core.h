@@ -1012,14 +1012,16 @@ RBC_HD void hydrostatic(const Consts<Real>& C, const CtxX<Real>& X, unsigned o_s
 // ------------------------------------------------------------------------------------------
 // CFL guard (fp32 throughput mode).  Above CFL ~ 1.5 the RK3 / 5th-order-upwind scheme is linearly unstable; the first plume
 // burst of a high-Ra flow started from noise gets there, fp64 rides it out on its 1e-9 smaller round-off
-// seed, fp32 leaves ~1 environment in 1000 with NaNs.  At the top of every RK3 step the cluster measures
+// seed, fp32 leaves ~1 environment in 1000 with NaNs.  At the top of every fourth RK3 step the cluster measures
 // max(|w| dt/dz, |u| dt/dx) of the environment (own rows, warp maxima, one DSMEM exchange behind a cluster barrier — 3 barriers
-// per RK3 step against ~25 k cycles per stage) and, above the limit, takes the step as ceil(CFL) equal parts.  Every CTA computes
+// per measurement against ~25 k cycles per stage) and, above the limit, takes the step as ceil(CFL) equal parts.  Every CTA computes
 // the same number, so the mbarrier channel counts stay in step.  Environments below the limit — all developed flows — are
-// untouched bit for bit.  Returns the number of parts (>= 1).
+// untouched bit for bit.  The measurement is repeated every CFL_EVERY RK3 steps (always with the full dt_solver) and the split
+// kept in between (`covers` = RK3 steps this measurement stands for, for the event counter).  Returns the number of parts (>= 1).
 // ------------------------------------------------------------------------------------------
+constexpr int CFL_EVERY = 4;
 template <typename G, typename Real>
-RBC_HD int cfl_parts(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, unsigned o_cur, int my_rank, Real dt, int sub)
+RBC_HD int cfl_parts(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Real>& X, int env, unsigned o_cur, int my_rank, Real dt, int sub, int covers)
 {
     (void)my_rank;
     constexpr int NX = G::NX, NT = G::NT, SX = G::SX, H = G::HALO;
@@ -1065,7 +1067,7 @@ RBC_HD int cfl_parts(const Consts<Real>& C, const EnvIO<Real>& io, const CtxX<Re
     int parts = 1;
     if (cfl > (double)C.cfl_limit) { parts = (int)ceil(cfl); parts = parts < 2 ? 2 : (parts > 8 ? 8 : parts); }
     if (parts > 1 && io.cfl_events != nullptr) {
-        RBX_PHASE_L(G, if (rank == 0 && tid == 0) io.cfl_events[env] += parts - 1;)
+        RBX_PHASE_L(G, if (rank == 0 && tid == 0) io.cfl_events[env] += (parts - 1) * covers;)
     }
     return parts;
 }
@@ -1330,12 +1332,15 @@ RBC_HD void env_action_step(const Consts<Real>& C, const EnvIO<Real>& io, const 
     unsigned o_cur = X.o_s0, o_nxt = X.o_s1;               // fp64 mode: o_s1 is unused, the predicted state is global
     Real last_dtau = Real(1);                              // set! projects with dtau = 1
     if (project_first) project<G, Real, NXT_GLOBAL, SPLIT>(C, X, o_cur, o_nxt, my_rank, S, false);
+    int parts = 1;
     for (int sub = 0; sub < nsub; ++sub) {
         const Real dt_sub = (sub == nsub - 1) ? C.dt_last : C.dt_full;
-        const int parts = (C.cfl_limit > Real(0)) ? cfl_parts<G>(C, io, X, env, o_cur, my_rank, dt_sub, sub) : 1;
+        // the flow changes little over CFL_EVERY RK3 steps (0.06 time units at dt_solver 0.015): measure once, keep the split
+        if (C.cfl_limit > Real(0) && sub % CFL_EVERY == 0) parts = cfl_parts<G>(C, io, X, env, o_cur, my_rank, C.dt_full, sub / CFL_EVERY, nsub - sub < CFL_EVERY ? nsub - sub : CFL_EVERY);
         const Real dt = parts > 1 ? dt_sub / Real(parts) : dt_sub;
-        for (int ps = 0; ps < 3 * parts; ++ps) {
-            const int stage = ps % 3;
+        RBC_NOUNROLL
+        for (int part = 0; part < parts; ++part)
+        for (int stage = 0; stage < 3; ++stage) {
             const int in_slab = (stage & 1) ? 0 : 1, out_slab = 1 - in_slab;
             if (SPLIT) hydrostatic<G, Real, NXT_GLOBAL>(C, X, o_cur, my_rank, S);
             RBX_PHASE_L(G, phase_edge_fluxes<G>(tid, rank, RBX_PTR(o_cur), RBX_PTR(X.o_edge));)

@@ -160,7 +160,7 @@ def test_pressure_split_set_projection_192():
 
 def test_cfl_guard_splits_fast_rk3_steps_and_leaves_slow_ones_alone(ckpt_ra1e5):
     """The CFL guard of the cluster kernels (`cfl_parts` in rbc2dx_core.h): an RK3 step whose max(|w| dt/dz, |u| dt/dx) exceeds
-    the limit is taken as ceil(CFL) equal parts.  Emulated kernel (96 x 64 over 2 CTAs) against the oracle stepped with the
+    the limit is taken as ceil(CFL) equal parts; the measurement is repeated every fourth RK3 step.  Emulated kernel (96 x 64 over 2 CTAs) against the oracle stepped with the
     schedule the guard must choose, decided here from the oracle's own states; below the limit nothing changes, bit for bit."""
     P = O.make_params(1e5, split_phy=False)
     c = ckpt_ra1e5
@@ -169,18 +169,19 @@ def test_cfl_guard_splits_fast_rk3_steps_and_leaves_slow_ones_alone(ckpt_ra1e5):
     a = np.linspace(-1, 1, 12).astype(np.float32)
     dz, dx = 2.0 / 64, 2 * np.pi / 96
     rb, ru, rw, parts_seen = b, u, w, []
-    for dt in O.substep_schedule(0.09):                                  # three RK3 steps of 0.03
-        cfl = max(np.abs(rw[:-1]).max() * dt / dz, np.abs(ru).max() * dt / dx)
-        parts = int(min(8, max(2, np.ceil(cfl)))) if cfl > 1.4 else 1
+    for n, dt in enumerate(O.substep_schedule(0.15)):                    # five RK3 steps of 0.03; measured before steps 0 and 4
+        if n % 4 == 0:
+            cfl = max(np.abs(rw[:-1]).max() * 0.03 / dz, np.abs(ru).max() * 0.03 / dx)
+            parts = int(min(8, max(2, np.ceil(cfl)))) if cfl > 1.4 else 1
         parts_seen.append(parts)
         r = O.step(P, rb, ru, rw, a.astype(np.float64), np.full(parts, dt / parts))
         rb, ru, rw = r["b"], r["u"], r["w"]
     assert parts_seen[0] == 2                                            # the guard really has something to do
     st = emu.packx(b[None], u[None], w[None])
-    g = emu.stepx(st, a[None], 1e5, 0.09, cl=2, precision=64, nxt_global=True, cfl_limit=1.4)
+    g = emu.stepx(st, a[None], 1e5, 0.15, cl=2, precision=64, nxt_global=True, cfl_limit=1.4)
     gb, gu, gw = emu.unpackx(g["state"], 96, 64)
     assert rel(gb[0], rb) < 1e-12 and rel(gu[0], ru) < 1e-12 and rel(gw[0], rw) < 1e-12
-    plain = emu.stepx(st, a[None], 1e5, 0.09, cl=2, precision=64, nxt_global=True)
+    plain = emu.stepx(st, a[None], 1e5, 0.15, cl=2, precision=64, nxt_global=True)
     assert rel(emu.unpackx(plain["state"], 96, 64)[0][0], rb) > 1e-6    # ... and without it the result differs
     # a developed flow (CFL ~ 0.9) is untouched by the guard, bit for bit, in the fp32 asynchronous variant too
     s0 = emu.packx(c.b[3][None], c.u[3][None], c.w[3][None])
