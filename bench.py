@@ -166,6 +166,23 @@ def secondary_configs(device: int):
         sim.close()
     except Exception as e:
         out["config4_3d_32x32x16_ra1e4"] = {"error": str(e)[:200]}
+    try:
+        # the resolution of the reference's own 3D runs (experiments/flowstats/flowstats_ra.py:27-36): 64 x 64 x 32, 50 RK3 steps per
+        # action; the stage-streaming kernels (rbc3dg) really move the roofline's bytes through HBM
+        B5, shape = 64, (32, 64, 64)
+        sim = backend.Sim3D(B5, ra=1e4, state_shape=shape, heater_duration=0.25, dt_solver=0.005, precision=32, device=device)
+        rng = np.random.default_rng(0)
+        base = np.concatenate([noise_initial_fields_3d(rng, shape, kick=0.05) for _ in range(4)])
+        sim.reset_from_fields(base[np.arange(B5) % 4], project=True)
+        a = torch.rand((B5, 8, 8), device=f"cuda:{device}") * 2 - 1
+        ms = timed(lambda: sim.step(a, want_obs=False), n_steps=1)
+        alg = sim.nsub * 10 * sim.nstate * 4
+        out["flowstats_3d_64x64x32_ra1e4"] = {"env_steps_per_s": B5 / ms * 1e3, "envs": B5, "rk3_steps": sim.nsub, "ms_per_step": ms,
+                                              "streaming_equiv_GBps": B5 / ms * 1e3 * alg / 1e9, "frac_of_hbm_peak": B5 / ms * 1e3 * alg / 1e9 / peak,
+                                              "kernel": "rbc3dg stage-streaming kernels (tendency, div+FFT, Thomas, inverse, correct)", "launch": sim.launch_info()}
+        sim.close()
+    except Exception as e:
+        out["flowstats_3d_64x64x32_ra1e4"] = {"error": str(e)[:200]}
     return out
 
 

@@ -291,9 +291,39 @@ RBC_HD Pair<Real> centred4_pair(Real a0, Real b0, Real c0, Real d0, Real a1, Rea
     return {centred4(a0, b0, c0, d0), centred4(a1, b1, c1, d1)};
 }
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+// RBC_UPWIND_SYM: select-free forms of the upwind choice, kept as measured alternatives (default 0 = selects).  With
+// S = (phiL + phiR)/2 (the 6-point centred reconstruction) and D = (phiL - phiR)/2 the upwinded flux  v > 0 ? v phiL : v phiR
+// equals  v S + |v| D:   60 S = (w0 + w5) - 8 (w1 + w4) + 37 (w2 + w3),   60 D = (w0 - w5) - 5 (w1 - w4) + 10 (w2 - w3).
+// That trades the 12 selects/compares of a pair (half-rate ALU pipe) for FMA-pipe work.  Measured on B200 with
+// tools/microbench/tendency_tile.cu (cycles per tendency stage): selects 11.36 k; = 1 (all packed: the operand pairs need
+// ~900 packing moves) 12.56 k; = 2 (scalar sums/differences, packed FMAs, no moves) 12.02 k.  The march is not ALU-bound.
+#ifndef RBC_UPWIND_SYM
+#define RBC_UPWIND_SYM 0
+#endif
 template <>
 __device__ __forceinline__ Pair<float> upwind5_pair<float>(float v0, const float* w0, float v1, const float* w1)
 {
+#if RBC_UPWIND_SYM
+    const float2 a0 = make_float2(w0[0], w1[0]), a1 = make_float2(w0[1], w1[1]), a2 = make_float2(w0[2], w1[2]);
+    const float2 a3 = make_float2(w0[3], w1[3]), a4 = make_float2(w0[4], w1[4]), a5 = make_float2(w0[5], w1[5]);
+#if RBC_UPWIND_SYM == 2
+    // sums and differences as scalar adds: their results land in adjacent registers, so the packed FMAs need no packing moves
+    const float2 s0 = make_float2(a0.x + a5.x, a0.y + a5.y), s1 = make_float2(a1.x + a4.x, a1.y + a4.y), s2 = make_float2(a2.x + a3.x, a2.y + a3.y);
+    const float2 d0 = make_float2(a0.x - a5.x, a0.y - a5.y), d1 = make_float2(a1.x - a4.x, a1.y - a4.y), d2 = make_float2(a2.x - a3.x, a2.y - a3.y);
+#else
+    const float2 s0 = __fadd2_rn(a0, a5), s1 = __fadd2_rn(a1, a4), s2 = __fadd2_rn(a2, a3);
+    const float2 d0 = __fadd2_rn(a0, make_float2(-a5.x, -a5.y)), d1 = __fadd2_rn(a1, make_float2(-a4.x, -a4.y)), d2 = __fadd2_rn(a2, make_float2(-a3.x, -a3.y));
+#endif
+    const float c0 = float(1.0 / 60.0), cs1 = float(-8.0 / 60.0), cs2 = float(37.0 / 60.0), cd1 = float(-5.0 / 60.0), cd2 = float(10.0 / 60.0);
+    float2 S = __fmul2_rn(make_float2(c0, c0), s0);
+    S = __ffma2_rn(make_float2(cs1, cs1), s1, S);
+    S = __ffma2_rn(make_float2(cs2, cs2), s2, S);
+    float2 D = __fmul2_rn(make_float2(c0, c0), d0);
+    D = __ffma2_rn(make_float2(cd1, cd1), d1, D);
+    D = __ffma2_rn(make_float2(cd2, cd2), d2, D);
+    const float2 f = __ffma2_rn(make_float2(fabsf(v0), fabsf(v1)), D, __fmul2_rn(make_float2(v0, v1), S));
+    return {f.x, f.y};
+#else
     const bool p0 = v0 > 0.f, p1 = v1 > 0.f;
     const float2 x0 = make_float2(p0 ? w0[0] : w0[5], p1 ? w1[0] : w1[5]);
     const float2 x1 = make_float2(p0 ? w0[1] : w0[4], p1 ? w1[1] : w1[4]);
@@ -308,6 +338,7 @@ __device__ __forceinline__ Pair<float> upwind5_pair<float>(float v0, const float
     phi = __ffma2_rn(make_float2(k4, k4), x4, phi);
     const float2 f = __fmul2_rn(make_float2(v0, v1), phi);
     return {f.x, f.y};
+#endif
 }
 template <>
 __device__ __forceinline__ Pair<float> centred4_pair<float>(float a0, float b0, float c0, float d0, float a1, float b1, float c1, float d1)
