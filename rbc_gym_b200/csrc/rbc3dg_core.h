@@ -220,26 +220,59 @@ RBC_HD Real cell_divergence(const Dims& D, const ConstsG<Real>& C, const Real* P
 // inverse = decimation in time (spans 1 .. n/2); together they need no bit-reversal pass.
 //   along x: line = row (ny lines of nx), element stride 1;  along y: line = column (nx lines of ny), element stride nx
 //   tw: [n/2] complex, tw[m] = exp(-2 pi i m / n)
+// All sizes are powers of two and passed as logarithms (ln = log2 n, ls = log2 span, lnl = log2 n_lines): the index split is
+// shifts and masks.  `lines_fastest` picks which index runs fastest over consecutive work items (= consecutive threads):
+// along y it must be the line, so that a warp touches 32 neighbouring columns of one row (conflict-free) instead of 32 rows
+// of one column (stride nx complex numbers = one bank: the first version's y passes were 32-way bank conflicts).
 // ------------------------------------------------------------------------------------------
-template <typename Real>
-RBC_HD void butterfly_dif(cx<Real>* Z, int n, int span, int line_stride, int elem_stride, const cx<Real>* tw, int item)
+struct Fly {
+    int a, b, tw;      // the two elements of the butterfly and its twiddle index
+};
+RBC_HD Fly fly_index(int ln, int ls, int lnl, int line_stride, int elem_stride, bool lines_fastest, int item)
 {
-    const int half = n >> 1, line = item / half, q = item % half, jj = q % span, grp = q / span;
-    const int a = line * line_stride + (grp * 2 * span + jj) * elem_stride, b = a + span * elem_stride;
-    const cx<Real> xa = Z[a], xb = Z[b], w = tw[jj * (half / span)];
-    Z[a] = cx<Real>{xa.re + xb.re, xa.im + xb.im};
-    const Real dr = xa.re - xb.re, di = xa.im - xb.im;
-    Z[b] = cx<Real>{dr * w.re - di * w.im, dr * w.im + di * w.re};
+    const int lh = ln - 1;                                   // log2 of the butterflies per line
+    const int line = lines_fastest ? (item & ((1 << lnl) - 1)) : (item >> lh);
+    const int q = lines_fastest ? (item >> lnl) : (item & ((1 << lh) - 1));
+    const int jj = q & ((1 << ls) - 1), grp = q >> ls;
+    Fly f;
+    f.a = line * line_stride + ((grp << (ls + 1)) + jj) * elem_stride;
+    f.b = f.a + (elem_stride << ls);
+    f.tw = jj << (lh - ls);
+    return f;
 }
 template <typename Real>
-RBC_HD void butterfly_dit_inv(cx<Real>* Z, int n, int span, int line_stride, int elem_stride, const cx<Real>* tw, int item)
+RBC_HD void butterfly_dif(cx<Real>* Z, int ln, int ls, int lnl, int line_stride, int elem_stride, bool lines_fastest, const cx<Real>* tw, int item)
 {
-    const int half = n >> 1, line = item / half, q = item % half, jj = q % span, grp = q / span;
-    const int a = line * line_stride + (grp * 2 * span + jj) * elem_stride, b = a + span * elem_stride;
-    const cx<Real> xa = Z[a], xb = Z[b], w = tw[jj * (half / span)];
+    const Fly f = fly_index(ln, ls, lnl, line_stride, elem_stride, lines_fastest, item);
+    const cx<Real> xa = Z[f.a], xb = Z[f.b], w = tw[f.tw];
+    Z[f.a] = cx<Real>{xa.re + xb.re, xa.im + xb.im};
+    const Real dr = xa.re - xb.re, di = xa.im - xb.im;
+    Z[f.b] = cx<Real>{dr * w.re - di * w.im, dr * w.im + di * w.re};
+}
+template <typename Real>
+RBC_HD void butterfly_dit_inv(cx<Real>* Z, int ln, int ls, int lnl, int line_stride, int elem_stride, bool lines_fastest, const cx<Real>* tw, int item)
+{
+    const Fly f = fly_index(ln, ls, lnl, line_stride, elem_stride, lines_fastest, item);
+    const cx<Real> xa = Z[f.a], xb = Z[f.b], w = tw[f.tw];
     const Real tr = xb.re * w.re + xb.im * w.im, ti = xb.im * w.re - xb.re * w.im;      // xb * conj(w)
-    Z[a] = cx<Real>{xa.re + tr, xa.im + ti};
-    Z[b] = cx<Real>{xa.re - tr, xa.im - ti};
+    Z[f.a] = cx<Real>{xa.re + tr, xa.im + ti};
+    Z[f.b] = cx<Real>{xa.re - tr, xa.im - ti};
+}
+// the passes of one plane as (direction, span) sequences; `run(n_items, fn)` executes fn(item) for every item and then
+// synchronises (a strided thread loop + __syncthreads on the device, a plain loop in the emulator)
+template <typename Real, typename Run>
+RBC_HD void plane_fft_forward(const Dims& D, cx<Real>* Z, const cx<Real>* twx, const cx<Real>* twy, Run run)
+{
+    const int items = D.ncol >> 1;
+    for (int ls = D.lx2 - 1; ls >= 0; --ls) run(items, [&](int it) { butterfly_dif<Real>(Z, D.lx2, ls, D.ly2, D.nx, 1, false, twx, it); });
+    for (int ls = D.ly2 - 1; ls >= 0; --ls) run(items, [&](int it) { butterfly_dif<Real>(Z, D.ly2, ls, D.lx2, 1, D.nx, true, twy, it); });
+}
+template <typename Real, typename Run>
+RBC_HD void plane_fft_inverse(const Dims& D, cx<Real>* Z, const cx<Real>* twx, const cx<Real>* twy, Run run)
+{
+    const int items = D.ncol >> 1;
+    for (int ls = 0; ls < D.ly2; ++ls) run(items, [&](int it) { butterfly_dit_inv<Real>(Z, D.ly2, ls, D.lx2, 1, D.nx, true, twy, it); });
+    for (int ls = 0; ls < D.lx2; ++ls) run(items, [&](int it) { butterfly_dit_inv<Real>(Z, D.lx2, ls, D.ly2, D.nx, 1, false, twx, it); });
 }
 
 // ------------------------------------------------------------------------------------------

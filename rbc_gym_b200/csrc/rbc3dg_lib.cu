@@ -38,6 +38,23 @@ g3_tendency_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real* kapp
                         G_all + (size_t)env * 4 * D.nc, Tb_all + (size_t)env * D.ncol, cell, dt, gam, zet, use_prev != 0, store_g != 0);
 }
 
+// one FFT stage on the device: the CTA's threads stride over the butterflies, then a barrier
+struct BlockRun {
+    template <typename F>
+    __device__ void operator()(int n_items, F fn) const
+    {
+        for (int it = threadIdx.x; it < n_items; it += blockDim.x) fn(it);
+        __syncthreads();
+    }
+};
+// twiddles of both directions into shared memory, behind the plane: [nx/2] then [ny/2] complex
+template <typename Real>
+__device__ void stage_twiddles(const Dims& D, cx<Real>* dst, const cx<Real>* twx, const cx<Real>* twy)
+{
+    const int hx = D.nx >> 1, hy = D.ny >> 1;
+    for (int q = threadIdx.x; q < hx + hy; q += blockDim.x) dst[q] = q < hx ? twx[q] : twy[q - hx];
+}
+
 // divergence of one level into a shared-memory plane, then the forward FFT in x and y (decimation in frequency)
 template <typename Real>
 __global__ void g3_div_fft_kernel(Dims D, ConstsG<Real> C, const Real* P_all, cx<Real>* Z_all, const cx<Real>* twx, const cx<Real>* twy,
@@ -48,16 +65,9 @@ __global__ void g3_div_fft_kernel(Dims D, ConstsG<Real> C, const Real* P_all, cx
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, k = blockIdx.x;
     const Real* P = P_all + (size_t)env * D.nstate;
     for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) Z[c] = cx<Real>{cell_divergence<Real>(D, C, P, c % D.nx, c / D.nx, k), Real(0)};
+    stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
     __syncthreads();
-    const int items_x = D.ny * (D.nx >> 1), items_y = D.nx * (D.ny >> 1);
-    for (int span = D.nx >> 1; span >= 1; span >>= 1) {
-        for (int it = threadIdx.x; it < items_x; it += blockDim.x) butterfly_dif<Real>(Z, D.nx, span, D.nx, 1, twx, it);
-        __syncthreads();
-    }
-    for (int span = D.ny >> 1; span >= 1; span >>= 1) {
-        for (int it = threadIdx.x; it < items_y; it += blockDim.x) butterfly_dif<Real>(Z, D.ny, span, 1, D.nx, twy, it);
-        __syncthreads();
-    }
+    plane_fft_forward<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
     cx<Real>* out = Z_all + ((size_t)env * D.nz + k) * D.ncol;
     for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) out[c] = Z[c];
 }
@@ -80,16 +90,9 @@ __global__ void g3_ifft_kernel(Dims D, const cx<Real>* Z_all, Real* phi_all, con
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, k = blockIdx.x;
     const cx<Real>* in = Z_all + ((size_t)env * D.nz + k) * D.ncol;
     for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) Z[c] = in[c];
+    stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
     __syncthreads();
-    const int items_x = D.ny * (D.nx >> 1), items_y = D.nx * (D.ny >> 1);
-    for (int span = 1; span <= (D.ny >> 1); span <<= 1) {
-        for (int it = threadIdx.x; it < items_y; it += blockDim.x) butterfly_dit_inv<Real>(Z, D.ny, span, 1, D.nx, twy, it);
-        __syncthreads();
-    }
-    for (int span = 1; span <= (D.nx >> 1); span <<= 1) {
-        for (int it = threadIdx.x; it < items_x; it += blockDim.x) butterfly_dit_inv<Real>(Z, D.nx, span, D.nx, 1, twx, it);
-        __syncthreads();
-    }
+    plane_fft_inverse<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
     const Real norm = Real(1) / (Real)D.ncol;
     Real* phi = phi_all + ((size_t)env * D.nz + k) * D.ncol;
     for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) phi[c] = Z[c].re * norm;
@@ -235,7 +238,7 @@ int create(const HostConfigG& hc, int nx, int ny, int nz, int num_envs, int prec
     p->D = make_dims(nx, ny, nz);
     p->hc = hc; p->B = num_envs; p->precision = precision; p->device = device;
     p->rs = precision == 32 ? 4 : 8;
-    p->smem = (size_t)p->D.ncol * 2 * p->rs;
+    p->smem = ((size_t)p->D.ncol + p->D.nx / 2 + p->D.ny / 2) * 2 * p->rs;      // one complex plane + the twiddles of both directions
     if (p->smem > 227 * 1024) { delete p; return rbc_fail("rbc3d_create: a horizontal plane of this grid does not fit the shared memory of an SM"); }
     cudaError_t e = cudaSuccess;
     if (precision == 32) {

@@ -6,6 +6,15 @@
 
 using namespace rbc3dg;
 
+// one FFT stage in the emulator: the work items one after the other (the device runs them on the threads of a CTA + barrier)
+struct SerialRun {
+    template <typename F>
+    void operator()(int n_items, F fn) const
+    {
+        for (int it = 0; it < n_items; ++it) fn(it);
+    }
+};
+
 template <typename Real>
 static void project(const Dims& D, const ConstsG<Real>& C, const HostConfigG& h, Real* P, std::vector<cx<Real>>& Z, std::vector<Real>& phi,
                     const std::vector<Real>& cp, const std::vector<cx<Real>>& twx, const std::vector<cx<Real>>& twy)
@@ -13,19 +22,13 @@ static void project(const Dims& D, const ConstsG<Real>& C, const HostConfigG& h,
     for (int k = 0; k < D.nz; ++k) {                                  // g3_div_fft_kernel: one "CTA" per level
         cx<Real>* Zk = Z.data() + (size_t)k * D.ncol;
         for (int c = 0; c < D.ncol; ++c) Zk[c] = cx<Real>{cell_divergence<Real>(D, C, P, c % D.nx, c / D.nx, k), Real(0)};
-        for (int span = D.nx >> 1; span >= 1; span >>= 1)
-            for (int it = 0; it < D.ny * (D.nx >> 1); ++it) butterfly_dif<Real>(Zk, D.nx, span, D.nx, 1, twx.data(), it);
-        for (int span = D.ny >> 1; span >= 1; span >>= 1)
-            for (int it = 0; it < D.nx * (D.ny >> 1); ++it) butterfly_dif<Real>(Zk, D.ny, span, 1, D.nx, twy.data(), it);
+        plane_fft_forward<Real>(D, Zk, twx.data(), twy.data(), SerialRun{});
     }
     const Real dz = (Real)(h.lz / D.nz);
     for (int m = 0; m < D.ncol; ++m) mode_thomas<Real>(D, Z.data(), cp.data(), dz * dz, m);      // g3_thomas_kernel
     for (int k = 0; k < D.nz; ++k) {                                  // g3_ifft_kernel
         cx<Real>* Zk = Z.data() + (size_t)k * D.ncol;
-        for (int span = 1; span <= (D.ny >> 1); span <<= 1)
-            for (int it = 0; it < D.nx * (D.ny >> 1); ++it) butterfly_dit_inv<Real>(Zk, D.ny, span, 1, D.nx, twy.data(), it);
-        for (int span = 1; span <= (D.nx >> 1); span <<= 1)
-            for (int it = 0; it < D.ny * (D.nx >> 1); ++it) butterfly_dit_inv<Real>(Zk, D.nx, span, D.nx, 1, twx.data(), it);
+        plane_fft_inverse<Real>(D, Zk, twx.data(), twy.data(), SerialRun{});
         for (int c = 0; c < D.ncol; ++c) phi[(size_t)k * D.ncol + c] = Zk[c].re * (Real(1) / (Real)D.ncol);
     }
     for (int cell = 0; cell < D.nc; ++cell) cell_correct<Real>(D, C, P, phi.data(), cell);       // g3_correct_kernel
