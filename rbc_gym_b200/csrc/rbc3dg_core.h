@@ -110,40 +110,43 @@ RBC_HD void cell_tendency(const Dims& D, const ConstsG<Real>& C, Real nu, Real k
                           const Real* RBC_RESTRICT Tb, int cell, Real dt, Real gam, Real zet, bool use_prev, bool store_g)
 {
     const int nx = D.nx, ny = D.ny, nz = D.nz, ncol = D.ncol;
-    const int i = cell % nx, j = (cell / nx) % ny, k = cell / ncol;
-    int xo[7], yo[7], zc[7], zw[7];
+    const int i = cell & (nx - 1), j = (cell >> D.lx2) & (ny - 1), k = cell >> (D.lx2 + D.ly2);      // nx, ny are powers of two
+    // element offsets inside one field: x- and y-windows on level k, z-windows through the column; 32-bit, shared by all fields
+    int xo[7], yo[7], ox[7], oy[7], ozc[7], ozw[7];
+    const int lev = k * ncol, colz = j * nx + i;
     RBC_UNROLL
     for (int d = 0; d < 7; ++d) {
-        int ii = i + d - 3, jj = j + d - 3, kk = k + d - 3;
-        ii = ii < 0 ? ii + nx : (ii >= nx ? ii - nx : ii);
-        jj = jj < 0 ? jj + ny : (jj >= ny ? jj - ny : jj);
-        xo[d] = ii; yo[d] = jj * nx;
-        zc[d] = (kk < 0 ? 0 : (kk > nz - 1 ? nz - 1 : kk)) * ncol;      // cell-centred fields: nz levels
-        zw[d] = (kk < 0 ? 0 : (kk > nz ? nz : kk)) * ncol;              // w: nz + 1 faces
+        const int kk = k + d - 3;
+        xo[d] = (i + d - 3) & (nx - 1);
+        yo[d] = ((j + d - 3) & (ny - 1)) << D.lx2;
+        ox[d] = lev + (j << D.lx2) + xo[d];
+        oy[d] = lev + yo[d] + i;
+        ozc[d] = (kk < 0 ? 0 : (kk > nz - 1 ? nz - 1 : kk)) * ncol + colz;      // cell-centred fields: nz levels
+        ozw[d] = (kk < 0 ? 0 : (kk > nz ? nz : kk)) * ncol + colz;              // w: nz + 1 faces
     }
     const Real* RBC_RESTRICT pb = S + D.gb;
     const Real* RBC_RESTRICT pu = S + D.gu;
     const Real* RBC_RESTRICT pv = S + D.gv;
     const Real* RBC_RESTRICT pw = S + D.gw;
-    const int row = zc[3] + yo[3], colz = yo[3] + xo[3], lev = zc[3];  // zc[3] == zw[3] == k * ncol
     Real bx[7], by[7], bz[7], ux[7], uy[7], uz[7], vx[7], vy[7], vz[7], wx[7], wy[7], wz[7];
     RBC_UNROLL
     for (int d = 0; d < 7; ++d) {
-        bx[d] = pb[row + xo[d]]; by[d] = pb[lev + yo[d] + xo[3]]; bz[d] = pb[zc[d] + colz];
-        ux[d] = pu[row + xo[d]]; uy[d] = pu[lev + yo[d] + xo[3]]; uz[d] = pu[zc[d] + colz];
-        vx[d] = pv[row + xo[d]]; vy[d] = pv[lev + yo[d] + xo[3]]; vz[d] = pv[zc[d] + colz];
-        wx[d] = pw[row + xo[d]]; wy[d] = pw[lev + yo[d] + xo[3]]; wz[d] = pw[zw[d] + colz];
+        bx[d] = pb[ox[d]]; by[d] = pb[oy[d]]; bz[d] = pb[ozc[d]];
+        ux[d] = pu[ox[d]]; uy[d] = pu[oy[d]]; uz[d] = pu[ozc[d]];
+        vx[d] = pv[ox[d]]; vy[d] = pv[oy[d]]; vz[d] = pv[ozc[d]];
+        wx[d] = pw[ox[d]]; wy[d] = pw[oy[d]]; wz[d] = pw[ozw[d]];
     }
     // advecting-velocity rows of the far faces: slot q <-> offset q - 2 along the interpolation direction
     Real v_jp[4], u_ip[4], w_kp_x[4], w_kp_y[4], u_ip_z[4], v_jp_z[4];
+    const int up1 = ozw[4] - colz;                                   // level offset of face k + 1 (<= nz: always there)
     RBC_UNROLL
     for (int q = 0; q < 4; ++q) {
-        v_jp[q] = pv[lev + yo[4] + xo[q + 1]];          // v(i-2..i+1, j+1, k)    -> u-flux through the y-face j+1
-        u_ip[q] = pu[lev + yo[q + 1] + xo[4]];          // u(i+1, j-2..j+1, k)    -> v-flux through the x-face i+1
-        w_kp_x[q] = pw[zw[4] + yo[3] + xo[q + 1]];      // w(i-2..i+1, j, k+1)    -> u-flux through the z-face k+1
-        w_kp_y[q] = pw[zw[4] + yo[q + 1] + xo[3]];      // w(i, j-2..j+1, k+1)    -> v-flux through the z-face k+1
-        u_ip_z[q] = pu[zc[q + 1] + yo[3] + xo[4]];      // u(i+1, j, k-2..k+1)    -> w-flux through the x-face i+1
-        v_jp_z[q] = pv[zc[q + 1] + yo[4] + xo[3]];      // v(i, j+1, k-2..k+1)    -> w-flux through the y-face j+1
+        v_jp[q] = pv[lev + yo[4] + xo[q + 1]];                       // v(i-2..i+1, j+1, k)    -> u-flux through the y-face j+1
+        u_ip[q] = pu[lev + yo[q + 1] + xo[4]];                       // u(i+1, j-2..j+1, k)    -> v-flux through the x-face i+1
+        w_kp_x[q] = pw[ox[q + 1] - lev + up1];                       // w(i-2..i+1, j, k+1)    -> u-flux through the z-face k+1
+        w_kp_y[q] = pw[oy[q + 1] - lev + up1];                       // w(i, j-2..j+1, k+1)    -> v-flux through the z-face k+1
+        u_ip_z[q] = pu[ozc[q + 1] - colz + (j << D.lx2) + xo[4]];    // u(i+1, j, k-2..k+1)    -> w-flux through the x-face i+1
+        v_jp_z[q] = pv[ozc[q + 1] - colz + yo[4] + i];               // v(i, j+1, k-2..k+1)    -> w-flux through the y-face j+1
     }
     const int of0 = (k >= 1) ? o_up_face(k, nz) : 0, of1 = (k + 1 <= nz - 1) ? o_up_face(k + 1, nz) : 0;
     const Real b0 = bx[3], u0 = ux[3], v0 = vx[3], w0 = wx[3];
