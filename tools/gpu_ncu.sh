@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary --envs-per-gpu ${1:-4096}"
 echo "== plain"; timeout 600 $CMD > gpurun_out/plain.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 tail -1 gpurun_out/plain.log | cut -c1-300; tail -2 gpurun_out/ncu_list.log | cut -c1-300
 echo "== ncu full"
 timeout 600 $CMD > gpurun_out/plain2.log 2>&1 &&
