@@ -105,6 +105,98 @@ RBC_HD double heater_patch_T(int heaters, double heater_limit, double b_hot, con
 // wrapping accessor for every stencil point (~7 400 instructions per cell, 1.67 ms per 64-environment stage at 64 x 64 x 32).
 // Window index d <-> offset d - 3 from the cell; a face "m-1 | m" along a direction uses slots m .. m + 5 of that window.
 // ------------------------------------------------------------------------------------------
+// the register windows of one cell (scalarised by the compiler once everything is inlined)
+template <typename Real>
+struct Windows {
+    Real bx[7], by[7], bz[7], ux[7], uy[7], uz[7], vx[7], vy[7], vz[7], wx[7], wy[7], wz[7];
+    // advecting-velocity rows of the far faces: slot q <-> offset q - 2 along the interpolation direction
+    Real v_jp[4];       // v(i-2..i+1, j+1, k)    -> u-flux through the y-face j+1
+    Real u_ip[4];       // u(i+1, j-2..j+1, k)    -> v-flux through the x-face i+1
+    Real w_kp_x[4];     // w(i-2..i+1, j, k+1)    -> u-flux through the z-face k+1
+    Real w_kp_y[4];     // w(i, j-2..j+1, k+1)    -> v-flux through the z-face k+1
+    Real u_ip_z[4];     // u(i+1, j, k-2..k+1)    -> w-flux through the x-face i+1
+    Real v_jp_z[4];     // v(i, j+1, k-2..k+1)    -> w-flux through the y-face j+1
+};
+template <typename Real>
+struct Tend {
+    Real b, u, v, w;
+};
+// the four tendencies of the cell at level k from its windows (tb = heater temperature below the column, read at k = 0 only)
+template <typename Real>
+RBC_HD Tend<Real> tendency_from_windows(const ConstsG<Real>& C, Real nu, Real kappa, int nz, int k, const Windows<Real>& W, Real tb)
+{
+    const Real *bx = W.bx, *by = W.by, *bz = W.bz, *ux = W.ux, *uy = W.uy, *uz = W.uz, *vx = W.vx, *vy = W.vy, *vz = W.vz, *wx = W.wx, *wy = W.wy, *wz = W.wz;
+    const int of0 = (k >= 1) ? o_up_face(k, nz) : 0, of1 = (k + 1 <= nz - 1) ? o_up_face(k + 1, nz) : 0;
+    const Real b0 = bx[3], u0 = ux[3], v0 = vx[3], w0 = wx[3];
+    Tend<Real> g;
+    g.w = Real(0);
+    {   // tracer: the advecting velocity is the face value itself
+        const Real Fx0 = upwind_ord(u0, bx, 5), Fx1 = upwind_ord(ux[4], bx + 1, 5);
+        const Real Fy0 = upwind_ord(v0, by, 5), Fy1 = upwind_ord(vy[4], by + 1, 5);
+        const Real Fz0 = of0 ? upwind_ord(w0, bz, of0) : Real(0);
+        const Real Fz1 = of1 ? upwind_ord(wz[4], bz + 1, of1) : Real(0);
+        const Real bdn = (k == 0) ? Real(2) * tb - b0 : bz[2];
+        const Real bup = (k == nz - 1) ? Real(2) * C.b_top - b0 : bz[4];
+        const Real lap = (bx[4] - Real(2) * b0 + bx[2]) * C.idx2 + (by[4] - Real(2) * b0 + by[2]) * C.idy2 + (bup - Real(2) * b0 + bdn) * C.idz2;
+        g.b = -((Fx1 - Fx0) * C.idx + (Fy1 - Fy0) * C.idy + (Fz1 - Fz0) * C.idz) + kappa * lap;
+    }
+    {   // u at (x-face i, j, k)
+        const Real F0 = upwind_ord(centred_ord(ux[1], ux[2], ux[3], ux[4], 4), ux, 5);
+        const Real F1 = upwind_ord(centred_ord(ux[2], ux[3], ux[4], ux[5], 4), ux + 1, 5);
+        const Real G0 = upwind_ord(centred_ord(vx[1], vx[2], vx[3], vx[4], 4), uy, 5);
+        const Real G1 = upwind_ord(centred_ord(W.v_jp[0], W.v_jp[1], W.v_jp[2], W.v_jp[3], 4), uy + 1, 5);
+        const Real H0 = of0 ? upwind_ord(centred_ord(wx[1], wx[2], wx[3], wx[4], 4), uz, of0) : Real(0);
+        const Real H1 = of1 ? upwind_ord(centred_ord(W.w_kp_x[0], W.w_kp_x[1], W.w_kp_x[2], W.w_kp_x[3], 4), uz + 1, of1) : Real(0);
+        const Real dn = (k == 0) ? -u0 : uz[2], up = (k == nz - 1) ? -u0 : uz[4];
+        const Real lap = (ux[4] - Real(2) * u0 + ux[2]) * C.idx2 + (uy[4] - Real(2) * u0 + uy[2]) * C.idy2 + (up - Real(2) * u0 + dn) * C.idz2;
+        g.u = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
+    }
+    {   // v at (i, y-face j, k)
+        const Real F0 = upwind_ord(centred_ord(uy[1], uy[2], uy[3], uy[4], 4), vx, 5);
+        const Real F1 = upwind_ord(centred_ord(W.u_ip[0], W.u_ip[1], W.u_ip[2], W.u_ip[3], 4), vx + 1, 5);
+        const Real G0 = upwind_ord(centred_ord(vy[1], vy[2], vy[3], vy[4], 4), vy, 5);
+        const Real G1 = upwind_ord(centred_ord(vy[2], vy[3], vy[4], vy[5], 4), vy + 1, 5);
+        const Real H0 = of0 ? upwind_ord(centred_ord(wy[1], wy[2], wy[3], wy[4], 4), vz, of0) : Real(0);
+        const Real H1 = of1 ? upwind_ord(centred_ord(W.w_kp_y[0], W.w_kp_y[1], W.w_kp_y[2], W.w_kp_y[3], 4), vz + 1, of1) : Real(0);
+        const Real dn = (k == 0) ? -v0 : vz[2], up = (k == nz - 1) ? -v0 : vz[4];
+        const Real lap = (vx[4] - Real(2) * v0 + vx[2]) * C.idx2 + (vy[4] - Real(2) * v0 + vy[2]) * C.idy2 + (up - Real(2) * v0 + dn) * C.idz2;
+        g.v = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
+    }
+    if (k >= 1) {   // w at (i, j, z-face k), interior faces only
+        const int oc = o_ce_face(k, nz);
+        const Real F0 = upwind_ord(centred_ord(uz[1], uz[2], uz[3], uz[4], oc), wx, 5);
+        const Real F1 = upwind_ord(centred_ord(W.u_ip_z[0], W.u_ip_z[1], W.u_ip_z[2], W.u_ip_z[3], oc), wx + 1, 5);
+        const Real G0 = upwind_ord(centred_ord(vz[1], vz[2], vz[3], vz[4], oc), wy, 5);
+        const Real G1 = upwind_ord(centred_ord(W.v_jp_z[0], W.v_jp_z[1], W.v_jp_z[2], W.v_jp_z[3], oc), wy + 1, 5);
+        const Real H0 = upwind_ord(centred_ord(wz[1], wz[2], wz[3], wz[4], o_ce_cen(k - 1, nz)), wz, o_up_cen(k - 1, nz));
+        const Real H1 = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen(k, nz)), wz + 1, o_up_cen(k, nz));
+        const Real lap = (wx[4] - Real(2) * w0 + wx[2]) * C.idx2 + (wy[4] - Real(2) * w0 + wy[2]) * C.idy2 + (wz[4] - Real(2) * w0 + wz[2]) * C.idz2;
+        g.w = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap + Real(0.5) * (bz[2] + b0);
+    }
+    return g;
+}
+// U* = U + dt (gamma G + zeta G-); G- <- G.  `cell` = index inside a field.  The previous-stage tendencies are fetched by the
+// caller BEFORE it gathers its windows (load_prev), so that their latency hides behind the whole flux evaluation.
+template <typename Real>
+RBC_HD Tend<Real> load_prev(const Dims& D, const Real* G, int cell, bool use_prev)
+{
+    Tend<Real> p{Real(0), Real(0), Real(0), Real(0)};
+    if (use_prev) { p.b = G[cell]; p.u = G[D.nc + cell]; p.v = G[2 * D.nc + cell]; p.w = G[3 * D.nc + cell]; }
+    return p;
+}
+template <typename Real>
+RBC_HD void rk3_substep_store(const Dims& D, Real* P, Real* G, int cell, int colz, int k, const Windows<Real>& W, const Tend<Real>& g,
+                              const Tend<Real>& prev, Real dt, Real gam, Real zet, bool store_g)
+{
+    P[D.gb + cell] = W.bx[3] + dt * (gam * g.b + zet * prev.b);
+    P[D.gu + cell] = W.ux[3] + dt * (gam * g.u + zet * prev.u);
+    P[D.gv + cell] = W.vx[3] + dt * (gam * g.v + zet * prev.v);
+    P[D.gw + cell] = (k >= 1) ? W.wx[3] + dt * (gam * g.w + zet * prev.w) : Real(0);
+    if (k == D.nz - 1) P[D.gw + D.nc + colz] = Real(0);              // top wall face
+    if (store_g) { G[cell] = g.b; G[D.nc + cell] = g.u; G[2 * D.nc + cell] = g.v; G[3 * D.nc + cell] = g.w; }
+}
+
+// one thread (work item) per cell, every window gathered from global memory
 template <typename Real>
 RBC_HD void cell_tendency(const Dims& D, const ConstsG<Real>& C, Real nu, Real kappa, const Real* RBC_RESTRICT S, Real* P, Real* G,
                           const Real* RBC_RESTRICT Tb, int cell, Real dt, Real gam, Real zet, bool use_prev, bool store_g)
@@ -128,81 +220,27 @@ RBC_HD void cell_tendency(const Dims& D, const ConstsG<Real>& C, Real nu, Real k
     const Real* RBC_RESTRICT pu = S + D.gu;
     const Real* RBC_RESTRICT pv = S + D.gv;
     const Real* RBC_RESTRICT pw = S + D.gw;
-    Real bx[7], by[7], bz[7], ux[7], uy[7], uz[7], vx[7], vy[7], vz[7], wx[7], wy[7], wz[7];
+    const Tend<Real> prev = load_prev<Real>(D, G, cell, use_prev);
+    Windows<Real> W;
     RBC_UNROLL
     for (int d = 0; d < 7; ++d) {
-        bx[d] = pb[ox[d]]; by[d] = pb[oy[d]]; bz[d] = pb[ozc[d]];
-        ux[d] = pu[ox[d]]; uy[d] = pu[oy[d]]; uz[d] = pu[ozc[d]];
-        vx[d] = pv[ox[d]]; vy[d] = pv[oy[d]]; vz[d] = pv[ozc[d]];
-        wx[d] = pw[ox[d]]; wy[d] = pw[oy[d]]; wz[d] = pw[ozw[d]];
+        W.bx[d] = pb[ox[d]]; W.by[d] = pb[oy[d]]; W.bz[d] = pb[ozc[d]];
+        W.ux[d] = pu[ox[d]]; W.uy[d] = pu[oy[d]]; W.uz[d] = pu[ozc[d]];
+        W.vx[d] = pv[ox[d]]; W.vy[d] = pv[oy[d]]; W.vz[d] = pv[ozc[d]];
+        W.wx[d] = pw[ox[d]]; W.wy[d] = pw[oy[d]]; W.wz[d] = pw[ozw[d]];
     }
-    // advecting-velocity rows of the far faces: slot q <-> offset q - 2 along the interpolation direction
-    Real v_jp[4], u_ip[4], w_kp_x[4], w_kp_y[4], u_ip_z[4], v_jp_z[4];
     const int up1 = ozw[4] - colz;                                   // level offset of face k + 1 (<= nz: always there)
     RBC_UNROLL
     for (int q = 0; q < 4; ++q) {
-        v_jp[q] = pv[lev + yo[4] + xo[q + 1]];                       // v(i-2..i+1, j+1, k)    -> u-flux through the y-face j+1
-        u_ip[q] = pu[lev + yo[q + 1] + xo[4]];                       // u(i+1, j-2..j+1, k)    -> v-flux through the x-face i+1
-        w_kp_x[q] = pw[ox[q + 1] - lev + up1];                       // w(i-2..i+1, j, k+1)    -> u-flux through the z-face k+1
-        w_kp_y[q] = pw[oy[q + 1] - lev + up1];                       // w(i, j-2..j+1, k+1)    -> v-flux through the z-face k+1
-        u_ip_z[q] = pu[ozc[q + 1] - colz + (j << D.lx2) + xo[4]];    // u(i+1, j, k-2..k+1)    -> w-flux through the x-face i+1
-        v_jp_z[q] = pv[ozc[q + 1] - colz + yo[4] + i];               // v(i, j+1, k-2..k+1)    -> w-flux through the y-face j+1
+        W.v_jp[q] = pv[lev + yo[4] + xo[q + 1]];
+        W.u_ip[q] = pu[lev + yo[q + 1] + xo[4]];
+        W.w_kp_x[q] = pw[ox[q + 1] - lev + up1];
+        W.w_kp_y[q] = pw[oy[q + 1] - lev + up1];
+        W.u_ip_z[q] = pu[ozc[q + 1] - colz + (j << D.lx2) + xo[4]];
+        W.v_jp_z[q] = pv[ozc[q + 1] - colz + yo[4] + i];
     }
-    const int of0 = (k >= 1) ? o_up_face(k, nz) : 0, of1 = (k + 1 <= nz - 1) ? o_up_face(k + 1, nz) : 0;
-    const Real b0 = bx[3], u0 = ux[3], v0 = vx[3], w0 = wx[3];
-    Real gb, gu, gv, gw = Real(0);
-    {   // tracer: the advecting velocity is the face value itself
-        const Real Fx0 = upwind_ord(u0, bx, 5), Fx1 = upwind_ord(ux[4], bx + 1, 5);
-        const Real Fy0 = upwind_ord(v0, by, 5), Fy1 = upwind_ord(vy[4], by + 1, 5);
-        const Real Fz0 = of0 ? upwind_ord(w0, bz, of0) : Real(0);
-        const Real Fz1 = of1 ? upwind_ord(wz[4], bz + 1, of1) : Real(0);
-        const Real bdn = (k == 0) ? Real(2) * Tb[j * nx + i] - b0 : bz[2];
-        const Real bup = (k == nz - 1) ? Real(2) * C.b_top - b0 : bz[4];
-        const Real lap = (bx[4] - Real(2) * b0 + bx[2]) * C.idx2 + (by[4] - Real(2) * b0 + by[2]) * C.idy2 + (bup - Real(2) * b0 + bdn) * C.idz2;
-        gb = -((Fx1 - Fx0) * C.idx + (Fy1 - Fy0) * C.idy + (Fz1 - Fz0) * C.idz) + kappa * lap;
-    }
-    {   // u at (x-face i, j, k)
-        const Real F0 = upwind_ord(centred_ord(ux[1], ux[2], ux[3], ux[4], 4), ux, 5);
-        const Real F1 = upwind_ord(centred_ord(ux[2], ux[3], ux[4], ux[5], 4), ux + 1, 5);
-        const Real G0 = upwind_ord(centred_ord(vx[1], vx[2], vx[3], vx[4], 4), uy, 5);
-        const Real G1 = upwind_ord(centred_ord(v_jp[0], v_jp[1], v_jp[2], v_jp[3], 4), uy + 1, 5);
-        const Real H0 = of0 ? upwind_ord(centred_ord(wx[1], wx[2], wx[3], wx[4], 4), uz, of0) : Real(0);
-        const Real H1 = of1 ? upwind_ord(centred_ord(w_kp_x[0], w_kp_x[1], w_kp_x[2], w_kp_x[3], 4), uz + 1, of1) : Real(0);
-        const Real dn = (k == 0) ? -u0 : uz[2], up = (k == nz - 1) ? -u0 : uz[4];
-        const Real lap = (ux[4] - Real(2) * u0 + ux[2]) * C.idx2 + (uy[4] - Real(2) * u0 + uy[2]) * C.idy2 + (up - Real(2) * u0 + dn) * C.idz2;
-        gu = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
-    }
-    {   // v at (i, y-face j, k)
-        const Real F0 = upwind_ord(centred_ord(uy[1], uy[2], uy[3], uy[4], 4), vx, 5);
-        const Real F1 = upwind_ord(centred_ord(u_ip[0], u_ip[1], u_ip[2], u_ip[3], 4), vx + 1, 5);
-        const Real G0 = upwind_ord(centred_ord(vy[1], vy[2], vy[3], vy[4], 4), vy, 5);
-        const Real G1 = upwind_ord(centred_ord(vy[2], vy[3], vy[4], vy[5], 4), vy + 1, 5);
-        const Real H0 = of0 ? upwind_ord(centred_ord(wy[1], wy[2], wy[3], wy[4], 4), vz, of0) : Real(0);
-        const Real H1 = of1 ? upwind_ord(centred_ord(w_kp_y[0], w_kp_y[1], w_kp_y[2], w_kp_y[3], 4), vz + 1, of1) : Real(0);
-        const Real dn = (k == 0) ? -v0 : vz[2], up = (k == nz - 1) ? -v0 : vz[4];
-        const Real lap = (vx[4] - Real(2) * v0 + vx[2]) * C.idx2 + (vy[4] - Real(2) * v0 + vy[2]) * C.idy2 + (up - Real(2) * v0 + dn) * C.idz2;
-        gv = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
-    }
-    if (k >= 1) {   // w at (i, j, z-face k), interior faces only
-        const int oc = o_ce_face(k, nz);
-        const Real F0 = upwind_ord(centred_ord(uz[1], uz[2], uz[3], uz[4], oc), wx, 5);
-        const Real F1 = upwind_ord(centred_ord(u_ip_z[0], u_ip_z[1], u_ip_z[2], u_ip_z[3], oc), wx + 1, 5);
-        const Real G0 = upwind_ord(centred_ord(vz[1], vz[2], vz[3], vz[4], oc), wy, 5);
-        const Real G1 = upwind_ord(centred_ord(v_jp_z[0], v_jp_z[1], v_jp_z[2], v_jp_z[3], oc), wy + 1, 5);
-        const Real H0 = upwind_ord(centred_ord(wz[1], wz[2], wz[3], wz[4], o_ce_cen(k - 1, nz)), wz, o_up_cen(k - 1, nz));
-        const Real H1 = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen(k, nz)), wz + 1, o_up_cen(k, nz));
-        const Real lap = (wx[4] - Real(2) * w0 + wx[2]) * C.idx2 + (wy[4] - Real(2) * w0 + wy[2]) * C.idy2 + (wz[4] - Real(2) * w0 + wz[2]) * C.idz2;
-        gw = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap + Real(0.5) * (bz[2] + b0);
-    }
-    // U* = U + dt (gamma G + zeta G-); G- <- G
-    Real pb_ = Real(0), pu_ = Real(0), pv_ = Real(0), pw_ = Real(0);
-    if (use_prev) { pb_ = G[cell]; pu_ = G[D.nc + cell]; pv_ = G[2 * D.nc + cell]; pw_ = G[3 * D.nc + cell]; }
-    P[D.gb + cell] = b0 + dt * (gam * gb + zet * pb_);
-    P[D.gu + cell] = u0 + dt * (gam * gu + zet * pu_);
-    P[D.gv + cell] = v0 + dt * (gam * gv + zet * pv_);
-    P[D.gw + cell] = (k >= 1) ? w0 + dt * (gam * gw + zet * pw_) : Real(0);
-    if (k == nz - 1) P[D.gw + D.nc + j * nx + i] = Real(0);          // top wall face
-    if (store_g) { G[cell] = gb; G[D.nc + cell] = gu; G[2 * D.nc + cell] = gv; G[3 * D.nc + cell] = gw; }
+    const Tend<Real> g = tendency_from_windows<Real>(C, nu, kappa, nz, k, W, (k == 0) ? Tb[colz] : Real(0));
+    rk3_substep_store<Real>(D, P, G, cell, colz, k, W, g, prev, dt, gam, zet, store_g);
 }
 
 // divergence of the predicted velocity at one cell of level k (the Poisson right-hand side; the 1/dtau of the

@@ -3,6 +3,7 @@
 // 64 x 64 x 32 environment already fills the GPU with 131 072 threads per launch.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,141 @@ g3_tendency_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real* kapp
     if (cell >= D.nc) return;
     cell_tendency<Real>(D, C, nu_env[env], kappa_env[env], S_all + (size_t)env * D.nstate, P_all + (size_t)env * D.nstate,
                         G_all + (size_t)env * 4 * D.nc, Tb_all + (size_t)env * D.ncol, cell, dt, gam, zet, use_prev != 0, store_g != 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tiled tendency (grids with nx % 32 == 0, ny % 16 == 0).  A CTA owns a 32 x 16 patch of columns and marches it up through the
+// levels: one thread per column, the z-windows of its own column slide through registers (one coalesced global load per field
+// and level), and everything it needs from its neighbours comes from a RING OF THREE LEVEL PLANES WITH HALO in shared memory
+// (38 x 22 values per field: the periodic wrap is resolved once, when a thread computes which element of a plane it copies),
+// so every stencil access of the march is a shared-memory load at a compile-time offset from the thread's own slot.  Level k
+// reads planes k and k + 1; plane k + 3 is copied meanwhile (cp.async, no register staging, two copy groups in flight); one
+// CTA barrier per level.  Same arithmetic as the per-cell kernel (tendency_from_windows), 1 480 -> 880 instructions per cell.
+// ------------------------------------------------------------------------------------------
+constexpr int TT_X = 32, TT_PW = 40;                   // patch width; padded plane row (38 used)
+template <int TT_Y>
+struct TileGeom {
+    static constexpr int NT = TT_X * TT_Y;             // threads
+    static constexpr int PH = TT_Y + 6;                // plane rows
+    static constexpr int PLANE = TT_PW * PH, SLOT = 4 * PLANE;
+    static constexpr int NE = (TT_X + 6) * PH;         // elements of one field plane a CTA copies
+    static constexpr int NQ = (NE + NT - 1) / NT;
+};
+
+template <typename Real>
+__device__ __forceinline__ void async_copy_value(Real* dst_shared, const Real* src_global)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
+    if (sizeof(Real) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src_global) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
+}
+
+// fp32: 128 registers per thread, i.e. 512 resident threads per SM — one 16-row CTA or two 8-row CTAs that hide each other's
+// barriers and copy waits; fp64 needs ~240 registers and runs one CTA per SM
+template <typename Real, int TT_Y>
+__global__ void __launch_bounds__(TT_X * TT_Y, sizeof(Real) == 4 ? 512 / (TT_X * TT_Y) : 1)
+g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real* kappa_env, const Real* S_all, Real* P_all, Real* G_all,
+                         const Real* Tb_all, const int* env_ids, Real dt, Real gam, Real zet, int use_prev, int store_g)
+{
+    constexpr int TT_NT = TileGeom<TT_Y>::NT, TT_PLANE = TileGeom<TT_Y>::PLANE, TT_SLOT = TileGeom<TT_Y>::SLOT, TT_NE = TileGeom<TT_Y>::NE,
+                  TT_NQ = TileGeom<TT_Y>::NQ;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Real* ring = reinterpret_cast<Real*>(smem_raw);
+    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    const int nx = D.nx, ny = D.ny, nz = D.nz, ncol = D.ncol;
+    const int tiles_x = nx / TT_X;
+    const int x0 = (blockIdx.x % tiles_x) * TT_X, y0 = (blockIdx.x / tiles_x) * TT_Y;
+    const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+    const int i = x0 + lx, j = y0 + ly, colz = j * nx + i;
+    const Real* __restrict__ S = S_all + (size_t)env * D.nstate;
+    Real* P = P_all + (size_t)env * D.nstate;
+    Real* G = G_all + (size_t)env * 4 * D.nc;
+    const Real nu = nu_env[env], kappa = kappa_env[env];
+    const Real tb = Tb_all[(size_t)env * ncol + colz];
+
+    // which elements of a plane this thread copies: global column (wrapped) and slot inside the padded plane
+    int goff[TT_NQ], soff[TT_NQ];
+#pragma unroll
+    for (int q = 0; q < TT_NQ; ++q) {
+        const int e = tid + q * TT_NT;
+        const int pr = e / (TT_X + 6), pc = e % (TT_X + 6);
+        goff[q] = e < TT_NE ? (((y0 - 3 + pr) & (ny - 1)) * nx + ((x0 - 3 + pc) & (nx - 1))) : -1;
+        soff[q] = pr * TT_PW + pc;
+    }
+    auto copy_plane = [&](int level) {                        // level <= nz: w has a face there, the cell-centred fields do not
+        Real* slot = ring + (level & 3) * TT_SLOT;
+        const int lo = level * ncol;
+#pragma unroll
+        for (int q = 0; q < TT_NQ; ++q) {
+            if (goff[q] >= 0) {
+                if (level < nz) {
+                    async_copy_value(slot + soff[q], S + D.gb + lo + goff[q]);
+                    async_copy_value(slot + TT_PLANE + soff[q], S + D.gu + lo + goff[q]);
+                    async_copy_value(slot + 2 * TT_PLANE + soff[q], S + D.gv + lo + goff[q]);
+                }
+                async_copy_value(slot + 3 * TT_PLANE + soff[q], S + D.gw + lo + goff[q]);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    copy_plane(0);
+    copy_plane(1);
+    if (2 <= nz) copy_plane(2); else asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // z-windows of the own column for level 0 (slot d <-> level d - 3, clamped like the per-cell kernel)
+    Windows<Real> W;
+#pragma unroll
+    for (int d = 0; d < 7; ++d) {
+        const int kc = d - 3 < 0 ? 0 : (d - 3 > nz - 1 ? nz - 1 : d - 3), kw = d - 3 < 0 ? 0 : (d - 3 > nz ? nz : d - 3);
+        W.bz[d] = S[D.gb + kc * ncol + colz]; W.uz[d] = S[D.gu + kc * ncol + colz]; W.vz[d] = S[D.gv + kc * ncol + colz];
+        W.wz[d] = S[D.gw + kw * ncol + colz];
+    }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");        // planes 0 and 1 are in
+    __syncthreads();
+    const int p0 = (ly + 3) * TT_PW + lx + 3;
+    {   // neighbour-column z-windows: slots 0..2 <-> levels -2, -1, 0 (all level 0 after the clamp; slot 3 is filled per level)
+        const Real* s0 = ring;
+        const Real un = s0[TT_PLANE + p0 + 1], vn = s0[2 * TT_PLANE + p0 + TT_PW];
+        W.u_ip_z[0] = un; W.u_ip_z[1] = un; W.u_ip_z[2] = un; W.u_ip_z[3] = un;
+        W.v_jp_z[0] = vn; W.v_jp_z[1] = vn; W.v_jp_z[2] = vn; W.v_jp_z[3] = vn;
+    }
+
+    for (int k = 0; k < nz; ++k) {
+        if (k + 3 <= nz) copy_plane(k + 3);                   // its slot held plane k - 1: everybody is past it
+        else asm volatile("cp.async.commit_group;" ::: "memory");      // keep one group per level so that wait_group 1 means "plane k + 2"
+        const Tend<Real> prev = load_prev<Real>(D, G, k * ncol + colz, use_prev != 0);
+        const Real* s0 = ring + (k & 3) * TT_SLOT;
+        const Real* s1 = ring + ((k + 1) & 3) * TT_SLOT;
+#pragma unroll
+        for (int d = 0; d < 7; ++d) {
+            W.bx[d] = s0[p0 + d - 3]; W.by[d] = s0[p0 + (d - 3) * TT_PW];
+            W.ux[d] = s0[TT_PLANE + p0 + d - 3]; W.uy[d] = s0[TT_PLANE + p0 + (d - 3) * TT_PW];
+            W.vx[d] = s0[2 * TT_PLANE + p0 + d - 3]; W.vy[d] = s0[2 * TT_PLANE + p0 + (d - 3) * TT_PW];
+            W.wx[d] = s0[3 * TT_PLANE + p0 + d - 3]; W.wy[d] = s0[3 * TT_PLANE + p0 + (d - 3) * TT_PW];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            W.v_jp[q] = s0[2 * TT_PLANE + p0 + TT_PW + q - 2];
+            W.u_ip[q] = s0[TT_PLANE + p0 + 1 + (q - 2) * TT_PW];
+            W.w_kp_x[q] = s1[3 * TT_PLANE + p0 + q - 2];
+            W.w_kp_y[q] = s1[3 * TT_PLANE + p0 + (q - 2) * TT_PW];
+        }
+        if (k + 1 < nz) { W.u_ip_z[3] = s1[TT_PLANE + p0 + 1]; W.v_jp_z[3] = s1[2 * TT_PLANE + p0 + TT_PW]; }
+        const Tend<Real> g = tendency_from_windows<Real>(C, nu, kappa, nz, k, W, tb);
+        rk3_substep_store<Real>(D, P, G, k * ncol + colz, colz, k, W, g, prev, dt, gam, zet, store_g != 0);
+        // slide the register windows up one level
+#pragma unroll
+        for (int d = 0; d < 6; ++d) { W.bz[d] = W.bz[d + 1]; W.uz[d] = W.uz[d + 1]; W.vz[d] = W.vz[d + 1]; W.wz[d] = W.wz[d + 1]; }
+        {
+            const int kn = k + 4, kc = kn > nz - 1 ? nz - 1 : kn, kw = kn > nz ? nz : kn;
+            W.bz[6] = S[D.gb + kc * ncol + colz]; W.uz[6] = S[D.gu + kc * ncol + colz]; W.vz[6] = S[D.gv + kc * ncol + colz];
+            W.wz[6] = S[D.gw + kw * ncol + colz];
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { W.u_ip_z[q] = W.u_ip_z[q + 1]; W.v_jp_z[q] = W.v_jp_z[q + 1]; }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");    // everything but the copy issued in this iteration: plane k + 2 is in
+        __syncthreads();
+    }
 }
 
 // one FFT stage on the device: the CTA's threads stride over the butterflies, then a barrier
@@ -180,6 +316,7 @@ struct Plan {
     int B = 0, precision = 32, device = 0;
     size_t rs = 4, smem = 0;
     int fft_threads = 256;
+    int tiled = 0;               // rows of the column patch of the tiled tendency (shared-memory plane ring; nx % 32 == 0, ny % rows == 0); 0 = per-cell kernel.  RBC_B200_G3_TILED=0|8|16 overrides
     void *P = nullptr, *G = nullptr, *Z = nullptr, *phi = nullptr, *Tb = nullptr, *cp = nullptr, *twx = nullptr, *twy = nullptr;
     void *nu = nullptr, *kappa = nullptr;          // per-environment diffusivities (Real)
     double* kappa_d = nullptr;                      // the same in fp64 for the Nusselt number
@@ -249,6 +386,18 @@ int create(const HostConfigG& hc, int nx, int ny, int nz, int num_envs, int prec
         if (e == cudaSuccess) e = cudaFuncSetAttribute(g3_ifft_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
     }
     if (e != cudaSuccess) { delete p; return rbc_fail(std::string("rbc3d_create: ") + cudaGetErrorString(e)); }
+    {
+        const char* sw = getenv("RBC_B200_G3_TILED");
+        const int want = sw ? atoi(sw) : 8;       // 8 rows: two CTAs per SM hide each other's barriers and copy waits (678 vs 634 env-steps/s at 64 x 64 x 32)
+        p->tiled = (nx % TT_X != 0 || want == 0) ? 0 : ((want >= 16 && ny % 16 == 0) ? 16 : (ny % 8 == 0 ? 8 : 0));
+        if (p->tiled) {
+            const int bytes = (int)(4 * (p->tiled == 16 ? TileGeom<16>::SLOT : TileGeom<8>::SLOT) * p->rs);
+            const void* fn = precision == 32 ? (p->tiled == 16 ? (const void*)g3_tendency_tiled_kernel<float, 16> : (const void*)g3_tendency_tiled_kernel<float, 8>)
+                                             : (p->tiled == 16 ? (const void*)g3_tendency_tiled_kernel<double, 16> : (const void*)g3_tendency_tiled_kernel<double, 8>);
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (e != cudaSuccess) { delete p; return rbc_fail(std::string("rbc3d_create: ") + cudaGetErrorString(e)); }
+        }
+    }
     const size_t B = num_envs, rs = p->rs;
     const Dims& D = p->D;
     struct { void** ptr; size_t bytes; } allocs[] = {
@@ -313,8 +462,17 @@ static int launch_t(Plan* p, const IoRaw& io, const int* env_ids, int n, int nsu
     for (int sub = 0; sub < nsub; ++sub) {
         const Real dt = (sub == nsub - 1) ? C.dt_last : C.dt_full;
         for (int stage = 0; stage < 3; ++stage) {
-            g3_tendency_kernel<Real><<<gcell, TB, 0, st>>>(D, C, (const Real*)p->nu, (const Real*)p->kappa, cur, nxt, (Real*)p->G, (const Real*)p->Tb,
-                                                          env_ids, dt, gam[stage], zet[stage], stage > 0, stage < 2);
+            if (p->tiled == 16)
+                g3_tendency_tiled_kernel<Real, 16><<<dim3((D.nx / TT_X) * (D.ny / 16), n), TileGeom<16>::NT, 4 * TileGeom<16>::SLOT * sizeof(Real), st>>>(
+                    D, C, (const Real*)p->nu, (const Real*)p->kappa, cur, nxt, (Real*)p->G, (const Real*)p->Tb, env_ids, dt, gam[stage], zet[stage],
+                    stage > 0, stage < 2);
+            else if (p->tiled == 8)
+                g3_tendency_tiled_kernel<Real, 8><<<dim3((D.nx / TT_X) * (D.ny / 8), n), TileGeom<8>::NT, 4 * TileGeom<8>::SLOT * sizeof(Real), st>>>(
+                    D, C, (const Real*)p->nu, (const Real*)p->kappa, cur, nxt, (Real*)p->G, (const Real*)p->Tb, env_ids, dt, gam[stage], zet[stage],
+                    stage > 0, stage < 2);
+            else
+                g3_tendency_kernel<Real><<<gcell, TB, 0, st>>>(D, C, (const Real*)p->nu, (const Real*)p->kappa, cur, nxt, (Real*)p->G, (const Real*)p->Tb,
+                                                              env_ids, dt, gam[stage], zet[stage], stage > 0, stage < 2);
             *launches += 1;
             int rc = project_t<Real>(p, C, nxt, env_ids, n, st, launches);
             if (rc) return rc;

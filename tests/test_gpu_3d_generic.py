@@ -72,6 +72,33 @@ def test_generic_kernels_agree_with_dedicated_kernel_on_registered_grid(monkeypa
     assert rel(out["generic"][0], out["dedicated"][0]) < 1e-11 and np.allclose(out["generic"][1], out["dedicated"][1], rtol=1e-10)
 
 
+@pytest.mark.parametrize("shape", [(16, 32, 64), (32, 64, 64), (6, 16, 32)])
+def test_tiled_tendency_equals_the_per_cell_kernel(monkeypatch, shape):
+    """The tendency of the generic path has two device forms: one thread per cell gathering its windows from global memory
+    (also what the host emulator runs), and — for nx % 32 == 0, ny % 16 == 0 — a 32 x 16 patch of columns per CTA marching up
+    through a ring of level planes with halo in shared memory.  Both evaluate `tendency_from_windows` on the same values, so a
+    rollout must agree to round-off of the fused-multiply-add contraction (in practice: bit for bit), in both precisions,
+    including grids where a patch is its own periodic neighbour and the shallowest supported column (nz = 6)."""
+    import torch
+    from rbc_gym_b200 import backend
+    from rbc_gym_b200.envs import noise_initial_fields_3d
+    f = np.concatenate([noise_initial_fields_3d(np.random.default_rng(s), shape, kick=0.05) for s in range(2)])
+    a = torch.rand((2, 8, 8), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) * 2 - 1
+    for prec, tol in ((64, 1e-13), (32, 2e-6)):
+        out = {}
+        for name, sw in (("tiled", "1"), ("cell", "0")):
+            monkeypatch.setenv("RBC_B200_G3_TILED", sw)
+            sim = backend.Sim3D(2, ra=2e4, state_shape=shape, heater_duration=0.05, precision=prec)
+            sim.reset_from_fields(f, project=True)
+            for _ in range(2):
+                _, _, nu, _, nan = sim.step(a)
+            assert int(nan.sum()) == 0
+            out[name] = (sim.fields(), nu.cpu().numpy())
+            sim.close()
+        assert rel(out["tiled"][0], out["cell"][0]) < tol, (prec, rel(out["tiled"][0], out["cell"][0]))
+        assert np.allclose(out["tiled"][1], out["cell"][1], rtol=100 * tol)
+
+
 def test_vector_env_on_a_generic_grid_and_per_environment_rayleigh():
     import torch
     from rbc_gym_b200.envs import RBCVectorEnv3D
