@@ -316,29 +316,62 @@ RBC_HD void plane_fft_inverse(const Dims& D, cx<Real>* Z, const cx<Real>* twx, c
     for (int ls = 0; ls < D.lx2; ++ls) run(items, [&](int it) { butterfly_dit_inv<Real>(Z, D.lx2, ls, D.ly2, D.nx, 1, false, twx, it); });
 }
 
-// ------------------------------------------------------------------------------------------
-// tridiagonal solve in z of one horizontal mode (Neumann ends), in place on the spectral array Zs[k][plane index];
-// cp[k][plane index] are the host-built reciprocal pivots 1 / (diag_k - cp_{k-1}), scale = dz^2
-// ------------------------------------------------------------------------------------------
-template <typename Real>
-RBC_HD void mode_thomas(const Dims& D, cx<Real>* Zs, const Real* cp, Real scale, int m)
+RBC_HD int bitrev(int v, int bits)
 {
-    const int nz = D.nz, ncol = D.ncol;
-    Real dr = Real(0), di = Real(0);
-    for (int k = 0; k < nz; ++k) {
-        const Real c = cp[(size_t)k * ncol + m];
-        cx<Real> f = Zs[(size_t)k * ncol + m];
-        dr = (f.re * scale - dr) * c;
-        di = (f.im * scale - di) * c;
-        Zs[(size_t)k * ncol + m] = cx<Real>{dr, di};
+    int r = 0;
+    for (int b = 0; b < bits; ++b) r |= ((v >> b) & 1) << (bits - 1 - b);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Two levels per complex plane.  The divergence is real, so plane p of the spectral array carries level 2p in its real and level
+// 2p + 1 in its imaginary part: half the FFT planes, half the spectral traffic.  The transform Z of a + i b is A + i B with the
+// Hermitian spectra A, B of the two real planes, so the z-solve — real coefficients, one mode at a time — separates them through
+// the pair of positions holding the wavenumbers m and -m:
+//     A(m) = (Z(m) + conj Z(-m)) / 2,      B(m) = (Z(m) - conj Z(-m)) / (2 i),
+// solves  T x = scale * F  for the complex column x_k(m), k = 0 .. nz-1 (Neumann ends; cp[k][position] are the host-built
+// reciprocal pivots 1 / (diag_k - cp_{k-1}), the same for m and -m), and writes back  X(m) = x_even + i x_odd,
+// X(-m) = conj(x_even) + i conj(x_odd), whose inverse transform is phi(level 2p) + i phi(level 2p + 1).
+// One work item per storage position q; the item of the smaller position of a pair does the work (a position that is its own
+// partner — wavenumbers 0 or n/2 in both directions — carries two real columns).  Between the sweeps the pair's two slots hold
+// the forward-eliminated even and odd level.  Positions are in bit-reversed order (no permutation pass in the FFTs).
+// ------------------------------------------------------------------------------------------
+RBC_HD int partner_position(const Dims& D, int q)
+{
+    const int rx = q & (D.nx - 1), ry = q >> D.lx2;
+    const int kx = bitrev(rx, D.lx2), ky = bitrev(ry, D.ly2);
+    return (bitrev((D.ny - ky) & (D.ny - 1), D.ly2) << D.lx2) + bitrev((D.nx - kx) & (D.nx - 1), D.lx2);
+}
+template <typename Real>
+RBC_HD void mode_pair_thomas(const Dims& D, cx<Real>* Zs, const Real* cp, Real scale, int q)
+{
+    const int nz = D.nz, ncol = D.ncol, nzp = (nz + 1) >> 1;
+    const int qp = partner_position(D, q);
+    if (qp < q) return;
+    const Real h = Real(0.5) * scale;
+    cx<Real> d{Real(0), Real(0)};                            // forward elimination, level after level
+    for (int p = 0; p < nzp; ++p) {
+        const cx<Real> A = Zs[(size_t)p * ncol + q], B = Zs[(size_t)p * ncol + qp];
+        const bool odd = 2 * p + 1 < nz;
+        const Real c0 = cp[(size_t)(2 * p) * ncol + q], c1 = odd ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
+        const cx<Real> d0{((A.re + B.re) * h - d.re) * c0, ((A.im - B.im) * h - d.im) * c0};
+        const cx<Real> d1{((A.im + B.im) * h - d0.re) * c1, ((B.re - A.re) * h - d0.im) * c1};
+        d = odd ? d1 : d0;
+        if (qp == q) Zs[(size_t)p * ncol + q] = cx<Real>{d0.re, d1.re};       // two real columns
+        else { Zs[(size_t)p * ncol + q] = d0; Zs[(size_t)p * ncol + qp] = d1; }
     }
-    Real xr = dr, xi = di;
-    for (int k = nz - 2; k >= 0; --k) {
-        const Real c = cp[(size_t)k * ncol + m];
-        const cx<Real> d = Zs[(size_t)k * ncol + m];
-        xr = d.re - c * xr;
-        xi = d.im - c * xi;
-        Zs[(size_t)k * ncol + m] = cx<Real>{xr, xi};
+    cx<Real> x{Real(0), Real(0)};                            // back substitution: x_k = d_k - c_k x_{k+1}, x_{nz} = 0
+    for (int p = nzp - 1; p >= 0; --p) {
+        const bool odd = 2 * p + 1 < nz;
+        cx<Real> d0 = Zs[(size_t)p * ncol + q], d1 = Zs[(size_t)p * ncol + qp];
+        if (qp == q) { d1 = cx<Real>{d0.im, Real(0)}; d0 = cx<Real>{d0.re, Real(0)}; }
+        const Real c0 = cp[(size_t)(2 * p) * ncol + q], c1 = odd ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
+        cx<Real> x1{Real(0), Real(0)};
+        if (odd) { x1 = cx<Real>{d1.re - c1 * x.re, d1.im - c1 * x.im}; x = x1; }
+        const cx<Real> x0{d0.re - c0 * x.re, d0.im - c0 * x.im};
+        x = x0;
+        Zs[(size_t)p * ncol + q] = cx<Real>{x0.re - x1.im, x0.im + x1.re};                       // x_even + i x_odd
+        if (qp != q) Zs[(size_t)p * ncol + qp] = cx<Real>{x0.re + x1.im, x1.re - x0.im};         // conj(x_even) + i conj(x_odd)
     }
 }
 
@@ -379,12 +412,6 @@ inline ConstsG<Real> make_consts(const Dims& D, const HostConfigG& h)
     C.kappa_d = kappa; C.delta_b_d = h.delta_b; C.b_top_d = h.b_top;
     C.dt_action = h.heater_duration * t_ff; C.episode_length = h.episode_length;
     return C;
-}
-inline int bitrev(int v, int bits)
-{
-    int r = 0;
-    for (int b = 0; b < bits; ++b) r |= ((v >> b) & 1) << (bits - 1 - b);
-    return r;
 }
 // reciprocal Thomas pivots per (k, ry, rx): position (ry, rx) of the transformed plane holds mode (bitrev ry, bitrev rx)
 inline void build_pivots_host(const Dims& D, double lx, double ly, double lz, double* cp /*nz*ncol*/)

@@ -191,20 +191,25 @@ __device__ void stage_twiddles(const Dims& D, cx<Real>* dst, const cx<Real>* twx
     for (int q = threadIdx.x; q < hx + hy; q += blockDim.x) dst[q] = q < hx ? twx[q] : twy[q - hx];
 }
 
-// divergence of one level into a shared-memory plane, then the forward FFT in x and y (decimation in frequency)
+// divergence of TWO levels (2p in the real, 2p + 1 in the imaginary part, see mode_pair_thomas) into a shared-memory plane, then the
+// forward FFT in x and y (decimation in frequency)
 template <typename Real>
 __global__ void g3_div_fft_kernel(Dims D, ConstsG<Real> C, const Real* P_all, cx<Real>* Z_all, const cx<Real>* twx, const cx<Real>* twy,
                                   const int* env_ids)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<Real>* Z = reinterpret_cast<cx<Real>*>(smem_raw);
-    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, k = blockIdx.x;
+    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, pz = blockIdx.x, nzp = (D.nz + 1) >> 1;
     const Real* P = P_all + (size_t)env * D.nstate;
-    for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) Z[c] = cx<Real>{cell_divergence<Real>(D, C, P, c % D.nx, c / D.nx, k), Real(0)};
+    const bool odd = 2 * pz + 1 < D.nz;
+    for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) {
+        const int i = c & (D.nx - 1), j = c >> D.lx2;
+        Z[c] = cx<Real>{cell_divergence<Real>(D, C, P, i, j, 2 * pz), odd ? cell_divergence<Real>(D, C, P, i, j, 2 * pz + 1) : Real(0)};
+    }
     stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
     __syncthreads();
     plane_fft_forward<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
-    cx<Real>* out = Z_all + ((size_t)env * D.nz + k) * D.ncol;
+    cx<Real>* out = Z_all + ((size_t)env * nzp + pz) * D.ncol;
     for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) out[c] = Z[c];
 }
 
@@ -212,26 +217,30 @@ template <typename Real>
 __global__ void g3_thomas_kernel(Dims D, cx<Real>* Z_all, const Real* cp, Real scale, const int* env_ids)
 {
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= D.ncol) return;
-    mode_thomas<Real>(D, Z_all + (size_t)env * D.nz * D.ncol, cp, scale, m);
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= D.ncol) return;
+    mode_pair_thomas<Real>(D, Z_all + (size_t)env * ((D.nz + 1) >> 1) * D.ncol, cp, scale, q);
 }
 
-// inverse FFT of one level (decimation in time, bit-reversed order in, natural order out) -> phi
+// inverse FFT of one plane (decimation in time, bit-reversed order in, natural order out) -> phi of levels 2p (real part) and 2p + 1
 template <typename Real>
 __global__ void g3_ifft_kernel(Dims D, const cx<Real>* Z_all, Real* phi_all, const cx<Real>* twx, const cx<Real>* twy, const int* env_ids)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<Real>* Z = reinterpret_cast<cx<Real>*>(smem_raw);
-    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, k = blockIdx.x;
-    const cx<Real>* in = Z_all + ((size_t)env * D.nz + k) * D.ncol;
+    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, pz = blockIdx.x, nzp = (D.nz + 1) >> 1;
+    const cx<Real>* in = Z_all + ((size_t)env * nzp + pz) * D.ncol;
     for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) Z[c] = in[c];
     stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
     __syncthreads();
     plane_fft_inverse<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
     const Real norm = Real(1) / (Real)D.ncol;
-    Real* phi = phi_all + ((size_t)env * D.nz + k) * D.ncol;
-    for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) phi[c] = Z[c].re * norm;
+    Real* phi = phi_all + ((size_t)env * D.nz + 2 * pz) * D.ncol;
+    const bool odd = 2 * pz + 1 < D.nz;
+    for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) {
+        phi[c] = Z[c].re * norm;
+        if (odd) phi[D.ncol + c] = Z[c].im * norm;
+    }
 }
 
 template <typename Real>
@@ -428,7 +437,7 @@ template <typename Real>
 static int project_t(Plan* p, const ConstsG<Real>& C, Real* buf, const int* env_ids, int n, cudaStream_t st, int64_t* launches)
 {
     const Dims& D = p->D;
-    const dim3 gplane(D.nz, n), gcell((D.nc + TB - 1) / TB, n), gmode((D.ncol + 127) / 128, n);
+    const dim3 gplane((D.nz + 1) / 2, n), gcell((D.nc + TB - 1) / TB, n), gmode((D.ncol + 127) / 128, n);
     const Real dz = (Real)(p->hc.lz / D.nz);
     g3_div_fft_kernel<Real><<<gplane, p->fft_threads, p->smem, st>>>(D, C, buf, (cx<Real>*)p->Z, (const cx<Real>*)p->twx, (const cx<Real>*)p->twy, env_ids);
     g3_thomas_kernel<Real><<<gmode, 128, 0, st>>>(D, (cx<Real>*)p->Z, (const Real*)p->cp, dz * dz, env_ids);

@@ -19,17 +19,23 @@ template <typename Real>
 static void project(const Dims& D, const ConstsG<Real>& C, const HostConfigG& h, Real* P, std::vector<cx<Real>>& Z, std::vector<Real>& phi,
                     const std::vector<Real>& cp, const std::vector<cx<Real>>& twx, const std::vector<cx<Real>>& twy)
 {
-    for (int k = 0; k < D.nz; ++k) {                                  // g3_div_fft_kernel: one "CTA" per level
-        cx<Real>* Zk = Z.data() + (size_t)k * D.ncol;
-        for (int c = 0; c < D.ncol; ++c) Zk[c] = cx<Real>{cell_divergence<Real>(D, C, P, c % D.nx, c / D.nx, k), Real(0)};
+    const int nzp = (D.nz + 1) / 2;
+    for (int pz = 0; pz < nzp; ++pz) {                                // g3_div_fft_kernel: one "CTA" per pair of levels
+        cx<Real>* Zk = Z.data() + (size_t)pz * D.ncol;
+        const bool odd = 2 * pz + 1 < D.nz;
+        for (int c = 0; c < D.ncol; ++c)
+            Zk[c] = cx<Real>{cell_divergence<Real>(D, C, P, c % D.nx, c / D.nx, 2 * pz), odd ? cell_divergence<Real>(D, C, P, c % D.nx, c / D.nx, 2 * pz + 1) : Real(0)};
         plane_fft_forward<Real>(D, Zk, twx.data(), twy.data(), SerialRun{});
     }
     const Real dz = (Real)(h.lz / D.nz);
-    for (int m = 0; m < D.ncol; ++m) mode_thomas<Real>(D, Z.data(), cp.data(), dz * dz, m);      // g3_thomas_kernel
-    for (int k = 0; k < D.nz; ++k) {                                  // g3_ifft_kernel
-        cx<Real>* Zk = Z.data() + (size_t)k * D.ncol;
+    for (int q = 0; q < D.ncol; ++q) mode_pair_thomas<Real>(D, Z.data(), cp.data(), dz * dz, q);   // g3_thomas_kernel
+    for (int pz = 0; pz < nzp; ++pz) {                                // g3_ifft_kernel
+        cx<Real>* Zk = Z.data() + (size_t)pz * D.ncol;
         plane_fft_inverse<Real>(D, Zk, twx.data(), twy.data(), SerialRun{});
-        for (int c = 0; c < D.ncol; ++c) phi[(size_t)k * D.ncol + c] = Zk[c].re * (Real(1) / (Real)D.ncol);
+        for (int c = 0; c < D.ncol; ++c) {
+            phi[(size_t)(2 * pz) * D.ncol + c] = Zk[c].re * (Real(1) / (Real)D.ncol);
+            if (2 * pz + 1 < D.nz) phi[(size_t)(2 * pz + 1) * D.ncol + c] = Zk[c].im * (Real(1) / (Real)D.ncol);
+        }
     }
     for (int cell = 0; cell < D.nc; ++cell) cell_correct<Real>(D, C, P, phi.data(), cell);       // g3_correct_kernel
 }

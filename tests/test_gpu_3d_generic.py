@@ -29,7 +29,7 @@ def projected_state(P, seed, amp=0.2):
     return (b, *O3.project(P, u, v, w))
 
 
-@pytest.mark.parametrize("shape", [(32, 64, 64), (8, 16, 32)])
+@pytest.mark.parametrize("shape", [(32, 64, 64), (8, 16, 32), (7, 8, 16)])      # the last: per-cell tendency, odd number of levels
 def test_generic_grid_matches_oracle(shape):
     import torch
     from oracle import oracle3d as O3

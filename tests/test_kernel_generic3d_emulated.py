@@ -31,7 +31,7 @@ def unpack(st, shape):
     return st[:n].reshape(shape), st[n:2 * n].reshape(shape), st[2 * n:3 * n].reshape(shape), st[3 * n:].reshape(nz + 1, ny, nx)
 
 
-@pytest.mark.parametrize("shape", [(16, 32, 32), (8, 16, 32), (12, 32, 16), (32, 64, 64)])
+@pytest.mark.parametrize("shape", [(16, 32, 32), (8, 16, 32), (12, 32, 16), (7, 8, 16), (32, 64, 64)])      # nz = 7: an unpaired top level in the spectral planes
 def test_generic_3d_kernels_match_oracle(shape):
     full = shape == (32, 64, 64)
     P = O3.make_params(5e3, shape=shape, split_phy=False)
