@@ -324,7 +324,7 @@ struct Plan {
     HostConfigG hc;
     int B = 0, precision = 32, device = 0;
     size_t rs = 4, smem = 0;
-    int fft_threads = 256;
+    int fft_threads = 512;
     int tiled = 0;               // rows of the column patch of the tiled tendency (shared-memory plane ring; nx % 32 == 0, ny % rows == 0); 0 = per-cell kernel.  RBC_B200_G3_TILED=0|8|16 overrides
     void *P = nullptr, *G = nullptr, *Z = nullptr, *phi = nullptr, *Tb = nullptr, *cp = nullptr, *twx = nullptr, *twy = nullptr;
     void *nu = nullptr, *kappa = nullptr;          // per-environment diffusivities (Real)
