@@ -65,6 +65,7 @@ struct ConstsG {
     double heater_limit, b_hot;
     double kappa_d, delta_b_d, b_top_d;
     double dt_action, episode_length;
+    int variant;                 // 0 = the scheme of SURVEY 8a.  Non-zero: experimental wall-order variants for the parity study of DESIGN.md section 2 (RBC_B200_G3_VARIANT)
 };
 
 // wall-order rules: centres -> z-face kf, z-faces -> centre kc
@@ -105,6 +106,25 @@ RBC_HD double heater_patch_T(int heaters, double heater_limit, double b_hot, con
 // wrapping accessor for every stencil point (~7 400 instructions per cell, 1.67 ms per 64-environment stage at 64 x 64 x 32).
 // Window index d <-> offset d - 3 from the cell; a face "m-1 | m" along a direction uses slots m .. m + 5 of that window.
 // ------------------------------------------------------------------------------------------
+// Parity-study variants of the wall rule.  The scheme of record reduces the order of BOTH biased stencils of a
+// face together (o_up_face / o_up_cen).  Variant bit 0 (centres -> z-face) and bit 1 (z-faces -> centre) let each biased stencil
+// keep the highest order that fits between the walls on its own: the left-biased one (cells kf-3 .. kf+1) and the right-biased
+// one (kf-2 .. kf+2) then switch order at different faces.
+template <typename Real>
+RBC_HD Real upwind_z_face(Real vel, const Real* win, int kf, int nz, int variant)
+{
+    if (!(variant & 1)) return upwind_ord(vel, win, o_up_face(kf, nz));
+    const int oL = (kf >= 3 && kf <= nz - 2) ? 5 : ((kf >= 2) ? 3 : 1), oR = (kf >= 2 && kf <= nz - 3) ? 5 : ((kf <= nz - 2) ? 3 : 1);
+    return upwind_ord(vel, win, vel > Real(0) ? oL : oR);
+}
+template <typename Real>
+RBC_HD Real upwind_z_cen(Real vel, const Real* win, int kc, int nz, int variant)
+{
+    if (!(variant & 2)) return upwind_ord(vel, win, o_up_cen(kc, nz));
+    const int oL = (kc >= 2 && kc <= nz - 2) ? 5 : ((kc >= 1) ? 3 : 1), oR = (kc >= 1 && kc <= nz - 3) ? 5 : ((kc <= nz - 2) ? 3 : 1);
+    return upwind_ord(vel, win, vel > Real(0) ? oL : oR);
+}
+
 // the register windows of one cell (scalarised by the compiler once everything is inlined)
 template <typename Real>
 struct Windows {
@@ -133,8 +153,8 @@ RBC_HD Tend<Real> tendency_from_windows(const ConstsG<Real>& C, Real nu, Real ka
     {   // tracer: the advecting velocity is the face value itself
         const Real Fx0 = upwind_ord(u0, bx, 5), Fx1 = upwind_ord(ux[4], bx + 1, 5);
         const Real Fy0 = upwind_ord(v0, by, 5), Fy1 = upwind_ord(vy[4], by + 1, 5);
-        const Real Fz0 = of0 ? upwind_ord(w0, bz, of0) : Real(0);
-        const Real Fz1 = of1 ? upwind_ord(wz[4], bz + 1, of1) : Real(0);
+        const Real Fz0 = of0 ? upwind_z_face(w0, bz, k, nz, C.variant) : Real(0);
+        const Real Fz1 = of1 ? upwind_z_face(wz[4], bz + 1, k + 1, nz, C.variant) : Real(0);
         const Real bdn = (k == 0) ? Real(2) * tb - b0 : bz[2];
         const Real bup = (k == nz - 1) ? Real(2) * C.b_top - b0 : bz[4];
         const Real lap = (bx[4] - Real(2) * b0 + bx[2]) * C.idx2 + (by[4] - Real(2) * b0 + by[2]) * C.idy2 + (bup - Real(2) * b0 + bdn) * C.idz2;
@@ -145,8 +165,8 @@ RBC_HD Tend<Real> tendency_from_windows(const ConstsG<Real>& C, Real nu, Real ka
         const Real F1 = upwind_ord(centred_ord(ux[2], ux[3], ux[4], ux[5], 4), ux + 1, 5);
         const Real G0 = upwind_ord(centred_ord(vx[1], vx[2], vx[3], vx[4], 4), uy, 5);
         const Real G1 = upwind_ord(centred_ord(W.v_jp[0], W.v_jp[1], W.v_jp[2], W.v_jp[3], 4), uy + 1, 5);
-        const Real H0 = of0 ? upwind_ord(centred_ord(wx[1], wx[2], wx[3], wx[4], 4), uz, of0) : Real(0);
-        const Real H1 = of1 ? upwind_ord(centred_ord(W.w_kp_x[0], W.w_kp_x[1], W.w_kp_x[2], W.w_kp_x[3], 4), uz + 1, of1) : Real(0);
+        const Real H0 = of0 ? upwind_z_face(centred_ord(wx[1], wx[2], wx[3], wx[4], 4), uz, k, nz, C.variant) : Real(0);
+        const Real H1 = of1 ? upwind_z_face(centred_ord(W.w_kp_x[0], W.w_kp_x[1], W.w_kp_x[2], W.w_kp_x[3], 4), uz + 1, k + 1, nz, C.variant) : Real(0);
         const Real dn = (k == 0) ? -u0 : uz[2], up = (k == nz - 1) ? -u0 : uz[4];
         const Real lap = (ux[4] - Real(2) * u0 + ux[2]) * C.idx2 + (uy[4] - Real(2) * u0 + uy[2]) * C.idy2 + (up - Real(2) * u0 + dn) * C.idz2;
         g.u = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
@@ -156,8 +176,8 @@ RBC_HD Tend<Real> tendency_from_windows(const ConstsG<Real>& C, Real nu, Real ka
         const Real F1 = upwind_ord(centred_ord(W.u_ip[0], W.u_ip[1], W.u_ip[2], W.u_ip[3], 4), vx + 1, 5);
         const Real G0 = upwind_ord(centred_ord(vy[1], vy[2], vy[3], vy[4], 4), vy, 5);
         const Real G1 = upwind_ord(centred_ord(vy[2], vy[3], vy[4], vy[5], 4), vy + 1, 5);
-        const Real H0 = of0 ? upwind_ord(centred_ord(wy[1], wy[2], wy[3], wy[4], 4), vz, of0) : Real(0);
-        const Real H1 = of1 ? upwind_ord(centred_ord(W.w_kp_y[0], W.w_kp_y[1], W.w_kp_y[2], W.w_kp_y[3], 4), vz + 1, of1) : Real(0);
+        const Real H0 = of0 ? upwind_z_face(centred_ord(wy[1], wy[2], wy[3], wy[4], 4), vz, k, nz, C.variant) : Real(0);
+        const Real H1 = of1 ? upwind_z_face(centred_ord(W.w_kp_y[0], W.w_kp_y[1], W.w_kp_y[2], W.w_kp_y[3], 4), vz + 1, k + 1, nz, C.variant) : Real(0);
         const Real dn = (k == 0) ? -v0 : vz[2], up = (k == nz - 1) ? -v0 : vz[4];
         const Real lap = (vx[4] - Real(2) * v0 + vx[2]) * C.idx2 + (vy[4] - Real(2) * v0 + vy[2]) * C.idy2 + (up - Real(2) * v0 + dn) * C.idz2;
         g.v = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
@@ -168,8 +188,8 @@ RBC_HD Tend<Real> tendency_from_windows(const ConstsG<Real>& C, Real nu, Real ka
         const Real F1 = upwind_ord(centred_ord(W.u_ip_z[0], W.u_ip_z[1], W.u_ip_z[2], W.u_ip_z[3], oc), wx + 1, 5);
         const Real G0 = upwind_ord(centred_ord(vz[1], vz[2], vz[3], vz[4], oc), wy, 5);
         const Real G1 = upwind_ord(centred_ord(W.v_jp_z[0], W.v_jp_z[1], W.v_jp_z[2], W.v_jp_z[3], oc), wy + 1, 5);
-        const Real H0 = upwind_ord(centred_ord(wz[1], wz[2], wz[3], wz[4], o_ce_cen(k - 1, nz)), wz, o_up_cen(k - 1, nz));
-        const Real H1 = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen(k, nz)), wz + 1, o_up_cen(k, nz));
+        const Real H0 = upwind_z_cen(centred_ord(wz[1], wz[2], wz[3], wz[4], o_ce_cen(k - 1, nz)), wz, k - 1, nz, C.variant);
+        const Real H1 = upwind_z_cen(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen(k, nz)), wz + 1, k, nz, C.variant);
         const Real lap = (wx[4] - Real(2) * w0 + wx[2]) * C.idx2 + (wy[4] - Real(2) * w0 + wy[2]) * C.idy2 + (wz[4] - Real(2) * w0 + wz[2]) * C.idz2;
         g.w = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap + Real(0.5) * (bz[2] + b0);
     }
@@ -411,6 +431,7 @@ inline ConstsG<Real> make_consts(const Dims& D, const HostConfigG& h)
     C.heaters = h.heaters; C.heater_limit = h.heater_limit; C.b_hot = h.b_top + h.delta_b;
     C.kappa_d = kappa; C.delta_b_d = h.delta_b; C.b_top_d = h.b_top;
     C.dt_action = h.heater_duration * t_ff; C.episode_length = h.episode_length;
+    C.variant = 0;
     return C;
 }
 // reciprocal Thomas pivots per (k, ry, rx): position (ry, rx) of the transformed plane holds mode (bitrev ry, bitrev rx)

@@ -325,6 +325,7 @@ struct Plan {
     int B = 0, precision = 32, device = 0;
     size_t rs = 4, smem = 0;
     int fft_threads = 512;
+    int variant = 0;             // RBC_B200_G3_VARIANT: wall-order variants of the parity study (rbc3dg_core.h); 0 = the scheme of record
     int tiled = 0;               // rows of the column patch of the tiled tendency (shared-memory plane ring; nx % 32 == 0, ny % rows == 0); 0 = per-cell kernel.  RBC_B200_G3_TILED=0|8|16 overrides
     void *P = nullptr, *G = nullptr, *Z = nullptr, *phi = nullptr, *Tb = nullptr, *cp = nullptr, *twx = nullptr, *twy = nullptr;
     void *nu = nullptr, *kappa = nullptr;          // per-environment diffusivities (Real)
@@ -396,6 +397,7 @@ int create(const HostConfigG& hc, int nx, int ny, int nz, int num_envs, int prec
     }
     if (e != cudaSuccess) { delete p; return rbc_fail(std::string("rbc3d_create: ") + cudaGetErrorString(e)); }
     {
+        if (const char* v = getenv("RBC_B200_G3_VARIANT")) p->variant = atoi(v);
         const char* sw = getenv("RBC_B200_G3_TILED");
         const int want = sw ? atoi(sw) : 8;       // 8 rows: two CTAs per SM hide each other's barriers and copy waits (678 vs 634 env-steps/s at 64 x 64 x 32)
         p->tiled = (nx % TT_X != 0 || want == 0) ? 0 : ((want >= 16 && ny % 16 == 0) ? 16 : (ny % 8 == 0 ? 8 : 0));
@@ -453,7 +455,8 @@ static int launch_t(Plan* p, const IoRaw& io, const int* env_ids, int n, int nsu
                     int64_t* launches)
 {
     const Dims& D = p->D;
-    const ConstsG<Real> C = make_consts<Real>(D, p->hc);
+    ConstsG<Real> C = make_consts<Real>(D, p->hc);
+    C.variant = p->variant;
     const Real gam[3] = {Real(8.0 / 15.0), Real(5.0 / 12.0), Real(3.0 / 4.0)};
     const Real zet[3] = {Real(0), Real(-17.0 / 60.0), Real(-5.0 / 12.0)};
     Real* S = (Real*)io.state;

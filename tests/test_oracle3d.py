@@ -77,3 +77,25 @@ def test_action_preprocessing_and_patches():
     assert np.allclose(Tb[20:24, 8:12], T[2, 5]) and np.allclose(Tb[8:12, 20:24], T[5, 2])
     big = O3.preprocess_action(P, 3 * np.sign(np.random.default_rng(0).standard_normal((8, 8))))
     assert big.max() <= 2.9 + 1e-12 and big.min() >= 1.1 - 1e-12      # scaled by K = max|a - mean|
+
+
+def test_time_scale_exact_diffusion_decay():
+    """The oracle's clock against an exact answer: with the fluid at rest a horizontally uniform perturbation
+    b' = eps sin(pi (k + 1/2) / nz) is an eigenvector of the discrete vertical diffusion (Dirichlet ghosts), stays in hydrostatic
+    balance (no flow) and decays as exp(-kappa (4/dz^2) sin^2(pi / 2 nz) t).  One flowstats sample — 50 RK3 steps of
+    dt_solver * t_ff = 0.02 (`rbc_sim3D_api.jl:43,65`) — must advance it by exactly one time unit: this pins the time scale of
+    the scheme (substep schedule, RK3 weights, t_ff), which the reference's phase-space fixtures cannot."""
+    shape = (16, 8, 8)
+    P = O3.make_params(5e3, shape=shape, split_phy=False)
+    nz = shape[0]
+    z = (np.arange(nz) + 0.5) * 2.0 / nz
+    base, mode, eps = 1 + (2 - z) / 2, np.sin(np.pi * (np.arange(nz) + 0.5) / nz), 1e-3
+    b = (base + eps * mode)[:, None, None] * np.ones(shape)
+    zero = np.zeros(shape)
+    dts = O3.substep_schedule(0.25, 0.005)
+    assert len(dts) == 50 and abs(dts.sum() - 1.0) < 1e-14
+    r = O3.step(P, b, zero, zero, np.zeros((nz + 1, *shape[1:])), np.zeros((8, 8)), dts)
+    amp = ((r["b"][:, 0, 0] - base) @ mode) / (mode @ mode)
+    rate = (1 / np.sqrt(0.7 * 5e3)) * (4 / (2.0 / nz) ** 2) * np.sin(np.pi / (2 * nz)) ** 2
+    assert abs(-np.log(amp / eps) / rate - 1.0) < 1e-9
+    assert np.abs(r["w"]).max() < 1e-14 and np.abs(r["u"]).max() < 1e-14
