@@ -59,10 +59,37 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc, self.thread = gpu_index, [], None, None
+        self._stop = threading.Event()
 
     def start(self):
+        """In-process NVML polling every 100 ms (clock + event-reason bitmask: two light queries).  An `nvidia-smi -lms 50` child
+        process was measured to perturb the launches of the timed loop on some boxes (device-resident `value` 6 % below the
+        host-buffer `e2e` of the same run); nvidia-smi at 250 ms is kept as the fallback when NVML cannot be loaded."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = (("hw_slowdown", pynvml.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", pynvml.nvmlClocksThrottleReasonSwPowerCap))
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((time.time(), ["", sm, mx, "", ""] + ["Active" if r & m else "Not Active" for _, m in bits]))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.1)
+            self.proc = "nvml"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -78,11 +105,13 @@ class ClockSampler:
         hundred ms to start, so the sampler is launched before the warm-up and the region is cut out afterwards."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        self._stop.set()
+        if self.proc != "nvml":
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, r in self.rows:

@@ -142,10 +142,63 @@ struct Tend {
     Real b, u, v, w;
 };
 // the four tendencies of the cell at level k from its windows (tb = heater temperature below the column, read at k = 0 only)
+// level k is "interior" when every z-stencil of the cell has its full order and no wall ghost is involved; the march of the tiled
+// kernel runs those levels through a branch-free instantiation
+RBC_HD bool interior_level(int k, int nz) { return k >= 3 && k <= nz - 4; }
+template <typename Real, bool INTERIOR>
+RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real kappa, int nz, int k, const Windows<Real>& W, Real tb);
 template <typename Real>
 RBC_HD Tend<Real> tendency_from_windows(const ConstsG<Real>& C, Real nu, Real kappa, int nz, int k, const Windows<Real>& W, Real tb)
 {
+    return tendency_from_windows_t<Real, false>(C, nu, kappa, nz, k, W, tb);
+}
+template <typename Real, bool INTERIOR>
+RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real kappa, int nz, int k, const Windows<Real>& W, Real tb)
+{
     const Real *bx = W.bx, *by = W.by, *bz = W.bz, *ux = W.ux, *uy = W.uy, *uz = W.uz, *vx = W.vx, *vy = W.vy, *vz = W.vz, *wx = W.wx, *wy = W.wy, *wz = W.wz;
+    if (INTERIOR) {
+        // the same expressions as the general body below with every order decision resolved: 5th / 4th order everywhere
+        const Real b0 = bx[3], u0 = ux[3], v0 = vx[3], w0 = wx[3];
+        Tend<Real> g;
+        {
+            const Real Fx0 = upwind_ord(u0, bx, 5), Fx1 = upwind_ord(ux[4], bx + 1, 5);
+            const Real Fy0 = upwind_ord(v0, by, 5), Fy1 = upwind_ord(vy[4], by + 1, 5);
+            const Real Fz0 = upwind_ord(w0, bz, 5), Fz1 = upwind_ord(wz[4], bz + 1, 5);
+            const Real lap = (bx[4] - Real(2) * b0 + bx[2]) * C.idx2 + (by[4] - Real(2) * b0 + by[2]) * C.idy2 + (bz[4] - Real(2) * b0 + bz[2]) * C.idz2;
+            g.b = -((Fx1 - Fx0) * C.idx + (Fy1 - Fy0) * C.idy + (Fz1 - Fz0) * C.idz) + kappa * lap;
+        }
+        {
+            const Real F0 = upwind_ord(centred_ord(ux[1], ux[2], ux[3], ux[4], 4), ux, 5);
+            const Real F1 = upwind_ord(centred_ord(ux[2], ux[3], ux[4], ux[5], 4), ux + 1, 5);
+            const Real G0 = upwind_ord(centred_ord(vx[1], vx[2], vx[3], vx[4], 4), uy, 5);
+            const Real G1 = upwind_ord(centred_ord(W.v_jp[0], W.v_jp[1], W.v_jp[2], W.v_jp[3], 4), uy + 1, 5);
+            const Real H0 = upwind_ord(centred_ord(wx[1], wx[2], wx[3], wx[4], 4), uz, 5);
+            const Real H1 = upwind_ord(centred_ord(W.w_kp_x[0], W.w_kp_x[1], W.w_kp_x[2], W.w_kp_x[3], 4), uz + 1, 5);
+            const Real lap = (ux[4] - Real(2) * u0 + ux[2]) * C.idx2 + (uy[4] - Real(2) * u0 + uy[2]) * C.idy2 + (uz[4] - Real(2) * u0 + uz[2]) * C.idz2;
+            g.u = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
+        }
+        {
+            const Real F0 = upwind_ord(centred_ord(uy[1], uy[2], uy[3], uy[4], 4), vx, 5);
+            const Real F1 = upwind_ord(centred_ord(W.u_ip[0], W.u_ip[1], W.u_ip[2], W.u_ip[3], 4), vx + 1, 5);
+            const Real G0 = upwind_ord(centred_ord(vy[1], vy[2], vy[3], vy[4], 4), vy, 5);
+            const Real G1 = upwind_ord(centred_ord(vy[2], vy[3], vy[4], vy[5], 4), vy + 1, 5);
+            const Real H0 = upwind_ord(centred_ord(wy[1], wy[2], wy[3], wy[4], 4), vz, 5);
+            const Real H1 = upwind_ord(centred_ord(W.w_kp_y[0], W.w_kp_y[1], W.w_kp_y[2], W.w_kp_y[3], 4), vz + 1, 5);
+            const Real lap = (vx[4] - Real(2) * v0 + vx[2]) * C.idx2 + (vy[4] - Real(2) * v0 + vy[2]) * C.idy2 + (vz[4] - Real(2) * v0 + vz[2]) * C.idz2;
+            g.v = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
+        }
+        {
+            const Real F0 = upwind_ord(centred_ord(uz[1], uz[2], uz[3], uz[4], 4), wx, 5);
+            const Real F1 = upwind_ord(centred_ord(W.u_ip_z[0], W.u_ip_z[1], W.u_ip_z[2], W.u_ip_z[3], 4), wx + 1, 5);
+            const Real G0 = upwind_ord(centred_ord(vz[1], vz[2], vz[3], vz[4], 4), wy, 5);
+            const Real G1 = upwind_ord(centred_ord(W.v_jp_z[0], W.v_jp_z[1], W.v_jp_z[2], W.v_jp_z[3], 4), wy + 1, 5);
+            const Real H0 = upwind_ord(centred_ord(wz[1], wz[2], wz[3], wz[4], 4), wz, 5);
+            const Real H1 = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], 4), wz + 1, 5);
+            const Real lap = (wx[4] - Real(2) * w0 + wx[2]) * C.idx2 + (wy[4] - Real(2) * w0 + wy[2]) * C.idy2 + (wz[4] - Real(2) * w0 + wz[2]) * C.idz2;
+            g.w = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap + Real(0.5) * (bz[2] + b0);
+        }
+        return g;
+    }
     const int of0 = (k >= 1) ? o_up_face(k, nz) : 0, of1 = (k + 1 <= nz - 1) ? o_up_face(k + 1, nz) : 0;
     const Real b0 = bx[3], u0 = ux[3], v0 = vx[3], w0 = wx[3];
     Tend<Real> g;

@@ -157,7 +157,8 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
             W.w_kp_y[q] = s1[3 * TT_PLANE + p0 + (q - 2) * TT_PW];
         }
         if (k + 1 < nz) { W.u_ip_z[3] = s1[TT_PLANE + p0 + 1]; W.v_jp_z[3] = s1[2 * TT_PLANE + p0 + TT_PW]; }
-        const Tend<Real> g = tendency_from_windows<Real>(C, nu, kappa, nz, k, W, tb);
+        const Tend<Real> g = interior_level(k, nz) ? tendency_from_windows_t<Real, true>(C, nu, kappa, nz, k, W, tb)
+                                                   : tendency_from_windows_t<Real, false>(C, nu, kappa, nz, k, W, tb);
         rk3_substep_store<Real>(D, P, G, k * ncol + colz, colz, k, W, g, prev, dt, gam, zet, store_g != 0);
         // slide the register windows up one level
 #pragma unroll
