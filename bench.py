@@ -15,6 +15,7 @@ from a device Philox generator seeded 1234 + rank.  Envs shard across ranks with
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -339,7 +340,7 @@ def main():
     # ---------------- device-resident throughput (`value`) ----------------
     # untimed pre-warm: bring the SM clock up from idle (120 MHz) before the W warm-up steps
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("RBC_BENCH_NO_CLOCKS"):
         sampler.start()
     env.reset(options={"checkpoint_idx": start_idx})
     t_pre = time.perf_counter()
@@ -347,21 +348,41 @@ def main():
         env.step(actions[0])
         torch.cuda.synchronize()
     env.reset(options={"checkpoint_idx": start_idx})
+    # warm-up with exactly the statements of the timed loop: besides torch's lazily loaded kernels this brings the caching
+    # allocator to its steady state — the results of step i are still referenced while step i + 1 allocates its copies, and a
+    # loop that first reaches that peak inside the timed region pays a cudaMalloc there (measured: a 2 ... 120 ms host stall in
+    # the SECOND timed step with an empty launch queue behind it, i.e. up to 10 % of a 20-step region)
     for i in range(W):
-        o_ = env.step(actions[i])
-        stats.accumulate(o_[1], o_[4]["nusselt_obs"], o_[4]["nusselt_state"], o_[4]["nan"])   # also warms torch's lazily loaded kernels
+        obs, rew, term, trunc, info = env.step(actions[i])
+        stats.accumulate(rew, info["nusselt_obs"], info["nusselt_state"], info["nan"])
     stats = EpisodeStats(dev)
+    # the queue is empty after the barrier: a host pause in the first steps of the region (a cyclic-GC pass costs tens of ms)
+    # would be GPU idle time, so collect now and keep the collector off while timing
+    gc.collect()
+    gc.disable()
     barrier()
     t_region0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = sim.launch_info()["launches"]
     e0.record()
+    diag = [] if os.environ.get("RBC_BENCH_DIAG") else None      # per-step device and host timeline (debugging aid, off by default)
     for i in range(K):
+        th = time.perf_counter()
         obs, rew, term, trunc, info = env.step(actions[W + i])
         stats.accumulate(rew, info["nusselt_obs"], info["nusselt_state"], info["nan"])
+        if diag is not None:
+            ev = torch.cuda.Event(enable_timing=True); ev.record()
+            diag.append((ev, (time.perf_counter() - th) * 1e3))
     e1.record()
     barrier()
+    gc.enable()
     elapsed_ms = e0.elapsed_time(e1)
+    if diag is not None and rank == 0:
+        prev, out_ = e0, []
+        for ev, host_ms in diag:
+            out_.append(f"{prev.elapsed_time(ev):.2f}/{host_ms:.2f}")
+            prev = ev
+        print("diag device ms per step / host ms per step: " + " ".join(out_), file=sys.stderr)
     launches = sim.launch_info()["launches"] - launches0
     clocks = sampler.stop(t_region0, time.time()) if rank == 0 else None
     # per-launch duration of the dominant kernel over the timed region: the library records a CUDA event pair around every

@@ -126,7 +126,17 @@ def test_info_state_and_deferred_nan_check():
     env.sim.reset_from_fields(f[4:5], env_ids=[4], project=False)
     env.step(a)                                                                  # the failing step itself does not synchronise ...
     with pytest.raises(RuntimeError, match="probably NaN"):
-        env.step(a)                                                              # ... the next call raises the reference's error
+        for _ in range(6):                                                       # ... a later call raises the reference's error: the first one
+            env.step(a)                                                          # whose predecessor's counter copy has completed (never blocks
+    env.close()                                                                  # on the device; at most five copies are kept in flight)
+    # once the device has caught up it is exactly the next call
+    env = RBCVectorEnv2D(6, rayleigh_number=100_000, heater_duration=0.15, checkpoint=CKPT, nan_policy="raise_deferred")
+    env.reset(seed=0)
+    env.sim.reset_from_fields(f[4:5], env_ids=[4], project=False)
+    env.step(a)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="probably NaN"):
+        env.step(a)
     env.close()
 
 
