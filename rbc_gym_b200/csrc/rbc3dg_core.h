@@ -372,21 +372,84 @@ RBC_HD void butterfly_dit_inv(cx<Real>* Z, int ln, int ls, int lnl, int line_str
     Z[f.a] = cx<Real>{xa.re + tr, xa.im + ti};
     Z[f.b] = cx<Real>{xa.re - tr, xa.im - ti};
 }
+// Two consecutive radix-2 stages on the four elements they connect (a radix-4 step written as its two radix-2 halves: the same
+// operations on the same values, so the result is bit-identical to running the stages one after the other): half the barriers
+// and half the shared-memory traffic of the transform.  One work item = 4 elements; n/4 items per line.
+//   forward (DIF): spans S = 2^ls, then S/2 (ls >= 1).  inverse (DIT): spans S = 2^ls, then 2S (ls <= ln - 2).
+template <typename Real>
+RBC_HD cx<Real> cmulw(cx<Real> d, cx<Real> w) { return cx<Real>{d.re * w.re - d.im * w.im, d.re * w.im + d.im * w.re}; }
+template <typename Real>
+RBC_HD cx<Real> cmulwc(cx<Real> b, cx<Real> w) { return cx<Real>{b.re * w.re + b.im * w.im, b.im * w.re - b.re * w.im}; }      // b * conj(w)
+template <typename Real>
+RBC_HD void butterfly2_dif(cx<Real>* Z, int ln, int ls, int lnl, int line_stride, int elem_stride, bool lines_fastest, const cx<Real>* tw, int item)
+{
+    const int lq = ln - 2, lh = ln - 1, S = 1 << ls, Sh = S >> 1;
+    const int line = lines_fastest ? (item & ((1 << lnl) - 1)) : (item >> lq);
+    const int q = lines_fastest ? (item >> lnl) : (item & ((1 << lq) - 1));
+    const int j = q & (Sh - 1), grp = q >> (ls - 1);
+    const int e0 = line * line_stride + ((grp << (ls + 1)) + j) * elem_stride, e1 = e0 + Sh * elem_stride, e2 = e0 + S * elem_stride,
+              e3 = e2 + Sh * elem_stride;
+    const cx<Real> x0 = Z[e0], x1 = Z[e1], x2 = Z[e2], x3 = Z[e3];
+    const cx<Real> wa = tw[j << (lh - ls)], wb = tw[(j + Sh) << (lh - ls)], wc = tw[j << (lh - ls + 1)];
+    // stage with span S: (e0, e2) and (e1, e3)
+    const cx<Real> y0{x0.re + x2.re, x0.im + x2.im}, y2 = cmulw(cx<Real>{x0.re - x2.re, x0.im - x2.im}, wa);
+    const cx<Real> y1{x1.re + x3.re, x1.im + x3.im}, y3 = cmulw(cx<Real>{x1.re - x3.re, x1.im - x3.im}, wb);
+    // stage with span S/2: (e0, e1) and (e2, e3)
+    Z[e0] = cx<Real>{y0.re + y1.re, y0.im + y1.im};
+    Z[e1] = cmulw(cx<Real>{y0.re - y1.re, y0.im - y1.im}, wc);
+    Z[e2] = cx<Real>{y2.re + y3.re, y2.im + y3.im};
+    Z[e3] = cmulw(cx<Real>{y2.re - y3.re, y2.im - y3.im}, wc);
+}
+template <typename Real>
+RBC_HD void butterfly2_dit_inv(cx<Real>* Z, int ln, int ls, int lnl, int line_stride, int elem_stride, bool lines_fastest, const cx<Real>* tw, int item)
+{
+    const int lq = ln - 2, lh = ln - 1, S = 1 << ls;
+    const int line = lines_fastest ? (item & ((1 << lnl) - 1)) : (item >> lq);
+    const int q = lines_fastest ? (item >> lnl) : (item & ((1 << lq) - 1));
+    const int j = q & (S - 1), grp = q >> ls;
+    const int e0 = line * line_stride + ((grp << (ls + 2)) + j) * elem_stride, e1 = e0 + S * elem_stride, e2 = e1 + S * elem_stride,
+              e3 = e2 + S * elem_stride;
+    const cx<Real> x0 = Z[e0], x1 = Z[e1], x2 = Z[e2], x3 = Z[e3];
+    const cx<Real> wa = tw[j << (lh - ls)], wc = tw[j << (lh - ls - 1)], wd = tw[(j + S) << (lh - ls - 1)];
+    // stage with span S: (e0, e1) and (e2, e3), both at position j of their group
+    const cx<Real> t1 = cmulwc(x1, wa), t3 = cmulwc(x3, wa);
+    const cx<Real> y0{x0.re + t1.re, x0.im + t1.im}, y1{x0.re - t1.re, x0.im - t1.im};
+    const cx<Real> y2{x2.re + t3.re, x2.im + t3.im}, y3{x2.re - t3.re, x2.im - t3.im};
+    // stage with span 2S: (e0, e2) at position j, (e1, e3) at position j + S
+    const cx<Real> u2 = cmulwc(y2, wc), u3 = cmulwc(y3, wd);
+    Z[e0] = cx<Real>{y0.re + u2.re, y0.im + u2.im};
+    Z[e2] = cx<Real>{y0.re - u2.re, y0.im - u2.im};
+    Z[e1] = cx<Real>{y1.re + u3.re, y1.im + u3.im};
+    Z[e3] = cx<Real>{y1.re - u3.re, y1.im - u3.im};
+}
 // the passes of one plane as (direction, span) sequences; `run(n_items, fn)` executes fn(item) for every item and then
-// synchronises (a strided thread loop + __syncthreads on the device, a plain loop in the emulator)
+// synchronises (a strided thread loop + __syncthreads on the device, a plain loop in the emulator).  Stages are taken two at a
+// time; an odd number of stages leaves one plain radix-2 stage.
+template <typename Real, typename Run>
+RBC_HD void line_fft_forward(const Dims& D, cx<Real>* Z, int ln, int lnl, int line_stride, int elem_stride, bool lines_fastest, const cx<Real>* tw, Run run)
+{
+    int ls = ln - 1;
+    for (; ls >= 1; ls -= 2) run(D.ncol >> 2, [&](int it) { butterfly2_dif<Real>(Z, ln, ls, lnl, line_stride, elem_stride, lines_fastest, tw, it); });
+    if (ls == 0) run(D.ncol >> 1, [&](int it) { butterfly_dif<Real>(Z, ln, 0, lnl, line_stride, elem_stride, lines_fastest, tw, it); });
+}
+template <typename Real, typename Run>
+RBC_HD void line_fft_inverse(const Dims& D, cx<Real>* Z, int ln, int lnl, int line_stride, int elem_stride, bool lines_fastest, const cx<Real>* tw, Run run)
+{
+    int ls = 0;
+    for (; ls + 1 <= ln - 1; ls += 2) run(D.ncol >> 2, [&](int it) { butterfly2_dit_inv<Real>(Z, ln, ls, lnl, line_stride, elem_stride, lines_fastest, tw, it); });
+    if (ls == ln - 1) run(D.ncol >> 1, [&](int it) { butterfly_dit_inv<Real>(Z, ln, ls, lnl, line_stride, elem_stride, lines_fastest, tw, it); });
+}
 template <typename Real, typename Run>
 RBC_HD void plane_fft_forward(const Dims& D, cx<Real>* Z, const cx<Real>* twx, const cx<Real>* twy, Run run)
 {
-    const int items = D.ncol >> 1;
-    for (int ls = D.lx2 - 1; ls >= 0; --ls) run(items, [&](int it) { butterfly_dif<Real>(Z, D.lx2, ls, D.ly2, D.nx, 1, false, twx, it); });
-    for (int ls = D.ly2 - 1; ls >= 0; --ls) run(items, [&](int it) { butterfly_dif<Real>(Z, D.ly2, ls, D.lx2, 1, D.nx, true, twy, it); });
+    line_fft_forward<Real>(D, Z, D.lx2, D.ly2, D.nx, 1, false, twx, run);
+    line_fft_forward<Real>(D, Z, D.ly2, D.lx2, 1, D.nx, true, twy, run);
 }
 template <typename Real, typename Run>
 RBC_HD void plane_fft_inverse(const Dims& D, cx<Real>* Z, const cx<Real>* twx, const cx<Real>* twy, Run run)
 {
-    const int items = D.ncol >> 1;
-    for (int ls = 0; ls < D.ly2; ++ls) run(items, [&](int it) { butterfly_dit_inv<Real>(Z, D.ly2, ls, D.lx2, 1, D.nx, true, twy, it); });
-    for (int ls = 0; ls < D.lx2; ++ls) run(items, [&](int it) { butterfly_dit_inv<Real>(Z, D.lx2, ls, D.ly2, D.nx, 1, false, twx, it); });
+    line_fft_inverse<Real>(D, Z, D.ly2, D.lx2, 1, D.nx, true, twy, run);
+    line_fft_inverse<Real>(D, Z, D.lx2, D.ly2, D.nx, 1, false, twx, run);
 }
 
 RBC_HD int bitrev(int v, int bits)
