@@ -78,6 +78,12 @@ class _VectorBase:
         self.torch = torch
         self.num_envs = int(num_envs)
         self.autoreset_mode = autoreset_mode
+        # the attributes gymnasium.vector.VectorEnv (1.x) carries besides the spaces: code written against the reference's
+        # `gym.make_vec(...)` result (`example/run_vectorized.py:11-31`) reads these
+        self.metadata = {"render_modes": ["rgb_array"], "render_fps": 10, "autoreset_mode": autoreset_mode}
+        self.render_mode = "rgb_array"
+        self.spec = None
+        self.closed = False
         # "raise": the reference's RuntimeError on the failing step (one 4-byte host read per step);
         # "raise_deferred": the same error without any synchronisation, raised by the NEXT call; "reset": re-initialise only the
         # failed environments inside the step (reported truncated, reward 0, info["nan"])
@@ -151,6 +157,11 @@ class _VectorBase:
 
     def close(self):
         self.sim.close()
+        self.closed = True
+
+    @property
+    def unwrapped(self):
+        return self
 
 
 class RBCVectorEnv2D(_VectorBase):

@@ -118,6 +118,10 @@ def test_info_state_and_deferred_nan_check():
     env = RBCVectorEnv2D(6, rayleigh_number=100_000, heater_duration=0.15, checkpoint=CKPT, info_state=True, nan_policy="raise_deferred")
     obs, info = env.reset(seed=0)
     assert info["state"].shape == (6, 3, 64, 96)                                 # rbc2D.py:211, opt-in for the batch
+    # the attribute surface of gymnasium.vector.VectorEnv that callers of gym.make_vec read
+    assert env.num_envs == 6 and env.unwrapped is env and not env.closed and env.metadata["autoreset_mode"] == "next_step"
+    assert env.single_observation_space.shape == (3, 8, 48) and env.observation_space.shape == (6, 3, 8, 48)
+    assert env.single_action_space.shape == (12,) and env.action_space.shape == (6, 12) and env.render_mode == "rgb_array"
     a = torch.zeros((6, 12), device="cuda")
     obs, rew, term, trunc, info = env.step(a)
     assert torch.equal(info["state"][:, :, ::8, ::2], obs) and info["t"].tolist() == [0.15] * 6 and info["step"].tolist() == [2] * 6
