@@ -327,7 +327,7 @@ struct Plan {
     HostConfigG hc;
     int B = 0, precision = 32, device = 0;
     size_t rs = 4, smem = 0;
-    int fft_threads = 512;
+    int fft_threads = 256;       // with the stages fused two at a time: 256 threads 860, 512 threads 854, 1024 threads 813 env-steps/s (RBC_B200_G3_FFT_THREADS)
     int variant = 0;             // RBC_B200_G3_VARIANT: wall-order variants of the parity study (rbc3dg_core.h); 0 = the scheme of record
     int tiled = 0;               // rows of the column patch of the tiled tendency (shared-memory plane ring; nx % 32 == 0, ny % rows == 0); 0 = per-cell kernel.  RBC_B200_G3_TILED=0|8|16 overrides
     void *P = nullptr, *G = nullptr, *Z = nullptr, *phi = nullptr, *Tb = nullptr, *cp = nullptr, *twx = nullptr, *twy = nullptr;
@@ -401,6 +401,7 @@ int create(const HostConfigG& hc, int nx, int ny, int nz, int num_envs, int prec
     if (e != cudaSuccess) { delete p; return rbc_fail(std::string("rbc3d_create: ") + cudaGetErrorString(e)); }
     {
         if (const char* v = getenv("RBC_B200_G3_VARIANT")) p->variant = atoi(v);
+        if (const char* v = getenv("RBC_B200_G3_FFT_THREADS")) { const int t = atoi(v); if (t >= 64 && t <= 1024 && t % 32 == 0) p->fft_threads = t; }
         const char* sw = getenv("RBC_B200_G3_TILED");
         const int want = sw ? atoi(sw) : 8;       // 8 rows: two CTAs per SM hide each other's barriers and copy waits (678 vs 634 env-steps/s at 64 x 64 x 32)
         p->tiled = (nx % TT_X != 0 || want == 0) ? 0 : ((want >= 16 && ny % 16 == 0) ? 16 : (ny % 8 == 0 ? 8 : 0));
