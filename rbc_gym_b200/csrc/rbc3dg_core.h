@@ -145,15 +145,19 @@ struct Tend {
 // level k is "interior" when every z-stencil of the cell has its full order and no wall ghost is involved; the march of the tiled
 // kernel runs those levels through a branch-free instantiation
 RBC_HD bool interior_level(int k, int nz) { return k >= 3 && k <= nz - 4; }
-template <typename Real, bool INTERIOR>
-RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real kappa, int nz, int k, const Windows<Real>& W, Real tb);
+// CARRY: a thread that marches a column upwards hands the four fluxes through the upper face of level k - 1 to level k, where
+// they are the fluxes through its lower face — the same function of the same values, so nothing changes in the result, but four
+// of the 24 reconstructions of a cell go away.  `zf` is that hand-over (in: lower-face fluxes of this level, out: upper-face
+// fluxes); without CARRY it is ignored.  (The w-flux is only available from level 1 on: level 0 does not evaluate it.)
+template <typename Real, bool INTERIOR, bool CARRY = false>
+RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real kappa, int nz, int k, const Windows<Real>& W, Real tb, Tend<Real>* zf = nullptr);
 template <typename Real>
 RBC_HD Tend<Real> tendency_from_windows(const ConstsG<Real>& C, Real nu, Real kappa, int nz, int k, const Windows<Real>& W, Real tb)
 {
-    return tendency_from_windows_t<Real, false>(C, nu, kappa, nz, k, W, tb);
+    return tendency_from_windows_t<Real, false, false>(C, nu, kappa, nz, k, W, tb, nullptr);
 }
-template <typename Real, bool INTERIOR>
-RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real kappa, int nz, int k, const Windows<Real>& W, Real tb)
+template <typename Real, bool INTERIOR, bool CARRY>
+RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real kappa, int nz, int k, const Windows<Real>& W, Real tb, Tend<Real>* zf)
 {
     const Real *bx = W.bx, *by = W.by, *bz = W.bz, *ux = W.ux, *uy = W.uy, *uz = W.uz, *vx = W.vx, *vy = W.vy, *vz = W.vz, *wx = W.wx, *wy = W.wy, *wz = W.wz;
     if (INTERIOR) {
@@ -163,7 +167,8 @@ RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real 
         {
             const Real Fx0 = upwind_ord(u0, bx, 5), Fx1 = upwind_ord(ux[4], bx + 1, 5);
             const Real Fy0 = upwind_ord(v0, by, 5), Fy1 = upwind_ord(vy[4], by + 1, 5);
-            const Real Fz0 = upwind_ord(w0, bz, 5), Fz1 = upwind_ord(wz[4], bz + 1, 5);
+            const Real Fz0 = CARRY ? zf->b : upwind_ord(w0, bz, 5), Fz1 = upwind_ord(wz[4], bz + 1, 5);
+            if (CARRY) zf->b = Fz1;
             const Real lap = (bx[4] - Real(2) * b0 + bx[2]) * C.idx2 + (by[4] - Real(2) * b0 + by[2]) * C.idy2 + (bz[4] - Real(2) * b0 + bz[2]) * C.idz2;
             g.b = -((Fx1 - Fx0) * C.idx + (Fy1 - Fy0) * C.idy + (Fz1 - Fz0) * C.idz) + kappa * lap;
         }
@@ -172,8 +177,9 @@ RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real 
             const Real F1 = upwind_ord(centred_ord(ux[2], ux[3], ux[4], ux[5], 4), ux + 1, 5);
             const Real G0 = upwind_ord(centred_ord(vx[1], vx[2], vx[3], vx[4], 4), uy, 5);
             const Real G1 = upwind_ord(centred_ord(W.v_jp[0], W.v_jp[1], W.v_jp[2], W.v_jp[3], 4), uy + 1, 5);
-            const Real H0 = upwind_ord(centred_ord(wx[1], wx[2], wx[3], wx[4], 4), uz, 5);
+            const Real H0 = CARRY ? zf->u : upwind_ord(centred_ord(wx[1], wx[2], wx[3], wx[4], 4), uz, 5);
             const Real H1 = upwind_ord(centred_ord(W.w_kp_x[0], W.w_kp_x[1], W.w_kp_x[2], W.w_kp_x[3], 4), uz + 1, 5);
+            if (CARRY) zf->u = H1;
             const Real lap = (ux[4] - Real(2) * u0 + ux[2]) * C.idx2 + (uy[4] - Real(2) * u0 + uy[2]) * C.idy2 + (uz[4] - Real(2) * u0 + uz[2]) * C.idz2;
             g.u = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
         }
@@ -182,8 +188,9 @@ RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real 
             const Real F1 = upwind_ord(centred_ord(W.u_ip[0], W.u_ip[1], W.u_ip[2], W.u_ip[3], 4), vx + 1, 5);
             const Real G0 = upwind_ord(centred_ord(vy[1], vy[2], vy[3], vy[4], 4), vy, 5);
             const Real G1 = upwind_ord(centred_ord(vy[2], vy[3], vy[4], vy[5], 4), vy + 1, 5);
-            const Real H0 = upwind_ord(centred_ord(wy[1], wy[2], wy[3], wy[4], 4), vz, 5);
+            const Real H0 = CARRY ? zf->v : upwind_ord(centred_ord(wy[1], wy[2], wy[3], wy[4], 4), vz, 5);
             const Real H1 = upwind_ord(centred_ord(W.w_kp_y[0], W.w_kp_y[1], W.w_kp_y[2], W.w_kp_y[3], 4), vz + 1, 5);
+            if (CARRY) zf->v = H1;
             const Real lap = (vx[4] - Real(2) * v0 + vx[2]) * C.idx2 + (vy[4] - Real(2) * v0 + vy[2]) * C.idy2 + (vz[4] - Real(2) * v0 + vz[2]) * C.idz2;
             g.v = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
         }
@@ -192,8 +199,9 @@ RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real 
             const Real F1 = upwind_ord(centred_ord(W.u_ip_z[0], W.u_ip_z[1], W.u_ip_z[2], W.u_ip_z[3], 4), wx + 1, 5);
             const Real G0 = upwind_ord(centred_ord(vz[1], vz[2], vz[3], vz[4], 4), wy, 5);
             const Real G1 = upwind_ord(centred_ord(W.v_jp_z[0], W.v_jp_z[1], W.v_jp_z[2], W.v_jp_z[3], 4), wy + 1, 5);
-            const Real H0 = upwind_ord(centred_ord(wz[1], wz[2], wz[3], wz[4], 4), wz, 5);
+            const Real H0 = CARRY ? zf->w : upwind_ord(centred_ord(wz[1], wz[2], wz[3], wz[4], 4), wz, 5);      // interior: k >= 3
             const Real H1 = upwind_ord(centred_ord(wz[2], wz[3], wz[4], wz[5], 4), wz + 1, 5);
+            if (CARRY) zf->w = H1;
             const Real lap = (wx[4] - Real(2) * w0 + wx[2]) * C.idx2 + (wy[4] - Real(2) * w0 + wy[2]) * C.idy2 + (wz[4] - Real(2) * w0 + wz[2]) * C.idz2;
             g.w = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap + Real(0.5) * (bz[2] + b0);
         }
@@ -206,8 +214,9 @@ RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real 
     {   // tracer: the advecting velocity is the face value itself
         const Real Fx0 = upwind_ord(u0, bx, 5), Fx1 = upwind_ord(ux[4], bx + 1, 5);
         const Real Fy0 = upwind_ord(v0, by, 5), Fy1 = upwind_ord(vy[4], by + 1, 5);
-        const Real Fz0 = of0 ? upwind_z_face(w0, bz, k, nz, C.variant) : Real(0);
+        const Real Fz0 = CARRY ? zf->b : (of0 ? upwind_z_face(w0, bz, k, nz, C.variant) : Real(0));
         const Real Fz1 = of1 ? upwind_z_face(wz[4], bz + 1, k + 1, nz, C.variant) : Real(0);
+        if (CARRY) zf->b = Fz1;
         const Real bdn = (k == 0) ? Real(2) * tb - b0 : bz[2];
         const Real bup = (k == nz - 1) ? Real(2) * C.b_top - b0 : bz[4];
         const Real lap = (bx[4] - Real(2) * b0 + bx[2]) * C.idx2 + (by[4] - Real(2) * b0 + by[2]) * C.idy2 + (bup - Real(2) * b0 + bdn) * C.idz2;
@@ -218,8 +227,9 @@ RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real 
         const Real F1 = upwind_ord(centred_ord(ux[2], ux[3], ux[4], ux[5], 4), ux + 1, 5);
         const Real G0 = upwind_ord(centred_ord(vx[1], vx[2], vx[3], vx[4], 4), uy, 5);
         const Real G1 = upwind_ord(centred_ord(W.v_jp[0], W.v_jp[1], W.v_jp[2], W.v_jp[3], 4), uy + 1, 5);
-        const Real H0 = of0 ? upwind_z_face(centred_ord(wx[1], wx[2], wx[3], wx[4], 4), uz, k, nz, C.variant) : Real(0);
+        const Real H0 = CARRY ? zf->u : (of0 ? upwind_z_face(centred_ord(wx[1], wx[2], wx[3], wx[4], 4), uz, k, nz, C.variant) : Real(0));
         const Real H1 = of1 ? upwind_z_face(centred_ord(W.w_kp_x[0], W.w_kp_x[1], W.w_kp_x[2], W.w_kp_x[3], 4), uz + 1, k + 1, nz, C.variant) : Real(0);
+        if (CARRY) zf->u = H1;
         const Real dn = (k == 0) ? -u0 : uz[2], up = (k == nz - 1) ? -u0 : uz[4];
         const Real lap = (ux[4] - Real(2) * u0 + ux[2]) * C.idx2 + (uy[4] - Real(2) * u0 + uy[2]) * C.idy2 + (up - Real(2) * u0 + dn) * C.idz2;
         g.u = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
@@ -229,8 +239,9 @@ RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real 
         const Real F1 = upwind_ord(centred_ord(W.u_ip[0], W.u_ip[1], W.u_ip[2], W.u_ip[3], 4), vx + 1, 5);
         const Real G0 = upwind_ord(centred_ord(vy[1], vy[2], vy[3], vy[4], 4), vy, 5);
         const Real G1 = upwind_ord(centred_ord(vy[2], vy[3], vy[4], vy[5], 4), vy + 1, 5);
-        const Real H0 = of0 ? upwind_z_face(centred_ord(wy[1], wy[2], wy[3], wy[4], 4), vz, k, nz, C.variant) : Real(0);
+        const Real H0 = CARRY ? zf->v : (of0 ? upwind_z_face(centred_ord(wy[1], wy[2], wy[3], wy[4], 4), vz, k, nz, C.variant) : Real(0));
         const Real H1 = of1 ? upwind_z_face(centred_ord(W.w_kp_y[0], W.w_kp_y[1], W.w_kp_y[2], W.w_kp_y[3], 4), vz + 1, k + 1, nz, C.variant) : Real(0);
+        if (CARRY) zf->v = H1;
         const Real dn = (k == 0) ? -v0 : vz[2], up = (k == nz - 1) ? -v0 : vz[4];
         const Real lap = (vx[4] - Real(2) * v0 + vx[2]) * C.idx2 + (vy[4] - Real(2) * v0 + vy[2]) * C.idy2 + (up - Real(2) * v0 + dn) * C.idz2;
         g.v = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap;
@@ -241,8 +252,9 @@ RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real 
         const Real F1 = upwind_ord(centred_ord(W.u_ip_z[0], W.u_ip_z[1], W.u_ip_z[2], W.u_ip_z[3], oc), wx + 1, 5);
         const Real G0 = upwind_ord(centred_ord(vz[1], vz[2], vz[3], vz[4], oc), wy, 5);
         const Real G1 = upwind_ord(centred_ord(W.v_jp_z[0], W.v_jp_z[1], W.v_jp_z[2], W.v_jp_z[3], oc), wy + 1, 5);
-        const Real H0 = upwind_z_cen(centred_ord(wz[1], wz[2], wz[3], wz[4], o_ce_cen(k - 1, nz)), wz, k - 1, nz, C.variant);
+        const Real H0 = (CARRY && k >= 2) ? zf->w : upwind_z_cen(centred_ord(wz[1], wz[2], wz[3], wz[4], o_ce_cen(k - 1, nz)), wz, k - 1, nz, C.variant);
         const Real H1 = upwind_z_cen(centred_ord(wz[2], wz[3], wz[4], wz[5], o_ce_cen(k, nz)), wz + 1, k, nz, C.variant);
+        if (CARRY) zf->w = H1;
         const Real lap = (wx[4] - Real(2) * w0 + wx[2]) * C.idx2 + (wy[4] - Real(2) * w0 + wy[2]) * C.idy2 + (wz[4] - Real(2) * w0 + wz[2]) * C.idz2;
         g.w = -((F1 - F0) * C.idx + (G1 - G0) * C.idy + (H1 - H0) * C.idz) + nu * lap + Real(0.5) * (bz[2] + b0);
     }

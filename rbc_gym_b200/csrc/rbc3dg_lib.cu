@@ -136,6 +136,7 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
         W.v_jp_z[0] = vn; W.v_jp_z[1] = vn; W.v_jp_z[2] = vn; W.v_jp_z[3] = vn;
     }
 
+    Tend<Real> zf{Real(0), Real(0), Real(0), Real(0)};      // fluxes through the lower face of the current level (wall: zero)
     for (int k = 0; k < nz; ++k) {
         if (k + 3 <= nz) copy_plane(k + 3);                   // its slot held plane k - 1: everybody is past it
         else asm volatile("cp.async.commit_group;" ::: "memory");      // keep one group per level so that wait_group 1 means "plane k + 2"
@@ -157,8 +158,8 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
             W.w_kp_y[q] = s1[3 * TT_PLANE + p0 + (q - 2) * TT_PW];
         }
         if (k + 1 < nz) { W.u_ip_z[3] = s1[TT_PLANE + p0 + 1]; W.v_jp_z[3] = s1[2 * TT_PLANE + p0 + TT_PW]; }
-        const Tend<Real> g = interior_level(k, nz) ? tendency_from_windows_t<Real, true>(C, nu, kappa, nz, k, W, tb)
-                                                   : tendency_from_windows_t<Real, false>(C, nu, kappa, nz, k, W, tb);
+        const Tend<Real> g = interior_level(k, nz) ? tendency_from_windows_t<Real, true, true>(C, nu, kappa, nz, k, W, tb, &zf)
+                                                   : tendency_from_windows_t<Real, false, true>(C, nu, kappa, nz, k, W, tb, &zf);
         rk3_substep_store<Real>(D, P, G, k * ncol + colz, colz, k, W, g, prev, dt, gam, zet, store_g != 0);
         // slide the register windows up one level
 #pragma unroll
