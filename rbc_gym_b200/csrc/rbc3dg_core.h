@@ -262,23 +262,38 @@ RBC_HD Tend<Real> tendency_from_windows_t(const ConstsG<Real>& C, Real nu, Real 
 }
 // U* = U + dt (gamma G + zeta G-); G- <- G.  `cell` = index inside a field.  The previous-stage tendencies are fetched by the
 // caller BEFORE it gathers its windows (load_prev), so that their latency hides behind the whole flux evaluation.
+// (`Gc`, `Pc`: the cell's slot in field b of the tendency slab / the predicted state; the other fields sit nc values apart — w of the
+// state too, since D.gw = 3 nc — so that a caller that knows the extents at compile time addresses everything off one pointer)
+template <typename Real>
+RBC_HD Tend<Real> load_prev_at(const Real* Gc, int nc, bool use_prev)
+{
+    Tend<Real> p{Real(0), Real(0), Real(0), Real(0)};
+    if (use_prev) { p.b = Gc[0]; p.u = Gc[nc]; p.v = Gc[2 * nc]; p.w = Gc[3 * nc]; }
+    return p;
+}
 template <typename Real>
 RBC_HD Tend<Real> load_prev(const Dims& D, const Real* G, int cell, bool use_prev)
 {
-    Tend<Real> p{Real(0), Real(0), Real(0), Real(0)};
-    if (use_prev) { p.b = G[cell]; p.u = G[D.nc + cell]; p.v = G[2 * D.nc + cell]; p.w = G[3 * D.nc + cell]; }
-    return p;
+    return load_prev_at<Real>(G + cell, D.nc, use_prev);
+}
+template <typename Real>
+RBC_HD void rk3_substep_store_at(const Dims& D, Real* Pc, Real* Gc, int k, const Windows<Real>& W, const Tend<Real>& g, const Tend<Real>& prev, Real dt,
+                                 Real gam, Real zet, bool store_g)
+{
+    const int nc = D.nc;
+    Pc[0] = W.bx[3] + dt * (gam * g.b + zet * prev.b);
+    Pc[nc] = W.ux[3] + dt * (gam * g.u + zet * prev.u);
+    Pc[2 * nc] = W.vx[3] + dt * (gam * g.v + zet * prev.v);
+    Pc[3 * nc] = (k >= 1) ? W.wx[3] + dt * (gam * g.w + zet * prev.w) : Real(0);
+    if (k == D.nz - 1) Pc[3 * nc + D.ncol] = Real(0);              // top wall face
+    if (store_g) { Gc[0] = g.b; Gc[nc] = g.u; Gc[2 * nc] = g.v; Gc[3 * nc] = g.w; }
 }
 template <typename Real>
 RBC_HD void rk3_substep_store(const Dims& D, Real* P, Real* G, int cell, int colz, int k, const Windows<Real>& W, const Tend<Real>& g,
                               const Tend<Real>& prev, Real dt, Real gam, Real zet, bool store_g)
 {
-    P[D.gb + cell] = W.bx[3] + dt * (gam * g.b + zet * prev.b);
-    P[D.gu + cell] = W.ux[3] + dt * (gam * g.u + zet * prev.u);
-    P[D.gv + cell] = W.vx[3] + dt * (gam * g.v + zet * prev.v);
-    P[D.gw + cell] = (k >= 1) ? W.wx[3] + dt * (gam * g.w + zet * prev.w) : Real(0);
-    if (k == D.nz - 1) P[D.gw + D.nc + colz] = Real(0);              // top wall face
-    if (store_g) { G[cell] = g.b; G[D.nc + cell] = g.u; G[2 * D.nc + cell] = g.v; G[3 * D.nc + cell] = g.w; }
+    (void)colz;
+    rk3_substep_store_at<Real>(D, P + cell, G + cell, k, W, g, prev, dt, gam, zet, store_g);
 }
 
 // one thread (work item) per cell, every window gathered from global memory
@@ -490,6 +505,10 @@ RBC_HD int partner_position(const Dims& D, int q)
     const int kx = bitrev(rx, D.lx2), ky = bitrev(ry, D.ly2);
     return (bitrev((D.ny - ky) & (D.ny - 1), D.ly2) << D.lx2) + bitrev((D.nx - kx) & (D.nx - 1), D.lx2);
 }
+// Both sweeps are chains of dependent steps whose operands do not depend on the chain, so they are fetched THOMAS_CHUNK plane pairs
+// at a time before the steps that use them: the kernel is one latency chain per thread (every block of the batch is resident at
+// once), and this cuts its serialised memory round trips from 2 nz/2 to 2 nz/2 / THOMAS_CHUNK.
+constexpr int THOMAS_CHUNK = 4;
 template <typename Real>
 RBC_HD void mode_pair_thomas(const Dims& D, cx<Real>* Zs, const Real* cp, Real scale, int q)
 {
@@ -497,29 +516,56 @@ RBC_HD void mode_pair_thomas(const Dims& D, cx<Real>* Zs, const Real* cp, Real s
     const int qp = partner_position(D, q);
     if (qp < q) return;
     const Real h = Real(0.5) * scale;
+    cx<Real> A[THOMAS_CHUNK], B[THOMAS_CHUNK];
+    Real c0[THOMAS_CHUNK], c1[THOMAS_CHUNK];
     cx<Real> d{Real(0), Real(0)};                            // forward elimination, level after level
-    for (int p = 0; p < nzp; ++p) {
-        const cx<Real> A = Zs[(size_t)p * ncol + q], B = Zs[(size_t)p * ncol + qp];
-        const bool odd = 2 * p + 1 < nz;
-        const Real c0 = cp[(size_t)(2 * p) * ncol + q], c1 = odd ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
-        const cx<Real> d0{((A.re + B.re) * h - d.re) * c0, ((A.im - B.im) * h - d.im) * c0};
-        const cx<Real> d1{((A.im + B.im) * h - d0.re) * c1, ((B.re - A.re) * h - d0.im) * c1};
-        d = odd ? d1 : d0;
-        if (qp == q) Zs[(size_t)p * ncol + q] = cx<Real>{d0.re, d1.re};       // two real columns
-        else { Zs[(size_t)p * ncol + q] = d0; Zs[(size_t)p * ncol + qp] = d1; }
+    for (int pb = 0; pb < nzp; pb += THOMAS_CHUNK) {
+        RBC_UNROLL
+        for (int r = 0; r < THOMAS_CHUNK; ++r) {
+            const int p = pb + r;
+            if (p < nzp) {
+                A[r] = Zs[(size_t)p * ncol + q]; B[r] = Zs[(size_t)p * ncol + qp];
+                c0[r] = cp[(size_t)(2 * p) * ncol + q]; c1[r] = (2 * p + 1 < nz) ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
+            }
+        }
+        RBC_UNROLL
+        for (int r = 0; r < THOMAS_CHUNK; ++r) {
+            const int p = pb + r;
+            if (p < nzp) {
+                const bool odd = 2 * p + 1 < nz;
+                const cx<Real> d0{((A[r].re + B[r].re) * h - d.re) * c0[r], ((A[r].im - B[r].im) * h - d.im) * c0[r]};
+                const cx<Real> d1{((A[r].im + B[r].im) * h - d0.re) * c1[r], ((B[r].re - A[r].re) * h - d0.im) * c1[r]};
+                d = odd ? d1 : d0;
+                if (qp == q) Zs[(size_t)p * ncol + q] = cx<Real>{d0.re, d1.re};       // two real columns
+                else { Zs[(size_t)p * ncol + q] = d0; Zs[(size_t)p * ncol + qp] = d1; }
+            }
+        }
     }
     cx<Real> x{Real(0), Real(0)};                            // back substitution: x_k = d_k - c_k x_{k+1}, x_{nz} = 0
-    for (int p = nzp - 1; p >= 0; --p) {
-        const bool odd = 2 * p + 1 < nz;
-        cx<Real> d0 = Zs[(size_t)p * ncol + q], d1 = Zs[(size_t)p * ncol + qp];
-        if (qp == q) { d1 = cx<Real>{d0.im, Real(0)}; d0 = cx<Real>{d0.re, Real(0)}; }
-        const Real c0 = cp[(size_t)(2 * p) * ncol + q], c1 = odd ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
-        cx<Real> x1{Real(0), Real(0)};
-        if (odd) { x1 = cx<Real>{d1.re - c1 * x.re, d1.im - c1 * x.im}; x = x1; }
-        const cx<Real> x0{d0.re - c0 * x.re, d0.im - c0 * x.im};
-        x = x0;
-        Zs[(size_t)p * ncol + q] = cx<Real>{x0.re - x1.im, x0.im + x1.re};                       // x_even + i x_odd
-        if (qp != q) Zs[(size_t)p * ncol + qp] = cx<Real>{x0.re + x1.im, x1.re - x0.im};         // conj(x_even) + i conj(x_odd)
+    for (int pb = nzp - 1; pb >= 0; pb -= THOMAS_CHUNK) {
+        RBC_UNROLL
+        for (int r = 0; r < THOMAS_CHUNK; ++r) {
+            const int p = pb - r;
+            if (p >= 0) {
+                A[r] = Zs[(size_t)p * ncol + q]; B[r] = Zs[(size_t)p * ncol + qp];
+                c0[r] = cp[(size_t)(2 * p) * ncol + q]; c1[r] = (2 * p + 1 < nz) ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
+            }
+        }
+        RBC_UNROLL
+        for (int r = 0; r < THOMAS_CHUNK; ++r) {
+            const int p = pb - r;
+            if (p >= 0) {
+                const bool odd = 2 * p + 1 < nz;
+                cx<Real> d0 = A[r], d1 = B[r];
+                if (qp == q) { d1 = cx<Real>{d0.im, Real(0)}; d0 = cx<Real>{d0.re, Real(0)}; }
+                cx<Real> x1{Real(0), Real(0)};
+                if (odd) { x1 = cx<Real>{d1.re - c1[r] * x.re, d1.im - c1[r] * x.im}; x = x1; }
+                const cx<Real> x0{d0.re - c0[r] * x.re, d0.im - c0[r] * x.im};
+                x = x0;
+                Zs[(size_t)p * ncol + q] = cx<Real>{x0.re - x1.im, x0.im + x1.re};                       // x_even + i x_odd
+                if (qp != q) Zs[(size_t)p * ncol + qp] = cx<Real>{x0.re + x1.im, x1.re - x0.im};         // conj(x_even) + i conj(x_odd)
+            }
+        }
     }
 }
 

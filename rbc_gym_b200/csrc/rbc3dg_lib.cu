@@ -48,14 +48,12 @@ g3_tendency_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real* kapp
 // reads planes k and k + 1; plane k + 3 is copied meanwhile (cp.async, no register staging, two copy groups in flight); one
 // CTA barrier per level.  Same arithmetic as the per-cell kernel (tendency_from_windows), 1 480 -> 880 instructions per cell.
 // ------------------------------------------------------------------------------------------
-constexpr int TT_X = 32, TT_PW = 40;                   // patch width; padded plane row (38 used)
+constexpr int TT_X = 32, TT_PW = 40;                   // patch width; plane row = 4 + 32 + 4 columns (3 + 32 + 3 read)
 template <int TT_Y>
 struct TileGeom {
     static constexpr int NT = TT_X * TT_Y;             // threads
     static constexpr int PH = TT_Y + 6;                // plane rows
     static constexpr int PLANE = TT_PW * PH, SLOT = 4 * PLANE;
-    static constexpr int NE = (TT_X + 6) * PH;         // elements of one field plane a CTA copies
-    static constexpr int NQ = (NE + NT - 1) / NT;
 };
 
 template <typename Real>
@@ -66,6 +64,12 @@ __device__ __forceinline__ void async_copy_value(Real* dst_shared, const Real* s
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
 }
 
+template <typename Real>
+__device__ __forceinline__ void async_copy_chunk(Real* dst_shared, const Real* src_global)      // 16 bytes, both 16-byte aligned
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
+}
+
 // fp32: 128 registers per thread, i.e. 512 resident threads per SM — one 16-row CTA or two 8-row CTAs that hide each other's
 // barriers and copy waits; fp64 needs ~240 registers and runs one CTA per SM
 template <typename Real, int TT_Y>
@@ -73,8 +77,7 @@ __global__ void __launch_bounds__(TT_X * TT_Y, sizeof(Real) == 4 ? 512 / (TT_X *
 g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real* kappa_env, const Real* S_all, Real* P_all, Real* G_all,
                          const Real* Tb_all, const int* env_ids, Real dt, Real gam, Real zet, int use_prev, int store_g)
 {
-    constexpr int TT_NT = TileGeom<TT_Y>::NT, TT_PLANE = TileGeom<TT_Y>::PLANE, TT_SLOT = TileGeom<TT_Y>::SLOT, TT_NE = TileGeom<TT_Y>::NE,
-                  TT_NQ = TileGeom<TT_Y>::NQ;
+    constexpr int TT_NT = TileGeom<TT_Y>::NT, TT_PLANE = TileGeom<TT_Y>::PLANE, TT_SLOT = TileGeom<TT_Y>::SLOT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Real* ring = reinterpret_cast<Real*>(smem_raw);
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
@@ -89,29 +92,27 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
     const Real nu = nu_env[env], kappa = kappa_env[env];
     const Real tb = Tb_all[(size_t)env * ncol + colz];
 
-    // which elements of a plane this thread copies: global column (wrapped) and slot inside the padded plane
-    int goff[TT_NQ], soff[TT_NQ];
+    // which 16-byte chunks of a level this thread copies.  A plane row starts four columns left of the patch (x0 is a multiple of 32,
+    // so every chunk is 16-byte aligned in global and in shared memory, and the periodic wrap moves whole chunks): TT_PW = 40 values
+    // = 4 + 32 + 4, of which the march reads 3 + 32 + 3.  All four fields of a level are one list of 4 * PH * (TT_PW / CH) chunks
+    // (560 per level for 8-row fp32 patches: 3 copy instructions per thread where the element-wise version issued 12).
+    constexpr int CH = 16 / (int)sizeof(Real), CPR = TT_PW / CH, NCHF = TileGeom<TT_Y>::PH * CPR, NCH = 4 * NCHF, NQ = (NCH + TT_NT - 1) / TT_NT;
+    int goff[NQ], soff[NQ];      // element offsets inside the state (field offset included) and inside a ring slot; goff < 0: nothing to copy
+    bool isw[NQ];                // chunk of w (copied for level nz too)
 #pragma unroll
-    for (int q = 0; q < TT_NQ; ++q) {
+    for (int q = 0; q < NQ; ++q) {
         const int e = tid + q * TT_NT;
-        const int pr = e / (TT_X + 6), pc = e % (TT_X + 6);
-        goff[q] = e < TT_NE ? (((y0 - 3 + pr) & (ny - 1)) * nx + ((x0 - 3 + pc) & (nx - 1))) : -1;
-        soff[q] = pr * TT_PW + pc;
+        const int f = e / NCHF, r = e % NCHF, pr = r / CPR, pc = r % CPR;
+        goff[q] = e < NCH ? (f * D.nc + ((y0 - 3 + pr) & (ny - 1)) * nx + ((x0 - 4 + pc * CH) & (nx - 1))) : -1;
+        soff[q] = f * TT_PLANE + pr * TT_PW + pc * CH;
+        isw[q] = f == 3;
     }
     auto copy_plane = [&](int level) {                        // level <= nz: w has a face there, the cell-centred fields do not
         Real* slot = ring + (level & 3) * TT_SLOT;
-        const int lo = level * ncol;
+        const Real* src = S + level * ncol;
 #pragma unroll
-        for (int q = 0; q < TT_NQ; ++q) {
-            if (goff[q] >= 0) {
-                if (level < nz) {
-                    async_copy_value(slot + soff[q], S + D.gb + lo + goff[q]);
-                    async_copy_value(slot + TT_PLANE + soff[q], S + D.gu + lo + goff[q]);
-                    async_copy_value(slot + 2 * TT_PLANE + soff[q], S + D.gv + lo + goff[q]);
-                }
-                async_copy_value(slot + 3 * TT_PLANE + soff[q], S + D.gw + lo + goff[q]);
-            }
-        }
+        for (int q = 0; q < NQ; ++q)
+            if (goff[q] >= 0 && (level < nz || isw[q])) async_copy_chunk(slot + soff[q], src + goff[q]);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     copy_plane(0);
@@ -128,7 +129,7 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
     }
     asm volatile("cp.async.wait_group 1;" ::: "memory");        // planes 0 and 1 are in
     __syncthreads();
-    const int p0 = (ly + 3) * TT_PW + lx + 3;
+    const int p0 = (ly + 3) * TT_PW + lx + 4;
     {   // neighbour-column z-windows: slots 0..2 <-> levels -2, -1, 0 (all level 0 after the clamp; slot 3 is filled per level)
         const Real* s0 = ring;
         const Real un = s0[TT_PLANE + p0 + 1], vn = s0[2 * TT_PLANE + p0 + TT_PW];
@@ -136,11 +137,15 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
         W.v_jp_z[0] = vn; W.v_jp_z[1] = vn; W.v_jp_z[2] = vn; W.v_jp_z[3] = vn;
     }
 
+    const Real* Scol = S + colz;                             // the thread's own column: field b, level 0 of the state, the predicted state
+    Real* Pcol = P + colz;                                  // and the tendency slab (fields nc values apart)
+    Real* Gcol = G + colz;
     Tend<Real> zf{Real(0), Real(0), Real(0), Real(0)};      // fluxes through the lower face of the current level (wall: zero)
     for (int k = 0; k < nz; ++k) {
         if (k + 3 <= nz) copy_plane(k + 3);                   // its slot held plane k - 1: everybody is past it
         else asm volatile("cp.async.commit_group;" ::: "memory");      // keep one group per level so that wait_group 1 means "plane k + 2"
-        const Tend<Real> prev = load_prev<Real>(D, G, k * ncol + colz, use_prev != 0);
+        Real* Gk = Gcol + k * ncol;
+        const Tend<Real> prev = load_prev_at<Real>(Gk, D.nc, use_prev != 0);
         const Real* s0 = ring + (k & 3) * TT_SLOT;
         const Real* s1 = ring + ((k + 1) & 3) * TT_SLOT;
 #pragma unroll
@@ -160,14 +165,15 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
         if (k + 1 < nz) { W.u_ip_z[3] = s1[TT_PLANE + p0 + 1]; W.v_jp_z[3] = s1[2 * TT_PLANE + p0 + TT_PW]; }
         const Tend<Real> g = interior_level(k, nz) ? tendency_from_windows_t<Real, true, true>(C, nu, kappa, nz, k, W, tb, &zf)
                                                    : tendency_from_windows_t<Real, false, true>(C, nu, kappa, nz, k, W, tb, &zf);
-        rk3_substep_store<Real>(D, P, G, k * ncol + colz, colz, k, W, g, prev, dt, gam, zet, store_g != 0);
+        rk3_substep_store_at<Real>(D, Pcol + k * ncol, Gk, k, W, g, prev, dt, gam, zet, store_g != 0);
         // slide the register windows up one level
 #pragma unroll
         for (int d = 0; d < 6; ++d) { W.bz[d] = W.bz[d + 1]; W.uz[d] = W.uz[d + 1]; W.vz[d] = W.vz[d + 1]; W.wz[d] = W.wz[d + 1]; }
         {
             const int kn = k + 4, kc = kn > nz - 1 ? nz - 1 : kn, kw = kn > nz ? nz : kn;
-            W.bz[6] = S[D.gb + kc * ncol + colz]; W.uz[6] = S[D.gu + kc * ncol + colz]; W.vz[6] = S[D.gv + kc * ncol + colz];
-            W.wz[6] = S[D.gw + kw * ncol + colz];
+            const Real* Sk = Scol + kc * ncol;
+            W.bz[6] = Sk[0]; W.uz[6] = Sk[D.nc]; W.vz[6] = Sk[2 * D.nc];
+            W.wz[6] = Scol[3 * D.nc + kw * ncol];
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q) { W.u_ip_z[q] = W.u_ip_z[q + 1]; W.v_jp_z[q] = W.v_jp_z[q + 1]; }
@@ -193,6 +199,45 @@ __device__ void stage_twiddles(const Dims& D, cx<Real>* dst, const cx<Real>* twx
     for (int q = threadIdx.x; q < hx + hy; q += blockDim.x) dst[q] = q < hx ? twx[q] : twy[q - hx];
 }
 
+// four consecutive values (16-byte aligned: rows are multiples of 8 values, field and environment strides multiples of 64) in one
+// or two vector accesses.  The vectorised kernels below evaluate exactly the expressions of cell_divergence / cell_correct on the
+// same values, four cells per thread, so that each thread has 64 ... 176 bytes in flight instead of 4 ... 48.
+template <typename Real>
+struct Quad {
+    Real v[4];
+};
+__device__ __forceinline__ Quad<float> ld4(const float* p)
+{
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    return Quad<float>{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ Quad<double> ld4(const double* p)
+{
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    return Quad<double>{{a.x, a.y, b.x, b.y}};
+}
+__device__ __forceinline__ void st4(float* p, const Quad<float>& q) { *reinterpret_cast<float4*>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]); }
+__device__ __forceinline__ void st4(double* p, const Quad<double>& q)
+{
+    *reinterpret_cast<double2*>(p) = make_double2(q.v[0], q.v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(q.v[2], q.v[3]);
+}
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
+
+// divergence of four cells of level k starting at column i (multiple of 4) of row j: the expression of cell_divergence
+template <typename Real>
+__device__ __forceinline__ Quad<Real> quad_divergence(const Dims& D, const ConstsG<Real>& C, const Real* P, int i, int j, int k, const Quad<Real>& wk,
+                                                      const Quad<Real>& wk1)
+{
+    const int row = (k * D.ny + j) * D.nx, rowp = (k * D.ny + ((j + 1) & (D.ny - 1))) * D.nx;
+    const Quad<Real> u = ld4(P + D.gu + row + i), v = ld4(P + D.gv + row + i), vp = ld4(P + D.gv + rowp + i);
+    const Real ur = P[D.gu + row + ((i + 4) & (D.nx - 1))];
+    Quad<Real> d;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) d.v[m] = ((m < 3 ? u.v[m + 1] : ur) - u.v[m]) * C.idx + (vp.v[m] - v.v[m]) * C.idy + (wk1.v[m] - wk.v[m]) * C.idz;
+    return d;
+}
+
 // divergence of TWO levels (2p in the real, 2p + 1 in the imaginary part, see mode_pair_thomas) into a shared-memory plane, then the
 // forward FFT in x and y (decimation in frequency)
 template <typename Real>
@@ -204,17 +249,31 @@ __global__ void g3_div_fft_kernel(Dims D, ConstsG<Real> C, const Real* P_all, cx
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, pz = blockIdx.x, nzp = (D.nz + 1) >> 1;
     const Real* P = P_all + (size_t)env * D.nstate;
     const bool odd = 2 * pz + 1 < D.nz;
-    // the twelve loads of a cell are independent of those of the next: unrolled so that four cells' worth are in flight per thread
+    if (aligned16(P)) {
+        // four cells per thread and iteration; the w face between the two levels is loaded once
+#pragma unroll 2
+        for (int c = 4 * threadIdx.x; c < D.ncol; c += 4 * blockDim.x) {
+            const int i = c & (D.nx - 1), j = c >> D.lx2, k = 2 * pz;
+            const Quad<Real> w0 = ld4(P + D.gw + k * D.ncol + c), w1 = ld4(P + D.gw + (k + 1) * D.ncol + c);
+            const Quad<Real> d0 = quad_divergence<Real>(D, C, P, i, j, k, w0, w1);
+            Quad<Real> d1{{Real(0), Real(0), Real(0), Real(0)}};
+            if (odd) d1 = quad_divergence<Real>(D, C, P, i, j, k + 1, w1, ld4(P + D.gw + (k + 2) * D.ncol + c));
+#pragma unroll
+            for (int m = 0; m < 4; ++m) Z[c + m] = cx<Real>{d0.v[m], d1.v[m]};
+        }
+    } else {
 #pragma unroll 4
-    for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) {
-        const int i = c & (D.nx - 1), j = c >> D.lx2;
-        Z[c] = cx<Real>{cell_divergence<Real>(D, C, P, i, j, 2 * pz), odd ? cell_divergence<Real>(D, C, P, i, j, 2 * pz + 1) : Real(0)};
+        for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) {
+            const int i = c & (D.nx - 1), j = c >> D.lx2;
+            Z[c] = cx<Real>{cell_divergence<Real>(D, C, P, i, j, 2 * pz), odd ? cell_divergence<Real>(D, C, P, i, j, 2 * pz + 1) : Real(0)};
+        }
     }
     stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
     __syncthreads();
     plane_fft_forward<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
-    cx<Real>* out = Z_all + ((size_t)env * nzp + pz) * D.ncol;
-    for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) out[c] = Z[c];
+    Real* out = reinterpret_cast<Real*>(Z_all + ((size_t)env * nzp + pz) * D.ncol);      // Z_all comes from cudaMalloc, planes are multiples of 512 bytes
+    const Real* Zr = reinterpret_cast<const Real*>(Z);
+    for (int c = 4 * threadIdx.x; c < 2 * D.ncol; c += 4 * blockDim.x) st4(out + c, ld4(Zr + c));
 }
 
 template <typename Real>
@@ -233,17 +292,20 @@ __global__ void g3_ifft_kernel(Dims D, const cx<Real>* Z_all, Real* phi_all, con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<Real>* Z = reinterpret_cast<cx<Real>*>(smem_raw);
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, pz = blockIdx.x, nzp = (D.nz + 1) >> 1;
-    const cx<Real>* in = Z_all + ((size_t)env * nzp + pz) * D.ncol;
-    for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) Z[c] = in[c];
+    const Real* in = reinterpret_cast<const Real*>(Z_all + ((size_t)env * nzp + pz) * D.ncol);
+    Real* Zr = reinterpret_cast<Real*>(Z);
+#pragma unroll 2
+    for (int c = 4 * threadIdx.x; c < 2 * D.ncol; c += 4 * blockDim.x) st4(Zr + c, ld4(in + c));
     stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
     __syncthreads();
     plane_fft_inverse<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
     const Real norm = Real(1) / (Real)D.ncol;
     Real* phi = phi_all + ((size_t)env * D.nz + 2 * pz) * D.ncol;
     const bool odd = 2 * pz + 1 < D.nz;
-    for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) {
-        phi[c] = Z[c].re * norm;
-        if (odd) phi[D.ncol + c] = Z[c].im * norm;
+    for (int c = 4 * threadIdx.x; c < D.ncol; c += 4 * blockDim.x) {
+        const Quad<Real> a = ld4(Zr + 2 * c), b = ld4(Zr + 2 * c + 4);        // four complex values
+        st4(phi + c, Quad<Real>{{a.v[0] * norm, a.v[2] * norm, b.v[0] * norm, b.v[2] * norm}});
+        if (odd) st4(phi + D.ncol + c, Quad<Real>{{a.v[1] * norm, a.v[3] * norm, b.v[1] * norm, b.v[3] * norm}});
     }
 }
 
@@ -255,6 +317,35 @@ g3_correct_kernel(Dims D, ConstsG<Real> C, Real* P_all, const Real* phi_all, con
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= D.nc) return;
     cell_correct<Real>(D, C, P_all + (size_t)env * D.nstate, phi_all + (size_t)env * D.nc, cell);
+}
+// the same for four consecutive cells of a row per thread (the expressions of cell_correct; vector loads and stores)
+template <typename Real>
+__global__ void __launch_bounds__(TB)
+g3_correct4_kernel(Dims D, ConstsG<Real> C, Real* P_all, const Real* phi_all, const int* env_ids)
+{
+    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    const int cell = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (cell >= D.nc) return;
+    Real* P = P_all + (size_t)env * D.nstate;
+    const Real* phi = phi_all + (size_t)env * D.nc;
+    const int i = cell & (D.nx - 1), j = (cell >> D.lx2) & (D.ny - 1), k = cell >> (D.lx2 + D.ly2);
+    const Quad<Real> ph = ld4(phi + cell), pj = ld4(phi + (k * D.ny + ((j - 1) & (D.ny - 1))) * D.nx + i);
+    const Real pl = phi[cell - i + ((i - 1) & (D.nx - 1))];
+    Quad<Real> u = ld4(P + D.gu + cell), v = ld4(P + D.gv + cell);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        u.v[m] -= (ph.v[m] - (m ? ph.v[m - 1] : pl)) * C.idx;
+        v.v[m] -= (ph.v[m] - pj.v[m]) * C.idy;
+    }
+    st4(P + D.gu + cell, u);
+    st4(P + D.gv + cell, v);
+    if (k >= 1) {
+        const Quad<Real> pk = ld4(phi + cell - D.ncol);
+        Quad<Real> w = ld4(P + D.gw + cell);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) w.v[m] -= (ph.v[m] - pk.v[m]) * C.idz;
+        st4(P + D.gw + cell, w);
+    }
 }
 
 // epilogue, part 1: Nusselt sum and NaN count of a chunk of cells (atomics into acc[env][2]); write-back to the environment's
@@ -449,7 +540,10 @@ static int project_t(Plan* p, const ConstsG<Real>& C, Real* buf, const int* env_
     g3_div_fft_kernel<Real><<<gplane, p->fft_threads, p->smem, st>>>(D, C, buf, (cx<Real>*)p->Z, (const cx<Real>*)p->twx, (const cx<Real>*)p->twy, env_ids);
     g3_thomas_kernel<Real><<<gmode, 128, 0, st>>>(D, (cx<Real>*)p->Z, (const Real*)p->cp, dz * dz, env_ids);
     g3_ifft_kernel<Real><<<gplane, p->fft_threads, p->smem, st>>>(D, (const cx<Real>*)p->Z, (Real*)p->phi, (const cx<Real>*)p->twx, (const cx<Real>*)p->twy, env_ids);
-    g3_correct_kernel<Real><<<gcell, TB, 0, st>>>(D, C, buf, (const Real*)p->phi, env_ids);
+    if ((reinterpret_cast<size_t>(buf) & 15) == 0)
+        g3_correct4_kernel<Real><<<dim3((D.nc / 4 + TB - 1) / TB, n), TB, 0, st>>>(D, C, buf, (const Real*)p->phi, env_ids);
+    else
+        g3_correct_kernel<Real><<<gcell, TB, 0, st>>>(D, C, buf, (const Real*)p->phi, env_ids);
     CK(cudaGetLastError());
     *launches += 4;
     return 0;
