@@ -505,10 +505,6 @@ RBC_HD int partner_position(const Dims& D, int q)
     const int kx = bitrev(rx, D.lx2), ky = bitrev(ry, D.ly2);
     return (bitrev((D.ny - ky) & (D.ny - 1), D.ly2) << D.lx2) + bitrev((D.nx - kx) & (D.nx - 1), D.lx2);
 }
-// Both sweeps are chains of dependent steps whose operands do not depend on the chain, so they are fetched THOMAS_CHUNK plane pairs
-// at a time before the steps that use them: the kernel is one latency chain per thread (every block of the batch is resident at
-// once), and this cuts its serialised memory round trips from 2 nz/2 to 2 nz/2 / THOMAS_CHUNK.
-constexpr int THOMAS_CHUNK = 4;
 template <typename Real>
 RBC_HD void mode_pair_thomas(const Dims& D, cx<Real>* Zs, const Real* cp, Real scale, int q)
 {
@@ -516,56 +512,29 @@ RBC_HD void mode_pair_thomas(const Dims& D, cx<Real>* Zs, const Real* cp, Real s
     const int qp = partner_position(D, q);
     if (qp < q) return;
     const Real h = Real(0.5) * scale;
-    cx<Real> A[THOMAS_CHUNK], B[THOMAS_CHUNK];
-    Real c0[THOMAS_CHUNK], c1[THOMAS_CHUNK];
     cx<Real> d{Real(0), Real(0)};                            // forward elimination, level after level
-    for (int pb = 0; pb < nzp; pb += THOMAS_CHUNK) {
-        RBC_UNROLL
-        for (int r = 0; r < THOMAS_CHUNK; ++r) {
-            const int p = pb + r;
-            if (p < nzp) {
-                A[r] = Zs[(size_t)p * ncol + q]; B[r] = Zs[(size_t)p * ncol + qp];
-                c0[r] = cp[(size_t)(2 * p) * ncol + q]; c1[r] = (2 * p + 1 < nz) ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
-            }
-        }
-        RBC_UNROLL
-        for (int r = 0; r < THOMAS_CHUNK; ++r) {
-            const int p = pb + r;
-            if (p < nzp) {
-                const bool odd = 2 * p + 1 < nz;
-                const cx<Real> d0{((A[r].re + B[r].re) * h - d.re) * c0[r], ((A[r].im - B[r].im) * h - d.im) * c0[r]};
-                const cx<Real> d1{((A[r].im + B[r].im) * h - d0.re) * c1[r], ((B[r].re - A[r].re) * h - d0.im) * c1[r]};
-                d = odd ? d1 : d0;
-                if (qp == q) Zs[(size_t)p * ncol + q] = cx<Real>{d0.re, d1.re};       // two real columns
-                else { Zs[(size_t)p * ncol + q] = d0; Zs[(size_t)p * ncol + qp] = d1; }
-            }
-        }
+    for (int p = 0; p < nzp; ++p) {
+        const cx<Real> A = Zs[(size_t)p * ncol + q], B = Zs[(size_t)p * ncol + qp];
+        const bool odd = 2 * p + 1 < nz;
+        const Real c0 = cp[(size_t)(2 * p) * ncol + q], c1 = odd ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
+        const cx<Real> d0{((A.re + B.re) * h - d.re) * c0, ((A.im - B.im) * h - d.im) * c0};
+        const cx<Real> d1{((A.im + B.im) * h - d0.re) * c1, ((B.re - A.re) * h - d0.im) * c1};
+        d = odd ? d1 : d0;
+        if (qp == q) Zs[(size_t)p * ncol + q] = cx<Real>{d0.re, d1.re};       // two real columns
+        else { Zs[(size_t)p * ncol + q] = d0; Zs[(size_t)p * ncol + qp] = d1; }
     }
     cx<Real> x{Real(0), Real(0)};                            // back substitution: x_k = d_k - c_k x_{k+1}, x_{nz} = 0
-    for (int pb = nzp - 1; pb >= 0; pb -= THOMAS_CHUNK) {
-        RBC_UNROLL
-        for (int r = 0; r < THOMAS_CHUNK; ++r) {
-            const int p = pb - r;
-            if (p >= 0) {
-                A[r] = Zs[(size_t)p * ncol + q]; B[r] = Zs[(size_t)p * ncol + qp];
-                c0[r] = cp[(size_t)(2 * p) * ncol + q]; c1[r] = (2 * p + 1 < nz) ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
-            }
-        }
-        RBC_UNROLL
-        for (int r = 0; r < THOMAS_CHUNK; ++r) {
-            const int p = pb - r;
-            if (p >= 0) {
-                const bool odd = 2 * p + 1 < nz;
-                cx<Real> d0 = A[r], d1 = B[r];
-                if (qp == q) { d1 = cx<Real>{d0.im, Real(0)}; d0 = cx<Real>{d0.re, Real(0)}; }
-                cx<Real> x1{Real(0), Real(0)};
-                if (odd) { x1 = cx<Real>{d1.re - c1[r] * x.re, d1.im - c1[r] * x.im}; x = x1; }
-                const cx<Real> x0{d0.re - c0[r] * x.re, d0.im - c0[r] * x.im};
-                x = x0;
-                Zs[(size_t)p * ncol + q] = cx<Real>{x0.re - x1.im, x0.im + x1.re};                       // x_even + i x_odd
-                if (qp != q) Zs[(size_t)p * ncol + qp] = cx<Real>{x0.re + x1.im, x1.re - x0.im};         // conj(x_even) + i conj(x_odd)
-            }
-        }
+    for (int p = nzp - 1; p >= 0; --p) {
+        const bool odd = 2 * p + 1 < nz;
+        cx<Real> d0 = Zs[(size_t)p * ncol + q], d1 = Zs[(size_t)p * ncol + qp];
+        if (qp == q) { d1 = cx<Real>{d0.im, Real(0)}; d0 = cx<Real>{d0.re, Real(0)}; }
+        const Real c0 = cp[(size_t)(2 * p) * ncol + q], c1 = odd ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
+        cx<Real> x1{Real(0), Real(0)};
+        if (odd) { x1 = cx<Real>{d1.re - c1 * x.re, d1.im - c1 * x.im}; x = x1; }
+        const cx<Real> x0{d0.re - c0 * x.re, d0.im - c0 * x.im};
+        x = x0;
+        Zs[(size_t)p * ncol + q] = cx<Real>{x0.re - x1.im, x0.im + x1.re};                       // x_even + i x_odd
+        if (qp != q) Zs[(size_t)p * ncol + qp] = cx<Real>{x0.re + x1.im, x1.re - x0.im};         // conj(x_even) + i conj(x_odd)
     }
 }
 
