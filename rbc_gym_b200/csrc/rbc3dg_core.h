@@ -456,6 +456,7 @@ template <typename Real, typename Run>
 RBC_HD void line_fft_forward(const Dims& D, cx<Real>* Z, int ln, int lnl, int line_stride, int elem_stride, bool lines_fastest, const cx<Real>* tw, Run run)
 {
     int ls = ln - 1;
+    RBC_UNROLL
     for (; ls >= 1; ls -= 2) run(D.ncol >> 2, [&](int it) { butterfly2_dif<Real>(Z, ln, ls, lnl, line_stride, elem_stride, lines_fastest, tw, it); });
     if (ls == 0) run(D.ncol >> 1, [&](int it) { butterfly_dif<Real>(Z, ln, 0, lnl, line_stride, elem_stride, lines_fastest, tw, it); });
 }
@@ -463,6 +464,7 @@ template <typename Real, typename Run>
 RBC_HD void line_fft_inverse(const Dims& D, cx<Real>* Z, int ln, int lnl, int line_stride, int elem_stride, bool lines_fastest, const cx<Real>* tw, Run run)
 {
     int ls = 0;
+    RBC_UNROLL
     for (; ls + 1 <= ln - 1; ls += 2) run(D.ncol >> 2, [&](int it) { butterfly2_dit_inv<Real>(Z, ln, ls, lnl, line_stride, elem_stride, lines_fastest, tw, it); });
     if (ls == ln - 1) run(D.ncol >> 1, [&](int it) { butterfly_dit_inv<Real>(Z, ln, ls, lnl, line_stride, elem_stride, lines_fastest, tw, it); });
 }

@@ -191,6 +191,32 @@ struct BlockRun {
         __syncthreads();
     }
 };
+// the same for a CTA size and (after inlining, with compile-time plane extents) an item count known to the compiler: the item loop
+// unrolls and the index arithmetic of every butterfly folds into constants
+template <int NT>
+struct BlockRunFixed {
+    template <typename F>
+    __device__ __forceinline__ void operator()(int n_items, F fn) const
+    {
+#pragma unroll
+        for (int it = threadIdx.x; it < n_items; it += NT) fn(it);
+        __syncthreads();
+    }
+};
+constexpr int FFT_NT = 256;      // CTA size of the plane kernels instantiated with compile-time extents
+// Plane extents known at compile time (LX2 = log2 nx, LY2 = log2 ny; 0 = the run-time grid).  Two thirds of the ~130 instructions of a
+// radix-4 step of the run-time version are index arithmetic (run-time shifts, masks and strides); with constant extents it folds away.
+// Same butterflies in the same order on the same values: bit-identical results.
+template <int LX2, int LY2>
+__device__ __forceinline__ Dims plane_dims(const Dims& D)
+{
+    if (LX2 == 0) return D;
+    Dims F = D;
+    F.nx = 1 << LX2; F.ny = 1 << LY2; F.ncol = 1 << (LX2 + LY2); F.lx2 = LX2; F.ly2 = LY2;
+    F.nc = F.ncol * D.nz; F.nw = F.ncol * (D.nz + 1); F.nstate = 3 * F.nc + F.nw;
+    F.gb = 0; F.gu = F.nc; F.gv = 2 * F.nc; F.gw = 3 * F.nc;
+    return F;
+}
 // twiddles of both directions into shared memory, behind the plane: [nx/2] then [ny/2] complex
 template <typename Real>
 __device__ void stage_twiddles(const Dims& D, cx<Real>* dst, const cx<Real>* twx, const cx<Real>* twy)
@@ -240,12 +266,13 @@ __device__ __forceinline__ Quad<Real> quad_divergence(const Dims& D, const Const
 
 // divergence of TWO levels (2p in the real, 2p + 1 in the imaginary part, see mode_pair_thomas) into a shared-memory plane, then the
 // forward FFT in x and y (decimation in frequency)
-template <typename Real>
-__global__ void g3_div_fft_kernel(Dims D, ConstsG<Real> C, const Real* P_all, cx<Real>* Z_all, const cx<Real>* twx, const cx<Real>* twy,
-                                  const int* env_ids)
+template <typename Real, int LX2 = 0, int LY2 = 0>
+__global__ void __launch_bounds__(LX2 ? FFT_NT : 1024)
+g3_div_fft_kernel(Dims D_arg, ConstsG<Real> C, const Real* P_all, cx<Real>* Z_all, const cx<Real>* twx, const cx<Real>* twy, const int* env_ids)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<Real>* Z = reinterpret_cast<cx<Real>*>(smem_raw);
+    const Dims D = plane_dims<LX2, LY2>(D_arg);
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, pz = blockIdx.x, nzp = (D.nz + 1) >> 1;
     const Real* P = P_all + (size_t)env * D.nstate;
     const bool odd = 2 * pz + 1 < D.nz;
@@ -270,7 +297,8 @@ __global__ void g3_div_fft_kernel(Dims D, ConstsG<Real> C, const Real* P_all, cx
     }
     stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
     __syncthreads();
-    plane_fft_forward<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
+    if (LX2) plane_fft_forward<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRunFixed<FFT_NT>{});
+    else plane_fft_forward<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
     Real* out = reinterpret_cast<Real*>(Z_all + ((size_t)env * nzp + pz) * D.ncol);      // Z_all comes from cudaMalloc, planes are multiples of 512 bytes
     const Real* Zr = reinterpret_cast<const Real*>(Z);
     for (int c = 4 * threadIdx.x; c < 2 * D.ncol; c += 4 * blockDim.x) st4(out + c, ld4(Zr + c));
@@ -286,11 +314,13 @@ __global__ void g3_thomas_kernel(Dims D, cx<Real>* Z_all, const Real* cp, Real s
 }
 
 // inverse FFT of one plane (decimation in time, bit-reversed order in, natural order out) -> phi of levels 2p (real part) and 2p + 1
-template <typename Real>
-__global__ void g3_ifft_kernel(Dims D, const cx<Real>* Z_all, Real* phi_all, const cx<Real>* twx, const cx<Real>* twy, const int* env_ids)
+template <typename Real, int LX2 = 0, int LY2 = 0>
+__global__ void __launch_bounds__(LX2 ? FFT_NT : 1024)
+g3_ifft_kernel(Dims D_arg, const cx<Real>* Z_all, Real* phi_all, const cx<Real>* twx, const cx<Real>* twy, const int* env_ids)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<Real>* Z = reinterpret_cast<cx<Real>*>(smem_raw);
+    const Dims D = plane_dims<LX2, LY2>(D_arg);
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, pz = blockIdx.x, nzp = (D.nz + 1) >> 1;
     const Real* in = reinterpret_cast<const Real*>(Z_all + ((size_t)env * nzp + pz) * D.ncol);
     Real* Zr = reinterpret_cast<Real*>(Z);
@@ -298,7 +328,8 @@ __global__ void g3_ifft_kernel(Dims D, const cx<Real>* Z_all, Real* phi_all, con
     for (int c = 4 * threadIdx.x; c < 2 * D.ncol; c += 4 * blockDim.x) st4(Zr + c, ld4(in + c));
     stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
     __syncthreads();
-    plane_fft_inverse<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
+    if (LX2) plane_fft_inverse<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRunFixed<FFT_NT>{});
+    else plane_fft_inverse<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
     const Real norm = Real(1) / (Real)D.ncol;
     Real* phi = phi_all + ((size_t)env * D.nz + 2 * pz) * D.ncol;
     const bool odd = 2 * pz + 1 < D.nz;
@@ -420,6 +451,7 @@ struct Plan {
     HostConfigG hc;
     int B = 0, precision = 32, device = 0;
     size_t rs = 4, smem = 0;
+    int fixed_plane = 0;         // 66 / 55: the plane kernels run their instantiation with compile-time extents (64 x 64 / 32 x 32 columns); RBC_B200_G3_FIXED_PLANE=0: run-time extents
     int fft_threads = 256;       // with the stages fused two at a time: 256 threads 860, 512 threads 854, 1024 threads 813 env-steps/s (RBC_B200_G3_FFT_THREADS)
     int variant = 0;             // RBC_B200_G3_VARIANT: wall-order variants of the parity study (rbc3dg_core.h); 0 = the scheme of record
     int tiled = 0;               // rows of the column patch of the tiled tendency (shared-memory plane ring; nx % 32 == 0, ny % rows == 0); 0 = per-cell kernel.  RBC_B200_G3_TILED=0|8|16 overrides
@@ -494,12 +526,16 @@ int create(const HostConfigG& hc, int nx, int ny, int nz, int num_envs, int prec
     p->smem = ((size_t)p->D.ncol + p->D.nx / 2 + p->D.ny / 2) * 2 * p->rs;      // one complex plane + the twiddles of both directions
     if (p->smem > 227 * 1024) { delete p; return rbc_fail("rbc3d_create: a horizontal plane of this grid does not fit the shared memory of an SM"); }
     cudaError_t e = cudaSuccess;
-    if (precision == 32) {
-        e = cudaFuncSetAttribute(g3_div_fft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(g3_ifft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-    } else {
-        e = cudaFuncSetAttribute(g3_div_fft_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(g3_ifft_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    {
+        const char* fx = getenv("RBC_B200_G3_FIXED_PLANE");
+        if (!(fx && atoi(fx) == 0)) p->fixed_plane = (nx == 64 && ny == 64) ? 66 : ((nx == 32 && ny == 32) ? 55 : 0);
+        const void* fns[6] = {precision == 32 ? (const void*)g3_div_fft_kernel<float> : (const void*)g3_div_fft_kernel<double>,
+                              precision == 32 ? (const void*)g3_ifft_kernel<float> : (const void*)g3_ifft_kernel<double>,
+                              precision == 32 ? (const void*)g3_div_fft_kernel<float, 6, 6> : (const void*)g3_div_fft_kernel<double, 6, 6>,
+                              precision == 32 ? (const void*)g3_ifft_kernel<float, 6, 6> : (const void*)g3_ifft_kernel<double, 6, 6>,
+                              precision == 32 ? (const void*)g3_div_fft_kernel<float, 5, 5> : (const void*)g3_div_fft_kernel<double, 5, 5>,
+                              precision == 32 ? (const void*)g3_ifft_kernel<float, 5, 5> : (const void*)g3_ifft_kernel<double, 5, 5>};
+        for (int q = 0; q < 6 && e == cudaSuccess; ++q) e = cudaFuncSetAttribute(fns[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
     }
     if (e != cudaSuccess) { delete p; return rbc_fail(std::string("rbc3d_create: ") + cudaGetErrorString(e)); }
     {
@@ -567,9 +603,15 @@ static int project_t(Plan* p, const ConstsG<Real>& C, Real* buf, const int* env_
     const Dims& D = p->D;
     const dim3 gplane((D.nz + 1) / 2, n), gcell((D.nc + TB - 1) / TB, n), gmode((D.ncol + 127) / 128, n);
     const Real dz = (Real)(p->hc.lz / D.nz);
-    g3_div_fft_kernel<Real><<<gplane, p->fft_threads, p->smem, st>>>(D, C, buf, (cx<Real>*)p->Z, (const cx<Real>*)p->twx, (const cx<Real>*)p->twy, env_ids);
-    g3_thomas_kernel<Real><<<gmode, 128, 0, st>>>(D, (cx<Real>*)p->Z, (const Real*)p->cp, dz * dz, env_ids);
-    g3_ifft_kernel<Real><<<gplane, p->fft_threads, p->smem, st>>>(D, (const cx<Real>*)p->Z, (Real*)p->phi, (const cx<Real>*)p->twx, (const cx<Real>*)p->twy, env_ids);
+    cx<Real>* Z = (cx<Real>*)p->Z;
+    const cx<Real>*twx = (const cx<Real>*)p->twx, *twy = (const cx<Real>*)p->twy;
+    if (p->fixed_plane == 66) g3_div_fft_kernel<Real, 6, 6><<<gplane, FFT_NT, p->smem, st>>>(D, C, buf, Z, twx, twy, env_ids);
+    else if (p->fixed_plane == 55) g3_div_fft_kernel<Real, 5, 5><<<gplane, FFT_NT, p->smem, st>>>(D, C, buf, Z, twx, twy, env_ids);
+    else g3_div_fft_kernel<Real><<<gplane, p->fft_threads, p->smem, st>>>(D, C, buf, Z, twx, twy, env_ids);
+    g3_thomas_kernel<Real><<<gmode, 128, 0, st>>>(D, Z, (const Real*)p->cp, dz * dz, env_ids);
+    if (p->fixed_plane == 66) g3_ifft_kernel<Real, 6, 6><<<gplane, FFT_NT, p->smem, st>>>(D, Z, (Real*)p->phi, twx, twy, env_ids);
+    else if (p->fixed_plane == 55) g3_ifft_kernel<Real, 5, 5><<<gplane, FFT_NT, p->smem, st>>>(D, Z, (Real*)p->phi, twx, twy, env_ids);
+    else g3_ifft_kernel<Real><<<gplane, p->fft_threads, p->smem, st>>>(D, Z, (Real*)p->phi, twx, twy, env_ids);
     if ((reinterpret_cast<size_t>(buf) & 15) == 0)
         g3_correct4_kernel<Real><<<dim3((D.nc / 4 + TB - 1) / TB, n), TB, 0, st>>>(D, C, buf, (const Real*)p->phi, env_ids);
     else
