@@ -40,13 +40,14 @@ g3_tendency_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real* kapp
 }
 
 // ------------------------------------------------------------------------------------------
-// Tiled tendency (grids with nx % 32 == 0, ny % 16 == 0).  A CTA owns a 32 x 16 patch of columns and marches it up through the
-// levels: one thread per column, the z-windows of its own column slide through registers (one coalesced global load per field
-// and level), and everything it needs from its neighbours comes from a RING OF THREE LEVEL PLANES WITH HALO in shared memory
-// (38 x 22 values per field: the periodic wrap is resolved once, when a thread computes which element of a plane it copies),
-// so every stencil access of the march is a shared-memory load at a compile-time offset from the thread's own slot.  Level k
-// reads planes k and k + 1; plane k + 3 is copied meanwhile (cp.async, no register staging, two copy groups in flight); one
-// CTA barrier per level.  Same arithmetic as the per-cell kernel (tendency_from_windows), 1 480 -> 880 instructions per cell.
+// Tiled tendency (grids with nx % 32 == 0, ny % 8 == 0).  A CTA owns a 32 x 8 (or 32 x 16) patch of columns and marches it up through
+// the levels: one thread per column, the z-windows of its own column slide through registers (one coalesced global load per field
+// and level), and everything it needs from its neighbours comes from a RING OF FOUR LEVEL PLANES WITH HALO in shared memory
+// (40 x 14 values per field: 4 + 32 + 4 columns, 3 + 8 + 3 rows; the periodic wrap is resolved once, when a thread computes which
+// 16-byte chunks of a level it copies), so every stencil access of the march is a shared-memory load at a compile-time offset from
+// the thread's own slot.  Level k reads planes k and k + 1; plane k + 3 is copied meanwhile (cp.async, 16 bytes per instruction, no
+// register staging, two copy groups in flight); one CTA barrier per level.  Same arithmetic as the per-cell kernel
+// (tendency_from_windows), 1 480 -> 685 instructions per cell.
 // ------------------------------------------------------------------------------------------
 constexpr int TT_X = 32, TT_PW = 40;                   // patch width; plane row = 4 + 32 + 4 columns (3 + 32 + 3 read)
 template <int TT_Y>
@@ -55,14 +56,6 @@ struct TileGeom {
     static constexpr int PH = TT_Y + 6;                // plane rows
     static constexpr int PLANE = TT_PW * PH, SLOT = 4 * PLANE;
 };
-
-template <typename Real>
-__device__ __forceinline__ void async_copy_value(Real* dst_shared, const Real* src_global)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
-    if (sizeof(Real) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src_global) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
-}
 
 template <typename Real>
 __device__ __forceinline__ void async_copy_chunk(Real* dst_shared, const Real* src_global)      // 16 bytes, both 16-byte aligned
