@@ -372,7 +372,8 @@ g3_correct4_kernel(Dims D, ConstsG<Real> C, Real* P_all, const Real* phi_all, co
     }
 }
 
-// epilogue, part 1: Nusselt sum and NaN count of a chunk of cells (atomics into acc[env][2]); write-back to the environment's
+// epilogue, part 1: Nusselt sum and NaN count of a chunk of cells (one partial per block into acc[env][block][2], added up in block
+// order by part 2: the Nusselt number — the reward — is reproducible bit for bit, which atomics would not give); write-back to the environment's
 // own array when the march ended in the other buffer; observation = get_state (rbc_sim3D_api.jl:106-121, rbc3D.py:229-232)
 template <typename Real>
 __global__ void __launch_bounds__(TB)
@@ -403,21 +404,23 @@ g3_reduce_kernel(Dims D, ConstsG<Real> C, const Real* cur_all, Real* st_all, flo
         if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { atomicAdd(&acc[2 * env], sa[0]); atomicAdd(&acc[2 * env + 1], sb[0]); }
+    if (threadIdx.x == 0) { acc[((size_t)env * gridDim.x + blockIdx.x) * 2] = sa[0]; acc[((size_t)env * gridDim.x + blockIdx.x) * 2 + 1] = sb[0]; }
 }
 
 // epilogue, part 2: Nusselt number, reward, NaN flag, clock and truncation of every listed environment
 template <typename Real>
-__global__ void g3_finalize_kernel(Dims D, ConstsG<Real> C, const double* kappa_env, const double* acc, rbc3dg_api::IoRaw io, const int* env_ids,
-                                   int n, int advance_clock)
+__global__ void g3_finalize_kernel(Dims D, ConstsG<Real> C, const double* kappa_env, const double* acc, int nblocks, rbc3dg_api::IoRaw io,
+                                   const int* env_ids, int n, int advance_clock)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const int env = env_ids ? env_ids[j] : j;
-    const double nu = 1.0 + (acc[2 * env] / (double)D.nc) / kappa_env[env];
+    double sum = 0, bad = 0;
+    for (int b = 0; b < nblocks; ++b) { sum += acc[((size_t)env * nblocks + b) * 2]; bad += acc[((size_t)env * nblocks + b) * 2 + 1]; }
+    const double nu = 1.0 + (sum / (double)D.nc) / kappa_env[env];
     io.nusselt[env] = nu;
     io.reward[env] = (float)(-nu);
-    io.nan_flag[env] = acc[2 * env + 1] > 0 ? 1 : 0;
+    io.nan_flag[env] = bad > 0 ? 1 : 0;
     if (advance_clock) {
         const double tn = io.t[env] + C.dt_action;
         io.t[env] = tn;
@@ -426,19 +429,12 @@ __global__ void g3_finalize_kernel(Dims D, ConstsG<Real> C, const double* kappa_
     }
 }
 
-__global__ void g3_zero_acc_kernel(double* acc, const int* env_ids, int n)
-{
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const int env = env_ids ? env_ids[j] : j;
-    acc[2 * env] = 0.0; acc[2 * env + 1] = 0.0;
-}
-
 }  // namespace
 
 namespace rbc3dg_api {
 
 constexpr int MAX_CHAINS = 4;
+constexpr int MAX_RBLOCKS = 128;      // blocks per environment of the epilogue reduction
 struct Plan {
     Dims D;
     HostConfigG hc;
@@ -550,7 +546,7 @@ int create(const HostConfigG& hc, int nx, int ny, int nz, int num_envs, int prec
     struct { void** ptr; size_t bytes; } allocs[] = {
         {&p->P, B * D.nstate * rs}, {&p->G, B * 4 * D.nc * rs}, {&p->Z, B * D.nc * 2 * rs}, {&p->phi, B * D.nc * rs},
         {&p->Tb, B * D.ncol * rs}, {&p->nu, B * rs}, {&p->kappa, B * rs}, {(void**)&p->kappa_d, B * sizeof(double)},
-        {(void**)&p->acc, B * 2 * sizeof(double)}};
+        {(void**)&p->acc, B * MAX_RBLOCKS * 2 * sizeof(double)}};
     for (auto& a : allocs) {
         e = cudaMalloc(a.ptr, a.bytes);
         if (e != cudaSuccess) { destroy(p); return rbc_fail(std::string("rbc3d_create: cudaMalloc: ") + cudaGetErrorString(e)); }
@@ -684,12 +680,11 @@ static int launch_t(Plan* p, const IoRaw& io, const int* env_ids, int n, int nsu
         CK(cudaEventRecord(p->ev_join[c - 1], strm[c]));
         CK(cudaStreamWaitEvent(st, p->ev_join[c - 1], 0));
     }
-    const int rblocks = (D.nc + 4 * TB - 1) / (4 * TB) < 128 ? (D.nc + 4 * TB - 1) / (4 * TB) : 128;
-    g3_zero_acc_kernel<<<(n + 127) / 128, 128, 0, st>>>(p->acc, env_ids, n);
+    const int rblocks = (D.nc + 4 * TB - 1) / (4 * TB) < MAX_RBLOCKS ? (D.nc + 4 * TB - 1) / (4 * TB) : MAX_RBLOCKS;
     g3_reduce_kernel<Real><<<dim3(rblocks, n), TB, 0, st>>>(D, C, cur, S, io.obs, p->acc, env_ids);
-    g3_finalize_kernel<Real><<<(n + 127) / 128, 128, 0, st>>>(D, C, p->kappa_d, p->acc, io, env_ids, n, advance_clock);
+    g3_finalize_kernel<Real><<<(n + 127) / 128, 128, 0, st>>>(D, C, p->kappa_d, p->acc, rblocks, io, env_ids, n, advance_clock);
     CK(cudaGetLastError());
-    *launches += 3;
+    *launches += 2;
     return 0;
 }
 

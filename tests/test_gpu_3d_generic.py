@@ -99,6 +99,39 @@ def test_tiled_tendency_equals_the_per_cell_kernel(monkeypatch, shape):
         assert np.allclose(out["tiled"][1], out["cell"][1], rtol=100 * tol)
 
 
+@pytest.mark.parametrize("shape,envs", [((32, 64, 64), 33), ((8, 32, 32), 5)])
+def test_chains_and_compile_time_plane_extents_change_no_bit(monkeypatch, shape, envs):
+    """Two scheduling / code-generation choices of the generic path must be invisible in the results: (i) the batch runs as up to four
+    independent chains on separate streams (`RBC_B200_G3_STREAMS`; uneven cuts here: 33 = 9 + 8 + 8 + 8, 5 = 3 + 2) — environments never
+    interact; (ii) the FFT plane kernels instantiated with compile-time plane extents for 64 x 64 and 32 x 32 columns
+    (`RBC_B200_G3_FIXED_PLANE`) run the same butterflies in the same order as the run-time-extent kernels.  Bitwise equality of a
+    two-step rollout, states and Nusselt numbers, in the throughput precision."""
+    import torch
+    from rbc_gym_b200 import backend
+    from rbc_gym_b200.envs import noise_initial_fields_3d
+    f = np.concatenate([noise_initial_fields_3d(np.random.default_rng(s), shape, kick=0.05) for s in range(4)])[np.arange(envs) % 4]
+    a = torch.rand((envs, 8, 8), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)) * 2 - 1
+    ra = np.linspace(5e3, 4e4, envs)
+    out = {}
+    for name, streams, fixed in (("product", None, None), ("one-chain", "1", None), ("two-chains", "2", None), ("run-time-planes", None, "0")):
+        for key, val in (("RBC_B200_G3_STREAMS", streams), ("RBC_B200_G3_FIXED_PLANE", fixed)):
+            if val is None:
+                monkeypatch.delenv(key, raising=False)
+            else:
+                monkeypatch.setenv(key, val)
+        sim = backend.Sim3D(envs, ra=1e4, state_shape=shape, heater_duration=0.05, precision=32)
+        sim.set_rayleigh(ra)
+        sim.reset_from_fields(f, project=True)
+        for _ in range(2):
+            _, _, nu, _, nan = sim.step(a)
+        assert int(nan.sum()) == 0
+        out[name] = (sim.fields().copy(), nu.cpu().numpy().copy())
+        sim.close()
+    for name in ("one-chain", "two-chains", "run-time-planes"):
+        assert np.array_equal(out[name][0], out["product"][0]), name
+        assert np.array_equal(out[name][1], out["product"][1]), name
+
+
 def test_vector_env_on_a_generic_grid_and_per_environment_rayleigh():
     import torch
     from rbc_gym_b200.envs import RBCVectorEnv3D
