@@ -663,8 +663,9 @@ class Sim3D:
 
     @property
     def fused_autoreset(self) -> bool:
-        """The auto-reset is fused into the dedicated 32 x 32 x 16 kernel only; other grids drive resets from the caller."""
-        return self.state_shape == (NZ3, NY3, NX3) and os.environ.get("RBC_B200_3D_GENERIC", "") != "1"
+        """The auto-reset is fused into the step on every grid: in the epilogue of the dedicated 32 x 32 x 16 kernel, and as batch
+        kernels behind the march of the stage-streaming path (`rbc3dg_lib.cu`)."""
+        return True
 
     def set_rayleigh(self, ra_per_env):
         """One Rayleigh number per environment (`rbc3d_set_rayleigh_per_env`; stage-streaming kernels, i.e. grids other than

@@ -222,7 +222,6 @@ static int dispatch3(rbc3d_sim* s, const float* actions, float* obs, float* rewa
                      int n, RunFlags3 F, bool time_it, bool want_obs = true, const rbc2d::VecIO& vec = rbc2d::VecIO())
 {
     if (s->plan) {
-        if (vec.mode >= 0) return rbc_fail("rbc3d: the fused vector step is available on the 32 x 32 x 16 grid only; drive resets from the caller");
         rbc3dg_api::IoRaw io;
         io.state = s->state;
         io.actions = actions ? actions : s->actions;
@@ -234,7 +233,7 @@ static int dispatch3(rbc3d_sim* s, const float* actions, float* obs, float* rewa
         io.nan_flag = nan ? nan : s->nan;
         if (n <= 0) return 0;
         if (time_it) CK(cudaEventRecord(s->ev0, s->stream));
-        int rc = rbc3dg_api::launch(s->plan, io, env_ids, n, F.nsub, F.project_first, F.advance_clock, s->stream, &s->launches);
+        int rc = rbc3dg_api::launch(s->plan, io, env_ids, n, F.nsub, F.project_first, F.advance_clock, s->stream, &s->launches, vec.mode >= 0 ? &vec : nullptr);
         if (rc) return rc;
         if (time_it) { CK(cudaEventRecord(s->ev1, s->stream)); s->timed = true; }
         return 0;

@@ -30,8 +30,10 @@ void destroy(Plan* p);
 // Rayleigh number per environment (host array [B]; nullptr restores the configuration's value for all)
 int set_rayleigh(Plan* p, const double* ra_host);
 // one pass over the listed environments: optional set! projection, nsub RK3 steps, epilogue (observation, Nusselt, flags, clock)
+// `vec` (mode >= 0, with advance_clock): the fused vector-env semantics of rbc2d::VecIO — auto-reset from the checkpoint bank in
+// next_step / same_step mode, NaN reset, episode returns, terminal observations (final_nu_a = terminal Nusselt number)
 int launch(Plan* p, const IoRaw& io, const int* env_ids, int n, int nsub, int project_first, int advance_clock, cudaStream_t stream,
-           int64_t* launches);
+           int64_t* launches, const rbc2d::VecIO* vec = nullptr);
 int nsub_of(const Plan* p);
 size_t smem_bytes(const Plan* p);
 int values_per_env(const Plan* p);

@@ -21,6 +21,7 @@ template <typename Real>
 __global__ void g3_heater_kernel(Dims D, ConstsG<Real> C, const float* actions, Real* Tb, const int* env_ids)
 {
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= D.ncol) return;
     Tb[(size_t)env * D.ncol + c] = (Real)heater_patch_T(C.heaters, C.heater_limit, C.b_hot, actions + (size_t)env * C.heaters * C.heaters,
@@ -33,6 +34,7 @@ g3_tendency_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real* kapp
                    const Real* Tb_all, const int* env_ids, Real dt, Real gam, Real zet, int use_prev, int store_g)
 {
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= D.nc) return;
     cell_tendency<Real>(D, C, nu_env[env], kappa_env[env], S_all + (size_t)env * D.nstate, P_all + (size_t)env * D.nstate,
@@ -74,6 +76,7 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Real* ring = reinterpret_cast<Real*>(smem_raw);
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const int nx = D.nx, ny = D.ny, nz = D.nz, ncol = D.ncol;
     const int tiles_x = nx / TT_X;
     const int x0 = (blockIdx.x % tiles_x) * TT_X, y0 = (blockIdx.x / tiles_x) * TT_Y;
@@ -267,6 +270,7 @@ g3_div_fft_kernel(Dims D_arg, ConstsG<Real> C, const Real* P_all, cx<Real>* Z_al
     cx<Real>* Z = reinterpret_cast<cx<Real>*>(smem_raw);
     const Dims D = plane_dims<LX2, LY2>(D_arg);
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, pz = blockIdx.x, nzp = (D.nz + 1) >> 1;
+    if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const Real* P = P_all + (size_t)env * D.nstate;
     const bool odd = 2 * pz + 1 < D.nz;
     if (aligned16(P)) {
@@ -301,6 +305,7 @@ template <typename Real>
 __global__ void g3_thomas_kernel(Dims D, cx<Real>* Z_all, const Real* cp, Real scale, const int* env_ids)
 {
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= D.ncol) return;
     mode_pair_thomas<Real>(D, Z_all + (size_t)env * ((D.nz + 1) >> 1) * D.ncol, cp, scale, q);
@@ -315,6 +320,7 @@ g3_ifft_kernel(Dims D_arg, const cx<Real>* Z_all, Real* phi_all, const cx<Real>*
     cx<Real>* Z = reinterpret_cast<cx<Real>*>(smem_raw);
     const Dims D = plane_dims<LX2, LY2>(D_arg);
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, pz = blockIdx.x, nzp = (D.nz + 1) >> 1;
+    if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const Real* in = reinterpret_cast<const Real*>(Z_all + ((size_t)env * nzp + pz) * D.ncol);
     Real* Zr = reinterpret_cast<Real*>(Z);
 #pragma unroll 2
@@ -338,6 +344,7 @@ __global__ void __launch_bounds__(TB)
 g3_correct_kernel(Dims D, ConstsG<Real> C, Real* P_all, const Real* phi_all, const int* env_ids)
 {
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= D.nc) return;
     cell_correct<Real>(D, C, P_all + (size_t)env * D.nstate, phi_all + (size_t)env * D.nc, cell);
@@ -348,6 +355,7 @@ __global__ void __launch_bounds__(TB)
 g3_correct4_kernel(Dims D, ConstsG<Real> C, Real* P_all, const Real* phi_all, const int* env_ids)
 {
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const int cell = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (cell >= D.nc) return;
     Real* P = P_all + (size_t)env * D.nstate;
@@ -429,6 +437,159 @@ __global__ void g3_finalize_kernel(Dims D, ConstsG<Real> C, const double* kappa_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The fused vector step on this path (rbc2d::VecIO; the semantics of env_epilogue3 / env_action_step3 in rbc3d_core.h, statement for
+// statement, spread over batch kernels): next_step environments that truncated on the previous call are re-initialised from the
+// checkpoint bank and skip the march; same_step truncations and NaN resets store the terminal observation / Nusselt number / return,
+// gather a new state and run the observation epilogue a second time.
+// ------------------------------------------------------------------------------------------
+__global__ void g3_vec_begin_kernel(const int* env_ids, int n, const int* pending, int* list)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int env = env_ids ? env_ids[j] : j;
+    list[j] = pending[env] ? -1 : env;
+}
+// state <- bank[checkpoint_draw(seed, id_offset + env, episode[env])] for the environments with which[env] != 0
+template <typename Real>
+__global__ void __launch_bounds__(TB)
+g3_vec_gather_kernel(Dims D, Real* st_all, rbc2d::VecIO V, const int* env_ids, const int* which)
+{
+    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    if (!which[env]) return;
+    const double* src = V.bank + (size_t)rbc2d::checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * D.nstate;
+    Real* st = st_all + (size_t)env * D.nstate;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < D.nstate; q += gridDim.x * blockDim.x) st[q] = (Real)src[q];
+}
+// Nusselt / NaN partials like g3_reduce_kernel, from the environment's own array where the march was skipped (`from_state`) and only
+// for the environments marked in `only` (second pass); no observation
+template <typename Real>
+__global__ void __launch_bounds__(TB)
+g3_vec_reduce_kernel(Dims D, ConstsG<Real> C, const Real* cur_all, Real* st_all, double* acc, const int* env_ids, const int* from_state, const int* only)
+{
+    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    if (only && !only[env]) return;
+    Real* st = st_all + (size_t)env * D.nstate;
+    const Real* cur = ((from_state && from_state[env]) || only) ? st : cur_all + (size_t)env * D.nstate;
+    double a = 0, bad = 0;
+    for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < D.nc; cell += gridDim.x * blockDim.x) {
+        const int k = cell / D.ncol;
+        const double b = (double)cur[D.gb + cell], u = (double)cur[D.gu + cell], v = (double)cur[D.gv + cell], w = (double)cur[D.gw + cell];
+        if (b != b || u != u || v != v || w != w) bad += 1;
+        const double zc = (k + 0.5) / D.nz, Tc = (1.0 - zc) * C.delta_b_d + C.b_top_d;
+        a += (b - Tc) * w;
+    }
+    if (cur != st)
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < D.nstate; q += gridDim.x * blockDim.x) st[q] = cur[q];
+    __shared__ double sa[TB], sb[TB];
+    sa[threadIdx.x] = a; sb[threadIdx.x] = bad;
+    __syncthreads();
+    for (int s = TB / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { acc[((size_t)env * gridDim.x + blockIdx.x) * 2] = sa[0]; acc[((size_t)env * gridDim.x + blockIdx.x) * 2 + 1] = sb[0]; }
+}
+// the bookkeeping of env_epilogue3 (first pass): flags, reward, return, clock, pending marks; do_reset[env] for the kernels behind it
+template <typename Real>
+__global__ void g3_vec_finalize_kernel(Dims D, ConstsG<Real> C, const double* kappa_env, const double* acc, int nblocks, rbc3dg_api::IoRaw io,
+                                       rbc2d::VecIO V, const int* env_ids, int n, int* do_reset_out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int env = env_ids ? env_ids[j] : j;
+    double sum = 0, nbad = 0;
+    for (int b = 0; b < nblocks; ++b) { sum += acc[((size_t)env * nblocks + b) * 2]; nbad += acc[((size_t)env * nblocks + b) * 2 + 1]; }
+    const double nu = 1.0 + (sum / (double)D.nc) / kappa_env[env];
+    const bool bad = nbad > 0;
+    const int pend = (V.mode == 1 && V.bank != nullptr) ? V.pending[env] : 0;
+    const double t_old = io.t[env];
+    const bool stepping = !pend;
+    const bool trunc_now = stepping && (t_old + C.dt_action >= C.episode_length);
+    const bool bad_reset = stepping && V.nan_reset && bad;
+    const bool do_reset = stepping && V.bank != nullptr && ((V.mode == 2 && trunc_now) || bad_reset);
+    do_reset_out[env] = do_reset ? 1 : 0;
+    if (pend) {
+        io.nusselt[env] = nu;
+        io.reward[env] = 0.0f;
+        io.nan_flag[env] = bad ? 1 : 0;
+        io.truncated[env] = 0;
+        io.t[env] = 0.0;
+        io.step_count[env] = 1;
+        V.episode[env] += 1;
+        V.ep_return[env] = 0.0;
+        V.pending[env] = 0;
+        return;
+    }
+    double rew = -nu;
+    if (bad_reset) rew = 0.0;
+    if (bad && V.nan_count != nullptr) atomicAdd(V.nan_count, 1);
+    io.reward[env] = (float)rew;
+    io.nan_flag[env] = bad ? 1 : 0;
+    const double ret = V.ep_return[env] + (double)(float)rew;
+    if (do_reset) {
+        if (V.final_nu_a != nullptr) V.final_nu_a[env] = nu;
+        if (V.final_return != nullptr) V.final_return[env] = ret;
+        io.truncated[env] = 1;
+    } else {
+        io.nusselt[env] = nu;
+        io.t[env] = t_old + C.dt_action;
+        io.step_count[env] += 1;
+        io.truncated[env] = (trunc_now || bad_reset) ? 1 : 0;
+        V.ep_return[env] = ret;
+        if (V.pending != nullptr) V.pending[env] = (V.mode == 1 && trunc_now && V.bank != nullptr) ? 1 : 0;
+    }
+}
+// observation (= get_state) of every listed environment; an environment that is re-initialised inside this step stores it as its
+// terminal observation instead and takes its new state from the bank (element by element: read, emit, overwrite)
+template <typename Real>
+__global__ void __launch_bounds__(TB)
+g3_vec_emit_kernel(Dims D, Real* st_all, float* obs, rbc2d::VecIO V, const int* env_ids, const int* do_reset)
+{
+    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    Real* st = st_all + (size_t)env * D.nstate;
+    if (!do_reset[env]) {
+        if (obs == nullptr) return;
+        float* ob = obs + (size_t)env * 4 * D.nc;
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < 4 * D.nc; q += gridDim.x * blockDim.x) ob[q] = (float)st[q];
+        return;
+    }
+    const double* src = V.bank + (size_t)rbc2d::checkpoint_draw(V.seed, V.id_offset + (unsigned long long)env, (unsigned long long)V.episode[env], V.n_ep) * D.nstate;
+    float* fo = V.final_obs ? V.final_obs + (size_t)env * 4 * D.nc : nullptr;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < D.nstate; q += gridDim.x * blockDim.x) {
+        if (fo != nullptr && q < 4 * D.nc) fo[q] = (float)st[q];
+        st[q] = (Real)src[q];
+    }
+}
+// second pass of the environments re-initialised inside this step: Nusselt number and observation of the new state, fresh episode
+template <typename Real>
+__global__ void g3_vec_finalize2_kernel(Dims D, const double* kappa_env, const double* acc, int nblocks, rbc3dg_api::IoRaw io, rbc2d::VecIO V,
+                                        const int* env_ids, int n, const int* do_reset)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int env = env_ids ? env_ids[j] : j;
+    if (!do_reset[env]) return;
+    double sum = 0;
+    for (int b = 0; b < nblocks; ++b) sum += acc[((size_t)env * nblocks + b) * 2];
+    io.nusselt[env] = 1.0 + (sum / (double)D.nc) / kappa_env[env];
+    io.t[env] = 0.0;
+    io.step_count[env] = 1;
+    V.episode[env] += 1;
+    V.ep_return[env] = 0.0;
+    if (V.pending != nullptr) V.pending[env] = 0;
+}
+template <typename Real>
+__global__ void __launch_bounds__(TB)
+g3_vec_emit2_kernel(Dims D, const Real* st_all, float* obs, const int* env_ids, const int* do_reset)
+{
+    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
+    if (!do_reset[env] || obs == nullptr) return;
+    const Real* st = st_all + (size_t)env * D.nstate;
+    float* ob = obs + (size_t)env * 4 * D.nc;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < 4 * D.nc; q += gridDim.x * blockDim.x) ob[q] = (float)st[q];
+}
+
 }  // namespace
 
 namespace rbc3dg_api {
@@ -456,6 +617,8 @@ struct Plan {
     // 1125 / 1187 / 1208 / 1241; 148 environments 1224 / 1267 / - / 1266; 14 environments 772 / 792 / - / 778.
     int streams = 0;             // 0 = 4 chains from 32 environments on, else 2; RBC_B200_G3_STREAMS=1..4 fixes the number
     int* iota = nullptr;         // 0 .. B-1: the environment list of a launch over the whole batch, so that it can be cut
+    int* vlist = nullptr;        // fused vector step: the march's environment list with -1 for environments that only re-initialise
+    int* do_reset = nullptr;     // fused vector step: environments re-initialised inside the current step
     cudaStream_t side[MAX_CHAINS - 1] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS - 1] = {};
 };
@@ -557,6 +720,9 @@ int create(const HostConfigG& hc, int nx, int ny, int nz, int num_envs, int prec
         std::vector<int> io(num_envs);
         for (int q = 0; q < num_envs; ++q) io[q] = q;
         e = cudaMalloc((void**)&p->iota, B * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&p->vlist, B * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&p->do_reset, B * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(p->do_reset, 0, B * sizeof(int));
         if (e == cudaSuccess) e = cudaMemcpy(p->iota, io.data(), B * sizeof(int), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
         for (int c = 0; c < MAX_CHAINS - 1 && e == cudaSuccess; ++c) {
@@ -578,6 +744,8 @@ void destroy(Plan* p)
     void* ptrs[] = {p->P, p->G, p->Z, p->phi, p->Tb, p->cp, p->twx, p->twy, p->nu, p->kappa, p->kappa_d, p->acc};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->iota) cudaFree(p->iota);
+    if (p->vlist) cudaFree(p->vlist);
+    if (p->do_reset) cudaFree(p->do_reset);
     for (int c = 0; c < MAX_CHAINS - 1; ++c) {
         if (p->side[c]) cudaStreamDestroy(p->side[c]);
         if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]);
@@ -630,7 +798,7 @@ static void tendency_t(Plan* p, const ConstsG<Real>& C, const Real* cur, Real* n
 
 template <typename Real>
 static int launch_t(Plan* p, const IoRaw& io, const int* env_ids, int n, int nsub, int project_first, int advance_clock, cudaStream_t st,
-                    int64_t* launches)
+                    int64_t* launches, const rbc2d::VecIO* vecp)
 {
     const Dims& D = p->D;
     ConstsG<Real> C = make_consts<Real>(D, p->hc);
@@ -640,6 +808,19 @@ static int launch_t(Plan* p, const IoRaw& io, const int* env_ids, int n, int nsu
     Real* S = (Real*)io.state;
     Real* cur = S;
     Real* nxt = (Real*)p->P;
+    // fused vector step (rbc2d::VecIO): next_step environments that truncated on the previous call take a new state from the bank and
+    // are struck from the march's list
+    const bool vec = vecp != nullptr && vecp->mode >= 0 && advance_clock;
+    const rbc2d::VecIO V = vec ? *vecp : rbc2d::VecIO();
+    const bool skip_pending = vec && V.mode == 1 && V.bank != nullptr;
+    const int eblocks = (D.nstate + 4 * TB - 1) / (4 * TB) < 128 ? (D.nstate + 4 * TB - 1) / (4 * TB) : 128;
+    const int* const listed = env_ids;          // the environments of this call (the epilogue covers all of them)
+    if (skip_pending) {
+        g3_vec_begin_kernel<<<(n + 127) / 128, 128, 0, st>>>(listed, n, V.pending, p->vlist);
+        g3_vec_gather_kernel<Real><<<dim3(eblocks, n), TB, 0, st>>>(D, S, V, listed, V.pending);
+        *launches += 2;
+        env_ids = p->vlist;
+    }
     // the chains: the whole list on the caller's stream, or equal parts of it on the caller's stream and the plan's side streams
     const int want = p->streams > 0 ? p->streams : (n >= 32 ? 4 : 2);
     const int nch = want < n ? want : (n < 1 ? 1 : n);
@@ -681,20 +862,34 @@ static int launch_t(Plan* p, const IoRaw& io, const int* env_ids, int n, int nsu
         CK(cudaStreamWaitEvent(st, p->ev_join[c - 1], 0));
     }
     const int rblocks = (D.nc + 4 * TB - 1) / (4 * TB) < MAX_RBLOCKS ? (D.nc + 4 * TB - 1) / (4 * TB) : MAX_RBLOCKS;
-    g3_reduce_kernel<Real><<<dim3(rblocks, n), TB, 0, st>>>(D, C, cur, S, io.obs, p->acc, env_ids);
-    g3_finalize_kernel<Real><<<(n + 127) / 128, 128, 0, st>>>(D, C, p->kappa_d, p->acc, rblocks, io, env_ids, n, advance_clock);
+    if (!vec) {
+        g3_reduce_kernel<Real><<<dim3(rblocks, n), TB, 0, st>>>(D, C, cur, S, io.obs, p->acc, env_ids);
+        g3_finalize_kernel<Real><<<(n + 127) / 128, 128, 0, st>>>(D, C, p->kappa_d, p->acc, rblocks, io, env_ids, n, advance_clock);
+        CK(cudaGetLastError());
+        *launches += 2;
+        return 0;
+    }
+    g3_vec_reduce_kernel<Real><<<dim3(rblocks, n), TB, 0, st>>>(D, C, cur, S, p->acc, listed, skip_pending ? V.pending : nullptr, nullptr);
+    g3_vec_finalize_kernel<Real><<<(n + 127) / 128, 128, 0, st>>>(D, C, p->kappa_d, p->acc, rblocks, io, V, listed, n, p->do_reset);
+    g3_vec_emit_kernel<Real><<<dim3(eblocks, n), TB, 0, st>>>(D, S, io.obs, V, listed, p->do_reset);
+    *launches += 3;
+    if (V.bank != nullptr && (V.mode == 2 || V.nan_reset)) {       // second pass of the environments re-initialised inside this step
+        g3_vec_reduce_kernel<Real><<<dim3(rblocks, n), TB, 0, st>>>(D, C, S, S, p->acc, listed, nullptr, p->do_reset);
+        g3_vec_finalize2_kernel<Real><<<(n + 127) / 128, 128, 0, st>>>(D, p->kappa_d, p->acc, rblocks, io, V, listed, n, p->do_reset);
+        g3_vec_emit2_kernel<Real><<<dim3(eblocks, n), TB, 0, st>>>(D, S, io.obs, listed, p->do_reset);
+        *launches += 3;
+    }
     CK(cudaGetLastError());
-    *launches += 2;
     return 0;
 }
 
 int launch(Plan* p, const IoRaw& io, const int* env_ids, int n, int nsub, int project_first, int advance_clock, cudaStream_t stream,
-           int64_t* launches)
+           int64_t* launches, const rbc2d::VecIO* vec)
 {
     if (n <= 0) return 0;
     if (n > 65535) return rbc_fail("rbc3d: at most 65535 environments per launch on this path");
-    return p->precision == 32 ? launch_t<float>(p, io, env_ids, n, nsub, project_first, advance_clock, stream, launches)
-                              : launch_t<double>(p, io, env_ids, n, nsub, project_first, advance_clock, stream, launches);
+    return p->precision == 32 ? launch_t<float>(p, io, env_ids, n, nsub, project_first, advance_clock, stream, launches, vec)
+                              : launch_t<double>(p, io, env_ids, n, nsub, project_first, advance_clock, stream, launches, vec);
 }
 
 int nsub_of(const Plan* p)

@@ -470,6 +470,8 @@ class RBCVectorEnv3D(_VectorBase):
         obs, rew, nu, trunc, nan, ex = self.sim.vec_step(actions, want_final_obs=same)
         info = self._info(nu, ex)
         info["nan"] = nan.to(t.bool)
+        if self.nan_policy == "reset":
+            info["nan_reset"] = info["nan"]
         if same:
             info["final_obs"] = self._out(ex["final_obs"])
             info["final_info"] = {"nusselt": self._out(ex["final_nusselt"]), "episode_return": self._out(ex["final_return"])}

@@ -80,13 +80,15 @@ def test_fused_step_on_the_cluster_kernel_grid():
         fused.close(); plain.close()
 
 
+@pytest.mark.parametrize("shape", [(16, 32, 32), (8, 16, 32), (16, 64, 64)])      # dedicated kernel; stage-streaming kernels (per-cell / tiled tendency)
 @pytest.mark.parametrize("mode", ["next_step", "same_step"])
-def test_fused_step_equals_python_driven_autoreset_3d(mode):
+def test_fused_step_equals_python_driven_autoreset_3d(mode, shape):
     import torch
     from rbc_gym_b200.envs import RBCVectorEnv3D
     rng = np.random.default_rng(0)
     n, nb = 20, 3
-    kw = dict(rayleigh_number=2500, heater_duration=0.03, dt_solver=0.01, episode_length=0.2, autoreset_mode=mode, seed=9, precision=32)
+    kw = dict(rayleigh_number=2500, heater_duration=0.03, dt_solver=0.01, episode_length=0.2, autoreset_mode=mode, seed=9, precision=32,
+              state_shape=shape)
     fused, plain = RBCVectorEnv3D(n, **kw), RBCVectorEnv3D(n, fused=False, **kw)
     # a bank of projected noisy states
     fused.sim.noise_reset(kick=0.05, generator=torch.Generator(device="cuda").manual_seed(4))
@@ -110,6 +112,38 @@ def test_fused_step_equals_python_driven_autoreset_3d(mode):
         n_trunc += int(tr.sum())
     assert n_trunc >= n
     fused.close(); plain.close()
+
+
+@pytest.mark.parametrize("shape", [(16, 32, 32), (8, 16, 32)])      # dedicated kernel epilogue; batch kernels of the stage-streaming path
+@pytest.mark.parametrize("mode", ["next_step", "same_step"])
+def test_nan_reset_policy_3d(mode, shape):
+    """`nan_policy="reset"` in 3D: the one environment whose fields went NaN is re-initialised from the bank inside the step (truncated,
+    reward 0, clock 0, finite observation, counted), the others step on; the step after that everybody steps normally."""
+    import torch
+    from rbc_gym_b200.envs import RBCVectorEnv3D
+    n = 5
+    env = RBCVectorEnv3D(n, rayleigh_number=2500, heater_duration=0.03, dt_solver=0.01, episode_length=10.0, autoreset_mode=mode, seed=2,
+                         precision=32, state_shape=shape, nan_policy="reset")
+    env.sim.noise_reset(kick=0.05, generator=torch.Generator(device="cuda").manual_seed(8))
+    env.sim.load_checkpoints(env.sim.fields()[:2])
+    env.reset()
+    f = env.sim.fields()
+    f[3, 777] = np.nan
+    env.sim.reset_from_fields(f[3:4], env_ids=[3], project=False)
+    a = torch.zeros((n, 8, 8), device="cuda")
+    obs, rew, term, trunc, info = env.step(a)
+    want = [False, False, False, True, False]
+    assert info["nan_reset"].tolist() == want and trunc.tolist() == want
+    assert rew[3].item() == 0 and torch.isfinite(obs).all() and (rew[[0, 1, 2, 4]] != 0).all()
+    t, step = env.sim.info()
+    dt = 0.03 * 4.0                                   # heater_duration in free-fall units of the height-2 domain
+    assert t[3] == 0.0 and step[3] == 1 and np.allclose(np.delete(t, 3), dt)
+    assert env.sim.vec_nan_count() == 1
+    obs, rew, term, trunc, info = env.step(a)
+    assert not trunc.any() and not info["nan_reset"].any() and torch.isfinite(rew).all() and (rew != 0).all()
+    t, step = env.sim.info()
+    assert t[3] == pytest.approx(dt) and t[0] == pytest.approx(2 * dt)
+    env.close()
 
 
 def test_info_state_and_deferred_nan_check():
