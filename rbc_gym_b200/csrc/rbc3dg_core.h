@@ -540,81 +540,6 @@ RBC_HD void mode_pair_thomas(const Dims& D, cx<Real>* Zs, const Real* cp, Real s
     }
 }
 
-// the positions that do the work of the z-solve (partner >= position), ascending, with their partners: [n][2]; returns n
-inline int build_mode_pairs_host(const Dims& D, int* pairs /*ncol * 2*/)
-{
-    int n = 0;
-    for (int q = 0; q < D.ncol; ++q) {
-        const int qp = partner_position(D, q);
-        if (qp >= q) { pairs[2 * n] = q; pairs[2 * n + 1] = qp; ++n; }
-    }
-    return n;
-}
-// mode_pair_thomas for planes that are not one array: `plane(p)` returns the base of plane p (the cluster kernel of rbc3dg_lib.cu maps
-// the shared memory of CTA p).  The statements of mode_pair_thomas; the operands, which do not depend on the chain, are fetched CHUNK
-// planes ahead of the steps that use them (a remote access costs a few hundred cycles and the chain has nz steps).
-template <typename Real, int CHUNK, typename PlaneFn>
-RBC_HD void mode_pair_thomas_planes(const Dims& D, PlaneFn plane, const Real* RBC_RESTRICT cp, Real scale, int q, int qp)
-{
-    const int nz = D.nz, ncol = D.ncol, nzp = (nz + 1) >> 1;
-    const Real h = Real(0.5) * scale;
-    cx<Real> A[CHUNK], B[CHUNK];
-    Real c0[CHUNK], c1[CHUNK];
-    cx<Real> d{Real(0), Real(0)};                            // forward elimination, level after level
-    for (int pb = 0; pb < nzp; pb += CHUNK) {
-        RBC_UNROLL
-        for (int r = 0; r < CHUNK; ++r) {
-            const int p = pb + r;
-            if (p < nzp) {
-                const cx<Real>* Zp = plane(p);
-                A[r] = Zp[q]; B[r] = Zp[qp];
-                c0[r] = cp[(size_t)(2 * p) * ncol + q]; c1[r] = (2 * p + 1 < nz) ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
-            }
-        }
-        RBC_UNROLL
-        for (int r = 0; r < CHUNK; ++r) {
-            const int p = pb + r;
-            if (p < nzp) {
-                const bool odd = 2 * p + 1 < nz;
-                const cx<Real> d0{((A[r].re + B[r].re) * h - d.re) * c0[r], ((A[r].im - B[r].im) * h - d.im) * c0[r]};
-                const cx<Real> d1{((A[r].im + B[r].im) * h - d0.re) * c1[r], ((B[r].re - A[r].re) * h - d0.im) * c1[r]};
-                d = odd ? d1 : d0;
-                cx<Real>* Zp = plane(p);
-                if (qp == q) Zp[q] = cx<Real>{d0.re, d1.re};       // two real columns
-                else { Zp[q] = d0; Zp[qp] = d1; }
-            }
-        }
-    }
-    cx<Real> x{Real(0), Real(0)};                            // back substitution: x_k = d_k - c_k x_{k+1}, x_{nz} = 0
-    for (int pb = nzp - 1; pb >= 0; pb -= CHUNK) {
-        RBC_UNROLL
-        for (int r = 0; r < CHUNK; ++r) {
-            const int p = pb - r;
-            if (p >= 0) {
-                const cx<Real>* Zp = plane(p);
-                A[r] = Zp[q]; B[r] = Zp[qp];
-                c0[r] = cp[(size_t)(2 * p) * ncol + q]; c1[r] = (2 * p + 1 < nz) ? cp[(size_t)(2 * p + 1) * ncol + q] : Real(0);
-            }
-        }
-        RBC_UNROLL
-        for (int r = 0; r < CHUNK; ++r) {
-            const int p = pb - r;
-            if (p >= 0) {
-                const bool odd = 2 * p + 1 < nz;
-                cx<Real> d0 = A[r], d1 = B[r];
-                if (qp == q) { d1 = cx<Real>{d0.im, Real(0)}; d0 = cx<Real>{d0.re, Real(0)}; }
-                cx<Real> x1{Real(0), Real(0)};
-                if (odd) { x1 = cx<Real>{d1.re - c1[r] * x.re, d1.im - c1[r] * x.im}; x = x1; }
-                const cx<Real> x0{d0.re - c0[r] * x.re, d0.im - c0[r] * x.im};
-                x = x0;
-                cx<Real>* Zp = plane(p);
-                Zp[q] = cx<Real>{x0.re - x1.im, x0.im + x1.re};                       // x_even + i x_odd
-                if (qp != q) Zp[qp] = cx<Real>{x0.re + x1.im, x1.re - x0.im};         // conj(x_even) + i conj(x_odd)
-            }
-        }
-    }
-}
-
 // velocity correction of one cell: U = U* - grad phi (interior w faces only)
 template <typename Real>
 RBC_HD void cell_correct(const Dims& D, const ConstsG<Real>& C, Real* P, const Real* phi, int cell)

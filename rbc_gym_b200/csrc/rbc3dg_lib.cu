@@ -1,7 +1,6 @@
 // rbc3dg_lib.cu — sm_100a kernels of the stage-streaming 3D action step for arbitrary grids (rbc3dg_core.h) and the plan
 // object rbc3d_lib.cu drives them through.  Every kernel runs over the whole batch (blockIdx.y = environment), so a single
 // 64 x 64 x 32 environment already fills the GPU with 131 072 threads per launch.
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -381,116 +380,6 @@ g3_correct4_kernel(Dims D, ConstsG<Real> C, Real* P_all, const Real* phi_all, co
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// The whole projection of an environment in ONE kernel: a thread-block cluster of nzp = ceil(nz / 2) CTAs owns the environment, CTA p
-// the plane pair (levels 2p, 2p + 1) — the four kernels above without their global intermediates.
-//   1. divergence of the two levels + forward FFT into the CTA's shared-memory plane            (g3_div_fft_kernel)
-//   2. z-solve: every CTA takes a share of the mode pairs, reads the pair's column THROUGH DISTRIBUTED SHARED MEMORY from all the
-//      planes of the cluster (four planes ahead of the dependent chain), solves, writes back   (g3_thomas_kernel)
-//   3. inverse FFT of the own plane: phi of the two levels                                      (g3_ifft_kernel)
-//   4. U = U* - grad phi for the two levels; phi of the level below the lower one is the imaginary part of the previous CTA's
-//      plane, read through distributed shared memory                                             (g3_correct4_kernel)
-// The spectral planes and phi never leave the chip: 200 MB of DRAM traffic per 64-environment stage instead of 414 MB.  Same
-// operations on the same values in every step (phi is rounded to the working precision before the differences, as the store to
-// global memory did), so the results are bit-identical to the four-kernel path.  Needs nzp <= 16 (clusters above 8 CTAs are the
-// non-portable size the B200 supports); other grids keep the four kernels.
-// ------------------------------------------------------------------------------------------
-constexpr int MAX_NZP = 16;
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-
-template <typename Real, int LX2, int LY2>
-__global__ void __launch_bounds__(FFT_NT, sizeof(Real) == 4 ? 6 : 3)
-g3_project_cluster_kernel(Dims D_arg, ConstsG<Real> C, Real* P_all, const Real* cp, Real scale, const cx<Real>* twx, const cx<Real>* twy,
-                          const int* env_ids, const int2* pairs, int npairs)
-{
-    namespace cg = cooperative_groups;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<Real>* Z = reinterpret_cast<cx<Real>*>(smem_raw);
-    const Dims D = plane_dims<LX2, LY2>(D_arg);
-    const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
-    if (env < 0) return;                                 // the whole cluster returns
-    cg::cluster_group cluster = cg::this_cluster();
-    const int pz = blockIdx.x, nzp = (D.nz + 1) >> 1, tid = threadIdx.x;
-    Real* P = P_all + (size_t)env * D.nstate;
-    const bool odd = 2 * pz + 1 < D.nz;
-
-    // 1. divergence + forward FFT (the statements of g3_div_fft_kernel)
-    for (int c = 4 * tid; c < D.ncol; c += 4 * FFT_NT) {
-        const int i = c & (D.nx - 1), j = c >> D.lx2, k = 2 * pz;
-        const Quad<Real> w0 = ld4(P + D.gw + k * D.ncol + c), w1 = ld4(P + D.gw + (k + 1) * D.ncol + c);
-        const Quad<Real> d0 = quad_divergence<Real>(D, C, P, i, j, k, w0, w1);
-        Quad<Real> d1{{Real(0), Real(0), Real(0), Real(0)}};
-        if (odd) d1 = quad_divergence<Real>(D, C, P, i, j, k + 1, w1, ld4(P + D.gw + (k + 2) * D.ncol + c));
-#pragma unroll
-        for (int m = 0; m < 4; ++m) Z[c + m] = cx<Real>{d0.v[m], d1.v[m]};
-    }
-    stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
-    __syncthreads();
-    if (LX2) plane_fft_forward<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRunFixed<FFT_NT>{});
-    else plane_fft_forward<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
-    cluster.sync();
-
-    // 2. z-solve of this CTA's share of the mode pairs, columns gathered from / scattered to the planes of the cluster
-    {
-        const int per = (npairs + nzp - 1) / nzp, first = pz * per, last = first + per < npairs ? first + per : npairs;
-        for (int t = first + tid; t < last; t += FFT_NT) {
-            const int2 qq = pairs[t];
-            mode_pair_thomas_planes<Real, 4>(D, [&](int p) { return cluster.map_shared_rank(Z, p); }, cp, scale, qq.x, qq.y);
-        }
-    }
-    cluster.sync();
-
-    // 3. inverse FFT: Z = phi(2 pz) + i phi(2 pz + 1), not yet normalised
-    if (LX2) plane_fft_inverse<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRunFixed<FFT_NT>{});
-    else plane_fft_inverse<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
-    cluster.sync();
-
-    // 4. pressure correction of the two levels (the expressions of cell_correct on phi = Z * norm rounded to Real)
-    {
-        const Real norm = Real(1) / (Real)D.ncol;
-        const cx<Real>* Zb = pz > 0 ? cluster.map_shared_rank(Z, pz - 1) : nullptr;      // phi of level 2 pz - 1 is its imaginary part
-        const int k0 = 2 * pz;
-        for (int c = 4 * tid; c < D.ncol; c += 4 * FFT_NT) {
-            const int i = c & (D.nx - 1), j = c >> D.lx2;
-            const int cl = c - i + ((i - 1) & (D.nx - 1)), cj = (((j - 1) & (D.ny - 1)) << D.lx2) + i;
-            Real ph0[4], ph1[4], pj0[4], pj1[4], pb[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const cx<Real> z = Z[c + m], zj = Z[cj + m];
-                ph0[m] = mul_rn(z.re, norm); ph1[m] = mul_rn(z.im, norm);
-                pj0[m] = mul_rn(zj.re, norm); pj1[m] = mul_rn(zj.im, norm);
-                pb[m] = Zb ? mul_rn(Zb[c + m].im, norm) : Real(0);
-            }
-            const cx<Real> zl = Z[cl];
-            const Real pl0 = mul_rn(zl.re, norm), pl1 = mul_rn(zl.im, norm);
-#pragma unroll
-            for (int lev = 0; lev < 2; ++lev) {
-                if (lev == 1 && !odd) break;
-                const int cell = (k0 + lev) * D.ncol + c;
-                const Real* ph = lev ? ph1 : ph0;
-                const Real* pj = lev ? pj1 : pj0;
-                const Real pl = lev ? pl1 : pl0;
-                Quad<Real> u = ld4(P + D.gu + cell), v = ld4(P + D.gv + cell);
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    u.v[m] -= (ph[m] - (m ? ph[m - 1] : pl)) * C.idx;
-                    v.v[m] -= (ph[m] - pj[m]) * C.idy;
-                }
-                st4(P + D.gu + cell, u);
-                st4(P + D.gv + cell, v);
-                if (k0 + lev >= 1) {
-                    Quad<Real> w = ld4(P + D.gw + cell);
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) w.v[m] -= (ph[m] - (lev ? ph0[m] : pb[m])) * C.idz;
-                    st4(P + D.gw + cell, w);
-                }
-            }
-        }
-    }
-    cluster.sync();      // nobody leaves while a neighbour may still read its plane
-}
-
 // epilogue, part 1: Nusselt sum and NaN count of a chunk of cells (one partial per block into acc[env][block][2], added up in block
 // order by part 2: the Nusselt number — the reward — is reproducible bit for bit, which atomics would not give); write-back to the environment's
 // own array when the march ended in the other buffer; observation = get_state (rbc_sim3D_api.jl:106-121, rbc3D.py:229-232)
@@ -728,34 +617,11 @@ struct Plan {
     // 1125 / 1187 / 1208 / 1241; 148 environments 1224 / 1267 / - / 1266; 14 environments 772 / 792 / - / 778.
     int streams = 0;             // 0 = 4 chains from 32 environments on, else 2; RBC_B200_G3_STREAMS=1..4 fixes the number
     int* iota = nullptr;         // 0 .. B-1: the environment list of a launch over the whole batch, so that it can be cut
-    int2* pairs = nullptr;       // working positions of the z-solve with their partners (build_mode_pairs_host)
-    int npairs = 0;
-    int fused_project = 0;       // 1: the projection runs as one cluster kernel per chain (g3_project_cluster_kernel); RBC_B200_G3_CLUSTER=0 turns it off
     int* vlist = nullptr;        // fused vector step: the march's environment list with -1 for environments that only re-initialise
     int* do_reset = nullptr;     // fused vector step: environments re-initialised inside the current step
     cudaStream_t side[MAX_CHAINS - 1] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS - 1] = {};
 };
-
-// the instantiation of the fused projection for this plan (compile-time plane extents where they exist)
-template <typename Real>
-static const void* project_cluster_fn(const Plan* p)
-{
-    if (p->fixed_plane == 66) return (const void*)g3_project_cluster_kernel<Real, 6, 6>;
-    if (p->fixed_plane == 55) return (const void*)g3_project_cluster_kernel<Real, 5, 5>;
-    return (const void*)g3_project_cluster_kernel<Real, 0, 0>;
-}
-static void project_cluster_config(const Plan* p, int n, cudaStream_t st, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr)
-{
-    *cfg = cudaLaunchConfig_t{};
-    cfg->gridDim = dim3((p->D.nz + 1) / 2, n);
-    cfg->blockDim = dim3(FFT_NT);
-    cfg->dynamicSmemBytes = p->smem;
-    cfg->stream = st;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (p->D.nz + 1) / 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg->attrs = attr; cfg->numAttrs = 1;
-}
 
 int supported(int nx, int ny, int nz) { return dims_supported(nx, ny, nz) ? 1 : 0; }
 size_t smem_bytes(const Plan* p) { return p->smem; }
@@ -850,29 +716,6 @@ int create(const HostConfigG& hc, int nx, int ny, int nz, int num_envs, int prec
         cudaMemset(*a.ptr, 0, a.bytes);
     }
     {
-        {   // the fused cluster projection: one CTA per plane pair, up to 16 CTAs per cluster
-            std::vector<int> pr((size_t)2 * p->D.ncol);
-            p->npairs = build_mode_pairs_host(p->D, pr.data());
-            e = cudaMalloc((void**)&p->pairs, (size_t)p->npairs * sizeof(int2));
-            if (e == cudaSuccess) e = cudaMemcpy(p->pairs, pr.data(), (size_t)p->npairs * sizeof(int2), cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) { destroy(p); return rbc_fail(std::string("rbc3d_create: ") + cudaGetErrorString(e)); }
-            const char* sw = getenv("RBC_B200_G3_CLUSTER");
-            const int nzp = (nz + 1) / 2;
-            if (!(sw && atoi(sw) == 0) && nzp >= 2 && nzp <= MAX_NZP) {
-                const void* fn = precision == 32 ? project_cluster_fn<float>(p) : project_cluster_fn<double>(p);
-                cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-                if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                if (ce == cudaSuccess && nzp > 8) ce = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-                int nc = 0;
-                if (ce == cudaSuccess) {
-                    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
-                    project_cluster_config(p, 1, nullptr, &cfg, attr);
-                    ce = cudaOccupancyMaxActiveClusters(&nc, fn, &cfg);
-                }
-                if (ce == cudaSuccess && nc >= 1) p->fused_project = 1;
-                else cudaGetLastError();          // this grid keeps the four-kernel projection
-            }
-        }
         if (const char* v = getenv("RBC_B200_G3_STREAMS")) { const int t = atoi(v); p->streams = t < 0 ? 0 : (t > MAX_CHAINS ? MAX_CHAINS : t); }
         std::vector<int> io(num_envs);
         for (int q = 0; q < num_envs; ++q) io[q] = q;
@@ -902,7 +745,6 @@ void destroy(Plan* p)
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->iota) cudaFree(p->iota);
     if (p->vlist) cudaFree(p->vlist);
-    if (p->pairs) cudaFree(p->pairs);
     if (p->do_reset) cudaFree(p->do_reset);
     for (int c = 0; c < MAX_CHAINS - 1; ++c) {
         if (p->side[c]) cudaStreamDestroy(p->side[c]);
@@ -918,19 +760,6 @@ static int project_t(Plan* p, const ConstsG<Real>& C, Real* buf, const int* env_
     const Dims& D = p->D;
     const dim3 gplane((D.nz + 1) / 2, n), gcell((D.nc + TB - 1) / TB, n), gmode((D.ncol + 127) / 128, n);
     const Real dz = (Real)(p->hc.lz / D.nz);
-    if (p->fused_project && (reinterpret_cast<size_t>(buf) & 15) == 0) {
-        cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
-        project_cluster_config(p, n, st, &cfg, attr);
-        const Real* cpv = (const Real*)p->cp;
-        const Real scale = dz * dz;
-        const cx<Real>*txx = (const cx<Real>*)p->twx, *tyy = (const cx<Real>*)p->twy;
-        const int2* pairs = p->pairs;
-        int npairs = p->npairs;
-        void* args[] = {(void*)&D, (void*)&C, (void*)&buf, (void*)&cpv, (void*)&scale, (void*)&txx, (void*)&tyy, (void*)&env_ids, (void*)&pairs, (void*)&npairs};
-        CK(cudaLaunchKernelExC(&cfg, project_cluster_fn<Real>(p), args));
-        *launches += 1;
-        return 0;
-    }
     cx<Real>* Z = (cx<Real>*)p->Z;
     const cx<Real>*twx = (const cx<Real>*)p->twx, *twy = (const cx<Real>*)p->twy;
     if (p->fixed_plane == 66) g3_div_fft_kernel<Real, 6, 6><<<gplane, FFT_NT, p->smem, st>>>(D, C, buf, Z, twx, twy, env_ids);

@@ -104,9 +104,7 @@ def test_chains_and_compile_time_plane_extents_change_no_bit(monkeypatch, shape,
     """Two scheduling / code-generation choices of the generic path must be invisible in the results: (i) the batch runs as up to four
     independent chains on separate streams (`RBC_B200_G3_STREAMS`; uneven cuts here: 33 = 9 + 8 + 8 + 8, 5 = 3 + 2) — environments never
     interact; (ii) the FFT plane kernels instantiated with compile-time plane extents for 64 x 64 and 32 x 32 columns
-    (`RBC_B200_G3_FIXED_PLANE`) run the same butterflies in the same order as the run-time-extent kernels; (iii) the projection as one
-    cluster kernel per environment (planes and phi in distributed shared memory, `RBC_B200_G3_CLUSTER`) performs the operations of the
-    four-kernel projection on the same values.  Bitwise equality of a
+    (`RBC_B200_G3_FIXED_PLANE`) run the same butterflies in the same order as the run-time-extent kernels.  Bitwise equality of a
     two-step rollout, states and Nusselt numbers, in the throughput precision."""
     import torch
     from rbc_gym_b200 import backend
@@ -115,10 +113,8 @@ def test_chains_and_compile_time_plane_extents_change_no_bit(monkeypatch, shape,
     a = torch.rand((envs, 8, 8), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)) * 2 - 1
     ra = np.linspace(5e3, 4e4, envs)
     out = {}
-    variants = (("product", None, None, None), ("one-chain", "1", None, None), ("two-chains", "2", None, None), ("run-time-planes", None, "0", None),
-                ("four-kernel-projection", None, None, "0"), ("four-kernel-projection, run-time planes", None, "0", "0"))
-    for name, streams, fixed, cluster in variants:
-        for key, val in (("RBC_B200_G3_STREAMS", streams), ("RBC_B200_G3_FIXED_PLANE", fixed), ("RBC_B200_G3_CLUSTER", cluster)):
+    for name, streams, fixed in (("product", None, None), ("one-chain", "1", None), ("two-chains", "2", None), ("run-time-planes", None, "0")):
+        for key, val in (("RBC_B200_G3_STREAMS", streams), ("RBC_B200_G3_FIXED_PLANE", fixed)):
             if val is None:
                 monkeypatch.delenv(key, raising=False)
             else:
@@ -131,7 +127,7 @@ def test_chains_and_compile_time_plane_extents_change_no_bit(monkeypatch, shape,
         assert int(nan.sum()) == 0
         out[name] = (sim.fields().copy(), nu.cpu().numpy().copy())
         sim.close()
-    for name, *_ in variants[1:]:
+    for name in ("one-chain", "two-chains", "run-time-planes"):
         assert np.array_equal(out[name][0], out["product"][0]), name
         assert np.array_equal(out[name][1], out["product"][1]), name
 
