@@ -44,12 +44,12 @@ g3_tendency_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real* kapp
 // ------------------------------------------------------------------------------------------
 // Tiled tendency (grids with nx % 32 == 0, ny % 8 == 0).  A CTA owns a 32 x 8 (or 32 x 16) patch of columns and marches it up through
 // the levels: one thread per column, the z-windows of its own column slide through registers (one coalesced global load per field
-// and level), and everything it needs from its neighbours comes from a RING OF FOUR LEVEL PLANES WITH HALO in shared memory
+// and level), and everything it needs from its neighbours comes from a RING OF LEVEL PLANES WITH HALO in shared memory
 // (40 x 14 values per field: 4 + 32 + 4 columns, 3 + 8 + 3 rows; the periodic wrap is resolved once, when a thread computes which
 // 16-byte chunks of a level it copies), so every stencil access of the march is a shared-memory load at a compile-time offset from
-// the thread's own slot.  Level k reads planes k and k + 1; plane k + 3 is copied meanwhile (cp.async, 16 bytes per instruction, no
-// register staging, two copy groups in flight); one CTA barrier per level.  Same arithmetic as the per-cell kernel
-// (tendency_from_windows), 1 480 -> 685 instructions per cell.
+// the thread's own slot.  Level k reads planes k and k + 1; plane k + 5 is copied meanwhile (cp.async, 16 bytes per instruction, no
+// register staging); the planes are handed over through mbarriers, not CTA barriers (see PIPE_R below).  Same arithmetic as the
+// per-cell kernel (tendency_from_windows), 1 480 -> 685 instructions per cell.
 // ------------------------------------------------------------------------------------------
 constexpr int TT_X = 32, TT_PW = 40;                   // patch width; plane row = 4 + 32 + 4 columns (3 + 32 + 3 read)
 template <int TT_Y>
@@ -65,8 +65,23 @@ __device__ __forceinline__ void async_copy_chunk(Real* dst_shared, const Real* s
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
 }
 
-// fp32: 128 registers per thread, i.e. 512 resident threads per SM — one 16-row CTA or two 8-row CTAs that hide each other's
-// barriers and copy waits; fp64 needs ~240 registers and runs one CTA per SM
+// No CTA barrier in the level loop: the ring has PIPE_R planes guarded by one "full" and one "empty" mbarrier per slot.  A thread's
+// copies of a plane arrive on the slot's full barrier when they land (cp.async.mbarrier.arrive), every thread arrives on the empty
+// barrier of a plane when it has finished the level that reads it last, and the copy of plane k + PIPE_DIST waits for the empty barrier
+// of the plane it overwrites (PIPE_R - PIPE_DIST = 3 levels back): the warps of a CTA may drift a few levels apart instead of meeting
+// at every level.  Measured against the form with one __syncthreads per level (ring of four): 1378 against 1298 env-steps/s at
+// (R, DIST) = (6, 4); (5, 3) 1309, (7, 4) 1378, (7, 5) 1376, (8, 5) 1400.
+// fp32: 128 registers per thread, i.e. 512 resident threads per SM — one 16-row CTA or two 8-row CTAs; fp64 needs ~240 registers and
+// runs one CTA per SM
+constexpr int PIPE_R = 8, PIPE_DIST = 5;
+__device__ __forceinline__ void pipe_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void pipe_mbar_wait(unsigned bar, unsigned phase)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+    } while (!ok);
+}
 template <typename Real, int TT_Y>
 __global__ void __launch_bounds__(TT_X * TT_Y, sizeof(Real) == 4 ? 512 / (TT_X * TT_Y) : 1)
 g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real* kappa_env, const Real* S_all, Real* P_all, Real* G_all,
@@ -75,6 +90,8 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
     constexpr int TT_NT = TileGeom<TT_Y>::NT, TT_PLANE = TileGeom<TT_Y>::PLANE, TT_SLOT = TileGeom<TT_Y>::SLOT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Real* ring = reinterpret_cast<Real*>(smem_raw);
+    constexpr int R = PIPE_R;
+    const unsigned bars = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)R * TT_SLOT * sizeof(Real));      // full[R], empty[R]
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y;
     if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const int nx = D.nx, ny = D.ny, nz = D.nz, ncol = D.ncol;
@@ -104,16 +121,23 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
         isw[q] = f == 3;
     }
     auto copy_plane = [&](int level) {                        // level <= nz: w has a face there, the cell-centred fields do not
-        Real* slot = ring + (level & 3) * TT_SLOT;
+        const int sl = level % R;
+        Real* slot = ring + sl * TT_SLOT;
         const Real* src = S + level * ncol;
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
             if (goff[q] >= 0 && (level < nz || isw[q])) async_copy_chunk(slot + soff[q], src + goff[q]);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        // the thread's arrival on the plane's "full" barrier happens when its copies have landed
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bars + 8u * sl) : "memory");
     };
-    copy_plane(0);
-    copy_plane(1);
-    if (2 <= nz) copy_plane(2); else asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < 2 * R; ++q) pipe_mbar_init(bars + 8u * q, TT_NT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < PIPE_DIST; ++l) copy_plane(l);          // nz >= 6 > PIPE_DIST - 1
 
     // z-windows of the own column for level 0 (slot d <-> level d - 3, clamped like the per-cell kernel)
     Windows<Real> W;
@@ -123,8 +147,7 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
         W.bz[d] = S[D.gb + kc * ncol + colz]; W.uz[d] = S[D.gu + kc * ncol + colz]; W.vz[d] = S[D.gv + kc * ncol + colz];
         W.wz[d] = S[D.gw + kw * ncol + colz];
     }
-    asm volatile("cp.async.wait_group 1;" ::: "memory");        // planes 0 and 1 are in
-    __syncthreads();
+    pipe_mbar_wait(bars, 0);                                    // plane 0 is in (plane 1 is awaited by level 0)
     const int p0 = (ly + 3) * TT_PW + lx + 4;
     {   // neighbour-column z-windows: slots 0..2 <-> levels -2, -1, 0 (all level 0 after the clamp; slot 3 is filled per level)
         const Real* s0 = ring;
@@ -138,12 +161,17 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
     Real* Gcol = G + colz;
     Tend<Real> zf{Real(0), Real(0), Real(0), Real(0)};      // fluxes through the lower face of the current level (wall: zero)
     for (int k = 0; k < nz; ++k) {
-        if (k + 3 <= nz) copy_plane(k + 3);                   // its slot held plane k - 1: everybody is past it
-        else asm volatile("cp.async.commit_group;" ::: "memory");      // keep one group per level so that wait_group 1 means "plane k + 2"
+        if (k + PIPE_DIST <= nz) {
+            // the slot of plane k + DIST held plane k + DIST - R, last read at that level: wait until everybody has released it
+            const int old = k + PIPE_DIST - R;
+            if (old >= 0) pipe_mbar_wait(bars + 8u * (R + old % R), (unsigned)((old / R) & 1));
+            copy_plane(k + PIPE_DIST);
+        }
+        pipe_mbar_wait(bars + 8u * ((k + 1) % R), (unsigned)(((k + 1) / R) & 1));      // plane k + 1 (plane k was awaited a level ago)
         Real* Gk = Gcol + k * ncol;
         const Tend<Real> prev = load_prev_at<Real>(Gk, D.nc, use_prev != 0);
-        const Real* s0 = ring + (k & 3) * TT_SLOT;
-        const Real* s1 = ring + ((k + 1) & 3) * TT_SLOT;
+        const Real* s0 = ring + (k % R) * TT_SLOT;
+        const Real* s1 = ring + ((k + 1) % R) * TT_SLOT;
 #pragma unroll
         for (int d = 0; d < 7; ++d) {
             W.bx[d] = s0[p0 + d - 3]; W.by[d] = s0[p0 + (d - 3) * TT_PW];
@@ -173,8 +201,7 @@ g3_tendency_tiled_kernel(Dims D, ConstsG<Real> C, const Real* nu_env, const Real
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q) { W.u_ip_z[q] = W.u_ip_z[q + 1]; W.v_jp_z[q] = W.v_jp_z[q + 1]; }
-        asm volatile("cp.async.wait_group 1;" ::: "memory");    // everything but the copy issued in this iteration: plane k + 2 is in
-        __syncthreads();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8u * (R + k % R)) : "memory");      // done with plane k
     }
 }
 
@@ -697,7 +724,7 @@ int create(const HostConfigG& hc, int nx, int ny, int nz, int num_envs, int prec
         const int want = sw ? atoi(sw) : 8;       // 8 rows: two CTAs per SM hide each other's barriers and copy waits (678 vs 634 env-steps/s at 64 x 64 x 32)
         p->tiled = (nx % TT_X != 0 || want == 0) ? 0 : ((want >= 16 && ny % 16 == 0) ? 16 : (ny % 8 == 0 ? 8 : 0));
         if (p->tiled) {
-            const int bytes = (int)(4 * (p->tiled == 16 ? TileGeom<16>::SLOT : TileGeom<8>::SLOT) * p->rs);
+            const int bytes = (int)((size_t)PIPE_R * (p->tiled == 16 ? TileGeom<16>::SLOT : TileGeom<8>::SLOT) * p->rs + 16 * PIPE_R);      // ring + mbarriers
             const void* fn = precision == 32 ? (p->tiled == 16 ? (const void*)g3_tendency_tiled_kernel<float, 16> : (const void*)g3_tendency_tiled_kernel<float, 8>)
                                              : (p->tiled == 16 ? (const void*)g3_tendency_tiled_kernel<double, 16> : (const void*)g3_tendency_tiled_kernel<double, 8>);
             e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -784,11 +811,12 @@ static void tendency_t(Plan* p, const ConstsG<Real>& C, const Real* cur, Real* n
                        cudaStream_t st, int64_t* launches)
 {
     const Dims& D = p->D;
+    const size_t sm16 = (size_t)PIPE_R * TileGeom<16>::SLOT * sizeof(Real) + 16 * PIPE_R, sm8 = (size_t)PIPE_R * TileGeom<8>::SLOT * sizeof(Real) + 16 * PIPE_R;
     if (p->tiled == 16)
-        g3_tendency_tiled_kernel<Real, 16><<<dim3((D.nx / TT_X) * (D.ny / 16), n), TileGeom<16>::NT, 4 * TileGeom<16>::SLOT * sizeof(Real), st>>>(
+        g3_tendency_tiled_kernel<Real, 16><<<dim3((D.nx / TT_X) * (D.ny / 16), n), TileGeom<16>::NT, sm16, st>>>(
             D, C, (const Real*)p->nu, (const Real*)p->kappa, cur, nxt, (Real*)p->G, (const Real*)p->Tb, env_ids, dt, gam, zet, stage > 0, stage < 2);
     else if (p->tiled == 8)
-        g3_tendency_tiled_kernel<Real, 8><<<dim3((D.nx / TT_X) * (D.ny / 8), n), TileGeom<8>::NT, 4 * TileGeom<8>::SLOT * sizeof(Real), st>>>(
+        g3_tendency_tiled_kernel<Real, 8><<<dim3((D.nx / TT_X) * (D.ny / 8), n), TileGeom<8>::NT, sm8, st>>>(
             D, C, (const Real*)p->nu, (const Real*)p->kappa, cur, nxt, (Real*)p->G, (const Real*)p->Tb, env_ids, dt, gam, zet, stage > 0, stage < 2);
     else
         g3_tendency_kernel<Real><<<dim3((D.nc + TB - 1) / TB, n), TB, 0, st>>>(D, C, (const Real*)p->nu, (const Real*)p->kappa, cur, nxt, (Real*)p->G,
