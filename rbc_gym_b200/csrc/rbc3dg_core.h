@@ -468,17 +468,23 @@ RBC_HD void line_fft_inverse(const Dims& D, cx<Real>* Z, int ln, int lnl, int li
     for (; ls + 1 <= ln - 1; ls += 2) run(D.ncol >> 2, [&](int it) { butterfly2_dit_inv<Real>(Z, ln, ls, lnl, line_stride, elem_stride, lines_fastest, tw, it); });
     if (ls == ln - 1) run(D.ncol >> 1, [&](int it) { butterfly_dit_inv<Real>(Z, ln, ls, lnl, line_stride, elem_stride, lines_fastest, tw, it); });
 }
+// `pitch`: elements between consecutive rows of the plane (0 = nx).  `x_rows_fastest`: consecutive work items of the x passes take the
+// same butterfly of consecutive ROWS instead of consecutive butterflies of one row — with an odd pitch that makes every shared-memory
+// access of the x passes conflict-free on the device (consecutive butterflies of a row are 4 or 16 elements apart in the later stages:
+// 4-way bank conflicts), and a warp shares its twiddles.  The set of butterflies and their order within a line do not change.
 template <typename Real, typename Run>
-RBC_HD void plane_fft_forward(const Dims& D, cx<Real>* Z, const cx<Real>* twx, const cx<Real>* twy, Run run)
+RBC_HD void plane_fft_forward(const Dims& D, cx<Real>* Z, const cx<Real>* twx, const cx<Real>* twy, Run run, int pitch = 0, bool x_rows_fastest = false)
 {
-    line_fft_forward<Real>(D, Z, D.lx2, D.ly2, D.nx, 1, false, twx, run);
-    line_fft_forward<Real>(D, Z, D.ly2, D.lx2, 1, D.nx, true, twy, run);
+    const int pt = pitch ? pitch : D.nx;
+    line_fft_forward<Real>(D, Z, D.lx2, D.ly2, pt, 1, x_rows_fastest, twx, run);
+    line_fft_forward<Real>(D, Z, D.ly2, D.lx2, 1, pt, true, twy, run);
 }
 template <typename Real, typename Run>
-RBC_HD void plane_fft_inverse(const Dims& D, cx<Real>* Z, const cx<Real>* twx, const cx<Real>* twy, Run run)
+RBC_HD void plane_fft_inverse(const Dims& D, cx<Real>* Z, const cx<Real>* twx, const cx<Real>* twy, Run run, int pitch = 0, bool x_rows_fastest = false)
 {
-    line_fft_inverse<Real>(D, Z, D.ly2, D.lx2, 1, D.nx, true, twy, run);
-    line_fft_inverse<Real>(D, Z, D.lx2, D.ly2, D.nx, 1, false, twx, run);
+    const int pt = pitch ? pitch : D.nx;
+    line_fft_inverse<Real>(D, Z, D.ly2, D.lx2, 1, pt, true, twy, run);
+    line_fft_inverse<Real>(D, Z, D.lx2, D.ly2, pt, 1, x_rows_fastest, twx, run);
 }
 
 RBC_HD int bitrev(int v, int bits)

@@ -296,6 +296,7 @@ g3_div_fft_kernel(Dims D_arg, ConstsG<Real> C, const Real* P_all, cx<Real>* Z_al
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<Real>* Z = reinterpret_cast<cx<Real>*>(smem_raw);
     const Dims D = plane_dims<LX2, LY2>(D_arg);
+    const int pitch = D.nx + 1;      // odd row pitch: see plane_fft_forward
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, pz = blockIdx.x, nzp = (D.nz + 1) >> 1;
     if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const Real* P = P_all + (size_t)env * D.nstate;
@@ -310,22 +311,26 @@ g3_div_fft_kernel(Dims D_arg, ConstsG<Real> C, const Real* P_all, cx<Real>* Z_al
             Quad<Real> d1{{Real(0), Real(0), Real(0), Real(0)}};
             if (odd) d1 = quad_divergence<Real>(D, C, P, i, j, k + 1, w1, ld4(P + D.gw + (k + 2) * D.ncol + c));
 #pragma unroll
-            for (int m = 0; m < 4; ++m) Z[c + m] = cx<Real>{d0.v[m], d1.v[m]};
+            for (int m = 0; m < 4; ++m) Z[j * pitch + i + m] = cx<Real>{d0.v[m], d1.v[m]};
         }
     } else {
 #pragma unroll 4
         for (int c = threadIdx.x; c < D.ncol; c += blockDim.x) {
             const int i = c & (D.nx - 1), j = c >> D.lx2;
-            Z[c] = cx<Real>{cell_divergence<Real>(D, C, P, i, j, 2 * pz), odd ? cell_divergence<Real>(D, C, P, i, j, 2 * pz + 1) : Real(0)};
+            Z[j * pitch + i] = cx<Real>{cell_divergence<Real>(D, C, P, i, j, 2 * pz), odd ? cell_divergence<Real>(D, C, P, i, j, 2 * pz + 1) : Real(0)};
         }
     }
-    stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
+    cx<Real>* tw = Z + D.ny * pitch;
+    stage_twiddles<Real>(D, tw, twx, twy);
     __syncthreads();
-    if (LX2) plane_fft_forward<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRunFixed<FFT_NT>{});
-    else plane_fft_forward<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
+    if (LX2) plane_fft_forward<Real>(D, Z, tw, tw + (D.nx >> 1), BlockRunFixed<FFT_NT>{}, pitch, true);
+    else plane_fft_forward<Real>(D, Z, tw, tw + (D.nx >> 1), BlockRun{}, pitch, true);
     Real* out = reinterpret_cast<Real*>(Z_all + ((size_t)env * nzp + pz) * D.ncol);      // Z_all comes from cudaMalloc, planes are multiples of 512 bytes
-    const Real* Zr = reinterpret_cast<const Real*>(Z);
-    for (int c = 4 * threadIdx.x; c < 2 * D.ncol; c += 4 * blockDim.x) st4(out + c, ld4(Zr + c));
+    for (int c = 2 * threadIdx.x; c < D.ncol; c += 2 * blockDim.x) {                         // two complex values = 16 bytes per store
+        const int zi = (c >> D.lx2) * pitch + (c & (D.nx - 1));
+        const cx<Real> a = Z[zi], b = Z[zi + 1];
+        st4(out + 2 * c, Quad<Real>{{a.re, a.im, b.re, b.im}});
+    }
 }
 
 template <typename Real>
@@ -349,20 +354,26 @@ g3_ifft_kernel(Dims D_arg, const cx<Real>* Z_all, Real* phi_all, const cx<Real>*
     const int env = env_ids ? env_ids[blockIdx.y] : blockIdx.y, pz = blockIdx.x, nzp = (D.nz + 1) >> 1;
     if (env < 0) return;      // an environment the fused vector step only re-initialises (next_step mode)
     const Real* in = reinterpret_cast<const Real*>(Z_all + ((size_t)env * nzp + pz) * D.ncol);
-    Real* Zr = reinterpret_cast<Real*>(Z);
+    const int pitch = D.nx + 1;      // odd row pitch: see plane_fft_forward
 #pragma unroll 2
-    for (int c = 4 * threadIdx.x; c < 2 * D.ncol; c += 4 * blockDim.x) st4(Zr + c, ld4(in + c));
-    stage_twiddles<Real>(D, Z + D.ncol, twx, twy);
+    for (int c = 2 * threadIdx.x; c < D.ncol; c += 2 * blockDim.x) {
+        const Quad<Real> q = ld4(in + 2 * c);
+        const int zi = (c >> D.lx2) * pitch + (c & (D.nx - 1));
+        Z[zi] = cx<Real>{q.v[0], q.v[1]}; Z[zi + 1] = cx<Real>{q.v[2], q.v[3]};
+    }
+    cx<Real>* tw = Z + D.ny * pitch;
+    stage_twiddles<Real>(D, tw, twx, twy);
     __syncthreads();
-    if (LX2) plane_fft_inverse<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRunFixed<FFT_NT>{});
-    else plane_fft_inverse<Real>(D, Z, Z + D.ncol, Z + D.ncol + (D.nx >> 1), BlockRun{});
+    if (LX2) plane_fft_inverse<Real>(D, Z, tw, tw + (D.nx >> 1), BlockRunFixed<FFT_NT>{}, pitch, true);
+    else plane_fft_inverse<Real>(D, Z, tw, tw + (D.nx >> 1), BlockRun{}, pitch, true);
     const Real norm = Real(1) / (Real)D.ncol;
     Real* phi = phi_all + ((size_t)env * D.nz + 2 * pz) * D.ncol;
     const bool odd = 2 * pz + 1 < D.nz;
     for (int c = 4 * threadIdx.x; c < D.ncol; c += 4 * blockDim.x) {
-        const Quad<Real> a = ld4(Zr + 2 * c), b = ld4(Zr + 2 * c + 4);        // four complex values
-        st4(phi + c, Quad<Real>{{a.v[0] * norm, a.v[2] * norm, b.v[0] * norm, b.v[2] * norm}});
-        if (odd) st4(phi + D.ncol + c, Quad<Real>{{a.v[1] * norm, a.v[3] * norm, b.v[1] * norm, b.v[3] * norm}});
+        const int zi = (c >> D.lx2) * pitch + (c & (D.nx - 1));
+        const cx<Real> z0 = Z[zi], z1 = Z[zi + 1], z2 = Z[zi + 2], z3 = Z[zi + 3];
+        st4(phi + c, Quad<Real>{{z0.re * norm, z1.re * norm, z2.re * norm, z3.re * norm}});
+        if (odd) st4(phi + D.ncol + c, Quad<Real>{{z0.im * norm, z1.im * norm, z2.im * norm, z3.im * norm}});
     }
 }
 
@@ -702,7 +713,7 @@ int create(const HostConfigG& hc, int nx, int ny, int nz, int num_envs, int prec
     p->D = make_dims(nx, ny, nz);
     p->hc = hc; p->B = num_envs; p->precision = precision; p->device = device;
     p->rs = precision == 32 ? 4 : 8;
-    p->smem = ((size_t)p->D.ncol + p->D.nx / 2 + p->D.ny / 2) * 2 * p->rs;      // one complex plane + the twiddles of both directions
+    p->smem = ((size_t)p->D.ny * (p->D.nx + 1) + p->D.nx / 2 + p->D.ny / 2) * 2 * p->rs;      // one complex plane (odd row pitch) + the twiddles of both directions
     if (p->smem > 227 * 1024) { delete p; return rbc_fail("rbc3d_create: a horizontal plane of this grid does not fit the shared memory of an SM"); }
     cudaError_t e = cudaSuccess;
     {
