@@ -632,7 +632,7 @@ g3_vec_emit2_kernel(Dims D, const Real* st_all, float* obs, const int* env_ids, 
 
 namespace rbc3dg_api {
 
-constexpr int MAX_CHAINS = 4;
+constexpr int MAX_CHAINS = 8;
 constexpr int MAX_RBLOCKS = 128;      // blocks per environment of the epilogue reduction
 struct Plan {
     Dims D;
@@ -651,9 +651,10 @@ struct Plan {
     // what the GPU holds at once (64 environments at 64 x 64 x 32: 1024 FFT planes on 888 resident CTAs, 1024 tendency patches on
     // 296), so the last wave of each launch leaves SMs idle until the next kernel of the chain may start.  With the batch cut into
     // independent chains the block scheduler fills the tail of one chain's kernel with another chain's next one.  Environments never
-    // interact, so results do not depend on the cut.  Measured at 64 x 64 x 32 (env-steps/s with 1 / 2 / 3 / 4 chains): 64 environments
-    // 1125 / 1187 / 1208 / 1241; 148 environments 1224 / 1267 / - / 1266; 14 environments 772 / 792 / - / 778.
-    int streams = 0;             // 0 = 4 chains from 32 environments on, else 2; RBC_B200_G3_STREAMS=1..4 fixes the number
+    // interact, so results do not depend on the cut.  Measured at 64 x 64 x 32 (env-steps/s with 1 / 2 / 3 / 4 chains, build of that day):
+    // 64 environments 1125 / 1187 / 1208 / 1241; 148 environments 1224 / 1267 / - / 1266; 14 environments 772 / 792 / - / 778.  Final build,
+    // 4 / 6 / 8 chains: 64 environments 1371 / 1432 / 1436, 148 environments 1413 / - / 1397.
+    int streams = 0;             // 0 = 8 chains for 16 .. 96 environments, 4 above, 2 below; RBC_B200_G3_STREAMS=1..8 fixes the number
     int* iota = nullptr;         // 0 .. B-1: the environment list of a launch over the whole batch, so that it can be cut
     int* vlist = nullptr;        // fused vector step: the march's environment list with -1 for environments that only re-initialise
     int* do_reset = nullptr;     // fused vector step: environments re-initialised inside the current step
@@ -861,7 +862,7 @@ static int launch_t(Plan* p, const IoRaw& io, const int* env_ids, int n, int nsu
         env_ids = p->vlist;
     }
     // the chains: the whole list on the caller's stream, or equal parts of it on the caller's stream and the plan's side streams
-    const int want = p->streams > 0 ? p->streams : (n >= 32 ? 4 : 2);
+    const int want = p->streams > 0 ? p->streams : (n > 96 ? 4 : (n >= 16 ? 8 : 2));
     const int nch = want < n ? want : (n < 1 ? 1 : n);
     const int* ids[MAX_CHAINS] = {env_ids};
     int cnt[MAX_CHAINS] = {n};
