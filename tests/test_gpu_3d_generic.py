@@ -101,9 +101,9 @@ def test_tiled_tendency_equals_the_per_cell_kernel(monkeypatch, shape):
 
 @pytest.mark.parametrize("shape,envs", [((32, 64, 64), 33), ((8, 32, 32), 5)])
 def test_chains_and_compile_time_plane_extents_change_no_bit(monkeypatch, shape, envs):
-    """Two scheduling / code-generation choices of the generic path must be invisible in the results: (i) the batch runs as up to four
-    independent chains on separate streams (`RBC_B200_G3_STREAMS`; uneven cuts here: 33 = 9 + 8 + 8 + 8, 5 = 3 + 2) — environments never
-    interact; (ii) the FFT plane kernels instantiated with compile-time plane extents for 64 x 64 and 32 x 32 columns
+    """Two scheduling / code-generation choices of the generic path must be invisible in the results: (i) the batch runs as up to eight
+    independent chains on separate streams (`RBC_B200_G3_STREAMS`; uneven cuts here: 33 environments over eight chains, 5 over two) —
+    environments never interact; (ii) the FFT plane kernels instantiated with compile-time plane extents for 64 x 64 and 32 x 32 columns
     (`RBC_B200_G3_FIXED_PLANE`) run the same butterflies in the same order as the run-time-extent kernels.  Bitwise equality of a
     two-step rollout, states and Nusselt numbers, in the throughput precision."""
     import torch
