@@ -43,7 +43,7 @@ extern "C" {
  * constants that the Julia API hard-codes (rbc_sim2D_api.jl:28-41), made explicit. */
 typedef struct rbc2d_config {
     int32_t num_envs;        /* B: environments in the on-device batch                                 */
-    int32_t nx, nz;          /* grid = state_shape[::-1]; registered: 96x64, 128x64, 192x128          */
+    int32_t nx, nz;          /* grid = state_shape[::-1]; registered: 96x64, 128x64, 192x128, 64x32, 64x64, 96x32, 96x128, 128x32, 128x128, 192x64 */
     int32_t obs_nx, obs_nz;  /* sensors = observation_shape[::-1]; must divide nx, nz (48, 8)          */
     int32_t heaters;         /* heater segments (12), <= 32                                            */
     double heater_limit;     /* 0.75                                                                   */

@@ -348,7 +348,7 @@ int rbc2d_create(const rbc2d_config* cfg, rbc2d_sim** out)
     *out = nullptr;
     const bool dedicated = (cfg->nx == NX && cfg->nz == NZ) && !rbc2dx_api::supported(cfg->nx, cfg->nz);
     if (!dedicated && !rbc2dx_api::supported(cfg->nx, cfg->nz))
-        return fail("rbc2d_create: registered grids are 96 x 64, 128 x 64 and 192 x 128");
+        return fail("rbc2d_create: registered grids are (nx x nz) 96 x 64, 128 x 64, 192 x 128 and 64 x 32, 64 x 64, 96 x 32, 96 x 128, 128 x 32, 128 x 128, 192 x 64");
     if (cfg->num_envs < 1) return fail("rbc2d_create: num_envs must be >= 1");
     if (cfg->precision != 32 && cfg->precision != 64) return fail("rbc2d_create: precision must be 32 or 64");
     if (cfg->heaters < 1 || cfg->heaters > MAX_HEATERS) return fail("rbc2d_create: heaters must be in 1..32");

@@ -30,6 +30,9 @@ struct IoRaw {
 // 1 when a cluster kernel is registered for this grid.  `force_cluster` (env RBC_B200_CLUSTER=1) also routes the
 // 96 x 64 grid through the cluster kernel (2 CTAs per environment) for cross-validation and measurement.
 int supported(int nx, int nz);
+int more_supported(int nx, int nz);          // the further registered grids of rbc2dx_more.cuh
+int create_more(Plan* p);                    // ... their plain-mode kernels (rbc2dx_more.cu)
+int create_more_split(Plan* p);              // ... their pressure-split kernels (rbc2dx_more_split.cu)
 int create(int nx, int nz, int precision, int split, int device, double lx, double lz, Plan** out);   // 0 or -1 (rbc_fail); split: pressure channels
 void destroy(Plan* p);
 int launch(Plan* p, const rbc2d::HostConfig& hc, const rbc2d::HostWrappers& wr, const IoRaw& io, const int* env_ids, int n,

@@ -25,7 +25,7 @@ int supported(int nx, int nz)
     if (nx == 192 && nz == 128) return 1;
     if (nx == 128 && nz == 64) return 1;
     if (nx == 96 && nz == 64 && (force_cluster() == 1 || force_cluster() == 2)) return 1;
-    return 0;
+    return more_supported(nx, nz);
 }
 
 int create(int nx, int nz, int precision, int split, int device, double lx, double lz, Plan** out)
@@ -35,7 +35,9 @@ int create(int nx, int nz, int precision, int split, int device, double lx, doub
     Plan* p = new Plan();
     p->nx = nx; p->nz = nz; p->precision = precision; p->device = device; p->lx = lx; p->lz = lz;
     int rc = -1;
-    if (split) {
+    if (more_supported(nx, nz)) {
+        rc = split ? create_more_split(p) : create_more(p);
+    } else if (split) {
         rc = create_split(p);
     } else if (nx == 192 && nz == 128) {
         // fp32: 4 CTAs x 32 rows, both state buffers on-chip; fp64: 8 CTAs x 16 rows, predicted state in global memory

@@ -89,6 +89,8 @@ extern "C" int emu_rbc2dx_step(const HostConfig* h, const HostWrappers* wp, doub
     using G192_1 = Grid<192, 128, 1, 2>;          // host-only: the whole grid in one "CTA" (plain two-sided Thomas, no SPIKE)
     using G192_2 = Grid<192, 128, 2, 2>;
     using G128_2 = Grid<128, 64, 2, 2, 4>;
+    using G64_1 = Grid<64, 64, 1, 4, 4>;           // two of the further registered grids (rbc2dx_more.cuh): the 4 x 8 FFT split on one CTA,
+    using G96x128_4 = Grid<96, 128, 4, 4, 6>;      // and four strips per slab with the 6 x 8 split over four CTAs
     if (nx == 96 && nz == 64 && cl == 1) DISPATCH(G96_1);
     if (nx == 96 && nz == 64 && cl == 2) DISPATCH(G96_2);
     if (nx == 96 && nz == 64 && cl == 4) DISPATCH(G96_4);
@@ -97,6 +99,8 @@ extern "C" int emu_rbc2dx_step(const HostConfig* h, const HostWrappers* wp, doub
     if (nx == 192 && nz == 128 && cl == 1) DISPATCH(G192_1);
     if (nx == 192 && nz == 128 && cl == 2) DISPATCH(G192_2);
     if (nx == 128 && nz == 64 && cl == 2) DISPATCH(G128_2);
+    if (nx == 64 && nz == 64 && cl == 1) DISPATCH(G64_1);
+    if (nx == 96 && nz == 128 && cl == 4) DISPATCH(G96x128_4);
     return -2;
 }
 

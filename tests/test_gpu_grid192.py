@@ -143,7 +143,8 @@ def test_unregistered_grid_is_rejected(B):
 
 
 @pytest.mark.parametrize("nx,nz,precision,tol,ptol", [(192, 128, 64, 1e-10, 1e-8), (192, 128, 32, 1e-5, 5e-3), (128, 64, 64, 1e-10, 1e-8),
-                                                      (128, 64, 32, 1e-5, 5e-3)])
+                                                      (128, 64, 32, 1e-5, 5e-3), (64, 64, 32, 1e-5, 5e-3), (96, 128, 64, 1e-10, 1e-8),
+                                                      (192, 64, 32, 1e-5, 5e-3), (128, 128, 64, 1e-10, 1e-8)])
 def test_pressure_channels_on_cluster_grids_match_oracle(B, nx, nz, precision, tol, ptol):
     """Pressure-split mode of the cluster kernel: the hydrostatic column integral and the zero-mean gauge of pNHS cross the
     CTAs of the cluster.  State, both pressure fields (get_state channels 3-4) and their sensor sub-sample against the
@@ -154,7 +155,7 @@ def test_pressure_channels_on_cluster_grids_match_oracle(B, nx, nz, precision, t
     states = [smooth_state(nx, nz, seed=s) for s in (0, 1)]
     acts = np.random.default_rng(11).uniform(-1, 1, (2, 12)).astype(np.float32)
     dt = 3 * DTS + 0.005
-    sim = B.Sim2D(n, ra=RA, dt_action=dt, dt_solver=DTS, state_shape=(nz, nx), obs_shape=(8, 48 if nx == 192 else 64), precision=precision,
+    sim = B.Sim2D(n, ra=RA, dt_action=dt, dt_solver=DTS, state_shape=(nz, nx), obs_shape=(8, 48 if nx in (192, 96) else 64), precision=precision,
                   pressure=True)
     sim.reset_from_fields(np.concatenate([B.pack_fields(*(a[None] for a in states[i % 2])) for i in range(n)]), project=False)
     obs, *_ = sim.step(torch.from_numpy(acts[np.arange(n) % 2]).cuda())
@@ -290,6 +291,31 @@ def test_power_of_two_grid_128x64_matches_oracle(B, precision, tol):
         assert rel(b[j], r["b"]) < tol and rel(u[j], r["u"]) < tol and rel(w[j], r["w"]) < tol
         ns, no = O.nusselt_state_obs(P, r["b"], r["u"], r["w"], (8, 64))
         assert nuo[j].item() == pytest.approx(no, abs=1e-8 if precision == 64 else 2e-3)
+    sim.close()
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-10), (32, 1e-5)])
+@pytest.mark.parametrize("nx,nz", [(64, 32), (64, 64), (96, 32), (96, 128), (128, 32), (128, 128), (192, 64)])
+def test_further_registered_grids_match_oracle(B, nx, nz, precision, tol):
+    """`state_shape` is a free keyword of the reference environment (`rbc2D.py:43-60`): the further registered decompositions of the
+    cluster kernel (`rbc2dx_more.cuh`: widths 64 ... 192 against heights 32 ... 128, one to eight CTAs per environment) against the
+    oracle on the same grid, one action step, both precisions, plus the sensor-grid Nusselt number."""
+    import torch
+    P = O.make_params(1e5, nx=nx, nz=nz, split_phy=False)
+    states = [smooth_state(nx, nz, seed=s) for s in (5, 6, 7)]
+    acts = np.random.default_rng(11).uniform(-1, 1, (3, 12)).astype(np.float32)
+    obs_shape = (8, 32)
+    sim = B.Sim2D(3, ra=1e5, dt_action=0.2, dt_solver=0.03, state_shape=(nz, nx), obs_shape=obs_shape, precision=precision)
+    sim.reset_from_fields(np.concatenate([B.pack_fields(b[None], u[None], w[None]) for b, u, w in states]), project=False)
+    obs, rew, nus, nuo, trunc, nan = sim.step(torch.from_numpy(acts).cuda())
+    b, u, w = B.split_fields(sim.fields(), (nz, nx))
+    assert not nan.any().item()
+    for j, (b0, u0, w0) in enumerate(states):
+        r = O.step(P, b0, u0, w0, acts[j].astype(np.float64), O.substep_schedule(0.2, 0.03))
+        assert rel(b[j], r["b"]) < tol and rel(u[j], r["u"]) < tol and rel(w[j], r["w"]) < tol, (j, rel(b[j], r["b"]), rel(u[j], r["u"]), rel(w[j], r["w"]))
+        ns, no = O.nusselt_state_obs(P, r["b"], r["u"], r["w"], obs_shape)
+        assert nuo[j].item() == pytest.approx(no, abs=1e-8 if precision == 64 else 2e-3)
+        assert nus[j].item() == pytest.approx(ns, abs=1e-8 if precision == 64 else 2e-3)
     sim.close()
 
 

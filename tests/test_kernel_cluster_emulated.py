@@ -36,7 +36,8 @@ def test_96x64_any_cluster_size_matches_oracle(ckpt_ra1e5, cl, nxt_global):
     assert np.all(e["nan"] == 0) and np.all(e["t"] == 0.09) and np.all(e["step"] == 2)
 
 
-@pytest.mark.parametrize("nx,nz,cl,obs", [(192, 128, 4, (8, 48)), (192, 128, 8, (16, 96)), (128, 64, 2, (8, 64))])
+@pytest.mark.parametrize("nx,nz,cl,obs", [(192, 128, 4, (8, 48)), (192, 128, 8, (16, 96)), (128, 64, 2, (8, 64)), (64, 64, 1, (8, 32)),
+                                          (96, 128, 4, (8, 48))])
 def test_other_grids_match_oracle(nx, nz, cl, obs):
     """config 3's grid (192 x 128, Ra=1e6, dt_solver=0.015: the heater's cubic blends fire) and a power-of-two
     width (4 x 16 FFT split), fp64 to round-off and fp32 within the stated tolerance."""
