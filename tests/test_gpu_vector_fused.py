@@ -82,12 +82,13 @@ def test_fused_step_on_the_cluster_kernel_grid():
 
 @pytest.mark.parametrize("shape", [(16, 32, 32), (8, 16, 32), (16, 64, 64)])      # dedicated kernel; stage-streaming kernels (per-cell / tiled tendency)
 @pytest.mark.parametrize("mode", ["next_step", "same_step"])
-def test_fused_step_equals_python_driven_autoreset_3d(mode, shape):
+@pytest.mark.parametrize("precision", [32, 64])
+def test_fused_step_equals_python_driven_autoreset_3d(mode, shape, precision):
     import torch
     from rbc_gym_b200.envs import RBCVectorEnv3D
     rng = np.random.default_rng(0)
     n, nb = 20, 3
-    kw = dict(rayleigh_number=2500, heater_duration=0.03, dt_solver=0.01, episode_length=0.2, autoreset_mode=mode, seed=9, precision=32,
+    kw = dict(rayleigh_number=2500, heater_duration=0.03, dt_solver=0.01, episode_length=0.2, autoreset_mode=mode, seed=9, precision=precision,
               state_shape=shape)
     fused, plain = RBCVectorEnv3D(n, **kw), RBCVectorEnv3D(n, fused=False, **kw)
     # a bank of projected noisy states
